@@ -1,0 +1,395 @@
+// genesis_b200 -- normalisation + gate / ReLU kernels (HBM-bound, NHWC fp32, 128-bit accesses).
+//
+// One family covers BatchNorm2d (train / eval), InstanceNorm2d(affine), GroupNorm and "no norm", each
+// followed by either the sylvester gate  out = hn * sigmoid(gn)  (y carries 2C channels: h | g;
+// reference third_party/sylvester/layers.py:42-54) or ReLU (modules/blocks.py:151-165).
+//
+// forward : stats (per-sample per-channel sum / sum-of-squares, double accumulators)
+//           -> finalize (mean, rstd, folded scale/shift per (n,c); BN running-stat update)
+//           -> apply   (out = post(scale*y + shift))
+// backward: bwd_stats (per (n,c): sum d_n, sum d_n*yhat) -> bwd_finalize (m1, m2 per (n,c); dgamma,
+//           dbeta) -> bwd_apply (dy = rstd*(gamma*d_n - m1 - yhat*m2))
+// where d_n is the gradient w.r.t. the normalised, affine-transformed value.
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------- forward stats
+// y [N, HW, C]; sums [N, C, 2] (double, pre-zeroed).  grid = (chunks, N), 256 threads.
+__global__ void __launch_bounds__(256) norm_stats_kernel(const float* __restrict__ y, double* __restrict__ sums,
+                                                         int HW, int C, int rows_per_block) {
+    const int q = C >> 2;
+    const int lanes = 256 / q;
+    const int t = threadIdx.x;
+    const int lane = t / q, quad = t - lane * q;
+    const int n = blockIdx.y;
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(HW, r0 + rows_per_block);
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+    if (lane < lanes) {
+        const float* base = y + ((long)n * HW) * C + quad * 4;
+        for (int r = r0 + lane; r < r1; r += lanes) {
+            const float4 v = g2_ldg4(base + (long)r * C);
+            s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+            ss[0] += v.x * v.x; ss[1] += v.y * v.y; ss[2] += v.z * v.z; ss[3] += v.w * v.w;
+        }
+    }
+    __shared__ double sm[256 * 8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { sm[t * 8 + j] = s[j]; sm[t * 8 + 4 + j] = ss[j]; }
+    __syncthreads();
+    // thread (quad, j) for j<8 sums over lanes
+    for (int o = t; o < q * 8; o += 256) {
+        const int qq = o >> 3, j = o & 7;
+        double acc = 0.0;
+        for (int l = 0; l < lanes; ++l) acc += sm[(l * q + qq) * 8 + j];
+        const int c = qq * 4 + (j & 3);
+        atomicAdd(sums + ((long)n * C + c) * 2 + (j >> 2), acc);
+    }
+}
+
+struct NormFinP {
+    const double* sums;                 // [N, C, 2]
+    const float *g0, *b0, *g1, *b1;     // affine of first / second half (g1,b1 null when not split)
+    float *rm0, *rv0, *rm1, *rv1;       // BN running stats (may be null)
+    float *mean, *rstd, *scale, *shift; // outputs [Ns, C]  (Ns = 1 for batch mode, N otherwise)
+    int N, HW, C, half, mode, groups, training;
+    float eps, momentum;
+};
+
+__global__ void norm_finalize_kernel(const NormFinP p) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Ns = p.mode == G2_NORM_BATCH ? 1 : p.N;
+    if (idx >= Ns * p.C) return;
+    const int n = idx / p.C, c = idx - n * p.C;
+    const bool second = c >= p.half;
+    const int ch = second ? c - p.half : c;
+    const float gamma = second ? (p.g1 ? p.g1[ch] : 1.f) : (p.g0 ? p.g0[ch] : 1.f);
+    const float beta = second ? (p.b1 ? p.b1[ch] : 0.f) : (p.b0 ? p.b0[ch] : 0.f);
+    double mean, var;
+    if (p.mode == G2_NORM_BATCH) {
+        float* rm = second ? p.rm1 : p.rm0;
+        float* rv = second ? p.rv1 : p.rv0;
+        if (p.training) {
+            double s = 0.0, ss = 0.0;
+            for (int i = 0; i < p.N; ++i) { s += p.sums[((long)i * p.C + c) * 2]; ss += p.sums[((long)i * p.C + c) * 2 + 1]; }
+            const double cnt = (double)p.N * p.HW;
+            mean = s / cnt; var = ss / cnt - mean * mean; if (var < 0.0) var = 0.0;
+            if (rm) {
+                rm[ch] = (1.f - p.momentum) * rm[ch] + p.momentum * (float)mean;
+                rv[ch] = (1.f - p.momentum) * rv[ch] + p.momentum * (float)(var * cnt / (cnt > 1.0 ? cnt - 1.0 : 1.0));
+            }
+        } else { mean = rm[ch]; var = rv[ch]; }
+    } else if (p.mode == G2_NORM_INSTANCE) {
+        const double s = p.sums[((long)n * p.C + c) * 2], ss = p.sums[((long)n * p.C + c) * 2 + 1];
+        mean = s / p.HW; var = ss / p.HW - mean * mean; if (var < 0.0) var = 0.0;
+    } else {  // group
+        const int cpg = p.C / p.groups, g = c / cpg;
+        double s = 0.0, ss = 0.0;
+        for (int j = 0; j < cpg; ++j) { s += p.sums[((long)n * p.C + g * cpg + j) * 2]; ss += p.sums[((long)n * p.C + g * cpg + j) * 2 + 1]; }
+        const double cnt = (double)p.HW * cpg;
+        mean = s / cnt; var = ss / cnt - mean * mean; if (var < 0.0) var = 0.0;
+    }
+    const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+    p.mean[idx] = (float)mean;
+    p.rstd[idx] = rstd;
+    p.scale[idx] = gamma * rstd;
+    p.shift[idx] = beta - (float)mean * gamma * rstd;
+}
+
+// ---------------------------------------------------------------------------------- forward apply
+// POST_GATE: y [N,HW,2C] -> out [N,HW,C];  POST_RELU: y [N,HW,C] -> out [N,HW,C].
+// scale/shift [Ns, Cy] (null -> identity), sn = stride over n (0 for batch mode).
+template <int POST>
+__global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict__ y, const float* __restrict__ scale,
+                                                         const float* __restrict__ shift, float* __restrict__ out,
+                                                         long total_quads, int HW, int C, int sn) {
+    const int q = C >> 2;
+    const int Cy = POST == G2_POST_GATE ? 2 * C : C;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total_quads; i += (long)gridDim.x * blockDim.x) {
+        const int quad = (int)(i % q);
+        const long row = i / q;               // n*HW + p
+        const int n = (int)(row / HW);
+        const int c = quad * 4;
+        const float* yp = y + row * Cy + c;
+        float4 h = g2_ldg4(yp);
+        float4 a = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (scale) { a = g2_ldg4(scale + (long)n * sn + c); b = g2_ldg4(shift + (long)n * sn + c); }
+        h.x = fmaf(a.x, h.x, b.x); h.y = fmaf(a.y, h.y, b.y); h.z = fmaf(a.z, h.z, b.z); h.w = fmaf(a.w, h.w, b.w);
+        float4 o;
+        if (POST == G2_POST_GATE) {
+            float4 g = g2_ldg4(yp + C);
+            float4 ag = make_float4(1.f, 1.f, 1.f, 1.f), bg = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (scale) { ag = g2_ldg4(scale + (long)n * sn + C + c); bg = g2_ldg4(shift + (long)n * sn + C + c); }
+            g.x = fmaf(ag.x, g.x, bg.x); g.y = fmaf(ag.y, g.y, bg.y); g.z = fmaf(ag.z, g.z, bg.z); g.w = fmaf(ag.w, g.w, bg.w);
+            o.x = h.x * g2_sigmoidf(g.x); o.y = h.y * g2_sigmoidf(g.y);
+            o.z = h.z * g2_sigmoidf(g.z); o.w = h.w * g2_sigmoidf(g.w);
+        } else {
+            o.x = fmaxf(h.x, 0.f); o.y = fmaxf(h.y, 0.f); o.z = fmaxf(h.z, 0.f); o.w = fmaxf(h.w, 0.f);
+        }
+        *reinterpret_cast<float4*>(out + row * C + c) = o;
+    }
+}
+
+// gradient w.r.t. the normalised+affine values for 4 channels
+template <int POST>
+__device__ __forceinline__ void post_grad(const float* __restrict__ yrow, const float* __restrict__ scale,
+                                          const float* __restrict__ shift, long sbase, int C, int c,
+                                          const float4 d, float4& dh, float4& dg) {
+    float4 h = g2_ldg4(yrow + c);
+    float4 a = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (scale) { a = g2_ldg4(scale + sbase + c); b = g2_ldg4(shift + sbase + c); }
+    h.x = fmaf(a.x, h.x, b.x); h.y = fmaf(a.y, h.y, b.y); h.z = fmaf(a.z, h.z, b.z); h.w = fmaf(a.w, h.w, b.w);
+    if (POST == G2_POST_GATE) {
+        float4 g = g2_ldg4(yrow + C + c);
+        float4 ag = make_float4(1.f, 1.f, 1.f, 1.f), bg = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (scale) { ag = g2_ldg4(scale + sbase + C + c); bg = g2_ldg4(shift + sbase + C + c); }
+        const float s0 = g2_sigmoidf(fmaf(ag.x, g.x, bg.x)), s1 = g2_sigmoidf(fmaf(ag.y, g.y, bg.y));
+        const float s2 = g2_sigmoidf(fmaf(ag.z, g.z, bg.z)), s3 = g2_sigmoidf(fmaf(ag.w, g.w, bg.w));
+        dh = make_float4(d.x * s0, d.y * s1, d.z * s2, d.w * s3);
+        dg = make_float4(d.x * h.x * s0 * (1.f - s0), d.y * h.y * s1 * (1.f - s1),
+                         d.z * h.z * s2 * (1.f - s2), d.w * h.w * s3 * (1.f - s3));
+    } else {
+        dh = make_float4(h.x > 0.f ? d.x : 0.f, h.y > 0.f ? d.y : 0.f, h.z > 0.f ? d.z : 0.f, h.w > 0.f ? d.w : 0.f);
+        dg = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// ---------------------------------------------------------------------------------- backward stats
+// sums2 [N, Cy, 2] (double, pre-zeroed): (sum d_n, sum d_n * yhat) per sample and normalised channel.
+template <int POST>
+__global__ void __launch_bounds__(256) norm_bwd_stats_kernel(const float* __restrict__ y, const float* __restrict__ dout,
+                                                             const float* __restrict__ scale, const float* __restrict__ shift,
+                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                             double* __restrict__ sums2, int HW, int C, int sn, int rows_per_block) {
+    const int q = C >> 2;
+    const int Cy = POST == G2_POST_GATE ? 2 * C : C;
+    const int lanes = 256 / q;
+    const int t = threadIdx.x;
+    const int lane = t / q, quad = t - lane * q;
+    const int n = blockIdx.y;
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(HW, r0 + rows_per_block);
+    const int c = quad * 4;
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    if (lane < lanes) {
+        const long sbase = (long)n * sn;
+        const float4 mh = g2_ldg4(mean + sbase + c), rh = g2_ldg4(rstd + sbase + c);
+        float4 mg = mh, rg = rh;
+        if (POST == G2_POST_GATE) { mg = g2_ldg4(mean + sbase + C + c); rg = g2_ldg4(rstd + sbase + C + c); }
+        for (int r = r0 + lane; r < r1; r += lanes) {
+            const long row = (long)n * HW + r;
+            const float* yrow = y + row * Cy;
+            const float4 d = g2_ldg4(dout + row * C + c);
+            float4 dh, dg;
+            post_grad<POST>(yrow, scale, shift, sbase, C, c, d, dh, dg);
+            const float4 yh = g2_ldg4(yrow + c);
+            acc[0] += dh.x; acc[1] += dh.y; acc[2] += dh.z; acc[3] += dh.w;
+            acc[4] += dh.x * (yh.x - mh.x) * rh.x; acc[5] += dh.y * (yh.y - mh.y) * rh.y;
+            acc[6] += dh.z * (yh.z - mh.z) * rh.z; acc[7] += dh.w * (yh.w - mh.w) * rh.w;
+            if (POST == G2_POST_GATE) {
+                const float4 yg = g2_ldg4(yrow + C + c);
+                acc[8] += dg.x; acc[9] += dg.y; acc[10] += dg.z; acc[11] += dg.w;
+                acc[12] += dg.x * (yg.x - mg.x) * rg.x; acc[13] += dg.y * (yg.y - mg.y) * rg.y;
+                acc[14] += dg.z * (yg.z - mg.z) * rg.z; acc[15] += dg.w * (yg.w - mg.w) * rg.w;
+            }
+        }
+    }
+    __shared__ double sm[256 * 16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) sm[t * 16 + j] = acc[j];
+    __syncthreads();
+    const int nj = POST == G2_POST_GATE ? 16 : 8;
+    for (int o = t; o < q * nj; o += 256) {
+        const int qq = o / nj, j = o - qq * nj;
+        double a = 0.0;
+        for (int l = 0; l < lanes; ++l) a += sm[(l * q + qq) * 16 + j];
+        const int cc = qq * 4 + (j & 3) + (j >= 8 ? C : 0);
+        atomicAdd(sums2 + ((long)n * Cy + cc) * 2 + ((j >> 2) & 1), a);
+    }
+}
+
+struct NormBwdFinP {
+    const double* sums2;                // [N, Cy, 2]
+    const float *g0, *g1;               // gamma halves (null -> 1)
+    float *m1, *m2;                     // [Ns, Cy]
+    float *dg0, *db0, *dg1, *db1;       // parameter grads (may be null)
+    int N, HW, Cy, half, mode, groups;
+};
+
+__global__ void norm_bwd_finalize_kernel(const NormBwdFinP p) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Ns = p.mode == G2_NORM_BATCH ? 1 : p.N;
+    if (idx >= Ns * p.Cy) return;
+    const int n = idx / p.Cy, c = idx - n * p.Cy;
+    auto gamma_of = [&](int cc) {
+        const bool sec = cc >= p.half; const int ch = sec ? cc - p.half : cc;
+        return sec ? (p.g1 ? p.g1[ch] : 1.f) : (p.g0 ? p.g0[ch] : 1.f);
+    };
+    double m1, m2;
+    if (p.mode == G2_NORM_BATCH) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int i = 0; i < p.N; ++i) { s1 += p.sums2[((long)i * p.Cy + c) * 2]; s2 += p.sums2[((long)i * p.Cy + c) * 2 + 1]; }
+        const double cnt = (double)p.N * p.HW, g = gamma_of(c);
+        m1 = g * s1 / cnt; m2 = g * s2 / cnt;
+    } else if (p.mode == G2_NORM_INSTANCE) {
+        const double g = gamma_of(c);
+        m1 = g * p.sums2[((long)n * p.Cy + c) * 2] / p.HW;
+        m2 = g * p.sums2[((long)n * p.Cy + c) * 2 + 1] / p.HW;
+    } else {
+        const int cpg = p.Cy / p.groups, g0 = (c / cpg) * cpg;
+        double s1 = 0.0, s2 = 0.0;
+        for (int j = 0; j < cpg; ++j) {
+            const double g = gamma_of(g0 + j);
+            s1 += g * p.sums2[((long)n * p.Cy + g0 + j) * 2];
+            s2 += g * p.sums2[((long)n * p.Cy + g0 + j) * 2 + 1];
+        }
+        const double cnt = (double)p.HW * cpg;
+        m1 = s1 / cnt; m2 = s2 / cnt;
+    }
+    p.m1[idx] = (float)m1;
+    p.m2[idx] = (float)m2;
+    if (n == 0) {   // parameter gradients: sum over all samples
+        double s1 = 0.0, s2 = 0.0;
+        for (int i = 0; i < p.N; ++i) { s1 += p.sums2[((long)i * p.Cy + c) * 2]; s2 += p.sums2[((long)i * p.Cy + c) * 2 + 1]; }
+        const bool sec = c >= p.half; const int ch = sec ? c - p.half : c;
+        float* dg = sec ? p.dg1 : p.dg0; float* db = sec ? p.db1 : p.db0;
+        if (dg) dg[ch] = (float)s2;
+        if (db) db[ch] = (float)s1;
+    }
+}
+
+// ---------------------------------------------------------------------------------- backward apply
+// dy [N,HW,Cy] = rstd * (gamma * d_n - m1 - yhat * m2)   (mode NONE: dy = d_n)
+template <int POST>
+__global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const float* __restrict__ y, const float* __restrict__ dout,
+                                                             const float* __restrict__ scale, const float* __restrict__ shift,
+                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                             const float* __restrict__ m1, const float* __restrict__ m2,
+                                                             float* __restrict__ dy, long total_quads, int HW, int C, int sn) {
+    const int q = C >> 2;
+    const int Cy = POST == G2_POST_GATE ? 2 * C : C;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total_quads; i += (long)gridDim.x * blockDim.x) {
+        const int quad = (int)(i % q);
+        const long row = i / q;
+        const int n = (int)(row / HW);
+        const int c = quad * 4;
+        const long sbase = (long)n * sn;
+        const float* yrow = y + row * Cy;
+        const float4 d = g2_ldg4(dout + row * C + c);
+        float4 dh, dg;
+        post_grad<POST>(yrow, scale, shift, sbase, C, c, d, dh, dg);
+        if (scale == nullptr) {      // no normalisation: dy = d_n
+            *reinterpret_cast<float4*>(dy + row * Cy + c) = dh;
+            if (POST == G2_POST_GATE) *reinterpret_cast<float4*>(dy + row * Cy + C + c) = dg;
+            continue;
+        }
+#pragma unroll
+        for (int half = 0; half < (POST == G2_POST_GATE ? 2 : 1); ++half) {
+            const int cc = c + half * C;
+            const float4 dn = half ? dg : dh;
+            const float4 yv = g2_ldg4(yrow + cc);
+            const float4 mu = g2_ldg4(mean + sbase + cc), rs = g2_ldg4(rstd + sbase + cc);
+            const float4 sc = g2_ldg4(scale + sbase + cc);           // gamma * rstd
+            const float4 a1 = g2_ldg4(m1 + sbase + cc), a2 = g2_ldg4(m2 + sbase + cc);
+            float4 o;
+            o.x = sc.x * dn.x - rs.x * (a1.x + (yv.x - mu.x) * rs.x * a2.x);
+            o.y = sc.y * dn.y - rs.y * (a1.y + (yv.y - mu.y) * rs.y * a2.y);
+            o.z = sc.z * dn.z - rs.z * (a1.z + (yv.z - mu.z) * rs.z * a2.z);
+            o.w = sc.w * dn.w - rs.w * (a1.w + (yv.w - mu.w) * rs.w * a2.w);
+            *reinterpret_cast<float4*>(dy + row * Cy + cc) = o;
+        }
+    }
+}
+
+inline int ew_blocks(long work) {
+    long b = (work + 255) / 256;
+    const long cap = 148L * 16;
+    return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" {
+
+int g2_norm_stats_f32(const float* y, double* sums, int N, int HW, int C, cudaStream_t stream) {
+    G2_CHECK_ARG(y && sums && N > 0 && HW > 0 && C >= 4 && (C % 4) == 0 && C <= 1024);
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)N * C, stream);
+    if (e != cudaSuccess) return (int)e;
+    const int lanes = 256 / (C / 4);
+    int rpb = lanes * 32;
+    // keep the grid near a few waves of 148 SMs
+    while ((long)g2_cdiv(HW, rpb) * N > 148L * 32 && rpb < HW) rpb *= 2;
+    dim3 grid(g2_cdiv(HW, rpb), N);
+    norm_stats_kernel<<<grid, 256, 0, stream>>>(y, sums, HW, C, rpb);
+    G2_LAUNCH_RET();
+}
+
+int g2_norm_finalize_f32(const double* sums, const float* g0, const float* b0, const float* g1, const float* b1,
+                         float* rm0, float* rv0, float* rm1, float* rv1, float* mean, float* rstd, float* scale,
+                         float* shift, int N, int HW, int C, int half, int mode, int groups, int training,
+                         float eps, float momentum, cudaStream_t stream) {
+    G2_CHECK_ARG(mean && rstd && scale && shift && N > 0 && C > 0 && half > 0 && half <= C);
+    G2_CHECK_ARG(mode == G2_NORM_BATCH || mode == G2_NORM_INSTANCE || mode == G2_NORM_GROUP);
+    if (mode == G2_NORM_GROUP) G2_CHECK_ARG(groups > 0 && C % groups == 0);
+    if (mode == G2_NORM_BATCH && !training) G2_CHECK_ARG(rm0 && rv0 && (half == C || (rm1 && rv1)));
+    else G2_CHECK_ARG(sums != nullptr);
+    NormFinP p{sums, g0, b0, g1, b1, rm0, rv0, rm1, rv1, mean, rstd, scale, shift, N, HW, C, half, mode, groups, training, eps, momentum};
+    const int Ns = mode == G2_NORM_BATCH ? 1 : N;
+    norm_finalize_kernel<<<g2_cdiv((long)Ns * C, 128), 128, 0, stream>>>(p);
+    G2_LAUNCH_RET();
+}
+
+int g2_norm_apply_f32(const float* y, const float* scale, const float* shift, float* out, int N, int HW, int C,
+                      int sn, int post, cudaStream_t stream) {
+    G2_CHECK_ARG(y && out && N > 0 && HW > 0 && C >= 4 && (C % 4) == 0 && (scale == nullptr) == (shift == nullptr));
+    const long quads = (long)N * HW * (C / 4);
+    if (post == G2_POST_GATE) norm_apply_kernel<G2_POST_GATE><<<ew_blocks(quads), 256, 0, stream>>>(y, scale, shift, out, quads, HW, C, sn);
+    else if (post == G2_POST_RELU) norm_apply_kernel<G2_POST_RELU><<<ew_blocks(quads), 256, 0, stream>>>(y, scale, shift, out, quads, HW, C, sn);
+    else return G2_ERR_ARG;
+    G2_LAUNCH_RET();
+}
+
+int g2_norm_bwd_stats_f32(const float* y, const float* dout, const float* scale, const float* shift, const float* mean,
+                          const float* rstd, double* sums2, int N, int HW, int C, int sn, int post, cudaStream_t stream) {
+    G2_CHECK_ARG(y && dout && scale && shift && mean && rstd && sums2 && N > 0 && HW > 0 && C >= 4 && (C % 4) == 0 && C <= 1024);
+    const int Cy = post == G2_POST_GATE ? 2 * C : C;
+    cudaError_t e = cudaMemsetAsync(sums2, 0, sizeof(double) * 2 * (size_t)N * Cy, stream);
+    if (e != cudaSuccess) return (int)e;
+    const int lanes = 256 / (C / 4);
+    int rpb = lanes * 32;
+    while ((long)g2_cdiv(HW, rpb) * N > 148L * 32 && rpb < HW) rpb *= 2;
+    dim3 grid(g2_cdiv(HW, rpb), N);
+    if (post == G2_POST_GATE) norm_bwd_stats_kernel<G2_POST_GATE><<<grid, 256, 0, stream>>>(y, dout, scale, shift, mean, rstd, sums2, HW, C, sn, rpb);
+    else if (post == G2_POST_RELU) norm_bwd_stats_kernel<G2_POST_RELU><<<grid, 256, 0, stream>>>(y, dout, scale, shift, mean, rstd, sums2, HW, C, sn, rpb);
+    else return G2_ERR_ARG;
+    G2_LAUNCH_RET();
+}
+
+int g2_norm_bwd_finalize_f32(const double* sums2, const float* g0, const float* g1, float* m1, float* m2, float* dg0,
+                             float* db0, float* dg1, float* db1, int N, int HW, int Cy, int half, int mode, int groups,
+                             cudaStream_t stream) {
+    G2_CHECK_ARG(sums2 && m1 && m2 && N > 0 && Cy > 0 && half > 0 && half <= Cy);
+    G2_CHECK_ARG(mode == G2_NORM_BATCH || mode == G2_NORM_INSTANCE || mode == G2_NORM_GROUP);
+    if (mode == G2_NORM_GROUP) G2_CHECK_ARG(groups > 0 && Cy % groups == 0);
+    NormBwdFinP p{sums2, g0, g1, m1, m2, dg0, db0, dg1, db1, N, HW, Cy, half, mode, groups};
+    const int Ns = mode == G2_NORM_BATCH ? 1 : N;
+    norm_bwd_finalize_kernel<<<g2_cdiv((long)Ns * Cy, 128), 128, 0, stream>>>(p);
+    G2_LAUNCH_RET();
+}
+
+int g2_norm_bwd_apply_f32(const float* y, const float* dout, const float* scale, const float* shift, const float* mean,
+                          const float* rstd, const float* m1, const float* m2, float* dy, int N, int HW, int C, int sn,
+                          int post, cudaStream_t stream) {
+    G2_CHECK_ARG(y && dout && dy && N > 0 && HW > 0 && C >= 4 && (C % 4) == 0);
+    if (scale) G2_CHECK_ARG(shift && mean && rstd && m1 && m2);
+    const long quads = (long)N * HW * (C / 4);
+    if (post == G2_POST_GATE) norm_bwd_apply_kernel<G2_POST_GATE><<<ew_blocks(quads), 256, 0, stream>>>(y, dout, scale, shift, mean, rstd, m1, m2, dy, quads, HW, C, sn);
+    else if (post == G2_POST_RELU) norm_bwd_apply_kernel<G2_POST_RELU><<<ew_blocks(quads), 256, 0, stream>>>(y, dout, scale, shift, mean, rstd, m1, m2, dy, quads, HW, C, sn);
+    else return G2_ERR_ARG;
+    G2_LAUNCH_RET();
+}
+
+}  // extern "C"

@@ -1,0 +1,212 @@
+// genesis_b200 -- small HBM-bound kernels: layout changes, stick-breaking scans, component-VAE input
+// packing, broadcast-add, activation gradients and simple reductions.  fp32, 128-bit accesses where the
+// shapes allow.
+#include "common.cuh"
+
+namespace {
+
+inline int ew_blocks(long work, int threads = 256) {
+    long b = (work + threads - 1) / threads;
+    const long cap = 148L * 16;
+    return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+// x [N,C,P] -> y [N,P,C]   (dir 0)   or   x [N,P,C] -> y [N,C,P]   (dir 1)
+__global__ void layout_kernel(const float* __restrict__ x, float* __restrict__ y, long total, int C, int P, int dir) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        // i indexes the OUTPUT (coalesced writes)
+        if (dir == 0) {
+            const int c = (int)(i % C); const long t = i / C; const int p = (int)(t % P); const long n = t / P;
+            y[i] = __ldg(x + (n * C + c) * P + p);
+        } else {
+            const int p = (int)(i % P); const long t = i / P; const int c = (int)(t % C); const long n = t / C;
+            y[i] = __ldg(x + (n * P + p) * C + c);
+        }
+    }
+}
+
+// Stick-breaking scan over K slots (reference modules/attention.py:40-50,114-130 and the fix-up at
+// models/genesis_config.py:169-171).  logits [nl, BP] with nl >= K-1 (GENESIS decodes nl = K logit maps,
+// the last one is unused for the masks); log_m [K, BP]; log_s [nl+1, BP].
+//   log_s_0 = 0;  log_m_k = log_s_k + logsig(a_k), log_s_{k+1} = log_s_k + logsig(-a_k)  (k < K-1)
+//   log_m_{K-1} = log_s_{K-1}
+__global__ void sbp_scan_fwd_kernel(const float* __restrict__ logits, float* __restrict__ log_m, float* __restrict__ log_s,
+                                    long BP4, int K, int nl) {
+    const long BP = BP4 * 4;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < BP4; i += (long)gridDim.x * blockDim.x) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(log_s + i * 4) = s;
+        for (int k = 0; k < nl; ++k) {
+            const float4 a = g2_ldg4(logits + k * BP + i * 4);
+            if (k < K - 1) {
+                float4 m;
+                m.x = s.x + g2_logsigmoid(a.x); m.y = s.y + g2_logsigmoid(a.y);
+                m.z = s.z + g2_logsigmoid(a.z); m.w = s.w + g2_logsigmoid(a.w);
+                *reinterpret_cast<float4*>(log_m + k * BP + i * 4) = m;
+            } else if (k == K - 1) {
+                *reinterpret_cast<float4*>(log_m + k * BP + i * 4) = s;
+            }
+            s.x += g2_logsigmoid(-a.x); s.y += g2_logsigmoid(-a.y);
+            s.z += g2_logsigmoid(-a.z); s.w += g2_logsigmoid(-a.w);
+            *reinterpret_cast<float4*>(log_s + (k + 1) * BP + i * 4) = s;
+        }
+        if (nl == K - 1) *reinterpret_cast<float4*>(log_m + (long)(K - 1) * BP + i * 4) = s;
+    }
+}
+
+// d logits from d log_m (log_s is a non-differentiated statistic).  Reverse scan:
+//   R_{K-1} = G_{K-1};  for k = K-2..0:  da_k = G_k * sig(-a_k) - R_{k+1} * sig(a_k);  R_k = G_k + R_{k+1}
+__global__ void sbp_scan_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ dlog_m,
+                                    float* __restrict__ dlogits, long BP, int K, int nl) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < BP; i += (long)gridDim.x * blockDim.x) {
+        float R = __ldg(dlog_m + (long)(K - 1) * BP + i);
+        for (int k = nl - 1; k >= K - 1; --k) dlogits[k * BP + i] = 0.f;
+        for (int k = K - 2; k >= 0; --k) {
+            const float a = __ldg(logits + k * BP + i);
+            const float G = __ldg(dlog_m + k * BP + i);
+            const float sg = 1.f / (1.f + expf(-a));
+            dlogits[k * BP + i] = G * (1.f - sg) - R * sg;
+            R += G;
+        }
+    }
+}
+
+// component-VAE encoder input (reference modules/component_vae.py:58-63): for slot k, image b:
+// out[(k*B+b), p, 0] = log_m[k,b,p];  out[(k*B+b), p, 1..3] = x[b, 0..2, p]      (x NCHW, out NHWC4)
+__global__ void comp_pack_kernel(const float* __restrict__ x, const float* __restrict__ log_m, float* __restrict__ out,
+                                 long total, int B, int P) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int p = (int)(i % P); const long kb = i / P; const int b = (int)(kb % B);
+        float4 o;
+        o.x = __ldg(log_m + i);
+        const float* xb = x + (long)b * 3 * P + p;
+        o.y = __ldg(xb); o.z = __ldg(xb + P); o.w = __ldg(xb + 2 * P);
+        *reinterpret_cast<float4*>(out + i * 4) = o;
+    }
+}
+
+// out[n,p,c] = act(a[n,c] + m[p,c])      (broadcast decoder first layer, see decoder ops)
+__global__ void bcast_add_act_kernel(const float* __restrict__ a, const float* __restrict__ m, float* __restrict__ out,
+                                     long total_quads, int P, int C, int act) {
+    const int q = C >> 2;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total_quads; i += (long)gridDim.x * blockDim.x) {
+        const int quad = (int)(i % q); const long row = i / q; const int p = (int)(row % P); const long n = row / P;
+        const float4 av = g2_ldg4(a + n * C + quad * 4), mv = g2_ldg4(m + (long)p * C + quad * 4);
+        float4 o;
+        o.x = g2_apply_act(av.x + mv.x, act, 0.f); o.y = g2_apply_act(av.y + mv.y, act, 0.f);
+        o.z = g2_apply_act(av.z + mv.z, act, 0.f); o.w = g2_apply_act(av.w + mv.w, act, 0.f);
+        *reinterpret_cast<float4*>(out + i * 4) = o;
+    }
+}
+
+// dpre = dout * act'(out)   (act given as G2_ACT_MUL_*_GRAD), elementwise
+__global__ void act_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, float* __restrict__ dpre,
+                               long total4, int act) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
+        const float4 d = g2_ldg4(dout + i * 4), o = g2_ldg4(out + i * 4);
+        float4 r;
+        r.x = g2_apply_act(d.x, act, o.x); r.y = g2_apply_act(d.y, act, o.y);
+        r.z = g2_apply_act(d.z, act, o.z); r.w = g2_apply_act(d.w, act, o.w);
+        *reinterpret_cast<float4*>(dpre + i * 4) = r;
+    }
+}
+
+// out[n, c] = sum_p x[n, p, c]      grid (chunks, N), atomicAdd into pre-zeroed out
+__global__ void __launch_bounds__(256) seg_colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int P, int C,
+                                                         int rows_per_block) {
+    const int q = C >> 2, lanes = 256 / q;
+    const int t = threadIdx.x, lane = t / q, quad = t - lane * q, n = blockIdx.y;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(P, r0 + rows_per_block);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < lanes)
+        for (int r = r0 + lane; r < r1; r += lanes) {
+            const float4 v = g2_ldg4(x + ((long)n * P + r) * C + quad * 4);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+    __shared__ float4 sm[256];
+    sm[t] = s;
+    __syncthreads();
+    if (t < q) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = 0; l < lanes; ++l) { const float4 v = sm[l * q + t]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+        float* o = out + (long)n * C + t * 4;
+        atomicAdd(o, a.x); atomicAdd(o + 1, a.y); atomicAdd(o + 2, a.z); atomicAdd(o + 3, a.w);
+    }
+}
+
+// out[j] = sum_n x[n, j]     (j < J), coalesced over j
+__global__ void sum_dim0_kernel(const float* __restrict__ x, float* __restrict__ out, int N, long J4) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < J4; i += (long)gridDim.x * blockDim.x) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int n = 0; n < N; ++n) {
+            const float4 v = g2_ldg4(x + ((long)n * J4 + i) * 4);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        *reinterpret_cast<float4*>(out + i * 4) = s;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int g2_layout_f32(const float* x, float* y, long N, int C, int P, int to_nchw, cudaStream_t stream) {
+    G2_CHECK_ARG(x && y && N > 0 && C > 0 && P > 0);
+    const long total = N * C * P;
+    layout_kernel<<<ew_blocks(total), 256, 0, stream>>>(x, y, total, C, P, to_nchw ? 1 : 0);
+    G2_LAUNCH_RET();
+}
+
+int g2_sbp_scan_fwd_f32(const float* logits, float* log_m, float* log_s, long BP, int K, int nl, cudaStream_t stream) {
+    G2_CHECK_ARG(logits && log_m && log_s && BP > 0 && (BP % 4) == 0 && K >= 2 && (nl == K || nl == K - 1));
+    sbp_scan_fwd_kernel<<<ew_blocks(BP / 4), 256, 0, stream>>>(logits, log_m, log_s, BP / 4, K, nl);
+    G2_LAUNCH_RET();
+}
+
+int g2_sbp_scan_bwd_f32(const float* logits, const float* dlog_m, float* dlogits, long BP, int K, int nl, cudaStream_t stream) {
+    G2_CHECK_ARG(logits && dlog_m && dlogits && BP > 0 && K >= 2 && (nl == K || nl == K - 1));
+    sbp_scan_bwd_kernel<<<ew_blocks(BP), 256, 0, stream>>>(logits, dlog_m, dlogits, BP, K, nl);
+    G2_LAUNCH_RET();
+}
+
+int g2_comp_pack_f32(const float* x, const float* log_m, float* out, int K, int B, int P, cudaStream_t stream) {
+    G2_CHECK_ARG(x && log_m && out && K > 0 && B > 0 && P > 0);
+    const long total = (long)K * B * P;
+    comp_pack_kernel<<<ew_blocks(total), 256, 0, stream>>>(x, log_m, out, total, B, P);
+    G2_LAUNCH_RET();
+}
+
+int g2_bcast_add_act_f32(const float* a, const float* m, float* out, long N, int P, int C, int act, cudaStream_t stream) {
+    G2_CHECK_ARG(a && m && out && N > 0 && P > 0 && C >= 4 && (C % 4) == 0);
+    const long quads = N * P * (C / 4);
+    bcast_add_act_kernel<<<ew_blocks(quads), 256, 0, stream>>>(a, m, out, quads, P, C, act);
+    G2_LAUNCH_RET();
+}
+
+int g2_act_bwd_f32(const float* dout, const float* out, float* dpre, long total, int act, cudaStream_t stream) {
+    G2_CHECK_ARG(dout && out && dpre && total > 0 && (total % 4) == 0);
+    G2_CHECK_ARG(act == G2_ACT_RELU || act == G2_ACT_ELU);
+    const int code = act == G2_ACT_RELU ? G2_ACT_MUL_RELU_GRAD : G2_ACT_MUL_ELU_GRAD;
+    act_bwd_kernel<<<ew_blocks(total / 4), 256, 0, stream>>>(dout, out, dpre, total / 4, code);
+    G2_LAUNCH_RET();
+}
+
+int g2_seg_colsum_f32(const float* x, float* out, int N, int P, int C, cudaStream_t stream) {
+    G2_CHECK_ARG(x && out && N > 0 && P > 0 && C >= 4 && (C % 4) == 0 && C <= 1024);
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N * C, stream);
+    if (e != cudaSuccess) return (int)e;
+    const int lanes = 256 / (C / 4);
+    int rpb = lanes * 32;
+    while ((long)g2_cdiv(P, rpb) * N > 148L * 32 && rpb < P) rpb *= 2;
+    dim3 grid(g2_cdiv(P, rpb), N);
+    seg_colsum_kernel<<<grid, 256, 0, stream>>>(x, out, P, C, rpb);
+    G2_LAUNCH_RET();
+}
+
+int g2_sum_dim0_f32(const float* x, float* out, int N, long J, cudaStream_t stream) {
+    G2_CHECK_ARG(x && out && N > 0 && J > 0 && (J % 4) == 0);
+    sum_dim0_kernel<<<ew_blocks(J / 4), 256, 0, stream>>>(x, out, N, J / 4);
+    G2_LAUNCH_RET();
+}
+
+}  // extern "C"

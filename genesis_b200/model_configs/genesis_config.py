@@ -1,0 +1,268 @@
+"""GENESIS (V1) plug-in: drop-in for the reference's models/genesis_config.py.
+
+Same Forge contract -- importing this file registers the model flags, `load(cfg)` returns an nn.Module whose
+`forward(x)` returns `(recon, losses, stats, att_stats, comp_stats)`, plus `sample()` / `get_features()` --
+and the same state_dict names, so `train.py --model_config .../genesis_config.py` runs unchanged
+(reference models/genesis_config.py:33-56, 145-271).  All convolutions, conv-transposes, linears, norms,
+the stick-breaking scan and the mixture likelihood run in hand-written sm_100a kernels (genesis_b200.ops).
+"""
+import os
+import sys
+
+import torch
+import torch.nn as nn
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+import genesis_b200  # noqa: E402
+
+try:
+    from forge import flags
+except ImportError:  # reference Forge not importable: use the bundled stand-in
+    genesis_b200.enable_compat()
+    from forge import flags
+try:
+    from attrdict import AttrDict
+except ImportError:
+    genesis_b200.enable_compat()
+    from attrdict import AttrDict
+
+from genesis_b200 import holders as H  # noqa: E402
+from genesis_b200 import ops  # noqa: E402
+
+# Flag names / defaults: reference models/genesis_config.py:33-52
+flags.DEFINE_boolean('two_stage', True, 'Use two stages if two, else only one.')
+flags.DEFINE_boolean('autoreg_prior', True, 'Autoregressive prior.')
+flags.DEFINE_boolean('comp_prior', True, 'Component prior.')
+flags.DEFINE_integer('attention_latents', 64, 'Latent dimension.')
+flags.DEFINE_string('enc_norm', 'bn', '{bn, in} - norm type in encoder.')
+flags.DEFINE_string('dec_norm', 'bn', '{bn, in} - norm type in decoder.')
+flags.DEFINE_integer('comp_enc_channels', 32, 'Starting number of channels.')
+flags.DEFINE_integer('comp_ldim', 16, 'Latent dimension of the VAE.')
+flags.DEFINE_integer('comp_dec_channels', 32, 'Num channels in Broadcast Decoder.')
+flags.DEFINE_integer('comp_dec_layers', 4, 'Num layers in Broadcast Decoder.')
+flags.DEFINE_boolean('comp_symmetric', False, 'Use same encoder/decoder as in attention VAE.')
+flags.DEFINE_boolean('pixel_bound', True, 'Bound pixel values to [0, 1].')
+flags.DEFINE_float('pixel_std1', 0.7, 'StdDev of reconstructed pixels.')
+flags.DEFINE_float('pixel_std2', 0.7, 'StdDev of reconstructed pixels.')
+flags.DEFINE_boolean('montecarlo_kl', True, 'Evaluate KL via MC samples.')
+
+
+def load(cfg):
+    return Genesis(cfg)
+
+
+class LatentSBPHolder(nn.Module):
+    """Holder for modules/attention.py:77-82 (core + posterior LSTM + Linear)."""
+
+    def __init__(self, core):
+        super().__init__()
+        self.core = core
+        self.lstm = nn.LSTM(core.z_size + 256, 2 * core.z_size)
+        self.linear = nn.Linear(2 * core.z_size, 2 * core.z_size)
+
+
+class NoiseMixin(object):
+    """eps / u source: torch's device RNG in production, a recorded tape for parity runs."""
+    _tape = None
+
+    def set_noise_tape(self, tape):
+        self._tape = tape
+
+    def _normal(self, shape, like):
+        if self._tape is not None:
+            return self._tape.normal(shape).to(like.device)
+        return torch.randn(shape, device=like.device, dtype=torch.float32)
+
+    def _uniform(self, shape, like):
+        if self._tape is not None:
+            return self._tape.uniform(shape).to(like.device)
+        return torch.rand(shape, device=like.device, dtype=torch.float32)
+
+
+class Genesis(nn.Module, NoiseMixin):
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.K_steps = cfg.K_steps
+        self.img_size = cfg.img_size
+        self.two_stage = cfg.two_stage
+        self.autoreg_prior = cfg.autoreg_prior
+        self.comp_prior = False
+        if self.two_stage and self.K_steps > 1:
+            self.comp_prior = cfg.comp_prior
+        self.ldim = cfg.attention_latents
+        self.pixel_bound = cfg.pixel_bound
+        if not hasattr(cfg, 'comp_symmetric'):
+            cfg.comp_symmetric = False
+        self.debug = cfg.debug
+        assert cfg.montecarlo_kl == True  # noqa: E712  (reference genesis_config.py:80)
+        if cfg.comp_symmetric or not self.two_stage or self.K_steps < 2:
+            raise NotImplementedError('engine covers the default two-stage GENESIS (SURVEY.md section 8f.4)')
+        input_channels = cfg.input_channels if hasattr(cfg, 'input_channels') else 3
+        # construction order == reference (genesis_config.py:86-138) so seeded init is identical
+        core = H.SylvesterVAE(self.ldim, [input_channels, cfg.img_size, cfg.img_size], 1,
+                              cfg.enc_norm, cfg.dec_norm)
+        self.att_steps = self.K_steps
+        self.att_process = LatentSBPHolder(core)
+        self.comp_vae = H.ComponentVAEHolder(nout=input_channels, cfg=cfg)
+        if self.autoreg_prior:
+            self.prior_lstm = nn.LSTM(self.ldim, 256)
+            self.prior_linear = nn.Linear(256, 2 * self.ldim)
+        if self.comp_prior:
+            self.prior_mlp = nn.Sequential(
+                nn.Linear(self.ldim, 256), nn.Identity(), nn.Linear(256, 256), nn.Identity(),
+                nn.Linear(256, 2 * cfg.comp_ldim))
+        std = cfg.pixel_std2 * torch.ones(1, 1, 1, 1, self.K_steps)
+        std[0, 0, 0, 0, 0] = cfg.pixel_std1
+        self.register_buffer('std', std)
+
+    # --------------------------------------------------------------------------------------------
+    def _masks(self, x):
+        """LatentSBP.forward (reference attention.py:84-133) + the K-th mask fix-up (genesis_config.py:169-171)."""
+        K, B = self.K_steps, x.shape[0]
+        ap, core = self.att_process, self.att_process.core
+        h = H.sylvester_encode(core, ops.to_nhwc(x), self.training)                     # [B,256]
+        wmv = torch.cat([core.q_z_mean.weight, core.q_z_var[0].weight], 0)
+        bmv = torch.cat([core.q_z_mean.bias, core.q_z_var[0].bias], 0)
+        mu, raw = torch.chunk(ops.linear(h, wmv, bmv), 2, dim=1)
+        sigma = H.to_sigma(raw)                     # sqrt(to_var(.)) == to_sigma(.) (VAE.py:126)
+        mu_k, sigma_k = [mu], [sigma]
+        z_k = [mu + sigma * self._normal(mu.shape, x)]
+        state = None
+        for _ in range(1, K):
+            out, state = H.lstm_step(torch.cat([h, z_k[-1]], dim=1), state, ap.lstm)
+            a, b = torch.chunk(ops.linear(out, ap.linear.weight, ap.linear.bias), 2, dim=1)
+            s = H.to_sigma(b)
+            mu_k.append(a)
+            sigma_k.append(s)
+            z_k.append(a + s * self._normal(a.shape, x))
+        logits = H.sylvester_decode(core, torch.cat(z_k, 0), self.training)             # [K*B,1,H,W]
+        logits = logits.view(K, B, 1, self.img_size, self.img_size)
+        log_m, log_s = ops.sbp_scan(logits, K)
+        att_stats = AttrDict(x_k=list(logits.unbind(0)), mu_k=mu_k, sigma_k=sigma_k, z_k=z_k)
+        return log_m, log_s, att_stats
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError('genesis_b200 runs on CUDA (sm_100a) only; there is no CPU path')
+        K, B = self.K_steps, x.shape[0]
+        x = x.contiguous().float()
+        log_m, log_s, att_stats = self._masks(x)                     # [K,B,1,H,W], [K+1,B,1,H,W]
+        # --- component VAE (reference component_vae.py:45-81), K slots batched k-major
+        cv = self.comp_vae
+        enc = H.comp_encode(cv.encoder_module, ops.comp_pack(x, log_m), 'elu')
+        cmu, cps = torch.chunk(enc, 2, dim=1)
+        csig = H.to_sigma(cps)
+        cz = cmu + csig * self._normal(cmu.shape, x)
+        x_r = H.broadcast_decode(cv.decoder_module, cz, 'elu', 3 if self.pixel_bound else 0)
+        x_r = x_r.view(K, B, x.shape[1], self.img_size, self.img_size)
+        # --- reconstruction + mixture likelihood (reference genesis_config.py:188-196)
+        err, recon, _ = ops.mixture_nll(x, x_r, log_m, self.std.reshape(-1), False)
+        losses = AttrDict()
+        losses['err'] = err
+        # --- KL terms (reference genesis_config.py:198-259)
+        z_k = att_stats.z_k
+        if self.autoreg_prior:
+            pmu, psig = H.autoreg_prior(z_k, self.prior_lstm, self.prior_linear)
+        else:
+            pmu, psig = [], []
+        losses['kl_m_k'] = [H.mc_kl(z_k[0], att_stats.mu_k[0], att_stats.sigma_k[0])]
+        for k in range(1, K):
+            if self.autoreg_prior:
+                losses['kl_m_k'].append(H.mc_kl(z_k[k], att_stats.mu_k[k], att_stats.sigma_k[k], pmu[k - 1], psig[k - 1]))
+            else:
+                losses['kl_m_k'].append(H.mc_kl(z_k[k], att_stats.mu_k[k], att_stats.sigma_k[k]))
+        att_stats['pmu_k'], att_stats['psigma_k'] = pmu, psig
+        comp_stats = AttrDict(mu_k=list(torch.chunk(cmu, K, 0)), sigma_k=list(torch.chunk(csig, K, 0)),
+                              z_k=list(torch.chunk(cz, K, 0)))
+        losses['kl_l_k'] = []
+        if self.comp_prior:
+            pm = self.prior_mlp
+            t = ops.linear(torch.cat(z_k, 0), pm[0].weight, pm[0].bias, 'elu')
+            t = ops.linear(t, pm[2].weight, pm[2].bias, 'elu')
+            a, b = torch.chunk(ops.linear(t, pm[4].weight, pm[4].bias), 2, dim=1)
+            cpmu, cpsig = torch.tanh(a), H.to_prior_sigma(b)
+            comp_stats['pmu_k'] = list(torch.chunk(cpmu, K, 0))
+            comp_stats['psigma_k'] = list(torch.chunk(cpsig, K, 0))
+            kl = H.mc_kl(cz, cmu, csig, cpmu, cpsig)
+        else:
+            kl = H.mc_kl(cz, cmu, csig)
+        losses['kl_l_k'] = list(torch.chunk(kl, K, 0))
+        # --- tracking (reference genesis_config.py:262-264)
+        log_m_k = list(log_m.unbind(0))
+        x_r_k = list(x_r.unbind(0))
+        with torch.no_grad():
+            mx = x_r * log_m.exp()
+        stats = AttrDict(recon=recon, log_m_k=log_m_k, log_s_k=list(log_s.unbind(0)), x_r_k=x_r_k,
+                         mx_r_k=list(mx.unbind(0)))
+        if self.debug or not self.training:
+            assert len(log_m_k) == self.K_steps
+            check_log_masks(log_m_k)
+        return recon, losses, stats, att_stats, comp_stats
+
+    @staticmethod
+    def x_loss(x, log_m_k, x_r_k, std, pixel_wise=False):
+        """Genesis.x_loss (reference genesis_config.py:273-286) on the fused kernel."""
+        if pixel_wise:
+            raise NotImplementedError
+        K = len(log_m_k)
+        if not torch.is_tensor(std):
+            std = torch.full((K,), float(std), device=x.device)
+        std = std.reshape(-1).to(x.device).float()
+        if std.numel() == 1:
+            std = std.expand(K).contiguous()
+        err, _, _ = ops.mixture_nll(x, torch.stack(list(x_r_k), 0), torch.stack(list(log_m_k), 0), std, False)
+        return err
+
+    def sample(self, batch_size, K_steps=None):
+        """Ancestral sampling (reference genesis_config.py:345-425) on the engine's decoders."""
+        K = self.K_steps if K_steps is None else K_steps
+        assert K == self.K_steps
+        dev = self.std.device
+        like = self.std
+        with torch.no_grad():
+            z_k = [self._normal((batch_size, self.ldim), like)]
+            if self.autoreg_prior:
+                state = None
+                for _ in range(1, self.att_steps):
+                    out, state = H.lstm_step(z_k[-1], state, self.prior_lstm)
+                    lo = ops.linear(out, self.prior_linear.weight, self.prior_linear.bias)
+                    mu = lo[:, :self.ldim]                      # reference :359 -- no tanh in sample()
+                    sig = H.to_prior_sigma(lo[:, self.ldim:])
+                    z_k.append(mu + sig * self._normal(mu.shape, like))
+            else:
+                z_k += [self._normal((batch_size, self.ldim), like) for _ in range(1, self.att_steps)]
+            logits = H.sylvester_decode(self.att_process.core, torch.cat(z_k, 0), self.training)
+            logits = logits.view(K, batch_size, 1, self.img_size, self.img_size)
+            log_m, log_s = ops.sbp_scan(logits, K)
+            if self.comp_prior:
+                pm = self.prior_mlp
+                t = ops.linear(torch.cat(z_k, 0), pm[0].weight, pm[0].bias, 'elu')
+                t = ops.linear(t, pm[2].weight, pm[2].bias, 'elu')
+                a, b = torch.chunk(ops.linear(t, pm[4].weight, pm[4].bias), 2, dim=1)
+                mu, sig = torch.tanh(a), H.to_prior_sigma(b)
+                zc = mu + sig * self._normal(mu.shape, like)
+            else:
+                zc = self._normal((K * batch_size, self.comp_vae.ldim), like)
+            x_k = H.broadcast_decode(self.comp_vae.decoder_module, zc, 'elu', 3 if self.pixel_bound else 0)
+            x_k = x_k.view(K, batch_size, -1, self.img_size, self.img_size)
+            mx = x_k * log_m.exp()
+            img = mx.sum(0)
+        stats = AttrDict(x_k=list(x_k.unbind(0)), log_m_k=list(log_m.unbind(0)),
+                         log_s_k=list(log_s.unbind(0)), mx_k=list(mx.unbind(0)))
+        return img, stats
+
+    def get_features(self, image_batch):
+        with torch.no_grad():
+            _, _, _, att_stats, comp_stats = self.forward(image_batch)
+        return torch.cat([*att_stats['z_k'][:self.K_steps - 1], *comp_stats['z_k']], dim=1)
+
+
+def check_log_masks(log_m_k):
+    """Invariant of reference utils/misc.py:258-270: masks sum to one within 1e-3, no NaNs."""
+    summed = torch.stack(list(log_m_k), dim=4).exp().sum(dim=4)
+    bad = torch.isnan(summed).any() | ((summed - 1.0).max() > 1e-3)
+    if bool(bad):
+        raise ValueError("Masks do not sum to 1.0. Not close enough.")

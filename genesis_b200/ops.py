@@ -1,0 +1,445 @@
+"""Autograd operators over the C ABI of libgenesis_b200.so.
+
+Every heavy operator of the hot path (conv, conv-transpose, linear, norm+gate/ReLU, stick-breaking scan,
+broadcast-decoder layers, mixture likelihood) is a torch.autograd.Function whose forward and backward
+enqueue hand-written sm_100a kernels on the current CUDA stream.  Activations are NHWC fp32.
+There is no CPU or library fallback: a non-CUDA tensor raises."""
+import torch
+from torch.autograd import Function
+
+from . import _lib
+
+ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
+NORM_NONE, NORM_BATCH, NORM_INSTANCE, NORM_GROUP = 0, 1, 2, 3
+POST_GATE, POST_RELU = 0, 1
+ACTS = {None: 0, 'none': 0, 'relu': 1, 'elu': 2}
+
+
+def _call(name, *args):
+    _lib.call(name, *args)
+
+
+def _new(like, *shape, dtype=torch.float32):
+    return torch.empty(shape, device=like.device, dtype=dtype)
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _act_bwd(dout, out, act):
+    if act == ACT_NONE:
+        return dout
+    dpre = torch.empty_like(dout)
+    _call('g2_act_bwd_f32', dout, out, dpre, dout.numel(), act)
+    return dpre
+
+
+def _colsum(x2d_rows, C, like):
+    out = _new(like, C)
+    _call('g2_colsum_f32', x2d_rows, out, x2d_rows.numel() // C, C, 0)
+    return out
+
+
+# ----------------------------------------------------------------------------------------- layout
+class _Layout(Function):
+    @staticmethod
+    def forward(ctx, x, to_nchw):
+        x = _c(x)
+        ctx.to_nchw = to_nchw
+        if to_nchw:
+            N, H, W, C = x.shape
+            y = _new(x, N, C, H, W)
+        else:
+            N, C, H, W = x.shape
+            y = _new(x, N, H, W, C)
+        _call('g2_layout_f32', x, y, N, C, H * W, 1 if to_nchw else 0)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return _Layout.apply(dy, not ctx.to_nchw), None
+
+
+def to_nhwc(x):
+    return _Layout.apply(x, False)
+
+
+def to_nchw(x):
+    return _Layout.apply(x, True)
+
+
+# ----------------------------------------------------------------------------------------- conv
+class _Conv(Function):
+    """nn.Conv2d on NHWC activations; w in torch layout [Co,Ci,R,S]."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, pad, act):
+        x = _c(x)
+        N, H, W, Ci = x.shape
+        Co, Ci2, R, S = w.shape
+        assert Ci == Ci2, (x.shape, w.shape)
+        Ho = (H + 2 * pad - R) // stride + 1
+        Wo = (W + 2 * pad - S) // stride + 1
+        wp = w.detach().permute(2, 3, 1, 0).contiguous()          # [R,S,Ci,Co]
+        out = _new(x, N, Ho, Wo, Co)
+        _call('g2_conv_igemm_f32', x, wp, b, None, out, N, H, W, Ci, Ho, Wo, Co, R, S, stride, pad, 0, 0, act)
+        ctx.save_for_backward(x, wp, out if act != ACT_NONE else None)
+        ctx.cfg = (stride, pad, act, b is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, wp, out = ctx.saved_tensors
+        stride, pad, act, has_b = ctx.cfg
+        N, H, W, Ci = x.shape
+        R, S, _, Co = wp.shape
+        dout = _c(dout)
+        _, Ho, Wo, _ = dout.shape
+        dpre = _act_bwd(dout, out, act)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            _call('g2_conv_igemm_f32', dpre, wp, None, None, dx, N, Ho, Wo, Co, H, W, Ci, R, S, stride, pad, 1, 1, 0)
+        if ctx.needs_input_grad[1]:
+            dwp = torch.empty_like(wp)
+            _call('g2_conv_wgrad_f32', x, dpre, dwp, N, H, W, Ci, Ho, Wo, Co, R, S, stride, pad, 0)
+            dw = dwp.permute(3, 2, 0, 1).contiguous()
+        if has_b and ctx.needs_input_grad[2]:
+            db = _colsum(dpre, Co, dpre)
+        return dx, dw, db, None, None, None
+
+
+def conv2d(x, w, b=None, stride=1, pad=0, act=None):
+    return _Conv.apply(x, w, b, stride, pad, ACTS[act])
+
+
+class _ConvT(Function):
+    """nn.ConvTranspose2d (output_padding = stride-1) on NHWC activations; w torch layout [Ci,Co,R,S]."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, pad, act):
+        x = _c(x)
+        N, H, W, Ci = x.shape
+        Ci2, Co, R, S = w.shape
+        assert Ci == Ci2, (x.shape, w.shape)
+        op = stride - 1
+        Ho = (H - 1) * stride - 2 * pad + R + op
+        Wo = (W - 1) * stride - 2 * pad + S + op
+        wp = w.detach().permute(2, 3, 0, 1).contiguous()          # [R,S,Ci,Co]
+        out = _new(x, N, Ho, Wo, Co)
+        _call('g2_conv_igemm_f32', x, wp, b, None, out, N, H, W, Ci, Ho, Wo, Co, R, S, stride, pad, 1, 0, act)
+        ctx.save_for_backward(x, wp, out if act != ACT_NONE else None)
+        ctx.cfg = (stride, pad, act, b is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, wp, out = ctx.saved_tensors
+        stride, pad, act, has_b = ctx.cfg
+        N, H, W, Ci = x.shape
+        R, S, _, Co = wp.shape
+        dout = _c(dout)
+        _, Ho, Wo, _ = dout.shape
+        dpre = _act_bwd(dout, out, act)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            _call('g2_conv_igemm_f32', dpre, wp, None, None, dx, N, Ho, Wo, Co, H, W, Ci, R, S, stride, pad, 0, 1, 0)
+        if ctx.needs_input_grad[1]:
+            dwp = torch.empty_like(wp)
+            _call('g2_conv_wgrad_f32', dpre, x, dwp, N, Ho, Wo, Co, H, W, Ci, R, S, stride, pad, 1)
+            dw = dwp.permute(2, 3, 0, 1).contiguous()
+        if has_b and ctx.needs_input_grad[2]:
+            db = _colsum(dpre, Co, dpre)
+        return dx, dw, db, None, None, None
+
+
+def conv_transpose2d(x, w, b=None, stride=1, pad=0, act=None):
+    return _ConvT.apply(x, w, b, stride, pad, ACTS[act])
+
+
+# ----------------------------------------------------------------------------------------- linear
+class _Linear(Function):
+    """y = act(x @ w.T + b);  x [M,K], w [N,K]."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        x = _c(x)
+        w = _c(w)
+        M, K = x.shape
+        N = w.shape[0]
+        y = _new(x, M, N)
+        _call('g2_gemm_f32', x, w, b, y, M, N, K, K, K, N, 0, 1, ACT_NONE, 0)
+        if act != ACT_NONE:      # split-K GEMMs cannot fuse the activation; keep it a separate pass
+            if N % 4 != 0:
+                raise RuntimeError('linear with activation needs N % 4 == 0')
+            pre = y
+            y = torch.empty_like(pre)
+            _call('g2_bcast_add_act_f32', pre, _zeros_row(pre, N), y, M, 1, N, act)
+        ctx.save_for_backward(x, w, y if act != ACT_NONE else None)
+        ctx.cfg = (act, b is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        act, has_b = ctx.cfg
+        M, K = x.shape
+        N = w.shape[0]
+        dpre = _act_bwd(_c(dy), y, act)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            _call('g2_gemm_f32', dpre, w, None, dx, M, K, N, N, K, K, 0, 0, ACT_NONE, 0)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(w)
+            _call('g2_gemm_f32', dpre, x, None, dw, N, K, M, N, K, K, 1, 0, ACT_NONE, 0)
+        if has_b and ctx.needs_input_grad[2]:
+            db = _colsum(dpre, N, dpre)
+        return dx, dw, db, None
+
+
+_ZERO_ROWS = {}
+
+
+def _zeros_row(like, n):
+    key = (like.device, n)
+    if key not in _ZERO_ROWS:
+        _ZERO_ROWS[key] = torch.zeros(n, device=like.device, dtype=torch.float32)
+    return _ZERO_ROWS[key]
+
+
+def linear(x, w, b=None, act=None):
+    return _Linear.apply(x, w, b, ACTS[act])
+
+
+# ----------------------------------------------------------------------------------------- norm + post
+class _NormPost(Function):
+    """y [N,H,W,Cy] -> post(norm(y)).  post = gate (Cy = 2C, out C channels) or ReLU.
+    params: (g0,b0) affine of the first half / whole, (g1,b1) affine of the second (gate) half."""
+
+    @staticmethod
+    def forward(ctx, y, g0, b0, g1, b1, rm0, rv0, rm1, rv1, mode, post, groups, training, eps, momentum):
+        y = _c(y)
+        N, H, W, Cy = y.shape
+        HW = H * W
+        C = Cy // 2 if post == POST_GATE else Cy
+        half = C if post == POST_GATE else Cy
+        out = _new(y, N, H, W, C)
+        if mode == NORM_NONE:
+            _call('g2_norm_apply_f32', y, None, None, out, N, HW, C, 0, post)
+            ctx.save_for_backward(y)
+            ctx.cfg = (mode, post, groups, half)
+            return out
+        Ns = 1 if mode == NORM_BATCH else N
+        sums = None
+        if not (mode == NORM_BATCH and not training):
+            sums = _new(y, N, Cy, 2, dtype=torch.float64)
+            _call('g2_norm_stats_f32', y, sums, N, HW, Cy)
+        mean, rstd, scale, shift = (_new(y, Ns, Cy) for _ in range(4))
+        _call('g2_norm_finalize_f32', sums, g0, b0, g1, b1, rm0, rv0, rm1, rv1, mean, rstd, scale, shift,
+              N, HW, Cy, half, mode, groups, 1 if training else 0, eps, momentum)
+        sn = 0 if mode == NORM_BATCH else Cy
+        _call('g2_norm_apply_f32', y, scale, shift, out, N, HW, C, sn, post)
+        ctx.save_for_backward(y, scale, shift, mean, rstd, g0, g1)
+        ctx.cfg = (mode, post, groups, half)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        mode, post, groups, half = ctx.cfg
+        dout = _c(dout)
+        if mode == NORM_NONE:
+            (y,) = ctx.saved_tensors
+            N, H, W, Cy = y.shape
+            C = dout.shape[3]
+            dy = torch.empty_like(y)
+            _call('g2_norm_bwd_apply_f32', y, dout, None, None, None, None, None, None, dy, N, H * W, C, 0, post)
+            return (dy,) + (None,) * 14
+        y, scale, shift, mean, rstd, g0, g1 = ctx.saved_tensors
+        N, H, W, Cy = y.shape
+        HW = H * W
+        C = dout.shape[3]
+        Ns = scale.shape[0]
+        sn = 0 if mode == NORM_BATCH else Cy
+        sums2 = _new(y, N, Cy, 2, dtype=torch.float64)
+        _call('g2_norm_bwd_stats_f32', y, dout, scale, shift, mean, rstd, sums2, N, HW, C, sn, post)
+        m1, m2 = _new(y, Ns, Cy), _new(y, Ns, Cy)
+        dg0 = _new(y, half) if g0 is not None else None
+        db0 = _new(y, half) if g0 is not None else None
+        dg1 = _new(y, Cy - half) if g1 is not None else None
+        db1 = _new(y, Cy - half) if g1 is not None else None
+        _call('g2_norm_bwd_finalize_f32', sums2, g0, g1, m1, m2, dg0, db0, dg1, db1, N, HW, Cy, half, mode, groups)
+        dy = torch.empty_like(y)
+        _call('g2_norm_bwd_apply_f32', y, dout, scale, shift, mean, rstd, m1, m2, dy, N, HW, C, sn, post)
+        return (dy, dg0, db0, dg1, db1) + (None,) * 10
+
+
+def norm_post(y, g0=None, b0=None, g1=None, b1=None, rm0=None, rv0=None, rm1=None, rv1=None,
+              mode=NORM_NONE, post=POST_GATE, groups=1, training=True, eps=1e-5, momentum=0.1):
+    return _NormPost.apply(y, g0, b0, g1, b1, rm0, rv0, rm1, rv1, mode, post, groups, training, eps, momentum)
+
+
+# ----------------------------------------------------------------------------------------- SBP scan
+class _SBPScan(Function):
+    """logits [nl,B,...] -> log_m [K,B,...], log_s [nl+1,B,...] (log_s is a statistic: no gradient)."""
+
+    @staticmethod
+    def forward(ctx, logits, K):
+        logits = _c(logits)
+        nl = logits.shape[0]
+        BP = logits[0].numel()
+        log_m = _new(logits, K, *logits.shape[1:])
+        log_s = _new(logits, nl + 1, *logits.shape[1:])
+        _call('g2_sbp_scan_fwd_f32', logits, log_m, log_s, BP, K, nl)
+        ctx.save_for_backward(logits)
+        ctx.K = K
+        ctx.mark_non_differentiable(log_s)
+        return log_m, log_s
+
+    @staticmethod
+    def backward(ctx, dlog_m, _dlog_s):
+        (logits,) = ctx.saved_tensors
+        nl = logits.shape[0]
+        d = torch.empty_like(logits)
+        _call('g2_sbp_scan_bwd_f32', logits, _c(dlog_m), d, logits[0].numel(), ctx.K, nl)
+        return d, None
+
+
+def sbp_scan(logits, K):
+    return _SBPScan.apply(logits, K)
+
+
+# ----------------------------------------------------------------------------------------- comp pack
+class _CompPack(Function):
+    """x [B,3,H,W] (NCHW), log_m [K,B,1,H,W] -> [K*B,H,W,4] NHWC with channel 0 = log_m, 1..3 = x."""
+
+    @staticmethod
+    def forward(ctx, x, log_m):
+        x, log_m = _c(x), _c(log_m)
+        K, B = log_m.shape[0], log_m.shape[1]
+        H, W = x.shape[2], x.shape[3]
+        out = _new(x, K * B, H, W, 4)
+        _call('g2_comp_pack_f32', x, log_m, out, K, B, H * W)
+        ctx.shape = log_m.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        return None, dout[..., 0].reshape(ctx.shape).contiguous()
+
+
+def comp_pack(x, log_m):
+    return _CompPack.apply(x, log_m)
+
+
+# ----------------------------------------------------------------------------------------- broadcast add
+class _BcastAddAct(Function):
+    """out[n,p,c] = act(a[n,c] + m[p,c])."""
+
+    @staticmethod
+    def forward(ctx, a, m, act):
+        a, m = _c(a), _c(m)
+        N, C = a.shape
+        P = m.shape[0]
+        out = _new(a, N, P, C)
+        _call('g2_bcast_add_act_f32', a, m, out, N, P, C, act)
+        ctx.save_for_backward(out)
+        ctx.act = act
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (out,) = ctx.saved_tensors
+        N, P, C = out.shape
+        dpre = _act_bwd(_c(dout), out, ctx.act)
+        da = dm = None
+        if ctx.needs_input_grad[0]:
+            da = _new(out, N, C)
+            _call('g2_seg_colsum_f32', dpre, da, N, P, C)
+        if ctx.needs_input_grad[1]:
+            dm = _new(out, P, C)
+            _call('g2_sum_dim0_f32', dpre, dm, N, P * C)
+        return da, dm, None
+
+
+def bcast_add_act(a, m, act=None):
+    return _BcastAddAct.apply(a, m, ACTS[act])
+
+
+# ----------------------------------------------------------------------------------------- 1x1 output head
+class _Out1x1(Function):
+    """h [N,H,W,Cin] NHWC -> out [N,nout,H,W] NCHW, sigmoid on the first nsig channels; w [nout,Cin,1,1]."""
+
+    @staticmethod
+    def forward(ctx, h, w, b, nsig):
+        h = _c(h)
+        N, H, W, Cin = h.shape
+        nout = w.shape[0]
+        w2 = w.detach().reshape(nout, Cin).contiguous()
+        out = _new(h, N, nout, H, W)
+        _call('g2_out1x1_fwd_f32', h, w2, b, out, N, H * W, Cin, nout, nsig)
+        ctx.save_for_backward(h, w2, out)
+        ctx.cfg = (nsig, b is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, w2, out = ctx.saved_tensors
+        nsig, has_b = ctx.cfg
+        N, H, W, Cin = h.shape
+        nout = w2.shape[0]
+        dh = torch.empty_like(h) if ctx.needs_input_grad[0] else None
+        dpre4 = _new(h, N, H, W, 4)
+        _call('g2_out1x1_bwd_f32', _c(dout), out, w2, dh, dpre4, N, H * W, Cin, nout, nsig)
+        dw = db = None
+        if ctx.needs_input_grad[1]:
+            dw4 = _new(h, 4, Cin)
+            _call('g2_conv_wgrad_f32', h, dpre4, dw4, N, H, W, Cin, H, W, 4, 1, 1, 1, 0, 1)
+            dw = dw4[:nout].reshape(nout, Cin, 1, 1).contiguous()
+        if has_b and ctx.needs_input_grad[2]:
+            db = _colsum(dpre4, 4, dpre4)[:nout].contiguous()
+        return dh, dw, db, None
+
+
+def out1x1(h, w, b=None, nsig=0):
+    return _Out1x1.apply(h, w, b, nsig)
+
+
+# ----------------------------------------------------------------------------------------- mixture loss
+class _Mixture(Function):
+    """Genesis.x_loss fused with recon (and log-softmax of mask logits when softmax=True).
+    x [B,3,H,W], xr [K,B,3,H,W], lm [K,B,1,H,W], std [K] -> err [B], recon [B,3,H,W],
+    log-softmax masks [K,B,1,H,W] (empty when softmax=False)."""
+
+    @staticmethod
+    def forward(ctx, x, xr, lm, std, softmax):
+        x, xr, lm, std = _c(x), _c(xr), _c(lm), _c(std)
+        K, B = lm.shape[0], lm.shape[1]
+        P = x.shape[2] * x.shape[3]
+        err = _new(x, B)
+        recon = torch.empty_like(x)
+        lse = torch.empty_like(x)
+        lm_out = torch.empty_like(lm) if softmax else None
+        _call('g2_mixture_fwd_f32', x, xr, lm, std, err, recon, lse, lm_out, K, B, P, 1 if softmax else 0)
+        ctx.save_for_backward(x, xr, lm_out if softmax else lm, std, lse)
+        ctx.softmax = softmax
+        if not softmax:
+            lm_out = _new(x, 0)
+        ctx.mark_non_differentiable(recon, lm_out)
+        return err, recon, lm_out
+
+    @staticmethod
+    def backward(ctx, gerr, _grecon, _glm):
+        x, xr, lm, std, lse = ctx.saved_tensors
+        K, B = lm.shape[0], lm.shape[1]
+        P = x.shape[2] * x.shape[3]
+        dxr = torch.empty_like(xr)
+        dlm = torch.empty_like(lm)
+        _call('g2_mixture_bwd_f32', x, xr, lm, std, lse, _c(gerr), dxr, dlm, K, B, P, 1 if ctx.softmax else 0)
+        return None, dxr, dlm, None, None
+
+
+def mixture_nll(x, xr, lm, std, softmax=False):
+    return _Mixture.apply(x, xr, lm, std, softmax)

@@ -1,0 +1,132 @@
+/* genesis_b200.h -- C ABI of libgenesis_b200.so (sm_100a).
+ *
+ * The reference (applied-ai-lab/genesis) has no native layer: every operator of its hot path is a
+ * PyTorch nn.Module call that ends in cuDNN / cuBLAS / ATen.  This library is what a replacement of
+ * those calls binds to.  Each entry point names the reference call sites it replaces (paths relative
+ * to the reference checkout).  Conventions:
+ *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller, including
+ *     workspaces and tensors saved for the backward pass; nothing is allocated or freed inside;
+ *   - all work is enqueued on `stream`; no host synchronisation; no global mutable state, so every
+ *     call is re-entrant per stream and CUDA-graph capturable;
+ *   - returns 0 on success, a negative G2_ERR_* code for a rejected argument, or a positive
+ *     cudaError_t from the launch;
+ *   - image activations are NHWC fp32 ([N, H*W, C] row-major) unless stated otherwise; tensors that
+ *     cross the model boundary (x, recon, x_r_k, log_m_k) are the reference's NCHW.
+ */
+#ifndef GENESIS_B200_H_
+#define GENESIS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* g2_stream_t; /* == cudaStream_t */
+
+#define G2_OK 0
+#define G2_ERR_ARG (-1)
+#define G2_ERR_UNSUPPORTED (-2)
+
+/* activation / epilogue codes */
+#define G2_ACT_NONE 0
+#define G2_ACT_RELU 1
+#define G2_ACT_ELU 2
+#define G2_ACT_MUL_RELU_GRAD 3 /* out = acc * relu'(pre), aux = saved post-activation */
+#define G2_ACT_MUL_ELU_GRAD 4
+#define G2_ACT_SIGMOID 5
+/* normalisation modes and post-ops */
+#define G2_NORM_NONE 0
+#define G2_NORM_BATCH 1
+#define G2_NORM_INSTANCE 2
+#define G2_NORM_GROUP 3
+#define G2_POST_GATE 0
+#define G2_POST_RELU 1
+
+int g2_abi_version(void);
+
+/* ---- convolutions, exact fp32 SIMT implicit GEMM (igemm_simt.cu) -----------------------------------
+ * Replaces F.conv2d / F.conv_transpose2d and their autograd backward for every conv of the path:
+ * third_party/sylvester/layers.py:19-20,43,65-67,90 (gated 5x5 / 16x16 convs and conv-transposes),
+ * modules/encoders.py:31-34 (3x3 s2), modules/decoders.py:27-31 (3x3 VALID, 1x1),
+ * modules/blocks.py:151-165 (3x3 p1), models/genesisv2_config.py:89-99 (conv-transpose 5x5 s2).
+ * mode 0: out[n,oh,ow,co] = b[co] + sum in[n,oh*S+r-P,ow*S+s-P,c] w[r,s,c,co]   (conv fwd, convT dgrad)
+ * mode 1: out[n,h,w,co] = b[co] + sum_{(h+P-r)%S==0,(w+P-s)%S==0} in[n,(h+P-r)/S,(w+P-s)/S,c] w[r,s,c,co]
+ *                                                                                (convT fwd, conv dgrad)
+ * w packed [R,S,Ci,Co] (wT=0) or [R,S,Co,Ci] (wT=1); bias/aux may be NULL; act = G2_ACT_*. */
+int g2_conv_igemm_f32(const float* in, const float* w, const float* bias, const float* aux, float* out,
+                      int N, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int R, int S, int stride,
+                      int pad, int mode, int wT, int act, g2_stream_t stream);
+/* dW[r,s,a,b] = sum_{n,oh,ow} g[n,oh*S+r-P,ow*S+s-P,a] * t[n,oh,ow,b]; dw layout [R,S,Cg,Ct] (outT=0) or
+ * [R,S,Ct,Cg] (outT=1); dw is overwritten. */
+int g2_conv_wgrad_f32(const float* g, const float* t, float* dw, int N, int Hg, int Wg, int Cg, int Ht,
+                      int Wt, int Ct, int R, int S, int stride, int pad, int outT, g2_stream_t stream);
+/* C[M,N] (+)= op(A)[M,K] op(B)[K,N] + bias[N], row-major.  Replaces nn.Linear / nn.LSTM matmuls
+ * (third_party/sylvester/VAE.py:100-104; modules/attention.py:81-82,94-97; modules/encoders.py:35-37;
+ * modules/unet.py:60-65; models/genesis_config.py:131-138; models/genesisv2_config.py:82-86,104-105)
+ * and the full-map gated convs VAE.py:23,29 viewed as GEMMs. */
+int g2_gemm_f32(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int lda,
+                int ldb, int ldc, int transA, int transB, int act, int accumulate, g2_stream_t stream);
+/* out[c] (+)= sum_m x[m,c]   (bias gradients) */
+int g2_colsum_f32(const float* x, float* out, long M, int C, int accumulate, g2_stream_t stream);
+
+/* ---- normalisation + gate / ReLU (norm.cu) ---------------------------------------------------------
+ * Replaces nn.BatchNorm2d / nn.InstanceNorm2d / nn.GroupNorm + sigmoid gate or ReLU and their backward:
+ * third_party/sylvester/layers.py:22-54,69-101; modules/blocks.py:151-165;
+ * models/genesisv2_config.py:92-98.  y is [N,HW,Cy]; for POST_GATE Cy = 2C (h | g), out is [N,HW,C]. */
+int g2_norm_stats_f32(const float* y, double* sums /*[N,Cy,2]*/, int N, int HW, int Cy, g2_stream_t stream);
+int g2_norm_finalize_f32(const double* sums, const float* g0, const float* b0, const float* g1, const float* b1,
+                         float* rm0, float* rv0, float* rm1, float* rv1, float* mean, float* rstd, float* scale,
+                         float* shift, int N, int HW, int Cy, int half, int mode, int groups, int training,
+                         float eps, float momentum, g2_stream_t stream);
+int g2_norm_apply_f32(const float* y, const float* scale, const float* shift, float* out, int N, int HW, int C,
+                      int sn, int post, g2_stream_t stream);
+int g2_norm_bwd_stats_f32(const float* y, const float* dout, const float* scale, const float* shift,
+                          const float* mean, const float* rstd, double* sums2 /*[N,Cy,2]*/, int N, int HW, int C,
+                          int sn, int post, g2_stream_t stream);
+int g2_norm_bwd_finalize_f32(const double* sums2, const float* g0, const float* g1, float* m1, float* m2,
+                             float* dg0, float* db0, float* dg1, float* db1, int N, int HW, int Cy, int half,
+                             int mode, int groups, g2_stream_t stream);
+int g2_norm_bwd_apply_f32(const float* y, const float* dout, const float* scale, const float* shift,
+                          const float* mean, const float* rstd, const float* m1, const float* m2, float* dy,
+                          int N, int HW, int C, int sn, int post, g2_stream_t stream);
+
+/* ---- layout, scans, packing, reductions (pointwise.cu) --------------------------------------------- */
+/* x [N,C,P] <-> y [N,P,C] */
+int g2_layout_f32(const float* x, float* y, long N, int C, int P, int to_nchw, g2_stream_t stream);
+/* stick-breaking scan, modules/attention.py:40-50,114-130 + models/genesis_config.py:169-171 */
+int g2_sbp_scan_fwd_f32(const float* logits, float* log_m, float* log_s, long BP, int K, int nl, g2_stream_t stream);
+int g2_sbp_scan_bwd_f32(const float* logits, const float* dlog_m, float* dlogits, long BP, int K, int nl,
+                        g2_stream_t stream);
+/* component-VAE encoder input: repeat(x) (+) cat(log_m), modules/component_vae.py:58-63 */
+int g2_comp_pack_f32(const float* x, const float* log_m, float* out, int K, int B, int P, g2_stream_t stream);
+/* out[n,p,c] = act(a[n,c] + m[p,c]): first broadcast-decoder layer without materialising the broadcast,
+ * modules/blocks.py:104-130 + modules/decoders.py:25-26 */
+int g2_bcast_add_act_f32(const float* a, const float* m, float* out, long N, int P, int C, int act,
+                         g2_stream_t stream);
+int g2_act_bwd_f32(const float* dout, const float* out, float* dpre, long total, int act, g2_stream_t stream);
+int g2_seg_colsum_f32(const float* x, float* out, int N, int P, int C, g2_stream_t stream);
+int g2_sum_dim0_f32(const float* x, float* out, int N, long J, g2_stream_t stream);
+
+/* ---- decoder head + mixture likelihood (loss.cu) ---------------------------------------------------
+ * out1x1: final 1x1 conv (+ sigmoid on the first nsig channels) writing NCHW planes:
+ * modules/decoders.py:31, modules/component_vae.py:89-93, third_party/sylvester/VAE.py:121,
+ * modules/unet.py:66, models/genesisv2_config.py:99. */
+int g2_out1x1_fwd_f32(const float* h, const float* w, const float* bias, float* out, long N, int P, int Cin,
+                      int nout, int nsig, g2_stream_t stream);
+int g2_out1x1_bwd_f32(const float* dout, const float* out, const float* w, float* dh, float* dpre4, long N,
+                      int P, int Cin, int nout, int nsig, g2_stream_t stream);
+/* Genesis.x_loss + recon (+ log-softmax of mask logits): models/genesis_config.py:188-190,273-286,
+ * models/monet_config.py:136-140, models/genesisv2_config.py:213-223. */
+int g2_mixture_fwd_f32(const float* x, const float* xr, const float* lm, const float* stdv, float* err,
+                       float* recon, float* lse, float* lm_out, int K, int B, int P, int softmax,
+                       g2_stream_t stream);
+int g2_mixture_bwd_f32(const float* x, const float* xr, const float* lm, const float* stdv, const float* lse,
+                       const float* gerr, float* dxr, float* dlm, int K, int B, int P, int softmax,
+                       g2_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENESIS_B200_H_ */

@@ -1,0 +1,104 @@
+"""ORACLE / test infrastructure -- generate tests/golden/*.npz FROM THE REAL REFERENCE.
+
+Run in the build container only (needs /root/reference):  python -m oracle.make_golden
+For each case: seed the reference model (torch.manual_seed(0) -> default init), build a synthetic
+batch (oracle/synth.py, seed 1), replay a NoiseTape (seed 2) through the reference's own forward,
+differentiate the train.py loss (beta=1) and store inputs, noise, outputs, per-parameter checksums
+and per-parameter gradient summaries.  Parameters themselves (up to 50 MB) are NOT stored: the
+engine re-creates them from the same seed, and the checksums prove they are the same tensors."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import functional as O, models as M, ref_loader, synth  # noqa: E402
+
+CASES = [  # name, model, K, img, B, generator
+    ('genesis_k5_b2', 'genesis', 5, 64, 2, 'multid'),
+    ('genesis_k3_b3', 'genesis', 3, 64, 3, 'rooms'),
+    ('genesisv2_k7_b2', 'genesisv2', 7, 64, 2, 'stacks'),
+    ('genesisv2_k4_b3', 'genesisv2', 4, 64, 3, 'rooms'),
+    ('monet_k7_b2', 'monet', 7, 64, 2, 'multid'),
+    ('monet128_k3_b1', 'monet', 3, 128, 1, 'multid'),
+]
+OUT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+
+def direction(n, idx):
+    """Fixed pseudo-random probe vector for gradient projections."""
+    i = torch.arange(n, dtype=torch.float64)
+    return torch.cos(0.37 * i + 1.3 * idx + 0.1)
+
+
+def param_checksums(sd):
+    names = sorted(sd.keys())
+    sums = np.array([[sd[k].double().sum().item(), sd[k].double().abs().sum().item()] for k in names])
+    return names, sums
+
+
+def ref_total_loss(losses):
+    """train.py:227-259 with beta = 1."""
+    tot = losses['err'].mean(0)
+    for key in ('kl_l_k', 'kl_m_k'):
+        if key in losses:
+            tot = tot + torch.stack(list(losses[key]), 1).mean(0).sum()
+    if 'kl_m' in losses and torch.is_tensor(losses['kl_m']) and losses['kl_m'].numel() > 1:
+        tot = tot + losses['kl_m'].mean(0)
+    return tot
+
+
+def run_case(name, model, K, img, B, gen):
+    cfg = M.make_cfg(model, K_steps=K, img_size=img)
+    ref = ref_loader.load_reference(model, cfg, seed=0)
+    ref.train()
+    names, sums = param_checksums(ref.state_dict())
+    x = torch.from_numpy(synth.GENERATORS[gen](B, img, 1)[0])
+    tape = O.NoiseTape(seed=2)
+    with ref_loader.replay_noise(tape):
+        recon, losses, stats, att, comp = ref(x)
+    ref_total_loss(losses).backward()
+    g = {}
+    pnames = [k for k, _ in ref.named_parameters()]
+    gsum = np.zeros((len(pnames), 2))
+    for i, (k, p) in enumerate(ref.named_parameters()):
+        if p.grad is not None:
+            gd = p.grad.double().flatten()
+            gsum[i] = [gd.norm().item(), (gd * direction(gd.numel(), i)).sum().item()]
+    g['x'] = x.numpy()
+    g['noise_kinds'] = np.array([k for k, _ in tape.record])
+    for i, (_, t) in enumerate(tape.record):
+        g['noise_%d' % i] = t.numpy()
+    g['param_names'] = np.array(names)
+    g['param_sums'] = sums
+    g['grad_names'] = np.array(pnames)
+    g['grad_sums'] = gsum
+    g['recon'] = recon.detach().numpy()
+    g['err'] = losses['err'].detach().numpy()
+    for key in ('kl_l_k', 'kl_m_k'):
+        if key in losses:
+            g[key] = torch.stack(list(losses[key]), 0).detach().numpy()
+    if 'kl_m' in losses and torch.is_tensor(losses['kl_m']) and losses['kl_m'].numel() > 1:
+        g['kl_m'] = losses['kl_m'].detach().numpy()
+    g['log_m_k'] = torch.stack(list(stats['log_m_k']), 0).detach().numpy()
+    if 'log_m_r_k' in stats:
+        g['log_m_r_k'] = torch.stack(list(stats['log_m_r_k']), 0).detach().numpy()
+    g['x_r_k'] = torch.stack(list(stats['x_r_k']), 0).detach().numpy().astype(np.float16)
+    sd = ref.state_dict()
+    bn = sorted(k for k in sd if k.endswith('running_mean') or k.endswith('running_var'))
+    if bn:
+        g['bn_names'] = np.array(bn)
+        g['bn_sums'] = np.array([[sd[k].double().sum().item(), sd[k].double().abs().sum().item()] for k in bn])
+    g['meta'] = np.array([model, str(K), str(img), str(B), gen])
+    os.makedirs(OUT_DIR, exist_ok=True)
+    path = os.path.join(OUT_DIR, name + '.npz')
+    np.savez_compressed(path, **g)
+    print(name, 'err', g['err'], '->', path, os.path.getsize(path) // 1024, 'KiB')
+
+
+if __name__ == '__main__':
+    if not ref_loader.available():
+        sys.exit('reference checkout not found at %s' % ref_loader.REF_ROOT)
+    for case in CASES:
+        run_case(*case)

@@ -1,0 +1,112 @@
+"""GPU: GENESIS (V1) engine vs the oracle and vs the golden vectors generated from the reference."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import models as M
+from oracle import synth
+
+import util_parity as U
+from test_oracle_golden import build_engine_model, golden_case, tape_from_golden, direction
+
+pytestmark = pytest.mark.gpu
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'genesis_k*.npz')))
+
+# fp32 tolerances: ELBO terms rel 1e-4, per-tensor gradient rel-L2 1e-2
+ERR_RTOL, KL_ATOL, GRAD_TOL = 1e-4, 5e-3, 1e-2
+
+
+@pytest.mark.parametrize('path', GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_genesis_matches_reference_golden(path):
+    g, model, K, img, B = golden_case(path)
+    m, cfg = build_engine_model(model, K, img)
+    m = m.cuda().train()
+    recon, losses, stats, att, comp = U.run_engine(m, torch.from_numpy(g['x']), tape_from_golden(g))
+    np.testing.assert_allclose(losses['err'].detach().cpu().numpy(), g['err'], rtol=ERR_RTOL)
+    np.testing.assert_allclose(recon.detach().cpu().numpy(), g['recon'], atol=2e-3)
+    np.testing.assert_allclose(torch.stack(stats['log_m_k'], 0).detach().cpu().numpy(), g['log_m_k'], atol=5e-3, rtol=1e-3)
+    for key in ('kl_l_k', 'kl_m_k'):
+        np.testing.assert_allclose(torch.stack(losses[key], 0).detach().cpu().numpy(), g[key], atol=KL_ATOL, rtol=1e-3)
+    gmax = max(float(s[0]) for s in g['grad_sums'])
+    params = dict(m.named_parameters())
+    for i, (n, (nrm, proj)) in enumerate(zip(g['grad_names'], g['grad_sums'])):
+        gd = params[str(n)].grad.detach().double().cpu().flatten()
+        tol = GRAD_TOL * nrm + 1e-4 * gmax
+        assert abs(gd.norm().item() - nrm) <= tol, (n, gd.norm().item(), nrm)
+        assert abs((gd * direction(gd.numel(), i)).sum().item() - proj) <= 4 * tol, (n, proj)
+    sd = m.state_dict()
+    for n, (s, a) in zip(g['bn_names'], g['bn_sums']):
+        t = sd[str(n)].double()
+        assert abs(t.sum().item() - s) <= 1e-3 * max(1.0, abs(s)), n
+        assert abs(t.abs().sum().item() - a) <= 1e-3 * max(1.0, a), n
+
+
+@pytest.mark.parametrize('K,B,gen', [(5, 4, 'multid'), (2, 3, 'rooms'), (5, 16, 'stacks')])
+def test_genesis_matches_oracle(K, B, gen):
+    m, cfg = build_engine_model('genesis', K, 64, seed=3)
+    m = m.cuda().train()
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    x = torch.from_numpy(synth.GENERATORS[gen](B, 64, 11)[0])
+    tape = U.make_tape(5)
+    out, P = U.run_oracle('genesis', sd0, x, tape, cfg)
+    recon, losses, stats, att, comp = U.run_engine(m, x, tape.rewound())
+    assert U.rel_l2(losses['err'], out['err']) < ERR_RTOL
+    assert U.rel_l2(recon, out['recon']) < 1e-3
+    for key in ('kl_l_k', 'kl_m_k'):
+        a = torch.stack(losses[key], 0).detach().cpu()
+        b = torch.stack(out[key], 0).detach()
+        assert (a - b).abs().max().item() < KL_ATOL + 1e-3 * b.abs().max().item(), key
+    for k in range(K):
+        assert (stats['log_m_k'][k].detach().cpu() - out['log_m_k'][k].detach()).abs().max().item() < 5e-3
+        assert U.rel_l2(stats['x_r_k'][k], out['x_r_k'][k]) < 1e-3
+        assert U.rel_l2(att['z_k'][k], out['att']['z_k'][k]) < 1e-3
+        assert U.rel_l2(comp['z_k'][k], out['comp']['z_k'][k]) < 1e-3
+    # masks sum to one (reference utils/misc.py:258-270)
+    s = torch.stack(stats['log_m_k'], 0).exp().sum(0)
+    assert (s - 1).abs().max().item() < 1e-3
+    worst = U.compare_grads(m, P, GRAD_TOL)
+    print('worst grad rel-L2', worst)
+    # BatchNorm running statistics follow the reference's update rule
+    sd1 = m.state_dict()
+    for name, v in out['bn_updates'].items():
+        if name.endswith('num_batches_tracked'):
+            assert int(sd1[name]) == int(v)
+        else:
+            assert U.rel_l2(sd1[name], v) < 1e-3, name
+
+
+def test_genesis_eval_sample_and_state_dict():
+    m, cfg = build_engine_model('genesis', 5, 64, seed=1)
+    m = m.cuda()
+    x = torch.from_numpy(synth.multid(2, 64, 3)[0]).cuda()
+    m.train()
+    m(x)                                  # one training step moves the BN running stats
+    m.eval()
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    tape = U.make_tape(9)
+    with torch.no_grad():
+        m.set_noise_tape(tape)
+        recon, losses, stats, att, comp = m(x)
+        m.set_noise_tape(None)
+    out, _ = U.run_oracle('genesis', sd0, x.cpu(), tape.rewound(), cfg, training=False)
+    assert U.rel_l2(losses['err'], out['err']) < ERR_RTOL
+    assert U.rel_l2(recon, out['recon']) < 1e-3
+    img, st = m.sample(3)
+    assert img.shape == (3, 3, 64, 64) and torch.isfinite(img).all()
+    assert len(st['log_m_k']) == 5
+    feats = m.get_features(x)
+    assert feats.shape == (2, 4 * 64 + 5 * 16)
+    # state_dict round trip with the reference's names
+    m2, _ = build_engine_model('genesis', 5, 64, seed=7)
+    m2.load_state_dict(m.state_dict())
+    for (k1, v1), (k2, v2) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1.cpu(), v2.cpu())
+
+
+def test_cpu_input_is_rejected():
+    m, cfg = build_engine_model('genesis', 5, 64)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 64, 64))

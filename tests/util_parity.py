@@ -1,0 +1,67 @@
+"""Shared helpers for the GPU parity tests: run the engine and the oracle on identical parameters,
+inputs and noise, and compare outputs and per-parameter gradients."""
+import torch
+
+from oracle import functional as O
+from oracle import models as M
+
+
+def engine_total_loss(losses, beta=1.0):
+    """train.py:227-259 with GECO's beta held fixed."""
+    loss = losses['err'].mean(0)
+    kl = 0.0
+    for key in ('kl_l_k', 'kl_m_k'):
+        if key in losses and len(losses[key]):
+            kl = kl + torch.stack(list(losses[key]), dim=1).mean(0).sum()
+    if 'kl_m' in losses and torch.is_tensor(losses['kl_m']) and losses['kl_m'].numel() > 1:
+        kl = kl + losses['kl_m'].mean(0)
+    return loss + beta * kl
+
+
+def run_engine(model, x, tape):
+    model.set_noise_tape(tape)
+    model.zero_grad(set_to_none=True)
+    recon, losses, stats, att, comp = model(x.cuda())
+    engine_total_loss(losses).backward()
+    torch.cuda.synchronize()
+    model.set_noise_tape(None)
+    return recon, losses, stats, att, comp
+
+
+def run_oracle(name, state_dict, x, tape, cfg, training=True):
+    P = {k: (v.detach().cpu().clone().requires_grad_(True) if v.is_floating_point() else v.detach().cpu().clone())
+         for k, v in state_dict.items()}
+    out = M.FORWARD[name](P, x.cpu(), tape, cfg, training=training)
+    M.total_loss(out).backward()
+    return out, P
+
+
+def rel_l2(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def compare_grads(model, P, tol, floor_frac=1e-4, skip=()):
+    """per-parameter relative L2 error of the gradients; parameters whose true gradient is (numerically)
+    zero -- e.g. conv biases feeding BatchNorm -- are compared on an absolute scale."""
+    gmax = max(p.grad.norm().item() for p in P.values() if torch.is_tensor(p) and p.grad is not None)
+    worst = (0.0, None)
+    for name, p in model.named_parameters():
+        ref = P[name].grad
+        if any(s in name for s in skip):
+            continue
+        if ref is None:
+            assert p.grad is None or p.grad.abs().max().item() == 0, name
+            continue
+        assert p.grad is not None, 'no gradient for ' + name
+        g = p.grad.detach().double().cpu()
+        denom = max(ref.double().norm().item(), floor_frac * gmax)
+        e = (g - ref.double()).norm().item() / denom
+        if e > worst[0]:
+            worst = (e, name)
+        assert e <= tol, 'grad mismatch %s: rel %.3e (|ref| %.3e)' % (name, e, ref.norm().item())
+    return worst
+
+
+def make_tape(seed):
+    return O.NoiseTape(seed=seed)
