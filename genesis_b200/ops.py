@@ -37,7 +37,11 @@ def _act_bwd(dout, out, act):
 
 def _colsum(x2d_rows, C, like):
     out = _new(like, C)
-    _call('g2_colsum_f32', x2d_rows, out, x2d_rows.numel() // C, C, 0)
+    rows = x2d_rows.numel() // C
+    if C > 1024 and C % 4 == 0:
+        _call('g2_sum_dim0_f32', x2d_rows, out, rows, C)
+    else:
+        _call('g2_colsum_f32', x2d_rows, out, rows, C, 0)
     return out
 
 
