@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""bench.py -- headline metric of BASELINE.json: images/sec, forward + backward (+ gradient all-reduce and
+Adam), GENESIS K=5 on 64x64 synthetic Multi-dSprites-shaped batches, B=64 per GPU, at N GPUs of one node.
+
+    python bench.py --gpus N --steps K --warmup W              # engine (one process per GPU; torchrun for N>1)
+    python bench.py --impl reference --steps K --warmup W      # reference arm: the oracle port of the
+                                                               # reference's PyTorch path on the host cores
+
+One JSON line on stdout (rank 0).  See DESIGN.md section 5 for what each key means.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = 'images/sec fwd+bwd 64x64 K=5'
+K_SLOTS, IMG, B_PER_GPU = 5, 64, 64
+FWD_GFLOP_PER_IMG = 6.059          # SURVEY.md section 8d (hooks on the reference model, 2*MACs)
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], tf_burst=d['bf16_tflops'], tf_sus=d['bf16_tflops_sustained'], src='measured')
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src='fallback')
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                f = [t.strip() for t in out.strip().split(',')]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unsampled']}
+        sm = sorted(int(float(s[0])) for s in self.samples)
+        reasons = []
+        for i, name in enumerate(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')):
+            if any(s[2 + i].lower().startswith('active') for s in self.samples):
+                reasons.append(name)
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': int(float(self.samples[0][1])), 'reasons': reasons,
+                'samples': len(sm)}
+
+
+def synthetic_batches(n_batches, batch, seed):
+    from oracle import synth    # test-infrastructure generator of dataset-shaped images (inputs only)
+    return [torch.from_numpy(synth.multid(batch, IMG, seed + i)[0]) for i in range(n_batches)]
+
+
+def build_cfg():
+    from genesis_b200.model_configs import genesis_config as plugin
+    from forge import flags
+    cfg = dict(flags.defaults())
+    cfg.update(debug=False, multi_gpu=False, img_size=IMG, K_steps=K_SLOTS)
+    from attrdict import AttrDict
+    return plugin, AttrDict(cfg)
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def cpu_port_step_fn(batch):
+    """The oracle port of the reference's PyTorch path (oracle/models.py) on the host: fwd + loss + bwd."""
+    from oracle import models as M, functional as O
+    plugin, cfg = build_cfg()
+    torch.manual_seed(0)
+    holder = plugin.load(cfg)
+    P = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in holder.state_dict().items()}
+    ocfg = M.make_cfg('genesis', K_steps=K_SLOTS, img_size=IMG)
+    xs = synthetic_batches(2, batch, 100)
+
+    def step(i):
+        for p in P.values():
+            if p.is_floating_point() and p.grad is not None:
+                p.grad = None
+        out = M.genesis_forward(P, xs[i % len(xs)], O.NoiseTape(seed=i), ocfg, training=True)
+        M.total_loss(out).backward()
+        return float(out['err'].mean())
+    return step
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_b = 16
+    step = cpu_port_step_fn(sample_b)
+    for i in range(max(1, min(args.warmup, 2))):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i)
+    dt = time.perf_counter() - t0
+    v = sample_b * args.steps / dt
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'GENESIS K=5 64x64 fwd+bwd, CPU sample batch=%d per step (config B=64)' % sample_b},
+        'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                         'sample': '%d steps x batch %d, torch %s CPU fp32, %d threads' % (args.steps, sample_b, torch.__version__, cores)},
+        'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def run_engine(args):
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the engine has no CPU path')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    from genesis_b200 import build, _lib, profiling, trainer
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+    plugin, cfg = build_cfg()
+    torch.manual_seed(0)
+    model = plugin.load(cfg).to(dev).train()
+    ts = trainer.TrainStep(model, lr=1e-4, img_size=IMG, world_size=world)
+    lib = _lib.lib()
+
+    n_in = 4
+    host = [t.pin_memory() for t in synthetic_batches(n_in, B_PER_GPU, 1000 * rank + 1)]
+    devx = [t.to(dev) for t in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- leg 1: device-resident inputs (value)
+    for i in range(max(3, args.warmup)):
+        ts.step_device(devx[i % n_in])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        elbo = ts.step_device(devx[i % n_in])
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.launches - l0
+    # ---- leg 2: end to end through the public API, pinned host inputs, loss read back every step
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    last = 0.0
+    for i in range(args.steps):
+        last = float(ts.step(host[i % n_in]).item())         # H2D copy in, D2H of the ELBO out, every step
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    sampler.stop_flag = True
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+
+    if rank == 0:
+        pk = peaks()
+        # ---- dominant kernel: per-call device time inside profiled steps, CUDA events on the launch stream
+        with profiling.Profiler() as prof:
+            for i in range(2):
+                ts.step_device(devx[i % n_in])
+        rows = prof.table()
+        total_ms = sum(r['ms'] for r in rows)
+        top = rows[0]
+        tensor_like = top['flops'] > 0 and top['key'].startswith(('g2_conv', 'g2_gemm'))
+        if tensor_like:
+            ach = top['flops'] / (top['ms'] * 1e-3) / 1e12
+            roof = {'bound': 'tensor', 'kernel': top['key'], 'achieved': ach, 'peak': pk['tf_sus'], 'unit': 'TFLOP/s',
+                    'frac': ach / pk['tf_sus'], 'traffic': None, 'peak_source': pk['src'] + ' bf16 sustained',
+                    'share_of_step': top['ms'] / total_ms, 'launch_ms': top['ms'] / top['calls']}
+        else:
+            ach = top['bytes'] / (top['ms'] * 1e-3) / 1e9
+            roof = {'bound': 'hbm', 'kernel': top['key'], 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s',
+                    'frac': ach / pk['hbm'], 'traffic': None, 'peak_source': pk['src'],
+                    'share_of_step': top['ms'] / total_ms, 'launch_ms': top['ms'] / top['calls']}
+        breakdown = [{'kernel': r['key'], 'ms_per_step': r['ms'] / 2, 'calls_per_step': r['calls'] // 2,
+                      'tflops': (r['flops'] / (r['ms'] * 1e-3) / 1e12) if r['flops'] else None,
+                      'gbs': (r['bytes'] / (r['ms'] * 1e-3) / 1e9) if r['bytes'] else None} for r in rows[:8]]
+        step_tf = 3 * FWD_GFLOP_PER_IMG * B_PER_GPU * world * args.steps / (ms * 1e-3) / 1e3
+        # ---- CPU baseline: bounded sample of the same workload with the oracle port on the host cores
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            sb = 16
+            step = cpu_port_step_fn(sb)
+            step(0)
+            t0 = time.perf_counter()
+            n_cpu = 3
+            for i in range(n_cpu):
+                step(i + 1)
+            dt = time.perf_counter() - t0
+            cpu = {'value': sb * n_cpu / dt, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                   'sample': '1 warm-up + %d steps of batch %d (config batch is 64), oracle port, torch CPU fp32' % (n_cpu, sb)}
+        imgs = B_PER_GPU * world * args.steps
+        line = {
+            'metric': METRIC, 'value': imgs / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(3, args.warmup), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'GENESIS K=5 64x64 Multi-dSprites-shaped, batch %d per GPU, fwd+bwd+allreduce+Adam+GECO' % B_PER_GPU,
+                       'global_batch': B_PER_GPU * world, 'parallelism': 'dp%d' % world,
+                       'l2': 'per-step working set (activations > 4 GB) exceeds the 126 MB L2; inputs rotate over %d batches' % n_in,
+                       'step_tflops_algorithmic': step_tf, 'last_elbo': last},
+            'e2e': {'value': imgs / (ms_e2e * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': B_PER_GPU * 3 * IMG * IMG * 4,
+                    'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': launches,
+            'clocks': sampler.summary(),
+            'roofline': roof,
+            'kernel_breakdown': breakdown,
+            'cpu_baseline': cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
+    ap.add_argument('--no-cpu-baseline', dest='no_cpu_baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == '__main__':
+    main()

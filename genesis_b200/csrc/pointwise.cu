@@ -210,3 +210,42 @@ int g2_sum_dim0_f32(const float* x, float* out, int N, long J, cudaStream_t stre
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------ optimiser
+// Fused Adam over a flat fp32 arena (reference train.py:175,263 uses torch.optim.Adam: lr, betas (0.9, 0.999),
+// eps 1e-8, no weight decay).  `step` is a device counter (float) so the kernel is CUDA-graph replayable;
+// grads are multiplied by grad_scale (1/world_size after an NCCL sum) and zeroed for the next step.
+namespace {
+__global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long n4, float lr, float b1, float b2, float eps, const float* __restrict__ step, float gscale,
+                            int zero_grad) {
+    const float t = __ldg(step);
+    const float c1 = 1.f - powf(b1, t), c2 = 1.f - powf(b2, t);
+    const float step_size = lr / c1, inv_c2 = rsqrtf(c2);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        float4 pp = *reinterpret_cast<float4*>(p + i * 4), gg = *reinterpret_cast<float4*>(g + i * 4);
+        float4 mm = *reinterpret_cast<float4*>(m + i * 4), vv = *reinterpret_cast<float4*>(v + i * 4);
+        float* pa = &pp.x; float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float gr = ga[j] * gscale;
+            ma[j] = b1 * ma[j] + (1.f - b1) * gr;
+            va[j] = b2 * va[j] + (1.f - b2) * gr * gr;
+            pa[j] -= step_size * ma[j] / (sqrtf(va[j]) * inv_c2 + eps);
+        }
+        *reinterpret_cast<float4*>(p + i * 4) = pp;
+        *reinterpret_cast<float4*>(m + i * 4) = mm;
+        *reinterpret_cast<float4*>(v + i * 4) = vv;
+        if (zero_grad) *reinterpret_cast<float4*>(g + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+}  // namespace
+
+extern "C" int g2_adam_f32(float* p, float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps,
+                           const float* step, float grad_scale, int zero_grad, cudaStream_t stream) {
+    G2_CHECK_ARG(p && g && m && v && step && n > 0 && (n % 4) == 0);
+    long b = (n / 4 + 255) / 256;
+    if (b > 148L * 16) b = 148L * 16;
+    adam_kernel<<<(int)b, 256, 0, stream>>>(p, g, m, v, n / 4, lr, b1, b2, eps, step, grad_scale, zero_grad);
+    G2_LAUNCH_RET();
+}

@@ -1,0 +1,112 @@
+"""Data-parallel training step of the engine: forward + loss assembly + backward + one gradient all-reduce +
+fused Adam, with GECO kept on the device.
+
+Mirrors the caller's hot loop in the reference (train.py:215-263 and utils/geco.py:35-51) without its host
+syncs.  One process per GPU; parameters and gradients live in flat fp32 arenas so the data-parallel exchange
+is ONE all-reduce per step over NCCL (NVLink / NVSwitch), with the batch-mean `err` and `kl` appended to the
+arena so every rank updates GECO's beta identically (replaces nn.DataParallel, train.py:153-155)."""
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+class GecoState(object):
+    """utils/geco.py:19-51 as device tensors (no .item()): loss = err + beta*kl; err_ema; beta update."""
+
+    def __init__(self, goal, step_size, device, alpha=0.99, beta_init=1.0, beta_min=1e-10, beta_max=1e10,
+                 speedup=10.0):
+        self.goal, self.step_size, self.alpha, self.speedup = float(goal), float(step_size), alpha, speedup
+        self.beta = torch.tensor(beta_init, device=device)
+        self.err_ema = torch.zeros((), device=device)
+        self.started = torch.zeros((), device=device)
+        self.beta_min, self.beta_max = beta_min, beta_max
+
+    @torch.no_grad()
+    def update(self, err):
+        ema = torch.where(self.started > 0, (1.0 - self.alpha) * err + self.alpha * self.err_ema, err)
+        self.err_ema.copy_(ema)
+        self.started.fill_(1.0)
+        constraint = self.goal - self.err_ema
+        rate = torch.where(constraint > 0, self.speedup * self.step_size, self.step_size) if self.speedup else self.step_size
+        self.beta.copy_((torch.exp(rate * constraint) * self.beta).clamp(self.beta_min, self.beta_max))
+
+
+class TrainStep(object):
+    """step(x) = one optimisation step on the local shard `x` (float32 [B,3,H,W], device or pinned host)."""
+
+    def __init__(self, model, lr=1e-4, img_size=64, g_goal=0.5655, g_lr=1e-5, g_alpha=0.99, g_init=1.0,
+                 g_min=1e-10, g_speedup=10.0, geco=True, world_size=1):
+        self.model = model
+        self.world = world_size
+        self.lr = lr
+        params = [p for p in model.parameters() if p.requires_grad]
+        dev = params[0].device
+        n = sum(p.numel() for p in params)
+        self.n_params = n
+        self.n_pad = (n + 3) // 4 * 4
+        # flat arenas: [params | pad], [grads | pad | err, kl, 0, 0]
+        self.flat_p = torch.zeros(self.n_pad, device=dev)
+        self.flat_g = torch.zeros(self.n_pad + 4, device=dev)
+        self.flat_m = torch.zeros(self.n_pad, device=dev)
+        self.flat_v = torch.zeros(self.n_pad, device=dev)
+        off = 0
+        for p in params:
+            k = p.numel()
+            self.flat_p[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[off:off + k].view_as(p)
+            p.grad = self.flat_g[off:off + k].view_as(p)
+            off += k
+        self.params = params
+        self.step_count = torch.zeros((), device=dev)
+        self.geco = None
+        if geco:
+            # reference train.py:159-169
+            self.geco = GecoState(g_goal * 3 * img_size ** 2, g_lr * (64 ** 2 / img_size ** 2), dev,
+                                  alpha=g_alpha, beta_init=g_init, beta_min=g_min, speedup=g_speedup)
+        self.x_dev = None
+
+    def loss_terms(self, losses):
+        """train.py:227-239."""
+        err = losses['err'].mean(0)
+        kl = err.new_zeros(())
+        for key in ('kl_l_k', 'kl_m_k'):
+            if key in losses and len(losses[key]):
+                kl = kl + torch.stack(list(losses[key]), dim=1).mean(0).sum()
+        for key in ('kl_l', 'kl_m'):
+            if key in losses and torch.is_tensor(losses[key]) and losses[key].numel() > 1:
+                kl = kl + losses[key].mean(0)
+        return err, kl
+
+    def step_device(self, x):
+        """x already resident on the device.  Returns the (detached) ELBO scalar tensor."""
+        recon, losses, stats, att, comp = self.model(x)
+        err, kl = self.loss_terms(losses)
+        beta = self.geco.beta if self.geco is not None else 1.0
+        loss = err + beta * kl
+        loss.backward()
+        tail = self.flat_g[self.n_pad:]
+        with torch.no_grad():
+            tail[0].copy_(err.detach())
+            tail[1].copy_(kl.detach())
+            if self.world > 1:
+                dist.all_reduce(self.flat_g)                      # ONE exchange per step
+            gerr, gkl = tail[0] / self.world, tail[1] / self.world
+            if self.geco is not None:
+                self.geco.update(gerr)
+            self.step_count += 1
+            elbo = (gerr + gkl).clone()
+            _lib.call('g2_adam_f32', self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.n_pad, self.lr,
+                      0.9, 0.999, 1e-8, self.step_count, 1.0 / self.world, 1)
+            tail.zero_()
+        return elbo
+
+    def step(self, x):
+        """Public entry point: x on the host (ideally pinned) or the device; returns the ELBO tensor."""
+        if not x.is_cuda:
+            dev = self.flat_p.device
+            if self.x_dev is None or self.x_dev.shape != x.shape:
+                self.x_dev = torch.empty(x.shape, device=dev, dtype=torch.float32)
+            self.x_dev.copy_(x, non_blocking=True)
+            x = self.x_dev
+        return self.step_device(x)

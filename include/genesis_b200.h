@@ -126,6 +126,12 @@ int g2_mixture_bwd_f32(const float* x, const float* xr, const float* lm, const f
                        const float* gerr, float* dxr, float* dlm, int K, int B, int P, int softmax,
                        g2_stream_t stream);
 
+/* ---- optimiser (pointwise.cu) --------------------------------------------------------------------
+ * Fused Adam over a flat fp32 parameter / gradient arena; replaces torch.optim.Adam.step() in the
+ * caller's loop (train.py:175,263).  `step` is a device-resident float counter (1-based). n % 4 == 0. */
+int g2_adam_f32(float* p, float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps,
+                const float* step, float grad_scale, int zero_grad, g2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
