@@ -52,6 +52,10 @@ class _Lib(object):
             fn.argtypes = [t for t, _, _ in sig]
             self._fn[name] = fn
 
+    def query(self, name, *args):
+        """Plain host-side query entry point (no stream, no launch); returns the int result."""
+        return self._fn[name](*args)
+
     def call(self, name, *args):
         sig = self.protos[name]
         if len(args) != len(sig) - 1:

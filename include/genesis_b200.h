@@ -126,6 +126,19 @@ int g2_mixture_bwd_f32(const float* x, const float* xr, const float* lm, const f
                        const float* gerr, float* dxr, float* dlm, int K, int B, int P, int softmax,
                        g2_stream_t stream);
 
+/* ---- TF32 tensor-core implicit GEMM: tcgen05.mma + TMEM + TMA (igemm_tc.cu) -------------------------
+ * Same call sites as g2_conv_igemm_f32 / g2_gemm_f32, for the shapes that fit the 128 x {32,64,128} UMMA
+ * tiles (Ci % 32 == 0, Co in {32,64,128} or a multiple of 64, power-of-two widths or VALID convs).
+ * Weights packed [R*S][Co][Ci].  g2_conv_tf32_supported returns 1/0 (it is a query, not an error code). */
+int g2_conv_tf32_supported(int N, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int R, int S, int stride,
+                           int pad, int mode);
+int g2_conv_igemm_tf32(const float* in, const float* w, const float* bias, float* out, int N, int Hi, int Wi,
+                       int Ci, int Ho, int Wo, int Co, int R, int S, int stride, int pad, int mode, int act,
+                       g2_stream_t stream);
+/* C[M,N] = A[M,K] W[N,K]^T + bias[N] */
+int g2_gemm_tf32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K,
+                 g2_stream_t stream);
+
 /* ---- optimiser (pointwise.cu) --------------------------------------------------------------------
  * Fused Adam over a flat fp32 parameter / gradient arena; replaces torch.optim.Adam.step() in the
  * caller's loop (train.py:175,263).  `step` is a device-resident float counter (1-based). n % 4 == 0. */

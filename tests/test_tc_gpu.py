@@ -1,0 +1,102 @@
+"""GPU: the tcgen05 / TMA TF32 implicit-GEMM kernel, called through the C ABI, against float64 torch
+convolutions.  With operands pre-rounded to TF32 the tensor-core products are exact, so the comparison is
+tight (fp32 accumulation order only); with raw fp32 operands the error is the TF32 rounding (~1e-3)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def tf32_round(t):
+    """Round-to-nearest-even to 10 mantissa bits (what the tensor map's TFLOAT32 load produces)."""
+    i = t.float().contiguous().view(torch.int32)
+    r = (i + 0xFFF + ((i >> 13) & 1)) & ~0x1FFF
+    return r.view(torch.float32)
+
+
+def run_conv(mode, N, H, W, Ci, Co, R, s, p, preround, seed=0):
+    from genesis_b200 import _lib
+    torch.manual_seed(seed)
+    x = torch.randn(N, Ci, H, W)
+    w = torch.randn((Co, Ci, R, R) if mode == 0 else (Ci, Co, R, R)) * 0.1
+    b = torch.randn(Co)
+    if preround:
+        x, w = tf32_round(x), tf32_round(w)
+    if mode == 0:
+        ref = F.conv2d(x.double(), w.double(), b.double(), stride=s, padding=p)
+        wp = w.permute(2, 3, 0, 1).reshape(R * R, Co, Ci)
+    else:
+        ref = F.conv_transpose2d(x.double(), w.double(), b.double(), stride=s, padding=p, output_padding=s - 1)
+        wp = w.permute(2, 3, 1, 0).reshape(R * R, Co, Ci)
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    lib = _lib.lib()
+    assert lib.query('g2_conv_tf32_supported', N, H, W, Ci, Ho, Wo, Co, R, R, s, p, mode) == 1
+    xg = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    out = torch.full((N, Ho, Wo, Co), float('nan'), device=DEV)
+    _lib.call('g2_conv_igemm_tf32', xg, wp.contiguous().to(DEV), b.to(DEV), out, N, H, W, Ci, Ho, Wo, Co, R, R, s, p, mode, 0)
+    torch.cuda.synchronize()
+    got = out.permute(0, 3, 1, 2).double().cpu()
+    assert torch.isfinite(got).all(), 'unwritten / non-finite outputs'
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    return err
+
+
+CASES = [  # mode, N, H, W, Ci, Co, R, stride, pad
+    (0, 2, 16, 16, 32, 64, 5, 1, 2),
+    (0, 2, 64, 64, 32, 64, 5, 1, 2),
+    (0, 2, 32, 32, 64, 128, 5, 1, 2),
+    (0, 3, 16, 16, 64, 128, 5, 1, 2),
+    (0, 2, 64, 64, 64, 64, 3, 1, 1),       # UNet block
+    (0, 2, 128, 128, 32, 32, 3, 1, 1),     # MONet-128 UNet block (TW = 128)
+    (0, 2, 70, 70, 32, 32, 3, 1, 0),       # broadcast decoder, flat tiles
+    (0, 2, 68, 68, 32, 32, 3, 1, 0),
+    (0, 2, 66, 66, 32, 32, 3, 1, 0),       # -> 64: 2-D tiles
+    (0, 1, 136, 136, 32, 32, 3, 1, 0),     # MONet-128 broadcast decoder
+    (0, 2, 64, 64, 32, 64, 5, 2, 2),       # stride-2 conv (parity planes)
+    (0, 2, 32, 32, 64, 128, 5, 2, 2),
+    (0, 2, 32, 32, 32, 64, 3, 2, 1),
+    (1, 2, 16, 16, 64, 128, 5, 1, 2),      # conv-transpose s1
+    (1, 2, 32, 32, 32, 64, 5, 1, 2),
+    (1, 2, 16, 16, 64, 64, 5, 2, 2),       # conv-transpose s2 (sub-pixel classes)
+    (1, 2, 32, 32, 32, 64, 5, 2, 2),
+    (1, 2, 32, 32, 64, 64, 5, 2, 2),
+    (1, 2, 32, 32, 32, 32, 3, 2, 1),
+]
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_conv_tf32_exact_on_prerounded_operands(case):
+    err = run_conv(*case, preround=True)
+    assert err < 2e-5, err
+
+
+@pytest.mark.parametrize('case', CASES[:3] + CASES[10:11] + CASES[15:16])
+def test_conv_tf32_precision_on_fp32_operands(case):
+    err = run_conv(*case, preround=False)
+    assert err < 3e-3, err
+
+
+def test_unsupported_shapes_are_reported():
+    from genesis_b200 import _lib
+    lib = _lib.lib()
+    assert lib.query('g2_conv_tf32_supported', 2, 64, 64, 3, 64, 64, 64, 5, 5, 1, 2, 0) == 0      # Ci = 3
+    assert lib.query('g2_conv_tf32_supported', 2, 8, 8, 64, 16, 16, 64, 5, 5, 2, 2, 1) == 0       # 8x8 class grid
+    assert lib.query('g2_conv_tf32_supported', 2, 4, 4, 64, 4, 4, 64, 3, 3, 1, 1, 0) == 0
+
+
+@pytest.mark.parametrize('M,N,K', [(64, 512, 16384), (320, 32768, 64), (448, 256, 4096), (100, 128, 96), (320, 256, 1024)])
+def test_gemm_tf32(M, N, K):
+    from genesis_b200 import _lib
+    torch.manual_seed(1)
+    a = tf32_round(torch.randn(M, K))
+    w = tf32_round(torch.randn(N, K) / K ** 0.5)
+    b = torch.randn(N)
+    ref = a.double() @ w.double().t() + b.double()
+    out = torch.full((M, N), float('nan'), device=DEV)
+    _lib.call('g2_gemm_tf32', a.to(DEV), w.to(DEV), b.to(DEV), out, M, N, K)
+    torch.cuda.synchronize()
+    got = out.double().cpu()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() / ref.abs().max().item() < 2e-5
