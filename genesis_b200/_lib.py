@@ -16,14 +16,18 @@ _CTYPES = {'int': ctypes.c_int, 'long': ctypes.c_long, 'float': ctypes.c_float, 
            'int64_t': ctypes.c_int64, 'unsigned': ctypes.c_uint}
 
 
+RESTYPES = {}
+
+
 def parse_header(path=HEADER):
     """-> {name: [(ctype, is_pointer, argname), ...]} for every `int g2_*(...)` prototype."""
     text = open(path).read()
     text = re.sub(r'/\*.*?\*/', ' ', text, flags=re.S)
     text = re.sub(r'//[^\n]*', ' ', text)
     protos = {}
-    for m in re.finditer(r'\bint\s+(g2_\w+)\s*\(([^)]*)\)\s*;', text):
-        name, args = m.group(1), m.group(2).strip()
+    for m in re.finditer(r'\b(int|long)\s+(g2_\w+)\s*\(([^)]*)\)\s*;', text):
+        name, args = m.group(2), m.group(3).strip()
+        RESTYPES[name] = ctypes.c_long if m.group(1) == 'long' else ctypes.c_int
         sig = []
         if args and args != 'void':
             for a in args.split(','):
@@ -48,7 +52,7 @@ class _Lib(object):
         self._fn = {}
         for name, sig in self.protos.items():
             fn = getattr(self.cdll, name)          # raises AttributeError if a declared symbol is missing
-            fn.restype = ctypes.c_int
+            fn.restype = RESTYPES.get(name, ctypes.c_int)
             fn.argtypes = [t for t, _, _ in sig]
             self._fn[name] = fn
 

@@ -1,0 +1,366 @@
+// genesis_b200 -- TF32 tensor-core weight gradient for sm_100a (tcgen05.mma, MN-major operands, TMA, TMEM).
+//
+//   dW[tap][a][b] = sum_{n,oh,ow} G_plane(tap)[n, oh+dh(tap), ow+dw(tap), a] * T[n, oh, ow, b]
+//
+// The reduction (UMMA K) runs over pixels, so both operands are consumed "MN-major": a TMA box of
+// [pixels][32 channels] (128-byte rows, SWIZZLE_128B_ATOM_32B) IS the canonical MN-major tile -- no transposes.
+//   A (M = 128) = four stacked 32-channel blocks, each one (tap, channel-block) of the shifted G window;
+//   B (N = Ct)  = the Ct/32 channel blocks of the un-shifted T tile;  K = 8 pixels per instruction.
+// One CTA owns a range of 64-pixel chunks and up to 512/Ct accumulators (M-groups) in TMEM, streams the G
+// blocks through a 4-stage mbarrier ring while the T tile of the chunk stays resident (double-buffered),
+// and finally writes its partial dW to a workspace; a second kernel reduces the partials over CTAs
+// (deterministic, no atomics) and writes dW in the requested layout.
+#include "common.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace wg {
+
+constexpr int CH = 64;                 // pixels per chunk
+constexpr int TILE_BYTES = CH * 128;   // one [64 pixels][32 channels] block
+constexpr int STAGES = 4;
+constexpr int MAX_BLK = 112;
+
+struct Maps { CUtensorMap g[4]; CUtensorMap t; };
+
+struct P {
+    float* ws;                    // [splits][ntaps][Cg][Ct]
+    int N, Ht, Wt, TH, TW, tiles_h, tiles_w, chunks_total, chunks_per_cta;
+    int Cg, Ct, ntaps, nblk, groups_per_cta;
+    short tap_plane[32], tap_dh[32], tap_dw[32];
+    short blk_tap[MAX_BLK], blk_cb[MAX_BLK];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) break;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+// MN-major TF32 operands must use the SWIZZLE_128B_BASE32B layout (layout type 1; measured with
+// g2_debug_umma_probe, tests/test_umma_layouts_gpu.py): 128-byte rows (32 channels of one pixel) whose 32-byte chunks
+// are XORed with (row & 3) -- what TMA's SWIZZLE_128B_ATOM_32B writes; 32-element atoms along M/N are `lbo` bytes
+// apart, 4-row K atoms 512 B apart.
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// BN = Ct (32, 64 or 128)
+template <int BN>
+__global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P p) {
+    constexpr int TB = BN / 32;                 // T channel blocks
+    constexpr int T_BYTES = TB * TILE_BYTES;
+    constexpr int G_STAGE = 4 * TILE_BYTES;     // one M-group = 4 blocks
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* sm = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    uint8_t* sG = sm;
+    uint8_t* sT = sm + STAGES * G_STAGE;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sT + 2 * T_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* accf = tempty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accf + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = blockIdx.x;
+    const int g_begin = blockIdx.y * p.groups_per_cta;                // first M-group of this CTA
+    const int ngroups_all = (p.nblk + 3) >> 2;
+    const int ng = min(p.groups_per_cta, ngroups_all - g_begin);
+    const int c_begin = split * p.chunks_per_cta;
+    const int nchunks = max(0, min(p.chunks_per_cta, p.chunks_total - c_begin));
+
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+            for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 1); }
+            mbar_init(accf, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;                                   // global stage counter
+            for (int c = 0; c < nchunks; ++c) {
+                const int chunk = c_begin + c;
+                const int tw_i = chunk % p.tiles_w;
+                const int th_i = (chunk / p.tiles_w) % p.tiles_h;
+                const int n = chunk / (p.tiles_w * p.tiles_h);
+                const int h0 = th_i * p.TH, w0 = tw_i * p.TW;
+                const int tb = c & 1;
+                mbar_wait(&tempty[tb], ((uint32_t)(c >> 1) & 1u) ^ 1u);
+                mbar_expect_tx(&tfull[tb], T_BYTES);
+#pragma unroll
+                for (int j = 0; j < TB; ++j)
+                    tma_load_4d(sT + tb * T_BYTES + j * TILE_BYTES, &maps.t, &tfull[tb], j * 32, w0, h0, n);
+                for (int g = 0; g < ng; ++g, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty[s], ((uint32_t)(it / STAGES) & 1u) ^ 1u);
+                    const int b0 = (g_begin + g) * 4;
+                    const int nb = min(4, p.nblk - b0);
+                    mbar_expect_tx(&full[s], nb * TILE_BYTES);
+                    for (int j = 0; j < nb; ++j) {
+                        const int tap = p.blk_tap[b0 + j];
+                        tma_load_4d(sG + s * G_STAGE + j * TILE_BYTES, &maps.g[p.tap_plane[tap]], &full[s],
+                                    p.blk_cb[b0 + j] * 32, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // a_major = b_major = MN (bits 15, 16); M = 128; N = BN; tf32 operands, fp32 accumulate
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                       ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            int it = 0;
+            for (int c = 0; c < nchunks; ++c) {
+                const int tb = c & 1;
+                mbar_wait(&tfull[tb], (uint32_t)(c >> 1) & 1u);
+                for (int g = 0; g < ng; ++g, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = smem_u32(sG + s * G_STAGE);
+                    const uint32_t b_addr = smem_u32(sT + tb * T_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < CH / 8; ++kk)       // 8 pixels (= 8 rows = 1024 B) per instruction
+                        umma_tf32(tmem_base + (uint32_t)(g * BN), make_desc_mn_sw128(a_addr + kk * 1024, TILE_BYTES),
+                                  make_desc_mn_sw128(b_addr + kk * 1024, TILE_BYTES), idesc, (c > 0 || kk > 0) ? 1u : 0u);
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&tempty[tb]);
+            }
+            umma_commit(accf);
+        }
+    } else {
+        const int q = warp & 3;                  // TMEM lane quarter == block index within the M-group
+        mbar_wait(accf, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float* wsp = p.ws + (long)split * p.ntaps * p.Cg * p.Ct;
+        for (int g = 0; g < ng; ++g) {
+            const int blk = (g_begin + g) * 4 + q;
+            const bool valid = blk < p.nblk;
+            const int tap = valid ? p.blk_tap[blk] : 0;
+            const int a = valid ? p.blk_cb[blk] * 32 + lane : 0;
+            float* dst = wsp + ((long)tap * p.Cg + a) * p.Ct;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * BN + c0), v);
+                if (valid) {
+                    if (nchunks == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0u;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<uint4*>(dst + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
+// dw = sum over splits of ws;  layout [taps][Cg][Ct] (outT = 0) or [taps][Ct][Cg] (outT = 1)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int taps, int Cg, int Ct, int outT) {
+    const long total = (long)taps * Cg * Ct;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < splits; ++k) s += __ldg(ws + (long)k * total + i);
+        if (outT) {
+            const int b = (int)(i % Ct); const long t = i / Ct; const int a = (int)(t % Cg); const long tap = t / Cg;
+            dw[(tap * Ct + b) * Cg + a] = s;
+        } else dw[i] = s;
+    }
+}
+
+PFN_cuTensorMapEncodeTiled get_encode() {
+    static PFN_cuTensorMapEncodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(f);
+    });
+    return fn;
+}
+
+bool encode4(CUtensorMap* m, const void* base, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+    PFN_cuTensorMapEncodeTiled enc = get_encode();
+    if (!enc) return false;
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, const_cast<void*>(base), dims, strides_bytes, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline int floordiv2(int t) { return (t - (t & 1)) / 2; }
+
+struct Plan { int TH, TW, tiles_h, tiles_w, chunks, ngroups, gpc, grid_y, splits, cpc; };
+
+bool make_plan(int N, int Hg, int Wg, int Cg, int Ht, int Wt, int Ct, int R, int S, int stride, Plan* pl) {
+    if (Cg % 32 != 0 || !(Ct == 32 || Ct == 64 || Ct == 128)) return false;
+    if (R * S > 32 || stride < 1 || stride > 2) return false;
+    if (stride == 2 && ((Hg | Wg) & 1)) return false;
+    const int nblk = R * S * (Cg / 32);
+    if (nblk > MAX_BLK) return false;
+    if ((long)Ht * Wt < 64) return false;
+    if ((Wt & (Wt - 1)) == 0 && Wt >= 8) { pl->TW = Wt < CH ? Wt : CH; pl->TH = CH / pl->TW; }
+    else { pl->TW = 8; pl->TH = 8; }
+    pl->tiles_w = g2_cdiv(Wt, pl->TW); pl->tiles_h = g2_cdiv(Ht, pl->TH);
+    pl->chunks = N * pl->tiles_h * pl->tiles_w;
+    pl->ngroups = (nblk + 3) / 4;
+    const int max_gpc = 512 / Ct;
+    pl->grid_y = g2_cdiv(pl->ngroups, max_gpc);
+    pl->gpc = g2_cdiv(pl->ngroups, pl->grid_y);
+    int splits = 148 / pl->grid_y;
+    if (splits < 1) splits = 1;
+    if (splits > pl->chunks) splits = pl->chunks;
+    pl->cpc = g2_cdiv(pl->chunks, splits);
+    pl->splits = g2_cdiv(pl->chunks, pl->cpc);
+    return true;
+}
+
+}  // namespace wg
+
+extern "C" {
+
+// Bytes of workspace g2_conv_wgrad_tf32 needs for this problem, or 0 if the shape is not supported.
+long g2_conv_wgrad_tf32_workspace(int N, int Hg, int Wg, int Cg, int Ht, int Wt, int Ct, int R, int S, int stride) {
+    wg::Plan pl;
+    if (!wg::make_plan(N, Hg, Wg, Cg, Ht, Wt, Ct, R, S, stride, &pl)) return 0;
+    return (long)pl.splits * R * S * Cg * Ct * (long)sizeof(float);
+}
+
+// Same contract as g2_conv_wgrad_f32 (TF32 operands, fp32 accumulation); `ws` is caller-owned scratch of
+// g2_conv_wgrad_tf32_workspace(...) bytes.
+int g2_conv_wgrad_tf32(const float* g, const float* t, float* dw, float* ws, int N, int Hg, int Wg, int Cg, int Ht, int Wt,
+                       int Ct, int R, int S, int stride, int pad, int outT, cudaStream_t stream) {
+    using namespace wg;
+    G2_CHECK_ARG(g && t && dw && ws && N > 0);
+    Plan pl;
+    if (!make_plan(N, Hg, Wg, Cg, Ht, Wt, Ct, R, S, stride, &pl)) return G2_ERR_UNSUPPORTED;
+    G2_CHECK_ARG((reinterpret_cast<uintptr_t>(g) & 15) == 0 && (reinterpret_cast<uintptr_t>(t) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(ws) & 15) == 0);
+    Maps maps;
+    memset(&maps, 0, sizeof(maps));
+    P p;
+    memset(&p, 0, sizeof(p));
+    p.ws = ws; p.N = N; p.Ht = Ht; p.Wt = Wt; p.TH = pl.TH; p.TW = pl.TW; p.tiles_h = pl.tiles_h; p.tiles_w = pl.tiles_w;
+    p.chunks_total = pl.chunks; p.chunks_per_cta = pl.cpc; p.Cg = Cg; p.Ct = Ct; p.ntaps = R * S;
+    p.groups_per_cta = pl.gpc;
+    for (int r = 0; r < R; ++r)
+        for (int s = 0; s < S; ++s) {
+            const int tap = r * S + s, tr = r - pad, ts = s - pad;
+            if (stride == 1) { p.tap_plane[tap] = 0; p.tap_dh[tap] = (short)tr; p.tap_dw[tap] = (short)ts; }
+            else {
+                p.tap_plane[tap] = (short)(((tr & 1) << 1) | (ts & 1));
+                p.tap_dh[tap] = (short)floordiv2(tr); p.tap_dw[tap] = (short)floordiv2(ts);
+            }
+        }
+    int nb = 0;
+    for (int tap = 0; tap < R * S; ++tap)
+        for (int cb = 0; cb < Cg / 32; ++cb) { p.blk_tap[nb] = (short)tap; p.blk_cb[nb] = (short)cb; ++nb; }
+    p.nblk = nb;
+    const cuuint32_t box[4] = {32, (cuuint32_t)pl.TW, (cuuint32_t)pl.TH, 1};
+    {
+        const cuuint64_t dims[4] = {(cuuint64_t)Ct, (cuuint64_t)Wt, (cuuint64_t)Ht, (cuuint64_t)N};
+        const cuuint64_t str[3] = {(cuuint64_t)Ct * 4, (cuuint64_t)Wt * Ct * 4, (cuuint64_t)Ht * Wt * Ct * 4};
+        if (!encode4(&maps.t, t, dims, str, box)) return G2_ERR_UNSUPPORTED;
+    }
+    if (stride == 1) {
+        const cuuint64_t dims[4] = {(cuuint64_t)Cg, (cuuint64_t)Wg, (cuuint64_t)Hg, (cuuint64_t)N};
+        const cuuint64_t str[3] = {(cuuint64_t)Cg * 4, (cuuint64_t)Wg * Cg * 4, (cuuint64_t)Hg * Wg * Cg * 4};
+        if (!encode4(&maps.g[0], g, dims, str, box)) return G2_ERR_UNSUPPORTED;
+    } else {
+        for (int plane = 0; plane < 4; ++plane) {
+            const int pr = plane >> 1, ps = plane & 1;
+            const cuuint64_t dims[4] = {(cuuint64_t)Cg, (cuuint64_t)Wg / 2, (cuuint64_t)Hg / 2, (cuuint64_t)N};
+            const cuuint64_t str[3] = {(cuuint64_t)2 * Cg * 4, (cuuint64_t)2 * Wg * Cg * 4, (cuuint64_t)Hg * Wg * Cg * 4};
+            if (!encode4(&maps.g[plane], g + ((long)pr * Wg + ps) * Cg, dims, str, box)) return G2_ERR_UNSUPPORTED;
+        }
+    }
+    dim3 grid((unsigned)pl.splits, (unsigned)pl.grid_y, 1);
+    cudaError_t e = cudaSuccess;
+#define WG_LAUNCH(BN)                                                                                                     \
+    {                                                                                                                     \
+        constexpr int smem = STAGES * 4 * TILE_BYTES + 2 * (BN / 32) * TILE_BYTES + (2 * STAGES + 5) * 8 + 16 + 1024;     \
+        static bool attr = false;                                                                                         \
+        if (!attr) {                                                                                                      \
+            e = cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);             \
+            if (e != cudaSuccess) return (int)e;                                                                          \
+            attr = true;                                                                                                  \
+        }                                                                                                                 \
+        wgrad_tc_kernel<BN><<<grid, 192, smem, stream>>>(maps, p);                                                        \
+    }
+    if (Ct == 32) WG_LAUNCH(32) else if (Ct == 64) WG_LAUNCH(64) else WG_LAUNCH(128)
+#undef WG_LAUNCH
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    const long total = (long)R * S * Cg * Ct;
+    long blocks = (total + 255) / 256;
+    if (blocks > 148L * 8) blocks = 148L * 8;
+    wgrad_reduce_kernel<<<(int)blocks, 256, 0, stream>>>(ws, dw, pl.splits, R * S, Cg, Ct, outT);
+    G2_LAUNCH_RET();
+}
+
+}  // extern "C"

@@ -15,8 +15,58 @@ POST_GATE, POST_RELU = 0, 1
 ACTS = {None: 0, 'none': 0, 'relu': 1, 'elu': 2}
 
 
+_PRECISION = {'mode': 'tf32'}
+
+
+def set_precision(mode):
+    """'tf32': tcgen05 tensor-core kernels wherever the shape fits (product default);
+    'fp32': exact-fp32 SIMT kernels everywhere (on-device cross-check)."""
+    assert mode in ('tf32', 'fp32')
+    _PRECISION['mode'] = mode
+
+
+def get_precision():
+    return _PRECISION['mode']
+
+
 def _call(name, *args):
     _lib.call(name, *args)
+
+
+def _tc_ok(N, Hi, Wi, Ci, Ho, Wo, Co, R, S, stride, pad, mode):
+    if _PRECISION['mode'] != 'tf32':
+        return False
+    return _lib.lib().query('g2_conv_tf32_supported', N, Hi, Wi, Ci, Ho, Wo, Co, R, S, stride, pad, mode) == 1
+
+
+def _wgrad_any(g, t, dims, R, S, stride, pad, outT, like):
+    """dW[r,s,a,b] = sum g[.., a] * t[.., b] on the tensor cores when supported, else fp32 SIMT.
+    Returns the packed gradient [R,S,Cg,Ct] (outT=0) or [R,S,Ct,Cg] (outT=1)."""
+    N, Hg, Wg, Cg, Ht, Wt, Ct = dims
+    dwp = _new(like, R, S, Ct, Cg) if outT else _new(like, R, S, Cg, Ct)
+    ws_bytes = 0
+    if _PRECISION['mode'] == 'tf32':
+        ws_bytes = _lib.lib().query('g2_conv_wgrad_tf32_workspace', N, Hg, Wg, Cg, Ht, Wt, Ct, R, S, stride)
+    if ws_bytes > 0:
+        ws = _new(like, ws_bytes // 4)
+        _call('g2_conv_wgrad_tf32', g, t, dwp, ws, N, Hg, Wg, Cg, Ht, Wt, Ct, R, S, stride, pad, outT)
+    else:
+        _call('g2_conv_wgrad_f32', g, t, dwp, N, Hg, Wg, Cg, Ht, Wt, Ct, R, S, stride, pad, outT)
+    return dwp
+
+
+def _conv_any(x, w_t, bias, out, dims, R, S, stride, pad, mode, act, perm_tc, perm_simt_wT):
+    """Run mode-0/1 implicit GEMM on the tensor cores when supported, else the fp32 SIMT kernel.
+    w_t: weight in torch layout; perm_tc: permutation giving [R,S,Cout_op,Cred_op];
+    perm_simt_wT: (permutation giving the packed SIMT weight, wT flag)."""
+    N, Hi, Wi, Ci, Ho, Wo, Co = dims
+    if _tc_ok(N, Hi, Wi, Ci, Ho, Wo, Co, R, S, stride, pad, mode):
+        wp = w_t.permute(*perm_tc).contiguous()
+        _call('g2_conv_igemm_tf32', x, wp, bias, out, N, Hi, Wi, Ci, Ho, Wo, Co, R, S, stride, pad, mode, act)
+    else:
+        perm, wT = perm_simt_wT
+        wp = w_t.permute(*perm).contiguous()
+        _call('g2_conv_igemm_f32', x, wp, bias, None, out, N, Hi, Wi, Ci, Ho, Wo, Co, R, S, stride, pad, mode, wT, act)
 
 
 def _new(like, *shape, dtype=torch.float32):
@@ -24,7 +74,12 @@ def _new(like, *shape, dtype=torch.float32):
 
 
 def _c(t):
-    return t if t.is_contiguous() else t.contiguous()
+    """contiguous and 16-byte aligned (TMA and float4 accesses need it; flat-arena views may not be)."""
+    if not t.is_contiguous():
+        return t.contiguous()
+    if t.data_ptr() % 16 != 0:
+        return t.clone()
+    return t
 
 
 def _act_bwd(dout, out, act):
@@ -85,29 +140,31 @@ class _Conv(Function):
         assert Ci == Ci2, (x.shape, w.shape)
         Ho = (H + 2 * pad - R) // stride + 1
         Wo = (W + 2 * pad - S) // stride + 1
-        wp = w.detach().permute(2, 3, 1, 0).contiguous()          # [R,S,Ci,Co]
+        wd = w.detach()
         out = _new(x, N, Ho, Wo, Co)
-        _call('g2_conv_igemm_f32', x, wp, b, None, out, N, H, W, Ci, Ho, Wo, Co, R, S, stride, pad, 0, 0, act)
-        ctx.save_for_backward(x, wp, out if act != ACT_NONE else None)
+        _conv_any(x, wd, b, out, (N, H, W, Ci, Ho, Wo, Co), R, S, stride, pad, 0, act,
+                  (2, 3, 0, 1), ((2, 3, 1, 0), 0))
+        ctx.save_for_backward(x, wd, out if act != ACT_NONE else None)
         ctx.cfg = (stride, pad, act, b is not None)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, wp, out = ctx.saved_tensors
+        x, wd, out = ctx.saved_tensors
         stride, pad, act, has_b = ctx.cfg
         N, H, W, Ci = x.shape
-        R, S, _, Co = wp.shape
+        Co, _, R, S = wd.shape
         dout = _c(dout)
         _, Ho, Wo, _ = dout.shape
         dpre = _act_bwd(dout, out, act)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            _call('g2_conv_igemm_f32', dpre, wp, None, None, dx, N, Ho, Wo, Co, H, W, Ci, R, S, stride, pad, 1, 1, 0)
+            # data gradient = mode 1 with reduction over Co: tensor-core pack [R,S,Ci,Co]; SIMT pack [R,S,Ci,Co] + wT
+            _conv_any(dpre, wd, None, dx, (N, Ho, Wo, Co, H, W, Ci), R, S, stride, pad, 1, ACT_NONE,
+                      (2, 3, 1, 0), ((2, 3, 1, 0), 1))
         if ctx.needs_input_grad[1]:
-            dwp = torch.empty_like(wp)
-            _call('g2_conv_wgrad_f32', x, dpre, dwp, N, H, W, Ci, Ho, Wo, Co, R, S, stride, pad, 0)
+            dwp = _wgrad_any(x, dpre, (N, H, W, Ci, Ho, Wo, Co), R, S, stride, pad, 0, x)
             dw = dwp.permute(3, 2, 0, 1).contiguous()
         if has_b and ctx.needs_input_grad[2]:
             db = _colsum(dpre, Co, dpre)
@@ -130,29 +187,31 @@ class _ConvT(Function):
         op = stride - 1
         Ho = (H - 1) * stride - 2 * pad + R + op
         Wo = (W - 1) * stride - 2 * pad + S + op
-        wp = w.detach().permute(2, 3, 0, 1).contiguous()          # [R,S,Ci,Co]
+        wd = w.detach()
         out = _new(x, N, Ho, Wo, Co)
-        _call('g2_conv_igemm_f32', x, wp, b, None, out, N, H, W, Ci, Ho, Wo, Co, R, S, stride, pad, 1, 0, act)
-        ctx.save_for_backward(x, wp, out if act != ACT_NONE else None)
+        _conv_any(x, wd, b, out, (N, H, W, Ci, Ho, Wo, Co), R, S, stride, pad, 1, act,
+                  (2, 3, 1, 0), ((2, 3, 0, 1), 0))
+        ctx.save_for_backward(x, wd, out if act != ACT_NONE else None)
         ctx.cfg = (stride, pad, act, b is not None)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, wp, out = ctx.saved_tensors
+        x, wd, out = ctx.saved_tensors
         stride, pad, act, has_b = ctx.cfg
         N, H, W, Ci = x.shape
-        R, S, _, Co = wp.shape
+        _, Co, R, S = wd.shape
         dout = _c(dout)
         _, Ho, Wo, _ = dout.shape
         dpre = _act_bwd(dout, out, act)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            _call('g2_conv_igemm_f32', dpre, wp, None, None, dx, N, Ho, Wo, Co, H, W, Ci, R, S, stride, pad, 0, 1, 0)
+            # data gradient = mode 0 with reduction over Co: tensor-core pack [R,S,Ci,Co]; SIMT pack [R,S,Ci,Co] + wT
+            _conv_any(dpre, wd, None, dx, (N, Ho, Wo, Co, H, W, Ci), R, S, stride, pad, 0, ACT_NONE,
+                      (2, 3, 0, 1), ((2, 3, 0, 1), 1))
         if ctx.needs_input_grad[1]:
-            dwp = torch.empty_like(wp)
-            _call('g2_conv_wgrad_f32', dpre, x, dwp, N, Ho, Wo, Co, H, W, Ci, R, S, stride, pad, 1)
+            dwp = _wgrad_any(dpre, x, (N, Ho, Wo, Co, H, W, Ci), R, S, stride, pad, 1, x)
             dw = dwp.permute(2, 3, 0, 1).contiguous()
         if has_b and ctx.needs_input_grad[2]:
             db = _colsum(dpre, Co, dpre)
@@ -174,7 +233,10 @@ class _Linear(Function):
         M, K = x.shape
         N = w.shape[0]
         y = _new(x, M, N)
-        _call('g2_gemm_f32', x, w, b, y, M, N, K, K, K, N, 0, 1, ACT_NONE, 0)
+        if _gemm_tc_ok(N, K):
+            _call('g2_gemm_tf32', x, w, b, y, M, N, K)
+        else:
+            _call('g2_gemm_f32', x, w, b, y, M, N, K, K, K, N, 0, 1, ACT_NONE, 0)
         if act != ACT_NONE:      # split-K GEMMs cannot fuse the activation; keep it a separate pass
             if N % 4 != 0:
                 raise RuntimeError('linear with activation needs N % 4 == 0')
@@ -195,13 +257,25 @@ class _Linear(Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            _call('g2_gemm_f32', dpre, w, None, dx, M, K, N, N, K, K, 0, 0, ACT_NONE, 0)
+            if _gemm_tc_ok(K, N):
+                _call('g2_gemm_tf32', dpre, w.t().contiguous(), None, dx, M, K, N)
+            else:
+                _call('g2_gemm_f32', dpre, w, None, dx, M, K, N, N, K, K, 0, 0, ACT_NONE, 0)
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(w)
-            _call('g2_gemm_f32', dpre, x, None, dw, N, K, M, N, K, K, 1, 0, ACT_NONE, 0)
+            if _gemm_tc_ok(K, M):
+                _call('g2_gemm_tf32', dpre.t().contiguous(), x.t().contiguous(), None, dw, N, K, M)
+            else:
+                _call('g2_gemm_f32', dpre, x, None, dw, N, K, M, N, K, K, 1, 0, ACT_NONE, 0)
         if has_b and ctx.needs_input_grad[2]:
             db = _colsum(dpre, N, dpre)
         return dx, dw, db, None
+
+
+def _gemm_tc_ok(n_out, k_red):
+    """g2_gemm_tf32 needs the reduction dim % 32 == 0 and the output width in {32,64,128} or % 64 == 0."""
+    return (_PRECISION['mode'] == 'tf32' and k_red % 32 == 0 and k_red >= 64
+            and (n_out in (32, 64, 128) or n_out % 64 == 0))
 
 
 _ZERO_ROWS = {}

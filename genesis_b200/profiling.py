@@ -11,18 +11,20 @@ def algo_cost(name, a):
     """(flops, bytes) a call must perform / move at minimum, from its arguments (pointer args included)."""
     f = b = 0
     if name in ('g2_conv_igemm_f32', 'g2_conv_igemm_tf32'):
-        N, Hi, Wi, Ci, Ho, Wo, Co, R, S, stride, pad, mode = a[5:17]
+        o = 5 if name.endswith('f32') and not name.endswith('tf32') else 4
+        N, Hi, Wi, Ci, Ho, Wo, Co, R, S, stride, pad, mode = a[o:o + 12]
         if mode == 0:
             f = 2.0 * N * Ho * Wo * Co * Ci * R * S
         else:
             f = 2.0 * N * Hi * Wi * Ci * Co * R * S
         b = 4.0 * (N * Hi * Wi * Ci + N * Ho * Wo * Co + R * S * Ci * Co)
     elif name in ('g2_conv_wgrad_f32', 'g2_conv_wgrad_tf32'):
-        N, Hg, Wg, Cg, Ht, Wt, Ct, R, S = a[3:12]
+        o = 4 if name.endswith('tf32') else 3
+        N, Hg, Wg, Cg, Ht, Wt, Ct, R, S = a[o:o + 9]
         f = 2.0 * N * Ht * Wt * Cg * Ct * R * S
         b = 4.0 * (N * Hg * Wg * Cg + N * Ht * Wt * Ct + R * S * Cg * Ct)
     elif name in ('g2_gemm_f32', 'g2_gemm_tf32'):
-        M, N, K = a[4:7]
+        M, N, K = a[4:7]           # (A, B, bias, C, M, N, K, ...) for both entry points
         f = 2.0 * M * N * K
         b = 4.0 * (M * K + N * K + M * N)
     elif name == 'g2_norm_stats_f32':

@@ -42,9 +42,10 @@ class TrainStep(object):
         self.lr = lr
         params = [p for p in model.parameters() if p.requires_grad]
         dev = params[0].device
-        n = sum(p.numel() for p in params)
-        self.n_params = n
-        self.n_pad = (n + 3) // 4 * 4
+        self.n_params = sum(p.numel() for p in params)
+        align = 64                                   # every parameter starts on a 256-byte boundary
+        n = sum((p.numel() + align - 1) // align * align for p in params)
+        self.n_pad = n
         # flat arenas: [params | pad], [grads | pad | err, kl, 0, 0]
         self.flat_p = torch.zeros(self.n_pad, device=dev)
         self.flat_g = torch.zeros(self.n_pad + 4, device=dev)
@@ -56,7 +57,7 @@ class TrainStep(object):
             self.flat_p[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat_p[off:off + k].view_as(p)
             p.grad = self.flat_g[off:off + k].view_as(p)
-            off += k
+            off += (k + align - 1) // align * align
         self.params = params
         self.step_count = torch.zeros((), device=dev)
         self.geco = None

@@ -135,9 +135,20 @@ int g2_conv_tf32_supported(int N, int Hi, int Wi, int Ci, int Ho, int Wo, int Co
 int g2_conv_igemm_tf32(const float* in, const float* w, const float* bias, float* out, int N, int Hi, int Wi,
                        int Ci, int Ho, int Wo, int Co, int R, int S, int stride, int pad, int mode, int act,
                        g2_stream_t stream);
+/* Weight gradient on the tensor cores (wgrad_tc.cu; MN-major operands): same contract as g2_conv_wgrad_f32 plus
+ * a caller-owned workspace of g2_conv_wgrad_tf32_workspace(...) bytes (0 = shape not supported). */
+long g2_conv_wgrad_tf32_workspace(int N, int Hg, int Wg, int Cg, int Ht, int Wt, int Ct, int R, int S, int stride);
+int g2_conv_wgrad_tf32(const float* g, const float* t, float* dw, float* ws, int N, int Hg, int Wg, int Cg, int Ht,
+                       int Wt, int Ct, int R, int S, int stride, int pad, int outT, g2_stream_t stream);
 /* C[M,N] = A[M,K] W[N,K]^T + bias[N] */
 int g2_gemm_tf32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K,
                  g2_stream_t stream);
+
+/* UMMA descriptor self-test (debug_umma.cu): runs `nk` tcgen05.mma.kind::tf32 (M=128) on caller-provided
+ * shared-memory images of A and B with caller-provided descriptor templates and dumps D[128][N]. */
+int g2_debug_umma_probe(const float* a_img, const float* b_img, float* D, int a_bytes, int b_bytes, long adesc_t,
+                        long bdesc_t, int idesc, int N, int nk, int a_kstep, int b_kstep, int a_off, int b_off,
+                        int base_off_auto, g2_stream_t stream);
 
 /* ---- optimiser (pointwise.cu) --------------------------------------------------------------------
  * Fused Adam over a flat fp32 parameter / gradient arena; replaces torch.optim.Adam.step() in the

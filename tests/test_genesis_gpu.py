@@ -15,12 +15,23 @@ from test_oracle_golden import build_engine_model, golden_case, tape_from_golden
 pytestmark = pytest.mark.gpu
 GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'genesis_k*.npz')))
 
-# fp32 tolerances: ELBO terms rel 1e-4, per-tensor gradient rel-L2 1e-2
-ERR_RTOL, KL_ATOL, GRAD_TOL = 1e-4, 5e-3, 1e-2
+# Stated tolerances: ELBO `err` rel 1e-4; KL terms abs 5e-3 + rel 1e-3;
+# per-tensor gradient rel-L2 1e-2 on the TF32 tensor-core path and 2e-3 on the exact-fp32 path.
+ERR_RTOL, KL_ATOL = 1e-4, 5e-3
+GRAD_TOLS = {'tf32': 1e-2, 'fp32': 2e-3}
+
+
+@pytest.fixture(params=['tf32', 'fp32'])
+def precision(request):
+    from genesis_b200 import ops
+    ops.set_precision(request.param)
+    yield request.param
+    ops.set_precision('tf32')
 
 
 @pytest.mark.parametrize('path', GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
-def test_genesis_matches_reference_golden(path):
+def test_genesis_matches_reference_golden(path, precision):
+    GRAD_TOL = GRAD_TOLS[precision]
     g, model, K, img, B = golden_case(path)
     m, cfg = build_engine_model(model, K, img)
     m = m.cuda().train()
@@ -45,7 +56,8 @@ def test_genesis_matches_reference_golden(path):
 
 
 @pytest.mark.parametrize('K,B,gen', [(5, 4, 'multid'), (2, 3, 'rooms'), (5, 16, 'stacks')])
-def test_genesis_matches_oracle(K, B, gen):
+def test_genesis_matches_oracle(K, B, gen, precision):
+    GRAD_TOL = GRAD_TOLS[precision]
     m, cfg = build_engine_model('genesis', K, 64, seed=3)
     m = m.cuda().train()
     sd0 = {k: v.clone() for k, v in m.state_dict().items()}

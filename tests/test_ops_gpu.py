@@ -14,6 +14,16 @@ def _ops():
     return ops
 
 
+@pytest.fixture(autouse=True)
+def exact_fp32_kernels():
+    """These tests pin the exact-fp32 SIMT kernels; the tensor-core path is covered by test_tc_gpu.py and
+    by test_ops_tf32 below."""
+    ops = _ops()
+    ops.set_precision('fp32')
+    yield
+    ops.set_precision('tf32')
+
+
 def close(a, b, rtol=2e-4, atol=None, name=''):
     a = a.detach().double().cpu()
     b = b.detach().double().cpu()
@@ -314,3 +324,31 @@ def test_mixture_nll(K, B, H, softmax):
     gg = grads([err], [xrg, lmg])
     close(gg[0], gr[0], name='dxr', rtol=5e-4)
     close(gg[1], gr[1], name='dlm', rtol=5e-4)
+
+
+@pytest.mark.parametrize('kind,case', [('conv', c) for c in CONV_CASES[1:3] + CONV_CASES[4:6] + CONV_CASES[7:8]]
+                         + [('convT', c) for c in CONVT_CASES[:3]])
+def test_ops_tf32(kind, case):
+    """Same operators through the tcgen05 path (forward + data gradient on tensor cores): TF32 tolerance."""
+    ops = _ops()
+    ops.set_precision('tf32')
+    N, H, W, Ci, Co, R, s, p, act = case
+    torch.manual_seed(21)
+    x = torch.randn(N, Ci, H, W, dtype=torch.float64)
+    w = torch.randn((Co, Ci, R, R) if kind == 'conv' else (Ci, Co, R, R), dtype=torch.float64) * 0.1
+    b = torch.randn(Co, dtype=torch.float64)
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+    if kind == 'conv':
+        ref = F.conv2d(xr, wr, br, stride=s, padding=p)
+    else:
+        ref = F.conv_transpose2d(xr, wr, br, stride=s, padding=p, output_padding=s - 1)
+    ref = {'elu': F.elu, 'relu': F.relu, None: lambda t: t}[act](ref)
+    xg = nhwc(x).float().to(DEV).requires_grad_(True)
+    wg, bg = w.float().to(DEV).requires_grad_(True), b.float().to(DEV).requires_grad_(True)
+    out = (ops.conv2d if kind == 'conv' else ops.conv_transpose2d)(xg, wg, bg, s, p, act)
+    close(nchw(out), ref, name='fwd', rtol=3e-3)
+    gr = grads([ref], [xr, wr, br])
+    gg = grads([nchw(out)], [xg, wg, bg])
+    close(nchw(gg[0]), gr[0], name='dx', rtol=3e-3)
+    close(gg[1], gr[1], name='dw', rtol=3e-3)
+    close(gg[2], gr[2], name='db', rtol=3e-3)

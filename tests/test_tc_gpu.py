@@ -100,3 +100,55 @@ def test_gemm_tf32(M, N, K):
     got = out.double().cpu()
     assert torch.isfinite(got).all()
     assert (got - ref).abs().max().item() / ref.abs().max().item() < 2e-5
+
+
+WGRAD_CASES = [  # kind, N, H, W, Ci, Co, R, stride, pad   (conv: x[N,H,W,Ci] -> y; convT: x[N,H,W,Ci] -> y upsampled)
+    ('conv', 2, 16, 16, 32, 64, 5, 1, 2),
+    ('conv', 3, 32, 32, 64, 128, 5, 1, 2),
+    ('conv', 2, 64, 64, 32, 64, 5, 1, 2),
+    ('conv', 2, 64, 64, 64, 64, 3, 1, 1),
+    ('conv', 2, 70, 70, 32, 32, 3, 1, 0),      # VALID, 8x8 chunks with ragged edges
+    ('conv', 2, 66, 66, 32, 32, 3, 1, 0),
+    ('conv', 2, 64, 64, 32, 64, 5, 2, 2),      # stride 2: parity planes of x
+    ('conv', 2, 32, 32, 32, 64, 3, 2, 1),
+    ('convT', 2, 16, 16, 64, 128, 5, 1, 2),
+    ('convT', 2, 16, 16, 64, 64, 5, 2, 2),     # stride 2: parity planes of dy
+    ('convT', 2, 32, 32, 32, 64, 5, 2, 2),
+]
+
+
+@pytest.mark.parametrize('case', WGRAD_CASES)
+def test_wgrad_tf32_exact_on_prerounded_operands(case):
+    from genesis_b200 import _lib
+    kind, N, H, W, Ci, Co, R, s, p = case
+    torch.manual_seed(3)
+    x = tf32_round(torch.randn(N, Ci, H, W))
+    if kind == 'conv':
+        w = torch.zeros(Co, Ci, R, R, dtype=torch.float64, requires_grad=True)
+        y = F.conv2d(x.double(), w, None, stride=s, padding=p)
+    else:
+        w = torch.zeros(Ci, Co, R, R, dtype=torch.float64, requires_grad=True)
+        y = F.conv_transpose2d(x.double(), w, None, stride=s, padding=p, output_padding=s - 1)
+    dy = tf32_round(torch.randn(y.shape))
+    (ref,) = torch.autograd.grad((y * dy.double()).sum(), [w])
+    Ho, Wo = y.shape[2], y.shape[3]
+    xg = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    dyg = dy.permute(0, 2, 3, 1).contiguous().to(DEV)
+    lib = _lib.lib()
+    if kind == 'conv':      # g = x (a = Ci), t = dy (b = Co); packed [R,S,Ci,Co]
+        dims = (N, H, W, Ci, Ho, Wo, Co)
+        g, t, outT = xg, dyg, 0
+        dwp = torch.full((R, R, Ci, Co), float('nan'), device=DEV)
+    else:                   # g = dy (a = Co), t = x (b = Ci); packed [R,S,Ci,Co] via outT
+        dims = (N, Ho, Wo, Co, H, W, Ci)
+        g, t, outT = dyg, xg, 1
+        dwp = torch.full((R, R, Ci, Co), float('nan'), device=DEV)
+    ws_bytes = lib.query('g2_conv_wgrad_tf32_workspace', *dims, R, R, s)
+    assert ws_bytes > 0
+    ws = torch.empty(ws_bytes // 4, device=DEV)
+    _lib.call('g2_conv_wgrad_tf32', g, t, dwp, ws, *dims, R, R, s, p, outT)
+    torch.cuda.synchronize()
+    got = (dwp.permute(3, 2, 0, 1) if kind == 'conv' else dwp.permute(2, 3, 0, 1)).double().cpu()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-5, err
