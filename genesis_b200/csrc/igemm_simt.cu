@@ -355,8 +355,40 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmP p) {
     }
 }
 
+// out[c] += sum_m x[m, c]   (C % 4 == 0): float4 loads, 256/(C/4) row lanes per block, smem reduce, atomicAdd
+__global__ void __launch_bounds__(256) colsum4_kernel(const float* __restrict__ x, float* __restrict__ out, long M, int C,
+                                                      long rows_per_block) {
+    const int q = C >> 2, lanes = 256 / q;
+    const int t = threadIdx.x, lane = t / q, quad = t - lane * q;
+    const long r0 = (long)blockIdx.x * rows_per_block;
+    const long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < lanes) {
+        long r = r0 + lane;
+        for (; r + 3L * lanes < r1; r += 4L * lanes) {          // 4 independent loads in flight
+            const float4 a = g2_ldg4(x + r * C + quad * 4), b = g2_ldg4(x + (r + lanes) * C + quad * 4);
+            const float4 c = g2_ldg4(x + (r + 2L * lanes) * C + quad * 4), d = g2_ldg4(x + (r + 3L * lanes) * C + quad * 4);
+            s.x += (a.x + b.x) + (c.x + d.x); s.y += (a.y + b.y) + (c.y + d.y);
+            s.z += (a.z + b.z) + (c.z + d.z); s.w += (a.w + b.w) + (c.w + d.w);
+        }
+        for (; r < r1; r += lanes) {
+            const float4 a = g2_ldg4(x + r * C + quad * 4);
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+        }
+    }
+    __shared__ float4 sm[256];
+    sm[t] = s;
+    __syncthreads();
+    if (t < q) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = 0; l < lanes; ++l) { const float4 v = sm[l * q + t]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+        float* o = out + t * 4;
+        atomicAdd(o, a.x); atomicAdd(o + 1, a.y); atomicAdd(o + 2, a.z); atomicAdd(o + 3, a.w);
+    }
+}
+
 __global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long M, int C, long rows_per_block) {
-    // out[c] += sum_m x[m, c];  block handles rows [blockIdx.x*rpb, ...), threads stride over (row-lane, c)
+    // generic C: out[c] += sum_m x[m, c];  block handles rows [blockIdx.x*rpb, ...), threads stride over (row-lane, c)
     extern __shared__ float sm[];
     const int lanes = blockDim.x / C > 0 ? blockDim.x / C : 1;   // row lanes per block (C <= blockDim.x)
     const int c = threadIdx.x % C, lane = threadIdx.x / C;
@@ -371,6 +403,33 @@ __global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ o
         float t = 0.f;
         for (int l = 0; l < lanes; ++l) t += sm[l * C + threadIdx.x];
         atomicAdd(out + threadIdx.x, t);
+    }
+}
+
+// 1x1 output-head weight gradient: dw[o][c] += sum_pix d[pix][o] * h[pix][c]   (d has 4 channels, Cin % 32 == 0).
+// One warp per pixel run: lane = channel (coalesced 128-byte row), d broadcast; block partials -> atomicAdd.
+__global__ void __launch_bounds__(256) head_wgrad_kernel(const float* __restrict__ h, const float* __restrict__ d4,
+                                                         float* __restrict__ dw, long NP, int Cin, long pix_per_block) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long p0 = (long)blockIdx.x * pix_per_block;
+    const long p1 = p0 + pix_per_block < NP ? p0 + pix_per_block : NP;
+    __shared__ float red[8][4][32];
+    for (int cb = 0; cb < Cin; cb += 32) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (long p = p0 + warp; p < p1; p += 8) {
+            const float hv = __ldg(h + p * Cin + cb + lane);
+            const float4 d = g2_ldg4(d4 + p * 4);
+            a0 = fmaf(d.x, hv, a0); a1 = fmaf(d.y, hv, a1); a2 = fmaf(d.z, hv, a2); a3 = fmaf(d.w, hv, a3);
+        }
+        __syncthreads();
+        red[warp][0][lane] = a0; red[warp][1][lane] = a1; red[warp][2][lane] = a2; red[warp][3][lane] = a3;
+        __syncthreads();
+        if (warp < 4) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += red[w][warp][lane];
+            atomicAdd(dw + (long)warp * Cin + cb + lane, s);
+        }
     }
 }
 
@@ -458,11 +517,29 @@ int g2_colsum_f32(const float* x, float* out, long M, int C, int accumulate, cud
         cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)C, stream);
         if (e != cudaSuccess) return (int)e;
     }
+    if ((C & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        const int lanes = 256 / (C / 4);
+        long rpb = (long)lanes * 16;
+        while (g2_cdiv(M, rpb) > 148L * 8) rpb *= 2;
+        colsum4_kernel<<<g2_cdiv(M, rpb), 256, 0, stream>>>(x, out, M, C, rpb);
+        G2_LAUNCH_RET();
+    }
     const int threads = C >= 256 ? ((C + 31) / 32 * 32) : 256;
     long rpb = (M + 148L * 4 - 1) / (148L * 4);
     if (rpb < 64) rpb = 64;
     const int blocks = g2_cdiv(M, rpb);
     colsum_kernel<<<blocks, threads, threads * sizeof(float), stream>>>(x, out, M, C, rpb);
+    G2_LAUNCH_RET();
+}
+
+// dw[4][Cin] = d4^T h  (rows >= nout of d4 are zero): weight gradient of the 1x1 output head.
+int g2_head_wgrad_f32(const float* h, const float* d4, float* dw, long NP, int Cin, cudaStream_t stream) {
+    G2_CHECK_ARG(h && d4 && dw && NP > 0 && Cin >= 32 && (Cin % 32) == 0);
+    cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * 4 * (size_t)Cin, stream);
+    if (e != cudaSuccess) return (int)e;
+    long ppb = 512;
+    while (g2_cdiv(NP, ppb) > 148L * 8) ppb *= 2;
+    head_wgrad_kernel<<<g2_cdiv(NP, ppb), 256, 0, stream>>>(h, d4, dw, NP, Cin, ppb);
     G2_LAUNCH_RET();
 }
 

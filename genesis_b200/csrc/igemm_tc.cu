@@ -287,6 +287,12 @@ int pick_bn(int Co) {
 
 inline int floordiv2(int t) { return (t - (t & 1)) / 2; }
 
+// 128-pixel tile of the virtual output grid: full rows for power-of-two widths, 8 x 16 otherwise (edges masked)
+inline void pick_tile(int Wv, int* TH, int* TW) {
+    if ((Wv & (Wv - 1)) == 0 && Wv >= 8) { *TW = Wv < 128 ? Wv : 128; *TH = 128 / *TW; }
+    else { *TW = 16; *TH = 8; }
+}
+
 }  // namespace tc
 
 extern "C" {
@@ -300,9 +306,7 @@ int g2_conv_tf32_supported(int N, int Hi, int Wi, int Ci, int Ho, int Wo, int Co
     const int Hv = (mode == 1 && stride == 2) ? Ho / 2 : Ho, Wv = (mode == 1 && stride == 2) ? Wo / 2 : Wo;
     if ((long)Hv * Wv < 128) return 0;
     const bool flat = (mode == 0 && stride == 1 && pad == 0 && (Wv & (Wv - 1)) != 0);
-    if (!flat) {
-        if ((Wv & (Wv - 1)) != 0 || Wv < 8) return 0;       // 2-D tiles need a power-of-two width
-    } else if ((long)(R - 1) * Wi + S - 1 > 32000) return 0;
+    if (flat && (long)(R - 1) * Wi + S - 1 > 32000) return 0;
     return 1;
 }
 
@@ -385,7 +389,8 @@ int g2_conv_igemm_tf32(const float* in, const float* w, const float* bias, float
                 cuuint32_t box[4] = {32, 128, 1, 1};
                 if (!encode(&maps.a[0], in, 4, dims, str, box)) return G2_ERR_UNSUPPORTED;
             } else if (mode == 0 && stride == 2) {
-                const int TW = p.Wv < 128 ? p.Wv : 128, TH = 128 / TW;
+                int TW, TH;
+                pick_tile(p.Wv, &TH, &TW);
                 for (int pl = 0; pl < 4; ++pl) {
                     const int pr = pl >> 1, ps = pl & 1;
                     cuuint64_t dims[4] = {(cuuint64_t)Ci, (cuuint64_t)Wi / 2, (cuuint64_t)Hi / 2, (cuuint64_t)N};
@@ -394,7 +399,8 @@ int g2_conv_igemm_tf32(const float* in, const float* w, const float* bias, float
                     if (!encode(&maps.a[pl], in + ((long)pr * Wi + ps) * Ci, 4, dims, str, box)) return G2_ERR_UNSUPPORTED;
                 }
             } else {
-                const int TW = p.Wv < 128 ? p.Wv : 128, TH = 128 / TW;
+                int TW, TH;
+                pick_tile(p.Wv, &TH, &TW);
                 cuuint64_t dims[4] = {(cuuint64_t)Ci, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)N};
                 cuuint64_t str[3] = {(cuuint64_t)Ci * 4, (cuuint64_t)Wi * Ci * 4, (cuuint64_t)Hi * Wi * Ci * 4};
                 cuuint32_t box[4] = {32, (uint32_t)TW, (uint32_t)TH, 1};
@@ -405,7 +411,7 @@ int g2_conv_igemm_tf32(const float* in, const float* w, const float* bias, float
             p.flat_wi = Wi; p.Hv = 1; p.Wv = (Ho - 1) * Wi + Wo;      // last valid flat position + 1
             p.TH = 1; p.TW = 128;
         } else {
-            p.TW = p.Wv < 128 ? p.Wv : 128; p.TH = 128 / p.TW;
+            pick_tile(p.Wv, &p.TH, &p.TW);
         }
         p.tiles_w = g2_cdiv(p.Wv, p.TW); p.tiles_h = g2_cdiv(p.Hv, p.TH);
         dim3 grid((unsigned)((long)N * p.tiles_h * p.tiles_w), (unsigned)(Co / BN), 1);

@@ -73,15 +73,30 @@ __global__ void sbp_scan_bwd_kernel(const float* __restrict__ logits, const floa
 
 // component-VAE encoder input (reference modules/component_vae.py:58-63): for slot k, image b:
 // out[(k*B+b), p, 0] = log_m[k,b,p];  out[(k*B+b), p, 1..3] = x[b, 0..2, p]      (x NCHW, out NHWC4)
+// `Cp` (multiple of 4) output channels: channels >= 4 are zero padding so the encoder's first conv fits the
+// 32-channel k-blocks of the tensor-core kernels.
 __global__ void comp_pack_kernel(const float* __restrict__ x, const float* __restrict__ log_m, float* __restrict__ out,
-                                 long total, int B, int P) {
+                                 long total, int B, int P, int Cp) {
+    const int q = Cp >> 2;
+    for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < total * q; j += (long)gridDim.x * blockDim.x) {
+        const int quad = (int)(j % q);
+        const long i = j / q;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (quad == 0) {
+            const int p = (int)(i % P); const long kb = i / P; const int b = (int)(kb % B);
+            o.x = __ldg(log_m + i);
+            const float* xb = x + (long)b * 3 * P + p;
+            o.y = __ldg(xb); o.z = __ldg(xb + P); o.w = __ldg(xb + 2 * P);
+        }
+        *reinterpret_cast<float4*>(out + j * 4) = o;
+    }
+}
+
+// x [N,C,P] (NCHW) -> y [N,P,Cp] (NHWC, channels >= C zero)
+__global__ void nhwc_pad_kernel(const float* __restrict__ x, float* __restrict__ y, long total, int C, int P, int Cp) {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int p = (int)(i % P); const long kb = i / P; const int b = (int)(kb % B);
-        float4 o;
-        o.x = __ldg(log_m + i);
-        const float* xb = x + (long)b * 3 * P + p;
-        o.y = __ldg(xb); o.z = __ldg(xb + P); o.w = __ldg(xb + 2 * P);
-        *reinterpret_cast<float4*>(out + i * 4) = o;
+        const int c = (int)(i % Cp); const long t = i / Cp; const int p = (int)(t % P); const long n = t / P;
+        y[i] = c < C ? __ldg(x + (n * C + c) * P + p) : 0.f;
     }
 }
 
@@ -169,10 +184,17 @@ int g2_sbp_scan_bwd_f32(const float* logits, const float* dlog_m, float* dlogits
     G2_LAUNCH_RET();
 }
 
-int g2_comp_pack_f32(const float* x, const float* log_m, float* out, int K, int B, int P, cudaStream_t stream) {
-    G2_CHECK_ARG(x && log_m && out && K > 0 && B > 0 && P > 0);
+int g2_comp_pack_f32(const float* x, const float* log_m, float* out, int K, int B, int P, int Cp, cudaStream_t stream) {
+    G2_CHECK_ARG(x && log_m && out && K > 0 && B > 0 && P > 0 && Cp >= 4 && (Cp % 4) == 0);
     const long total = (long)K * B * P;
-    comp_pack_kernel<<<ew_blocks(total), 256, 0, stream>>>(x, log_m, out, total, B, P);
+    comp_pack_kernel<<<ew_blocks(total * (Cp / 4)), 256, 0, stream>>>(x, log_m, out, total, B, P, Cp);
+    G2_LAUNCH_RET();
+}
+
+int g2_nhwc_pad_f32(const float* x, float* y, long N, int C, int P, int Cp, cudaStream_t stream) {
+    G2_CHECK_ARG(x && y && N > 0 && C > 0 && P > 0 && Cp >= C);
+    const long total = N * P * Cp;
+    nhwc_pad_kernel<<<ew_blocks(total), 256, 0, stream>>>(x, y, total, C, P, Cp);
     G2_LAUNCH_RET();
 }
 

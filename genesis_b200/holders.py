@@ -183,13 +183,18 @@ def mc_kl(z, mu, sigma, pmu=None, psigma=None):
 
 
 # ------------------------------------------------------------------------------------------- forward blocks
+def pad_cin(w, cin):
+    """zero-pad a conv weight [Co,Ci,R,S] along Ci (matches activations zero-padded to `cin` channels)."""
+    return w if w.shape[1] == cin else F.pad(w, (0, 0, 0, 0, 0, cin - w.shape[1]))
+
+
 def gated_forward(layer, x, training):
     """GatedConv2d / GatedConvTranspose2d forward on NHWC x (reference layers.py:42-54, 88-101)."""
     conv = layer.conv
     if layer.transposed:
         y = ops.conv_transpose2d(x, conv.weight, conv.bias, layer.stride, layer.pad)
     else:
-        y = ops.conv2d(x, conv.weight, conv.bias, layer.stride, layer.pad)
+        y = ops.conv2d(x, pad_cin(conv.weight, x.shape[3]), conv.bias, layer.stride, layer.pad)
     return gate_norm(layer, y, training)
 
 
@@ -289,7 +294,7 @@ def comp_encode(enc, packed, act):
     m = enc.module
     h = packed
     for i in (0, 2, 4, 6):
-        h = ops.conv2d(h, m[i].weight, m[i].bias, 2, 1, act)
+        h = ops.conv2d(h, pad_cin(m[i].weight, h.shape[3]), m[i].bias, 2, 1, act)
     N, fh, fw, c = h.shape
     w = m[9].weight                                        # [256, c*fh*fw] in NCHW flatten order
     wm = w.view(w.shape[0], c, fh, fw).permute(0, 2, 3, 1).reshape(w.shape[0], -1)

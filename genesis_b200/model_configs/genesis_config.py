@@ -123,7 +123,9 @@ class Genesis(nn.Module, NoiseMixin):
         """LatentSBP.forward (reference attention.py:84-133) + the K-th mask fix-up (genesis_config.py:169-171)."""
         K, B = self.K_steps, x.shape[0]
         ap, core = self.att_process, self.att_process.core
-        h = H.sylvester_encode(core, ops.to_nhwc(x), self.training)                     # [B,256]
+        tc = ops.get_precision() == 'tf32'      # tensor-core kernels want 32-channel k-blocks: zero-pad the image
+        xh = ops.to_nhwc_padded(x, 32) if tc else ops.to_nhwc(x)
+        h = H.sylvester_encode(core, xh, self.training)                                 # [B,256]
         wmv = torch.cat([core.q_z_mean.weight, core.q_z_var[0].weight], 0)
         bmv = torch.cat([core.q_z_mean.bias, core.q_z_var[0].bias], 0)
         mu, raw = torch.chunk(ops.linear(h, wmv, bmv), 2, dim=1)
@@ -152,7 +154,7 @@ class Genesis(nn.Module, NoiseMixin):
         log_m, log_s, att_stats = self._masks(x)                     # [K,B,1,H,W], [K+1,B,1,H,W]
         # --- component VAE (reference component_vae.py:45-81), K slots batched k-major
         cv = self.comp_vae
-        enc = H.comp_encode(cv.encoder_module, ops.comp_pack(x, log_m), 'elu')
+        enc = H.comp_encode(cv.encoder_module, ops.comp_pack(x, log_m, 32 if ops.get_precision() == 'tf32' else 4), 'elu')
         cmu, cps = torch.chunk(enc, 2, dim=1)
         csig = H.to_sigma(cps)
         cz = cmu + csig * self._normal(cmu.shape, x)

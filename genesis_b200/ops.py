@@ -394,22 +394,32 @@ class _CompPack(Function):
     """x [B,3,H,W] (NCHW), log_m [K,B,1,H,W] -> [K*B,H,W,4] NHWC with channel 0 = log_m, 1..3 = x."""
 
     @staticmethod
-    def forward(ctx, x, log_m):
+    def forward(ctx, x, log_m, cp):
         x, log_m = _c(x), _c(log_m)
         K, B = log_m.shape[0], log_m.shape[1]
         H, W = x.shape[2], x.shape[3]
-        out = _new(x, K * B, H, W, 4)
-        _call('g2_comp_pack_f32', x, log_m, out, K, B, H * W)
+        out = _new(x, K * B, H, W, cp)
+        _call('g2_comp_pack_f32', x, log_m, out, K, B, H * W, cp)
         ctx.shape = log_m.shape
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        return None, dout[..., 0].reshape(ctx.shape).contiguous()
+        return None, dout[..., 0].reshape(ctx.shape).contiguous(), None
 
 
-def comp_pack(x, log_m):
-    return _CompPack.apply(x, log_m)
+def comp_pack(x, log_m, cp=4):
+    """cp = 4, or 32 (zero-padded) so the first encoder conv runs on the tensor cores."""
+    return _CompPack.apply(x, log_m, cp)
+
+
+def to_nhwc_padded(x, cp):
+    """NCHW input image -> NHWC with channels zero-padded to cp (no gradient: x is data)."""
+    x = _c(x.detach())
+    N, C, H, W = x.shape
+    y = _new(x, N, H, W, cp)
+    _call('g2_nhwc_pad_f32', x, y, N, C, H * W, cp)
+    return y
 
 
 # ----------------------------------------------------------------------------------------- broadcast add
@@ -474,7 +484,10 @@ class _Out1x1(Function):
         dw = db = None
         if ctx.needs_input_grad[1]:
             dw4 = _new(h, 4, Cin)
-            _call('g2_conv_wgrad_f32', h, dpre4, dw4, N, H, W, Cin, H, W, 4, 1, 1, 1, 0, 1)
+            if Cin % 32 == 0:
+                _call('g2_head_wgrad_f32', h, dpre4, dw4, N * H * W, Cin)
+            else:
+                _call('g2_conv_wgrad_f32', h, dpre4, dw4, N, H, W, Cin, H, W, 4, 1, 1, 1, 0, 1)
             dw = dw4[:nout].reshape(nout, Cin, 1, 1).contiguous()
         if has_b and ctx.needs_input_grad[2]:
             db = _colsum(dpre4, 4, dpre4)[:nout].contiguous()

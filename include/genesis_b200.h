@@ -71,6 +71,9 @@ int g2_gemm_f32(const float* A, const float* B, const float* bias, float* C, int
 /* out[c] (+)= sum_m x[m,c]   (bias gradients) */
 int g2_colsum_f32(const float* x, float* out, long M, int C, int accumulate, g2_stream_t stream);
 
+/* dw[4][Cin] = sum_pix d4[pix][:]^T h[pix][:] -- weight gradient of the 1x1 output heads (out1x1). */
+int g2_head_wgrad_f32(const float* h, const float* d4, float* dw, long NP, int Cin, g2_stream_t stream);
+
 /* ---- normalisation + gate / ReLU (norm.cu) ---------------------------------------------------------
  * Replaces nn.BatchNorm2d / nn.InstanceNorm2d / nn.GroupNorm + sigmoid gate or ReLU and their backward:
  * third_party/sylvester/layers.py:22-54,69-101; modules/blocks.py:151-165;
@@ -100,7 +103,9 @@ int g2_sbp_scan_fwd_f32(const float* logits, float* log_m, float* log_s, long BP
 int g2_sbp_scan_bwd_f32(const float* logits, const float* dlog_m, float* dlogits, long BP, int K, int nl,
                         g2_stream_t stream);
 /* component-VAE encoder input: repeat(x) (+) cat(log_m), modules/component_vae.py:58-63 */
-int g2_comp_pack_f32(const float* x, const float* log_m, float* out, int K, int B, int P, g2_stream_t stream);
+int g2_comp_pack_f32(const float* x, const float* log_m, float* out, int K, int B, int P, int Cp, g2_stream_t stream);
+/* x [N,C,P] (NCHW) -> y [N,P,Cp] (NHWC, zero channels C..Cp-1): lets the 3-channel image feed 32-channel k-blocks */
+int g2_nhwc_pad_f32(const float* x, float* y, long N, int C, int P, int Cp, g2_stream_t stream);
 /* out[n,p,c] = act(a[n,c] + m[p,c]): first broadcast-decoder layer without materialising the broadcast,
  * modules/blocks.py:104-130 + modules/decoders.py:25-26 */
 int g2_bcast_add_act_f32(const float* a, const float* m, float* out, long N, int P, int C, int act,

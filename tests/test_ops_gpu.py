@@ -255,6 +255,12 @@ def test_comp_pack_and_layout():
     out = ops.comp_pack(x.to(DEV), lmg)
     ref = torch.cat([lm.reshape(K * B, 1, H, H), x.repeat(K, 1, 1, 1)], dim=1)
     close(nchw(out), ref, atol=0, rtol=0)
+    out32 = ops.comp_pack(x.to(DEV), lmg, 32)
+    close(nchw(out32)[:, :4], ref, atol=0, rtol=0)
+    assert out32[..., 4:].abs().max().item() == 0
+    xp = ops.to_nhwc_padded(x.to(DEV), 32)
+    close(xp[..., :3], nhwc(x), atol=0, rtol=0)
+    assert xp[..., 3:].abs().max().item() == 0
     g = grads([out], [lmg])[0]
     assert g.shape == lm.shape
     t = torch.randn(3, 5, 4, 6)
