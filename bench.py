@@ -158,6 +158,14 @@ def run_engine(args):
     n_in = 4
     host = [t.pin_memory() for t in synthetic_batches(n_in, B_PER_GPU, 1000 * rank + 1)]
     devx = [t.to(dev) for t in host]
+    graphed = False
+    if not args.no_graph:
+        try:
+            ts.capture(devx[0])
+            graphed = True
+        except Exception as exc:   # report, do not hide: the eager path is still our kernels, just launch-bound
+            sys.stderr.write('CUDA graph capture failed (%s: %s); running eagerly\n' % (type(exc).__name__, exc))
+            ts.graph = None
 
     def barrier():
         if world > 1:
@@ -179,7 +187,7 @@ def run_engine(args):
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = lib.launches - l0
+    launches = (ts.launches_per_step * args.steps) if graphed else (lib.launches - l0)
     # ---- leg 2: end to end through the public API, pinned host inputs, loss read back every step
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -198,10 +206,10 @@ def run_engine(args):
 
     if rank == 0:
         pk = peaks()
-        # ---- dominant kernel: per-call device time inside profiled steps, CUDA events on the launch stream
+        # ---- dominant kernel: per-call device time inside profiled (eager) steps, CUDA events on the launch stream
         with profiling.Profiler() as prof:
             for i in range(2):
-                ts.step_device(devx[i % n_in])
+                ts._step_eager(devx[i % n_in])
         rows = prof.table()
         total_ms = sum(r['ms'] for r in rows)
         top = rows[0]
@@ -243,7 +251,8 @@ def run_engine(args):
             'config': {'workload': 'GENESIS K=5 64x64 Multi-dSprites-shaped, batch %d per GPU, fwd+bwd+allreduce+Adam+GECO' % B_PER_GPU,
                        'global_batch': B_PER_GPU * world, 'parallelism': 'dp%d' % world,
                        'l2': 'per-step working set (activations > 4 GB) exceeds the 126 MB L2; inputs rotate over %d batches' % n_in,
-                       'step_tflops_algorithmic': step_tf, 'last_elbo': last},
+                       'step_tflops_algorithmic': step_tf, 'last_elbo': last, 'cuda_graph': graphed,
+                       'precision': 'tf32 tensor-core operands, fp32 accumulate / storage'},
             'e2e': {'value': imgs / (ms_e2e * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': B_PER_GPU * 3 * IMG * IMG * 4,
                     'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': launches,
@@ -265,6 +274,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
     ap.add_argument('--no-cpu-baseline', dest='no_cpu_baseline', action='store_true')
+    ap.add_argument('--no-graph', dest='no_graph', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)

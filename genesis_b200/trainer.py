@@ -66,6 +66,8 @@ class TrainStep(object):
             self.geco = GecoState(g_goal * 3 * img_size ** 2, g_lr * (64 ** 2 / img_size ** 2), dev,
                                   alpha=g_alpha, beta_init=g_init, beta_min=g_min, speedup=g_speedup)
         self.x_dev = None
+        self.graph = None
+        self.launches_per_step = None
 
     def loss_terms(self, losses):
         """train.py:227-239."""
@@ -79,8 +81,38 @@ class TrainStep(object):
                 kl = kl + losses[key].mean(0)
         return err, kl
 
+    def capture(self, x_example, warmup=3):
+        """Capture forward + backward + all-reduce + GECO + Adam of one step into a CUDA graph (static input
+        buffer, static ELBO output).  After this, step()/step_device() replay the graph: zero host work per step."""
+        dev = self.flat_p.device
+        self.x_static = torch.empty_like(x_example, device=dev)
+        self.x_static.copy_(x_example)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._step_eager(self.x_static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        lib = _lib.lib()
+        l0 = lib.launches
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.elbo_static = self._step_eager(self.x_static)
+        self.launches_per_step = lib.launches - l0
+        self.graph = graph
+        return self
+
     def step_device(self, x):
         """x already resident on the device.  Returns the (detached) ELBO scalar tensor."""
+        if self.graph is not None:
+            if x is not self.x_static:
+                self.x_static.copy_(x, non_blocking=True)
+            self.graph.replay()
+            return self.elbo_static
+        return self._step_eager(x)
+
+    def _step_eager(self, x):
         recon, losses, stats, att, comp = self.model(x)
         err, kl = self.loss_terms(losses)
         beta = self.geco.beta if self.geco is not None else 1.0
@@ -105,9 +137,13 @@ class TrainStep(object):
     def step(self, x):
         """Public entry point: x on the host (ideally pinned) or the device; returns the ELBO tensor."""
         if not x.is_cuda:
-            dev = self.flat_p.device
-            if self.x_dev is None or self.x_dev.shape != x.shape:
-                self.x_dev = torch.empty(x.shape, device=dev, dtype=torch.float32)
-            self.x_dev.copy_(x, non_blocking=True)
-            x = self.x_dev
+            if self.graph is not None:
+                self.x_static.copy_(x, non_blocking=True)
+                x = self.x_static
+            else:
+                dev = self.flat_p.device
+                if self.x_dev is None or self.x_dev.shape != x.shape:
+                    self.x_dev = torch.empty(x.shape, device=dev, dtype=torch.float32)
+                self.x_dev.copy_(x, non_blocking=True)
+                x = self.x_dev
         return self.step_device(x)
