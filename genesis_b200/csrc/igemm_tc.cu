@@ -36,7 +36,7 @@ struct Maps { CUtensorMap a[4]; CUtensorMap b; };
 
 struct P {
     float* out; const float* bias;
-    int N, Hv, Wv, TH, TW, tiles_h, tiles_w;
+    int N, Hv, Wv, TH, TW, TNB, tiles_h, tiles_w;
     int Ho, Wo, Co, os, ph, pw, flat_wi;
     int ntaps, cblocks, kb_total, kb_per_split, act, atomic;
     Taps taps;
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ Ma
     const int t = blockIdx.x;
     const int tw_i = t % p.tiles_w;
     const int th_i = (t / p.tiles_w) % p.tiles_h;
-    const int n = t / (p.tiles_w * p.tiles_h);
+    const int n = (t / (p.tiles_w * p.tiles_h)) * p.TNB;      // first image of the tile (TNB images per tile)
     const int h0 = th_i * p.TH, w0 = tw_i * p.TW;
     const int n0c = blockIdx.y * BN;
     const int kb0 = blockIdx.z * p.kb_per_split;
@@ -186,14 +186,16 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ Ma
         const int row = q * 32 + lane;
         mbar_wait(accf, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int th = row / p.TW, tw = row - th * p.TW;
+        const int per_img = p.TH * p.TW;
+        const int tn = row / per_img, rem = row - tn * per_img;
+        const int th = rem / p.TW, tw = rem - th * p.TW;
         const int hv = h0 + th, wv = w0 + tw;
-        bool valid = hv < p.Hv && wv < p.Wv;
+        bool valid = hv < p.Hv && wv < p.Wv && (n + tn) < p.N;
         int oh, ow;
         if (p.flat_wi > 0) { oh = wv / p.flat_wi; ow = wv - oh * p.flat_wi; }
         else { oh = hv * p.os + p.ph; ow = wv * p.os + p.pw; }
         valid = valid && oh < p.Ho && ow < p.Wo;
-        float* outp = p.out + (((long)n * p.Ho + oh) * p.Wo + ow) * p.Co + n0c;
+        float* outp = p.out + (((long)(n + tn) * p.Ho + oh) * p.Wo + ow) * p.Co + n0c;
         const bool add_bias = p.bias != nullptr && blockIdx.z == 0;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -287,9 +289,13 @@ int pick_bn(int Co) {
 
 inline int floordiv2(int t) { return (t - (t & 1)) / 2; }
 
-// 128-pixel tile of the virtual output grid: full rows for power-of-two widths, 8 x 16 otherwise (edges masked)
-inline void pick_tile(int Wv, int* TH, int* TW) {
-    if ((Wv & (Wv - 1)) == 0 && Wv >= 8) { *TW = Wv < 128 ? Wv : 128; *TH = 128 / *TW; }
+// 128-pixel tile of the virtual output grid: full rows for power-of-two widths, 8 x 16 otherwise (edges masked);
+// maps smaller than 128 pixels (power-of-two sides) put TNB whole images into one tile.
+inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+inline void pick_tile(int Hv, int Wv, int* TH, int* TW, int* TNB) {
+    *TNB = 1;
+    if ((long)Hv * Wv < 128 && is_pow2(Hv) && is_pow2(Wv)) { *TW = Wv; *TH = Hv; *TNB = 128 / (Hv * Wv); }
+    else if (is_pow2(Wv) && Wv >= 8) { *TW = Wv < 128 ? Wv : 128; *TH = 128 / *TW; }
     else { *TW = 16; *TH = 8; }
 }
 
@@ -304,7 +310,7 @@ int g2_conv_tf32_supported(int N, int Hi, int Wi, int Ci, int Ho, int Wo, int Co
     if (stride == 2 && mode == 0 && ((Hi | Wi) & 1)) return 0;
     if (stride == 2 && mode == 1 && ((Ho | Wo) & 1)) return 0;
     const int Hv = (mode == 1 && stride == 2) ? Ho / 2 : Ho, Wv = (mode == 1 && stride == 2) ? Wo / 2 : Wo;
-    if ((long)Hv * Wv < 128) return 0;
+    if ((long)Hv * Wv < 128 && !(tc::is_pow2(Hv) && tc::is_pow2(Wv) && Hv * Wv >= 16)) return 0;
     const bool flat = (mode == 0 && stride == 1 && pad == 0 && (Wv & (Wv - 1)) != 0);
     if (flat && (long)(R - 1) * Wi + S - 1 > 32000) return 0;
     return 1;
@@ -389,32 +395,32 @@ int g2_conv_igemm_tf32(const float* in, const float* w, const float* bias, float
                 cuuint32_t box[4] = {32, 128, 1, 1};
                 if (!encode(&maps.a[0], in, 4, dims, str, box)) return G2_ERR_UNSUPPORTED;
             } else if (mode == 0 && stride == 2) {
-                int TW, TH;
-                pick_tile(p.Wv, &TH, &TW);
+                int TW, TH, TNB;
+                pick_tile(p.Hv, p.Wv, &TH, &TW, &TNB);
                 for (int pl = 0; pl < 4; ++pl) {
                     const int pr = pl >> 1, ps = pl & 1;
                     cuuint64_t dims[4] = {(cuuint64_t)Ci, (cuuint64_t)Wi / 2, (cuuint64_t)Hi / 2, (cuuint64_t)N};
                     cuuint64_t str[3] = {(cuuint64_t)2 * Ci * 4, (cuuint64_t)2 * Wi * Ci * 4, (cuuint64_t)Hi * Wi * Ci * 4};
-                    cuuint32_t box[4] = {32, (uint32_t)TW, (uint32_t)TH, 1};
+                    cuuint32_t box[4] = {32, (uint32_t)TW, (uint32_t)TH, (uint32_t)TNB};
                     if (!encode(&maps.a[pl], in + ((long)pr * Wi + ps) * Ci, 4, dims, str, box)) return G2_ERR_UNSUPPORTED;
                 }
             } else {
-                int TW, TH;
-                pick_tile(p.Wv, &TH, &TW);
+                int TW, TH, TNB;
+                pick_tile(p.Hv, p.Wv, &TH, &TW, &TNB);
                 cuuint64_t dims[4] = {(cuuint64_t)Ci, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)N};
                 cuuint64_t str[3] = {(cuuint64_t)Ci * 4, (cuuint64_t)Wi * Ci * 4, (cuuint64_t)Hi * Wi * Ci * 4};
-                cuuint32_t box[4] = {32, (uint32_t)TW, (uint32_t)TH, 1};
+                cuuint32_t box[4] = {32, (uint32_t)TW, (uint32_t)TH, (uint32_t)TNB};
                 if (!encode(&maps.a[0], in, 4, dims, str, box)) return G2_ERR_UNSUPPORTED;
             }
         }
         if (flat) {
             p.flat_wi = Wi; p.Hv = 1; p.Wv = (Ho - 1) * Wi + Wo;      // last valid flat position + 1
-            p.TH = 1; p.TW = 128;
+            p.TH = 1; p.TW = 128; p.TNB = 1;
         } else {
-            pick_tile(p.Wv, &p.TH, &p.TW);
+            pick_tile(p.Hv, p.Wv, &p.TH, &p.TW, &p.TNB);
         }
         p.tiles_w = g2_cdiv(p.Wv, p.TW); p.tiles_h = g2_cdiv(p.Hv, p.TH);
-        dim3 grid((unsigned)((long)N * p.tiles_h * p.tiles_w), (unsigned)(Co / BN), 1);
+        dim3 grid((unsigned)((long)g2_cdiv(N, p.TNB) * p.tiles_h * p.tiles_w), (unsigned)(Co / BN), 1);
         const int rc = dispatch(maps, p, BN, grid, stream);
         if (rc != G2_OK) return rc;
     }
@@ -443,7 +449,7 @@ int g2_gemm_tf32(const float* A, const float* W, const float* bias, float* C, in
     }
     P p;
     memset(&p, 0, sizeof(p));
-    p.out = C; p.bias = bias; p.N = 1; p.Hv = 1; p.Wv = M; p.TH = 1; p.TW = 128; p.tiles_h = 1; p.tiles_w = g2_cdiv(M, 128);
+    p.out = C; p.bias = bias; p.N = 1; p.Hv = 1; p.Wv = M; p.TH = 1; p.TW = 128; p.TNB = 1; p.tiles_h = 1; p.tiles_w = g2_cdiv(M, 128);
     p.Ho = 1; p.Wo = M; p.Co = N; p.os = 1; p.ntaps = 1; p.cblocks = K / 32; p.kb_total = K / 32; p.act = G2_ACT_NONE;
     const int tiles = p.tiles_w * (N / BN);
     int splits = 1;

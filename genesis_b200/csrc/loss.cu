@@ -87,6 +87,7 @@ struct MixP {
     float* lse;            // [B,3,P]  saved log sum_k exp(.) for the backward
     float* lm_out;         // [K,B,P]  log-softmax masks (softmax != 0), else unused
     int K, B, P, softmax;
+    int xr_cs, lm_cs;      // channels per (k,b) slot in xr (3 dense, 4 when packed with the mask logit) / in lm (1 or 4)
 };
 
 __device__ __forceinline__ void lse_push(float& m, float& s, float a) {
@@ -101,12 +102,13 @@ __global__ void __launch_bounds__(256) mixture_fwd_kernel(const MixP p) {
     float part = 0.f;
     if (i4 < P4) {
         const long KBP = (long)p.B * p.P;
-        const float* lmb = p.lm + (long)b * p.P + i4 * 4;
+        const long LKB = KBP * p.lm_cs;                       // lm stride between slots k
+        const float* lmb = p.lm + (long)b * p.P * p.lm_cs + i4 * 4;
         float4 mnorm = make_float4(0.f, 0.f, 0.f, 0.f);      // log sum_k exp(logit_k) when softmax
         if (p.softmax) {
             float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, s[4] = {0.f, 0.f, 0.f, 0.f};
             for (int k = 0; k < p.K; ++k) {
-                const float4 l = g2_ldg4(lmb + k * KBP);
+                const float4 l = g2_ldg4(lmb + k * LKB);
                 lse_push(m[0], s[0], l.x); lse_push(m[1], s[1], l.y); lse_push(m[2], s[2], l.z); lse_push(m[3], s[3], l.w);
             }
             mnorm = make_float4(m[0] + logf(s[0]), m[1] + logf(s[1]), m[2] + logf(s[2]), m[3] + logf(s[3]));
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(256) mixture_fwd_kernel(const MixP p) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) { mx[c][j] = -INFINITY; sm[c][j] = 0.f; rc[c][j] = 0.f; }
         for (int k = 0; k < p.K; ++k) {
-            float4 l = g2_ldg4(lmb + k * KBP);
+            float4 l = g2_ldg4(lmb + k * LKB);
             if (p.softmax) {
                 l.x -= mnorm.x; l.y -= mnorm.y; l.z -= mnorm.z; l.w -= mnorm.w;
                 *reinterpret_cast<float4*>(p.lm_out + k * KBP + (long)b * p.P + i4 * 4) = l;
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(256) mixture_fwd_kernel(const MixP p) {
             for (int j = 0; j < 4; ++j) mk[j] = expf(lv[j]);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float4 r4 = g2_ldg4(p.xr + (((long)k * p.B + b) * 3 + c) * p.P + i4 * 4);
+                const float4 r4 = g2_ldg4(p.xr + (((long)k * p.B + b) * p.xr_cs + c) * p.P + i4 * 4);
                 const float rv[4] = {r4.x, r4.y, r4.z, r4.w};
                 const float xx[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
 #pragma unroll
@@ -166,6 +168,7 @@ struct MixBP {
     float* dxr;            // [K,B,3,P]
     float* dlm;            // [K,B,P]   gradient w.r.t. log masks, or w.r.t. mask LOGITS when softmax != 0
     int K, B, P, softmax;
+    int xr_cs, lm_cs, dlm_cs;   // slot strides (channels) of xr/dxr, of lm, of dlm
 };
 
 // r_kc = exp(a_kc - lse_c);  d err / d log m_k = - sum_c r_kc;  d err / d xr_kc = - r_kc (x_c - xr_kc)/std_k^2
@@ -184,14 +187,14 @@ __global__ void __launch_bounds__(256) mixture_bwd_kernel(const MixBP p) {
         xv[c] = g2_ldg4(p.x + o); Lv[c] = g2_ldg4(p.lse + o);
     }
     for (int k = 0; k < p.K; ++k) {
-        const float4 l = g2_ldg4(p.lm + k * KBP + (long)b * p.P + i4 * 4);
+        const float4 l = g2_ldg4(p.lm + ((long)k * p.B + b) * p.lm_cs * p.P + i4 * 4);
         const float sd = __ldg(p.stdv + k);
         const float inv2v = 0.5f / (sd * sd), cst = -logf(sd) - 0.9189385332046727f;
         const float lv[4] = {l.x, l.y, l.z, l.w};
         float gm[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const long o = (((long)k * p.B + b) * 3 + c) * p.P + i4 * 4;
+            const long o = (((long)k * p.B + b) * p.xr_cs + c) * p.P + i4 * 4;
             const float4 r4 = g2_ldg4(p.xr + o);
             const float rv[4] = {r4.x, r4.y, r4.z, r4.w};
             const float xx[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(256) mixture_bwd_kernel(const MixBP p) {
         } else {
             o4 = make_float4(-g * gm[0], -g * gm[1], -g * gm[2], -g * gm[3]);
         }
-        *reinterpret_cast<float4*>(p.dlm + k * KBP + (long)b * p.P + i4 * 4) = o4;
+        *reinterpret_cast<float4*>(p.dlm + ((long)k * p.B + b) * p.dlm_cs * p.P + i4 * 4) = o4;
     }
 }
 
@@ -238,21 +241,23 @@ int g2_out1x1_bwd_f32(const float* dout, const float* out, const float* w, float
 }
 
 int g2_mixture_fwd_f32(const float* x, const float* xr, const float* lm, const float* stdv, float* err, float* recon,
-                       float* lse, float* lm_out, int K, int B, int P, int softmax, cudaStream_t stream) {
+                       float* lse, float* lm_out, int K, int B, int P, int softmax, int xr_cs, int lm_cs, cudaStream_t stream) {
     G2_CHECK_ARG(x && xr && lm && stdv && err && recon && lse && K >= 1 && B > 0 && P > 0 && (P % 4) == 0);
+    G2_CHECK_ARG(xr_cs >= 3 && lm_cs >= 1);
     if (softmax) G2_CHECK_ARG(lm_out != nullptr);
     cudaError_t e = cudaMemsetAsync(err, 0, sizeof(float) * (size_t)B, stream);
     if (e != cudaSuccess) return (int)e;
-    MixP p{x, xr, lm, stdv, err, recon, lse, lm_out, K, B, P, softmax};
+    MixP p{x, xr, lm, stdv, err, recon, lse, lm_out, K, B, P, softmax, xr_cs, lm_cs};
     dim3 grid(g2_cdiv(P / 4, 256), B);
     mixture_fwd_kernel<<<grid, 256, 0, stream>>>(p);
     G2_LAUNCH_RET();
 }
 
 int g2_mixture_bwd_f32(const float* x, const float* xr, const float* lm, const float* stdv, const float* lse,
-                       const float* gerr, float* dxr, float* dlm, int K, int B, int P, int softmax, cudaStream_t stream) {
+                       const float* gerr, float* dxr, float* dlm, int K, int B, int P, int softmax, int xr_cs, int lm_cs,
+                       int dlm_cs, cudaStream_t stream) {
     G2_CHECK_ARG(x && xr && lm && stdv && lse && gerr && dxr && dlm && K >= 1 && B > 0 && P > 0 && (P % 4) == 0);
-    MixBP p{x, xr, lm, stdv, lse, gerr, dxr, dlm, K, B, P, softmax};
+    MixBP p{x, xr, lm, stdv, lse, gerr, dxr, dlm, K, B, P, softmax, xr_cs, lm_cs, dlm_cs};
     dim3 grid(g2_cdiv(P / 4, 256), B);
     mixture_bwd_kernel<<<grid, 256, 0, stream>>>(p);
     G2_LAUNCH_RET();

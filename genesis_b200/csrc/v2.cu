@@ -1,0 +1,337 @@
+// genesis_b200 -- kernels specific to GENESIS-V2 / MONet: nearest resampling for the UNet, the instance-colouring
+// stick-breaking process (IC-SBP) and the masked feature pooling.  fp32, NHWC.
+#include "common.cuh"
+
+namespace {
+
+inline int ew_blocks(long work, int threads = 256) {
+    long b = (work + threads - 1) / threads;
+    const long cap = 148L * 16;
+    return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+// ------------------------------------------------------------------------------------------ nearest x0.5 / x2
+// mode 0: y[n,h,w,:] = x[n,2h,2w,:]            (F.interpolate(scale_factor=0.5,'nearest'), reference unet.py:77-78)
+// mode 1: y[n,h,w,:] = x[n,h/2,w/2,:]          (scale_factor=2.0, unet.py:88-89)
+// mode 2: y (HxW, zeros except y[n,2h,2w,:] = x[n,h,w,:])       = backward of mode 0   (x is H/2 x W/2)
+// mode 3: y[n,h,w,:] = sum_{a,b<2} x[n,2h+a,2w+b,:]              = backward of mode 1   (x is 2H x 2W)
+// Ho, Wo are the OUTPUT sizes; C % 4 == 0.
+__global__ void resample_kernel(const float* __restrict__ x, float* __restrict__ y, long total_quads, int Ho, int Wo, int C, int mode) {
+    const int q = C >> 2;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total_quads; i += (long)gridDim.x * blockDim.x) {
+        const int quad = (int)(i % q); long t = i / q;
+        const int w = (int)(t % Wo); t /= Wo;
+        const int h = (int)(t % Ho); const long n = t / Ho;
+        float4 v;
+        if (mode == 0) {
+            v = g2_ldg4(x + ((n * (2 * Ho) + 2 * h) * (2L * Wo) + 2 * w) * C + quad * 4);
+        } else if (mode == 1) {
+            v = g2_ldg4(x + ((n * (Ho / 2) + h / 2) * (long)(Wo / 2) + w / 2) * C + quad * 4);
+        } else if (mode == 2) {
+            v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!((h | w) & 1)) v = g2_ldg4(x + ((n * (Ho / 2) + h / 2) * (long)(Wo / 2) + w / 2) * C + quad * 4);
+        } else {
+            const float* b = x + ((n * (2 * Ho) + 2 * h) * (2L * Wo) + 2 * w) * C + quad * 4;
+            const float4 a0 = g2_ldg4(b), a1 = g2_ldg4(b + C), a2 = g2_ldg4(b + 2L * Wo * C), a3 = g2_ldg4(b + 2L * Wo * C + C);
+            v = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y), (a0.z + a1.z) + (a2.z + a3.z),
+                            (a0.w + a1.w) + (a2.w + a3.w));
+        }
+        *reinterpret_cast<float4*>(y + i * 4) = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ IC-SBP
+// InstanceColouringSBP.forward, gaussian kernel (reference modules/attention.py:177-223).  One CTA per image.
+// colour [B,P,CD] (NHWC, CD = 8), u [B,P] uniform draws, log_sigma scalar.  steps = K-1.
+//   per step k: idx = argmax_p u_p * exp(log_s_k,p) (lowest index wins ties); seed = colour[idx];
+//               alpha = exp(-|colour_p - seed|^2 / exp(log_sigma)); ac = clamp(alpha, .01, .99)
+//               log_m_k = log_s_k + log ac;  log_s_{k+1} = log_s_k + log(1 - ac)
+//   log_m_{K-1} = log_s_{K-1}.   Outputs log_m [K,B,P], log_s [K,B,P], seed_idx [K-1,B] (int32).
+constexpr int CD = 8;
+constexpr int IC_THREADS = 1024;
+constexpr int IC_MAXPPT = 16;       // pixels per thread (P <= 16384)
+
+__global__ void __launch_bounds__(IC_THREADS) icsbp_fwd_kernel(const float* __restrict__ colour, const float* __restrict__ u,
+                                                               const float* __restrict__ log_sigma, float* __restrict__ log_m,
+                                                               float* __restrict__ log_s, int* __restrict__ seed_idx, int B, int P, int K) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int ppt = (P + IC_THREADS - 1) / IC_THREADS;
+    __shared__ float s_val[32];
+    __shared__ int s_idx[32];
+    __shared__ float s_seed[CD];
+    __shared__ int s_best;
+    const float inv_sigma = 1.f / expf(__ldg(log_sigma));
+    const float* col = colour + (long)b * P * CD;
+    float ls[IC_MAXPPT];
+#pragma unroll
+    for (int j = 0; j < IC_MAXPPT; ++j) ls[j] = 0.f;
+    const long KB = (long)B * P;
+    for (int k = 0; k < K - 1; ++k) {
+        // ---- block argmax of u * scope (first maximum, as torch.argmax)
+        float best = -1.f; int bi = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < IC_MAXPPT; ++j) {
+            const int p = tid + j * IC_THREADS;
+            if (j < ppt && p < P) {
+                const float v = __ldg(u + (long)b * P + p) * expf(ls[j]);
+                if (v > best) { best = v; bi = p; }       // p increases with j: keeps the lowest index on ties
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if ((tid & 31) == 0) { s_val[tid >> 5] = best; s_idx[tid >> 5] = bi; }
+        __syncthreads();
+        if (tid < 32) {
+            best = s_val[tid]; bi = s_idx[tid];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if (tid == 0) { s_best = bi; seed_idx[(long)k * B + b] = bi; }
+        }
+        __syncthreads();
+        if (tid < CD) s_seed[tid] = __ldg(col + (long)s_best * CD + tid);
+        __syncthreads();
+        // ---- masks
+#pragma unroll
+        for (int j = 0; j < IC_MAXPPT; ++j) {
+            const int p = tid + j * IC_THREADS;
+            if (j < ppt && p < P) {
+                const float4 c0 = g2_ldg4(col + (long)p * CD), c1 = g2_ldg4(col + (long)p * CD + 4);
+                const float d0 = c0.x - s_seed[0], d1 = c0.y - s_seed[1], d2 = c0.z - s_seed[2], d3 = c0.w - s_seed[3];
+                const float d4 = c1.x - s_seed[4], d5 = c1.y - s_seed[5], d6 = c1.z - s_seed[6], d7 = c1.w - s_seed[7];
+                const float dist = ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3)) + ((d4 * d4 + d5 * d5) + (d6 * d6 + d7 * d7));
+                float a = expf(-dist * inv_sigma);
+                a = fminf(fmaxf(a, 0.01f), 0.99f);
+                log_s[k * KB + (long)b * P + p] = ls[j];
+                log_m[k * KB + (long)b * P + p] = ls[j] + logf(a);
+                ls[j] += logf(1.f - a);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < IC_MAXPPT; ++j) {
+        const int p = tid + j * IC_THREADS;
+        if (j < ppt && p < P) {
+            log_s[(long)(K - 1) * KB + (long)b * P + p] = ls[j];
+            log_m[(long)(K - 1) * KB + (long)b * P + p] = ls[j];
+        }
+    }
+}
+
+// Backward: dcolour [B,P,CD], dlog_sigma partial per image [B] (summed by the caller), from dlog_m [K,B,P].
+// alpha does not depend on the scope, so only the seed indices of the forward are needed.  Reverse scan:
+//   R = G_{K-1};  for k = K-2..0: d(alpha_c) = G_k / ac - R / (1 - ac)   (straight-through clamp);  R += G_k
+//   d(dist) = -d(alpha) * alpha / sigma;  d log_sigma += d(alpha) * alpha * dist / sigma
+//   d colour_p += 2 (colour_p - seed) d(dist);  d seed -= sum_p 2 (colour_p - seed) d(dist)  -> colour[idx_k]
+__global__ void __launch_bounds__(IC_THREADS) icsbp_bwd_kernel(const float* __restrict__ colour, const float* __restrict__ log_sigma,
+                                                               const int* __restrict__ seed_idx, const float* __restrict__ dlog_m,
+                                                               float* __restrict__ dcolour, float* __restrict__ dlog_sigma_b,
+                                                               int B, int P, int K) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int ppt = (P + IC_THREADS - 1) / IC_THREADS;
+    __shared__ float s_seed[CD];
+    __shared__ float s_red[32][CD + 1];
+    const float inv_sigma = 1.f / expf(__ldg(log_sigma));
+    const float* col = colour + (long)b * P * CD;
+    float* dcol = dcolour + (long)b * P * CD;
+    const long KB = (long)B * P;
+    // each thread owns pixels tid + j*1024: their dcolour rows are accumulated in global memory (L2-resident,
+    // 128 KB per image) instead of 128 registers per thread
+    float R[IC_MAXPPT];
+#pragma unroll
+    for (int j = 0; j < IC_MAXPPT; ++j) {
+        const int p = tid + j * IC_THREADS;
+        const bool ok = j < ppt && p < P;
+        R[j] = ok ? __ldg(dlog_m + (long)(K - 1) * KB + (long)b * P + p) : 0.f;
+        if (ok) {
+            *reinterpret_cast<float4*>(dcol + (long)p * CD) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(dcol + (long)p * CD + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    float dls = 0.f;
+    for (int k = K - 2; k >= 0; --k) {
+        const int sidx = __ldg(seed_idx + (long)k * B + b);
+        __syncthreads();
+        if (tid < CD) s_seed[tid] = __ldg(col + (long)sidx * CD + tid);
+        __syncthreads();
+        float dseed[CD];
+#pragma unroll
+        for (int c = 0; c < CD; ++c) dseed[c] = 0.f;
+#pragma unroll
+        for (int j = 0; j < IC_MAXPPT; ++j) {
+            const int p = tid + j * IC_THREADS;
+            if (j < ppt && p < P) {
+                const float4 c0 = g2_ldg4(col + (long)p * CD), c1 = g2_ldg4(col + (long)p * CD + 4);
+                const float df[CD] = {c0.x - s_seed[0], c0.y - s_seed[1], c0.z - s_seed[2], c0.w - s_seed[3],
+                                      c1.x - s_seed[4], c1.y - s_seed[5], c1.z - s_seed[6], c1.w - s_seed[7]};
+                float dist = 0.f;
+#pragma unroll
+                for (int c = 0; c < CD; ++c) dist += df[c] * df[c];
+                const float a = expf(-dist * inv_sigma);
+                const float ac = fminf(fmaxf(a, 0.01f), 0.99f);
+                const float G = __ldg(dlog_m + (long)k * KB + (long)b * P + p);
+                const float da = G / ac - R[j] / (1.f - ac);
+                R[j] += G;
+                const float dd = -da * a * inv_sigma;
+                dls += da * a * dist * inv_sigma;
+                float g[CD];
+#pragma unroll
+                for (int c = 0; c < CD; ++c) { g[c] = 2.f * df[c] * dd; dseed[c] -= g[c]; }
+                float4* dp = reinterpret_cast<float4*>(dcol + (long)p * CD);
+                float4 o0 = dp[0], o1 = dp[1];
+                o0.x += g[0]; o0.y += g[1]; o0.z += g[2]; o0.w += g[3];
+                o1.x += g[4]; o1.y += g[5]; o1.z += g[6]; o1.w += g[7];
+                dp[0] = o0; dp[1] = o1;
+            }
+        }
+        // block-reduce dseed (8 values) and add it to the seed pixel's gradient (held by exactly one thread)
+#pragma unroll
+        for (int c = 0; c < CD; ++c) dseed[c] = g2_warp_sum(dseed[c]);
+        if ((tid & 31) == 0)
+#pragma unroll
+            for (int c = 0; c < CD; ++c) s_red[tid >> 5][c] = dseed[c];
+        __syncthreads();
+        if (tid == sidx % IC_THREADS) {          // the thread that owns the seed pixel adds d(seed)
+#pragma unroll
+            for (int c = 0; c < CD; ++c) {
+                float t = 0.f;
+                for (int w = 0; w < IC_THREADS / 32; ++w) t += s_red[w][c];
+                dcol[(long)sidx * CD + c] += t;
+            }
+        }
+    }
+    __shared__ float red2[32];
+    dls = g2_block_sum(dls, red2);
+    if (tid == 0) dlog_sigma_b[b] = dls;
+}
+
+// ------------------------------------------------------------------------------------------ masked pooling
+// num[k,b,c] = sum_p exp(log_m[k,b,p]) f[b,p,c];  msum[k,b] = sum_p exp(log_m[k,b,p])
+// (reference models/genesisv2_config.py:147-152; the feature head is evaluated once, not K times).
+// grid (chunks, B); block = C threads (C = 128); K <= 16.
+constexpr int MP_MAXK = 16;
+constexpr int MP_CHUNK = 64;
+__global__ void masked_pool_fwd_kernel(const float* __restrict__ f, const float* __restrict__ log_m, float* __restrict__ num,
+                                       float* __restrict__ msum, int B, int P, int C, int K, int pix_per_block) {
+    const int b = blockIdx.y, c = threadIdx.x;
+    const int p0 = blockIdx.x * pix_per_block, p1 = min(P, p0 + pix_per_block);
+    __shared__ float sm[MP_MAXK][MP_CHUNK];
+    float acc[MP_MAXK], ms[MP_MAXK];
+#pragma unroll
+    for (int k = 0; k < MP_MAXK; ++k) { acc[k] = 0.f; ms[k] = 0.f; }
+    for (int pb = p0; pb < p1; pb += MP_CHUNK) {
+        const int np = min(MP_CHUNK, p1 - pb);
+        __syncthreads();
+        for (int i = threadIdx.x; i < K * MP_CHUNK; i += blockDim.x) {
+            const int k = i / MP_CHUNK, j = i - k * MP_CHUNK;
+            sm[k][j] = j < np ? expf(__ldg(log_m + ((long)k * B + b) * P + pb + j)) : 0.f;
+        }
+        __syncthreads();
+        for (int j = 0; j < np; ++j) {
+            const float fv = __ldg(f + ((long)b * P + pb + j) * C + c);
+#pragma unroll
+            for (int k = 0; k < MP_MAXK; ++k)
+                if (k < K) acc[k] = fmaf(sm[k][j], fv, acc[k]);
+        }
+        if (c < K) for (int j = 0; j < np; ++j) ms[0] += sm[c][j];
+    }
+    for (int k = 0; k < K; ++k) atomicAdd(num + ((long)k * B + b) * C + c, acc[k]);
+    if (c < K) atomicAdd(msum + (long)c * B + b, ms[0]);
+}
+
+// df[b,p,c] = sum_k m_kp dnum[k,b,c];   dlog_m[k,b,p] = m_kp (sum_c f[b,p,c] dnum[k,b,c] + dmsum[k,b])
+// grid (chunks, B); block = 256 threads = 8 warps; one warp per pixel, lanes stride over channels.
+__global__ void __launch_bounds__(256) masked_pool_bwd_kernel(const float* __restrict__ f, const float* __restrict__ log_m,
+                                                              const float* __restrict__ dnum, const float* __restrict__ dmsum,
+                                                              float* __restrict__ df, float* __restrict__ dlog_m, int B, int P, int C,
+                                                              int K, int pix_per_block) {
+    extern __shared__ float sd[];          // dnum [K][C]
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < K * C; i += blockDim.x) {
+        const int k = i / C, c = i - k * C;
+        sd[i] = __ldg(dnum + ((long)k * B + b) * C + c);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p0 = blockIdx.x * pix_per_block, p1 = min(P, p0 + pix_per_block);
+    for (int p = p0 + warp; p < p1; p += 8) {
+        float m[MP_MAXK], dot[MP_MAXK];
+#pragma unroll
+        for (int k = 0; k < MP_MAXK; ++k) { m[k] = k < K ? expf(__ldg(log_m + ((long)k * B + b) * P + p)) : 0.f; dot[k] = 0.f; }
+        for (int c = lane; c < C; c += 32) {
+            const float fv = __ldg(f + ((long)b * P + p) * C + c);
+            float g = 0.f;
+#pragma unroll
+            for (int k = 0; k < MP_MAXK; ++k)
+                if (k < K) { const float d = sd[k * C + c]; g = fmaf(m[k], d, g); dot[k] = fmaf(fv, d, dot[k]); }
+            df[((long)b * P + p) * C + c] = g;
+        }
+#pragma unroll
+        for (int k = 0; k < MP_MAXK; ++k)
+            if (k < K) {
+                const float t = g2_warp_sum(dot[k]);
+                if (lane == 0) dlog_m[((long)k * B + b) * P + p] = m[k] * (t + __ldg(dmsum + (long)k * B + b));
+            }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int g2_resample_f32(const float* x, float* y, long N, int Ho, int Wo, int C, int mode, cudaStream_t stream) {
+    G2_CHECK_ARG(x && y && N > 0 && Ho > 0 && Wo > 0 && C >= 4 && (C % 4) == 0 && mode >= 0 && mode <= 3);
+    if (mode == 1 || mode == 2) G2_CHECK_ARG((Ho % 2) == 0 && (Wo % 2) == 0);
+    const long quads = N * Ho * Wo * (C / 4);
+    resample_kernel<<<ew_blocks(quads), 256, 0, stream>>>(x, y, quads, Ho, Wo, C, mode);
+    G2_LAUNCH_RET();
+}
+
+int g2_icsbp_fwd_f32(const float* colour, const float* u, const float* log_sigma, float* log_m, float* log_s, int* seed_idx,
+                     int B, int P, int K, int colour_dim, cudaStream_t stream) {
+    G2_CHECK_ARG(colour && u && log_sigma && log_m && log_s && seed_idx && B > 0 && K >= 2);
+    G2_CHECK_ARG(colour_dim == CD && P > 0 && P <= IC_THREADS * IC_MAXPPT);
+    icsbp_fwd_kernel<<<B, IC_THREADS, 0, stream>>>(colour, u, log_sigma, log_m, log_s, seed_idx, B, P, K);
+    G2_LAUNCH_RET();
+}
+
+int g2_icsbp_bwd_f32(const float* colour, const float* log_sigma, const int* seed_idx, const float* dlog_m, float* dcolour,
+                     float* dlog_sigma_b, int B, int P, int K, int colour_dim, cudaStream_t stream) {
+    G2_CHECK_ARG(colour && log_sigma && seed_idx && dlog_m && dcolour && dlog_sigma_b && B > 0 && K >= 2);
+    G2_CHECK_ARG(colour_dim == CD && P > 0 && P <= IC_THREADS * IC_MAXPPT);
+    icsbp_bwd_kernel<<<B, IC_THREADS, 0, stream>>>(colour, log_sigma, seed_idx, dlog_m, dcolour, dlog_sigma_b, B, P, K);
+    G2_LAUNCH_RET();
+}
+
+int g2_masked_pool_fwd_f32(const float* f, const float* log_m, float* num, float* msum, int B, int P, int C, int K, cudaStream_t stream) {
+    G2_CHECK_ARG(f && log_m && num && msum && B > 0 && P > 0 && C >= 32 && C <= 1024 && (C % 32) == 0 && K >= 1 && K <= MP_MAXK);
+    cudaError_t e = cudaMemsetAsync(num, 0, sizeof(float) * (size_t)K * B * C, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(msum, 0, sizeof(float) * (size_t)K * B, stream);
+    if (e != cudaSuccess) return (int)e;
+    int ppb = 512;
+    while ((long)g2_cdiv(P, ppb) * B < 296 && ppb > MP_CHUNK) ppb /= 2;
+    dim3 grid(g2_cdiv(P, ppb), B);
+    masked_pool_fwd_kernel<<<grid, C, 0, stream>>>(f, log_m, num, msum, B, P, C, K, ppb);
+    G2_LAUNCH_RET();
+}
+
+int g2_masked_pool_bwd_f32(const float* f, const float* log_m, const float* dnum, const float* dmsum, float* df, float* dlog_m,
+                           int B, int P, int C, int K, cudaStream_t stream) {
+    G2_CHECK_ARG(f && log_m && dnum && dmsum && df && dlog_m && B > 0 && P > 0 && C >= 32 && K >= 1 && K <= MP_MAXK);
+    G2_CHECK_ARG((size_t)K * C * sizeof(float) <= 48 * 1024);
+    int ppb = 256;
+    while ((long)g2_cdiv(P, ppb) * B < 296 && ppb > 32) ppb /= 2;
+    dim3 grid(g2_cdiv(P, ppb), B);
+    masked_pool_bwd_kernel<<<grid, 256, (size_t)K * C * sizeof(float), stream>>>(f, log_m, dnum, dmsum, df, dlog_m, B, P, C, K, ppb);
+    G2_LAUNCH_RET();
+}
+
+}  // extern "C"

@@ -26,7 +26,7 @@ struct Maps { CUtensorMap g[4]; CUtensorMap t; };
 
 struct P {
     float* ws;                    // [splits][ntaps][Cg][Ct]
-    int N, Ht, Wt, TH, TW, tiles_h, tiles_w, chunks_total, chunks_per_cta;
+    int N, Ht, Wt, TH, TW, TNB, tiles_h, tiles_w, chunks_total, chunks_per_cta;
     int Cg, Ct, ntaps, nblk, groups_per_cta;
     short tap_plane[32], tap_dh[32], tap_dw[32];
     short blk_tap[MAX_BLK], blk_cb[MAX_BLK];
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
                 const int chunk = c_begin + c;
                 const int tw_i = chunk % p.tiles_w;
                 const int th_i = (chunk / p.tiles_w) % p.tiles_h;
-                const int n = chunk / (p.tiles_w * p.tiles_h);
+                const int n = (chunk / (p.tiles_w * p.tiles_h)) * p.TNB;
                 const int h0 = th_i * p.TH, w0 = tw_i * p.TW;
                 const int tb = c & 1;
                 mbar_wait(&tempty[tb], ((uint32_t)(c >> 1) & 1u) ^ 1u);
@@ -255,7 +255,7 @@ bool encode4(CUtensorMap* m, const void* base, const cuuint64_t* dims, const cuu
 
 inline int floordiv2(int t) { return (t - (t & 1)) / 2; }
 
-struct Plan { int TH, TW, tiles_h, tiles_w, chunks, ngroups, gpc, grid_y, splits, cpc; };
+struct Plan { int TH, TW, TNB, tiles_h, tiles_w, chunks, ngroups, gpc, grid_y, splits, cpc; };
 
 bool make_plan(int N, int Hg, int Wg, int Cg, int Ht, int Wt, int Ct, int R, int S, int stride, Plan* pl) {
     if (Cg % 32 != 0 || !(Ct == 32 || Ct == 64 || Ct == 128)) return false;
@@ -263,11 +263,15 @@ bool make_plan(int N, int Hg, int Wg, int Cg, int Ht, int Wt, int Ct, int R, int
     if (stride == 2 && ((Hg | Wg) & 1)) return false;
     const int nblk = R * S * (Cg / 32);
     if (nblk > MAX_BLK) return false;
-    if ((long)Ht * Wt < 64) return false;
-    if ((Wt & (Wt - 1)) == 0 && Wt >= 8) { pl->TW = Wt < CH ? Wt : CH; pl->TH = CH / pl->TW; }
+    const bool p2 = Ht > 0 && Wt > 0 && (Ht & (Ht - 1)) == 0 && (Wt & (Wt - 1)) == 0;
+    pl->TNB = 1;
+    if ((long)Ht * Wt < 64) {
+        if (!p2 || Ht * Wt < 8) return false;
+        pl->TW = Wt; pl->TH = Ht; pl->TNB = CH / (Ht * Wt);          // several whole images per 64-pixel chunk
+    } else if ((Wt & (Wt - 1)) == 0 && Wt >= 8) { pl->TW = Wt < CH ? Wt : CH; pl->TH = CH / pl->TW; }
     else { pl->TW = 8; pl->TH = 8; }
     pl->tiles_w = g2_cdiv(Wt, pl->TW); pl->tiles_h = g2_cdiv(Ht, pl->TH);
-    pl->chunks = N * pl->tiles_h * pl->tiles_w;
+    pl->chunks = g2_cdiv(N, pl->TNB) * pl->tiles_h * pl->tiles_w;
     pl->ngroups = (nblk + 3) / 4;
     const int max_gpc = 512 / Ct;
     pl->grid_y = g2_cdiv(pl->ngroups, max_gpc);
@@ -305,7 +309,7 @@ int g2_conv_wgrad_tf32(const float* g, const float* t, float* dw, float* ws, int
     memset(&maps, 0, sizeof(maps));
     P p;
     memset(&p, 0, sizeof(p));
-    p.ws = ws; p.N = N; p.Ht = Ht; p.Wt = Wt; p.TH = pl.TH; p.TW = pl.TW; p.tiles_h = pl.tiles_h; p.tiles_w = pl.tiles_w;
+    p.ws = ws; p.N = N; p.Ht = Ht; p.Wt = Wt; p.TH = pl.TH; p.TW = pl.TW; p.TNB = pl.TNB; p.tiles_h = pl.tiles_h; p.tiles_w = pl.tiles_w;
     p.chunks_total = pl.chunks; p.chunks_per_cta = pl.cpc; p.Cg = Cg; p.Ct = Ct; p.ntaps = R * S;
     p.groups_per_cta = pl.gpc;
     for (int r = 0; r < R; ++r)
@@ -321,7 +325,7 @@ int g2_conv_wgrad_tf32(const float* g, const float* t, float* dw, float* ws, int
     for (int tap = 0; tap < R * S; ++tap)
         for (int cb = 0; cb < Cg / 32; ++cb) { p.blk_tap[nb] = (short)tap; p.blk_cb[nb] = (short)cb; ++nb; }
     p.nblk = nb;
-    const cuuint32_t box[4] = {32, (cuuint32_t)pl.TW, (cuuint32_t)pl.TH, 1};
+    const cuuint32_t box[4] = {32, (cuuint32_t)pl.TW, (cuuint32_t)pl.TH, (cuuint32_t)pl.TNB};
     {
         const cuuint64_t dims[4] = {(cuuint64_t)Ct, (cuuint64_t)Wt, (cuuint64_t)Ht, (cuuint64_t)N};
         const cuuint64_t str[3] = {(cuuint64_t)Ct * 4, (cuuint64_t)Wt * Ct * 4, (cuuint64_t)Ht * Wt * Ct * 4};

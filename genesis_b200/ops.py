@@ -513,7 +513,7 @@ class _Mixture(Function):
         recon = torch.empty_like(x)
         lse = torch.empty_like(x)
         lm_out = torch.empty_like(lm) if softmax else None
-        _call('g2_mixture_fwd_f32', x, xr, lm, std, err, recon, lse, lm_out, K, B, P, 1 if softmax else 0)
+        _call('g2_mixture_fwd_f32', x, xr, lm, std, err, recon, lse, lm_out, K, B, P, 1 if softmax else 0, 3, 1)
         ctx.save_for_backward(x, xr, lm_out if softmax else lm, std, lse)
         ctx.softmax = softmax
         if not softmax:
@@ -528,9 +528,151 @@ class _Mixture(Function):
         P = x.shape[2] * x.shape[3]
         dxr = torch.empty_like(xr)
         dlm = torch.empty_like(lm)
-        _call('g2_mixture_bwd_f32', x, xr, lm, std, lse, _c(gerr), dxr, dlm, K, B, P, 1 if ctx.softmax else 0)
+        _call('g2_mixture_bwd_f32', x, xr, lm, std, lse, _c(gerr), dxr, dlm, K, B, P, 1 if ctx.softmax else 0, 3, 1, 1)
         return None, dxr, dlm, None, None
 
 
 def mixture_nll(x, xr, lm, std, softmax=False):
     return _Mixture.apply(x, xr, lm, std, softmax)
+
+
+class _MixturePacked(Function):
+    """Mixture likelihood on a packed decoder output dec [K,B,4,H,W] (planes 0-2 = x_r, plane 3 = mask logit).
+    mode 'softmax': masks = log_softmax over K of plane 3 (GENESIS-V2, genesisv2_config.py:213-223); gradients flow to
+    all 4 planes.  mode 'given': masks = lm [K,B,1,H,W] (MONet, monet_config.py:92-105); gradients flow to planes 0-2
+    and to lm, plane 3 gets zero here (its gradient comes from the mask KL)."""
+
+    @staticmethod
+    def forward(ctx, x, dec, lm, std, softmax):
+        x, dec, std = _c(x), _c(dec), _c(std)
+        K, B = dec.shape[0], dec.shape[1]
+        P = x.shape[2] * x.shape[3]
+        err = _new(x, B)
+        recon = torch.empty_like(x)
+        lse = torch.empty_like(x)
+        if softmax:
+            lm_out = _new(x, K, B, 1, x.shape[2], x.shape[3])
+            _call('g2_mixture_fwd_f32', x, dec, dec.data_ptr() + 12 * P, std, err, recon, lse, lm_out, K, B, P, 1, 4, 4)
+            ctx.save_for_backward(x, dec, lm_out, std, lse)
+        else:
+            lm = _c(lm)
+            lm_out = _new(x, 0)
+            _call('g2_mixture_fwd_f32', x, dec, lm, std, err, recon, lse, None, K, B, P, 0, 4, 1)
+            ctx.save_for_backward(x, dec, lm, std, lse)
+        ctx.softmax = softmax
+        ctx.mark_non_differentiable(recon, lm_out)
+        return err, recon, lm_out
+
+    @staticmethod
+    def backward(ctx, gerr, _grecon, _glm):
+        x, dec, lm, std, lse = ctx.saved_tensors
+        K, B = dec.shape[0], dec.shape[1]
+        P = x.shape[2] * x.shape[3]
+        if ctx.softmax:
+            ddec = torch.empty_like(dec)
+            _call('g2_mixture_bwd_f32', x, dec, lm, std, lse, _c(gerr), ddec, ddec.data_ptr() + 12 * P, K, B, P, 1, 4, 1, 4)
+            return None, ddec, None, None, None
+        ddec = torch.zeros_like(dec)
+        dlm = torch.empty_like(lm)
+        _call('g2_mixture_bwd_f32', x, dec, lm, std, lse, _c(gerr), ddec, dlm, K, B, P, 0, 4, 1, 1)
+        return None, ddec, dlm, None, None
+
+
+def mixture_nll_packed(x, dec, lm, std, softmax):
+    return _MixturePacked.apply(x, dec, lm, std, softmax)
+
+
+# ----------------------------------------------------------------------------------------- UNet resampling
+class _Resample(Function):
+    @staticmethod
+    def forward(ctx, x, up):
+        x = _c(x)
+        N, H, W, C = x.shape
+        Ho, Wo = (2 * H, 2 * W) if up else (H // 2, W // 2)
+        y = _new(x, N, Ho, Wo, C)
+        _call('g2_resample_f32', x, y, N, Ho, Wo, C, 1 if up else 0)
+        ctx.up = up
+        ctx.in_hw = (H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        N, _, _, C = dy.shape
+        H, W = ctx.in_hw
+        dx = _new(dy, N, H, W, C)
+        _call('g2_resample_f32', dy, dx, N, H, W, C, 3 if ctx.up else 2)
+        return dx, None
+
+
+def down2(x):
+    """F.interpolate(scale_factor=0.5, mode='nearest') on NHWC (reference unet.py:77-78)."""
+    return _Resample.apply(x, False)
+
+
+def up2(x):
+    """F.interpolate(scale_factor=2.0, mode='nearest') on NHWC (reference unet.py:88-89)."""
+    return _Resample.apply(x, True)
+
+
+# ----------------------------------------------------------------------------------------- IC-SBP
+class _ICSBP(Function):
+    """colour [B,H,W,8] NHWC, u [B,1,H,W], log_sigma [] -> log_m [K,B,1,H,W], log_s [K,B,1,H,W], seed_idx [K-1,B]."""
+
+    @staticmethod
+    def forward(ctx, colour, u, log_sigma, K):
+        colour, u = _c(colour), _c(u)
+        B, H, W, CD = colour.shape
+        P = H * W
+        log_m = _new(colour, K, B, 1, H, W)
+        log_s = _new(colour, K, B, 1, H, W)
+        idx = torch.empty((K - 1, B), device=colour.device, dtype=torch.int32)
+        ls = log_sigma.detach().reshape(1).float().contiguous()
+        _call('g2_icsbp_fwd_f32', colour, u, ls, log_m, log_s, idx, B, P, K, CD)
+        ctx.save_for_backward(colour, ls, idx)
+        ctx.K = K
+        ctx.mark_non_differentiable(log_s, idx)
+        return log_m, log_s, idx
+
+    @staticmethod
+    def backward(ctx, dlog_m, _dls, _didx):
+        colour, ls, idx = ctx.saved_tensors
+        B, H, W, CD = colour.shape
+        dcol = torch.empty_like(colour)
+        dsig = _new(colour, B)
+        _call('g2_icsbp_bwd_f32', colour, ls, idx, _c(dlog_m), dcol, dsig, B, H * W, ctx.K, CD)
+        return dcol, None, dsig.sum().reshape(()), None
+
+
+def icsbp(colour, u, log_sigma, K):
+    return _ICSBP.apply(colour, u, log_sigma, K)
+
+
+# ----------------------------------------------------------------------------------------- masked pooling
+class _MaskedPool(Function):
+    """f [B,H,W,C] NHWC, log_m [K,B,1,H,W] -> num [K,B,C] = sum_p m f, msum [K,B] = sum_p m."""
+
+    @staticmethod
+    def forward(ctx, f, log_m):
+        f, log_m = _c(f), _c(log_m)
+        B, H, W, C = f.shape
+        K = log_m.shape[0]
+        num = _new(f, K, B, C)
+        msum = _new(f, K, B)
+        _call('g2_masked_pool_fwd_f32', f, log_m, num, msum, B, H * W, C, K)
+        ctx.save_for_backward(f, log_m)
+        return num, msum
+
+    @staticmethod
+    def backward(ctx, dnum, dmsum):
+        f, log_m = ctx.saved_tensors
+        B, H, W, C = f.shape
+        K = log_m.shape[0]
+        df = torch.empty_like(f)
+        dlm = torch.empty_like(log_m)
+        _call('g2_masked_pool_bwd_f32', f, log_m, _c(dnum), _c(dmsum), df, dlm, B, H * W, C, K)
+        return df, dlm
+
+
+def masked_pool(f, log_m):
+    return _MaskedPool.apply(f, log_m)

@@ -114,6 +114,22 @@ int g2_act_bwd_f32(const float* dout, const float* out, float* dpre, long total,
 int g2_seg_colsum_f32(const float* x, float* out, int N, int P, int C, g2_stream_t stream);
 int g2_sum_dim0_f32(const float* x, float* out, int N, long J, g2_stream_t stream);
 
+/* ---- GENESIS-V2 / MONet specific (v2.cu) -----------------------------------------------------------
+ * nearest x0.5 / x2 resampling of modules/unet.py:77-78,88-89 (modes 0,1) and their adjoints (modes 2,3);
+ * Ho, Wo are the OUTPUT sizes. */
+int g2_resample_f32(const float* x, float* y, long N, int Ho, int Wo, int C, int mode, g2_stream_t stream);
+/* InstanceColouringSBP.forward, gaussian kernel, modules/attention.py:177-223: one CTA per image loops the K-1
+ * steps (argmax seed -> distance -> exp -> clamp -> log scan).  colour [B,P,8] NHWC, u [B,P]. */
+int g2_icsbp_fwd_f32(const float* colour, const float* u, const float* log_sigma, float* log_m, float* log_s,
+                     int* seed_idx, int B, int P, int K, int colour_dim, g2_stream_t stream);
+int g2_icsbp_bwd_f32(const float* colour, const float* log_sigma, const int* seed_idx, const float* dlog_m,
+                     float* dcolour, float* dlog_sigma_b, int B, int P, int K, int colour_dim, g2_stream_t stream);
+/* masked feature pooling of models/genesisv2_config.py:147-152: num[k,b,c] = sum_p m_k f, msum[k,b] = sum_p m_k */
+int g2_masked_pool_fwd_f32(const float* f, const float* log_m, float* num, float* msum, int B, int P, int C, int K,
+                           g2_stream_t stream);
+int g2_masked_pool_bwd_f32(const float* f, const float* log_m, const float* dnum, const float* dmsum, float* df,
+                           float* dlog_m, int B, int P, int C, int K, g2_stream_t stream);
+
 /* ---- decoder head + mixture likelihood (loss.cu) ---------------------------------------------------
  * out1x1: final 1x1 conv (+ sigmoid on the first nsig channels) writing NCHW planes:
  * modules/decoders.py:31, modules/component_vae.py:89-93, third_party/sylvester/VAE.py:121,
@@ -125,11 +141,13 @@ int g2_out1x1_bwd_f32(const float* dout, const float* out, const float* w, float
 /* Genesis.x_loss + recon (+ log-softmax of mask logits): models/genesis_config.py:188-190,273-286,
  * models/monet_config.py:136-140, models/genesisv2_config.py:213-223. */
 int g2_mixture_fwd_f32(const float* x, const float* xr, const float* lm, const float* stdv, float* err,
-                       float* recon, float* lse, float* lm_out, int K, int B, int P, int softmax,
-                       g2_stream_t stream);
+                       float* recon, float* lse, float* lm_out, int K, int B, int P, int softmax, int xr_cs,
+                       int lm_cs, g2_stream_t stream);
 int g2_mixture_bwd_f32(const float* x, const float* xr, const float* lm, const float* stdv, const float* lse,
-                       const float* gerr, float* dxr, float* dlm, int K, int B, int P, int softmax,
-                       g2_stream_t stream);
+                       const float* gerr, float* dxr, float* dlm, int K, int B, int P, int softmax, int xr_cs,
+                       int lm_cs, int dlm_cs, g2_stream_t stream);
+/* xr_cs / lm_cs / dlm_cs: channels per (slot,image) in the xr / lm / dlm tensors -- 3,1,1 for separate tensors, 4,4,4
+ * when x_r and the mask logit are the 4 planes of one decoder output [K,B,4,P] (lm = dec + 3P). */
 
 /* ---- TF32 tensor-core implicit GEMM: tcgen05.mma + TMEM + TMA (igemm_tc.cu) -------------------------
  * Same call sites as g2_conv_igemm_f32 / g2_gemm_f32, for the shapes that fit the 128 x {32,64,128} UMMA

@@ -63,6 +63,13 @@ CASES = [  # mode, N, H, W, Ci, Co, R, stride, pad
     (1, 2, 32, 32, 32, 64, 5, 2, 2),
     (1, 2, 32, 32, 64, 64, 5, 2, 2),
     (1, 2, 32, 32, 32, 32, 3, 2, 1),
+    (0, 5, 8, 8, 64, 64, 3, 1, 1),         # small maps: several images per 128-pixel tile
+    (0, 11, 4, 4, 128, 128, 3, 1, 1),
+    (0, 6, 16, 16, 32, 64, 3, 2, 1),       # -> 8x8
+    (1, 7, 4, 4, 128, 64, 5, 2, 2),        # GENESIS-V2 decoder layer 1 (66 -> 128 padded channels), 4x4 class grid
+    (1, 5, 8, 8, 64, 64, 5, 2, 2),
+    (0, 3, 72, 72, 32, 64, 5, 1, 2),       # non power-of-two width with padding: 8x16 tiles
+    (1, 2, 68, 68, 32, 32, 3, 1, 0),       # data-gradient of a VALID conv (70x70 output)
 ]
 
 
@@ -82,8 +89,8 @@ def test_unsupported_shapes_are_reported():
     from genesis_b200 import _lib
     lib = _lib.lib()
     assert lib.query('g2_conv_tf32_supported', 2, 64, 64, 3, 64, 64, 64, 5, 5, 1, 2, 0) == 0      # Ci = 3
-    assert lib.query('g2_conv_tf32_supported', 2, 8, 8, 64, 16, 16, 64, 5, 5, 2, 2, 1) == 0       # 8x8 class grid
-    assert lib.query('g2_conv_tf32_supported', 2, 4, 4, 64, 4, 4, 64, 3, 3, 1, 1, 0) == 0
+    assert lib.query('g2_conv_tf32_supported', 2, 6, 6, 64, 6, 6, 64, 3, 3, 1, 1, 0) == 0         # 6x6 < 128 pixels, not 2^k
+    assert lib.query('g2_conv_tf32_supported', 2, 2, 2, 64, 2, 2, 64, 3, 3, 1, 1, 0) == 0
 
 
 @pytest.mark.parametrize('M,N,K', [(64, 512, 16384), (320, 32768, 64), (448, 256, 4096), (100, 128, 96), (320, 256, 1024)])
@@ -114,6 +121,10 @@ WGRAD_CASES = [  # kind, N, H, W, Ci, Co, R, stride, pad   (conv: x[N,H,W,Ci] ->
     ('convT', 2, 16, 16, 64, 128, 5, 1, 2),
     ('convT', 2, 16, 16, 64, 64, 5, 2, 2),     # stride 2: parity planes of dy
     ('convT', 2, 32, 32, 32, 64, 5, 2, 2),
+    ('conv', 9, 4, 4, 128, 128, 3, 1, 1),     # small maps: several images per chunk
+    ('conv', 5, 16, 16, 32, 64, 3, 2, 1),
+    ('convT', 6, 4, 4, 128, 64, 5, 2, 2),    # GENESIS-V2 decoder layer 1 (66 -> 128 padded channels)
+    ('conv', 3, 8, 8, 64, 64, 3, 1, 1),
 ]
 
 
