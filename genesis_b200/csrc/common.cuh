@@ -23,7 +23,7 @@ enum {
 // norm modes
 enum { G2_NORM_NONE = 0, G2_NORM_BATCH = 1, G2_NORM_INSTANCE = 2, G2_NORM_GROUP = 3 };
 // norm post-ops
-enum { G2_POST_GATE = 0, G2_POST_RELU = 1 };
+enum { G2_POST_GATE = 0, G2_POST_RELU = 1, G2_POST_NONE = 2 };
 
 static inline int g2_cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 

@@ -220,6 +220,98 @@ __global__ void __launch_bounds__(256) mixture_bwd_kernel(const MixBP p) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------ MONet mask KL
+// MONet.kl_m_loss (reference models/monet_config.py:157-170) fused with get_mask_recon_stack(softmax, log=True)
+// (:136-140):   q_k = max(exp(lm_k), 1e-5) / sum_j max(exp(lm_j), 1e-5)            (torch Categorical renormalises)
+//               lr_k = logit_k - logsumexp_j logit_j  (written to lmr);  p_k = max(exp(lr_k), 1e-5) / sum_j (...)
+//               kl_b = sum_pixels sum_k q_k (log q_k - log p_k)
+// lm [K,B,lm_cs,P] (plane 0), logits [K,B,lg_cs,P] (plane 0 of the given base pointer).  One thread = one pixel quad.
+struct MklP {
+    const float* lm; const float* lg; float* lmr; float* kl; const float* gkl; float* dlm; float* dlg;
+    int K, B, P, lm_cs, lg_cs, dlm_cs, dlg_cs, accumulate_dlm;
+};
+constexpr float MKL_FLOOR = 1e-5f;
+constexpr float MKL_EPS = 1.1920928955078125e-07f;   // torch.finfo(float32).eps used by probs_to_logits
+
+template <bool BWD>
+__global__ void __launch_bounds__(256) mask_kl_kernel(const MklP p) {
+    const int b = blockIdx.y;
+    const int i4 = blockIdx.x * blockDim.x + threadIdx.x;
+    float part = 0.f;
+    if (i4 < p.P / 4) {
+        const long off = (long)i4 * 4;
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, se[4] = {0.f, 0.f, 0.f, 0.f}, Q[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < p.K; ++k) {
+            const float4 l4 = g2_ldg4(p.lg + ((long)k * p.B + b) * p.lg_cs * p.P + off);
+            const float4 m4 = g2_ldg4(p.lm + ((long)k * p.B + b) * p.lm_cs * p.P + off);
+            const float l[4] = {l4.x, l4.y, l4.z, l4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (l[j] > mx[j]) { se[j] = se[j] * expf(mx[j] - l[j]) + 1.f; mx[j] = l[j]; } else se[j] += expf(l[j] - mx[j]);
+                Q[j] += fmaxf(expf(m[j]), MKL_FLOOR);
+            }
+        }
+        float lse[4], Pn[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) lse[j] = mx[j] + logf(se[j]);
+        for (int k = 0; k < p.K; ++k) {
+            const float4 l4 = g2_ldg4(p.lg + ((long)k * p.B + b) * p.lg_cs * p.P + off);
+            const float lr[4] = {l4.x - lse[0], l4.y - lse[1], l4.z - lse[2], l4.w - lse[3]};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Pn[j] += fmaxf(expf(lr[j]), MKL_FLOOR);
+            if (!BWD) *reinterpret_cast<float4*>(p.lmr + ((long)k * p.B + b) * p.P + off) = make_float4(lr[0], lr[1], lr[2], lr[3]);
+        }
+        float f[4] = {0.f, 0.f, 0.f, 0.f}, gs[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < p.K; ++k) {
+            const float4 l4 = g2_ldg4(p.lg + ((long)k * p.B + b) * p.lg_cs * p.P + off);
+            const float4 m4 = g2_ldg4(p.lm + ((long)k * p.B + b) * p.lm_cs * p.P + off);
+            const float l[4] = {l4.x, l4.y, l4.z, l4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float qn = fmaxf(expf(m[j]), MKL_FLOOR) / Q[j];
+                const float er = expf(l[j] - lse[j]);
+                const float pn = fmaxf(er, MKL_FLOOR) / Pn[j];
+                const float d = logf(fminf(fmaxf(qn, MKL_EPS), 1.f - MKL_EPS)) - logf(fminf(fmaxf(pn, MKL_EPS), 1.f - MKL_EPS));
+                f[j] += qn * d;
+                if (BWD) gs[j] += er > MKL_FLOOR ? er * (1.f - qn / pn) / Pn[j] : 0.f;     // sum_j d f / d lr_j
+            }
+        }
+        if (!BWD) {
+            part = (f[0] + f[1]) + (f[2] + f[3]);
+        } else {
+            const float g = __ldg(p.gkl + b);
+            for (int k = 0; k < p.K; ++k) {
+                const float4 l4 = g2_ldg4(p.lg + ((long)k * p.B + b) * p.lg_cs * p.P + off);
+                const float4 m4 = g2_ldg4(p.lm + ((long)k * p.B + b) * p.lm_cs * p.P + off);
+                const float l[4] = {l4.x, l4.y, l4.z, l4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w};
+                float dm[4], dl[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float em = expf(m[j]);
+                    const float qn = fmaxf(em, MKL_FLOOR) / Q[j];
+                    const float er = expf(l[j] - lse[j]);
+                    const float pn = fmaxf(er, MKL_FLOOR) / Pn[j];
+                    const float d = logf(fminf(fmaxf(qn, MKL_EPS), 1.f - MKL_EPS)) - logf(fminf(fmaxf(pn, MKL_EPS), 1.f - MKL_EPS));
+                    dm[j] = em > MKL_FLOOR ? g * em * (d - f[j]) / Q[j] : 0.f;
+                    const float glr = er > MKL_FLOOR ? er * (1.f - qn / pn) / Pn[j] : 0.f;
+                    dl[j] = g * (glr - er * gs[j]);
+                }
+                float* dmp = p.dlm + ((long)k * p.B + b) * p.dlm_cs * p.P + off;
+                float4 o = make_float4(dm[0], dm[1], dm[2], dm[3]);
+                if (p.accumulate_dlm) { const float4 a = *reinterpret_cast<const float4*>(dmp); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+                *reinterpret_cast<float4*>(dmp) = o;
+                *reinterpret_cast<float4*>(p.dlg + ((long)k * p.B + b) * p.dlg_cs * p.P + off) = make_float4(dl[0], dl[1], dl[2], dl[3]);
+            }
+        }
+    }
+    if (!BWD) {
+        __shared__ float red[32];
+        part = g2_block_sum(part, red);
+        if (threadIdx.x == 0) atomicAdd(p.kl + b, part);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -260,6 +352,27 @@ int g2_mixture_bwd_f32(const float* x, const float* xr, const float* lm, const f
     MixBP p{x, xr, lm, stdv, lse, gerr, dxr, dlm, K, B, P, softmax, xr_cs, lm_cs, dlm_cs};
     dim3 grid(g2_cdiv(P / 4, 256), B);
     mixture_bwd_kernel<<<grid, 256, 0, stream>>>(p);
+    G2_LAUNCH_RET();
+}
+
+int g2_mask_kl_fwd_f32(const float* lm, const float* logits, float* lmr, float* kl, int K, int B, int P, int lm_cs, int lg_cs,
+                       cudaStream_t stream) {
+    G2_CHECK_ARG(lm && logits && lmr && kl && K >= 1 && B > 0 && P > 0 && (P % 4) == 0 && lm_cs >= 1 && lg_cs >= 1);
+    cudaError_t e = cudaMemsetAsync(kl, 0, sizeof(float) * (size_t)B, stream);
+    if (e != cudaSuccess) return (int)e;
+    MklP p{lm, logits, lmr, kl, nullptr, nullptr, nullptr, K, B, P, lm_cs, lg_cs, 1, 1, 0};
+    dim3 grid(g2_cdiv(P / 4, 256), B);
+    mask_kl_kernel<false><<<grid, 256, 0, stream>>>(p);
+    G2_LAUNCH_RET();
+}
+
+int g2_mask_kl_bwd_f32(const float* lm, const float* logits, const float* gkl, float* dlm, float* dlogits, int K, int B, int P,
+                       int lm_cs, int lg_cs, int dlm_cs, int dlg_cs, int accumulate_dlm, cudaStream_t stream) {
+    G2_CHECK_ARG(lm && logits && gkl && dlm && dlogits && K >= 1 && B > 0 && P > 0 && (P % 4) == 0);
+    G2_CHECK_ARG(lm_cs >= 1 && lg_cs >= 1 && dlm_cs >= 1 && dlg_cs >= 1);
+    MklP p{lm, logits, nullptr, nullptr, gkl, dlm, dlogits, K, B, P, lm_cs, lg_cs, dlm_cs, dlg_cs, accumulate_dlm};
+    dim3 grid(g2_cdiv(P / 4, 256), B);
+    mask_kl_kernel<true><<<grid, 256, 0, stream>>>(p);
     G2_LAUNCH_RET();
 }
 

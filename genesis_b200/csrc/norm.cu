@@ -124,8 +124,10 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict
             g.x = fmaf(ag.x, g.x, bg.x); g.y = fmaf(ag.y, g.y, bg.y); g.z = fmaf(ag.z, g.z, bg.z); g.w = fmaf(ag.w, g.w, bg.w);
             o.x = h.x * g2_sigmoidf(g.x); o.y = h.y * g2_sigmoidf(g.y);
             o.z = h.z * g2_sigmoidf(g.z); o.w = h.w * g2_sigmoidf(g.w);
-        } else {
+        } else if (POST == G2_POST_RELU) {
             o.x = fmaxf(h.x, 0.f); o.y = fmaxf(h.y, 0.f); o.z = fmaxf(h.z, 0.f); o.w = fmaxf(h.w, 0.f);
+        } else {
+            o = h;
         }
         *reinterpret_cast<float4*>(out + row * C + c) = o;
     }
@@ -149,8 +151,11 @@ __device__ __forceinline__ void post_grad(const float* __restrict__ yrow, const 
         dh = make_float4(d.x * s0, d.y * s1, d.z * s2, d.w * s3);
         dg = make_float4(d.x * h.x * s0 * (1.f - s0), d.y * h.y * s1 * (1.f - s1),
                          d.z * h.z * s2 * (1.f - s2), d.w * h.w * s3 * (1.f - s3));
-    } else {
+    } else if (POST == G2_POST_RELU) {
         dh = make_float4(h.x > 0.f ? d.x : 0.f, h.y > 0.f ? d.y : 0.f, h.z > 0.f ? d.z : 0.f, h.w > 0.f ? d.w : 0.f);
+        dg = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+        dh = d;
         dg = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
@@ -348,6 +353,7 @@ int g2_norm_apply_f32(const float* y, const float* scale, const float* shift, fl
     const long quads = (long)N * HW * (C / 4);
     if (post == G2_POST_GATE) norm_apply_kernel<G2_POST_GATE><<<ew_blocks(quads), 256, 0, stream>>>(y, scale, shift, out, quads, HW, C, sn);
     else if (post == G2_POST_RELU) norm_apply_kernel<G2_POST_RELU><<<ew_blocks(quads), 256, 0, stream>>>(y, scale, shift, out, quads, HW, C, sn);
+    else if (post == G2_POST_NONE) norm_apply_kernel<G2_POST_NONE><<<ew_blocks(quads), 256, 0, stream>>>(y, scale, shift, out, quads, HW, C, sn);
     else return G2_ERR_ARG;
     G2_LAUNCH_RET();
 }
@@ -364,6 +370,7 @@ int g2_norm_bwd_stats_f32(const float* y, const float* dout, const float* scale,
     dim3 grid(g2_cdiv(HW, rpb), N);
     if (post == G2_POST_GATE) norm_bwd_stats_kernel<G2_POST_GATE><<<grid, 256, 0, stream>>>(y, dout, scale, shift, mean, rstd, sums2, HW, C, sn, rpb);
     else if (post == G2_POST_RELU) norm_bwd_stats_kernel<G2_POST_RELU><<<grid, 256, 0, stream>>>(y, dout, scale, shift, mean, rstd, sums2, HW, C, sn, rpb);
+    else if (post == G2_POST_NONE) norm_bwd_stats_kernel<G2_POST_NONE><<<grid, 256, 0, stream>>>(y, dout, scale, shift, mean, rstd, sums2, HW, C, sn, rpb);
     else return G2_ERR_ARG;
     G2_LAUNCH_RET();
 }
@@ -388,6 +395,7 @@ int g2_norm_bwd_apply_f32(const float* y, const float* dout, const float* scale,
     const long quads = (long)N * HW * (C / 4);
     if (post == G2_POST_GATE) norm_bwd_apply_kernel<G2_POST_GATE><<<ew_blocks(quads), 256, 0, stream>>>(y, dout, scale, shift, mean, rstd, m1, m2, dy, quads, HW, C, sn);
     else if (post == G2_POST_RELU) norm_bwd_apply_kernel<G2_POST_RELU><<<ew_blocks(quads), 256, 0, stream>>>(y, dout, scale, shift, mean, rstd, m1, m2, dy, quads, HW, C, sn);
+    else if (post == G2_POST_NONE) norm_bwd_apply_kernel<G2_POST_NONE><<<ew_blocks(quads), 256, 0, stream>>>(y, dout, scale, shift, mean, rstd, m1, m2, dy, quads, HW, C, sn);
     else return G2_ERR_ARG;
     G2_LAUNCH_RET();
 }

@@ -320,3 +320,48 @@ def broadcast_decode(dec, z, act, nsig):
         h = ops.conv2d(h, c.weight, c.bias, 1, 0, act)
     last = dec.seq[1 + 2 * L]
     return ops.out1x1(h, last.weight, last.bias, nsig)
+
+
+# ------------------------------------------------------------------------------------------- UNet
+def conv_norm_relu(block, h, norm):
+    """ConvINReLU / ConvGNReLU (reference modules/blocks.py:151-165) on NHWC h: 3x3 p1 conv without bias, then the
+    per-sample norm fused with ReLU."""
+    conv, nrm = block[0], block[1]
+    y = ops.conv2d(h, pad_cin(conv.weight, h.shape[3]), None, 1, 1)
+    if norm == 'in':
+        return ops.norm_post(y, nrm.weight, nrm.bias, mode=ops.NORM_INSTANCE, post=ops.POST_RELU, eps=nrm.eps)
+    return ops.norm_post(y, nrm.weight, nrm.bias, mode=ops.NORM_GROUP, groups=nrm.num_groups, post=ops.POST_RELU,
+                         eps=nrm.eps)
+
+
+def unet_forward(unet, h):
+    """UNet.forward without final_conv (reference modules/unet.py:69-90) on NHWC h (channels may be zero-padded).
+    Skips are taken before the nearest x0.5; the bottleneck MLP sees the NCHW flattening of the reference (its
+    weights are re-indexed to the NHWC order instead of transposing the activations)."""
+    nb, norm = unet.num_blocks, unet.norm
+    skip = []
+    for i in range(nb):
+        h = conv_norm_relu(unet.down[i], h, norm)
+        skip.append(h)
+        if i < nb - 1:
+            h = ops.down2(h)
+    N, f, _, c = h.shape
+    m = unet.mlp
+    w1 = m[1].weight.view(-1, c, f, f).permute(0, 2, 3, 1).reshape(m[1].weight.shape[0], -1)
+    u = ops.linear(h.reshape(N, -1), w1, m[1].bias, 'relu')
+    u = ops.linear(u, m[3].weight, m[3].bias, 'relu')
+    w5 = m[5].weight.view(c, f, f, -1).permute(1, 2, 0, 3).reshape(c * f * f, -1)
+    b5 = m[5].bias.view(c, f, f).permute(1, 2, 0).reshape(-1)
+    u = ops.linear(u, w5, b5, 'relu').view(N, f, f, c)
+    for i in range(nb):
+        u = conv_norm_relu(unet.up[i], torch.cat([u, skip[-1 - i]], dim=3), norm)
+        if i < nb - 1:
+            u = ops.up2(u)
+    return u
+
+
+def layer_norm(x, ln):
+    """nn.LayerNorm over the last dim of x [N,C] = a one-group, one-pixel GroupNorm."""
+    N, C = x.shape
+    return ops.norm_post(x.view(N, 1, 1, C), ln.weight, ln.bias, mode=ops.NORM_GROUP, groups=1, post=ops.POST_NONE,
+                         eps=ln.eps).view(N, C)

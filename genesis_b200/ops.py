@@ -11,7 +11,7 @@ from . import _lib
 
 ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
 NORM_NONE, NORM_BATCH, NORM_INSTANCE, NORM_GROUP = 0, 1, 2, 3
-POST_GATE, POST_RELU = 0, 1
+POST_GATE, POST_RELU, POST_NONE = 0, 1, 2
 ACTS = {None: 0, 'none': 0, 'relu': 1, 'elu': 2}
 
 
@@ -631,6 +631,7 @@ class _ICSBP(Function):
         _call('g2_icsbp_fwd_f32', colour, u, ls, log_m, log_s, idx, B, P, K, CD)
         ctx.save_for_backward(colour, ls, idx)
         ctx.K = K
+        ctx.ls_dtype = log_sigma.dtype
         ctx.mark_non_differentiable(log_s, idx)
         return log_m, log_s, idx
 
@@ -641,7 +642,7 @@ class _ICSBP(Function):
         dcol = torch.empty_like(colour)
         dsig = _new(colour, B)
         _call('g2_icsbp_bwd_f32', colour, ls, idx, _c(dlog_m), dcol, dsig, B, H * W, ctx.K, CD)
-        return dcol, None, dsig.sum().reshape(()), None
+        return dcol, None, dsig.sum().reshape(()).to(ctx.ls_dtype), None
 
 
 def icsbp(colour, u, log_sigma, K):
@@ -676,3 +677,40 @@ class _MaskedPool(Function):
 
 def masked_pool(f, log_m):
     return _MaskedPool.apply(f, log_m)
+
+
+# ----------------------------------------------------------------------------------------- MONet loss head
+class _MonetLoss(Function):
+    """MONet reconstruction + mask-KL terms on the packed decoder output (reference monet_config.py:85-107).
+    x [B,3,H,W]; dec [K,B,4,H,W] (planes 0-2 = x_r after the pixel-bound sigmoid, plane 3 = mask logits);
+    lm [K,B,1,H,W] inferred log masks; std [K].  Returns err [B], kl_m [B], recon, log_m_r [K,B,1,H,W]."""
+
+    @staticmethod
+    def forward(ctx, x, dec, lm, std):
+        x, dec, lm, std = _c(x), _c(dec), _c(lm), _c(std)
+        K, B = dec.shape[0], dec.shape[1]
+        P = x.shape[2] * x.shape[3]
+        err, kl = _new(x, B), _new(x, B)
+        recon, lse = torch.empty_like(x), torch.empty_like(x)
+        lmr = torch.empty_like(lm)
+        _call('g2_mixture_fwd_f32', x, dec, lm, std, err, recon, lse, None, K, B, P, 0, 4, 1)
+        _call('g2_mask_kl_fwd_f32', lm, dec.data_ptr() + 12 * P, lmr, kl, K, B, P, 1, 4)
+        ctx.save_for_backward(x, dec, lm, std, lse)
+        ctx.mark_non_differentiable(recon, lmr)
+        return err, kl, recon, lmr
+
+    @staticmethod
+    def backward(ctx, gerr, gkl, _grecon, _glmr):
+        x, dec, lm, std, lse = ctx.saved_tensors
+        K, B = dec.shape[0], dec.shape[1]
+        P = x.shape[2] * x.shape[3]
+        ddec = torch.empty_like(dec)
+        dlm = torch.empty_like(lm)
+        _call('g2_mixture_bwd_f32', x, dec, lm, std, lse, _c(gerr), ddec, dlm, K, B, P, 0, 4, 1, 1)
+        _call('g2_mask_kl_bwd_f32', lm, dec.data_ptr() + 12 * P, _c(gkl), dlm, ddec.data_ptr() + 12 * P, K, B, P,
+              1, 4, 1, 4, 1)
+        return None, ddec, dlm, None
+
+
+def monet_loss(x, dec, lm, std):
+    return _MonetLoss.apply(x, dec, lm, std)

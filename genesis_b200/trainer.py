@@ -77,7 +77,7 @@ class TrainStep(object):
             if key in losses and len(losses[key]):
                 kl = kl + torch.stack(list(losses[key]), dim=1).mean(0).sum()
         for key in ('kl_l', 'kl_m'):
-            if key in losses and torch.is_tensor(losses[key]) and losses[key].numel() > 1:
+            if key in losses and torch.is_tensor(losses[key]):
                 kl = kl + losses[key].mean(0)
         return err, kl
 

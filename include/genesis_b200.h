@@ -43,6 +43,7 @@ typedef struct CUstream_st* g2_stream_t; /* == cudaStream_t */
 #define G2_NORM_GROUP 3
 #define G2_POST_GATE 0
 #define G2_POST_RELU 1
+#define G2_POST_NONE 2 /* normalise only (LayerNorm of models/genesisv2_config.py:83) */
 
 int g2_abi_version(void);
 
@@ -148,6 +149,14 @@ int g2_mixture_bwd_f32(const float* x, const float* xr, const float* lm, const f
                        int lm_cs, int dlm_cs, g2_stream_t stream);
 /* xr_cs / lm_cs / dlm_cs: channels per (slot,image) in the xr / lm / dlm tensors -- 3,1,1 for separate tensors, 4,4,4
  * when x_r and the mask logit are the 4 planes of one decoder output [K,B,4,P] (lm = dec + 3P). */
+
+/* MONet.kl_m_loss fused with the log-softmax of the reconstructed mask logits: models/monet_config.py:136-140,157-170.
+ * lm [K,B,lm_cs,P] log masks (plane 0), logits [K,B,lg_cs,P] (plane 0 of the pointer given) -> lmr [K,B,P], kl [B].
+ * bwd: dlm (+= when accumulate_dlm) and dlogits get d(sum_b gkl_b kl_b). */
+int g2_mask_kl_fwd_f32(const float* lm, const float* logits, float* lmr, float* kl, int K, int B, int P, int lm_cs,
+                       int lg_cs, g2_stream_t stream);
+int g2_mask_kl_bwd_f32(const float* lm, const float* logits, const float* gkl, float* dlm, float* dlogits, int K, int B,
+                       int P, int lm_cs, int lg_cs, int dlm_cs, int dlg_cs, int accumulate_dlm, g2_stream_t stream);
 
 /* ---- TF32 tensor-core implicit GEMM: tcgen05.mma + TMEM + TMA (igemm_tc.cu) -------------------------
  * Same call sites as g2_conv_igemm_f32 / g2_gemm_f32, for the shapes that fit the 128 x {32,64,128} UMMA

@@ -44,7 +44,7 @@ def ref_total_loss(losses):
     for key in ('kl_l_k', 'kl_m_k'):
         if key in losses:
             tot = tot + torch.stack(list(losses[key]), 1).mean(0).sum()
-    if 'kl_m' in losses and torch.is_tensor(losses['kl_m']) and losses['kl_m'].numel() > 1:
+    if 'kl_m' in losses and torch.is_tensor(losses['kl_m']):
         tot = tot + losses['kl_m'].mean(0)
     return tot
 
@@ -79,7 +79,7 @@ def run_case(name, model, K, img, B, gen):
     for key in ('kl_l_k', 'kl_m_k'):
         if key in losses:
             g[key] = torch.stack(list(losses[key]), 0).detach().numpy()
-    if 'kl_m' in losses and torch.is_tensor(losses['kl_m']) and losses['kl_m'].numel() > 1:
+    if 'kl_m' in losses and torch.is_tensor(losses['kl_m']):
         g['kl_m'] = losses['kl_m'].detach().numpy()
     g['log_m_k'] = torch.stack(list(stats['log_m_k']), 0).detach().numpy()
     if 'log_m_r_k' in stats:

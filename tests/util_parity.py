@@ -13,7 +13,7 @@ def engine_total_loss(losses, beta=1.0):
     for key in ('kl_l_k', 'kl_m_k'):
         if key in losses and len(losses[key]):
             kl = kl + torch.stack(list(losses[key]), dim=1).mean(0).sum()
-    if 'kl_m' in losses and torch.is_tensor(losses['kl_m']) and losses['kl_m'].numel() > 1:
+    if 'kl_m' in losses and torch.is_tensor(losses['kl_m']):
         kl = kl + losses['kl_m'].mean(0)
     return loss + beta * kl
 
@@ -67,3 +67,16 @@ def compare_grads(model, P, tol, floor_frac=1e-4, skip=()):
 
 def make_tape(seed):
     return O.NoiseTape(seed=seed)
+
+
+def global_grad_rel_l2(model, P):
+    """|| g_engine - g_oracle || / || g_oracle || over the concatenation of all parameter gradients."""
+    num = den = 0.0
+    for name, p in model.named_parameters():
+        ref = P[name].grad
+        if ref is None:
+            continue
+        den += ref.double().pow(2).sum().item()
+        g = p.grad.detach().double().cpu() if p.grad is not None else torch.zeros_like(ref, dtype=torch.float64)
+        num += (g - ref.double()).pow(2).sum().item()
+    return (num / max(den, 1e-300)) ** 0.5
