@@ -22,8 +22,21 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 METRIC = 'images/sec fwd+bwd 64x64 K=5'
-K_SLOTS, IMG, B_PER_GPU = 5, 64, 64
-FWD_GFLOP_PER_IMG = 6.059          # SURVEY.md section 8d (hooks on the reference model, 2*MACs)
+# Headline workload = BASELINE.json configs[1] (c2).  --workload c3/c4/c5 time the other configs' per-GPU shapes
+# (extra measurements; the driver only runs the default).
+WORKLOADS = {   # name: (model, K, img, batch per GPU, generator, fwd GFLOP / image as the engine computes it: SURVEY.md 8d)
+    'c2': ('genesis', 5, 64, 64, 'multid', 6.059),
+    'c3': ('genesisv2', 7, 64, 128, 'stacks', 3.675),
+    'c4': ('genesisv2', 11, 64, 32, 'rooms', 4.801),
+    'c5': ('monet', 7, 128, 64, 'multid', 14.022),
+}
+MODEL, K_SLOTS, IMG, B_PER_GPU, GEN, FWD_GFLOP_PER_IMG = WORKLOADS['c2']
+
+
+def select_workload(name):
+    global MODEL, K_SLOTS, IMG, B_PER_GPU, GEN, FWD_GFLOP_PER_IMG, METRIC
+    MODEL, K_SLOTS, IMG, B_PER_GPU, GEN, FWD_GFLOP_PER_IMG = WORKLOADS[name]
+    METRIC = 'images/sec fwd+bwd %dx%d K=%d' % (IMG, IMG, K_SLOTS)
 
 
 def peaks():
@@ -69,11 +82,12 @@ class ClockSampler(threading.Thread):
 
 def synthetic_batches(n_batches, batch, seed):
     from oracle import synth    # test-infrastructure generator of dataset-shaped images (inputs only)
-    return [torch.from_numpy(synth.multid(batch, IMG, seed + i)[0]) for i in range(n_batches)]
+    return [torch.from_numpy(synth.GENERATORS[GEN](batch, IMG, seed + i)[0]) for i in range(n_batches)]
 
 
 def build_cfg():
-    from genesis_b200.model_configs import genesis_config as plugin
+    import importlib
+    plugin = importlib.import_module('genesis_b200.model_configs.%s_config' % MODEL)
     from forge import flags
     cfg = dict(flags.defaults())
     cfg.update(debug=False, multi_gpu=False, img_size=IMG, K_steps=K_SLOTS)
@@ -89,14 +103,14 @@ def cpu_port_step_fn(batch):
     torch.manual_seed(0)
     holder = plugin.load(cfg)
     P = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in holder.state_dict().items()}
-    ocfg = M.make_cfg('genesis', K_steps=K_SLOTS, img_size=IMG)
+    ocfg = M.make_cfg(MODEL, K_steps=K_SLOTS, img_size=IMG)
     xs = synthetic_batches(2, batch, 100)
 
     def step(i):
         for p in P.values():
             if p.is_floating_point() and p.grad is not None:
                 p.grad = None
-        out = M.genesis_forward(P, xs[i % len(xs)], O.NoiseTape(seed=i), ocfg, training=True)
+        out = M.FORWARD[MODEL](P, xs[i % len(xs)], O.NoiseTape(seed=i), ocfg, training=True)
         M.total_loss(out).backward()
         return float(out['err'].mean())
     return step
@@ -121,7 +135,7 @@ def run_reference_arm(args):
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'GENESIS K=5 64x64 fwd+bwd, CPU sample batch=%d per step (config B=64)' % sample_b},
+        'config': {'workload': '%s K=%d %dx%d fwd+bwd, CPU sample batch=%d per step (config B=%d)' % (MODEL, K_SLOTS, IMG, IMG, sample_b, B_PER_GPU)},
         'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
                          'sample': '%d steps x batch %d, torch %s CPU fp32, %d threads' % (args.steps, sample_b, torch.__version__, cores)},
         'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -242,13 +256,13 @@ def run_engine(args):
                 step(i + 1)
             dt = time.perf_counter() - t0
             cpu = {'value': sb * n_cpu / dt, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                   'sample': '1 warm-up + %d steps of batch %d (config batch is 64), oracle port, torch CPU fp32' % (n_cpu, sb)}
+                   'sample': '1 warm-up + %d steps of batch %d (config batch is %d), oracle port, torch CPU fp32' % (n_cpu, sb, B_PER_GPU)}
         imgs = B_PER_GPU * world * args.steps
         line = {
             'metric': METRIC, 'value': imgs / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(3, args.warmup), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'GENESIS K=5 64x64 Multi-dSprites-shaped, batch %d per GPU, fwd+bwd+allreduce+Adam+GECO' % B_PER_GPU,
+            'config': {'workload': '%s K=%d %dx%d %s-shaped synthetic, batch %d per GPU, fwd+bwd+allreduce+Adam+GECO' % (MODEL, K_SLOTS, IMG, IMG, GEN, B_PER_GPU),
                        'global_batch': B_PER_GPU * world, 'parallelism': 'dp%d' % world,
                        'l2': 'per-step working set (activations > 4 GB) exceeds the 126 MB L2; inputs rotate over %d batches' % n_in,
                        'step_tflops_algorithmic': step_tf, 'last_elbo': last, 'cuda_graph': graphed,
@@ -275,7 +289,9 @@ def main():
     ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
     ap.add_argument('--no-cpu-baseline', dest='no_cpu_baseline', action='store_true')
     ap.add_argument('--no-graph', dest='no_graph', action='store_true')
+    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    select_workload(args.workload)
     if args.impl == 'reference':
         run_reference_arm(args)
     else:

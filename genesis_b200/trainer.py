@@ -32,6 +32,47 @@ class GecoState(object):
         self.beta.copy_((torch.exp(rate * constraint) * self.beta).clamp(self.beta_min, self.beta_max))
 
 
+class FlatArena(object):
+    """Flat fp32 parameter and gradient arenas: [params | pad] and [grads | pad | err, kl, 0, 0].  Every parameter starts
+    on a 256-byte boundary; `p.data` / `p.grad` become views, so autograd accumulates straight into the arena and the
+    data-parallel exchange is one collective over `flat_g` (the 4 trailing floats carry the batch-mean err / kl so that
+    every rank updates GECO identically)."""
+    ALIGN = 64
+    TAIL = 4
+
+    def __init__(self, params):
+        dev = params[0].device
+        a = self.ALIGN
+        self.n_params = sum(p.numel() for p in params)
+        self.n_pad = sum((p.numel() + a - 1) // a * a for p in params)
+        self.flat_p = torch.zeros(self.n_pad, device=dev)
+        self.flat_g = torch.zeros(self.n_pad + self.TAIL, device=dev)
+        off = 0
+        for p in params:
+            k = p.numel()
+            self.flat_p[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[off:off + k].view_as(p)
+            p.grad = self.flat_g[off:off + k].view_as(p)
+            off += (k + a - 1) // a * a
+        self.tail = self.flat_g[self.n_pad:]
+
+    def exchange(self, err, kl, world):
+        """ONE all-reduce(sum) of gradients + (err, kl); returns the global-batch means of err and kl.  Gradients are left
+        as the SUM over ranks: the optimiser applies the 1/world scale."""
+        self.tail[0].copy_(err)
+        self.tail[1].copy_(kl)
+        if world > 1:
+            dist.all_reduce(self.flat_g)
+        return self.tail[0] / world, self.tail[1] / world
+
+
+def shard_batch(x, rank, world):
+    """Contiguous batch shard of rank `rank` (equal shards; the reference's DataParallel scatter, train.py:153-155)."""
+    assert x.shape[0] % world == 0, 'global batch must divide by the number of ranks'
+    per = x.shape[0] // world
+    return x[rank * per:(rank + 1) * per]
+
+
 class TrainStep(object):
     """step(x) = one optimisation step on the local shard `x` (float32 [B,3,H,W], device or pinned host)."""
 
@@ -41,23 +82,12 @@ class TrainStep(object):
         self.world = world_size
         self.lr = lr
         params = [p for p in model.parameters() if p.requires_grad]
-        dev = params[0].device
-        self.n_params = sum(p.numel() for p in params)
-        align = 64                                   # every parameter starts on a 256-byte boundary
-        n = sum((p.numel() + align - 1) // align * align for p in params)
-        self.n_pad = n
-        # flat arenas: [params | pad], [grads | pad | err, kl, 0, 0]
-        self.flat_p = torch.zeros(self.n_pad, device=dev)
-        self.flat_g = torch.zeros(self.n_pad + 4, device=dev)
+        self.arena = FlatArena(params)
+        self.n_params, self.n_pad = self.arena.n_params, self.arena.n_pad
+        self.flat_p, self.flat_g = self.arena.flat_p, self.arena.flat_g
+        dev = self.flat_p.device
         self.flat_m = torch.zeros(self.n_pad, device=dev)
         self.flat_v = torch.zeros(self.n_pad, device=dev)
-        off = 0
-        for p in params:
-            k = p.numel()
-            self.flat_p[off:off + k].copy_(p.data.reshape(-1))
-            p.data = self.flat_p[off:off + k].view_as(p)
-            p.grad = self.flat_g[off:off + k].view_as(p)
-            off += (k + align - 1) // align * align
         self.params = params
         self.step_count = torch.zeros((), device=dev)
         self.geco = None
@@ -118,13 +148,9 @@ class TrainStep(object):
         beta = self.geco.beta if self.geco is not None else 1.0
         loss = err + beta * kl
         loss.backward()
-        tail = self.flat_g[self.n_pad:]
+        tail = self.arena.tail
         with torch.no_grad():
-            tail[0].copy_(err.detach())
-            tail[1].copy_(kl.detach())
-            if self.world > 1:
-                dist.all_reduce(self.flat_g)                      # ONE exchange per step
-            gerr, gkl = tail[0] / self.world, tail[1] / self.world
+            gerr, gkl = self.arena.exchange(err.detach(), kl.detach(), self.world)      # ONE exchange per step
             if self.geco is not None:
                 self.geco.update(gerr)
             self.step_count += 1
