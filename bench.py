@@ -156,7 +156,8 @@ def run_engine(args):
     dev = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=dev)
+        import datetime
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     from genesis_b200 import build, _lib, profiling, trainer
     if rank == 0:
@@ -218,12 +219,14 @@ def run_engine(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
 
+    # ---- dominant kernel: per-call device time inside profiled (eager) steps, CUDA events on the launch stream.
+    # Every rank runs them (the step contains the gradient all-reduce); rank 0 reports.
+    with profiling.Profiler() as prof:
+        for i in range(2):
+            ts._step_eager(devx[i % n_in])
+    barrier()
     if rank == 0:
         pk = peaks()
-        # ---- dominant kernel: per-call device time inside profiled (eager) steps, CUDA events on the launch stream
-        with profiling.Profiler() as prof:
-            for i in range(2):
-                ts._step_eager(devx[i % n_in])
         rows = prof.table()
         total_ms = sum(r['ms'] for r in rows)
         top = rows[0]
@@ -277,8 +280,13 @@ def run_engine(args):
         }
         print(json.dumps(line))
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # Tear-down: drop the captured graph (it holds the NCCL communicator's captured work) before leaving, and do not
+        # call destroy_process_group() -- with a live captured all-reduce it can block for the watchdog timeout.
+        barrier()
+        ts.graph = None
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
