@@ -1,0 +1,546 @@
+// genesis_b200 -- "halo" TF32 implicit GEMM for sm_100a: the stride-1 convolutions (forward, data gradient,
+// conv-transpose forward, and each sub-pixel class of a stride-2 conv-transpose) with the activation window
+// loaded into shared memory ONCE per CTA and every filter tap issued from it through shifted UMMA descriptors.
+//
+//     out[n, h*os+ph, w*os+pw, co] = act(bias[co] + sum_tap sum_c X[n, h+dh(tap), w+dw(tap), c] * W[widx(tap)][co][c])
+//
+// over the virtual output grid (h, w) in [0,Hv) x [0,Wv); X is zero outside the image.
+//
+// Layout trick: a CTA owns TH output rows of one image (or TNB whole small images).  One TMA box
+// {32 channels, Wp = Wv + dw-span pixels, rows, images} lands the zero-padded input window in shared memory as a
+// FLAT run of 128-byte pixel rows with pitch Wp (out-of-bounds fill supplies the padding).  In that flat space the
+// output position f = h_local*Wp + w reads input row f + toff(tap), toff = (dh-dh_min)*Wp + (dw-dw_min): every tap
+// is the SAME K-major SWIZZLE_128B operand shifted by toff rows.  The 128-byte swizzle is a function of the absolute
+// shared-memory address (tests/test_umma_layouts_gpu.py), so a descriptor may start at any row.  M tiles are 128
+// consecutive flat positions; positions with w >= Wv (the Wp-Wv pad columns) are computed and dropped.
+// Versus one TMA load per (tile, tap) this cuts L2->SMEM traffic by ~taps/halo-overhead (3x3: 4-5x, 5x5: 8-14x).
+//
+// Roles: warp 0 = TMA producer (activation window in up to 4 row chunks, weight taps through a ring),
+// warp 1 = TMEM allocator + MMA issuer (tap-outer, tile-inner so each weight tile is loaded once per CTA),
+// warps 2-5 = epilogue (tcgen05.ld -> bias/activation -> global).  Two CTAs per SM overlap load / MMA / epilogue.
+#include "umma.cuh"
+#include <cudaTypedefs.h>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+namespace halo {
+using namespace umma;
+
+constexpr int MAX_TAPS = 32;
+constexpr int MAX_CHUNKS = 8;
+
+struct Maps { CUtensorMap a; CUtensorMap b; };
+
+struct P {
+    float* out; const float* bias;
+    int N, Hv, Wv, TH, TW, TNB, Wp, RH; // RH: window rows per image (TH + dh-span); Wp: window pitch (>= TW + dw-span)
+    int ch_rows, nch, ch_pix;           // rows per chunk (TMA box rows), chunks, pixel rows per chunk (= ch_rows*Wp*TNB)
+    int tiles_h, tiles_w, dh_min, dw_min, span_h;
+    int Ho, Wo, Co, os, ph, pw;
+    int ntaps, cblocks, act, tmem_cols, a_bytes;
+    int toff[MAX_TAPS];
+    short widx[MAX_TAPS];
+};
+
+template <int ACT> __device__ __forceinline__ float act_apply(float v) {
+    if (ACT == G2_ACT_RELU) return fmaxf(v, 0.f);
+    if (ACT == G2_ACT_ELU) return v > 0.f ? v : expm1f(v);
+    if (ACT == G2_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+    return v;
+}
+
+// One epilogue warp: TMEM lanes 32q..32q+31 of every M tile -> +bias -> activation -> global.
+// Each lane owns one output pixel row in TMEM; the 32 x 128-byte block is transposed through a swizzled 4 KB
+// staging tile so that every store instruction writes four complete 128-byte pixel rows (8 lanes x 16 B each).
+template <int BN, int ACT>
+__device__ __forceinline__ void epilogue(const P& p, uint32_t tmem_base, const float* sBias, float* stage, int m_tiles, int n0,
+                                         int h0, int w0, int n0c, int imgs_valid, int rows_valid, int cols_valid) {
+    const int lane = threadIdx.x & 31, q = (threadIdx.x >> 5) & 3;
+    const int img_pix = p.RH * p.Wp;
+    const int sub = lane >> 3, chunk = lane & 7;
+    for (int t = 0; t < m_tiles; ++t) {
+        const int f = t * 128 + q * 32 + lane;
+        const int i = f / img_pix, rem = f - i * img_pix;
+        const int hl = rem / p.Wp, w = rem - hl * p.Wp;
+        const bool valid = i < imgs_valid && hl < rows_valid && w < cols_valid;
+        const int oh = (h0 + hl) * p.os + p.ph, ow = (w0 + w) * p.os + p.pw;
+        const int pix = valid ? ((n0 + i) * p.Ho + oh) * p.Wo + ow : -1;        // < 2^31 output pixels (checked on the host)
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * BN + c0), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 b = *reinterpret_cast<const float4*>(sBias + c0 + 4 * j);
+                float4 o;
+                o.x = act_apply<ACT>(__uint_as_float(v[4 * j]) + b.x);
+                o.y = act_apply<ACT>(__uint_as_float(v[4 * j + 1]) + b.y);
+                o.z = act_apply<ACT>(__uint_as_float(v[4 * j + 2]) + b.z);
+                o.w = act_apply<ACT>(__uint_as_float(v[4 * j + 3]) + b.w);
+                *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) = o;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int r4 = 0; r4 < 8; ++r4) {
+                const int row = r4 * 4 + sub;
+                const int rp = __shfl_sync(0xffffffffu, pix, row);
+                const float4 o = *reinterpret_cast<const float4*>(stage + row * 32 + ((chunk ^ (row & 7)) << 2));
+                if (rp >= 0) *reinterpret_cast<float4*>(p.out + (size_t)rp * p.Co + n0c + c0 + chunk * 4) = o;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P p) {
+    constexpr int B_BYTES = BN * 128;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* sm = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    uint8_t* sA = sm;
+    uint8_t* sB = sm + p.a_bytes;
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+    uint64_t* emptyA = fullA + MAX_CHUNKS;
+    uint64_t* fullB = emptyA + 1;
+    uint64_t* emptyB = fullB + STAGES;
+    uint64_t* accf = emptyB + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accf + 1);
+    float* sBias = reinterpret_cast<float*>(fullA) + 64;        // 256 B past the barrier block
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tw_i = blockIdx.x % p.tiles_w;
+    const int th_i = (blockIdx.x / p.tiles_w) % p.tiles_h;
+    const int n0 = (blockIdx.x / (p.tiles_w * p.tiles_h)) * p.TNB;
+    const int h0 = th_i * p.TH, w0 = tw_i * p.TW;
+    const int n0c = blockIdx.y * BN;
+    const int rows_valid = min(p.TH, p.Hv - h0);
+    const int cols_valid = min(p.TW, p.Wv - w0);
+    const int imgs_valid = min(p.TNB, p.N - n0);
+    // number of 128-position M tiles that contain a valid output, and window chunks they read
+    const int f_last = ((imgs_valid - 1) * p.RH + rows_valid - 1) * p.Wp + cols_valid - 1;
+    const int m_tiles = f_last / 128 + 1;
+    const int nch = p.TNB > 1 ? 1 : min(p.nch, (rows_valid + p.span_h + p.ch_rows - 1) / p.ch_rows);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&maps.a);
+        prefetch_tmap(&maps.b);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int j = 0; j < MAX_CHUNKS; ++j) mbar_init(&fullA[j], 1);
+            mbar_init(emptyA, 1);
+            for (int s = 0; s < STAGES; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+            mbar_init(accf, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + BN) sBias[threadIdx.x - 64] = p.bias ? p.bias[n0c + threadIdx.x - 64] : 0.f;
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---- TMA producer: the whole warp walks the schedule (uniform control flow), one elected lane issues
+        const uint32_t ch_bytes = (uint32_t)p.ch_pix * 128u;
+        int bi = 0;
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+            if (cb > 0) mbar_wait(emptyA, (uint32_t)(cb - 1) & 1u);     // all MMAs of the previous channel block retired
+            if (elect_one()) {
+                for (int j = 0; j < nch; ++j) {
+                    mbar_expect_tx(&fullA[j], ch_bytes);
+                    tma_load_4d(sA + (size_t)j * ch_bytes, &maps.a, &fullA[j], cb * 32, w0 + p.dw_min, h0 + p.dh_min + j * p.ch_rows, n0);
+                }
+            }
+            __syncwarp();
+            for (int tap = 0; tap < p.ntaps; ++tap, ++bi) {
+                const int s = bi % STAGES;
+                mbar_wait(&emptyB[s], ((uint32_t)(bi / STAGES) & 1u) ^ 1u);
+                if (elect_one()) {
+                    mbar_expect_tx(&fullB[s], B_BYTES);
+                    tma_load_3d(sB + s * B_BYTES, &maps.b, &fullB[s], cb * 32, n0c, p.widx[tap]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer: uniform control flow, one elected lane issues tcgen05.mma / commit
+        constexpr uint32_t idesc = idesc_tf32(BN);
+        const uint64_t hi = desc_k_sw128_hi();
+        const uint32_t a0 = smem_u32(sA) >> 4;
+        int bi = 0;
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+            int waited = 0;
+            for (int tap = 0; tap < p.ntaps; ++tap, ++bi) {
+                const int s = bi % STAGES;
+                mbar_wait(&fullB[s], (uint32_t)(bi / STAGES) & 1u);
+                const uint64_t bdesc = make_desc_k_sw128(smem_u32(sB + s * B_BYTES));
+                const int toff = p.toff[tap];
+                // activation chunks this tap reads (monotone in the tile index: wait for the last tile's)
+                const int need = min(nch - 1, (128 * (m_tiles - 1) + 127 + toff) / p.ch_pix);
+                while (waited <= need) { mbar_wait(&fullA[waited], (uint32_t)cb & 1u); ++waited; }
+                fence_after();
+                const uint32_t alo = a0 + (uint32_t)toff * 8u;
+                const uint32_t first = (cb | tap) != 0 ? 1u : 0u;
+                if (elect_one()) {
+                    for (int t = 0; t < m_tiles; ++t) {
+                        const uint64_t adesc = hi | (uint64_t)((alo + (uint32_t)t * 1024u) & 0x3FFFu);
+                        const uint32_t d = tmem_base + (uint32_t)(t * BN);
+                        mma_tf32(d, adesc, bdesc, idesc, first);        // 4 x (K = 8 tf32 = 32 B) per 128-byte row
+                        mma_tf32(d, adesc + 2, bdesc + 2, idesc, 1u);
+                        mma_tf32(d, adesc + 4, bdesc + 4, idesc, 1u);
+                        mma_tf32(d, adesc + 6, bdesc + 6, idesc, 1u);
+                    }
+                    commit(&emptyB[s]);                 // weight stage free when these MMAs retire
+                }
+                __syncwarp();
+            }
+            if (elect_one()) commit(emptyA);            // activation window free
+            __syncwarp();
+        }
+        if (elect_one()) commit(accf);                  // all accumulators complete
+        __syncwarp();
+    } else {
+        // ---- epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31
+        mbar_wait(accf, 0);
+        fence_after();
+        // the activation window is dead once every MMA has retired: reuse its first 16 KB as store staging
+        float* stage = reinterpret_cast<float*>(sA) + (warp & 3) * 1024;
+        switch (p.act) {
+            case G2_ACT_RELU: epilogue<BN, G2_ACT_RELU>(p, tmem_base, sBias, stage, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid); break;
+            case G2_ACT_ELU: epilogue<BN, G2_ACT_ELU>(p, tmem_base, sBias, stage, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid); break;
+            case G2_ACT_SIGMOID: epilogue<BN, G2_ACT_SIGMOID>(p, tmem_base, sBias, stage, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid); break;
+            default: epilogue<BN, G2_ACT_NONE>(p, tmem_base, sBias, stage, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid); break;
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static PFN_cuTensorMapEncodeTiled get_encode() {
+    static PFN_cuTensorMapEncodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(f);
+    });
+    return fn;
+}
+
+static bool encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                   const cuuint32_t* box) {
+    PFN_cuTensorMapEncodeTiled enc = get_encode();
+    if (!enc) return false;
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+static int gcd(int a, int b) { return b ? gcd(b, a % b) : a; }
+
+// tunables (environment, read once): shared-memory budget per CTA in KB (113 = two CTAs per SM), TMEM columns per CTA
+static int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s && *s ? atoi(s) : dflt;
+}
+static int g_enabled = -1;
+static int budget_bytes() { static int v = env_int("G2_HALO_SMEM_KB", 112) * 1024; return v; }
+static int max_cols() { static int v = env_int("G2_HALO_TMEM_COLS", 256); return v; }
+
+template <int BN> constexpr int stages_for() { return BN == 32 ? 4 : (BN == 64 ? 2 : 2); }
+
+struct Geo {
+    int TH, TW, TNB, RH, Wp, ch_rows, nch, m, a_bytes, tiles_h, tiles_w;
+    double cost;     // estimated SM clocks per image
+};
+
+static inline int m_of(int imgs, int RH, int rows, int Wp, int cols) { return (((imgs - 1) * RH + rows - 1) * Wp + cols - 1) / 128 + 1; }
+
+// Choose the CTA tile for one (class of a) convolution: TH x TW output pixels of one image (or TNB whole small
+// images), window pitch Wp (exact, or rounded up to 8 pixels so that any row count keeps chunks 1024-byte aligned).
+// The cost model is the per-SM time of all CTAs of an image: max(MMA clocks, L2->SMEM clocks) + a fixed per-CTA cost.
+static bool pick_geo(int N, int Hv, int Wv, int span_h, int span_w, int ntaps, int cblocks, int BN, int stages, Geo* best) {
+    const int fixed = stages * BN * 128 + 768 + 1024;
+    const double clk_mma = 4.0 * (BN == 32 ? 40 : BN == 64 ? 48 : 64) * ntaps * cblocks;   // per M tile (SMEM-read bound for small N)
+    const double l2_rate = 28.0;           // bytes / clock / SM sustained by TMA tile loads (measured 21-33)
+    const double cta_fixed = 1500.0;       // prologue + pipeline fill + epilogue tail not hidden by the sibling CTA
+    const double b_bytes = (double)ntaps * cblocks * BN * 128;
+    bool found = false;
+    for (int nsplit = 1; nsplit <= 4; ++nsplit) {
+        const int TW = (Wv + nsplit - 1) / nsplit;
+        const int tiles_w = (Wv + TW - 1) / TW;
+        if (tiles_w != nsplit) continue;
+        const int cols_last = Wv - (tiles_w - 1) * TW;
+        for (int variant = 0; variant < 2; ++variant) {
+            int Wp = TW + span_w;
+            if (variant == 1) {
+                if (Wp % 8 == 0) continue;
+                Wp = (Wp + 7) / 8 * 8;
+            }
+            if (Wp > 256) continue;
+            const int gran = 8 / gcd(Wp, 8);                     // rows per chunk must keep chunk bases 1024-byte aligned
+            const int off_max = span_h * Wp + span_w;
+            auto consider = [&](int TH, int TNB) {
+                Geo g;
+                g.TH = TH; g.TW = TW; g.TNB = TNB; g.RH = TH + span_h; g.Wp = Wp; g.tiles_w = tiles_w;
+                g.m = m_of(TNB, g.RH, TH, Wp, TW);
+                if (g.m * BN > max_cols()) return;
+                int loaded_pix;
+                if (TNB > 1) {
+                    if (g.RH > 256) return;
+                    g.ch_rows = g.RH; g.nch = 1;
+                    loaded_pix = g.RH * Wp * TNB;
+                } else {
+                    // fewest loaded rows with at most MAX_CHUNKS chunks; ties -> more (smaller) chunks for earlier MMA start
+                    int best_rows = 1 << 30;
+                    g.ch_rows = 0; g.nch = 0;
+                    for (int cr = gran; cr <= 256; cr += gran) {
+                        const int nch = (g.RH + cr - 1) / cr;
+                        if (nch > MAX_CHUNKS) continue;
+                        if (nch * cr < best_rows) { best_rows = nch * cr; g.ch_rows = cr; g.nch = nch; }
+                        if (nch == 1) break;
+                    }
+                    if (g.nch == 0) return;
+                    loaded_pix = best_rows * Wp;
+                }
+                int alloc_pix = loaded_pix;
+                if (128 * g.m + off_max > alloc_pix) alloc_pix = 128 * g.m + off_max;
+                g.a_bytes = ((alloc_pix * 128 + 1023) / 1024) * 1024;
+                if (g.a_bytes + fixed > budget_bytes()) return;
+                double tiles, ctas, bytes;
+                if (TNB > 1) {
+                    g.tiles_h = 1;
+                    const int groups = (N + TNB - 1) / TNB;
+                    tiles = (double)groups * g.m / N;
+                    ctas = (double)groups / N;
+                    bytes = ctas * (cblocks * loaded_pix * 128.0 + b_bytes);
+                } else {
+                    g.tiles_h = (Hv + TH - 1) / TH;
+                    const int rows_last = Hv - (g.tiles_h - 1) * TH;
+                    tiles = (double)(g.tiles_h - 1) * ((tiles_w - 1) * m_of(1, g.RH, TH, Wp, TW) + m_of(1, g.RH, TH, Wp, cols_last)) +
+                            ((tiles_w - 1) * m_of(1, g.RH, rows_last, Wp, TW) + m_of(1, g.RH, rows_last, Wp, cols_last));
+                    ctas = (double)g.tiles_h * tiles_w;
+                    bytes = ctas * (cblocks * loaded_pix * 128.0 + b_bytes);
+                }
+                const double mma = tiles * clk_mma, load = bytes / l2_rate;
+                g.cost = (mma > load ? mma : load) + 0.25 * (mma > load ? load : mma) + ctas * cta_fixed;
+                if (!found || g.cost < best->cost) {
+                    *best = g;
+                    found = true;
+                }
+            };
+            for (int TH = 1; TH <= Hv; ++TH) consider(TH, 1);
+            if (nsplit == 1)
+                for (int TNB = 2; TNB <= 16 && TNB <= N; ++TNB) consider(Hv, TNB);
+        }
+    }
+    return found;
+}
+
+template <int BN>
+static int launch(const Maps& maps, const P& p, dim3 grid, cudaStream_t stream) {
+    constexpr int STAGES = stages_for<BN>();
+    const int smem = p.a_bytes + STAGES * BN * 128 + 768 + 1024;
+    static int attr_set = 0;
+    if (attr_set < smem) {
+        cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = 227 * 1024;
+    }
+    conv_halo_kernel<BN, STAGES><<<grid, 192, smem, stream>>>(maps, p);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? G2_OK : (int)e;
+}
+
+static int pick_bn(int Co) {
+    if (Co == 32 || Co == 64 || Co == 128) return Co;
+    if (Co % 128 == 0) return 128;
+    if (Co % 64 == 0) return 64;
+    return 0;
+}
+static int stages_of(int BN) { return BN == 32 ? stages_for<32>() : BN == 64 ? stages_for<64>() : stages_for<128>(); }
+
+struct TapSet { int n; int dh[MAX_TAPS], dw[MAX_TAPS], widx[MAX_TAPS]; int os, ph, pw, Hv, Wv; };
+
+// Enumerate the tap sets (1, or 4 sub-pixel classes) of a problem; returns the number of classes or 0 if the
+// halo kernel does not cover it.
+static int tap_sets(int Hi, int Wi, int Ho, int Wo, int R, int S, int stride, int pad, int mode, TapSet* ts) {
+    if (R * S > MAX_TAPS) return 0;
+    if (stride == 1) {
+        TapSet& t = ts[0];
+        t.n = 0; t.os = 1; t.ph = 0; t.pw = 0; t.Hv = Ho; t.Wv = Wo;
+        for (int r = 0; r < R; ++r)
+            for (int s = 0; s < S; ++s) {
+                t.dh[t.n] = mode == 0 ? r - pad : pad - r;
+                t.dw[t.n] = mode == 0 ? s - pad : pad - s;
+                t.widx[t.n] = r * S + s;
+                ++t.n;
+            }
+        return 1;
+    }
+    if (stride == 2 && mode == 1) {
+        if ((Ho | Wo) & 1) return 0;
+        int nc = 0;
+        for (int cls = 0; cls < 4; ++cls) {
+            TapSet& t = ts[nc];
+            t.n = 0; t.os = 2; t.ph = cls >> 1; t.pw = cls & 1; t.Hv = Ho / 2; t.Wv = Wo / 2;
+            for (int r = 0; r < R; ++r)
+                for (int s = 0; s < S; ++s) {
+                    const int th = t.ph + pad - r, tw = t.pw + pad - s;
+                    if ((th & 1) || (tw & 1)) continue;
+                    t.dh[t.n] = th / 2; t.dw[t.n] = tw / 2; t.widx[t.n] = r * S + s;
+                    ++t.n;
+                }
+            if (t.n == 0) return 0;        // a class without taps would need a bias-only fill: leave it to the tile kernel
+            ++nc;
+        }
+        return nc;
+    }
+    return 0;
+}
+
+static void spans(const TapSet& t, int* dh_min, int* dw_min, int* span_h, int* span_w) {
+    int a = t.dh[0], b = t.dh[0], c = t.dw[0], d = t.dw[0];
+    for (int i = 1; i < t.n; ++i) {
+        a = t.dh[i] < a ? t.dh[i] : a; b = t.dh[i] > b ? t.dh[i] : b;
+        c = t.dw[i] < c ? t.dw[i] : c; d = t.dw[i] > d ? t.dw[i] : d;
+    }
+    *dh_min = a; *dw_min = c; *span_h = b - a; *span_w = d - c;
+}
+
+static bool enabled() {
+    if (g_enabled < 0) g_enabled = env_int("G2_HALO", 1) ? 1 : 0;
+    return g_enabled == 1;
+}
+
+}  // namespace halo
+
+extern "C" {
+
+// Runtime switch for A/B measurements (scripts/conv_bench.py): returns the previous setting.
+int g2_conv_halo_enable(int on) {
+    const int prev = halo::enabled() ? 1 : 0;
+    halo::g_enabled = on ? 1 : 0;
+    return prev;
+}
+
+// 1 if the halo kernel takes this problem (g2_conv_igemm_tf32 then routes to it), else 0.
+int g2_conv_halo_supported(int N, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int R, int S, int stride, int pad, int mode) {
+    using namespace halo;
+    if (!enabled()) return 0;
+    if (Ci % 32 != 0 || N <= 0 || (long)N * Ho * Wo >= (1L << 31)) return 0;
+    const int BN = pick_bn(Co);
+    if (BN == 0) return 0;
+    TapSet ts[4];
+    const int nc = tap_sets(Hi, Wi, Ho, Wo, R, S, stride, pad, mode, ts);
+    if (nc == 0) return 0;
+    for (int c = 0; c < nc; ++c) {
+        if ((long)ts[c].Hv * ts[c].Wv < 256) return 0;       // tiny maps: the dense-tile kernel packs them better
+        int dh_min, dw_min, sh, sw;
+        spans(ts[c], &dh_min, &dw_min, &sh, &sw);
+        Geo g;
+        if (!pick_geo(N, ts[c].Hv, ts[c].Wv, sh, sw, ts[c].n, Ci / 32, BN, stages_of(BN), &g)) return 0;
+    }
+    return 1;
+}
+
+// Same contract as g2_conv_igemm_tf32 for the problems g2_conv_halo_supported accepts.
+int g2_conv_halo_tf32(const float* in, const float* w, const float* bias, float* out, int N, int Hi, int Wi, int Ci,
+                      int Ho, int Wo, int Co, int R, int S, int stride, int pad, int mode, int act, cudaStream_t stream) {
+    using namespace halo;
+    G2_CHECK_ARG(in && w && out && N > 0);
+    G2_CHECK_ARG((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    if (Ci % 32 != 0 || (long)N * Ho * Wo >= (1L << 31)) return G2_ERR_UNSUPPORTED;
+    const int BN = pick_bn(Co);
+    if (BN == 0) return G2_ERR_UNSUPPORTED;
+    TapSet ts[4];
+    const int nc = tap_sets(Hi, Wi, Ho, Wo, R, S, stride, pad, mode, ts);
+    if (nc == 0) return G2_ERR_UNSUPPORTED;
+    Maps maps;
+    memset(&maps, 0, sizeof(maps));
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)Ci, (cuuint64_t)Co, (cuuint64_t)(R * S)};
+        cuuint64_t str[2] = {(cuuint64_t)Ci * 4, (cuuint64_t)Ci * Co * 4};
+        cuuint32_t box[3] = {32, (uint32_t)BN, 1};
+        if (!encode(&maps.b, w, 3, dims, str, box)) return G2_ERR_UNSUPPORTED;
+    }
+    for (int c = 0; c < nc; ++c) {
+        const TapSet& t = ts[c];
+        int dh_min, dw_min, sh, sw;
+        spans(t, &dh_min, &dw_min, &sh, &sw);
+        Geo g;
+        if (!pick_geo(N, t.Hv, t.Wv, sh, sw, t.n, Ci / 32, BN, stages_of(BN), &g)) return G2_ERR_UNSUPPORTED;
+        P p;
+        memset(&p, 0, sizeof(p));
+        p.out = out; p.bias = bias; p.N = N; p.Hv = t.Hv; p.Wv = t.Wv; p.TH = g.TH; p.TW = g.TW; p.TNB = g.TNB;
+        p.Wp = g.Wp; p.RH = g.RH; p.ch_rows = g.ch_rows; p.nch = g.nch; p.ch_pix = g.ch_rows * p.Wp * g.TNB;
+        p.tiles_h = g.tiles_h; p.tiles_w = g.tiles_w; p.dh_min = dh_min; p.dw_min = dw_min; p.span_h = sh;
+        p.Ho = Ho; p.Wo = Wo; p.Co = Co; p.os = t.os; p.ph = t.ph; p.pw = t.pw;
+        p.ntaps = t.n; p.cblocks = Ci / 32; p.act = act; p.a_bytes = g.a_bytes;
+        int cols = 32;
+        while (cols < g.m * BN) cols <<= 1;
+        p.tmem_cols = cols;
+        for (int i = 0; i < t.n; ++i) {
+            p.toff[i] = (t.dh[i] - dh_min) * p.Wp + (t.dw[i] - dw_min);
+            p.widx[i] = (short)t.widx[i];
+        }
+        {
+            cuuint64_t dims[4] = {(cuuint64_t)Ci, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)N};
+            cuuint64_t str[3] = {(cuuint64_t)Ci * 4, (cuuint64_t)Wi * Ci * 4, (cuuint64_t)Hi * Wi * Ci * 4};
+            cuuint32_t box[4] = {32, (uint32_t)p.Wp, (uint32_t)g.ch_rows, (uint32_t)g.TNB};
+            if (!encode(&maps.a, in, 4, dims, str, box)) return G2_ERR_UNSUPPORTED;
+        }
+        dim3 grid((unsigned)(((N + g.TNB - 1) / g.TNB) * g.tiles_h * g.tiles_w), (unsigned)(Co / BN), 1);
+        int rc;
+        switch (BN) {
+            case 32: rc = launch<32>(maps, p, grid, stream); break;
+            case 64: rc = launch<64>(maps, p, grid, stream); break;
+            default: rc = launch<128>(maps, p, grid, stream); break;
+        }
+        if (rc != G2_OK) return rc;
+    }
+    return G2_OK;
+}
+
+// Launch plan of class `cls` for tests (tests/test_halo_plan.py replays it in numpy) and DESIGN.md:
+// plan[0..21] = {nclasses, TH, TNB, RH, ch_rows, nch, m_tiles, a_bytes, tiles_h, Wp, dh_min, dw_min, os, ph, pw, Hv, Wv,
+//                ntaps, BN, smem_bytes, TW, tiles_w}, plan[32+i] = toff[i], plan[64+i] = widx[i].
+int g2_conv_halo_plan(int N, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int R, int S, int stride, int pad, int mode,
+                      int cls, int* plan) {
+    using namespace halo;
+    const int BN = pick_bn(Co);
+    TapSet ts[4];
+    if (BN == 0 || !plan) return G2_ERR_ARG;
+    const int nc = tap_sets(Hi, Wi, Ho, Wo, R, S, stride, pad, mode, ts);
+    if (nc == 0 || cls < 0 || cls >= nc) return G2_ERR_UNSUPPORTED;
+    const TapSet& t = ts[cls];
+    int dh_min, dw_min, sh, sw;
+    spans(t, &dh_min, &dw_min, &sh, &sw);
+    Geo g;
+    if (!pick_geo(N, t.Hv, t.Wv, sh, sw, t.n, Ci / 32, BN, stages_of(BN), &g)) return G2_ERR_UNSUPPORTED;
+    const int Wp = g.Wp;
+    const int v[22] = {nc, g.TH, g.TNB, g.RH, g.ch_rows, g.nch, g.m, g.a_bytes, g.tiles_h, Wp, dh_min, dw_min, t.os, t.ph, t.pw,
+                       t.Hv, t.Wv, t.n, BN, g.a_bytes + stages_of(BN) * BN * 128 + 768 + 1024, g.TW, g.tiles_w};
+    for (int i = 0; i < 96; ++i) plan[i] = 0;
+    for (int i = 0; i < 22; ++i) plan[i] = v[i];
+    for (int i = 0; i < t.n; ++i) {
+        plan[32 + i] = (t.dh[i] - dh_min) * Wp + (t.dw[i] - dw_min);
+        plan[64 + i] = t.widx[i];
+    }
+    return G2_OK;
+}
+
+}  // extern "C"

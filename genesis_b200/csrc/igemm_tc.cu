@@ -303,6 +303,11 @@ inline void pick_tile(int Hv, int Wv, int* TH, int* TW, int* TNB) {
 
 extern "C" {
 
+// halo kernel (igemm_halo.cu): stride-1 problems and stride-2 conv-transpose classes with the activation window resident
+int g2_conv_halo_supported(int N, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int R, int S, int stride, int pad, int mode);
+int g2_conv_halo_tf32(const float* in, const float* w, const float* bias, float* out, int N, int Hi, int Wi, int Ci,
+                      int Ho, int Wo, int Co, int R, int S, int stride, int pad, int mode, int act, cudaStream_t stream);
+
 // 1 if g2_conv_igemm_tf32 handles this problem, else 0 (the caller then uses the exact fp32 kernel).
 int g2_conv_tf32_supported(int N, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int R, int S, int stride, int pad, int mode) {
     if (Ci % 32 != 0 || tc::pick_bn(Co) == 0) return 0;
@@ -325,6 +330,10 @@ int g2_conv_igemm_tf32(const float* in, const float* w, const float* bias, float
     if (!g2_conv_tf32_supported(N, Hi, Wi, Ci, Ho, Wo, Co, R, S, stride, pad, mode)) return G2_ERR_UNSUPPORTED;
     G2_CHECK_ARG((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    if (g2_conv_halo_supported(N, Hi, Wi, Ci, Ho, Wo, Co, R, S, stride, pad, mode)) {
+        const int rc = g2_conv_halo_tf32(in, w, bias, out, N, Hi, Wi, Ci, Ho, Wo, Co, R, S, stride, pad, mode, act, stream);
+        if (rc != G2_ERR_UNSUPPORTED) return rc;
+    }
     const int BN = pick_bn(Co);
     Maps maps;
     memset(&maps, 0, sizeof(maps));

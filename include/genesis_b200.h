@@ -176,6 +176,22 @@ int g2_conv_wgrad_tf32(const float* g, const float* t, float* dw, float* ws, int
 int g2_gemm_tf32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K,
                  g2_stream_t stream);
 
+/* Halo variant of g2_conv_igemm_tf32 (igemm_halo.cu): stride-1 problems and the sub-pixel classes of stride-2
+ * conv-transposes with the zero-padded activation window loaded once per CTA and all filter taps issued from it
+ * through shifted UMMA descriptors.  g2_conv_igemm_tf32 routes to it whenever g2_conv_halo_supported() == 1;
+ * g2_conv_halo_enable(0/1) switches the routing at run time (A/B measurements) and returns the previous setting;
+ * g2_conv_halo_plan fills plan[96] with the launch plan of sub-pixel class `cls` (host-only query, no launch):
+ * {nclasses, TH, TNB, RH, chunk_rows, chunks, m_tiles, a_bytes, tiles_h, Wp, dh_min, dw_min, os, ph, pw, Hv, Wv,
+ *  ntaps, BN, smem_bytes}, plan[32+i] = flat row offset of tap i, plan[64+i] = its weight index. */
+int g2_conv_halo_enable(int on);
+int g2_conv_halo_supported(int N, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int R, int S, int stride,
+                           int pad, int mode);
+int g2_conv_halo_tf32(const float* in, const float* w, const float* bias, float* out, int N, int Hi, int Wi,
+                      int Ci, int Ho, int Wo, int Co, int R, int S, int stride, int pad, int mode, int act,
+                      g2_stream_t stream);
+int g2_conv_halo_plan(int N, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int R, int S, int stride, int pad,
+                      int mode, int cls, int* plan);
+
 /* UMMA descriptor self-test (debug_umma.cu): runs `nk` tcgen05.mma.kind::tf32 (M=128) on caller-provided
  * shared-memory images of A and B with caller-provided descriptor templates and dumps D[128][N]. */
 int g2_debug_umma_probe(const float* a_img, const float* b_img, float* D, int a_bytes, int b_bytes, long adesc_t,
