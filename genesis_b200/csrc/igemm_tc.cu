@@ -19,7 +19,7 @@
 // A (pixels x 32 channels) and B (Cout x 32 channels) tiles are K-major, 128 B per row, SWIZZLE_128B.
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
 // (tcgen05.ld -> bias/activation -> global).
-#include "common.cuh"
+#include "umma.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <mutex>
@@ -105,6 +105,44 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+template <int ACT> __device__ __forceinline__ float act_apply(float v) {
+    if (ACT == G2_ACT_RELU) return fmaxf(v, 0.f);
+    if (ACT == G2_ACT_ELU) return v > 0.f ? v : expm1f(v);
+    if (ACT == G2_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+    return v;
+}
+
+// One epilogue warp: its 32 TMEM lanes (one output pixel each, `pix` = flat output pixel or -1) -> +bias -> act -> global.
+template <int BN, int ACT>
+__device__ __forceinline__ void store_tile(float* out, int Co, int n0c, uint32_t tmem_base, const float* sBias, float* stage, long pix) {
+    const int lane = threadIdx.x & 31, q = (threadIdx.x >> 5) & 3;
+    const int sub = lane >> 3, chunk = lane & 7;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 b = *reinterpret_cast<const float4*>(sBias + c0 + 4 * j);
+            float4 o;
+            o.x = act_apply<ACT>(__uint_as_float(v[4 * j]) + b.x);
+            o.y = act_apply<ACT>(__uint_as_float(v[4 * j + 1]) + b.y);
+            o.z = act_apply<ACT>(__uint_as_float(v[4 * j + 2]) + b.z);
+            o.w = act_apply<ACT>(__uint_as_float(v[4 * j + 3]) + b.w);
+            *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) = o;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r4 = 0; r4 < 8; ++r4) {
+            const int row = r4 * 4 + sub;
+            const long rp = __shfl_sync(0xffffffffu, pix, row);
+            const float4 o = *reinterpret_cast<const float4*>(stage + row * 32 + ((chunk ^ (row & 7)) << 2));
+            if (rp >= 0) *reinterpret_cast<float4*>(out + rp * Co + n0c + c0 + chunk * 4) = o;
+        }
+        __syncwarp();
+    }
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P p) {
     constexpr int B_BYTES = BN * 128;
@@ -118,6 +156,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ Ma
     uint64_t* empty = full + STAGES;
     uint64_t* accf = empty + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accf + 1);
+    float* sBias = reinterpret_cast<float*>(full) + 32;           // 128 B past the barrier block
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // tile coordinates
@@ -144,42 +183,48 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ Ma
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + BN) sBias[threadIdx.x - 64] = p.bias ? p.bias[n0c + threadIdx.x - 64] : 0.f;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            for (int i = 0; i < nkb; ++i) {
-                const int kb = kb0 + i;
-                const int s = i % STAGES;
-                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-                mbar_wait(&empty[s], ph ^ 1u);
+        // whole warp walks the schedule (uniform control flow); one elected lane issues the TMA loads
+        for (int i = 0; i < nkb; ++i) {
+            const int kb = kb0 + i;
+            const int s = i % STAGES;
+            const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+            mbar_wait(&empty[s], ph ^ 1u);
+            if (umma::elect_one()) {
                 mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
                 const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
                 tma_load_4d(sA + s * A_BYTES, &maps.a[p.taps.plane[tap]], &full[s], cb * 32, w0 + p.taps.dw[tap],
                             h0 + p.taps.dh[tap], n);
                 tma_load_3d(sB + s * B_BYTES, &maps.b, &full[s], cb * 32, n0c, p.taps.widx[tap]);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-                mbar_wait(&full[s], ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t adesc = make_desc_k_sw128(smem_u32(sA + s * A_BYTES));
-                const uint64_t bdesc = make_desc_k_sw128(smem_u32(sB + s * B_BYTES));
-#pragma unroll
-                for (int k = 0; k < 4; ++k)     // 4 x (K = 8 tf32 = 32 B) per 128-byte row
-                    umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % STAGES;
+            const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+            mbar_wait(&full[s], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t adesc = make_desc_k_sw128(smem_u32(sA + s * A_BYTES));
+            const uint64_t bdesc = make_desc_k_sw128(smem_u32(sB + s * B_BYTES));
+            if (umma::elect_one()) {
+                umma_tf32(tmem_base, adesc, bdesc, idesc, i > 0 ? 1u : 0u);      // 4 x (K = 8 tf32 = 32 B) per 128-byte row
+                umma_tf32(tmem_base, adesc + 2, bdesc + 2, idesc, 1u);
+                umma_tf32(tmem_base, adesc + 4, bdesc + 4, idesc, 1u);
+                umma_tf32(tmem_base, adesc + 6, bdesc + 6, idesc, 1u);
                 umma_commit(&empty[s]);          // frees the smem stage when these MMAs retire
             }
-            umma_commit(accf);                   // accumulator complete
+            __syncwarp();
         }
+        if (umma::elect_one()) umma_commit(accf);    // accumulator complete
+        __syncwarp();
     } else {
         // ---- epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31
         const int q = warp & 3;
@@ -195,31 +240,29 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ Ma
         if (p.flat_wi > 0) { oh = wv / p.flat_wi; ow = wv - oh * p.flat_wi; }
         else { oh = hv * p.os + p.ph; ow = wv * p.os + p.pw; }
         valid = valid && oh < p.Ho && ow < p.Wo;
-        float* outp = p.out + (((long)(n + tn) * p.Ho + oh) * p.Wo + ow) * p.Co + n0c;
-        const bool add_bias = p.bias != nullptr && blockIdx.z == 0;
+        const long pix = valid ? ((long)(n + tn) * p.Ho + oh) * p.Wo + ow : -1;
+        if (p.atomic) {
+            float* outp = p.out + pix * p.Co + n0c;
+            const bool add_bias = p.bias != nullptr && blockIdx.z == 0;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            if (valid) {
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                if (valid) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 o;
-                    o.x = __uint_as_float(v[j]); o.y = __uint_as_float(v[j + 1]);
-                    o.z = __uint_as_float(v[j + 2]); o.w = __uint_as_float(v[j + 3]);
-                    if (add_bias) {
-                        const float4 b = g2_ldg4(p.bias + n0c + c0 + j);
-                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                    }
-                    if (p.atomic) {
-                        atomicAdd(outp + c0 + j, o.x); atomicAdd(outp + c0 + j + 1, o.y);
-                        atomicAdd(outp + c0 + j + 2, o.z); atomicAdd(outp + c0 + j + 3, o.w);
-                    } else {
-                        o.x = g2_apply_act(o.x, p.act, 0.f); o.y = g2_apply_act(o.y, p.act, 0.f);
-                        o.z = g2_apply_act(o.z, p.act, 0.f); o.w = g2_apply_act(o.w, p.act, 0.f);
-                        *reinterpret_cast<float4*>(outp + c0 + j) = o;
-                    }
+                    for (int j = 0; j < 32; ++j)
+                        atomicAdd(outp + c0 + j, __uint_as_float(v[j]) + (add_bias ? sBias[c0 + j] : 0.f));
                 }
+            }
+        } else {
+            // all MMAs have retired, so stage 0 of the A ring is free: transpose each 32 x 128-byte block through a swizzled
+            // 4 KB staging tile so that every store instruction writes four complete 128-byte rows
+            float* stage = reinterpret_cast<float*>(sA) + q * 1024;
+            switch (p.act) {
+                case G2_ACT_RELU: store_tile<BN, G2_ACT_RELU>(p.out, p.Co, n0c, tmem_base, sBias, stage, pix); break;
+                case G2_ACT_ELU: store_tile<BN, G2_ACT_ELU>(p.out, p.Co, n0c, tmem_base, sBias, stage, pix); break;
+                case G2_ACT_SIGMOID: store_tile<BN, G2_ACT_SIGMOID>(p.out, p.Co, n0c, tmem_base, sBias, stage, pix); break;
+                default: store_tile<BN, G2_ACT_NONE>(p.out, p.Co, n0c, tmem_base, sBias, stage, pix); break;
             }
         }
     }
@@ -259,7 +302,7 @@ bool encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, 
 
 template <int BN, int STAGES>
 int launch(const Maps& maps, const P& p, dim3 grid, cudaStream_t stream) {
-    constexpr int smem = STAGES * (A_BYTES + BN * 128) + (2 * STAGES + 1) * 8 + 16 + 1024;
+    constexpr int smem = STAGES * (A_BYTES + BN * 128) + 128 + BN * 4 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -57,9 +57,14 @@ struct NormFinP {
     float eps, momentum;
 };
 
+// Batch mode: one WARP per channel (lanes stride over the N per-sample partial sums, then shuffle-reduce);
+// instance / group mode: one thread per (n, c).
 __global__ void norm_finalize_kernel(const NormFinP p) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int Ns = p.mode == G2_NORM_BATCH ? 1 : p.N;
+    const bool batch = p.mode == G2_NORM_BATCH;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int idx = batch ? gid >> 5 : gid;
+    const int lane = threadIdx.x & 31;
+    const int Ns = batch ? 1 : p.N;
     if (idx >= Ns * p.C) return;
     const int n = idx / p.C, c = idx - n * p.C;
     const bool second = c >= p.half;
@@ -67,19 +72,21 @@ __global__ void norm_finalize_kernel(const NormFinP p) {
     const float gamma = second ? (p.g1 ? p.g1[ch] : 1.f) : (p.g0 ? p.g0[ch] : 1.f);
     const float beta = second ? (p.b1 ? p.b1[ch] : 0.f) : (p.b0 ? p.b0[ch] : 0.f);
     double mean, var;
-    if (p.mode == G2_NORM_BATCH) {
+    if (batch) {
         float* rm = second ? p.rm1 : p.rm0;
         float* rv = second ? p.rv1 : p.rv0;
         if (p.training) {
             double s = 0.0, ss = 0.0;
-            for (int i = 0; i < p.N; ++i) { s += p.sums[((long)i * p.C + c) * 2]; ss += p.sums[((long)i * p.C + c) * 2 + 1]; }
+            for (int i = lane; i < p.N; i += 32) { s += p.sums[((long)i * p.C + c) * 2]; ss += p.sums[((long)i * p.C + c) * 2 + 1]; }
+            s = g2_warp_sum_d(s); ss = g2_warp_sum_d(ss);
             const double cnt = (double)p.N * p.HW;
             mean = s / cnt; var = ss / cnt - mean * mean; if (var < 0.0) var = 0.0;
-            if (rm) {
+            if (rm && lane == 0) {
                 rm[ch] = (1.f - p.momentum) * rm[ch] + p.momentum * (float)mean;
                 rv[ch] = (1.f - p.momentum) * rv[ch] + p.momentum * (float)(var * cnt / (cnt > 1.0 ? cnt - 1.0 : 1.0));
             }
         } else { mean = rm[ch]; var = rv[ch]; }
+        if (lane != 0) return;
     } else if (p.mode == G2_NORM_INSTANCE) {
         const double s = p.sums[((long)n * p.C + c) * 2], ss = p.sums[((long)n * p.C + c) * 2 + 1];
         mean = s / p.HW; var = ss / p.HW - mean * mean; if (var < 0.0) var = 0.0;
@@ -224,22 +231,38 @@ struct NormBwdFinP {
     int N, HW, Cy, half, mode, groups;
 };
 
-__global__ void norm_bwd_finalize_kernel(const NormBwdFinP p) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int Ns = p.mode == G2_NORM_BATCH ? 1 : p.N;
-    if (idx >= Ns * p.Cy) return;
-    const int n = idx / p.Cy, c = idx - n * p.Cy;
+// Blocks [0, main_blocks): one thread per (n, c) -> m1, m2 (instance / group mode).
+// Blocks [main_blocks, ..): one WARP per channel sums the per-sample partials over N (lanes stride, shuffle-reduce)
+// -> dgamma, dbeta, and in batch mode also m1, m2 (main_blocks = 0 there).
+__global__ void norm_bwd_finalize_kernel(const NormBwdFinP p, int main_blocks) {
     auto gamma_of = [&](int cc) {
         const bool sec = cc >= p.half; const int ch = sec ? cc - p.half : cc;
         return sec ? (p.g1 ? p.g1[ch] : 1.f) : (p.g0 ? p.g0[ch] : 1.f);
     };
-    double m1, m2;
-    if (p.mode == G2_NORM_BATCH) {
+    if ((int)blockIdx.x >= main_blocks) {
+        const int c = (((int)blockIdx.x - main_blocks) * blockDim.x + threadIdx.x) >> 5;
+        const int lane = threadIdx.x & 31;
+        if (c >= p.Cy) return;
         double s1 = 0.0, s2 = 0.0;
-        for (int i = 0; i < p.N; ++i) { s1 += p.sums2[((long)i * p.Cy + c) * 2]; s2 += p.sums2[((long)i * p.Cy + c) * 2 + 1]; }
-        const double cnt = (double)p.N * p.HW, g = gamma_of(c);
-        m1 = g * s1 / cnt; m2 = g * s2 / cnt;
-    } else if (p.mode == G2_NORM_INSTANCE) {
+        for (int i = lane; i < p.N; i += 32) { s1 += p.sums2[((long)i * p.Cy + c) * 2]; s2 += p.sums2[((long)i * p.Cy + c) * 2 + 1]; }
+        s1 = g2_warp_sum_d(s1); s2 = g2_warp_sum_d(s2);
+        if (lane != 0) return;
+        if (p.mode == G2_NORM_BATCH) {
+            const double cnt = (double)p.N * p.HW, g = gamma_of(c);
+            p.m1[c] = (float)(g * s1 / cnt);
+            p.m2[c] = (float)(g * s2 / cnt);
+        }
+        const bool sec = c >= p.half; const int ch = sec ? c - p.half : c;
+        float* dg = sec ? p.dg1 : p.dg0; float* db = sec ? p.db1 : p.db0;
+        if (dg) dg[ch] = (float)s2;
+        if (db) db[ch] = (float)s1;
+        return;
+    }
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.N * p.Cy) return;
+    const int n = idx / p.Cy, c = idx - n * p.Cy;
+    double m1, m2;
+    if (p.mode == G2_NORM_INSTANCE) {
         const double g = gamma_of(c);
         m1 = g * p.sums2[((long)n * p.Cy + c) * 2] / p.HW;
         m2 = g * p.sums2[((long)n * p.Cy + c) * 2 + 1] / p.HW;
@@ -256,14 +279,6 @@ __global__ void norm_bwd_finalize_kernel(const NormBwdFinP p) {
     }
     p.m1[idx] = (float)m1;
     p.m2[idx] = (float)m2;
-    if (n == 0) {   // parameter gradients: sum over all samples
-        double s1 = 0.0, s2 = 0.0;
-        for (int i = 0; i < p.N; ++i) { s1 += p.sums2[((long)i * p.Cy + c) * 2]; s2 += p.sums2[((long)i * p.Cy + c) * 2 + 1]; }
-        const bool sec = c >= p.half; const int ch = sec ? c - p.half : c;
-        float* dg = sec ? p.dg1 : p.dg0; float* db = sec ? p.db1 : p.db0;
-        if (dg) dg[ch] = (float)s2;
-        if (db) db[ch] = (float)s1;
-    }
 }
 
 // ---------------------------------------------------------------------------------- backward apply
@@ -343,7 +358,7 @@ int g2_norm_finalize_f32(const double* sums, const float* g0, const float* b0, c
     else G2_CHECK_ARG(sums != nullptr);
     NormFinP p{sums, g0, b0, g1, b1, rm0, rv0, rm1, rv1, mean, rstd, scale, shift, N, HW, C, half, mode, groups, training, eps, momentum};
     const int Ns = mode == G2_NORM_BATCH ? 1 : N;
-    norm_finalize_kernel<<<g2_cdiv((long)Ns * C, 128), 128, 0, stream>>>(p);
+    norm_finalize_kernel<<<g2_cdiv((long)Ns * C * (mode == G2_NORM_BATCH ? 32 : 1), 128), 128, 0, stream>>>(p);
     G2_LAUNCH_RET();
 }
 
@@ -382,8 +397,8 @@ int g2_norm_bwd_finalize_f32(const double* sums2, const float* g0, const float* 
     G2_CHECK_ARG(mode == G2_NORM_BATCH || mode == G2_NORM_INSTANCE || mode == G2_NORM_GROUP);
     if (mode == G2_NORM_GROUP) G2_CHECK_ARG(groups > 0 && Cy % groups == 0);
     NormBwdFinP p{sums2, g0, g1, m1, m2, dg0, db0, dg1, db1, N, HW, Cy, half, mode, groups};
-    const int Ns = mode == G2_NORM_BATCH ? 1 : N;
-    norm_bwd_finalize_kernel<<<g2_cdiv((long)Ns * Cy, 128), 128, 0, stream>>>(p);
+    const int main_blocks = mode == G2_NORM_BATCH ? 0 : g2_cdiv((long)N * Cy, 128);
+    norm_bwd_finalize_kernel<<<main_blocks + g2_cdiv((long)Cy * 32, 128), 128, 0, stream>>>(p, main_blocks);
     G2_LAUNCH_RET();
 }
 

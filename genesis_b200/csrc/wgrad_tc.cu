@@ -33,6 +33,11 @@ struct P {
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -131,23 +136,27 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            int it = 0;                                   // global stage counter
-            for (int c = 0; c < nchunks; ++c) {
-                const int chunk = c_begin + c;
-                const int tw_i = chunk % p.tiles_w;
-                const int th_i = (chunk / p.tiles_w) % p.tiles_h;
-                const int n = (chunk / (p.tiles_w * p.tiles_h)) * p.TNB;
-                const int h0 = th_i * p.TH, w0 = tw_i * p.TW;
-                const int tb = c & 1;
-                mbar_wait(&tempty[tb], ((uint32_t)(c >> 1) & 1u) ^ 1u);
+        // whole warp walks the schedule (uniform control flow); one elected lane issues the TMA loads
+        int it = 0;                                   // global stage counter
+        for (int c = 0; c < nchunks; ++c) {
+            const int chunk = c_begin + c;
+            const int tw_i = chunk % p.tiles_w;
+            const int th_i = (chunk / p.tiles_w) % p.tiles_h;
+            const int n = (chunk / (p.tiles_w * p.tiles_h)) * p.TNB;
+            const int h0 = th_i * p.TH, w0 = tw_i * p.TW;
+            const int tb = c & 1;
+            mbar_wait(&tempty[tb], ((uint32_t)(c >> 1) & 1u) ^ 1u);
+            if (elect_one()) {
                 mbar_expect_tx(&tfull[tb], T_BYTES);
 #pragma unroll
                 for (int j = 0; j < TB; ++j)
                     tma_load_4d(sT + tb * T_BYTES + j * TILE_BYTES, &maps.t, &tfull[tb], j * 32, w0, h0, n);
-                for (int g = 0; g < ng; ++g, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait(&empty[s], ((uint32_t)(it / STAGES) & 1u) ^ 1u);
+            }
+            __syncwarp();
+            for (int g = 0; g < ng; ++g, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(&empty[s], ((uint32_t)(it / STAGES) & 1u) ^ 1u);
+                if (elect_one()) {
                     const int b0 = (g_begin + g) * 4;
                     const int nb = min(4, p.nblk - b0);
                     mbar_expect_tx(&full[s], nb * TILE_BYTES);
@@ -157,33 +166,37 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
                                     p.blk_cb[b0 + j] * 32, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n);
                     }
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // a_major = b_major = MN (bits 15, 16); M = 128; N = BN; tf32 operands, fp32 accumulate
-            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                                       ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            int it = 0;
-            for (int c = 0; c < nchunks; ++c) {
-                const int tb = c & 1;
-                mbar_wait(&tfull[tb], (uint32_t)(c >> 1) & 1u);
-                for (int g = 0; g < ng; ++g, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1u);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_addr = smem_u32(sG + s * G_STAGE);
-                    const uint32_t b_addr = smem_u32(sT + tb * T_BYTES);
+        // a_major = b_major = MN (bits 15, 16); M = 128; N = BN; tf32 operands, fp32 accumulate
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        int it = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            const int tb = c & 1;
+            mbar_wait(&tfull[tb], (uint32_t)(c >> 1) & 1u);
+            const uint64_t bdesc = make_desc_mn_sw128(smem_u32(sT + tb * T_BYTES), TILE_BYTES);
+            for (int g = 0; g < ng; ++g, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t adesc = make_desc_mn_sw128(smem_u32(sG + s * G_STAGE), TILE_BYTES);
+                const uint32_t d = tmem_base + (uint32_t)(g * BN);
+                if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < CH / 8; ++kk)       // 8 pixels (= 8 rows = 1024 B) per instruction
-                        umma_tf32(tmem_base + (uint32_t)(g * BN), make_desc_mn_sw128(a_addr + kk * 1024, TILE_BYTES),
-                                  make_desc_mn_sw128(b_addr + kk * 1024, TILE_BYTES), idesc, (c > 0 || kk > 0) ? 1u : 0u);
+                    for (int kk = 0; kk < CH / 8; ++kk)       // 8 pixels (= 8 rows = 1024 B = 64 descriptor units) per instruction
+                        umma_tf32(d, adesc + 64 * kk, bdesc + 64 * kk, idesc, (c > 0 || kk > 0) ? 1u : 0u);
                     umma_commit(&empty[s]);
                 }
-                umma_commit(&tempty[tb]);
+                __syncwarp();
             }
-            umma_commit(accf);
+            if (elect_one()) umma_commit(&tempty[tb]);
+            __syncwarp();
         }
+        if (elect_one()) umma_commit(accf);
+        __syncwarp();
     } else {
         const int q = warp & 3;                  // TMEM lane quarter == block index within the M-group
         mbar_wait(accf, 0);
