@@ -490,9 +490,9 @@ int g2_gemm_f32(const float* A, const float* B, const float* bias, float* C, int
     G2_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0);
     const int tiles = g2_cdiv(M, 64) * g2_cdiv(N, 64);
     int splits = 1;
-    if (tiles < 148 && K >= 1024 && act == G2_ACT_NONE) {
+    if (tiles < 148 && K >= 512 && act == G2_ACT_NONE) {
         splits = (296 + tiles - 1) / tiles;
-        const int maxs = K / 256;
+        const int maxs = K / 128;
         if (splits > maxs) splits = maxs;
         if (splits < 1) splits = 1;
     }

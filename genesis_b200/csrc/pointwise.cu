@@ -233,6 +233,35 @@ int g2_sum_dim0_f32(const float* x, float* out, int N, long J, cudaStream_t stre
 
 }  // extern "C"
 
+// ------------------------------------------------------------------------------------------ weight packs
+// One pass over a torch-layout conv weight writes both tensor-core operand packs:
+//   packA[tap][co][ci_pad] (reduction over Ci: conv forward / conv-transpose forward)
+//   packB[tap][ci_pad][co] (reduction over Co: the matching data gradient); channels ci >= Ci are zero.
+// transposed = 0: w is Conv2d [Co,Ci,R,S]; 1: ConvTranspose2d [Ci,Co,R,S].
+namespace {
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, float* __restrict__ pa, float* __restrict__ pb, int Co, int Ci,
+                                        int Cip, int RS, int transposed) {
+    const long total = (long)RS * Co * Cip;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % Cip); const long t = i / Cip; const int co = (int)(t % Co); const int tap = (int)(t / Co);
+        float v = 0.f;
+        if (ci < Ci) v = __ldg(w + (transposed ? ((long)ci * Co + co) : ((long)co * Ci + ci)) * RS + tap);
+        pa[i] = v;
+        if (pb) pb[((long)tap * Cip + ci) * Co + co] = v;
+    }
+}
+}  // namespace
+
+extern "C" int g2_pack_conv_weight_f32(const float* w, float* packA, float* packB, int Co, int Ci, int Ci_pad, int RS,
+                                       int transposed, cudaStream_t stream) {
+    G2_CHECK_ARG(w && packA && Co > 0 && Ci > 0 && Ci_pad >= Ci && RS > 0);
+    const long total = (long)RS * Co * Ci_pad;
+    long blocks = (total + 255) / 256;
+    if (blocks > 148L * 8) blocks = 148L * 8;
+    pack_conv_weight_kernel<<<(int)blocks, 256, 0, stream>>>(w, packA, packB, Co, Ci, Ci_pad, RS, transposed);
+    G2_LAUNCH_RET();
+}
+
 // ------------------------------------------------------------------------------------------ optimiser
 // Fused Adam over a flat fp32 arena (reference train.py:175,263 uses torch.optim.Adam: lr, betas (0.9, 0.999),
 // eps 1e-8, no weight decay).  `step` is a device counter (float) so the kernel is CUDA-graph replayable;

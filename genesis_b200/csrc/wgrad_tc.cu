@@ -231,16 +231,19 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
     }
 }
 
-// dw = sum over splits of ws;  layout [taps][Cg][Ct] (outT = 0) or [taps][Ct][Cg] (outT = 1)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int taps, int Cg, int Ct, int outT) {
+// dw[tap*s_tap + a*s_a + b*s_b] (+)= sum over splits of ws[split][tap][a][b]   for a < a_lim, b < b_lim.
+// Packed layouts: [taps][Cg][Ct] = (Cg*Ct, Ct, 1), [taps][Ct][Cg] = (Cg*Ct, 1, Cg); torch Conv2d weight [Co,Ci,R,S] with
+// a = Ci, b = Co: (1, RS, Ci*RS); ConvTranspose2d weight [Ci,Co,R,S] with a = Co, b = Ci: (1, RS, Co*RS).
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int taps, int Cg, int Ct,
+                                    long s_tap, long s_a, long s_b, int a_lim, int b_lim, int accumulate) {
     const long total = (long)taps * Cg * Ct;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int b = (int)(i % Ct); const long t = i / Ct; const int a = (int)(t % Cg); const long tap = t / Cg;
+        if (a >= a_lim || b >= b_lim) continue;
         float s = 0.f;
         for (int k = 0; k < splits; ++k) s += __ldg(ws + (long)k * total + i);
-        if (outT) {
-            const int b = (int)(i % Ct); const long t = i / Ct; const int a = (int)(t % Cg); const long tap = t / Cg;
-            dw[(tap * Ct + b) * Cg + a] = s;
-        } else dw[i] = s;
+        float* dst = dw + tap * s_tap + a * s_a + b * s_b;
+        *dst = accumulate ? *dst + s : s;
     }
 }
 
@@ -310,8 +313,9 @@ long g2_conv_wgrad_tf32_workspace(int N, int Hg, int Wg, int Cg, int Ht, int Wt,
 
 // Same contract as g2_conv_wgrad_f32 (TF32 operands, fp32 accumulation); `ws` is caller-owned scratch of
 // g2_conv_wgrad_tf32_workspace(...) bytes.
-int g2_conv_wgrad_tf32(const float* g, const float* t, float* dw, float* ws, int N, int Hg, int Wg, int Cg, int Ht, int Wt,
-                       int Ct, int R, int S, int stride, int pad, int outT, cudaStream_t stream) {
+static int wgrad_impl(const float* g, const float* t, float* dw, float* ws, int N, int Hg, int Wg, int Cg, int Ht, int Wt,
+                      int Ct, int R, int S, int stride, int pad, long s_tap, long s_a, long s_b, int a_lim, int b_lim,
+                      int accumulate, cudaStream_t stream) {
     using namespace wg;
     G2_CHECK_ARG(g && t && dw && ws && N > 0);
     Plan pl;
@@ -376,8 +380,23 @@ int g2_conv_wgrad_tf32(const float* g, const float* t, float* dw, float* ws, int
     const long total = (long)R * S * Cg * Ct;
     long blocks = (total + 255) / 256;
     if (blocks > 148L * 8) blocks = 148L * 8;
-    wgrad_reduce_kernel<<<(int)blocks, 256, 0, stream>>>(ws, dw, pl.splits, R * S, Cg, Ct, outT);
+    wgrad_reduce_kernel<<<(int)blocks, 256, 0, stream>>>(ws, dw, pl.splits, R * S, Cg, Ct, s_tap, s_a, s_b, a_lim, b_lim, accumulate);
     G2_LAUNCH_RET();
+}
+
+int g2_conv_wgrad_tf32(const float* g, const float* t, float* dw, float* ws, int N, int Hg, int Wg, int Cg, int Ht, int Wt,
+                       int Ct, int R, int S, int stride, int pad, int outT, cudaStream_t stream) {
+    if (outT) return wgrad_impl(g, t, dw, ws, N, Hg, Wg, Cg, Ht, Wt, Ct, R, S, stride, pad, (long)Cg * Ct, 1, Cg, Cg, Ct, 0, stream);
+    return wgrad_impl(g, t, dw, ws, N, Hg, Wg, Cg, Ht, Wt, Ct, R, S, stride, pad, (long)Cg * Ct, Ct, 1, Cg, Ct, 0, stream);
+}
+
+// Weight gradient written straight into a tensor of arbitrary (tap, a, b) strides -- e.g. the torch-layout .grad of the
+// parameter -- optionally accumulating, restricted to a < a_lim, b < b_lim (zero-padded channels are dropped).
+int g2_conv_wgrad_tf32_to(const float* g, const float* t, float* dw, float* ws, int N, int Hg, int Wg, int Cg, int Ht, int Wt,
+                          int Ct, int R, int S, int stride, int pad, long s_tap, long s_a, long s_b, int a_lim, int b_lim,
+                          int accumulate, cudaStream_t stream) {
+    G2_CHECK_ARG(a_lim > 0 && a_lim <= Cg && b_lim > 0 && b_lim <= Ct);
+    return wgrad_impl(g, t, dw, ws, N, Hg, Wg, Cg, Ht, Wt, Ct, R, S, stride, pad, s_tap, s_a, s_b, a_lim, b_lim, accumulate, stream);
 }
 
 }  // extern "C"

@@ -194,7 +194,7 @@ def gated_forward(layer, x, training):
     if layer.transposed:
         y = ops.conv_transpose2d(x, conv.weight, conv.bias, layer.stride, layer.pad)
     else:
-        y = ops.conv2d(x, pad_cin(conv.weight, x.shape[3]), conv.bias, layer.stride, layer.pad)
+        y = ops.conv2d(x, conv.weight, conv.bias, layer.stride, layer.pad)
     return gate_norm(layer, y, training)
 
 
@@ -294,7 +294,7 @@ def comp_encode(enc, packed, act):
     m = enc.module
     h = packed
     for i in (0, 2, 4, 6):
-        h = ops.conv2d(h, pad_cin(m[i].weight, h.shape[3]), m[i].bias, 2, 1, act)
+        h = ops.conv2d(h, m[i].weight, m[i].bias, 2, 1, act)
     N, fh, fw, c = h.shape
     w = m[9].weight                                        # [256, c*fh*fw] in NCHW flatten order
     wm = w.view(w.shape[0], c, fh, fw).permute(0, 2, 3, 1).reshape(w.shape[0], -1)
@@ -327,7 +327,7 @@ def conv_norm_relu(block, h, norm):
     """ConvINReLU / ConvGNReLU (reference modules/blocks.py:151-165) on NHWC h: 3x3 p1 conv without bias, then the
     per-sample norm fused with ReLU."""
     conv, nrm = block[0], block[1]
-    y = ops.conv2d(h, pad_cin(conv.weight, h.shape[3]), None, 1, 1)
+    y = ops.conv2d(h, conv.weight, None, 1, 1)
     if norm == 'in':
         return ops.norm_post(y, nrm.weight, nrm.bias, mode=ops.NORM_INSTANCE, post=ops.POST_RELU, eps=nrm.eps)
     return ops.norm_post(y, nrm.weight, nrm.bias, mode=ops.NORM_GROUP, groups=nrm.num_groups, post=ops.POST_RELU,

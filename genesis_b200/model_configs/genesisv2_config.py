@@ -132,10 +132,7 @@ class GenesisV2(nn.Module, _g.NoiseMixin):
                        z.new_zeros(N, d, d, cpad - z.shape[1] - 2)], dim=3).contiguous()
         for ci in (1, 4, 7, 10):
             conv, gn = dm[ci], dm[ci + 1]
-            w = conv.weight
-            if w.shape[0] != h.shape[3]:                     # zero rows for the zero-padded input channels
-                w = torch.cat([w, w.new_zeros(h.shape[3] - w.shape[0], *w.shape[1:])], dim=0)
-            y = ops.conv_transpose2d(h, w, conv.bias, 2, 2)
+            y = ops.conv_transpose2d(h, conv.weight, conv.bias, 2, 2)     # the op zero-pads the weight to h's channel count
             h = ops.norm_post(y, gn.weight, gn.bias, mode=ops.NORM_GROUP, groups=gn.num_groups, post=ops.POST_RELU, eps=gn.eps)
         return ops.out1x1(h, dm[13].weight, dm[13].bias, 3 if self.pixel_bound else 0)
 

@@ -129,46 +129,139 @@ def to_nchw(x):
 
 
 # ----------------------------------------------------------------------------------------- conv
+_DIRECT = {'on': False}
+
+
+def set_direct_grad(on):
+    """True (set by trainer.TrainStep, which owns flat, pre-zeroed gradient arenas): weight / bias gradients of the conv
+    and linear operators are ACCUMULATED by the kernels straight into `param.grad` (torch layout) and the autograd
+    Functions return None for them -- no permute copy and no AccumulateGrad add per parameter.
+    False (drop-in mode under the reference's train.py): gradients are returned to autograd as usual."""
+    _DIRECT['on'] = bool(on)
+
+
+def _direct(p):
+    return (_DIRECT['on'] and p is not None and p.is_leaf and p.requires_grad and p.grad is not None
+            and p.grad.is_contiguous() and p.grad.data_ptr() % 16 == 0)
+
+
+def _pad_dim(w, dim, size):
+    if w.shape[dim] == size:
+        return w
+    shape = list(w.shape)
+    shape[dim] = size - w.shape[dim]
+    return torch.cat([w, w.new_zeros(shape)], dim=dim)
+
+
+def _bias_grad(dpre, b, C):
+    """Bias gradient = column sum of dpre [rows, C]; accumulated into b.grad in direct mode (returns None)."""
+    rows = dpre.numel() // C
+    if _direct(b) and not (C > 1024 and C % 4 == 0):
+        _call('g2_colsum_f32', dpre, b.grad, rows, C, 1)
+        return None
+    return _colsum(dpre, C, dpre)
+
+
+def _conv_fwd_common(ctx, x, w, b, stride, pad, act, transposed):
+    """Shared forward of Conv2d (mode 0) / ConvTranspose2d (mode 1, output_padding = stride-1).  The weight may have fewer
+    input channels than x (x zero-padded to a 32-channel k-block): the missing channels are zero in the packs."""
+    x = _c(x)
+    N, H, W, Cx = x.shape
+    if transposed:
+        Ci, Co, R, S = w.shape
+        op = stride - 1
+        Ho = (H - 1) * stride - 2 * pad + R + op
+        Wo = (W - 1) * stride - 2 * pad + S + op
+    else:
+        Co, Ci, R, S = w.shape
+        Ho = (H + 2 * pad - R) // stride + 1
+        Wo = (W + 2 * pad - S) // stride + 1
+    assert Ci <= Cx, (x.shape, w.shape)
+    mode_f, mode_d = (1, 0) if transposed else (0, 1)
+    wd = w.detach()
+    out = _new(x, N, Ho, Wo, Co)
+    pb = None
+    if _tc_ok(N, H, W, Cx, Ho, Wo, Co, R, S, stride, pad, mode_f):
+        pa = _new(x, R * S, Co, Cx)
+        if ctx.needs_input_grad[0] and _tc_ok(N, Ho, Wo, Co, H, W, Cx, R, S, stride, pad, mode_d):
+            pb = _new(x, R * S, Cx, Co)
+        _call('g2_pack_conv_weight_f32', _c(wd), pa, pb, Co, Ci, Cx, R * S, 1 if transposed else 0)
+        _call('g2_conv_igemm_tf32', x, pa, b, out, N, H, W, Cx, Ho, Wo, Co, R, S, stride, pad, mode_f, act)
+    else:
+        wp = _pad_dim(wd, 0 if transposed else 1, Cx)
+        perm = (2, 3, 0, 1) if transposed else (2, 3, 1, 0)          # [R,S,Cred,Cout]
+        _call('g2_conv_igemm_f32', x, wp.permute(*perm).contiguous(), b, None, out, N, H, W, Cx, Ho, Wo, Co, R, S, stride, pad,
+              mode_f, 0, act)
+    ctx.save_for_backward(x, wd, out if act != ACT_NONE else None, pb)
+    ctx.params = (w, b)
+    ctx.cfg = (stride, pad, act, b is not None, transposed)
+    return out
+
+
+def _conv_bwd_common(ctx, dout):
+    x, wd, out, pb = ctx.saved_tensors
+    w_param, b_param = ctx.params
+    stride, pad, act, has_b, transposed = ctx.cfg
+    N, H, W, Cx = x.shape
+    if transposed:
+        Ci, Co, R, S = wd.shape
+    else:
+        Co, Ci, R, S = wd.shape
+    dout = _c(dout)
+    _, Ho, Wo, _ = dout.shape
+    mode_d = 0 if transposed else 1
+    dpre = _act_bwd(dout, out, act)
+    dx = dw = db = None
+    if ctx.needs_input_grad[0]:
+        dx = torch.empty_like(x)
+        if pb is not None:
+            _call('g2_conv_igemm_tf32', dpre, pb, None, dx, N, Ho, Wo, Co, H, W, Cx, R, S, stride, pad, mode_d, ACT_NONE)
+        else:   # data gradient = the other mode with the reduction over Co: SIMT pack [R,S,Cx,Co] + wT (or the TC pack)
+            wp = _pad_dim(wd, 0 if transposed else 1, Cx)
+            perm = (2, 3, 0, 1) if transposed else (2, 3, 1, 0)      # [R,S,Cx,Co]
+            _conv_any(dpre, wp, None, dx, (N, Ho, Wo, Co, H, W, Cx), R, S, stride, pad, mode_d, ACT_NONE, perm, (perm, 1))
+    if ctx.needs_input_grad[1]:
+        # conv: g = x (a = Cx), t = dpre (b = Co);  conv-transpose: g = dpre (a = Co), t = x (b = Cx)
+        if transposed:
+            g, t, dims = dpre, x, (N, Ho, Wo, Co, H, W, Cx)
+            strides, lims = (1, R * S, Co * R * S), (Co, Ci)         # torch [Ci,Co,R,S]: a = Co, b = Ci
+        else:
+            g, t, dims = x, dpre, (N, H, W, Cx, Ho, Wo, Co)
+            strides, lims = (1, R * S, Ci * R * S), (Ci, Co)         # torch [Co,Ci,R,S]: a = Ci, b = Co
+        ws_bytes = 0
+        if _PRECISION['mode'] == 'tf32':
+            ws_bytes = _lib.lib().query('g2_conv_wgrad_tf32_workspace', *dims, R, S, stride)
+        if ws_bytes > 0:
+            ws = _new(x, ws_bytes // 4)
+            if _direct(w_param):
+                _call('g2_conv_wgrad_tf32_to', g, t, w_param.grad, ws, *dims, R, S, stride, pad, *strides, *lims, 1)
+            else:
+                dw = torch.empty_like(wd)
+                _call('g2_conv_wgrad_tf32_to', g, t, dw, ws, *dims, R, S, stride, pad, *strides, *lims, 0)
+        else:
+            if transposed:
+                dwp = _new(x, R, S, Cx, Co)
+                _call('g2_conv_wgrad_f32', g, t, dwp, *dims, R, S, stride, pad, 1)
+                dw = dwp.permute(2, 3, 0, 1)[:Ci].contiguous()
+            else:
+                dwp = _new(x, R, S, Cx, Co)
+                _call('g2_conv_wgrad_f32', g, t, dwp, *dims, R, S, stride, pad, 0)
+                dw = dwp.permute(3, 2, 0, 1)[:, :Ci].contiguous()
+    if has_b and ctx.needs_input_grad[2]:
+        db = _bias_grad(dpre, b_param, Co)
+    return dx, dw, db, None, None, None
+
+
 class _Conv(Function):
-    """nn.Conv2d on NHWC activations; w in torch layout [Co,Ci,R,S]."""
+    """nn.Conv2d on NHWC activations; w in torch layout [Co,Ci,R,S] (Ci may be smaller than x's zero-padded channels)."""
 
     @staticmethod
     def forward(ctx, x, w, b, stride, pad, act):
-        x = _c(x)
-        N, H, W, Ci = x.shape
-        Co, Ci2, R, S = w.shape
-        assert Ci == Ci2, (x.shape, w.shape)
-        Ho = (H + 2 * pad - R) // stride + 1
-        Wo = (W + 2 * pad - S) // stride + 1
-        wd = w.detach()
-        out = _new(x, N, Ho, Wo, Co)
-        _conv_any(x, wd, b, out, (N, H, W, Ci, Ho, Wo, Co), R, S, stride, pad, 0, act,
-                  (2, 3, 0, 1), ((2, 3, 1, 0), 0))
-        ctx.save_for_backward(x, wd, out if act != ACT_NONE else None)
-        ctx.cfg = (stride, pad, act, b is not None)
-        return out
+        return _conv_fwd_common(ctx, x, w, b, stride, pad, act, False)
 
     @staticmethod
     def backward(ctx, dout):
-        x, wd, out = ctx.saved_tensors
-        stride, pad, act, has_b = ctx.cfg
-        N, H, W, Ci = x.shape
-        Co, _, R, S = wd.shape
-        dout = _c(dout)
-        _, Ho, Wo, _ = dout.shape
-        dpre = _act_bwd(dout, out, act)
-        dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
-            # data gradient = mode 1 with reduction over Co: tensor-core pack [R,S,Ci,Co]; SIMT pack [R,S,Ci,Co] + wT
-            _conv_any(dpre, wd, None, dx, (N, Ho, Wo, Co, H, W, Ci), R, S, stride, pad, 1, ACT_NONE,
-                      (2, 3, 1, 0), ((2, 3, 1, 0), 1))
-        if ctx.needs_input_grad[1]:
-            dwp = _wgrad_any(x, dpre, (N, H, W, Ci, Ho, Wo, Co), R, S, stride, pad, 0, x)
-            dw = dwp.permute(3, 2, 0, 1).contiguous()
-        if has_b and ctx.needs_input_grad[2]:
-            db = _colsum(dpre, Co, dpre)
-        return dx, dw, db, None, None, None
+        return _conv_bwd_common(ctx, dout)
 
 
 def conv2d(x, w, b=None, stride=1, pad=0, act=None):
@@ -180,42 +273,11 @@ class _ConvT(Function):
 
     @staticmethod
     def forward(ctx, x, w, b, stride, pad, act):
-        x = _c(x)
-        N, H, W, Ci = x.shape
-        Ci2, Co, R, S = w.shape
-        assert Ci == Ci2, (x.shape, w.shape)
-        op = stride - 1
-        Ho = (H - 1) * stride - 2 * pad + R + op
-        Wo = (W - 1) * stride - 2 * pad + S + op
-        wd = w.detach()
-        out = _new(x, N, Ho, Wo, Co)
-        _conv_any(x, wd, b, out, (N, H, W, Ci, Ho, Wo, Co), R, S, stride, pad, 1, act,
-                  (2, 3, 1, 0), ((2, 3, 0, 1), 0))
-        ctx.save_for_backward(x, wd, out if act != ACT_NONE else None)
-        ctx.cfg = (stride, pad, act, b is not None)
-        return out
+        return _conv_fwd_common(ctx, x, w, b, stride, pad, act, True)
 
     @staticmethod
     def backward(ctx, dout):
-        x, wd, out = ctx.saved_tensors
-        stride, pad, act, has_b = ctx.cfg
-        N, H, W, Ci = x.shape
-        _, Co, R, S = wd.shape
-        dout = _c(dout)
-        _, Ho, Wo, _ = dout.shape
-        dpre = _act_bwd(dout, out, act)
-        dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
-            # data gradient = mode 0 with reduction over Co: tensor-core pack [R,S,Ci,Co]; SIMT pack [R,S,Ci,Co] + wT
-            _conv_any(dpre, wd, None, dx, (N, Ho, Wo, Co, H, W, Ci), R, S, stride, pad, 0, ACT_NONE,
-                      (2, 3, 0, 1), ((2, 3, 0, 1), 1))
-        if ctx.needs_input_grad[1]:
-            dwp = _wgrad_any(dpre, x, (N, Ho, Wo, Co, H, W, Ci), R, S, stride, pad, 1, x)
-            dw = dwp.permute(2, 3, 0, 1).contiguous()
-        if has_b and ctx.needs_input_grad[2]:
-            db = _colsum(dpre, Co, dpre)
-        return dx, dw, db, None, None, None
+        return _conv_bwd_common(ctx, dout)
 
 
 def conv_transpose2d(x, w, b=None, stride=1, pad=0, act=None):
@@ -224,32 +286,36 @@ def conv_transpose2d(x, w, b=None, stride=1, pad=0, act=None):
 
 # ----------------------------------------------------------------------------------------- linear
 class _Linear(Function):
-    """y = act(x @ w.T + b);  x [M,K], w [N,K]."""
+    """y = act(x @ w.T + b);  x [M,K], w [N,K].  Large products run on the tensor cores (TF32); the many small ones
+    (LSTM steps, latent heads: a few MFLOP) on the exact-fp32 SIMT GEMM, which takes transposed operands in place (no
+    transpose copies), fuses the activation and can accumulate the weight gradient straight into `w.grad`."""
 
     @staticmethod
     def forward(ctx, x, w, b, act):
         x = _c(x)
-        w = _c(w)
+        wd = _c(w.detach())
         M, K = x.shape
-        N = w.shape[0]
+        N = wd.shape[0]
         y = _new(x, M, N)
-        if _gemm_tc_ok(N, K):
-            _call('g2_gemm_tf32', x, w, b, y, M, N, K)
+        if _gemm_tc_ok(M, N, K):
+            _call('g2_gemm_tf32', x, wd, b, y, M, N, K)
+            if act != ACT_NONE:      # split-K GEMMs cannot fuse the activation; keep it a separate pass
+                if N % 4 != 0:
+                    raise RuntimeError('linear with activation needs N % 4 == 0')
+                pre = y
+                y = torch.empty_like(pre)
+                _call('g2_bcast_add_act_f32', pre, _zeros_row(pre, N), y, M, 1, N, act)
         else:
-            _call('g2_gemm_f32', x, w, b, y, M, N, K, K, K, N, 0, 1, ACT_NONE, 0)
-        if act != ACT_NONE:      # split-K GEMMs cannot fuse the activation; keep it a separate pass
-            if N % 4 != 0:
-                raise RuntimeError('linear with activation needs N % 4 == 0')
-            pre = y
-            y = torch.empty_like(pre)
-            _call('g2_bcast_add_act_f32', pre, _zeros_row(pre, N), y, M, 1, N, act)
-        ctx.save_for_backward(x, w, y if act != ACT_NONE else None)
+            _call('g2_gemm_f32', x, wd, b, y, M, N, K, K, K, N, 0, 1, act, 0)
+        ctx.save_for_backward(x, wd, y if act != ACT_NONE else None)
+        ctx.params = (w, b)
         ctx.cfg = (act, b is not None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, w, y = ctx.saved_tensors
+        w_param, b_param = ctx.params
         act, has_b = ctx.cfg
         M, K = x.shape
         N = w.shape[0]
@@ -257,23 +323,32 @@ class _Linear(Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            if _gemm_tc_ok(K, N):
+            if _gemm_tc_ok(M, K, N):
                 _call('g2_gemm_tf32', dpre, w.t().contiguous(), None, dx, M, K, N)
             else:
                 _call('g2_gemm_f32', dpre, w, None, dx, M, K, N, N, K, K, 0, 0, ACT_NONE, 0)
         if ctx.needs_input_grad[1]:
-            dw = torch.empty_like(w)
-            if _gemm_tc_ok(K, M):
+            direct = _direct(w_param)
+            if _gemm_tc_ok(N, K, M):
+                dw = torch.empty_like(w)
                 _call('g2_gemm_tf32', dpre.t().contiguous(), x.t().contiguous(), None, dw, N, K, M)
+                if direct:
+                    w_param.grad.add_(dw)
+                    dw = None
+            elif direct:
+                _call('g2_gemm_f32', dpre, x, None, w_param.grad, N, K, M, N, K, K, 1, 0, ACT_NONE, 1)
             else:
+                dw = torch.empty_like(w)
                 _call('g2_gemm_f32', dpre, x, None, dw, N, K, M, N, K, K, 1, 0, ACT_NONE, 0)
         if has_b and ctx.needs_input_grad[2]:
-            db = _colsum(dpre, N, dpre)
+            db = _bias_grad(dpre, b_param, N)
         return dx, dw, db, None
 
 
-def _gemm_tc_ok(n_out, k_red):
-    """g2_gemm_tf32 needs the reduction dim % 32 == 0 and the output width in {32,64,128} or % 64 == 0."""
+def _gemm_tc_ok(m_rows, n_out, k_red):
+    """g2_gemm_tf32 needs the reduction dim % 32 == 0 and the output width in {32,64,128} or % 64 == 0.  Measured on
+    B200: even for the LSTM-step sized products (a few MFLOP) the tensor-core kernel (~6-10 us, latency-bound) beats the
+    un-pipelined SIMT GEMM (20-70 us), so every supported shape goes to it."""
     return (_PRECISION['mode'] == 'tf32' and k_red % 32 == 0 and k_red >= 64
             and (n_out in (32, 64, 128) or n_out % 64 == 0))
 

@@ -8,7 +8,7 @@ arena so every rank updates GECO's beta identically (replaces nn.DataParallel, t
 import torch
 import torch.distributed as dist
 
-from . import _lib
+from . import _lib, ops
 
 
 class GecoState(object):
@@ -143,11 +143,17 @@ class TrainStep(object):
         return self._step_eager(x)
 
     def _step_eager(self, x):
-        recon, losses, stats, att, comp = self.model(x)
-        err, kl = self.loss_terms(losses)
-        beta = self.geco.beta if self.geco is not None else 1.0
-        loss = err + beta * kl
-        loss.backward()
+        # the arena gradients are pre-zeroed and re-zeroed by the fused Adam kernel, so the conv / linear kernels may
+        # accumulate weight and bias gradients straight into p.grad (no permute copy + AccumulateGrad add per parameter)
+        ops.set_direct_grad(True)
+        try:
+            recon, losses, stats, att, comp = self.model(x)
+            err, kl = self.loss_terms(losses)
+            beta = self.geco.beta if self.geco is not None else 1.0
+            loss = err + beta * kl
+            loss.backward()
+        finally:
+            ops.set_direct_grad(False)
         tail = self.arena.tail
         with torch.no_grad():
             gerr, gkl = self.arena.exchange(err.detach(), kl.detach(), self.world)      # ONE exchange per step

@@ -173,6 +173,17 @@ long g2_conv_wgrad_tf32_workspace(int N, int Hg, int Wg, int Cg, int Ht, int Wt,
 int g2_conv_wgrad_tf32(const float* g, const float* t, float* dw, float* ws, int N, int Hg, int Wg, int Cg, int Ht,
                        int Wt, int Ct, int R, int S, int stride, int pad, int outT, g2_stream_t stream);
 /* C[M,N] = A[M,K] W[N,K]^T + bias[N] */
+/* As g2_conv_wgrad_tf32, but dw is addressed as dw[tap*s_tap + a*s_a + b*s_b] for a < a_lim (channel of g), b < b_lim
+ * (channel of t) -- e.g. the torch-layout .grad of the parameter (Conv2d [Co,Ci,R,S], a = Ci, b = Co: strides
+ * (1, R*S, Ci*R*S)) -- and is accumulated into when accumulate != 0.  Replaces the permute + AccumulateGrad add. */
+int g2_conv_wgrad_tf32_to(const float* g, const float* t, float* dw, float* ws, int N, int Hg, int Wg, int Cg, int Ht,
+                          int Wt, int Ct, int R, int S, int stride, int pad, long s_tap, long s_a, long s_b, int a_lim,
+                          int b_lim, int accumulate, g2_stream_t stream);
+/* Both tensor-core operand packs of a torch-layout conv weight in one pass: packA[tap][co][ci_pad] (forward) and
+ * packB[tap][ci_pad][co] (data gradient; may be NULL); input channels >= Ci are zero.  transposed: 0 = Conv2d
+ * [Co,Ci,R,S], 1 = ConvTranspose2d [Ci,Co,R,S]. */
+int g2_pack_conv_weight_f32(const float* w, float* packA, float* packB, int Co, int Ci, int Ci_pad, int RS,
+                            int transposed, g2_stream_t stream);
 int g2_gemm_tf32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K,
                  g2_stream_t stream);
 

@@ -5,12 +5,17 @@ import os
 from genesis_b200 import _lib
 
 
+# host-only queries / switches: no launch, no stream
+QUERIES = ('g2_abi_version', 'g2_conv_tf32_supported', 'g2_conv_wgrad_tf32_workspace', 'g2_conv_halo_enable',
+           'g2_conv_halo_supported', 'g2_conv_halo_plan')
+
+
 def test_header_parses():
     protos = _lib.parse_header()
     assert len(protos) >= 20
     for name, sig in protos.items():
         assert name.startswith('g2_')
-        if name not in ('g2_abi_version', 'g2_conv_tf32_supported', 'g2_conv_wgrad_tf32_workspace'):
+        if name not in QUERIES:
             assert sig[-1][2] == 'stream', name     # every compute entry point takes the stream last
 
 
