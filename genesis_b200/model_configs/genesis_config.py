@@ -97,6 +97,7 @@ class Genesis(nn.Module, NoiseMixin):
         if not hasattr(cfg, 'comp_symmetric'):
             cfg.comp_symmetric = False
         self.debug = cfg.debug
+        self.side_stream = True         # overlap the prior / KL branch with the decoders (see forward)
         assert cfg.montecarlo_kl == True  # noqa: E712  (reference genesis_config.py:80)
         if cfg.comp_symmetric or not self.two_stage or self.K_steps < 2:
             raise NotImplementedError('engine covers the default two-stage GENESIS (SURVEY.md section 8f.4)')
@@ -152,45 +153,65 @@ class Genesis(nn.Module, NoiseMixin):
         K, B = self.K_steps, x.shape[0]
         x = x.contiguous().float()
         log_m, log_s, att_stats = self._masks(x)                     # [K,B,1,H,W], [K+1,B,1,H,W]
+        z_k = att_stats.z_k
+        # The prior / KL branch (LSTM prior over z_k, prior MLP, MC-KL sums: ~250 tiny latency-bound kernels on [B,64]
+        # tensors) does not feed the decoders, so it runs on a side stream beside the large decoder kernels.  Autograd
+        # replays each node's backward on its forward stream, so the overlap carries to the backward pass; under CUDA
+        # graph capture this becomes a parallel branch of the graph.
+        cur = torch.cuda.current_stream()
+        side = ops.side_stream(x.device) if (self.side_stream and torch.is_grad_enabled()) else cur
+        if side is not cur:
+            side.wait_stream(cur)
+            for t_ in z_k + att_stats.mu_k + att_stats.sigma_k:      # allocated on `cur`, read (fwd and bwd) on `side`
+                t_.record_stream(side)
+        with torch.cuda.stream(side):
+            # --- KL terms of the mask latents (reference genesis_config.py:198-228, 288-343)
+            if self.autoreg_prior:
+                pmu, psig = H.autoreg_prior(z_k, self.prior_lstm, self.prior_linear)
+            else:
+                pmu, psig = [], []
+            kl_m_k = [H.mc_kl(z_k[0], att_stats.mu_k[0], att_stats.sigma_k[0])]
+            for k in range(1, K):
+                if self.autoreg_prior:
+                    kl_m_k.append(H.mc_kl(z_k[k], att_stats.mu_k[k], att_stats.sigma_k[k], pmu[k - 1], psig[k - 1]))
+                else:
+                    kl_m_k.append(H.mc_kl(z_k[k], att_stats.mu_k[k], att_stats.sigma_k[k]))
+            if self.comp_prior:
+                pm = self.prior_mlp
+                t = ops.linear(torch.cat(z_k, 0), pm[0].weight, pm[0].bias, 'elu')
+                t = ops.linear(t, pm[2].weight, pm[2].bias, 'elu')
+                a, b = torch.chunk(ops.linear(t, pm[4].weight, pm[4].bias), 2, dim=1)
+                cpmu, cpsig = torch.tanh(a), H.to_prior_sigma(b)
         # --- component VAE (reference component_vae.py:45-81), K slots batched k-major
         cv = self.comp_vae
         enc = H.comp_encode(cv.encoder_module, ops.comp_pack(x, log_m, 32 if ops.get_precision() == 'tf32' else 4), 'elu')
         cmu, cps = torch.chunk(enc, 2, dim=1)
         csig = H.to_sigma(cps)
         cz = cmu + csig * self._normal(cmu.shape, x)
+        if side is not cur:
+            side.wait_stream(cur)           # cz, cmu, csig are ready
+            for t_ in (cz, cmu, csig, enc):
+                t_.record_stream(side)
+        with torch.cuda.stream(side):
+            # --- KL of the component latents (reference genesis_config.py:230-259)
+            kl = H.mc_kl(cz, cmu, csig, cpmu, cpsig) if self.comp_prior else H.mc_kl(cz, cmu, csig)
         x_r = H.broadcast_decode(cv.decoder_module, cz, 'elu', 3 if self.pixel_bound else 0)
         x_r = x_r.view(K, B, x.shape[1], self.img_size, self.img_size)
         # --- reconstruction + mixture likelihood (reference genesis_config.py:188-196)
         err, recon, _ = ops.mixture_nll(x, x_r, log_m, self.std.reshape(-1), False)
+        if side is not cur:
+            cur.wait_stream(side)           # join: the KL terms are consumed by the caller on the current stream
+            for t_ in kl_m_k + [kl] + pmu + psig + ([cpmu, cpsig] if self.comp_prior else []):
+                t_.record_stream(cur)
         losses = AttrDict()
         losses['err'] = err
-        # --- KL terms (reference genesis_config.py:198-259)
-        z_k = att_stats.z_k
-        if self.autoreg_prior:
-            pmu, psig = H.autoreg_prior(z_k, self.prior_lstm, self.prior_linear)
-        else:
-            pmu, psig = [], []
-        losses['kl_m_k'] = [H.mc_kl(z_k[0], att_stats.mu_k[0], att_stats.sigma_k[0])]
-        for k in range(1, K):
-            if self.autoreg_prior:
-                losses['kl_m_k'].append(H.mc_kl(z_k[k], att_stats.mu_k[k], att_stats.sigma_k[k], pmu[k - 1], psig[k - 1]))
-            else:
-                losses['kl_m_k'].append(H.mc_kl(z_k[k], att_stats.mu_k[k], att_stats.sigma_k[k]))
+        losses['kl_m_k'] = kl_m_k
         att_stats['pmu_k'], att_stats['psigma_k'] = pmu, psig
         comp_stats = AttrDict(mu_k=list(torch.chunk(cmu, K, 0)), sigma_k=list(torch.chunk(csig, K, 0)),
                               z_k=list(torch.chunk(cz, K, 0)))
-        losses['kl_l_k'] = []
         if self.comp_prior:
-            pm = self.prior_mlp
-            t = ops.linear(torch.cat(z_k, 0), pm[0].weight, pm[0].bias, 'elu')
-            t = ops.linear(t, pm[2].weight, pm[2].bias, 'elu')
-            a, b = torch.chunk(ops.linear(t, pm[4].weight, pm[4].bias), 2, dim=1)
-            cpmu, cpsig = torch.tanh(a), H.to_prior_sigma(b)
             comp_stats['pmu_k'] = list(torch.chunk(cpmu, K, 0))
             comp_stats['psigma_k'] = list(torch.chunk(cpsig, K, 0))
-            kl = H.mc_kl(cz, cmu, csig, cpmu, cpsig)
-        else:
-            kl = H.mc_kl(cz, cmu, csig)
         losses['kl_l_k'] = list(torch.chunk(kl, K, 0))
         # --- tracking (reference genesis_config.py:262-264)
         log_m_k = list(log_m.unbind(0))

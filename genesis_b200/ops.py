@@ -33,6 +33,45 @@ def _call(name, *args):
     _lib.call(name, *args)
 
 
+_SIDE = {}
+
+
+def side_stream(device, idx=0):
+    """Auxiliary CUDA streams per device for work that does not feed the critical path: idx 0 = the prior / KL branch of
+    the forward (and its backward), idx 1 = parameter-gradient kernels in direct-gradient mode."""
+    dev = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    key = (dev, idx)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
+
+
+class _GradStream(object):
+    """Direct-gradient mode: weight / bias gradient kernels write into param.grad and nothing reads them before the
+    optimiser, so they are enqueued on side stream 1 (fork after the operands are ready; trainer.TrainStep joins once
+    after backward).  The data-gradient chain -- the critical path of the backward pass -- never waits for them."""
+
+    def __init__(self, *operands):
+        self.cur = torch.cuda.current_stream()
+        self.side = side_stream(operands[0].device, 1)
+        self.side.wait_stream(self.cur)
+        for t in operands:
+            t.record_stream(self.side)
+        self.ctx = torch.cuda.stream(self.side)
+
+    def __enter__(self):
+        return self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        return self.ctx.__exit__(*a)
+
+
+def join_grad_stream(device):
+    """Make the current stream wait for all parameter-gradient kernels queued on the gradient side stream."""
+    if (torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device(), 1) in _SIDE:
+        torch.cuda.current_stream().wait_stream(side_stream(device, 1))
+
+
 def _tc_ok(N, Hi, Wi, Ci, Ho, Wo, Co, R, S, stride, pad, mode):
     if _PRECISION['mode'] != 'tf32':
         return False
@@ -231,13 +270,17 @@ def _conv_bwd_common(ctx, dout):
         ws_bytes = 0
         if _PRECISION['mode'] == 'tf32':
             ws_bytes = _lib.lib().query('g2_conv_wgrad_tf32_workspace', *dims, R, S, stride)
-        if ws_bytes > 0:
-            ws = _new(x, ws_bytes // 4)
-            if _direct(w_param):
+        if ws_bytes > 0 and _direct(w_param):
+            with _GradStream(g, t):
+                ws = _new(x, ws_bytes // 4)
                 _call('g2_conv_wgrad_tf32_to', g, t, w_param.grad, ws, *dims, R, S, stride, pad, *strides, *lims, 1)
-            else:
-                dw = torch.empty_like(wd)
-                _call('g2_conv_wgrad_tf32_to', g, t, dw, ws, *dims, R, S, stride, pad, *strides, *lims, 0)
+                if has_b and ctx.needs_input_grad[2] and _direct(b_param):
+                    _bias_grad(dpre, b_param, Co)
+                    has_b = False
+        elif ws_bytes > 0:
+            ws = _new(x, ws_bytes // 4)
+            dw = torch.empty_like(wd)
+            _call('g2_conv_wgrad_tf32_to', g, t, dw, ws, *dims, R, S, stride, pad, *strides, *lims, 0)
         else:
             if transposed:
                 dwp = _new(x, R, S, Cx, Co)
@@ -328,15 +371,20 @@ class _Linear(Function):
             else:
                 _call('g2_gemm_f32', dpre, w, None, dx, M, K, N, N, K, K, 0, 0, ACT_NONE, 0)
         if ctx.needs_input_grad[1]:
-            direct = _direct(w_param)
-            if _gemm_tc_ok(N, K, M):
+            if _direct(w_param):
+                with _GradStream(dpre, x):
+                    if _gemm_tc_ok(N, K, M):
+                        dwt = torch.empty_like(w)
+                        _call('g2_gemm_tf32', dpre.t().contiguous(), x.t().contiguous(), None, dwt, N, K, M)
+                        w_param.grad.add_(dwt)
+                    else:
+                        _call('g2_gemm_f32', dpre, x, None, w_param.grad, N, K, M, N, K, K, 1, 0, ACT_NONE, 1)
+                    if has_b and ctx.needs_input_grad[2] and _direct(b_param):
+                        _bias_grad(dpre, b_param, N)
+                        has_b = False
+            elif _gemm_tc_ok(N, K, M):
                 dw = torch.empty_like(w)
                 _call('g2_gemm_tf32', dpre.t().contiguous(), x.t().contiguous(), None, dw, N, K, M)
-                if direct:
-                    w_param.grad.add_(dw)
-                    dw = None
-            elif direct:
-                _call('g2_gemm_f32', dpre, x, None, w_param.grad, N, K, M, N, K, K, 1, 0, ACT_NONE, 1)
             else:
                 dw = torch.empty_like(w)
                 _call('g2_gemm_f32', dpre, x, None, dw, N, K, M, N, K, K, 1, 0, ACT_NONE, 0)

@@ -152,6 +152,7 @@ class TrainStep(object):
             beta = self.geco.beta if self.geco is not None else 1.0
             loss = err + beta * kl
             loss.backward()
+            ops.join_grad_stream(self.flat_p.device)      # parameter-gradient kernels run on a side stream
         finally:
             ops.set_direct_grad(False)
         tail = self.arena.tail

@@ -20,6 +20,7 @@ def grads_of(m, x, seed, direct, pre=0.0):
     try:
         recon, losses, stats, att, comp = m(x)
         U.engine_total_loss(losses).backward()
+        ops.join_grad_stream(x.device)
     finally:
         ops.set_direct_grad(False)
         m.set_noise_tape(None)
