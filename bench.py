@@ -221,26 +221,41 @@ def run_engine(args):
 
     # ---- dominant kernel: per-call device time inside profiled (eager) steps, CUDA events on the launch stream.
     # Every rank runs them (the step contains the gradient all-reduce); rank 0 reports.
+    from genesis_b200 import ops
+    ops.set_side_streams(False)       # serial: per-kernel event times are not inflated by concurrent side-stream kernels
     with profiling.Profiler() as prof:
         for i in range(2):
             ts._step_eager(devx[i % n_in])
+    ops.set_side_streams(True)
     barrier()
     if rank == 0:
         pk = peaks()
         rows = prof.table()
         total_ms = sum(r['ms'] for r in rows)
         top = rows[0]
+        # DRAM bytes per launch of the dominant kernel from the committed ncu pass (profiles/r01_traffic.json; c2 only)
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+        if args.workload == 'c2' and os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if top['key'] in tj:
+                traffic = tj[top['key']]['dram_bytes_per_launch']
+                traffic_src = 'profiles/r01_traffic.json (ncu dram__bytes_read+write per launch, %d launches of one step)' % tj[top['key']]['launches']
         tensor_like = top['flops'] > 0 and top['key'].startswith(('g2_conv', 'g2_gemm'))
         if tensor_like:
             ach = top['flops'] / (top['ms'] * 1e-3) / 1e12
             roof = {'bound': 'tensor', 'kernel': top['key'], 'achieved': ach, 'peak': pk['tf_sus'], 'unit': 'TFLOP/s',
-                    'frac': ach / pk['tf_sus'], 'traffic': None, 'peak_source': pk['src'] + ' bf16 sustained',
-                    'share_of_step': top['ms'] / total_ms, 'launch_ms': top['ms'] / top['calls']}
+                    'frac': ach / pk['tf_sus'], 'traffic': traffic, 'traffic_source': traffic_src,
+                    'peak_source': pk['src'] + ' bf16 sustained (kernel runs TF32 operands: nominal TF32 dense peak is half of bf16)',
+                    'share_of_step': top['ms'] / total_ms, 'launch_ms': top['ms'] / top['calls'],
+                    'algorithmic_flops_per_launch': top['flops'] / top['calls'],
+                    'algorithmic_bytes_per_launch': top['bytes'] / top['calls']}
         else:
             ach = top['bytes'] / (top['ms'] * 1e-3) / 1e9
             roof = {'bound': 'hbm', 'kernel': top['key'], 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s',
-                    'frac': ach / pk['hbm'], 'traffic': None, 'peak_source': pk['src'],
-                    'share_of_step': top['ms'] / total_ms, 'launch_ms': top['ms'] / top['calls']}
+                    'frac': ach / pk['hbm'], 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': pk['src'],
+                    'share_of_step': top['ms'] / total_ms, 'launch_ms': top['ms'] / top['calls'],
+                    'algorithmic_bytes_per_launch': top['bytes'] / top['calls']}
         breakdown = [{'kernel': r['key'], 'ms_per_step': r['ms'] / 2, 'calls_per_step': r['calls'] // 2,
                       'tflops': (r['flops'] / (r['ms'] * 1e-3) / 1e12) if r['flops'] else None,
                       'gbs': (r['bytes'] / (r['ms'] * 1e-3) / 1e9) if r['bytes'] else None} for r in rows[:8]]
@@ -269,7 +284,8 @@ def run_engine(args):
                        'global_batch': B_PER_GPU * world, 'parallelism': 'dp%d' % world,
                        'l2': 'per-step working set (activations > 4 GB) exceeds the 126 MB L2; inputs rotate over %d batches' % n_in,
                        'step_tflops_algorithmic': step_tf, 'last_elbo': last, 'cuda_graph': graphed,
-                       'precision': 'tf32 tensor-core operands, fp32 accumulate / storage'},
+                       'precision': 'tf32 tensor-core operands, fp32 accumulate / storage',
+                       'streams': 'one captured graph; prior/KL branch and parameter-gradient kernels on side streams'},
             'e2e': {'value': imgs / (ms_e2e * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': B_PER_GPU * 3 * IMG * IMG * 4,
                     'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': launches,

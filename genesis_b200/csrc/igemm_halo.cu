@@ -29,6 +29,7 @@ using namespace umma;
 
 constexpr int MAX_TAPS = 32;
 constexpr int MAX_CHUNKS = 8;
+constexpr int MAX_STAGES = 12;
 
 struct Maps { CUtensorMap a; CUtensorMap b; };
 
@@ -38,7 +39,8 @@ struct P {
     int ch_rows, nch, ch_pix;           // rows per chunk (TMA box rows), chunks, pixel rows per chunk (= ch_rows*Wp*TNB)
     int tiles_h, tiles_w, dh_min, dw_min, span_h;
     int Ho, Wo, Co, os, ph, pw;
-    int ntaps, cblocks, act, tmem_cols, a_bytes;
+    int ntaps, cblocks, act, tmem_cols, a_bytes, stages, epi;
+    long long* dbg;                     // optional per-CTA phase timestamps [grid][8] (scripts/conv_bench.py --timeline)
     int toff[MAX_TAPS];
     short widx[MAX_TAPS];
 };
@@ -94,7 +96,55 @@ __device__ __forceinline__ void epilogue(const P& p, uint32_t tmem_base, const f
     }
 }
 
-template <int BN, int STAGES>
+// Bulk-copy epilogue: each lane owns one output pixel = one 128-byte row per 32-channel group.  The lane writes its row
+// into a private staging row (pitch 144 B: conflict-free float4 stores), makes it visible to the async proxy and hands it
+// to the bulk-copy engine (cp.async.bulk shared -> global, 128 B), so the LSU sees 8 STS per lane instead of
+// 8 STS + 8 SHFL + 8 LDS + 8 STG.  Two staging rows per lane: the copy of group g drains while group g+1 is computed.
+template <int BN, int ACT>
+__device__ __forceinline__ void epilogue_bulk(const P& p, uint32_t tmem_base, const float* sBias, uint8_t* stage_base, int nbuf,
+                                              int m_tiles, int n0, int h0, int w0, int n0c, int imgs_valid, int rows_valid,
+                                              int cols_valid) {
+    const int lane = threadIdx.x & 31, q = (threadIdx.x >> 5) & 3;
+    const int img_pix = p.RH * p.Wp;
+    uint8_t* my = stage_base + (size_t)(q * 32 + lane) * 144;             // this lane's row in buffer 0; buffer 1 is 128*144 B further
+    int it = 0;
+    for (int t = 0; t < m_tiles; ++t) {
+        const int f = t * 128 + q * 32 + lane;
+        const int i = f / img_pix, rem = f - i * img_pix;
+        const int hl = rem / p.Wp, w = rem - hl * p.Wp;
+        const bool valid = i < imgs_valid && hl < rows_valid && w < cols_valid;
+        const int oh = (h0 + hl) * p.os + p.ph, ow = (w0 + w) * p.os + p.pw;
+        float* orow = p.out + ((size_t)((n0 + i) * p.Ho + oh) * p.Wo + ow) * p.Co + n0c;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32, ++it) {
+            uint32_t v[32];
+            tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * BN + c0), v);
+            float* row = reinterpret_cast<float*>(my + (nbuf == 2 ? (it & 1) * (128 * 144) : 0));
+            // the bulk copy that last read this staging row must have finished reading it
+            if (nbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 b = *reinterpret_cast<const float4*>(sBias + c0 + 4 * j);
+                float4 o;
+                o.x = act_apply<ACT>(__uint_as_float(v[4 * j]) + b.x);
+                o.y = act_apply<ACT>(__uint_as_float(v[4 * j + 1]) + b.y);
+                o.z = act_apply<ACT>(__uint_as_float(v[4 * j + 2]) + b.z);
+                o.w = act_apply<ACT>(__uint_as_float(v[4 * j + 3]) + b.w);
+                *reinterpret_cast<float4*>(row + 4 * j) = o;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (valid)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;"
+                             ::"l"(orow + c0), "r"(smem_u32(row)) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all rows written before the CTA retires
+}
+
+template <int BN>
 __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P p) {
     constexpr int B_BYTES = BN * 128;
     extern __shared__ uint8_t smem_raw[];
@@ -102,13 +152,14 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
     uint8_t* sm = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     uint8_t* sA = sm;
     uint8_t* sB = sm + p.a_bytes;
+    const int STAGES = p.stages;
     uint64_t* fullA = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
     uint64_t* emptyA = fullA + MAX_CHUNKS;
     uint64_t* fullB = emptyA + 1;
-    uint64_t* emptyB = fullB + STAGES;
-    uint64_t* accf = emptyB + STAGES;
+    uint64_t* emptyB = fullB + MAX_STAGES;
+    uint64_t* accf = emptyB + MAX_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accf + 1);
-    float* sBias = reinterpret_cast<float*>(fullA) + 64;        // 256 B past the barrier block
+    float* sBias = reinterpret_cast<float*>(fullA) + 96;        // 384 B past the start of the barrier block
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tw_i = blockIdx.x % p.tiles_w;
@@ -124,6 +175,8 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
     const int m_tiles = f_last / 128 + 1;
     const int nch = p.TNB > 1 ? 1 : min(p.nch, (rows_valid + p.span_h + p.ch_rows - 1) / p.ch_rows);
 
+    long long* dbg = p.dbg ? p.dbg + ((long)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+    if (dbg && threadIdx.x == 32) { dbg[0] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); dbg[7] = sm; }
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.a);
         prefetch_tmap(&maps.b);
@@ -132,7 +185,7 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
         if (lane == 0) {
             for (int j = 0; j < MAX_CHUNKS; ++j) mbar_init(&fullA[j], 1);
             mbar_init(emptyA, 1);
-            for (int s = 0; s < STAGES; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+            for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
             mbar_init(accf, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -144,11 +197,13 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
     __syncthreads();
     fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (dbg && threadIdx.x == 32) dbg[1] = clock64();          // prologue done
 
     if (warp == 0) {
         // ---- TMA producer: the whole warp walks the schedule (uniform control flow), one elected lane issues
         const uint32_t ch_bytes = (uint32_t)p.ch_pix * 128u;
         int bi = 0;
+        uint32_t bph = 0;
         for (int cb = 0; cb < p.cblocks; ++cb) {
             if (cb > 0) mbar_wait(emptyA, (uint32_t)(cb - 1) & 1u);     // all MMAs of the previous channel block retired
             if (elect_one()) {
@@ -158,14 +213,15 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
                 }
             }
             __syncwarp();
-            for (int tap = 0; tap < p.ntaps; ++tap, ++bi) {
-                const int s = bi % STAGES;
-                mbar_wait(&emptyB[s], ((uint32_t)(bi / STAGES) & 1u) ^ 1u);
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+                const int s = bi;
+                mbar_wait(&emptyB[s], bph ^ 1u);
                 if (elect_one()) {
                     mbar_expect_tx(&fullB[s], B_BYTES);
                     tma_load_3d(sB + s * B_BYTES, &maps.b, &fullB[s], cb * 32, n0c, p.widx[tap]);
                 }
                 __syncwarp();
+                if (++bi == STAGES) { bi = 0; bph ^= 1u; }
             }
         }
     } else if (warp == 1) {
@@ -174,17 +230,19 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
         const uint64_t hi = desc_k_sw128_hi();
         const uint32_t a0 = smem_u32(sA) >> 4;
         int bi = 0;
+        uint32_t bph = 0;
         for (int cb = 0; cb < p.cblocks; ++cb) {
             int waited = 0;
-            for (int tap = 0; tap < p.ntaps; ++tap, ++bi) {
-                const int s = bi % STAGES;
-                mbar_wait(&fullB[s], (uint32_t)(bi / STAGES) & 1u);
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+                const int s = bi;
+                mbar_wait(&fullB[s], bph);
                 const uint64_t bdesc = make_desc_k_sw128(smem_u32(sB + s * B_BYTES));
                 const int toff = p.toff[tap];
                 // activation chunks this tap reads (monotone in the tile index: wait for the last tile's)
                 const int need = min(nch - 1, (128 * (m_tiles - 1) + 127 + toff) / p.ch_pix);
                 while (waited <= need) { mbar_wait(&fullA[waited], (uint32_t)cb & 1u); ++waited; }
                 fence_after();
+                if (dbg && lane == 0 && cb == 0 && tap == 0) dbg[2] = clock64();      // first weight tile + its activation chunks landed
                 const uint32_t alo = a0 + (uint32_t)toff * 8u;
                 const uint32_t first = (cb | tap) != 0 ? 1u : 0u;
                 if (elect_one()) {
@@ -199,17 +257,29 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
                     commit(&emptyB[s]);                 // weight stage free when these MMAs retire
                 }
                 __syncwarp();
+                if (++bi == STAGES) { bi = 0; bph ^= 1u; }
             }
             if (elect_one()) commit(emptyA);            // activation window free
             __syncwarp();
         }
         if (elect_one()) commit(accf);                  // all accumulators complete
         __syncwarp();
+        if (dbg && lane == 0) dbg[3] = clock64();       // last MMA issued
     } else {
         // ---- epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31
         mbar_wait(accf, 0);
         fence_after();
-        // the activation window is dead once every MMA has retired: reuse its first 16 KB as store staging
+        if (dbg && threadIdx.x == 64) dbg[4] = clock64();       // accumulators complete
+        // the activation window is dead once every MMA has retired: reuse its head as store staging
+        if (p.epi) {
+            const int nbuf = p.a_bytes >= 2 * 128 * 144 ? 2 : 1;
+            switch (p.act) {
+                case G2_ACT_RELU: epilogue_bulk<BN, G2_ACT_RELU>(p, tmem_base, sBias, sA, nbuf, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid); break;
+                case G2_ACT_ELU: epilogue_bulk<BN, G2_ACT_ELU>(p, tmem_base, sBias, sA, nbuf, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid); break;
+                case G2_ACT_SIGMOID: epilogue_bulk<BN, G2_ACT_SIGMOID>(p, tmem_base, sBias, sA, nbuf, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid); break;
+                default: epilogue_bulk<BN, G2_ACT_NONE>(p, tmem_base, sBias, sA, nbuf, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid); break;
+            }
+        } else {
         float* stage = reinterpret_cast<float*>(sA) + (warp & 3) * 1024;
         switch (p.act) {
             case G2_ACT_RELU: epilogue<BN, G2_ACT_RELU>(p, tmem_base, sBias, stage, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid); break;
@@ -217,6 +287,8 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
             case G2_ACT_SIGMOID: epilogue<BN, G2_ACT_SIGMOID>(p, tmem_base, sBias, stage, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid); break;
             default: epilogue<BN, G2_ACT_NONE>(p, tmem_base, sBias, stage, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid); break;
         }
+        }
+        if (dbg && threadIdx.x == 64) dbg[5] = clock64();       // epilogue of warp 2 done
     }
     fence_before();
     __syncthreads();
@@ -256,10 +328,21 @@ static int env_int(const char* name, int dflt) {
     return s && *s ? atoi(s) : dflt;
 }
 static int g_enabled = -1;
+static long long* g_dbg = nullptr;
 static int budget_bytes() { static int v = env_int("G2_HALO_SMEM_KB", 112) * 1024; return v; }
+static int epi_mode() { static int v = env_int("G2_HALO_EPI", 0); return v; }
 static int max_cols() { static int v = env_int("G2_HALO_TMEM_COLS", 256); return v; }
 
-template <int BN> constexpr int stages_for() { return BN == 32 ? 4 : (BN == 64 ? 2 : 2); }
+// Weight-ring depth (tunable by environment for experiments).  Measured on B200 (gpurun_out/conv_bench_v6.txt): deeper rings
+// (6/4/3, 9/5/3, 12/6/4) are 0-25 % SLOWER than 4/2/2 because the shared memory they take shrinks the activation tile.
+static int stages_of(int BN, int ntaps, int cblocks) {
+    static int c32 = env_int("G2_HALO_STAGES_32", 4), c64 = env_int("G2_HALO_STAGES_64", 2), c128 = env_int("G2_HALO_STAGES_128", 2);
+    int cap = BN == 32 ? c32 : BN == 64 ? c64 : c128;
+    if (cap > MAX_STAGES) cap = MAX_STAGES;
+    if (cap < 1) cap = 1;
+    const int tiles = ntaps * cblocks;
+    return tiles < cap ? tiles : cap;
+}
 
 struct Geo {
     int TH, TW, TNB, RH, Wp, ch_rows, nch, m, a_bytes, tiles_h, tiles_w;
@@ -272,7 +355,7 @@ static inline int m_of(int imgs, int RH, int rows, int Wp, int cols) { return ((
 // images), window pitch Wp (exact, or rounded up to 8 pixels so that any row count keeps chunks 1024-byte aligned).
 // The cost model is the per-SM time of all CTAs of an image: max(MMA clocks, L2->SMEM clocks) + a fixed per-CTA cost.
 static bool pick_geo(int N, int Hv, int Wv, int span_h, int span_w, int ntaps, int cblocks, int BN, int stages, Geo* best) {
-    const int fixed = stages * BN * 128 + 768 + 1024;
+    const int fixed = stages * BN * 128 + 1024 + 1024;
     const double clk_mma = 4.0 * (BN == 32 ? 40 : BN == 64 ? 48 : 64) * ntaps * cblocks;   // per M tile (SMEM-read bound for small N)
     const double l2_rate = 28.0;           // bytes / clock / SM sustained by TMA tile loads (measured 21-33)
     const double cta_fixed = 1500.0;       // prologue + pipeline fill + epilogue tail not hidden by the sibling CTA
@@ -318,6 +401,7 @@ static bool pick_geo(int N, int Hv, int Wv, int span_h, int span_w, int ntaps, i
                 int alloc_pix = loaded_pix;
                 if (128 * g.m + off_max > alloc_pix) alloc_pix = 128 * g.m + off_max;
                 g.a_bytes = ((alloc_pix * 128 + 1023) / 1024) * 1024;
+                if (g.a_bytes < 128 * 144) g.a_bytes = 128 * 144;      // epilogue staging: 128 rows x 144 B
                 if (g.a_bytes + fixed > budget_bytes()) return;
                 double tiles, ctas, bytes;
                 if (TNB > 1) {
@@ -351,15 +435,14 @@ static bool pick_geo(int N, int Hv, int Wv, int span_h, int span_w, int ntaps, i
 
 template <int BN>
 static int launch(const Maps& maps, const P& p, dim3 grid, cudaStream_t stream) {
-    constexpr int STAGES = stages_for<BN>();
-    const int smem = p.a_bytes + STAGES * BN * 128 + 768 + 1024;
+    const int smem = p.a_bytes + p.stages * BN * 128 + 1024 + 1024;
     static int attr_set = 0;
     if (attr_set < smem) {
-        cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
         attr_set = 227 * 1024;
     }
-    conv_halo_kernel<BN, STAGES><<<grid, 192, smem, stream>>>(maps, p);
+    conv_halo_kernel<BN><<<grid, 192, smem, stream>>>(maps, p);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? G2_OK : (int)e;
 }
@@ -370,7 +453,6 @@ static int pick_bn(int Co) {
     if (Co % 64 == 0) return 64;
     return 0;
 }
-static int stages_of(int BN) { return BN == 32 ? stages_for<32>() : BN == 64 ? stages_for<64>() : stages_for<128>(); }
 
 struct TapSet { int n; int dh[MAX_TAPS], dw[MAX_TAPS], widx[MAX_TAPS]; int os, ph, pw, Hv, Wv; };
 
@@ -436,6 +518,15 @@ int g2_conv_halo_enable(int on) {
     return prev;
 }
 
+// Debug only (scripts/conv_bench.py --timeline): device buffer of [CTAs][8] int64 that subsequent halo launches fill with
+// clock64() at {start, prologue done, first operands landed, last MMA issued, accumulators complete, epilogue done, -, smid};
+// pass NULL to switch it off.  Returns 0.
+int g2_conv_halo_debug(int64_t* buf) {
+    static_assert(sizeof(long long) == sizeof(int64_t), "");
+    halo::g_dbg = reinterpret_cast<long long*>(buf);
+    return 0;
+}
+
 // 1 if the halo kernel takes this problem (g2_conv_igemm_tf32 then routes to it), else 0.
 int g2_conv_halo_supported(int N, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int R, int S, int stride, int pad, int mode) {
     using namespace halo;
@@ -451,7 +542,7 @@ int g2_conv_halo_supported(int N, int Hi, int Wi, int Ci, int Ho, int Wo, int Co
         int dh_min, dw_min, sh, sw;
         spans(ts[c], &dh_min, &dw_min, &sh, &sw);
         Geo g;
-        if (!pick_geo(N, ts[c].Hv, ts[c].Wv, sh, sw, ts[c].n, Ci / 32, BN, stages_of(BN), &g)) return 0;
+        if (!pick_geo(N, ts[c].Hv, ts[c].Wv, sh, sw, ts[c].n, Ci / 32, BN, stages_of(BN, ts[c].n, Ci / 32), &g)) return 0;
     }
     return 1;
 }
@@ -482,14 +573,14 @@ int g2_conv_halo_tf32(const float* in, const float* w, const float* bias, float*
         int dh_min, dw_min, sh, sw;
         spans(t, &dh_min, &dw_min, &sh, &sw);
         Geo g;
-        if (!pick_geo(N, t.Hv, t.Wv, sh, sw, t.n, Ci / 32, BN, stages_of(BN), &g)) return G2_ERR_UNSUPPORTED;
+        if (!pick_geo(N, t.Hv, t.Wv, sh, sw, t.n, Ci / 32, BN, stages_of(BN, t.n, Ci / 32), &g)) return G2_ERR_UNSUPPORTED;
         P p;
         memset(&p, 0, sizeof(p));
         p.out = out; p.bias = bias; p.N = N; p.Hv = t.Hv; p.Wv = t.Wv; p.TH = g.TH; p.TW = g.TW; p.TNB = g.TNB;
         p.Wp = g.Wp; p.RH = g.RH; p.ch_rows = g.ch_rows; p.nch = g.nch; p.ch_pix = g.ch_rows * p.Wp * g.TNB;
         p.tiles_h = g.tiles_h; p.tiles_w = g.tiles_w; p.dh_min = dh_min; p.dw_min = dw_min; p.span_h = sh;
         p.Ho = Ho; p.Wo = Wo; p.Co = Co; p.os = t.os; p.ph = t.ph; p.pw = t.pw;
-        p.ntaps = t.n; p.cblocks = Ci / 32; p.act = act; p.a_bytes = g.a_bytes;
+        p.ntaps = t.n; p.cblocks = Ci / 32; p.act = act; p.a_bytes = g.a_bytes; p.stages = stages_of(BN, t.n, Ci / 32); p.dbg = g_dbg; p.epi = epi_mode();
         int cols = 32;
         while (cols < g.m * BN) cols <<= 1;
         p.tmem_cols = cols;
@@ -530,10 +621,10 @@ int g2_conv_halo_plan(int N, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int
     int dh_min, dw_min, sh, sw;
     spans(t, &dh_min, &dw_min, &sh, &sw);
     Geo g;
-    if (!pick_geo(N, t.Hv, t.Wv, sh, sw, t.n, Ci / 32, BN, stages_of(BN), &g)) return G2_ERR_UNSUPPORTED;
+    if (!pick_geo(N, t.Hv, t.Wv, sh, sw, t.n, Ci / 32, BN, stages_of(BN, t.n, Ci / 32), &g)) return G2_ERR_UNSUPPORTED;
     const int Wp = g.Wp;
     const int v[22] = {nc, g.TH, g.TNB, g.RH, g.ch_rows, g.nch, g.m, g.a_bytes, g.tiles_h, Wp, dh_min, dw_min, t.os, t.ph, t.pw,
-                       t.Hv, t.Wv, t.n, BN, g.a_bytes + stages_of(BN) * BN * 128 + 768 + 1024, g.TW, g.tiles_w};
+                       t.Hv, t.Wv, t.n, BN, g.a_bytes + stages_of(BN, t.n, Ci / 32) * BN * 128 + 1024 + 1024, g.TW, g.tiles_w};
     for (int i = 0; i < 96; ++i) plan[i] = 0;
     for (int i = 0; i < 22; ++i) plan[i] = v[i];
     for (int i = 0; i < t.n; ++i) {

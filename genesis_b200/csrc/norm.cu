@@ -340,7 +340,7 @@ int g2_norm_stats_f32(const float* y, double* sums, int N, int HW, int C, cudaSt
     if (e != cudaSuccess) return (int)e;
     const int lanes = 256 / (C / 4);
     int rpb = lanes * 32;
-    // keep the grid near a few waves of 148 SMs
+    // keep the grid near a few waves of 148 SMs (measured: 4x smaller blocks are 15-20 % slower -- reduction + atomics tail)
     while ((long)g2_cdiv(HW, rpb) * N > 148L * 32 && rpb < HW) rpb *= 2;
     dim3 grid(g2_cdiv(HW, rpb), N);
     norm_stats_kernel<<<grid, 256, 0, stream>>>(y, sums, HW, C, rpb);

@@ -159,7 +159,7 @@ class Genesis(nn.Module, NoiseMixin):
         # replays each node's backward on its forward stream, so the overlap carries to the backward pass; under CUDA
         # graph capture this becomes a parallel branch of the graph.
         cur = torch.cuda.current_stream()
-        side = ops.side_stream(x.device) if (self.side_stream and torch.is_grad_enabled()) else cur
+        side = ops.side_stream(x.device) if (self.side_stream and ops.side_streams_enabled() and torch.is_grad_enabled()) else cur
         if side is not cur:
             side.wait_stream(cur)
             for t_ in z_k + att_stats.mu_k + att_stats.sigma_k:      # allocated on `cur`, read (fwd and bwd) on `side`
@@ -257,7 +257,12 @@ class Genesis(nn.Module, NoiseMixin):
                     z_k.append(mu + sig * self._normal(mu.shape, like))
             else:
                 z_k += [self._normal((batch_size, self.ldim), like) for _ in range(1, self.att_steps)]
-            logits = H.sylvester_decode(self.att_process.core, torch.cat(z_k, 0), self.training)
+            core = self.att_process.core
+            if self.training and core.dec_norm == 'bn':
+                # the reference decodes every z_m on its own (attention.py:61): BatchNorm batch statistics are per slot
+                logits = torch.cat([H.sylvester_decode(core, z, True) for z in z_k], 0)
+            else:
+                logits = H.sylvester_decode(core, torch.cat(z_k, 0), self.training)
             logits = logits.view(K, batch_size, 1, self.img_size, self.img_size)
             log_m, log_s = ops.sbp_scan(logits, K)
             if self.comp_prior:
@@ -266,9 +271,11 @@ class Genesis(nn.Module, NoiseMixin):
                 t = ops.linear(t, pm[2].weight, pm[2].bias, 'elu')
                 a, b = torch.chunk(ops.linear(t, pm[4].weight, pm[4].bias), 2, dim=1)
                 mu, sig = torch.tanh(a), H.to_prior_sigma(b)
-                zc = mu + sig * self._normal(mu.shape, like)
+                # one draw per slot, in slot order (reference :392-397)
+                eps = torch.cat([self._normal((batch_size, mu.shape[1]), like) for _ in range(K)], 0)
+                zc = mu + sig * eps
             else:
-                zc = self._normal((K * batch_size, self.comp_vae.ldim), like)
+                zc = torch.cat([self._normal((batch_size, self.comp_vae.ldim), like) for _ in range(K)], 0)
             x_k = H.broadcast_decode(self.comp_vae.decoder_module, zc, 'elu', 3 if self.pixel_bound else 0)
             x_k = x_k.view(K, batch_size, -1, self.img_size, self.img_size)
             mx = x_k * log_m.exp()

@@ -34,6 +34,16 @@ def _call(name, *args):
 
 
 _SIDE = {}
+_SIDE_ON = {'on': True}
+
+
+def set_side_streams(on):
+    """False: run everything on the current stream (clean per-kernel timing in bench.py's profiled steps)."""
+    _SIDE_ON['on'] = bool(on)
+
+
+def side_streams_enabled():
+    return _SIDE_ON['on']
 
 
 def side_stream(device, idx=0):
@@ -53,10 +63,11 @@ class _GradStream(object):
 
     def __init__(self, *operands):
         self.cur = torch.cuda.current_stream()
-        self.side = side_stream(operands[0].device, 1)
-        self.side.wait_stream(self.cur)
-        for t in operands:
-            t.record_stream(self.side)
+        self.side = side_stream(operands[0].device, 1) if _SIDE_ON['on'] else self.cur
+        if self.side is not self.cur:
+            self.side.wait_stream(self.cur)
+            for t in operands:
+                t.record_stream(self.side)
         self.ctx = torch.cuda.stream(self.side)
 
     def __enter__(self):
@@ -94,6 +105,16 @@ def _wgrad_any(g, t, dims, R, S, stride, pad, outT, like):
     return dwp
 
 
+def _conv_tc(x, pack, bias, out, dims, R, S, stride, pad, mode, act):
+    """Tensor-core implicit GEMM through the entry point that will run it: the halo kernel (activation window resident,
+    taps via shifted descriptors) when it covers the problem, else the tile kernel -- same contract, separate profile rows."""
+    N, Hi, Wi, Ci, Ho, Wo, Co = dims
+    if _lib.lib().query('g2_conv_halo_supported', N, Hi, Wi, Ci, Ho, Wo, Co, R, S, stride, pad, mode) == 1:
+        _call('g2_conv_halo_tf32', x, pack, bias, out, N, Hi, Wi, Ci, Ho, Wo, Co, R, S, stride, pad, mode, act)
+    else:
+        _call('g2_conv_igemm_tf32', x, pack, bias, out, N, Hi, Wi, Ci, Ho, Wo, Co, R, S, stride, pad, mode, act)
+
+
 def _conv_any(x, w_t, bias, out, dims, R, S, stride, pad, mode, act, perm_tc, perm_simt_wT):
     """Run mode-0/1 implicit GEMM on the tensor cores when supported, else the fp32 SIMT kernel.
     w_t: weight in torch layout; perm_tc: permutation giving [R,S,Cout_op,Cred_op];
@@ -101,7 +122,7 @@ def _conv_any(x, w_t, bias, out, dims, R, S, stride, pad, mode, act, perm_tc, pe
     N, Hi, Wi, Ci, Ho, Wo, Co = dims
     if _tc_ok(N, Hi, Wi, Ci, Ho, Wo, Co, R, S, stride, pad, mode):
         wp = w_t.permute(*perm_tc).contiguous()
-        _call('g2_conv_igemm_tf32', x, wp, bias, out, N, Hi, Wi, Ci, Ho, Wo, Co, R, S, stride, pad, mode, act)
+        _conv_tc(x, wp, bias, out, dims, R, S, stride, pad, mode, act)
     else:
         perm, wT = perm_simt_wT
         wp = w_t.permute(*perm).contiguous()
@@ -225,7 +246,7 @@ def _conv_fwd_common(ctx, x, w, b, stride, pad, act, transposed):
         if ctx.needs_input_grad[0] and _tc_ok(N, Ho, Wo, Co, H, W, Cx, R, S, stride, pad, mode_d):
             pb = _new(x, R * S, Cx, Co)
         _call('g2_pack_conv_weight_f32', _c(wd), pa, pb, Co, Ci, Cx, R * S, 1 if transposed else 0)
-        _call('g2_conv_igemm_tf32', x, pa, b, out, N, H, W, Cx, Ho, Wo, Co, R, S, stride, pad, mode_f, act)
+        _conv_tc(x, pa, b, out, (N, H, W, Cx, Ho, Wo, Co), R, S, stride, pad, mode_f, act)
     else:
         wp = _pad_dim(wd, 0 if transposed else 1, Cx)
         perm = (2, 3, 0, 1) if transposed else (2, 3, 1, 0)          # [R,S,Cred,Cout]
@@ -254,7 +275,7 @@ def _conv_bwd_common(ctx, dout):
     if ctx.needs_input_grad[0]:
         dx = torch.empty_like(x)
         if pb is not None:
-            _call('g2_conv_igemm_tf32', dpre, pb, None, dx, N, Ho, Wo, Co, H, W, Cx, R, S, stride, pad, mode_d, ACT_NONE)
+            _conv_tc(dpre, pb, None, dx, (N, Ho, Wo, Co, H, W, Cx), R, S, stride, pad, mode_d, ACT_NONE)
         else:   # data gradient = the other mode with the reduction over Co: SIMT pack [R,S,Cx,Co] + wT (or the TC pack)
             wp = _pad_dim(wd, 0 if transposed else 1, Cx)
             perm = (2, 3, 0, 1) if transposed else (2, 3, 1, 0)      # [R,S,Cx,Co]

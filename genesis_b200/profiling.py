@@ -10,7 +10,7 @@ from . import _lib
 def algo_cost(name, a):
     """(flops, bytes) a call must perform / move at minimum, from its arguments (pointer args included)."""
     f = b = 0
-    if name in ('g2_conv_igemm_f32', 'g2_conv_igemm_tf32'):
+    if name in ('g2_conv_igemm_f32', 'g2_conv_igemm_tf32', 'g2_conv_halo_tf32'):
         o = 5 if name.endswith('f32') and not name.endswith('tf32') else 4
         N, Hi, Wi, Ci, Ho, Wo, Co, R, S, stride, pad, mode = a[o:o + 12]
         if mode == 0:
@@ -18,8 +18,8 @@ def algo_cost(name, a):
         else:
             f = 2.0 * N * Hi * Wi * Ci * Co * R * S
         b = 4.0 * (N * Hi * Wi * Ci + N * Ho * Wo * Co + R * S * Ci * Co)
-    elif name in ('g2_conv_wgrad_f32', 'g2_conv_wgrad_tf32'):
-        o = 4 if name.endswith('tf32') else 3
+    elif name in ('g2_conv_wgrad_f32', 'g2_conv_wgrad_tf32', 'g2_conv_wgrad_tf32_to'):
+        o = 3 if name == 'g2_conv_wgrad_f32' else 4
         N, Hg, Wg, Cg, Ht, Wt, Ct, R, S = a[o:o + 9]
         f = 2.0 * N * Ht * Wt * Cg * Ct * R * S
         b = 4.0 * (N * Hg * Wg * Cg + N * Ht * Wt * Ct + R * S * Cg * Ct)

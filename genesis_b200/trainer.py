@@ -22,6 +22,19 @@ class GecoState(object):
         self.started = torch.zeros((), device=device)
         self.beta_min, self.beta_max = beta_min, beta_max
 
+    def state(self):
+        """What train.py:410-416 stores in a checkpoint ('beta', 'err_ema')."""
+        return {'beta': self.beta.detach().clone(), 'err_ema': self.err_ema.detach().clone()}
+
+    @torch.no_grad()
+    def load_state(self, state):
+        """Restore from a reference checkpoint dict (train.py:197-203)."""
+        if 'beta' in state:
+            self.beta.copy_(torch.as_tensor(state['beta'], dtype=torch.float32))
+        if 'err_ema' in state:
+            self.err_ema.copy_(torch.as_tensor(state['err_ema'], dtype=torch.float32))
+            self.started.fill_(1.0)
+
     @torch.no_grad()
     def update(self, err):
         ema = torch.where(self.started > 0, (1.0 - self.alpha) * err + self.alpha * self.err_ema, err)

@@ -195,6 +195,8 @@ int g2_gemm_tf32(const float* A, const float* W, const float* bias, float* C, in
  * {nclasses, TH, TNB, RH, chunk_rows, chunks, m_tiles, a_bytes, tiles_h, Wp, dh_min, dw_min, os, ph, pw, Hv, Wv,
  *  ntaps, BN, smem_bytes}, plan[32+i] = flat row offset of tap i, plan[64+i] = its weight index. */
 int g2_conv_halo_enable(int on);
+/* debug: per-CTA clock64() phase timestamps of subsequent halo launches into a device buffer [CTAs][8] (NULL = off) */
+int g2_conv_halo_debug(int64_t* buf);
 int g2_conv_halo_supported(int N, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int R, int S, int stride,
                            int pad, int mode);
 int g2_conv_halo_tf32(const float* in, const float* w, const float* bias, float* out, int N, int Hi, int Wi,

@@ -97,8 +97,46 @@ def run_case(name, model, K, img, B, gen):
     print(name, 'err', g['err'], '->', path, os.path.getsize(path) // 1024, 'KiB')
 
 
+SAMPLE_CASES = [  # name, forward case that precedes it (same model instance: BatchNorm running stats), sample batch
+    ('sample_genesis_k5', 'genesis_k5_b2', 3),
+    ('sample_genesisv2_k7', 'genesisv2_k7_b2', 3),
+    ('sample_monet_k7', 'monet_k7_b2', 2),
+]
+
+
+def run_sample_case(name, fwd_case, sb):
+    """sample() of the real reference as its callers use it (train.py:425-472, scripts/compute_fid.py:104-125): one
+    training-mode forward first (moves the BatchNorm running statistics off their initial values), then model.eval() and
+    model.sample(batch) with a recorded noise tape (seed 7)."""
+    _, model, K, img, B, gen = next(c for c in CASES if c[0] == fwd_case)
+    cfg = M.make_cfg(model, K_steps=K, img_size=img)
+    ref = ref_loader.load_reference(model, cfg, seed=0)
+    ref.train()
+    x = torch.from_numpy(synth.GENERATORS[gen](B, img, 1)[0])
+    with ref_loader.replay_noise(O.NoiseTape(seed=2)):
+        ref(x)
+    ref.eval()
+    tape = O.NoiseTape(seed=7)
+    with torch.no_grad(), ref_loader.replay_noise(tape):
+        image, stats = ref.sample(sb, K)
+    g = {'meta': np.array([model, str(K), str(img), str(sb), fwd_case])}
+    g['noise_kinds'] = np.array([k for k, _ in tape.record])
+    for i, (_, t) in enumerate(tape.record):
+        g['noise_%d' % i] = t.numpy()
+    g['image'] = image.numpy()
+    g['log_m_k'] = torch.stack(list(stats['log_m_k']), 0).numpy()
+    g['x_k'] = torch.stack(list(stats['x_k']), 0).numpy().astype(np.float16)
+    path = os.path.join(OUT_DIR, name + '.npz')
+    np.savez_compressed(path, **g)
+    print(name, 'image mean', float(image.mean()), '->', path, os.path.getsize(path) // 1024, 'KiB')
+
+
 if __name__ == '__main__':
     if not ref_loader.available():
         sys.exit('reference checkout not found at %s' % ref_loader.REF_ROOT)
-    for case in CASES:
-        run_case(*case)
+    only_samples = '--samples' in sys.argv
+    if not only_samples:
+        for case in CASES:
+            run_case(*case)
+    for case in SAMPLE_CASES:
+        run_sample_case(*case)

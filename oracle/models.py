@@ -270,6 +270,83 @@ def genesisv2_forward(P, x, tape, cfg, training=True):
                 bn_updates={})
 
 
+# ============================================================================ sample() (ancestral sampling)
+def genesis_sample(P, batch_size, tape, cfg, training=False):
+    """Genesis.sample (models/genesis_config.py:345-425) with LatentSBP.masks_from_zm_k (modules/attention.py:53-74):
+    z_m,1 ~ N(0,1); z_m,k ~ N(mu, sigma) from the prior LSTM (no tanh on mu in sample(), :359); every z_m decoded
+    SEPARATELY (:61), K+1 masks cut back to K (:371-373); z_c,k ~ N(tanh, to_prior_sigma) from prior_mlp(z_m,k), one draw
+    per slot (:392-397); batched component decode; composite."""
+    K, img = cfg.K_steps, cfg.img_size
+    dt = torch.float32
+    ldim = cfg.attention_latents
+    upd = {}
+    zm_k = [tape.normal((batch_size, ldim), dt)]
+    if cfg.autoreg_prior:
+        state = None
+        for _ in range(1, K):
+            out, state = O.lstm_cell(zm_k[-1], state, P, 'prior_lstm')
+            lo = O.linear(out, P, 'prior_linear')
+            mu, sigma = lo[:, :ldim], O.to_prior_sigma(lo[:, ldim:])
+            zm_k.append(mu + sigma * tape.normal(mu.shape, dt))
+    else:
+        zm_k += [tape.normal((batch_size, ldim), dt) for _ in range(1, K)]
+    logits_k = [O.sylvester_decode(zm, P, 'att_process.core', img, cfg.dec_norm, training, upd)[:, :1] for zm in zm_k]
+    log_m_k, log_s_k = O.stick_breaking(logits_k)
+    del log_m_k[-1]
+    log_m_k[K - 1] = log_s_k[K - 1]
+    zc_k = []
+    for zm in zm_k:
+        if cfg.comp_prior:
+            t = F.elu(O.linear(zm, P, 'prior_mlp.0'))
+            t = F.elu(O.linear(t, P, 'prior_mlp.2'))
+            a, b = torch.chunk(O.linear(t, P, 'prior_mlp.4'), 2, dim=1)
+            mu, sigma = torch.tanh(a), O.to_prior_sigma(b)
+            zc_k.append(mu + sigma * tape.normal(mu.shape, dt))
+        else:
+            zc_k.append(tape.normal((batch_size, cfg.comp_ldim), dt))
+    x = O.broadcast_decoder(torch.cat(zc_k, 0), P, 'comp_vae.decoder_module', img, cfg.comp_dec_layers, O.act_fn('elu'))
+    if cfg.pixel_bound:
+        x = torch.sigmoid(x)
+    x_k = list(torch.chunk(x, K, 0))
+    image = sum(m.exp() * xk for m, xk in zip(log_m_k, x_k))
+    return dict(image=image, x_k=x_k, log_m_k=log_m_k, log_s_k=log_s_k)
+
+
+def genesisv2_sample(P, batch_size, tape, cfg, training=False):
+    """GenesisV2.sample (models/genesisv2_config.py:227-256): z_1 ~ N(0,1), z_k ~ N(tanh(.), to_prior_sigma(.)) from the
+    prior LSTM, then decode_latents (:205-225)."""
+    K, img, fd = cfg.K_steps, cfg.img_size, cfg.feat_dim
+    dt = torch.float32
+    z_k = [tape.normal((batch_size, fd), dt)]
+    if cfg.autoreg_prior:
+        state = None
+        for _ in range(1, K):
+            out, state = O.lstm_cell(z_k[-1], state, P, 'prior_lstm')
+            a, b = torch.chunk(O.linear(out, P, 'prior_linear'), 2, dim=1)
+            mu, sigma = torch.tanh(a), O.to_prior_sigma(b)
+            z_k.append(mu + sigma * tape.normal(mu.shape, dt))
+    else:
+        z_k += [tape.normal((batch_size, fd), dt) for _ in range(1, K)]
+    dec_k = [v2_decoder(z, P, img) for z in z_k]
+    x_k = [torch.sigmoid(d[:, :3]) if cfg.pixel_bound else d[:, :3] for d in dec_k]
+    log_m_k = mask_recon_log_softmax([d[:, 3:] for d in dec_k])
+    image = sum(m.exp() * xk for m, xk in zip(log_m_k, x_k))
+    return dict(image=image, x_k=x_k, log_m_k=log_m_k)
+
+
+def monet_sample(P, batch_size, tape, cfg, training=False):
+    """MONet.sample (models/monet_config.py:172-198): one N(0,1) draw for all K*B slots, broadcast-decode, softmax masks."""
+    K, img = cfg.K_steps, cfg.img_size
+    z = tape.normal((batch_size * K, cfg.comp_ldim), torch.float32)
+    dec = O.broadcast_decoder(z, P, 'comp_vae.decoder_module', img, cfg.comp_dec_layers, O.act_fn('relu'))
+    x = torch.sigmoid(dec[:, :3]) if cfg.pixel_bound else dec[:, :3]
+    x_k = list(torch.chunk(x, K, 0))
+    log_m_k = mask_recon_log_softmax(list(torch.chunk(dec[:, 3:], K, 0)))
+    image = sum(m.exp() * xk for m, xk in zip(log_m_k, x_k))
+    return dict(image=image, x_k=x_k, log_m_k=log_m_k)
+
+
+SAMPLE = {'genesis': genesis_sample, 'genesisv2': genesisv2_sample, 'monet': monet_sample}
 FORWARD = {'genesis': genesis_forward, 'genesisv2': genesisv2_forward, 'monet': monet_forward}
 
 

@@ -42,6 +42,12 @@ def replay_noise(tape):
     import torch.distributions.utils as tdu
     orig_sn = tdn._standard_normal
     orig_uniform = torch.Tensor.uniform_
+    orig_normal = torch.normal
+
+    def normal(mean, std, *a, **k):         # Normal.sample() -> torch.normal(loc, scale): the sample() paths
+        if torch.is_tensor(mean) and torch.is_tensor(std):
+            return mean + std * tape.normal(tuple(mean.shape), mean.dtype).to(mean.device)
+        return orig_normal(mean, std, *a, **k)
 
     def sn(shape, dtype, device):
         return tape.normal(tuple(shape), dtype).to(device)
@@ -53,9 +59,11 @@ def replay_noise(tape):
     tdn._standard_normal = sn
     tdu._standard_normal = sn
     torch.Tensor.uniform_ = uni
+    torch.normal = normal
     try:
         yield
     finally:
         tdn._standard_normal = orig_sn
         tdu._standard_normal = orig_sn
         torch.Tensor.uniform_ = orig_uniform
+        torch.normal = orig_normal

@@ -134,5 +134,39 @@ def main():
         json.dump(rows, open(out_path, 'w'), indent=1)
 
 
-if __name__ == '__main__':
+
+
+def timeline(name):
+    """Per-CTA phase durations (SM clocks) of one halo launch: where a CTA's lifetime goes."""
+    import ctypes
+    mode, N, H, W, Ci, Co, R, s, p = SHAPES[name]
+    Ho, Wo = out_hw(mode, H, W, R, s, p)
+    dev = torch.device('cuda', 0)
+    lib = _lib.lib()
+    x = torch.randn(N, H, W, Ci, device=dev); w = torch.randn(R * R, Co, Ci, device=dev) * 0.05; b = torch.randn(Co, device=dev)
+    out = torch.empty(N, Ho, Wo, Co, device=dev)
+    buf = torch.zeros(1 << 16, 8, dtype=torch.int64, device=dev)
+    for i in range(3):
+        if i == 2:
+            lib.query('g2_conv_halo_debug', ctypes.c_void_p(buf.data_ptr()))
+        _lib.call('g2_conv_igemm_tf32', x, w, b, out, N, H, W, Ci, Ho, Wo, Co, R, R, s, p, mode, 0)
+    torch.cuda.synchronize()
+    lib.query('g2_conv_halo_debug', None)
+    t = buf.cpu()
+    t = t[t[:, 0] > 0].double()
+    names = ['prologue', 'wait first operands', 'MMA issue (all taps)', 'drain to accumulators complete', 'epilogue']
+    d = [t[:, 1] - t[:, 0], t[:, 2] - t[:, 1], t[:, 3] - t[:, 2], t[:, 4] - t[:, 3], t[:, 5] - t[:, 4]]
+    print('%s: %d CTAs, lifetime mean %.0f clk' % (name, t.shape[0], (t[:, 5] - t[:, 0]).mean()))
+    for n_, v in zip(names, d):
+        print('   %-32s mean %8.0f  p10 %8.0f  p90 %8.0f clk' % (n_, v.mean(), v.kthvalue(max(1, int(0.1 * len(v))))[0], v.kthvalue(max(1, int(0.9 * len(v))))[0]))
+    # concurrency: CTAs per SM over the kernel
+    span = (t[:, 5].max() - t[:, 0].min())
+    print('   kernel span (max end - min start, mixed SM clocks) %.0f clk; sum lifetimes / (148 * span) = %.2f CTAs resident per SM'
+          % (span, (t[:, 5] - t[:, 0]).sum() / (148 * span)))
+
+
+if '--timeline' in sys.argv:
+    for nm in sys.argv[sys.argv.index('--timeline') + 1].split(','):
+        timeline(nm)
+elif __name__ == '__main__':
     main()

@@ -3,7 +3,8 @@ import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
-from genesis_b200 import profiling, trainer
+from genesis_b200 import ops, profiling, trainer
+ops.set_side_streams(False)
 
 plugin, cfg = bench.build_cfg()
 torch.manual_seed(0)
