@@ -170,23 +170,35 @@ class GenesisV2(nn.Module, _g.NoiseMixin):
         z = mu + sigma * eps
         z_k = list(torch.chunk(z, K, 0))
         mu_k, sigma_k = list(torch.chunk(mu, K, 0)), list(torch.chunk(sigma, K, 0))
+        # --- KL (reference genesis_config.py:288-343): the prior LSTM + MC-KL sums are ~200 tiny kernels that do not feed the
+        # decoder, so they run on a side stream beside it (same scheme as genesis_config.py; backward follows automatically)
+        cur = torch.cuda.current_stream()
+        side = ops.side_stream(x.device) if (ops.side_streams_enabled() and torch.is_grad_enabled()) else cur
+        if side is not cur:
+            side.wait_stream(cur)
+            for t_ in (z, mu, sigma):
+                t_.record_stream(side)
+        with torch.cuda.stream(side):
+            if self.autoreg_prior and K > 1:
+                pmu, psig = H.autoreg_prior(z_k, self.prior_lstm, self.prior_linear)
+            else:
+                pmu, psig = [], []
+            kl = [H.mc_kl(z_k[0], mu_k[0], sigma_k[0])]
+            for k in range(1, K):
+                if pmu:
+                    kl.append(H.mc_kl(z_k[k], mu_k[k], sigma_k[k], pmu[k - 1], psig[k - 1]))
+                else:
+                    kl.append(H.mc_kl(z_k[k], mu_k[k], sigma_k[k]))
         # --- decode + softmax-mask mixture likelihood (reference :164-169, 205-225)
         dec = self._decode(z).view(K, B, 4, S, S)
         std = torch.full((K,), float(self.std), device=x.device)
         err, recon, log_m_r = ops.mixture_nll_packed(x, dec, None, std, True)
+        if side is not cur:
+            cur.wait_stream(side)
+            for t_ in kl + pmu + psig:
+                t_.record_stream(cur)
         losses = AttrDict()
         losses['err'] = err
-        # --- KL (reference genesis_config.py:288-343)
-        if self.autoreg_prior and K > 1:
-            pmu, psig = H.autoreg_prior(z_k, self.prior_lstm, self.prior_linear)
-        else:
-            pmu, psig = [], []
-        kl = [H.mc_kl(z_k[0], mu_k[0], sigma_k[0])]
-        for k in range(1, K):
-            if pmu:
-                kl.append(H.mc_kl(z_k[k], mu_k[k], sigma_k[k], pmu[k - 1], psig[k - 1]))
-            else:
-                kl.append(H.mc_kl(z_k[k], mu_k[k], sigma_k[k]))
         losses['kl_l_k'] = kl
         # --- tracking
         log_m_k = list(log_m.unbind(0))

@@ -613,6 +613,7 @@ class _Out1x1(Function):
         out = _new(h, N, nout, H, W)
         _call('g2_out1x1_fwd_f32', h, w2, b, out, N, H * W, Cin, nout, nsig)
         ctx.save_for_backward(h, w2, out)
+        ctx.params = (w, b)
         ctx.cfg = (nsig, b is not None)
         return out
 
@@ -626,6 +627,16 @@ class _Out1x1(Function):
         dpre4 = _new(h, N, H, W, 4)
         _call('g2_out1x1_bwd_f32', _c(dout), out, w2, dh, dpre4, N, H * W, Cin, nout, nsig)
         dw = db = None
+        w_param, b_param = ctx.params
+        if ctx.needs_input_grad[1] and Cin % 32 == 0 and _direct(w_param) and (not has_b or _direct(b_param)):
+            # direct-gradient mode: head weight / bias gradients accumulate into param.grad on the gradient side stream
+            with _GradStream(h, dpre4):
+                dw4 = _new(h, 4, Cin)
+                _call('g2_head_wgrad_f32', h, dpre4, dw4, N * H * W, Cin)
+                w_param.grad.view(nout, Cin).add_(dw4[:nout])
+                if has_b and ctx.needs_input_grad[2]:
+                    b_param.grad.add_(_colsum(dpre4, 4, dpre4)[:nout])
+            return dh, None, None, None
         if ctx.needs_input_grad[1]:
             dw4 = _new(h, 4, Cin)
             if Cin % 32 == 0:
