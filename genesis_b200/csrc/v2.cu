@@ -248,7 +248,11 @@ __global__ void masked_pool_fwd_kernel(const float* __restrict__ f, const float*
 }
 
 // df[b,p,c] = sum_k m_kp dnum[k,b,c];   dlog_m[k,b,p] = m_kp (sum_c f[b,p,c] dnum[k,b,c] + dmsum[k,b])
-// grid (chunks, B); block = 256 threads = 8 warps; one warp per pixel, lanes stride over channels.
+// grid (chunks, B); block = 256 threads = 8 warps.  A warp works on FOUR pixels at a time: lane = (pixel lane/8, channel
+// group lane%8), each lane owns C/8 channels as float4s, so every lane has C/32 independent 16-byte loads in flight (the
+// first version -- one pixel per warp, 178 registers, one block per SM -- was latency-bound at 2 ms for B=128).
+// KMAX bounds the per-lane arrays (m, dot); CPL = C/32 float4s per lane.
+template <int KMAX, int CPL>
 __global__ void __launch_bounds__(256) masked_pool_bwd_kernel(const float* __restrict__ f, const float* __restrict__ log_m,
                                                               const float* __restrict__ dnum, const float* __restrict__ dmsum,
                                                               float* __restrict__ df, float* __restrict__ dlog_m, int B, int P, int C,
@@ -261,24 +265,45 @@ __global__ void __launch_bounds__(256) masked_pool_bwd_kernel(const float* __res
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = lane >> 3, cg = lane & 7;
+    const int c0 = cg * 4;                 // float4 j of this lane covers channels c0 + 32*j .. +3
     const int p0 = blockIdx.x * pix_per_block, p1 = min(P, p0 + pix_per_block);
-    for (int p = p0 + warp; p < p1; p += 8) {
-        float m[MP_MAXK], dot[MP_MAXK];
+    for (int pb = p0 + warp * 4; pb < p1; pb += 32) {
+        const int p = pb + sub;
+        const bool ok = p < p1;
+        const int pc = ok ? p : p1 - 1;
+        float4 fv[CPL];
 #pragma unroll
-        for (int k = 0; k < MP_MAXK; ++k) { m[k] = k < K ? expf(__ldg(log_m + ((long)k * B + b) * P + p)) : 0.f; dot[k] = 0.f; }
-        for (int c = lane; c < C; c += 32) {
-            const float fv = __ldg(f + ((long)b * P + p) * C + c);
-            float g = 0.f;
+        for (int j = 0; j < CPL; ++j) fv[j] = g2_ldg4(f + ((long)b * P + pc) * C + c0 + 32 * j);
+        float m[KMAX], dot[KMAX];
 #pragma unroll
-            for (int k = 0; k < MP_MAXK; ++k)
-                if (k < K) { const float d = sd[k * C + c]; g = fmaf(m[k], d, g); dot[k] = fmaf(fv, d, dot[k]); }
-            df[((long)b * P + p) * C + c] = g;
+        for (int k = 0; k < KMAX; ++k) { m[k] = k < K ? expf(__ldg(log_m + ((long)k * B + b) * P + pc)) : 0.f; dot[k] = 0.f; }
+        float4 g[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+            if (k < K) {
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) {
+                    const float4 d = *reinterpret_cast<const float4*>(sd + k * C + c0 + 32 * j);
+                    g[j].x = fmaf(m[k], d.x, g[j].x); g[j].y = fmaf(m[k], d.y, g[j].y);
+                    g[j].z = fmaf(m[k], d.z, g[j].z); g[j].w = fmaf(m[k], d.w, g[j].w);
+                    dot[k] = fmaf(fv[j].x, d.x, fmaf(fv[j].y, d.y, fmaf(fv[j].z, d.z, fmaf(fv[j].w, d.w, dot[k]))));
+                }
+            }
+        if (ok) {
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) *reinterpret_cast<float4*>(df + ((long)b * P + p) * C + c0 + 32 * j) = g[j];
         }
 #pragma unroll
-        for (int k = 0; k < MP_MAXK; ++k)
+        for (int k = 0; k < KMAX; ++k)
             if (k < K) {
-                const float t = g2_warp_sum(dot[k]);
-                if (lane == 0) dlog_m[((long)k * B + b) * P + p] = m[k] * (t + __ldg(dmsum + (long)k * B + b));
+                float t = dot[k];
+                t += __shfl_xor_sync(0xffffffffu, t, 1);
+                t += __shfl_xor_sync(0xffffffffu, t, 2);
+                t += __shfl_xor_sync(0xffffffffu, t, 4);
+                if (ok && cg == 0) dlog_m[((long)k * B + b) * P + p] = m[k] * (t + __ldg(dmsum + (long)k * B + b));
             }
     }
 }
@@ -325,12 +350,21 @@ int g2_masked_pool_fwd_f32(const float* f, const float* log_m, float* num, float
 
 int g2_masked_pool_bwd_f32(const float* f, const float* log_m, const float* dnum, const float* dmsum, float* df, float* dlog_m,
                            int B, int P, int C, int K, cudaStream_t stream) {
-    G2_CHECK_ARG(f && log_m && dnum && dmsum && df && dlog_m && B > 0 && P > 0 && C >= 32 && K >= 1 && K <= MP_MAXK);
+    G2_CHECK_ARG(f && log_m && dnum && dmsum && df && dlog_m && B > 0 && P > 0 && C >= 32 && (C % 32) == 0 && K >= 1 && K <= MP_MAXK);
     G2_CHECK_ARG((size_t)K * C * sizeof(float) <= 48 * 1024);
+    G2_CHECK_ARG((reinterpret_cast<uintptr_t>(f) & 15) == 0 && (reinterpret_cast<uintptr_t>(df) & 15) == 0);
     int ppb = 256;
     while ((long)g2_cdiv(P, ppb) * B < 296 && ppb > 32) ppb /= 2;
     dim3 grid(g2_cdiv(P, ppb), B);
-    masked_pool_bwd_kernel<<<grid, 256, (size_t)K * C * sizeof(float), stream>>>(f, log_m, dnum, dmsum, df, dlog_m, B, P, C, K, ppb);
+    const size_t smem = (size_t)K * C * sizeof(float);
+#define MP_LAUNCH(KM, CP) masked_pool_bwd_kernel<KM, CP><<<grid, 256, smem, stream>>>(f, log_m, dnum, dmsum, df, dlog_m, B, P, C, K, ppb)
+    const int cpl = C / 32;
+    if (cpl == 4) { if (K <= 8) MP_LAUNCH(8, 4); else MP_LAUNCH(16, 4); }
+    else if (cpl == 2) { if (K <= 8) MP_LAUNCH(8, 2); else MP_LAUNCH(16, 2); }
+    else if (cpl == 1) { if (K <= 8) MP_LAUNCH(8, 1); else MP_LAUNCH(16, 1); }
+    else if (cpl == 8) { if (K <= 8) MP_LAUNCH(8, 8); else MP_LAUNCH(16, 8); }
+    else return G2_ERR_UNSUPPORTED;
+#undef MP_LAUNCH
     G2_LAUNCH_RET();
 }
 
