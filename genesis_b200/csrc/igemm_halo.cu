@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
     const int m_tiles = f_last / 128 + 1;
     const int nch = p.TNB > 1 ? 1 : min(p.nch, (rows_valid + p.span_h + p.ch_rows - 1) / p.ch_rows);
 
-    long long* dbg = p.dbg ? p.dbg + ((long)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+    long long* dbg = p.dbg ? p.dbg + ((long)blockIdx.y * gridDim.x + blockIdx.x) * 64 : nullptr;    // [8 phase stamps | 2 per tap]
     if (dbg && threadIdx.x == 32) { dbg[0] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); dbg[7] = sm; }
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.a);
@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
             for (int tap = 0; tap < p.ntaps; ++tap) {
                 const int s = bi;
                 mbar_wait(&fullB[s], bph);
+                if (dbg && lane == 0 && cb == 0 && tap < 28) dbg[8 + 2 * tap] = clock64();          // weight tile of this tap landed
                 const uint64_t bdesc = make_desc_k_sw128(smem_u32(sB + s * B_BYTES));
                 const int toff = p.toff[tap];
                 // activation chunks this tap reads (monotone in the tile index: wait for the last tile's)
@@ -257,6 +258,7 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
                     commit(&emptyB[s]);                 // weight stage free when these MMAs retire
                 }
                 __syncwarp();
+                if (dbg && lane == 0 && cb == 0 && tap < 28) dbg[9 + 2 * tap] = clock64();          // MMAs of this tap issued
                 if (++bi == STAGES) { bi = 0; bph ^= 1u; }
             }
             if (elect_one()) commit(emptyA);            // activation window free
@@ -518,7 +520,7 @@ int g2_conv_halo_enable(int on) {
     return prev;
 }
 
-// Debug only (scripts/conv_bench.py --timeline): device buffer of [CTAs][8] int64 that subsequent halo launches fill with
+// Debug only (scripts/conv_bench.py --timeline): device buffer of [CTAs][64] int64 that subsequent halo launches fill with
 // clock64() at {start, prologue done, first operands landed, last MMA issued, accumulators complete, epilogue done, -, smid};
 // pass NULL to switch it off.  Returns 0.
 int g2_conv_halo_debug(int64_t* buf) {

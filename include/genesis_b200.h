@@ -195,7 +195,7 @@ int g2_gemm_tf32(const float* A, const float* W, const float* bias, float* C, in
  * {nclasses, TH, TNB, RH, chunk_rows, chunks, m_tiles, a_bytes, tiles_h, Wp, dh_min, dw_min, os, ph, pw, Hv, Wv,
  *  ntaps, BN, smem_bytes}, plan[32+i] = flat row offset of tap i, plan[64+i] = its weight index. */
 int g2_conv_halo_enable(int on);
-/* debug: per-CTA clock64() phase timestamps of subsequent halo launches into a device buffer [CTAs][8] (NULL = off) */
+/* debug: per-CTA clock64() phase timestamps of subsequent halo launches into a device buffer [CTAs][64] (NULL = off) */
 int g2_conv_halo_debug(int64_t* buf);
 int g2_conv_halo_supported(int N, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int R, int S, int stride,
                            int pad, int mode);
@@ -204,6 +204,16 @@ int g2_conv_halo_tf32(const float* in, const float* w, const float* bias, float*
                       g2_stream_t stream);
 int g2_conv_halo_plan(int N, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int R, int S, int stride, int pad,
                       int mode, int cls, int* plan);
+
+/* ---- evaluation metrics (metrics.cu) ------------------------------------------------------------------
+ * Adjusted Rand index (all pixels / foreground only) and segmentation covering (mean / size-weighted, with / without the
+ * background) per image from one confusion matrix per image; replaces utils/misc.py:101-114 (average_ari over
+ * sklearn.metrics.adjusted_rand_score) and :173-235 (average_segcover) as called by train.py:536-546, plus the argmax
+ * over slots (train.py:541).  Exactly one of log_m [K,B,P] (fp32, slot-major) / pred [B,P] (int64) is non-NULL;
+ * inst [B,P] int64 ground-truth labels (0 = background; labels outside 0..31 are ignored); seg_out [B,P] int64 or NULL;
+ * out [B][8] doubles = {ari, ari_fg, msc, msc_fg, msc_scaled, msc_fg_scaled, labels present, pixels counted}. */
+int g2_seg_metrics(const float* log_m, const int64_t* pred, const int64_t* inst, int64_t* seg_out, double* out, int B,
+                   int P, int K, g2_stream_t stream);
 
 /* UMMA descriptor self-test (debug_umma.cu): runs `nk` tcgen05.mma.kind::tf32 (M=128) on caller-provided
  * shared-memory images of A and B with caller-provided descriptor templates and dumps D[128][N]. */

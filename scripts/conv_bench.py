@@ -145,7 +145,7 @@ def timeline(name):
     lib = _lib.lib()
     x = torch.randn(N, H, W, Ci, device=dev); w = torch.randn(R * R, Co, Ci, device=dev) * 0.05; b = torch.randn(Co, device=dev)
     out = torch.empty(N, Ho, Wo, Co, device=dev)
-    buf = torch.zeros(1 << 16, 8, dtype=torch.int64, device=dev)
+    buf = torch.zeros(1 << 14, 64, dtype=torch.int64, device=dev)
     for i in range(3):
         if i == 2:
             lib.query('g2_conv_halo_debug', ctypes.c_void_p(buf.data_ptr()))
@@ -159,6 +159,15 @@ def timeline(name):
     print('%s: %d CTAs, lifetime mean %.0f clk' % (name, t.shape[0], (t[:, 5] - t[:, 0]).mean()))
     for n_, v in zip(names, d):
         print('   %-32s mean %8.0f  p10 %8.0f  p90 %8.0f clk' % (n_, v.mean(), v.kthvalue(max(1, int(0.1 * len(v))))[0], v.kthvalue(max(1, int(0.9 * len(v))))[0]))
+    ntap = R * R if s == 1 else 9
+    ntap = min(ntap, 28)
+    w_ = t[:, 8:8 + 2 * ntap:2]
+    i_ = t[:, 9:9 + 2 * ntap:2]
+    okc = (w_ > 0).all(1) & (i_ > 0).all(1)
+    if okc.any():
+        w_, i_, base = w_[okc], i_[okc], t[okc, 2:3]
+        print('   per tap (clk since first operands landed): weight-ready ' + ' '.join('%d' % v for v in (w_ - base).mean(0).tolist()))
+        print('   per tap: MMAs issued                                    ' + ' '.join('%d' % v for v in (i_ - base).mean(0).tolist()))
     # concurrency: CTAs per SM over the kernel
     span = (t[:, 5].max() - t[:, 0].min())
     print('   kernel span (max end - min start, mixed SM clocks) %.0f clk; sum lifetimes / (148 * span) = %.2f CTAs resident per SM'
