@@ -248,11 +248,15 @@ def lstm_step(x, state, lstm):
     """One step of nn.LSTM (1 layer; gates i,f,g,o) with our GEMM; x [B,in]."""
     gates = ops.linear(x, lstm.weight_ih_l0, lstm.bias_ih_l0)
     if state is None:
-        gates = gates + lstm.bias_hh_l0
+        # h_0 = 0.  The recurrent term still goes through ops.linear (it returns exactly bias_hh) so that EVERY use of
+        # bias_hh_l0 / weight_hh_l0 takes the same gradient path: in direct-gradient mode the kernels accumulate into
+        # param.grad on the gradient side stream, and a second, autograd-side `grad +=` of the same tensor on the main
+        # stream (what `gates + lstm.bias_hh_l0` produced) could interleave with them.
+        h_prev = x.new_zeros(x.shape[0], lstm.weight_hh_l0.shape[1])
         c_prev = None
     else:
         h_prev, c_prev = state
-        gates = gates + ops.linear(h_prev, lstm.weight_hh_l0, lstm.bias_hh_l0)
+    gates = gates + ops.linear(h_prev, lstm.weight_hh_l0, lstm.bias_hh_l0)
     i, f, g, o = torch.chunk(gates, 4, dim=1)
     c = torch.sigmoid(i) * torch.tanh(g)
     if c_prev is not None:

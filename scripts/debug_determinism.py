@@ -43,7 +43,7 @@ for prec in ('fp32', 'tf32'):
     m, cfg = build_engine_model('genesis', 3, 64)
     m = m.cuda().train()
     x = torch.from_numpy(synth.GENERATORS['multid'](4, 64, 5)[0]).cuda()
-    a = grads_of(m, x, 11, False); b = grads_of(m, x, 11, False)
+    a, _ = grads_of(m, x, 11, False); b, _ = grads_of(m, x, 11, False)
     worst = sorted(((((b[n] - a[n]).norm() / (a[n].norm() + 1e-20)).item(), n) for n in a if a[n] is not None and a[n].norm() > 1e-3), reverse=True)[:4]
     print(prec, 'run-to-run worst:', worst)
 ops.set_precision('tf32')

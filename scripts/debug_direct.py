@@ -9,9 +9,9 @@ model, K, img, B, gen = sys.argv[1], int(sys.argv[2]), 64, int(sys.argv[3]), 'mu
 m, cfg = build_engine_model(model, K, img)
 m = m.cuda().train()
 x = torch.from_numpy(synth.GENERATORS[gen](B, img, 5)[0]).cuda()
-a = grads_of(m, x, 11, False)
-b = grads_of(m, x, 11, False)
-c = grads_of(m, x, 11, True, 0.25)
+a, _ = grads_of(m, x, 11, False)
+b, _ = grads_of(m, x, 11, False)
+c, _ = grads_of(m, x, 11, True, 0.25)
 def rel(u, v):
     return ((u - v).norm() / (v.norm() + 1e-20)).item()
 print('%-55s %10s %10s %10s' % ('param', 'auto-auto', 'dir-auto', '|g|'))
