@@ -174,6 +174,8 @@ def normal_log_prob(z, mu, sigma):
 
 def mc_kl(z, mu, sigma, pmu=None, psigma=None):
     """sum_d [log q(z) - log p(z)]; p = N(0,1) when pmu is None (reference genesis_config.py:328-336)."""
+    if ops.fused_latent() and z.is_cuda:
+        return ops.mc_kl(z, mu, sigma, pmu, psigma)
     log_q = normal_log_prob(z, mu, sigma).sum(dim=1)
     if pmu is None:
         log_p = (-0.5 * z ** 2 - 0.5 * LOG_2PI).sum(dim=1)
@@ -256,7 +258,11 @@ def lstm_step(x, state, lstm):
         c_prev = None
     else:
         h_prev, c_prev = state
-    gates = gates + ops.linear(h_prev, lstm.weight_hh_l0, lstm.bias_hh_l0)
+    gh = ops.linear(h_prev, lstm.weight_hh_l0, lstm.bias_hh_l0)
+    if ops.fused_latent():
+        h, c = ops.lstm_cell(gates, gh, c_prev)
+        return h, (h, c)
+    gates = gates + gh
     i, f, g, o = torch.chunk(gates, 4, dim=1)
     c = torch.sigmoid(i) * torch.tanh(g)
     if c_prev is not None:
@@ -273,10 +279,27 @@ def autoreg_prior(z_k, lstm, lin):
     for z in z_k[:-1]:
         out, state = lstm_step(z, state, lstm)
         lo = ops.linear(out, lin.weight, lin.bias)
-        a, b = torch.chunk(lo, 2, dim=1)
-        pmu.append(torch.tanh(a))
-        psig.append(to_prior_sigma(b))
+        m, s_ = prior_head(lo)
+        pmu.append(m)
+        psig.append(s_)
     return pmu, psig
+
+
+def prior_head(lo, use_tanh=True):
+    """lo [B,2D] -> (tanh(lo[:, :D]), to_prior_sigma(lo[:, D:])) (reference genesis_config.py:306-314, 234-239)."""
+    if ops.fused_latent():
+        return ops.prior_head(lo, use_tanh)
+    a, b = torch.chunk(lo, 2, dim=1)
+    return (torch.tanh(a) if use_tanh else a), to_prior_sigma(b)
+
+
+def gauss_head(lo, eps):
+    """lo [B,2D] = (mu | raw) -> z = mu + to_sigma(raw) * eps, mu, sigma (reference attention.py:98-103, component_vae.py:64-69)."""
+    if ops.fused_latent():
+        return ops.gauss_head(lo, eps)
+    mu, raw = torch.chunk(lo, 2, dim=1)
+    sigma = to_sigma(raw)
+    return mu + sigma * eps, mu, sigma
 
 
 _COORDS = {}

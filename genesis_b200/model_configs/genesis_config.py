@@ -129,18 +129,16 @@ class Genesis(nn.Module, NoiseMixin):
         h = H.sylvester_encode(core, xh, self.training)                                 # [B,256]
         wmv = torch.cat([core.q_z_mean.weight, core.q_z_var[0].weight], 0)
         bmv = torch.cat([core.q_z_mean.bias, core.q_z_var[0].bias], 0)
-        mu, raw = torch.chunk(ops.linear(h, wmv, bmv), 2, dim=1)
-        sigma = H.to_sigma(raw)                     # sqrt(to_var(.)) == to_sigma(.) (VAE.py:126)
-        mu_k, sigma_k = [mu], [sigma]
-        z_k = [mu + sigma * self._normal(mu.shape, x)]
+        # sigma = to_sigma(raw): sqrt(to_var(.)) == to_sigma(.) (VAE.py:126)
+        z, mu, sigma = H.gauss_head(ops.linear(h, wmv, bmv), self._normal((B, self.ldim), x))
+        mu_k, sigma_k, z_k = [mu], [sigma], [z]
         state = None
         for _ in range(1, K):
             out, state = H.lstm_step(torch.cat([h, z_k[-1]], dim=1), state, ap.lstm)
-            a, b = torch.chunk(ops.linear(out, ap.linear.weight, ap.linear.bias), 2, dim=1)
-            s = H.to_sigma(b)
+            z, a, s = H.gauss_head(ops.linear(out, ap.linear.weight, ap.linear.bias), self._normal((B, self.ldim), x))
             mu_k.append(a)
             sigma_k.append(s)
-            z_k.append(a + s * self._normal(a.shape, x))
+            z_k.append(z)
         logits = H.sylvester_decode(core, torch.cat(z_k, 0), self.training)             # [K*B,1,H,W]
         logits = logits.view(K, B, 1, self.img_size, self.img_size)
         log_m, log_s = ops.sbp_scan(logits, K)
@@ -180,14 +178,11 @@ class Genesis(nn.Module, NoiseMixin):
                 pm = self.prior_mlp
                 t = ops.linear(torch.cat(z_k, 0), pm[0].weight, pm[0].bias, 'elu')
                 t = ops.linear(t, pm[2].weight, pm[2].bias, 'elu')
-                a, b = torch.chunk(ops.linear(t, pm[4].weight, pm[4].bias), 2, dim=1)
-                cpmu, cpsig = torch.tanh(a), H.to_prior_sigma(b)
+                cpmu, cpsig = H.prior_head(ops.linear(t, pm[4].weight, pm[4].bias))
         # --- component VAE (reference component_vae.py:45-81), K slots batched k-major
         cv = self.comp_vae
         enc = H.comp_encode(cv.encoder_module, ops.comp_pack(x, log_m, 32 if ops.get_precision() == 'tf32' else 4), 'elu')
-        cmu, cps = torch.chunk(enc, 2, dim=1)
-        csig = H.to_sigma(cps)
-        cz = cmu + csig * self._normal(cmu.shape, x)
+        cz, cmu, csig = H.gauss_head(enc, self._normal((enc.shape[0], enc.shape[1] // 2), x))
         if side is not cur:
             side.wait_stream(cur)           # cz, cmu, csig are ready
             for t_ in (cz, cmu, csig, enc):

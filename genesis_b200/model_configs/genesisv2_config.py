@@ -163,11 +163,10 @@ class GenesisV2(nn.Module, _g.NoiseMixin):
         zh = self.z_head
         t = H.layer_norm(obj, zh[0])
         t = ops.linear(t, zh[1].weight, zh[1].bias, 'relu')
-        mu, sps = torch.chunk(ops.linear(t, zh[3].weight, zh[3].bias), 2, dim=1)
-        sigma = H.to_sigma(sps)
+        lo = ops.linear(t, zh[3].weight, zh[3].bias)
         # the reference draws one [B,64] normal per slot, in slot order (:156-157)
-        eps = torch.cat([self._normal((B, mu.shape[1]), x) for _ in range(K)], 0)
-        z = mu + sigma * eps
+        eps = torch.cat([self._normal((B, lo.shape[1] // 2), x) for _ in range(K)], 0)
+        z, mu, sigma = H.gauss_head(lo, eps)
         z_k = list(torch.chunk(z, K, 0))
         mu_k, sigma_k = list(torch.chunk(mu, K, 0)), list(torch.chunk(sigma, K, 0))
         # --- KL (reference genesis_config.py:288-343): the prior LSTM + MC-KL sums are ~200 tiny kernels that do not feed the

@@ -100,9 +100,7 @@ class MONet(nn.Module, _g.NoiseMixin):
         log_m = torch.stack(log_m_k, 0)                                     # [K,B,1,H,W]
         cv = self.comp_vae
         enc = H.comp_encode(cv.encoder_module, ops.comp_pack(x, log_m, 32 if ops.get_precision() == 'tf32' else 4), 'relu')
-        cmu, cps = torch.chunk(enc, 2, dim=1)
-        csig = H.to_sigma(cps)
-        cz = cmu + csig * self._normal(cmu.shape, x)
+        cz, cmu, csig = H.gauss_head(enc, self._normal((enc.shape[0], enc.shape[1] // 2), x))
         dec = H.broadcast_decode(cv.decoder_module, cz, 'relu', 3 if self.pixel_bound else 0)
         dec = dec.view(K, B, 4, self.img_size, self.img_size)
         err, kl_m, recon, log_m_r = ops.monet_loss(x, dec, log_m, self.std.reshape(-1))

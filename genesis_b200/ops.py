@@ -869,3 +869,129 @@ class _MonetLoss(Function):
 
 def monet_loss(x, dec, lm, std):
     return _MonetLoss.apply(x, dec, lm, std)
+
+
+# ----------------------------------------------------------------------------------------- fused latent path
+# One kernel each for the LSTM cell, the Gaussian head (to_sigma + rsample), the prior head (tanh / to_prior_sigma) and the
+# Monte-Carlo KL, forward and backward (csrc/latent.cu).  Switched by set_fused_latent(); OFF by default until the kernels
+# have been validated on a B200 (tests/test_pending_next_round.py) -- the ATen formulation in holders.py stays the
+# validated path.
+_FUSED = {'on': False}
+
+
+def set_fused_latent(on):
+    _FUSED['on'] = bool(on)
+
+
+def fused_latent():
+    return _FUSED['on']
+
+
+class _LSTMCell(Function):
+    """gx, gh [B,4H] (the two gate GEMMs incl. biases), c_prev [B,H] or None -> h, c."""
+
+    @staticmethod
+    def forward(ctx, gx, gh, c_prev):
+        gx, gh = _c(gx), _c(gh)
+        B, H = gx.shape[0], gx.shape[1] // 4
+        cp = _c(c_prev) if c_prev is not None else None
+        h, c = _new(gx, B, H), _new(gx, B, H)
+        _call('g2_lstm_cell_fwd_f32', gx, gh, cp, h, c, B, H)
+        ctx.save_for_backward(gx, gh, cp, c)
+        return h, c
+
+    @staticmethod
+    def backward(ctx, dh, dc):
+        gx, gh, cp, c = ctx.saved_tensors
+        B, H = c.shape
+        dg = torch.empty_like(gx)
+        dcp = torch.empty_like(c) if cp is not None else None
+        _call('g2_lstm_cell_bwd_f32', gx, gh, cp, c, _c(dh) if dh is not None else None, _c(dc) if dc is not None else None,
+              dg, dcp, B, H)
+        return dg, dg, dcp
+
+
+def lstm_cell(gx, gh, c_prev=None):
+    return _LSTMCell.apply(gx, gh, c_prev)
+
+
+class _GaussHead(Function):
+    """lo [B,2D] = (mu | raw), eps [B,D] -> z, mu, sigma (sigma = softplus(raw + 0.5) + 1e-8, z = mu + sigma * eps)."""
+
+    @staticmethod
+    def forward(ctx, lo, eps):
+        lo, eps = _c(lo), _c(eps)
+        B, D = lo.shape[0], lo.shape[1] // 2
+        z, mu, sigma = _new(lo, B, D), _new(lo, B, D), _new(lo, B, D)
+        _call('g2_gauss_head_fwd_f32', lo, eps, z, mu, sigma, B, D)
+        ctx.save_for_backward(lo, eps)
+        return z, mu, sigma
+
+    @staticmethod
+    def backward(ctx, dz, dmu, dsigma):
+        lo, eps = ctx.saved_tensors
+        B, D = eps.shape
+        dlo = torch.empty_like(lo)
+        _call('g2_gauss_head_bwd_f32', lo, eps, _c(dz) if dz is not None else None, _c(dmu) if dmu is not None else None,
+              _c(dsigma) if dsigma is not None else None, dlo, B, D)
+        return dlo, None
+
+
+def gauss_head(lo, eps):
+    return _GaussHead.apply(lo, eps)
+
+
+class _PriorHead(Function):
+    """lo [B,2D] = (a | b) -> pmu = tanh(a) (or a), psigma = sigmoid(b + 4) + 1e-4."""
+
+    @staticmethod
+    def forward(ctx, lo, use_tanh):
+        lo = _c(lo)
+        B, D = lo.shape[0], lo.shape[1] // 2
+        pmu, psig = _new(lo, B, D), _new(lo, B, D)
+        _call('g2_prior_head_fwd_f32', lo, pmu, psig, B, D, 1 if use_tanh else 0)
+        ctx.save_for_backward(pmu, psig)
+        ctx.use_tanh = use_tanh
+        return pmu, psig
+
+    @staticmethod
+    def backward(ctx, dpmu, dpsig):
+        pmu, psig = ctx.saved_tensors
+        B, D = pmu.shape
+        dlo = _new(pmu, B, 2 * D)
+        _call('g2_prior_head_bwd_f32', pmu, psig, _c(dpmu) if dpmu is not None else None,
+              _c(dpsig) if dpsig is not None else None, dlo, B, D, 1 if ctx.use_tanh else 0)
+        return dlo, None
+
+
+def prior_head(lo, use_tanh=True):
+    return _PriorHead.apply(lo, use_tanh)
+
+
+class _MCKL(Function):
+    """kl[b] = sum_d log N(z;mu,sigma) - log N(z;pmu,psigma)   (pmu None: standard-normal prior)."""
+
+    @staticmethod
+    def forward(ctx, z, mu, sigma, pmu, psigma):
+        z, mu, sigma = _c(z), _c(mu), _c(sigma)
+        pmu = _c(pmu) if pmu is not None else None
+        psigma = _c(psigma) if psigma is not None else None
+        B, D = z.shape
+        kl = _new(z, B)
+        _call('g2_mc_kl_fwd_f32', z, mu, sigma, pmu, psigma, kl, B, D)
+        ctx.save_for_backward(z, mu, sigma, pmu, psigma)
+        return kl
+
+    @staticmethod
+    def backward(ctx, dkl):
+        z, mu, sigma, pmu, psigma = ctx.saved_tensors
+        B, D = z.shape
+        dz, dmu, dsig = torch.empty_like(z), torch.empty_like(z), torch.empty_like(z)
+        dpmu = torch.empty_like(z) if pmu is not None else None
+        dpsig = torch.empty_like(z) if pmu is not None else None
+        _call('g2_mc_kl_bwd_f32', z, mu, sigma, pmu, psigma, _c(dkl), dz, dmu, dsig, dpmu, dpsig, B, D)
+        return dz, dmu, dsig, dpmu, dpsig
+
+
+def mc_kl(z, mu, sigma, pmu=None, psigma=None):
+    return _MCKL.apply(z, mu, sigma, pmu, psigma)

@@ -205,6 +205,35 @@ int g2_conv_halo_tf32(const float* in, const float* w, const float* bias, float*
 int g2_conv_halo_plan(int N, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int R, int S, int stride, int pad,
                       int mode, int cls, int* plan);
 
+/* ---- latent path, fused elementwise kernels (latent.cu) ---------------------------------------------
+ * LSTM cell after the two gate GEMMs (gates = gx + gh, [B,4H], order i,f,g,o; c_prev NULL = zero state): replaces the
+ * sigmoid/tanh/mul/add chain of one torch.nn.LSTM step (modules/attention.py:94-97, models/genesis_config.py:301-305).
+ * bwd: dgates [B,4H] is the gradient of both gx and gh; dh / dc / dc_prev may be NULL. */
+int g2_lstm_cell_fwd_f32(const float* gx, const float* gh, const float* c_prev, float* h, float* c, int B, int H,
+                         g2_stream_t stream);
+int g2_lstm_cell_bwd_f32(const float* gx, const float* gh, const float* c_prev, const float* c, const float* dh,
+                         const float* dc, float* dgates, float* dc_prev, int B, int H, g2_stream_t stream);
+/* Gaussian head on the un-chunked Linear output lo [B,2D] = (mu | raw): sigma = softplus(raw + 0.5) + 1e-8
+ * (modules/blocks.py:22-23), z = mu + sigma * eps (rsample with caller-supplied noise: component_vae.py:67-69,
+ * attention.py:98-103); mu is also written contiguously.  bwd: dlo = (dz + dmu | (dz*eps + dsigma) * sigmoid(raw + 0.5));
+ * dz / dmu / dsigma may be NULL. */
+int g2_gauss_head_fwd_f32(const float* lo, const float* eps, float* z, float* mu, float* sigma, int B, int D,
+                          g2_stream_t stream);
+int g2_gauss_head_bwd_f32(const float* lo, const float* eps, const float* dz, const float* dmu, const float* dsigma,
+                          float* dlo, int B, int D, g2_stream_t stream);
+/* Prior head on lo [B,2D] = (a | b): pmu = tanh(a) (use_tanh = 0: pmu = a, Genesis.sample genesis_config.py:359),
+ * psigma = sigmoid(b + 4) + 1e-4 (modules/blocks.py:28-34). */
+int g2_prior_head_fwd_f32(const float* lo, float* pmu, float* psigma, int B, int D, int use_tanh, g2_stream_t stream);
+int g2_prior_head_bwd_f32(const float* pmu, const float* psigma, const float* dpmu, const float* dpsigma, float* dlo,
+                          int B, int D, int use_tanh, g2_stream_t stream);
+/* Monte-Carlo KL per row: kl[b] = sum_d log N(z;mu,sigma) - log N(z;pmu,psigma) (models/genesis_config.py:328-336);
+ * pmu = psigma = NULL: standard-normal prior.  bwd writes the gradients of all five inputs for a given dkl[B]. */
+int g2_mc_kl_fwd_f32(const float* z, const float* mu, const float* sigma, const float* pmu, const float* psigma,
+                     float* kl, int B, int D, g2_stream_t stream);
+int g2_mc_kl_bwd_f32(const float* z, const float* mu, const float* sigma, const float* pmu, const float* psigma,
+                     const float* dkl, float* dz, float* dmu, float* dsigma, float* dpmu, float* dpsigma, int B, int D,
+                     g2_stream_t stream);
+
 /* ---- evaluation metrics (metrics.cu) ------------------------------------------------------------------
  * Adjusted Rand index (all pixels / foreground only) and segmentation covering (mean / size-weighted, with / without the
  * background) per image from one confusion matrix per image; replaces utils/misc.py:101-114 (average_ari over

@@ -49,3 +49,68 @@ def test_lstm_first_step_matches_later_step_path():
     h.sum().backward()
     assert lstm.bias_hh_l0.grad is not None and lstm.weight_hh_l0.grad.abs().max().item() == 0.0
     assert (lstm.bias_hh_l0.grad - lstm.bias_ih_l0.grad).abs().max().item() < 1e-5
+
+
+def test_fused_latent_ops_equal_autograd():
+    """csrc/latent.cu through ops.lstm_cell / gauss_head / prior_head / mc_kl vs torch autograd on the ATen formulation."""
+    from genesis_b200 import holders as H, ops
+    torch.manual_seed(0)
+    dev = 'cuda'
+
+    def both(fn, inputs, n_out):
+        outs = []
+        for fused in (False, True):
+            ops.set_fused_latent(fused)
+            try:
+                xs = [t.clone().requires_grad_(True) if t is not None else None for t in inputs]
+                o = fn(*xs)
+                o = o if isinstance(o, tuple) else (o,)
+                w = [torch.randn_like(t) for t in o[:n_out]]
+                torch.manual_seed(1)
+                w = [torch.randn_like(t) for t in o[:n_out]]
+                loss = sum((t * wt).sum() for t, wt in zip(o[:n_out], w))
+                g = torch.autograd.grad(loss, [t for t in xs if t is not None])
+                outs.append(([t.detach() for t in o[:n_out]], g))
+            finally:
+                ops.set_fused_latent(False)
+        for a, b in zip(outs[0][0] + list(outs[0][1]), outs[1][0] + list(outs[1][1])):
+            assert (a - b).abs().max().item() <= 2e-5 * max(1.0, a.abs().max().item())
+
+    B, Hh, D = 6, 128, 64
+    lstm = torch.nn.LSTM(96, Hh).to(dev)
+    x = torch.randn(B, 96, device=dev)
+    both(lambda xx: H.lstm_step(xx, None, lstm)[1], [x], 2)                                            # first step: (h, c)
+    st = (torch.randn(B, Hh, device=dev), torch.randn(B, Hh, device=dev))
+    both(lambda xx, h0, c0: H.lstm_step(xx, (h0, c0), lstm)[1], [x, st[0], st[1]], 2)
+    lo, eps = torch.randn(B, 2 * D, device=dev) * 3, torch.randn(B, D, device=dev)
+    both(lambda l: H.gauss_head(l, eps), [lo], 3)
+    both(lambda l: H.prior_head(l), [lo], 2)
+    z, mu, pmu = (torch.randn(B, D, device=dev) for _ in range(3))
+    sg, psg = torch.rand(B, D, device=dev) + 0.2, torch.rand(B, D, device=dev) + 0.2
+    both(lambda *a: H.mc_kl(*a), [z, mu, sg, pmu, psg], 1)
+    both(lambda a, b, c: H.mc_kl(a, b, c), [z, mu, sg], 1)
+
+
+@pytest.mark.parametrize('model,K,B,gen', [('genesis', 3, 4, 'multid'), ('genesisv2', 4, 3, 'stacks'), ('monet', 3, 2, 'multid')])
+def test_fused_latent_model_equals_unfused(model, K, B, gen):
+    """Whole-model forward + backward with ops.set_fused_latent(True) vs the validated ATen formulation."""
+    import util_parity as U
+    from genesis_b200 import ops
+    from oracle import synth
+    from test_oracle_golden import build_engine_model
+    m, cfg = build_engine_model(model, K, 64)
+    m = m.cuda().train()
+    x = torch.from_numpy(synth.GENERATORS[gen](B, 64, 5)[0]).cuda()
+    res = []
+    for fused in (False, True):
+        ops.set_fused_latent(fused)
+        try:
+            recon, losses, stats, att, comp = U.run_engine(m, x.cpu(), U.make_tape(11))
+        finally:
+            ops.set_fused_latent(False)
+        res.append((losses['err'].detach().clone(), {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}))
+    assert (res[0][0] - res[1][0]).abs().max().item() <= 1e-4 * res[0][0].abs().max().item()
+    gmax = max(g.norm().item() for g in res[0][1].values())
+    for n, g in res[0][1].items():
+        d = (res[1][1][n] - g).norm().item()
+        assert d <= 2e-2 * g.norm().item() + 1e-3 * gmax, (n, d, g.norm().item())       # run-to-run TF32 noise is ~1e-3
