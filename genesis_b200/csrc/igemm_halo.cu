@@ -30,6 +30,7 @@ using namespace umma;
 constexpr int MAX_TAPS = 32;
 constexpr int MAX_CHUNKS = 8;
 constexpr int MAX_STAGES = 12;
+constexpr int MAX_PSTAGES = 64;     // persistent variant: up to 64 resident (channel block, tap) weight tiles
 
 struct Maps { CUtensorMap a; CUtensorMap b; };
 
@@ -297,6 +298,206 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------------ persistent variant
+// EXPERIMENTAL (G2_HALO_PERSISTENT=1; off by default: written after the round-1 GPU budget was spent, not yet run on a B200).
+// One CTA per SM walks the work items (item = the tile the kernel above gives to one CTA) with a static stride.  Two
+// activation windows, two TMEM accumulator sets and a dedicated store-staging tile let the three roles run ahead of one
+// another: the producer loads window i+1 while the MMA warp works on window i, and the epilogue drains accumulator set
+// (i & 1) under the MMAs of item i+1 -- the MMA phase, which already runs at the shared-memory operand-read bound
+// (DESIGN.md 3.1), then covers the whole lifetime.  Weights stay resident when all taps fit (3x3), else they stream
+// through the ring once per item.
+constexpr int PSTAGE_BYTES = 4 * 4096;      // epilogue staging: 4 warps x (32 rows x 128 B)
+
+struct PP {
+    P p;                                // per-item geometry, as for the kernel above
+    int items_x, items_y;               // work items: blockIdx.x / blockIdx.y space of the non-persistent launch
+    int acc_cols;                       // TMEM columns of one accumulator set (m_tiles * BN)
+    int b_resident;                     // 1: every (cb, tap) weight tile has its own stage and is loaded once per CTA
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1) conv_halo_persistent_kernel(const __grid_constant__ Maps maps, const __grid_constant__ PP pp) {
+    const P& p = pp.p;
+    constexpr int B_BYTES = BN * 128;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* sm = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    uint8_t* sA0 = sm;                                   // two windows of p.a_bytes
+    uint8_t* sB = sm + 2 * (size_t)p.a_bytes;
+    const int STAGES = p.stages;
+    uint8_t* sStage = sB + (size_t)STAGES * B_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + PSTAGE_BYTES);
+    uint64_t* fullA = bars;                              // [2][MAX_CHUNKS]
+    uint64_t* emptyA = fullA + 2 * MAX_CHUNKS;           // [2]
+    uint64_t* fullB = emptyA + 2;                        // [MAX_PSTAGES]
+    uint64_t* emptyB = fullB + MAX_PSTAGES;
+    uint64_t* accFull = emptyB + MAX_PSTAGES;            // [2]
+    uint64_t* accEmpty = accFull + 2;                    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accEmpty + 2);
+    float* sBias = reinterpret_cast<float*>(bars) + 384; // 1.5 KB past the start of the barrier block (150 barriers = 1.2 KB)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_items = pp.items_x * pp.items_y;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&maps.a);
+        prefetch_tmap(&maps.b);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int j = 0; j < 2 * MAX_CHUNKS; ++j) mbar_init(&fullA[j], 1);
+            for (int j = 0; j < 2; ++j) { mbar_init(&emptyA[j], 1); mbar_init(&accFull[j], 1); mbar_init(&accEmpty[j], 4); }
+            for (int s = 0; s < MAX_PSTAGES; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // geometry of work item `item` (same decomposition as conv_halo_kernel's blockIdx)
+    auto decode = [&](int item, int& n0, int& h0, int& w0, int& n0c, int& rows_valid, int& cols_valid, int& imgs_valid, int& m_tiles,
+                      int& nch) {
+        const int bx = item % pp.items_x, by = item / pp.items_x;
+        const int tw_i = bx % p.tiles_w, th_i = (bx / p.tiles_w) % p.tiles_h;
+        n0 = (bx / (p.tiles_w * p.tiles_h)) * p.TNB;
+        h0 = th_i * p.TH; w0 = tw_i * p.TW; n0c = by * BN;
+        rows_valid = min(p.TH, p.Hv - h0); cols_valid = min(p.TW, p.Wv - w0); imgs_valid = min(p.TNB, p.N - n0);
+        m_tiles = (((imgs_valid - 1) * p.RH + rows_valid - 1) * p.Wp + cols_valid - 1) / 128 + 1;
+        nch = p.TNB > 1 ? 1 : min(p.nch, (rows_valid + p.span_h + p.ch_rows - 1) / p.ch_rows);
+    };
+
+    if (warp == 0) {
+        // ---- TMA producer
+        const uint32_t ch_bytes = (uint32_t)p.ch_pix * 128u;
+        int bi = 0; uint32_t bph = 0;
+        int u = 0;                                        // activation-window load counter: buffer u & 1, use (u >> 1)
+        bool b_loaded = false;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int n0, h0, w0, n0c, rv, cv, iv, mt, nch;
+            decode(item, n0, h0, w0, n0c, rv, cv, iv, mt, nch);
+            for (int cb = 0; cb < p.cblocks; ++cb, ++u) {
+                const int buf = u & 1;
+                mbar_wait(&emptyA[buf], (((uint32_t)(u >> 1)) & 1u) ^ 1u);
+                if (elect_one()) {
+                    for (int j = 0; j < nch; ++j) {
+                        mbar_expect_tx(&fullA[buf * MAX_CHUNKS + j], ch_bytes);
+                        tma_load_4d(sA0 + (size_t)buf * p.a_bytes + (size_t)j * ch_bytes, &maps.a, &fullA[buf * MAX_CHUNKS + j], cb * 32,
+                                    w0 + p.dw_min, h0 + p.dh_min + j * p.ch_rows, n0);
+                    }
+                }
+                __syncwarp();
+                if (pp.b_resident) {
+                    if (!b_loaded && elect_one()) {       // all (cb, tap) weight tiles once per CTA (items_y == 1 when resident)
+                        for (int c2 = 0; c2 < p.cblocks; ++c2)
+                            for (int tap = 0; tap < p.ntaps; ++tap) {
+                                const int s = c2 * p.ntaps + tap;
+                                mbar_expect_tx(&fullB[s], B_BYTES);
+                                tma_load_3d(sB + s * B_BYTES, &maps.b, &fullB[s], c2 * 32, n0c, p.widx[tap]);
+                            }
+                    }
+                    b_loaded = true;
+                    __syncwarp();
+                } else {
+                    for (int tap = 0; tap < p.ntaps; ++tap) {
+                        const int s = bi;
+                        mbar_wait(&emptyB[s], bph ^ 1u);
+                        if (elect_one()) {
+                            mbar_expect_tx(&fullB[s], B_BYTES);
+                            tma_load_3d(sB + s * B_BYTES, &maps.b, &fullB[s], cb * 32, n0c, p.widx[tap]);
+                        }
+                        __syncwarp();
+                        if (++bi == STAGES) { bi = 0; bph ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer
+        constexpr uint32_t idesc = idesc_tf32(BN);
+        const uint64_t hi = desc_k_sw128_hi();
+        int bi = 0; uint32_t bph = 0;
+        int u = 0, it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            int n0, h0, w0, n0c, rv, cv, iv, m_tiles, nch;
+            decode(item, n0, h0, w0, n0c, rv, cv, iv, m_tiles, nch);
+            const int acc = it & 1;
+            mbar_wait(&accEmpty[acc], (((uint32_t)(it >> 1)) & 1u) ^ 1u);      // the epilogue has drained this accumulator set
+            fence_after();
+            const uint32_t tacc = tmem_base + (uint32_t)(acc * pp.acc_cols);
+            for (int cb = 0; cb < p.cblocks; ++cb, ++u) {
+                const int buf = u & 1;
+                const uint32_t aph = ((uint32_t)(u >> 1)) & 1u;
+                const uint32_t a0 = smem_u32(sA0 + (size_t)buf * p.a_bytes) >> 4;
+                int waited = 0;
+                for (int tap = 0; tap < p.ntaps; ++tap) {
+                    int s; uint32_t ph;
+                    if (pp.b_resident) { s = cb * p.ntaps + tap; ph = 0; } else { s = bi; ph = bph; }
+                    mbar_wait(&fullB[s], ph);
+                    const uint64_t bdesc = make_desc_k_sw128(smem_u32(sB + s * B_BYTES));
+                    const int toff = p.toff[tap];
+                    const int need = min(nch - 1, (128 * (m_tiles - 1) + 127 + toff) / p.ch_pix);
+                    while (waited <= need) { mbar_wait(&fullA[buf * MAX_CHUNKS + waited], aph); ++waited; }
+                    fence_after();
+                    const uint32_t alo = a0 + (uint32_t)toff * 8u;
+                    const uint32_t first = (cb | tap) != 0 ? 1u : 0u;
+                    if (elect_one()) {
+                        for (int t = 0; t < m_tiles; ++t) {
+                            const uint64_t adesc = hi | (uint64_t)((alo + (uint32_t)t * 1024u) & 0x3FFFu);
+                            const uint32_t d = tacc + (uint32_t)(t * BN);
+                            mma_tf32(d, adesc, bdesc, idesc, first);
+                            mma_tf32(d, adesc + 2, bdesc + 2, idesc, 1u);
+                            mma_tf32(d, adesc + 4, bdesc + 4, idesc, 1u);
+                            mma_tf32(d, adesc + 6, bdesc + 6, idesc, 1u);
+                        }
+                        if (!pp.b_resident) commit(&emptyB[s]);
+                    }
+                    __syncwarp();
+                    if (!pp.b_resident && ++bi == STAGES) { bi = 0; bph ^= 1u; }
+                }
+                if (elect_one()) commit(&emptyA[buf]);           // window free when these MMAs retire
+                __syncwarp();
+            }
+            if (elect_one()) commit(&accFull[acc]);
+            __syncwarp();
+        }
+    } else {
+        // ---- epilogue warps: drain accumulator set (it & 1) while the MMA warp fills the other one
+        float* stage = reinterpret_cast<float*>(sStage) + (warp & 3) * 1024;
+        int it = 0, last_n0c = -1;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            int n0, h0, w0, n0c, rows_valid, cols_valid, imgs_valid, m_tiles, nch;
+            decode(item, n0, h0, w0, n0c, rows_valid, cols_valid, imgs_valid, m_tiles, nch);
+            const int acc = it & 1;
+            if (n0c != last_n0c) {                               // bias of this output-channel block (4 epilogue warps = 128 threads)
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int tI = threadIdx.x - 64;
+                if (tI < BN) sBias[tI] = p.bias ? p.bias[n0c + tI] : 0.f;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                last_n0c = n0c;
+            }
+            mbar_wait(&accFull[acc], ((uint32_t)(it >> 1)) & 1u);
+            fence_after();
+            const uint32_t tacc = tmem_base + (uint32_t)(acc * pp.acc_cols);
+            switch (p.act) {
+                case G2_ACT_RELU: epilogue<BN, G2_ACT_RELU>(p, tacc, sBias, stage, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid); break;
+                case G2_ACT_ELU: epilogue<BN, G2_ACT_ELU>(p, tacc, sBias, stage, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid); break;
+                case G2_ACT_SIGMOID: epilogue<BN, G2_ACT_SIGMOID>(p, tacc, sBias, stage, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid); break;
+                default: epilogue<BN, G2_ACT_NONE>(p, tacc, sBias, stage, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid); break;
+            }
+            fence_before();                                      // our tcgen05.ld's are complete (wait::ld inside) before we hand the set back
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&accEmpty[acc]);
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
 // ------------------------------------------------------------------------------------------ host side
 static PFN_cuTensorMapEncodeTiled get_encode() {
     static PFN_cuTensorMapEncodeTiled fn = nullptr;
@@ -356,7 +557,8 @@ static inline int m_of(int imgs, int RH, int rows, int Wp, int cols) { return ((
 // Choose the CTA tile for one (class of a) convolution: TH x TW output pixels of one image (or TNB whole small
 // images), window pitch Wp (exact, or rounded up to 8 pixels so that any row count keeps chunks 1024-byte aligned).
 // The cost model is the per-SM time of all CTAs of an image: max(MMA clocks, L2->SMEM clocks) + a fixed per-CTA cost.
-static bool pick_geo(int N, int Hv, int Wv, int span_h, int span_w, int ntaps, int cblocks, int BN, int stages, Geo* best) {
+static bool pick_geo(int N, int Hv, int Wv, int span_h, int span_w, int ntaps, int cblocks, int BN, int stages, Geo* best,
+                     int a_budget = -1, int col_limit = -1) {
     const int fixed = stages * BN * 128 + 1024 + 1024;
     const double clk_mma = 4.0 * (BN == 32 ? 40 : BN == 64 ? 48 : 64) * ntaps * cblocks;   // per M tile (SMEM-read bound for small N)
     const double l2_rate = 28.0;           // bytes / clock / SM sustained by TMA tile loads (measured 21-33)
@@ -381,7 +583,7 @@ static bool pick_geo(int N, int Hv, int Wv, int span_h, int span_w, int ntaps, i
                 Geo g;
                 g.TH = TH; g.TW = TW; g.TNB = TNB; g.RH = TH + span_h; g.Wp = Wp; g.tiles_w = tiles_w;
                 g.m = m_of(TNB, g.RH, TH, Wp, TW);
-                if (g.m * BN > max_cols()) return;
+                if (g.m * BN > (col_limit > 0 ? col_limit : max_cols())) return;
                 int loaded_pix;
                 if (TNB > 1) {
                     if (g.RH > 256) return;
@@ -404,7 +606,7 @@ static bool pick_geo(int N, int Hv, int Wv, int span_h, int span_w, int ntaps, i
                 if (128 * g.m + off_max > alloc_pix) alloc_pix = 128 * g.m + off_max;
                 g.a_bytes = ((alloc_pix * 128 + 1023) / 1024) * 1024;
                 if (g.a_bytes < 128 * 144) g.a_bytes = 128 * 144;      // epilogue staging: 128 rows x 144 B
-                if (g.a_bytes + fixed > budget_bytes()) return;
+                if (a_budget > 0 ? g.a_bytes > a_budget : g.a_bytes + fixed > budget_bytes()) return;
                 double tiles, ctas, bytes;
                 if (TNB > 1) {
                     g.tiles_h = 1;
@@ -445,6 +647,23 @@ static int launch(const Maps& maps, const P& p, dim3 grid, cudaStream_t stream) 
         attr_set = 227 * 1024;
     }
     conv_halo_kernel<BN><<<grid, 192, smem, stream>>>(maps, p);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? G2_OK : (int)e;
+}
+
+static int persistent_mode() { static int v = env_int("G2_HALO_PERSISTENT", 0); return v; }
+
+template <int BN>
+static int launch_persistent(const Maps& maps, const PP& pp, int n_ctas, cudaStream_t stream) {
+    const int smem = 2 * pp.p.a_bytes + pp.p.stages * BN * 128 + PSTAGE_BYTES + 2048 + 512 + 1024;
+    if (smem > 227 * 1024) return G2_ERR_UNSUPPORTED;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_halo_persistent_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    conv_halo_persistent_kernel<BN><<<n_ctas, 192, smem, stream>>>(maps, pp);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? G2_OK : (int)e;
 }
@@ -575,7 +794,16 @@ int g2_conv_halo_tf32(const float* in, const float* w, const float* bias, float*
         int dh_min, dw_min, sh, sw;
         spans(t, &dh_min, &dw_min, &sh, &sw);
         Geo g;
-        if (!pick_geo(N, t.Hv, t.Wv, sh, sw, t.n, Ci / 32, BN, stages_of(BN, t.n, Ci / 32), &g)) return G2_ERR_UNSUPPORTED;
+        // experimental persistent variant: weights resident when all (cb, tap) tiles fit beside two windows, else a deeper ring
+        const int b_all = t.n * (Ci / 32);
+        const bool resident = persistent_mode() && Co == BN && b_all <= MAX_PSTAGES && b_all * BN * 128 <= 72 * 1024;
+        const int pstages = resident ? b_all : (BN == 32 ? 8 : BN == 64 ? 4 : 2);
+        bool use_p = false;
+        if (persistent_mode()) {
+            const int a_budget = (227 * 1024 - 1024 - pstages * BN * 128 - PSTAGE_BYTES - 2048 - 512) / 2;
+            use_p = a_budget >= 128 * 144 && pick_geo(N, t.Hv, t.Wv, sh, sw, t.n, Ci / 32, BN, pstages, &g, a_budget, 256);
+        }
+        if (!use_p && !pick_geo(N, t.Hv, t.Wv, sh, sw, t.n, Ci / 32, BN, stages_of(BN, t.n, Ci / 32), &g)) return G2_ERR_UNSUPPORTED;
         P p;
         memset(&p, 0, sizeof(p));
         p.out = out; p.bias = bias; p.N = N; p.Hv = t.Hv; p.Wv = t.Wv; p.TH = g.TH; p.TW = g.TW; p.TNB = g.TNB;
@@ -598,6 +826,26 @@ int g2_conv_halo_tf32(const float* in, const float* w, const float* bias, float*
         }
         dim3 grid((unsigned)(((N + g.TNB - 1) / g.TNB) * g.tiles_h * g.tiles_w), (unsigned)(Co / BN), 1);
         int rc;
+        if (use_p) {
+            PP pp;
+            pp.p = p;
+            pp.p.stages = pstages;
+            pp.items_x = (int)grid.x; pp.items_y = (int)grid.y;
+            pp.acc_cols = g.m * BN;
+            pp.b_resident = resident ? 1 : 0;
+            int pc = 32;
+            while (pc < 2 * pp.acc_cols) pc <<= 1;
+            pp.p.tmem_cols = pc;
+            const long items = (long)grid.x * grid.y;
+            const int n_ctas = (int)(items < 148 ? items : 148);
+            switch (BN) {
+                case 32: rc = launch_persistent<32>(maps, pp, n_ctas, stream); break;
+                case 64: rc = launch_persistent<64>(maps, pp, n_ctas, stream); break;
+                default: rc = launch_persistent<128>(maps, pp, n_ctas, stream); break;
+            }
+            if (rc != G2_OK) return rc;
+            continue;
+        }
         switch (BN) {
             case 32: rc = launch<32>(maps, p, grid, stream); break;
             case 64: rc = launch<64>(maps, p, grid, stream); break;

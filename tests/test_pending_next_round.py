@@ -114,3 +114,15 @@ def test_fused_latent_model_equals_unfused(model, K, B, gen):
     for n, g in res[0][1].items():
         d = (res[1][1][n] - g).norm().item()
         assert d <= 2e-2 * g.norm().item() + 1e-3 * gmax, (n, d, g.norm().item())       # run-to-run TF32 noise is ~1e-3
+
+
+def test_persistent_halo_kernel_passes_the_halo_suite():
+    """The experimental persistent variant of the halo kernel (G2_HALO_PERSISTENT=1, read once per process) must pass the
+    same exactness tests as the default kernel; run them in a child process with the switch on."""
+    import subprocess
+    import sys
+    env = dict(os.environ, G2_HALO_PERSISTENT='1')
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(here, 'test_halo_gpu.py'), os.path.join(here, 'test_tc_gpu.py'),
+                        '-x', '-q', '-m', 'gpu'], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
