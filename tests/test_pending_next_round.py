@@ -126,3 +126,26 @@ def test_persistent_halo_kernel_passes_the_halo_suite():
     r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(here, 'test_halo_gpu.py'), os.path.join(here, 'test_tc_gpu.py'),
                         '-x', '-q', '-m', 'gpu'], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_mn_major_operand_with_row_shift_and_overlapping_atoms():
+    """Feasibility probe for the halo layout of the weight-gradient kernel: an MN-major TF32 A operand (pixels are the K
+    dimension, SWIZZLE_128B_BASE32B) that (1) starts at an arbitrary pixel row of a resident window and (2) takes its four
+    32-channel M atoms from the SAME window shifted by one pixel each (LBO = 128 B: four filter taps of one row as one
+    M = 128 operand).  If the swizzle is a function of the absolute shared-memory address, as it is for K-major operands
+    (tests/test_umma_layouts_gpu.py), both hold."""
+    import numpy as np
+    from test_umma_layouts_gpu import N, desc, idesc, image, probe
+    rng = np.random.RandomState(2)
+    npix = 16                                              # K = 16 pixels = 2 MMAs of 8
+    win = rng.randint(-3, 4, (npix + 16, 32)).astype(np.float32)          # one 32-channel window, more rows than one operand
+    Bb = rng.randint(-3, 4, (N // 32, npix, 32)).astype(np.float32)
+    b1 = np.concatenate([image(Bb[j], 8, 3) for j in range(N // 32)])
+    refB = Bb.transpose(0, 2, 1).reshape(N, npix)                         # [n][pix]
+    tileB = npix * 128
+    a_img = image(win, 8, 3)                                              # rows swizzled by their ABSOLUTE index & 3
+    for shift in (0, 1, 2, 5):
+        # four atoms = the window shifted by 0, 1, 2, 3 pixels: D[j*32 + c][n] = sum_pix win[shift + j + pix][c] * B[n][pix]
+        ref = np.concatenate([win[shift + j:shift + j + npix].T for j in range(4)], 0) @ refB.T
+        got = probe(a_img, b1, desc(128, 512, 1), desc(tileB, 512, 1), idesc(N, 1, 1), npix // 8, 1024, 1024, a_off=shift * 128)
+        np.testing.assert_allclose(got, ref, atol=1e-3, err_msg='shift %d' % shift)
