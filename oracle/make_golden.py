@@ -131,7 +131,46 @@ def run_sample_case(name, fwd_case, sb):
     print(name, 'image mean', float(image.mean()), '->', path, os.path.getsize(path) // 1024, 'KiB')
 
 
+EVAL_CASES = [('eval_genesis_k5', 'genesis_k5_b2'), ('eval_genesisv2_k7', 'genesisv2_k7_b2'), ('eval_monet_k7', 'monet_k7_b2')]
+
+
+def run_eval_case(name, fwd_case):
+    """model.eval() forward as in the reference's evaluation loop (train.py:479-546): one training-mode forward first (BatchNorm
+    running statistics), then eval() + no_grad forward on a second batch with a recorded noise tape (seed 9)."""
+    _, model, K, img, B, gen = next(c for c in CASES if c[0] == fwd_case)
+    cfg = M.make_cfg(model, K_steps=K, img_size=img)
+    ref = ref_loader.load_reference(model, cfg, seed=0)
+    ref.train()
+    x = torch.from_numpy(synth.GENERATORS[gen](B, img, 1)[0])
+    with ref_loader.replay_noise(O.NoiseTape(seed=2)):
+        ref(x)
+    ref.eval()
+    x2 = torch.from_numpy(synth.GENERATORS[gen](B, img, 3)[0])
+    tape = O.NoiseTape(seed=9)
+    with torch.no_grad(), ref_loader.replay_noise(tape):
+        recon, losses, stats, att, comp = ref(x2)
+    g = {'meta': np.array([model, str(K), str(img), str(B), fwd_case, gen]), 'x': x2.numpy()}
+    g['noise_kinds'] = np.array([k for k, _ in tape.record])
+    for i, (_, t) in enumerate(tape.record):
+        g['noise_%d' % i] = t.numpy()
+    g['recon'] = recon.numpy()
+    g['err'] = losses['err'].numpy()
+    for key in ('kl_l_k', 'kl_m_k'):
+        if key in losses and len(losses[key]):
+            g[key] = torch.stack(list(losses[key]), 0).numpy()
+    if 'kl_m' in losses and torch.is_tensor(losses['kl_m']):
+        g['kl_m'] = losses['kl_m'].numpy()
+    g['log_m_k'] = torch.stack(list(stats['log_m_k']), 0).numpy()
+    path = os.path.join(OUT_DIR, name + '.npz')
+    np.savez_compressed(path, **g)
+    print(name, 'err', g['err'], '->', path, os.path.getsize(path) // 1024, 'KiB')
+
+
 if __name__ == '__main__':
+    if '--evals' in sys.argv:
+        for case in EVAL_CASES:
+            run_eval_case(*case)
+        sys.exit(0)
     if not ref_loader.available():
         sys.exit('reference checkout not found at %s' % ref_loader.REF_ROOT)
     only_samples = '--samples' in sys.argv

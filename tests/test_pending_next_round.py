@@ -149,3 +149,27 @@ def test_mn_major_operand_with_row_shift_and_overlapping_atoms():
         ref = np.concatenate([win[shift + j:shift + j + npix].T for j in range(4)], 0) @ refB.T
         got = probe(a_img, b1, desc(128, 512, 1), desc(tileB, 512, 1), idesc(N, 1, 1), npix // 8, 1024, 1024, a_off=shift * 128)
         np.testing.assert_allclose(got, ref, atol=1e-3, err_msg='shift %d' % shift)
+
+
+@pytest.mark.parametrize('name', ['eval_genesis_k5', 'eval_genesisv2_k7', 'eval_monet_k7'])
+def test_engine_eval_forward_matches_reference(name):
+    """Engine model.eval() forward vs the reference's (tests/golden/eval_*.npz; oracle side: tests/test_eval_golden.py)."""
+    import numpy as np
+    from oracle import functional as O, synth
+    from test_oracle_golden import build_engine_model, tape_from_golden
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', name + '.npz'), allow_pickle=False)
+    model, K, img, B, fwd, gen = (str(v) for v in g['meta'])
+    K, img, B = int(K), int(img), int(B)
+    m, cfg = build_engine_model(model, K, img)
+    m = m.cuda().train()
+    m.set_noise_tape(O.NoiseTape(seed=2))
+    with torch.no_grad():
+        m(torch.from_numpy(synth.GENERATORS[gen](B, img, 1)[0]).cuda())
+    m.eval()
+    m.set_noise_tape(tape_from_golden(g))
+    with torch.no_grad():
+        recon, losses, stats, att, comp = m(torch.from_numpy(g['x']).cuda())
+    m.set_noise_tape(None)
+    np.testing.assert_allclose(losses['err'].cpu().numpy(), g['err'], rtol=1e-4)
+    np.testing.assert_allclose(recon.cpu().numpy(), g['recon'], atol=3e-3)
+    np.testing.assert_allclose(torch.stack(list(stats['log_m_k']), 0).cpu().numpy(), g['log_m_k'], atol=1e-2, rtol=1e-2)
