@@ -231,8 +231,9 @@ def sylvester_encode(core, x_nhwc, training):
     return gate_norm(last, y.view(B, 1, 1, -1), training).view(B, -1)
 
 
-def sylvester_decode(core, z, training):
-    """core.decode(z) (reference VAE.py:143-153) -> mask logits, NCHW [N, nout, H, W]."""
+def sylvester_decode(core, z, training, nsig=0):
+    """core.decode(z) (reference VAE.py:143-153) -> NCHW [N, nout, H, W] (mask logits for GENESIS; the BaselineVAE applies the
+    pixel-bound sigmoid to its `nsig` image channels in the same kernel)."""
     N = z.shape[0]
     first = core.p_x_nn[0]
     w = first.conv.weight                                  # [z, 2C, k, k]
@@ -243,7 +244,7 @@ def sylvester_decode(core, z, training):
     h = gate_norm(first, y, training)
     for i in range(1, len(core.p_x_nn)):
         h = gated_forward(core.p_x_nn[i], h, training)
-    return ops.out1x1(h, core.p_x_mean.weight, core.p_x_mean.bias, 0)
+    return ops.out1x1(h, core.p_x_mean.weight, core.p_x_mean.bias, nsig)
 
 
 def lstm_step(x, state, lstm):

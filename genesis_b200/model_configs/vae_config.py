@@ -1,0 +1,92 @@
+"""BaselineVAE plug-in (config c1): drop-in for the reference's models/vae_config.py.
+
+Same Forge contract (flags of vae_config.py:26-31, `load(cfg)`, forward -> (recon, losses{err, kl_l}, stats{x, mu, sigma, z},
+None, None), sample(), get_features()) and the same state_dict names (`vae.q_z_nn.*`, `vae.q_z_mean`, `vae.q_z_var.0`,
+`vae.p_x_nn.*`, `vae.p_x_mean`), on the engine's kernels: the gated conv encoder / conv-transpose decoder are the ones
+GENESIS uses for its attention core (holders.sylvester_encode / sylvester_decode), the Gaussian pixel likelihood is the
+mixture kernel with one slot and a zero log-mask.  The default `broadcast_decoder=False` variant only.
+NOTE: written after the round-1 GPU budget was spent -- exercised on a B200 by tests/test_pending_next_round.py first."""
+import os
+import sys
+
+import torch
+import torch.nn as nn
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+import genesis_b200  # noqa: E402
+
+try:
+    from forge import flags
+except ImportError:
+    genesis_b200.enable_compat()
+    from forge import flags
+try:
+    from attrdict import AttrDict
+except ImportError:
+    genesis_b200.enable_compat()
+    from attrdict import AttrDict
+
+from genesis_b200 import holders as H  # noqa: E402
+from genesis_b200 import ops  # noqa: E402
+from genesis_b200.model_configs.genesis_config import NoiseMixin  # noqa: E402
+
+# Flag names / defaults: reference models/vae_config.py:26-31
+flags.DEFINE_integer('latent_dimension', 64, 'Latent channels.')
+flags.DEFINE_boolean('broadcast_decoder', False, 'Use broadcast decoder instead of deconv.')
+flags.DEFINE_boolean('pixel_bound', True, 'Bound pixel values to [0, 1].')
+flags.DEFINE_float('pixel_std', 0.7, 'StdDev of reconstructed pixels.')
+
+
+def load(cfg):
+    return BaselineVAE(cfg)
+
+
+class BaselineVAE(nn.Module, NoiseMixin):
+
+    def __init__(self, cfg):
+        super().__init__()
+        cfg.K_steps = None                                   # reference vae_config.py:44
+        self.ldim = cfg.latent_dimension
+        self.pixel_std = cfg.pixel_std
+        self.pixel_bound = cfg.pixel_bound
+        self.debug = cfg.debug
+        self.img_size = cfg.img_size
+        if getattr(cfg, 'broadcast_decoder', False):
+            raise NotImplementedError('engine covers the default deconvolutional BaselineVAE (SURVEY.md section 8f.4)')
+        nin = cfg.input_channels if hasattr(cfg, 'input_channels') else 3
+        self.vae = H.SylvesterVAE(self.ldim, [nin, cfg.img_size, cfg.img_size], nin)
+        self.register_buffer('_std', torch.full((1,), float(cfg.pixel_std)), persistent=False)
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError('genesis_b200 runs on CUDA (sm_100a) only; there is no CPU path')
+        x = x.contiguous().float()
+        B = x.shape[0]
+        core = self.vae
+        tc = ops.get_precision() == 'tf32'
+        xh = ops.to_nhwc_padded(x, 32) if tc else ops.to_nhwc(x)
+        h = H.sylvester_encode(core, xh, self.training)                                   # [B,256]
+        wmv = torch.cat([core.q_z_mean.weight, core.q_z_var[0].weight], 0)
+        bmv = torch.cat([core.q_z_mean.bias, core.q_z_var[0].bias], 0)
+        z, mu, sigma = H.gauss_head(ops.linear(h, wmv, bmv), self._normal((B, self.ldim), x))
+        recon = H.sylvester_decode(core, z, self.training, 3 if self.pixel_bound else 0)   # NCHW [B,nin,H,W]
+        # -log N(x; recon, std) summed over pixels = the mixture likelihood with one slot and log m = 0
+        log_m = torch.zeros(1, B, 1, self.img_size, self.img_size, device=x.device)
+        err, _, _ = ops.mixture_nll(x, recon.unsqueeze(0), log_m, self._std, False)
+        kl = H.mc_kl(z, mu, sigma)
+        losses = AttrDict(err=err, kl_l=kl)
+        stats = AttrDict(x=recon, mu=mu, sigma=sigma, z=z)
+        return recon, losses, stats, None, None
+
+    def sample(self, batch_size, *args, **kwargs):
+        with torch.no_grad():
+            z = self._normal((batch_size, self.ldim), self._std)
+            x = H.sylvester_decode(self.vae, z, self.training, 3 if self.pixel_bound else 0)
+        return x, AttrDict(z=z)
+
+    def get_features(self, image_batch):
+        with torch.no_grad():
+            _, _, stats, _, _ = self.forward(image_batch)
+        return stats.z

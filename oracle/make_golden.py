@@ -131,6 +131,38 @@ def run_sample_case(name, fwd_case, sb):
     print(name, 'image mean', float(image.mean()), '->', path, os.path.getsize(path) // 1024, 'KiB')
 
 
+def run_vae_case(name='vae_b4', B=4, img=64, gen='multid'):
+    """BaselineVAE (config c1, models/vae_config.py): forward + backward of err.mean + kl_l.mean (train.py:227-239)."""
+    cfg = M.make_cfg('vae', K_steps=1, img_size=img)
+    ref = ref_loader.load_reference('vae', cfg, seed=0)
+    ref.train()
+    names, sums = param_checksums(ref.state_dict())
+    x = torch.from_numpy(synth.GENERATORS[gen](B, img, 1)[0])
+    tape = O.NoiseTape(seed=2)
+    with ref_loader.replay_noise(tape):
+        recon, losses, stats, _, _ = ref(x)
+    (losses['err'].mean(0) + losses['kl_l'].mean(0)).backward()
+    pnames = [k for k, _ in ref.named_parameters()]
+    gsum = np.zeros((len(pnames), 2))
+    for i, (k, p) in enumerate(ref.named_parameters()):
+        if p.grad is not None:
+            gd = p.grad.double().flatten()
+            gsum[i] = [gd.norm().item(), (gd * direction(gd.numel(), i)).sum().item()]
+    g = {'x': x.numpy(), 'meta': np.array(['vae', '1', str(img), str(B), gen])}
+    g['noise_kinds'] = np.array([k for k, _ in tape.record])
+    for i, (_, t) in enumerate(tape.record):
+        g['noise_%d' % i] = t.numpy()
+    g['param_names'], g['param_sums'] = np.array(names), sums
+    g['grad_names'], g['grad_sums'] = np.array(pnames), gsum
+    g['recon'] = recon.detach().numpy()
+    g['err'] = losses['err'].detach().numpy()
+    g['kl_l'] = losses['kl_l'].detach().numpy()
+    g['z'] = stats['z'].detach().numpy()
+    path = os.path.join(OUT_DIR, name + '.npz')
+    np.savez_compressed(path, **g)
+    print(name, 'err', g['err'], '->', path, os.path.getsize(path) // 1024, 'KiB')
+
+
 EVAL_CASES = [('eval_genesis_k5', 'genesis_k5_b2'), ('eval_genesisv2_k7', 'genesisv2_k7_b2'), ('eval_monet_k7', 'monet_k7_b2')]
 
 
@@ -167,6 +199,9 @@ def run_eval_case(name, fwd_case):
 
 
 if __name__ == '__main__':
+    if '--vae' in sys.argv:
+        run_vae_case()
+        sys.exit(0)
     if '--evals' in sys.argv:
         for case in EVAL_CASES:
             run_eval_case(*case)

@@ -37,7 +37,7 @@ MONET_DEFAULTS = dict(GENESIS_DEFAULTS, filter_start=32, prior_mode='softmax')  
 
 
 def make_cfg(model, **over):
-    base = {'genesis': GENESIS_DEFAULTS, 'genesisv2': GENESISV2_DEFAULTS, 'monet': MONET_DEFAULTS}[model]
+    base = {'genesis': GENESIS_DEFAULTS, 'genesisv2': GENESISV2_DEFAULTS, 'monet': MONET_DEFAULTS, 'vae': VAE_DEFAULTS}[model]
     cfg = Cfg(base, debug=False, multi_gpu=False, img_size=64, K_steps=5)
     cfg.update(over)
     return cfg
@@ -270,6 +270,28 @@ def genesisv2_forward(P, x, tape, cfg, training=True):
                 bn_updates={})
 
 
+# ============================================================================ BaselineVAE (config c1)
+VAE_DEFAULTS = dict(latent_dimension=64, broadcast_decoder=False, pixel_bound=True, pixel_std=0.7)  # models/vae_config.py:26-31
+
+
+def vae_forward(P, x, tape, cfg, training=True):
+    """BaselineVAE.forward (models/vae_config.py:63-89) over third_party/sylvester/VAE.forward (VAE.py:155-168): gated conv
+    encoder without norms -> (mu, sqrt(to_var)) -> rsample -> gated conv-transpose decoder -> sigmoid; err = -sum log N(x;
+    recon, pixel_std); kl = sum_d log q(z) - log N(z; 0, 1)."""
+    img, dt = cfg.img_size, x.dtype
+    upd = {}
+    h = O.sylvester_q_z_nn(x, P, 'vae.q_z_nn', img, None, training, upd).flatten(1)
+    mu = O.linear(h, P, 'vae.q_z_mean')
+    sigma = O.to_var(O.linear(h, P, 'vae.q_z_var.0')).sqrt()
+    z = mu + sigma * tape.normal(mu.shape, dt)
+    recon = O.sylvester_decode(z, P, 'vae', img, None, training, upd)
+    if cfg.pixel_bound:
+        recon = torch.sigmoid(recon)
+    err = -O.normal_log_prob(x, recon, torch.tensor(cfg.pixel_std, dtype=dt)).sum(dim=(1, 2, 3))
+    kl = O.mc_kl(z, mu, sigma)
+    return dict(recon=recon, err=err, kl_l=kl, mu=mu, sigma=sigma, z=z, bn_updates=upd)
+
+
 # ============================================================================ sample() (ancestral sampling)
 def genesis_sample(P, batch_size, tape, cfg, training=False):
     """Genesis.sample (models/genesis_config.py:345-425) with LatentSBP.masks_from_zm_k (modules/attention.py:53-74):
@@ -347,7 +369,7 @@ def monet_sample(P, batch_size, tape, cfg, training=False):
 
 
 SAMPLE = {'genesis': genesis_sample, 'genesisv2': genesisv2_sample, 'monet': monet_sample}
-FORWARD = {'genesis': genesis_forward, 'genesisv2': genesisv2_forward, 'monet': monet_forward}
+FORWARD = {'genesis': genesis_forward, 'genesisv2': genesisv2_forward, 'monet': monet_forward, 'vae': vae_forward}
 
 
 def total_loss(out, beta=1.0):
@@ -360,4 +382,6 @@ def total_loss(out, beta=1.0):
             kl = kl + torch.stack(out[key], dim=1).mean(0).sum()
     if 'kl_m' in out:
         kl = kl + out['kl_m'].mean(0)
+    if 'kl_l' in out:                       # BaselineVAE (train.py:228-229)
+        kl = kl + out['kl_l'].mean(0)
     return loss + beta * kl

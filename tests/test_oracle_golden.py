@@ -11,7 +11,7 @@ from oracle import functional as O
 from oracle import models as M
 
 GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', '*.npz'))
-              if not os.path.basename(p).startswith(('sample_', 'eval_')))   # sample_* / eval_*: tests/test_sample_golden.py, test_eval_golden.py
+              if not os.path.basename(p).startswith(('sample_', 'eval_', 'vae_')))   # sample_* / eval_*: tests/test_sample_golden.py, test_eval_golden.py
 
 
 def load_plugin(model):

@@ -173,3 +173,26 @@ def test_engine_eval_forward_matches_reference(name):
     np.testing.assert_allclose(losses['err'].cpu().numpy(), g['err'], rtol=1e-4)
     np.testing.assert_allclose(recon.cpu().numpy(), g['recon'], atol=3e-3)
     np.testing.assert_allclose(torch.stack(list(stats['log_m_k']), 0).cpu().numpy(), g['log_m_k'], atol=1e-2, rtol=1e-2)
+
+
+def test_vae_engine_matches_reference_golden():
+    """BaselineVAE plug-in (genesis_b200/model_configs/vae_config.py) forward + backward vs tests/golden/vae_b4.npz."""
+    import numpy as np
+    from test_oracle_golden import build_engine_model, direction, tape_from_golden
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'vae_b4.npz'))
+    m, cfg = build_engine_model('vae', 1, 64)
+    m = m.cuda().train()
+    m.set_noise_tape(tape_from_golden(g))
+    recon, losses, stats, _, _ = m(torch.from_numpy(g['x']).cuda())
+    (losses['err'].mean(0) + losses['kl_l'].mean(0)).backward()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(losses['err'].detach().cpu().numpy(), g['err'], rtol=1e-4)
+    np.testing.assert_allclose(losses['kl_l'].detach().cpu().numpy(), g['kl_l'], rtol=1e-3, atol=5e-3)
+    np.testing.assert_allclose(recon.detach().cpu().numpy(), g['recon'], atol=2e-3)
+    gmax = max(float(s[0]) for s in g['grad_sums'])
+    params = dict(m.named_parameters())
+    for i, (n, (nrm, proj)) in enumerate(zip(g['grad_names'], g['grad_sums'])):
+        gd = params[str(n)].grad.detach().double().cpu().flatten()
+        tol = 1e-2 * nrm + 1e-4 * gmax
+        assert abs(gd.norm().item() - nrm) <= tol, (n, gd.norm().item(), nrm)
+        assert abs((gd * direction(gd.numel(), i)).sum().item() - proj) <= 4 * tol, (n, proj)
