@@ -49,8 +49,8 @@ def ref_total_loss(losses):
     return tot
 
 
-def run_case(name, model, K, img, B, gen):
-    cfg = M.make_cfg(model, K_steps=K, img_size=img)
+def run_case(name, model, K, img, B, gen, **over):
+    cfg = M.make_cfg(model, K_steps=K, img_size=img, **over)
     ref = ref_loader.load_reference(model, cfg, seed=0)
     ref.train()
     names, sums = param_checksums(ref.state_dict())
@@ -91,6 +91,8 @@ def run_case(name, model, K, img, B, gen):
         g['bn_names'] = np.array(bn)
         g['bn_sums'] = np.array([[sd[k].double().sum().item(), sd[k].double().abs().sum().item()] for k in bn])
     g['meta'] = np.array([model, str(K), str(img), str(B), gen])
+    if over:
+        g['overrides'] = np.array(['%s=%s' % kv for kv in sorted(over.items())])
     os.makedirs(OUT_DIR, exist_ok=True)
     path = os.path.join(OUT_DIR, name + '.npz')
     np.savez_compressed(path, **g)
@@ -199,6 +201,9 @@ def run_eval_case(name, fwd_case):
 
 
 if __name__ == '__main__':
+    if '--variants' in sys.argv:     # non-default model variants
+        run_case('variant_genesis_k3_in', 'genesis', 3, 64, 3, 'multid', enc_norm='in', dec_norm='in')
+        sys.exit(0)
     if '--vae' in sys.argv:
         run_vae_case()
         sys.exit(0)

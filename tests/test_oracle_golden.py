@@ -11,7 +11,7 @@ from oracle import functional as O
 from oracle import models as M
 
 GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', '*.npz'))
-              if not os.path.basename(p).startswith(('sample_', 'eval_', 'vae_')))   # sample_* / eval_*: tests/test_sample_golden.py, test_eval_golden.py
+              if not os.path.basename(p).startswith(('sample_', 'eval_', 'vae_', 'variant_')))   # sample_* / eval_*: tests/test_sample_golden.py, test_eval_golden.py
 
 
 def load_plugin(model):
@@ -25,8 +25,8 @@ def golden_case(path):
     return g, model, int(K), int(img), int(B)
 
 
-def build_engine_model(model, K, img, seed=0):
-    cfg = M.make_cfg(model, K_steps=K, img_size=img)
+def build_engine_model(model, K, img, seed=0, **over):
+    cfg = M.make_cfg(model, K_steps=K, img_size=img, **over)
     torch.manual_seed(seed)
     return load_plugin(model).load(cfg), cfg
 

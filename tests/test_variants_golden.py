@@ -1,0 +1,51 @@
+"""Non-default model variants against the REAL reference, CPU side: golden vectors from
+oracle/make_golden.py --variants; the engine's holders re-create the variant's seeded parameters and the oracle reproduces
+outputs and gradient summaries.  Variants so far: GENESIS with enc_norm = dec_norm = 'in' (genesis_config.py:39-40)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import models as M
+from test_oracle_golden import build_engine_model, direction, tape_from_golden
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+VARIANTS = sorted(glob.glob(os.path.join(HERE, 'golden', 'variant_*.npz')))
+
+
+def overrides(g):
+    out = {}
+    for kv in g['overrides']:
+        k, v = str(kv).split('=')
+        out[k] = v
+    return out
+
+
+@pytest.mark.parametrize('path', VARIANTS, ids=[os.path.basename(p)[:-4] for p in VARIANTS])
+def test_variant_oracle_matches_reference(path):
+    g = np.load(path)
+    model, K, img, B, gen = (str(v) for v in g['meta'])
+    m, cfg = build_engine_model(model, int(K), int(img), **overrides(g))
+    sd = m.state_dict()
+    assert sorted(sd.keys()) == list(g['param_names'])
+    for n, (s, a) in zip(g['param_names'], g['param_sums']):
+        assert abs(sd[str(n)].double().sum().item() - s) <= 1e-9 * max(1.0, abs(s)), n
+    P = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    out = M.FORWARD[model](P, torch.from_numpy(g['x']), tape_from_golden(g), cfg, training=True)
+    np.testing.assert_allclose(out['err'].detach().numpy(), g['err'], rtol=2e-6)
+    np.testing.assert_allclose(out['recon'].detach().numpy(), g['recon'], atol=2e-6)
+    np.testing.assert_allclose(torch.stack(out['log_m_k'], 0).detach().numpy(), g['log_m_k'], atol=2e-4, rtol=1e-5)
+    for key in ('kl_l_k', 'kl_m_k'):
+        np.testing.assert_allclose(torch.stack(out[key], 0).detach().numpy(), g[key], atol=2e-4, rtol=1e-5)
+    M.total_loss(out).backward()
+    gmax = max(float(s[0]) for s in g['grad_sums'])
+    for i, (n, (nrm, proj)) in enumerate(zip(g['grad_names'], g['grad_sums'])):
+        gr = P[str(n)].grad
+        if gr is None:
+            assert nrm == 0.0, n
+            continue
+        gd = gr.double().flatten()
+        tol = 2e-4 * nrm + 1e-6 * gmax + 1e-7
+        assert abs(gd.norm().item() - nrm) <= tol, (n, gd.norm().item(), nrm)
