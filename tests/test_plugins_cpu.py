@@ -1,0 +1,106 @@
+"""CPU: the HOST LOGIC of the plug-ins (genesis_b200/model_configs/*.py) and of holders.py -- everything between the Forge
+`load(cfg)` boundary and the kernel calls -- with the kernel layer replaced by its plain-torch contract
+(tests/cpu_ops_mock.py), against the oracle on identical parameters, inputs and noise: outputs, loss terms, BatchNorm buffer
+updates and the gradient of every parameter (autograd runs through the stand-ins).  What this pins without a GPU: slot /
+batch bookkeeping (k-major stacking), NHWC <-> NCHW edges, weight re-indexing of the full-map convs and MLPs, the first
+broadcast-decoder layer split, noise draw order, KL / prior wiring, the K-th mask fix-up, sample().  The kernels are checked
+against the same oracle on the GPU."""
+import numpy as np
+import pytest
+import torch
+
+import cpu_ops_mock
+from oracle import functional as O
+from oracle import models as M
+from oracle import synth
+from test_oracle_golden import build_engine_model
+
+
+def run_plugin(monkeypatch, model, K, B, gen, seed=3, **over):
+    from genesis_b200 import ops
+    cpu_ops_mock.install(monkeypatch, ops)
+    m, cfg = build_engine_model(model, K, 64, **over)
+    m.train()
+    sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = torch.from_numpy(synth.GENERATORS[gen](B, 64, 5)[0])
+    m.set_noise_tape(O.NoiseTape(seed=seed))
+    out = m(x.as_subclass(cpu_ops_mock.AsCuda))
+    m.set_noise_tape(None)
+    P = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in sd0.items()}
+    ref = M.FORWARD[model](P, x, O.NoiseTape(seed=seed), cfg, training=True)
+    return m, out, P, ref
+
+
+def check_grads(m, P, tol=2e-3):
+    gmax = max(p.grad.norm().item() for p in P.values() if torch.is_tensor(p) and p.grad is not None)
+    for n, p in m.named_parameters():
+        ref = P[n].grad
+        if ref is None:
+            assert p.grad is None or p.grad.abs().max().item() == 0, n
+            continue
+        assert p.grad is not None, n
+        d = (p.grad.detach() - ref).norm().item()
+        assert d <= tol * ref.norm().item() + 1e-5 * gmax, (n, d, ref.norm().item())
+
+
+def stack(ts):
+    return torch.stack([torch.as_tensor(t) for t in ts], 0).detach().numpy()
+
+
+@pytest.mark.parametrize('K,B,gen', [(3, 3, 'multid'), (2, 2, 'rooms')])
+def test_genesis_host_logic(monkeypatch, K, B, gen):
+    m, (recon, losses, stats, att, comp), P, ref = run_plugin(monkeypatch, 'genesis', K, B, gen)
+    np.testing.assert_allclose(losses['err'].detach().numpy(), ref['err'].detach().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(recon.detach().numpy(), ref['recon'].detach().numpy(), atol=1e-5)
+    np.testing.assert_allclose(stack(stats['log_m_k']), stack(ref['log_m_k']), atol=1e-4)
+    np.testing.assert_allclose(stack(losses['kl_m_k']), stack(ref['kl_m_k']), atol=1e-3, rtol=1e-4)
+    np.testing.assert_allclose(stack(losses['kl_l_k']), stack(ref['kl_l_k']), atol=1e-3, rtol=1e-4)
+    np.testing.assert_allclose(stack(comp['z_k']), stack(ref['comp']['z_k']), atol=1e-5)
+    import util_parity as U
+    U.engine_total_loss(losses).backward()
+    M.total_loss(ref).backward()
+    check_grads(m, P)
+    for n, v in ref['bn_updates'].items():                      # BatchNorm running statistics moved as in the reference
+        np.testing.assert_allclose(m.state_dict()[n].numpy(), v.numpy(), rtol=1e-4, atol=1e-6, err_msg=n)
+
+
+def test_genesis_instance_norm_variant_host_logic(monkeypatch):
+    m, (recon, losses, stats, att, comp), P, ref = run_plugin(monkeypatch, 'genesis', 3, 2, 'multid', enc_norm='in', dec_norm='in')
+    np.testing.assert_allclose(losses['err'].detach().numpy(), ref['err'].detach().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(stack(stats['log_m_k']), stack(ref['log_m_k']), atol=1e-4)
+
+
+def test_monet_host_logic(monkeypatch):
+    m, (recon, losses, stats, att, comp), P, ref = run_plugin(monkeypatch, 'monet', 3, 2, 'multid')
+    np.testing.assert_allclose(losses['err'].detach().numpy(), ref['err'].detach().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(losses['kl_m'].detach().numpy(), ref['kl_m'].detach().numpy(), rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(recon.detach().numpy(), ref['recon'].detach().numpy(), atol=1e-5)
+    np.testing.assert_allclose(stack(stats['log_m_k']), stack(ref['log_m_k']), atol=1e-4)
+    np.testing.assert_allclose(stack(losses['kl_l_k']), stack(ref['kl_l_k']), atol=1e-3, rtol=1e-4)
+    import util_parity as U
+    U.engine_total_loss(losses).backward()
+    M.total_loss(ref).backward()
+    check_grads(m, P, tol=5e-3)
+
+
+def test_genesisv2_host_logic(monkeypatch):
+    m, (recon, losses, stats, att, comp), P, ref = run_plugin(monkeypatch, 'genesisv2', 4, 2, 'stacks')
+    np.testing.assert_allclose(losses['err'].detach().numpy(), ref['err'].detach().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(recon.detach().numpy(), ref['recon'].detach().numpy(), atol=1e-5)
+    np.testing.assert_allclose(stack(stats['log_m_k']), stack(ref['log_m_k']), atol=1e-4)
+    np.testing.assert_allclose(stack(stats['log_m_r_k']), stack(ref['log_m_r_k']), atol=1e-4)
+    np.testing.assert_allclose(stack(losses['kl_l_k']), stack(ref['kl_l_k']), atol=1e-3, rtol=1e-4)
+    import util_parity as U
+    U.engine_total_loss(losses).backward()
+    M.total_loss(ref).backward()
+    check_grads(m, P, tol=5e-3)
+
+
+def test_vae_host_logic(monkeypatch):
+    m, (recon, losses, stats, _, _), P, ref = run_plugin(monkeypatch, 'vae', 1, 3, 'multid')
+    np.testing.assert_allclose(losses['err'].detach().numpy(), ref['err'].detach().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(losses['kl_l'].detach().numpy(), ref['kl_l'].detach().numpy(), rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(recon.detach().numpy(), ref['recon'].detach().numpy(), atol=1e-5)
+    (losses['err'].mean(0) + losses['kl_l'].mean(0)).backward()
+    M.total_loss(ref).backward()
+    check_grads(m, P)
