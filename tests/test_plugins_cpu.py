@@ -104,3 +104,23 @@ def test_vae_host_logic(monkeypatch):
     (losses['err'].mean(0) + losses['kl_l'].mean(0)).backward()
     M.total_loss(ref).backward()
     check_grads(m, P)
+
+
+@pytest.mark.parametrize('model,K', [('genesis', 4), ('genesisv2', 5), ('monet', 4)])
+@pytest.mark.parametrize('training', [False, True])
+def test_sample_host_logic(monkeypatch, model, K, training):
+    """sample() (row a22) through the contract stand-ins vs the oracle's restatement; training=True exercises the per-slot
+    BatchNorm decode of GENESIS (reference attention.py:61)."""
+    from genesis_b200 import ops
+    cpu_ops_mock.install(monkeypatch, ops)
+    m, cfg = build_engine_model(model, K, 64)
+    m.train(training)
+    P = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m.set_noise_tape(O.NoiseTape(seed=5))
+    img, stats = m.sample(3, K)
+    m.set_noise_tape(None)
+    with torch.no_grad():
+        ref = M.SAMPLE[model](P, 3, O.NoiseTape(seed=5), cfg, training=training)
+    np.testing.assert_allclose(img.numpy(), ref['image'].numpy(), atol=1e-5)
+    np.testing.assert_allclose(stack(stats['log_m_k']), stack(ref['log_m_k']), atol=1e-4)
+    np.testing.assert_allclose(stack(stats['x_k']), stack(ref['x_k']), atol=1e-5)
