@@ -99,15 +99,20 @@ class Genesis(nn.Module, NoiseMixin):
         self.debug = cfg.debug
         self.side_stream = True         # overlap the prior / KL branch with the decoders (see forward)
         assert cfg.montecarlo_kl == True  # noqa: E712  (reference genesis_config.py:80)
-        if cfg.comp_symmetric or not self.two_stage or self.K_steps < 2:
-            raise NotImplementedError('engine covers the default two-stage GENESIS (SURVEY.md section 8f.4)')
+        if cfg.comp_symmetric or self.K_steps < 2:
+            raise NotImplementedError('engine covers two-stage and one-stage GENESIS with K >= 2 and the MONet-style component '
+                                      'VAE (SURVEY.md section 8f.4)')
         input_channels = cfg.input_channels if hasattr(cfg, 'input_channels') else 3
         # construction order == reference (genesis_config.py:86-138) so seeded init is identical
         core = H.SylvesterVAE(self.ldim, [input_channels, cfg.img_size, cfg.img_size], 1,
                               cfg.enc_norm, cfg.dec_norm)
         self.att_steps = self.K_steps
         self.att_process = LatentSBPHolder(core)
-        self.comp_vae = H.ComponentVAEHolder(nout=input_channels, cfg=cfg)
+        if self.two_stage:
+            self.comp_vae = H.ComponentVAEHolder(nout=input_channels, cfg=cfg)
+        else:       # one stage: the mask latents are decoded into appearances directly (reference genesis_config.py:121-126)
+            self.decoder = H.BroadcastDecoderHolder(self.ldim, input_channels, cfg.comp_dec_channels, cfg.comp_dec_layers,
+                                                    cfg.img_size)
         if self.autoreg_prior:
             self.prior_lstm = nn.LSTM(self.ldim, 256)
             self.prior_linear = nn.Linear(256, 2 * self.ldim)
@@ -152,6 +157,8 @@ class Genesis(nn.Module, NoiseMixin):
         x = x.contiguous().float()
         log_m, log_s, att_stats = self._masks(x)                     # [K,B,1,H,W], [K+1,B,1,H,W]
         z_k = att_stats.z_k
+        if not self.two_stage:
+            return self._forward_one_stage(x, log_m, log_s, att_stats)
         # The prior / KL branch (LSTM prior over z_k, prior MLP, MC-KL sums: ~250 tiny latency-bound kernels on [B,64]
         # tensors) does not feed the decoders, so it runs on a side stream beside the large decoder kernels.  Autograd
         # replays each node's backward on its forward stream, so the overlap carries to the backward pass; under CUDA
@@ -220,6 +227,35 @@ class Genesis(nn.Module, NoiseMixin):
             check_log_masks(log_m_k)
         return recon, losses, stats, att_stats, comp_stats
 
+    def _forward_one_stage(self, x, log_m, log_s, att_stats):
+        """two_stage=False (reference genesis_config.py:178-185, 198-228): appearances = BroadcastDecoder(z_m,k), no component
+        VAE and no component KL; losses = {err, kl_m_k}; comp_stats is None."""
+        K, B = self.K_steps, x.shape[0]
+        z_k = att_stats.z_k
+        x_r = H.broadcast_decode(self.decoder, torch.cat(z_k, 0), 'elu', 3 if self.pixel_bound else 0)
+        x_r = x_r.view(K, B, x.shape[1], self.img_size, self.img_size)
+        err, recon, _ = ops.mixture_nll(x, x_r, log_m, self.std.reshape(-1), False)
+        if self.autoreg_prior:
+            pmu, psig = H.autoreg_prior(z_k, self.prior_lstm, self.prior_linear)
+        else:
+            pmu, psig = [], []
+        kl_m_k = [H.mc_kl(z_k[0], att_stats.mu_k[0], att_stats.sigma_k[0])]
+        for k in range(1, K):
+            if self.autoreg_prior:
+                kl_m_k.append(H.mc_kl(z_k[k], att_stats.mu_k[k], att_stats.sigma_k[k], pmu[k - 1], psig[k - 1]))
+            else:
+                kl_m_k.append(H.mc_kl(z_k[k], att_stats.mu_k[k], att_stats.sigma_k[k]))
+        losses = AttrDict(err=err, kl_m_k=kl_m_k)
+        att_stats['pmu_k'], att_stats['psigma_k'] = pmu, psig
+        log_m_k = list(log_m.unbind(0))
+        x_r_k = list(x_r.unbind(0))
+        with torch.no_grad():
+            mx = x_r * log_m.exp()
+        stats = AttrDict(recon=recon, log_m_k=log_m_k, log_s_k=list(log_s.unbind(0)), x_r_k=x_r_k, mx_r_k=list(mx.unbind(0)))
+        if self.debug or not self.training:
+            check_log_masks(log_m_k)
+        return recon, losses, stats, att_stats, None
+
     @staticmethod
     def x_loss(x, log_m_k, x_r_k, std, pixel_wise=False):
         """Genesis.x_loss (reference genesis_config.py:273-286) on the fused kernel."""
@@ -260,6 +296,13 @@ class Genesis(nn.Module, NoiseMixin):
                 logits = H.sylvester_decode(core, torch.cat(z_k, 0), self.training)
             logits = logits.view(K, batch_size, 1, self.img_size, self.img_size)
             log_m, log_s = ops.sbp_scan(logits, K)
+            if not self.two_stage:                     # reference :404-409
+                x_k = H.broadcast_decode(self.decoder, torch.cat(z_k, 0), 'elu', 3 if self.pixel_bound else 0)
+                x_k = x_k.view(K, batch_size, -1, self.img_size, self.img_size)
+                mx = x_k * log_m.exp()
+                stats = AttrDict(x_k=list(x_k.unbind(0)), log_m_k=list(log_m.unbind(0)), log_s_k=list(log_s.unbind(0)),
+                                 mx_k=list(mx.unbind(0)))
+                return mx.sum(0), stats
             if self.comp_prior:
                 pm = self.prior_mlp
                 t = ops.linear(torch.cat(z_k, 0), pm[0].weight, pm[0].bias, 'elu')
@@ -282,6 +325,8 @@ class Genesis(nn.Module, NoiseMixin):
     def get_features(self, image_batch):
         with torch.no_grad():
             _, _, _, att_stats, comp_stats = self.forward(image_batch)
+        if comp_stats is None:          # one stage: no component latents
+            return torch.cat(att_stats['z_k'][:self.K_steps - 1], dim=1)
         return torch.cat([*att_stats['z_k'][:self.K_steps - 1], *comp_stats['z_k']], dim=1)
 
 

@@ -203,6 +203,7 @@ def run_eval_case(name, fwd_case):
 if __name__ == '__main__':
     if '--variants' in sys.argv:     # non-default model variants
         run_case('variant_genesis_k3_in', 'genesis', 3, 64, 3, 'multid', enc_norm='in', dec_norm='in')
+        run_case('variant_genesis_k3_onestage', 'genesis', 3, 64, 2, 'multid', two_stage=False)
         sys.exit(0)
     if '--vae' in sys.argv:
         run_vae_case()

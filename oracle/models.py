@@ -81,8 +81,21 @@ def genesis_forward(P, x, tape, cfg, training=True):
     # genesis_config.py:169-171: drop mask K, last kept mask := its scope
     del log_m_k[-1]
     log_m_k[K - 1] = log_s_k[K - 1]
-    # --- component VAE (component_vae.py:55-81)
     act = O.act_fn('elu')
+    if not cfg.two_stage:
+        # one stage (genesis_config.py:121-126, 178-185): appearances decoded from the mask latents, no component VAE / KL
+        x_r = O.broadcast_decoder(torch.cat(z_k, 0), P, 'decoder', img, cfg.comp_dec_layers, act)
+        if cfg.pixel_bound:
+            x_r = torch.sigmoid(x_r)
+        x_r_k = list(torch.chunk(x_r, K, 0))
+        recon = sum(m.exp() * xr for m, xr in zip(log_m_k, x_r_k))
+        err = O.mixture_nll(x, log_m_k, x_r_k, _stds(P, cfg, K, dt))
+        pmu_k, psig_k = O.autoreg_prior(z_k, P) if cfg.autoreg_prior else ([None] * K, [None] * K)
+        kl_m_k = [O.mc_kl(z_k[k], mu_k[k], sigma_k[k], pmu_k[k], psig_k[k]) for k in range(K)]
+        return dict(recon=recon, err=err, kl_m_k=kl_m_k, log_m_k=log_m_k, log_s_k=log_s_k, x_r_k=x_r_k,
+                    att=dict(x_k=x_k, mu_k=mu_k, sigma_k=sigma_k, z_k=z_k, pmu_k=pmu_k[1:], psigma_k=psig_k[1:]), comp=None,
+                    bn_updates=upd)
+    # --- component VAE (component_vae.py:55-81)
     enc_in = torch.cat([torch.cat(log_m_k, 0), x.repeat(K, 1, 1, 1)], dim=1)
     enc = O.monet_comp_encoder(enc_in, P, 'comp_vae.encoder_module', act)
     cmu, cps = torch.chunk(enc, 2, dim=1)
@@ -316,6 +329,13 @@ def genesis_sample(P, batch_size, tape, cfg, training=False):
     log_m_k, log_s_k = O.stick_breaking(logits_k)
     del log_m_k[-1]
     log_m_k[K - 1] = log_s_k[K - 1]
+    if not cfg.two_stage:               # genesis_config.py:404-409
+        x = O.broadcast_decoder(torch.cat(zm_k, 0), P, 'decoder', img, cfg.comp_dec_layers, O.act_fn('elu'))
+        if cfg.pixel_bound:
+            x = torch.sigmoid(x)
+        x_k = list(torch.chunk(x, K, 0))
+        image = sum(m.exp() * xk for m, xk in zip(log_m_k, x_k))
+        return dict(image=image, x_k=x_k, log_m_k=log_m_k, log_s_k=log_s_k)
     zc_k = []
     for zm in zm_k:
         if cfg.comp_prior:

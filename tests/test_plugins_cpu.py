@@ -70,6 +70,27 @@ def test_genesis_instance_norm_variant_host_logic(monkeypatch):
     np.testing.assert_allclose(stack(stats['log_m_k']), stack(ref['log_m_k']), atol=1e-4)
 
 
+def test_genesis_one_stage_variant_host_logic(monkeypatch):
+    """two_stage=False: BroadcastDecoder on the mask latents, losses = {err, kl_m_k}, comp_stats None; also its sample()."""
+    m, (recon, losses, stats, att, comp), P, ref = run_plugin(monkeypatch, 'genesis', 3, 2, 'multid', two_stage=False)
+    assert comp is None and 'kl_l_k' not in losses
+    np.testing.assert_allclose(losses['err'].detach().numpy(), ref['err'].detach().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(recon.detach().numpy(), ref['recon'].detach().numpy(), atol=1e-5)
+    np.testing.assert_allclose(stack(losses['kl_m_k']), stack(ref['kl_m_k']), atol=1e-3, rtol=1e-4)
+    import util_parity as U
+    U.engine_total_loss(losses).backward()
+    M.total_loss(ref).backward()
+    check_grads(m, P)
+    m.eval()
+    m.set_noise_tape(O.NoiseTape(seed=6))
+    img, st = m.sample(2, 3)
+    m.set_noise_tape(None)
+    with torch.no_grad():
+        sref = M.SAMPLE['genesis']({k: v.detach() for k, v in m.state_dict().items()}, 2, O.NoiseTape(seed=6),
+                                   M.make_cfg('genesis', K_steps=3, img_size=64, two_stage=False), training=False)
+    np.testing.assert_allclose(img.numpy(), sref['image'].numpy(), atol=1e-5)
+
+
 def test_monet_host_logic(monkeypatch):
     m, (recon, losses, stats, att, comp), P, ref = run_plugin(monkeypatch, 'monet', 3, 2, 'multid')
     np.testing.assert_allclose(losses['err'].detach().numpy(), ref['err'].detach().numpy(), rtol=1e-5)
