@@ -145,3 +145,16 @@ def test_sample_host_logic(monkeypatch, model, K, training):
     np.testing.assert_allclose(img.numpy(), ref['image'].numpy(), atol=1e-5)
     np.testing.assert_allclose(stack(stats['log_m_k']), stack(ref['log_m_k']), atol=1e-4)
     np.testing.assert_allclose(stack(stats['x_k']), stack(ref['x_k']), atol=1e-5)
+
+
+@pytest.mark.parametrize('model,K,gen,over', [('genesis', 3, 'rooms', dict(comp_prior=False)),
+                                              ('genesisv2', 4, 'stacks', dict(autoreg_prior=False))])
+def test_prior_flag_variants_host_logic(monkeypatch, model, K, gen, over):
+    """comp_prior=False (standard-normal component prior) and GENESIS-V2 with autoreg_prior=False."""
+    m, (recon, losses, stats, att, comp), P, ref = run_plugin(monkeypatch, model, K, 2, gen, **over)
+    np.testing.assert_allclose(losses['err'].detach().numpy(), ref['err'].detach().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(stack(losses['kl_l_k']), stack(ref['kl_l_k']), atol=1e-3, rtol=1e-4)
+    import util_parity as U
+    U.engine_total_loss(losses).backward()
+    M.total_loss(ref).backward()
+    check_grads(m, P, tol=5e-3)
