@@ -117,6 +117,42 @@ class ComponentVAEHolder(nn.Module):
                                                      cfg.comp_dec_layers, cfg.img_size)
 
 
+class _GatedCore(object):
+    """Adapter that lets sylvester_encode / sylvester_decode run on free-standing gated-conv stacks (the comp_symmetric
+    component VAE): q_z_nn / p_x_nn are nn.Sequential of GatedLayer, p_x_mean a 1x1 Conv2d."""
+
+    def __init__(self, q_z_nn=None, p_x_nn=None, p_x_mean=None):
+        self.q_z_nn, self.p_x_nn, self.p_x_mean = q_z_nn, p_x_nn, p_x_mean
+
+
+def make_symmetric_component_vae(comp_vae, nin, cfg, last_kernel):
+    """Replace the MONet-style encoder / broadcast decoder of a ComponentVAEHolder by the gated conv stacks of reference
+    genesis_config.py:101-120 (comp_symmetric=True).  Called AFTER the default modules were constructed, as the reference
+    does, so the seeded initialisation consumes the generator in the same order.  state_dict names:
+    encoder_module.0.{0-5}.(conv|h_norm|g_norm), decoder_module.1.{0-5}.*, decoder_module.2.(weight|bias)."""
+    strides = [1, 2, 1, 2, 1]
+    cin, cout = [nin + 1, 32, 32, 64, 64], [32, 32, 64, 64, 64]
+    enc = [GatedLayer(i, o, 5, s, 2, norm=cfg.enc_norm) for i, o, s in zip(cin, cout, strides)]
+    enc.append(GatedLayer(cout[-1], 2 * cfg.comp_ldim, last_kernel, 1, 0))
+    comp_vae.encoder_module = nn.Sequential(nn.Sequential(*enc), nn.Identity())
+    cin, cout = [64, 64, 32, 32, 32], [64, 32, 32, 32, 32]
+    dec = [GatedLayer(cfg.comp_ldim, cin[0], last_kernel, 1, 0, transposed=True)]
+    dec += [GatedLayer(i, o, 5, s, 2, transposed=True, out_pad=s - 1, norm=cfg.dec_norm) for i, o, s in zip(cin, cout, strides)]
+    comp_vae.decoder_module = nn.Sequential(nn.Identity(), nn.Sequential(*dec), nn.Conv2d(32, nin, 1))
+    return comp_vae
+
+
+def symmetric_comp_encode(comp_vae, packed, training):
+    """packed NHWC [K*B,H,W,cp] (channel 0 = log-mask, 1..3 = image) -> [K*B, 2*ldim]."""
+    return sylvester_encode(_GatedCore(q_z_nn=comp_vae.encoder_module[0]), packed, training)
+
+
+def symmetric_comp_decode(comp_vae, z, training, nsig):
+    """z [K*B, ldim] -> NCHW [K*B, nin, H, W] with the pixel-bound sigmoid on the first nsig channels."""
+    dm = comp_vae.decoder_module
+    return sylvester_decode(_GatedCore(p_x_nn=dm[1], p_x_mean=dm[2]), z, training, nsig)
+
+
 def _conv_block(nin, nout, norm):
     """modules/blocks.py:144-165: Conv3x3 (no bias with a norm) + IN(affine) / GN(8) [+ ReLU]."""
     if norm == 'in':

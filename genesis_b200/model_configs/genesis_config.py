@@ -99,9 +99,9 @@ class Genesis(nn.Module, NoiseMixin):
         self.debug = cfg.debug
         self.side_stream = True         # overlap the prior / KL branch with the decoders (see forward)
         assert cfg.montecarlo_kl == True  # noqa: E712  (reference genesis_config.py:80)
-        if cfg.comp_symmetric or self.K_steps < 2:
-            raise NotImplementedError('engine covers two-stage and one-stage GENESIS with K >= 2 and the MONet-style component '
-                                      'VAE (SURVEY.md section 8f.4)')
+        self.comp_symmetric = bool(cfg.comp_symmetric) and self.two_stage
+        if self.K_steps < 2:
+            raise NotImplementedError('engine covers GENESIS with K >= 2 (SURVEY.md section 8f.4)')
         input_channels = cfg.input_channels if hasattr(cfg, 'input_channels') else 3
         # construction order == reference (genesis_config.py:86-138) so seeded init is identical
         core = H.SylvesterVAE(self.ldim, [input_channels, cfg.img_size, cfg.img_size], 1,
@@ -110,6 +110,8 @@ class Genesis(nn.Module, NoiseMixin):
         self.att_process = LatentSBPHolder(core)
         if self.two_stage:
             self.comp_vae = H.ComponentVAEHolder(nout=input_channels, cfg=cfg)
+            if self.comp_symmetric:     # reference genesis_config.py:101-120
+                H.make_symmetric_component_vae(self.comp_vae, input_channels, cfg, core.last_kernel_size)
         else:       # one stage: the mask latents are decoded into appearances directly (reference genesis_config.py:121-126)
             self.decoder = H.BroadcastDecoderHolder(self.ldim, input_channels, cfg.comp_dec_channels, cfg.comp_dec_layers,
                                                     cfg.img_size)
@@ -188,7 +190,11 @@ class Genesis(nn.Module, NoiseMixin):
                 cpmu, cpsig = H.prior_head(ops.linear(t, pm[4].weight, pm[4].bias))
         # --- component VAE (reference component_vae.py:45-81), K slots batched k-major
         cv = self.comp_vae
-        enc = H.comp_encode(cv.encoder_module, ops.comp_pack(x, log_m, 32 if ops.get_precision() == 'tf32' else 4), 'elu')
+        packed = ops.comp_pack(x, log_m, 32 if ops.get_precision() == 'tf32' else 4)
+        if self.comp_symmetric:
+            enc = H.symmetric_comp_encode(cv, packed, self.training)
+        else:
+            enc = H.comp_encode(cv.encoder_module, packed, 'elu')
         cz, cmu, csig = H.gauss_head(enc, self._normal((enc.shape[0], enc.shape[1] // 2), x))
         if side is not cur:
             side.wait_stream(cur)           # cz, cmu, csig are ready
@@ -197,7 +203,10 @@ class Genesis(nn.Module, NoiseMixin):
         with torch.cuda.stream(side):
             # --- KL of the component latents (reference genesis_config.py:230-259)
             kl = H.mc_kl(cz, cmu, csig, cpmu, cpsig) if self.comp_prior else H.mc_kl(cz, cmu, csig)
-        x_r = H.broadcast_decode(cv.decoder_module, cz, 'elu', 3 if self.pixel_bound else 0)
+        if self.comp_symmetric:
+            x_r = H.symmetric_comp_decode(cv, cz, self.training, 3 if self.pixel_bound else 0)
+        else:
+            x_r = H.broadcast_decode(cv.decoder_module, cz, 'elu', 3 if self.pixel_bound else 0)
         x_r = x_r.view(K, B, x.shape[1], self.img_size, self.img_size)
         # --- reconstruction + mixture likelihood (reference genesis_config.py:188-196)
         err, recon, _ = ops.mixture_nll(x, x_r, log_m, self.std.reshape(-1), False)
@@ -314,7 +323,10 @@ class Genesis(nn.Module, NoiseMixin):
                 zc = mu + sig * eps
             else:
                 zc = torch.cat([self._normal((batch_size, self.comp_vae.ldim), like) for _ in range(K)], 0)
-            x_k = H.broadcast_decode(self.comp_vae.decoder_module, zc, 'elu', 3 if self.pixel_bound else 0)
+            if self.comp_symmetric:
+                x_k = H.symmetric_comp_decode(self.comp_vae, zc, self.training, 3 if self.pixel_bound else 0)
+            else:
+                x_k = H.broadcast_decode(self.comp_vae.decoder_module, zc, 'elu', 3 if self.pixel_bound else 0)
             x_k = x_k.view(K, batch_size, -1, self.img_size, self.img_size)
             mx = x_k * log_m.exp()
             img = mx.sum(0)

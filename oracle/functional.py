@@ -186,17 +186,20 @@ def sylvester_q_z_nn(x, P, prefix, img_size, norm, training, updates):
     return gated_conv(h, P, '%s.%d' % (prefix, len(strides)), 1, 0, None, training, updates)
 
 
-def sylvester_decode(z, P, prefix, img_size, norm, training, updates):
+def sylvester_decode(z, P, prefix, img_size, norm, training, updates, nn_prefix=None, mean_prefix=None):
     """VAE.decode (VAE.py:143-153) with build_gc_decoder (VAE.py:27-33): un-normed gated
-    conv-transpose 1x1 -> kz x kz, five gated 5x5 conv-transposes (p=2, op=s-1) with norm, 1x1 conv."""
+    conv-transpose 1x1 -> kz x kz, five gated 5x5 conv-transposes (p=2, op=s-1) with norm, 1x1 conv.
+    nn_prefix / mean_prefix name the stack and the 1x1 conv when they are not `<prefix>.p_x_nn` / `<prefix>.p_x_mean`
+    (the comp_symmetric component decoder, genesis_config.py:110-120)."""
     _, strides = sylvester_strides(img_size)
     strides = list(reversed(strides))
+    nn_prefix = nn_prefix or prefix + '.p_x_nn'
+    mean_prefix = mean_prefix or prefix + '.p_x_mean'
     h = z.view(z.shape[0], -1, 1, 1)
-    h = gated_conv(h, P, prefix + '.p_x_nn.0', 1, 0, None, training, updates, transpose=True)
+    h = gated_conv(h, P, nn_prefix + '.0', 1, 0, None, training, updates, transpose=True)
     for i, s in enumerate(strides):
-        h = gated_conv(h, P, '%s.p_x_nn.%d' % (prefix, i + 1), s, 2, norm, training, updates,
-                       transpose=True)
-    return F.conv2d(h, P[prefix + '.p_x_mean.weight'], P[prefix + '.p_x_mean.bias'])
+        h = gated_conv(h, P, '%s.%d' % (nn_prefix, i + 1), s, 2, norm, training, updates, transpose=True)
+    return F.conv2d(h, P[mean_prefix + '.weight'], P[mean_prefix + '.bias'])
 
 
 def lstm_cell(x, state, P, name):

@@ -205,6 +205,7 @@ if __name__ == '__main__':
         run_case('variant_genesis_k3_in', 'genesis', 3, 64, 3, 'multid', enc_norm='in', dec_norm='in')
         run_case('variant_genesis_k3_onestage', 'genesis', 3, 64, 2, 'multid', two_stage=False)
         run_case('variant_genesis_k3_nocompprior', 'genesis', 3, 64, 2, 'rooms', comp_prior=False)     # (autoreg_prior=False crashes in the reference itself: genesis_config.py:212 uses self.prior_lstm unconditionally)
+        run_case('variant_genesis_k3_symmetric', 'genesis', 3, 64, 2, 'multid', comp_symmetric=True)
         run_case('variant_genesisv2_k4_noprior', 'genesisv2', 4, 64, 2, 'stacks', autoreg_prior=False)
         sys.exit(0)
     if '--vae' in sys.argv:

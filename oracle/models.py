@@ -97,11 +97,19 @@ def genesis_forward(P, x, tape, cfg, training=True):
                     bn_updates=upd)
     # --- component VAE (component_vae.py:55-81)
     enc_in = torch.cat([torch.cat(log_m_k, 0), x.repeat(K, 1, 1, 1)], dim=1)
-    enc = O.monet_comp_encoder(enc_in, P, 'comp_vae.encoder_module', act)
+    sym = cfg.get('comp_symmetric', False)
+    if sym:     # genesis_config.py:101-120: the component VAE uses the attention core's gated conv stacks
+        enc = O.sylvester_q_z_nn(enc_in, P, 'comp_vae.encoder_module.0', img, cfg.enc_norm, training, upd).flatten(1)
+    else:
+        enc = O.monet_comp_encoder(enc_in, P, 'comp_vae.encoder_module', act)
     cmu, cps = torch.chunk(enc, 2, dim=1)
     csig = O.to_sigma(cps)
     cz = cmu + csig * tape.normal(cmu.shape, dt)
-    x_r = O.broadcast_decoder(cz, P, 'comp_vae.decoder_module', img, cfg.comp_dec_layers, act)
+    if sym:
+        x_r = O.sylvester_decode(cz, P, None, img, cfg.dec_norm, training, upd, nn_prefix='comp_vae.decoder_module.1',
+                                 mean_prefix='comp_vae.decoder_module.2')
+    else:
+        x_r = O.broadcast_decoder(cz, P, 'comp_vae.decoder_module', img, cfg.comp_dec_layers, act)
     if cfg.pixel_bound:
         x_r = torch.sigmoid(x_r)
     x_r_k = list(torch.chunk(x_r, K, 0))
@@ -346,7 +354,11 @@ def genesis_sample(P, batch_size, tape, cfg, training=False):
             zc_k.append(mu + sigma * tape.normal(mu.shape, dt))
         else:
             zc_k.append(tape.normal((batch_size, cfg.comp_ldim), dt))
-    x = O.broadcast_decoder(torch.cat(zc_k, 0), P, 'comp_vae.decoder_module', img, cfg.comp_dec_layers, O.act_fn('elu'))
+    if cfg.get('comp_symmetric', False):
+        x = O.sylvester_decode(torch.cat(zc_k, 0), P, None, img, cfg.dec_norm, training, upd, nn_prefix='comp_vae.decoder_module.1',
+                               mean_prefix='comp_vae.decoder_module.2')
+    else:
+        x = O.broadcast_decoder(torch.cat(zc_k, 0), P, 'comp_vae.decoder_module', img, cfg.comp_dec_layers, O.act_fn('elu'))
     if cfg.pixel_bound:
         x = torch.sigmoid(x)
     x_k = list(torch.chunk(x, K, 0))

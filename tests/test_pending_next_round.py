@@ -235,3 +235,22 @@ def test_variant_genesis_one_stage_engine_matches_reference():
     for i, (n, (nrm, proj)) in enumerate(zip(g['grad_names'], g['grad_sums'])):
         gd = params[str(n)].grad.detach().double().cpu().flatten()
         assert abs(gd.norm().item() - nrm) <= 2e-2 * nrm + 1e-4 * gmax, (n, gd.norm().item(), nrm)
+
+
+def test_variant_genesis_comp_symmetric_engine_matches_reference():
+    """GENESIS with comp_symmetric=True: engine vs tests/golden/variant_genesis_k3_symmetric.npz."""
+    import numpy as np
+    import util_parity as U
+    from test_oracle_golden import build_engine_model, tape_from_golden
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'variant_genesis_k3_symmetric.npz'))
+    m, cfg = build_engine_model('genesis', 3, 64, comp_symmetric=True)
+    m = m.cuda().train()
+    recon, losses, stats, att, comp = U.run_engine(m, torch.from_numpy(g['x']), tape_from_golden(g))
+    np.testing.assert_allclose(losses['err'].detach().cpu().numpy(), g['err'], rtol=1e-4)
+    np.testing.assert_allclose(recon.detach().cpu().numpy(), g['recon'], atol=2e-3)
+    np.testing.assert_allclose(torch.stack(losses['kl_l_k'], 0).detach().cpu().numpy(), g['kl_l_k'], atol=1e-2, rtol=1e-3)
+    gmax = max(float(s[0]) for s in g['grad_sums'])
+    params = dict(m.named_parameters())
+    for i, (n, (nrm, proj)) in enumerate(zip(g['grad_names'], g['grad_sums'])):
+        gd = params[str(n)].grad.detach().double().cpu().flatten()
+        assert abs(gd.norm().item() - nrm) <= 2e-2 * nrm + 1e-4 * gmax, (n, gd.norm().item(), nrm)

@@ -158,3 +158,32 @@ def test_prior_flag_variants_host_logic(monkeypatch, model, K, gen, over):
     U.engine_total_loss(losses).backward()
     M.total_loss(ref).backward()
     check_grads(m, P, tol=5e-3)
+
+
+def test_genesis_comp_symmetric_variant_host_logic(monkeypatch):
+    """comp_symmetric=True (reference genesis_config.py:101-120): gated conv component VAE with BatchNorm over the K*B slots."""
+    m, (recon, losses, stats, att, comp), P, ref = run_plugin(monkeypatch, 'genesis', 3, 2, 'multid', comp_symmetric=True)
+    np.testing.assert_allclose(losses['err'].detach().numpy(), ref['err'].detach().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(recon.detach().numpy(), ref['recon'].detach().numpy(), atol=1e-5)
+    np.testing.assert_allclose(stack(losses['kl_l_k']), stack(ref['kl_l_k']), atol=1e-3, rtol=1e-4)
+    import util_parity as U
+    U.engine_total_loss(losses).backward()
+    M.total_loss(ref).backward()
+    check_grads(m, P)
+    for n, v in ref['bn_updates'].items():
+        np.testing.assert_allclose(m.state_dict()[n].numpy(), v.numpy(), rtol=1e-4, atol=1e-6, err_msg=n)
+
+
+def test_genesis_comp_symmetric_sample_host_logic(monkeypatch):
+    from genesis_b200 import ops
+    cpu_ops_mock.install(monkeypatch, ops)
+    m, cfg = build_engine_model('genesis', 3, 64, comp_symmetric=True)
+    m.eval()
+    P = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m.set_noise_tape(O.NoiseTape(seed=8))
+    img, stats = m.sample(2, 3)
+    m.set_noise_tape(None)
+    with torch.no_grad():
+        ref = M.SAMPLE['genesis'](P, 2, O.NoiseTape(seed=8), cfg, training=False)
+    np.testing.assert_allclose(img.numpy(), ref['image'].numpy(), atol=1e-5)
+    np.testing.assert_allclose(stack(stats['x_k']), stack(ref['x_k']), atol=1e-5)
