@@ -90,9 +90,9 @@ class GenesisV2(nn.Module, _g.NoiseMixin):
         self.debug = cfg.debug
         self.multi_gpu = cfg.multi_gpu
         self.img_size = cfg.img_size
-        if cfg.kernel != 'gaussian' or not cfg.semiconv or cfg.dynamic_K or cfg.klm_loss:
-            raise NotImplementedError('engine covers the default GENESIS-V2 (gaussian kernel, semiconv, fixed K, '
-                                      'no klm_loss); SURVEY.md section 8f.4')
+        if cfg.kernel != 'gaussian' or not cfg.semiconv or cfg.dynamic_K:
+            raise NotImplementedError('engine covers GENESIS-V2 with the gaussian kernel, semiconv and fixed K '
+                                      '(SURVEY.md section 8f.4)')
         if cfg.feat_dim != 64:
             raise NotImplementedError('engine is tiled for feat_dim=64')
         c = cfg.feat_dim
@@ -198,6 +198,8 @@ class GenesisV2(nn.Module, _g.NoiseMixin):
                 t_.record_stream(cur)
         losses = AttrDict()
         losses['err'] = err
+        if self.klm_loss:           # reference :171-176: KL(masks || reconstructed masks)
+            losses['kl_m'] = ops.mask_kl(log_m, dec, self.detach_mr_in_klm)
         losses['kl_l_k'] = kl
         # --- tracking
         log_m_k = list(log_m.unbind(0))

@@ -871,6 +871,39 @@ def monet_loss(x, dec, lm, std):
     return _MonetLoss.apply(x, dec, lm, std)
 
 
+# ----------------------------------------------------------------------------------------- stand-alone mask KL
+class _MaskKL(Function):
+    """MONet.kl_m_loss between given log-masks lm [K,B,1,H,W] and the log-softmax over K of plane 3 of dec [K,B,4,H,W]
+    (GENESIS-V2 `klm_loss`, reference genesisv2_config.py:171-176 -> monet_config.py:157-170) -> kl [B].
+    detach=True (`detach_mr_in_klm`, the default): no gradient to the decoder logits."""
+
+    @staticmethod
+    def forward(ctx, lm, dec, detach):
+        lm, dec = _c(lm), _c(dec)
+        K, B = dec.shape[0], dec.shape[1]
+        P = dec.shape[3] * dec.shape[4]
+        kl = _new(lm, B)
+        lmr = torch.empty_like(lm)
+        _call('g2_mask_kl_fwd_f32', lm, dec.data_ptr() + 12 * P, lmr, kl, K, B, P, 1, 4)
+        ctx.save_for_backward(lm, dec)
+        ctx.detach = detach
+        return kl
+
+    @staticmethod
+    def backward(ctx, gkl):
+        lm, dec = ctx.saved_tensors
+        K, B = dec.shape[0], dec.shape[1]
+        P = dec.shape[3] * dec.shape[4]
+        dlm = torch.empty_like(lm)
+        ddec = torch.zeros_like(dec)
+        _call('g2_mask_kl_bwd_f32', lm, dec.data_ptr() + 12 * P, _c(gkl), dlm, ddec.data_ptr() + 12 * P, K, B, P, 1, 4, 1, 4, 0)
+        return dlm, (None if ctx.detach else ddec), None
+
+
+def mask_kl(lm, dec, detach=True):
+    return _MaskKL.apply(lm, dec, detach)
+
+
 # ----------------------------------------------------------------------------------------- fused latent path
 # One kernel each for the LSTM cell, the Gaussian head (to_sigma + rsample), the prior head (tanh / to_prior_sigma) and the
 # Monte-Carlo KL, forward and backward (csrc/latent.cu).  Switched by set_fused_latent(); OFF by default until the kernels

@@ -206,6 +206,8 @@ if __name__ == '__main__':
         run_case('variant_genesis_k3_onestage', 'genesis', 3, 64, 2, 'multid', two_stage=False)
         run_case('variant_genesis_k3_nocompprior', 'genesis', 3, 64, 2, 'rooms', comp_prior=False)     # (autoreg_prior=False crashes in the reference itself: genesis_config.py:212 uses self.prior_lstm unconditionally)
         run_case('variant_genesis_k3_symmetric', 'genesis', 3, 64, 2, 'multid', comp_symmetric=True)
+        run_case('variant_genesisv2_k4_klm', 'genesisv2', 4, 64, 2, 'stacks', klm_loss=True)
+        run_case('variant_genesisv2_k4_klm_nodetach', 'genesisv2', 4, 64, 2, 'rooms', klm_loss=True, detach_mr_in_klm=False)
         run_case('variant_genesisv2_k4_noprior', 'genesisv2', 4, 64, 2, 'stacks', autoreg_prior=False)
         sys.exit(0)
     if '--vae' in sys.argv:

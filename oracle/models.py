@@ -284,11 +284,15 @@ def genesisv2_forward(P, x, tape, cfg, training=True):
     else:
         pmu_k, psig_k = [None] * K, [None] * K
     kl_l_k = [O.mc_kl(z_k[k], mu_k[k], sigma_k[k], pmu_k[k], psig_k[k]) for k in range(K)]
-    return dict(recon=recon, err=err, kl_l_k=kl_l_k, log_m_k=log_m_k, log_s_k=log_s_k, x_r_k=x_r_k,
-                log_m_r_k=log_m_r_k,
-                att=dict(colour=colour, delta=delta, seeds=seeds, seed_idx=idxs),
-                comp=dict(mu_k=mu_k, sigma_k=sigma_k, z_k=z_k, pmu_k=pmu_k[1:], psigma_k=psig_k[1:]),
-                bn_updates={})
+    out = dict(recon=recon, err=err, kl_l_k=kl_l_k, log_m_k=log_m_k, log_s_k=log_s_k, x_r_k=x_r_k,
+               log_m_r_k=log_m_r_k,
+               att=dict(colour=colour, delta=delta, seeds=seeds, seed_idx=idxs),
+               comp=dict(mu_k=mu_k, sigma_k=sigma_k, z_k=z_k, pmu_k=pmu_k[1:], psigma_k=psig_k[1:]),
+               bn_updates={})
+    if cfg.get('klm_loss', False):          # genesisv2_config.py:171-176: KL(masks || reconstructed masks), the latter detached by default
+        lmr = [m.detach() for m in log_m_r_k] if cfg.get('detach_mr_in_klm', True) else log_m_r_k
+        out['kl_m'] = monet_kl_m(log_m_k, lmr)
+    return out
 
 
 # ============================================================================ BaselineVAE (config c1)

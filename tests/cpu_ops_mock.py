@@ -130,6 +130,16 @@ def monet_loss(x, dec, lm, std):
     return err, kl, recon, lmr.detach()
 
 
+def mask_kl(lm, dec, detach=True):
+    K, B = lm.shape[0], lm.shape[1]
+    lmr = torch.log_softmax(dec[:, :, 3:], dim=0)
+    if detach:
+        lmr = lmr.detach()
+    q = lm.exp().clamp_min(1e-5).permute(1, 2, 3, 4, 0).reshape(-1, K)
+    p = lmr.exp().clamp_min(1e-5).permute(1, 2, 3, 4, 0).reshape(-1, K)
+    return O.categorical_kl(q, p).view(B, -1).sum(dim=1)
+
+
 def down2(x):
     return F.interpolate(x.permute(0, 3, 1, 2), scale_factor=0.5, mode='nearest').permute(0, 2, 3, 1).contiguous()
 
@@ -164,7 +174,7 @@ def install(monkeypatch, ops):
     g = globals()
     for name in ('to_nhwc', 'to_nchw', 'to_nhwc_padded', 'conv2d', 'conv_transpose2d', 'linear', 'norm_post', 'sbp_scan',
                  'comp_pack', 'bcast_add_act', 'out1x1', 'mixture_nll', 'mixture_nll_packed', 'monet_loss', 'down2', 'up2',
-                 'icsbp', 'masked_pool'):
+                 'icsbp', 'masked_pool', 'mask_kl'):
         monkeypatch.setattr(ops, name, g[name])
     monkeypatch.setattr(ops, 'get_precision', lambda: 'fp32')
     monkeypatch.setattr(ops, 'side_streams_enabled', lambda: False)

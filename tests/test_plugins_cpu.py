@@ -187,3 +187,15 @@ def test_genesis_comp_symmetric_sample_host_logic(monkeypatch):
         ref = M.SAMPLE['genesis'](P, 2, O.NoiseTape(seed=8), cfg, training=False)
     np.testing.assert_allclose(img.numpy(), ref['image'].numpy(), atol=1e-5)
     np.testing.assert_allclose(stack(stats['x_k']), stack(ref['x_k']), atol=1e-5)
+
+
+@pytest.mark.parametrize('detach', [True, False])
+def test_genesisv2_klm_loss_variant_host_logic(monkeypatch, detach):
+    """klm_loss=True (reference genesisv2_config.py:171-176), with and without detach_mr_in_klm."""
+    m, (recon, losses, stats, att, comp), P, ref = run_plugin(monkeypatch, 'genesisv2', 4, 2, 'stacks', klm_loss=True,
+                                                              detach_mr_in_klm=detach)
+    np.testing.assert_allclose(losses['kl_m'].detach().numpy(), ref['kl_m'].detach().numpy(), rtol=1e-4, atol=1e-3)
+    import util_parity as U
+    U.engine_total_loss(losses).backward()
+    M.total_loss(ref).backward()
+    check_grads(m, P, tol=5e-3)
