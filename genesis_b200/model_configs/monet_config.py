@@ -59,8 +59,8 @@ class MONet(nn.Module, _g.NoiseMixin):
         self.debug = cfg.debug
         self.pixel_bound = cfg.pixel_bound
         self.img_size = cfg.img_size
-        if self.prior_mode != 'softmax':
-            raise NotImplementedError("engine covers prior_mode='softmax' (SURVEY.md section 8f.4)")
+        if self.prior_mode not in ('softmax', 'scope'):
+            raise ValueError("No valid prior mode.")         # reference monet_config.py:155
         if not hasattr(cfg, 'filter_start'):
             cfg['filter_start'] = 32
         core = H.UNetHolder(int(math.log2(cfg.img_size) - 1), cfg.img_size, cfg.filter_start, 4, 1, norm='in')
@@ -103,7 +103,14 @@ class MONet(nn.Module, _g.NoiseMixin):
         cz, cmu, csig = H.gauss_head(enc, self._normal((enc.shape[0], enc.shape[1] // 2), x))
         dec = H.broadcast_decode(cv.decoder_module, cz, 'relu', 3 if self.pixel_bound else 0)
         dec = dec.view(K, B, 4, self.img_size, self.img_size)
-        err, kl_m, recon, log_m_r = ops.monet_loss(x, dec, log_m, self.std.reshape(-1))
+        if self.prior_mode == 'scope':
+            # reference monet_config.py:141-153: reconstructed masks by stick-breaking over the decoder's mask logits
+            err, recon, _ = ops.mixture_nll_packed(x, dec, log_m, self.std.reshape(-1), False)
+            log_m_r, _ = ops.sbp_scan(dec[:, :, 3:4].contiguous(), K)
+            kl_m = ops.mask_kl(log_m, log_m_r, False)
+            log_m_r = log_m_r.detach()
+        else:
+            err, kl_m, recon, log_m_r = ops.monet_loss(x, dec, log_m, self.std.reshape(-1))
         losses = AttrDict()
         losses['err'] = err
         losses['kl_m'] = kl_m
@@ -135,7 +142,10 @@ class MONet(nn.Module, _g.NoiseMixin):
             z = self._normal((batch_size * K, self.comp_vae.ldim), like)
             dec = H.broadcast_decode(self.comp_vae.decoder_module, z, 'relu', 3 if self.pixel_bound else 0)
             dec = dec.view(K, batch_size, 4, self.img_size, self.img_size)
-            log_m = F.log_softmax(dec[:, :, 3:], dim=0)
+            if self.prior_mode == 'scope':
+                log_m, _ = ops.sbp_scan(dec[:, :, 3:4].contiguous(), K)
+            else:
+                log_m = F.log_softmax(dec[:, :, 3:], dim=0)
             x_k = dec[:, :, :3]
             mx = x_k * log_m.exp()
             img = mx.sum(0)

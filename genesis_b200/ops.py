@@ -873,31 +873,38 @@ def monet_loss(x, dec, lm, std):
 
 # ----------------------------------------------------------------------------------------- stand-alone mask KL
 class _MaskKL(Function):
-    """MONet.kl_m_loss between given log-masks lm [K,B,1,H,W] and the log-softmax over K of plane 3 of dec [K,B,4,H,W]
-    (GENESIS-V2 `klm_loss`, reference genesisv2_config.py:171-176 -> monet_config.py:157-170) -> kl [B].
-    detach=True (`detach_mr_in_klm`, the default): no gradient to the decoder logits."""
+    """MONet.kl_m_loss (monet_config.py:157-170) between given log-masks lm [K,B,1,H,W] and the log-softmax over K of mask
+    logits -> kl [B].  The logits are plane 3 of a packed decoder output dec [K,B,4,H,W] (GENESIS-V2 `klm_loss`,
+    genesisv2_config.py:171-176) or a plain [K,B,1,H,W] tensor (MONet prior_mode='scope': the stick-breaking log-masks,
+    which the log-softmax leaves unchanged because they already sum to one).
+    detach=True (`detach_mr_in_klm`, the V2 default): no gradient to the logits."""
 
     @staticmethod
-    def forward(ctx, lm, dec, detach):
-        lm, dec = _c(lm), _c(dec)
-        K, B = dec.shape[0], dec.shape[1]
-        P = dec.shape[3] * dec.shape[4]
+    def forward(ctx, lm, logits, detach):
+        lm, logits = _c(lm), _c(logits)
+        K, B = logits.shape[0], logits.shape[1]
+        cs = logits.shape[2]
+        assert cs in (1, 4)
+        P = logits.shape[3] * logits.shape[4]
+        off = 12 * P if cs == 4 else 0
         kl = _new(lm, B)
         lmr = torch.empty_like(lm)
-        _call('g2_mask_kl_fwd_f32', lm, dec.data_ptr() + 12 * P, lmr, kl, K, B, P, 1, 4)
-        ctx.save_for_backward(lm, dec)
+        _call('g2_mask_kl_fwd_f32', lm, logits.data_ptr() + off, lmr, kl, K, B, P, 1, cs)
+        ctx.save_for_backward(lm, logits)
         ctx.detach = detach
         return kl
 
     @staticmethod
     def backward(ctx, gkl):
-        lm, dec = ctx.saved_tensors
-        K, B = dec.shape[0], dec.shape[1]
-        P = dec.shape[3] * dec.shape[4]
+        lm, logits = ctx.saved_tensors
+        K, B = logits.shape[0], logits.shape[1]
+        cs = logits.shape[2]
+        P = logits.shape[3] * logits.shape[4]
+        off = 12 * P if cs == 4 else 0
         dlm = torch.empty_like(lm)
-        ddec = torch.zeros_like(dec)
-        _call('g2_mask_kl_bwd_f32', lm, dec.data_ptr() + 12 * P, _c(gkl), dlm, ddec.data_ptr() + 12 * P, K, B, P, 1, 4, 1, 4, 0)
-        return dlm, (None if ctx.detach else ddec), None
+        dlg = torch.zeros_like(logits)
+        _call('g2_mask_kl_bwd_f32', lm, logits.data_ptr() + off, _c(gkl), dlm, dlg.data_ptr() + off, K, B, P, 1, cs, 1, cs, 0)
+        return dlm, (None if ctx.detach else dlg), None
 
 
 def mask_kl(lm, dec, detach=True):

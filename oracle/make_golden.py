@@ -208,6 +208,7 @@ if __name__ == '__main__':
         run_case('variant_genesis_k3_symmetric', 'genesis', 3, 64, 2, 'multid', comp_symmetric=True)
         run_case('variant_genesisv2_k4_klm', 'genesisv2', 4, 64, 2, 'stacks', klm_loss=True)
         run_case('variant_genesisv2_k4_klm_nodetach', 'genesisv2', 4, 64, 2, 'rooms', klm_loss=True, detach_mr_in_klm=False)
+        run_case('variant_monet_k4_scope', 'monet', 4, 64, 2, 'multid', prior_mode='scope')
         run_case('variant_genesisv2_k4_noprior', 'genesisv2', 4, 64, 2, 'stacks', autoreg_prior=False)
         sys.exit(0)
     if '--vae' in sys.argv:

@@ -149,6 +149,20 @@ def mask_recon_log_softmax(logits_k):
     return [ls[..., k] for k in range(len(logits_k))]
 
 
+def mask_recon_log_scope(logits_k):
+    """MONet.get_mask_recon_stack, prior_mode='scope', log=True (monet_config.py:141-153): stick-breaking over the mask logits,
+    the last mask takes the remaining scope."""
+    log_s = torch.zeros_like(logits_k[0])
+    out = []
+    for step, a in enumerate(logits_k):
+        if step == len(logits_k) - 1:
+            out.append(log_s)
+        else:
+            out.append(log_s + F.logsigmoid(a))
+            log_s = log_s + F.logsigmoid(-a)
+    return out
+
+
 def monet_kl_m(log_m_k, log_m_r_k):
     """MONet.kl_m_loss (monet_config.py:157-170)."""
     B = log_m_k[0].shape[0]
@@ -184,7 +198,10 @@ def monet_forward(P, x, tape, cfg, training=True):
     x_r_k = [d[:, :3] for d in dec_k]
     if cfg.pixel_bound:
         x_r_k = [torch.sigmoid(t) for t in x_r_k]
-    log_m_r_k = mask_recon_log_softmax([d[:, 3:] for d in dec_k])
+    if cfg.get('prior_mode', 'softmax') == 'scope':
+        log_m_r_k = mask_recon_log_scope([d[:, 3:] for d in dec_k])
+    else:
+        log_m_r_k = mask_recon_log_softmax([d[:, 3:] for d in dec_k])
     recon = sum(m.exp() * xr for m, xr in zip(log_m_k, x_r_k))
     err = O.mixture_nll(x, log_m_k, x_r_k, _stds(P, cfg, K, dt))
     kl_m = monet_kl_m(log_m_k, log_m_r_k)
@@ -399,7 +416,10 @@ def monet_sample(P, batch_size, tape, cfg, training=False):
     dec = O.broadcast_decoder(z, P, 'comp_vae.decoder_module', img, cfg.comp_dec_layers, O.act_fn('relu'))
     x = torch.sigmoid(dec[:, :3]) if cfg.pixel_bound else dec[:, :3]
     x_k = list(torch.chunk(x, K, 0))
-    log_m_k = mask_recon_log_softmax(list(torch.chunk(dec[:, 3:], K, 0)))
+    if cfg.get('prior_mode', 'softmax') == 'scope':
+        log_m_k = mask_recon_log_scope(list(torch.chunk(dec[:, 3:], K, 0)))
+    else:
+        log_m_k = mask_recon_log_softmax(list(torch.chunk(dec[:, 3:], K, 0)))
     image = sum(m.exp() * xk for m, xk in zip(log_m_k, x_k))
     return dict(image=image, x_k=x_k, log_m_k=log_m_k)
 

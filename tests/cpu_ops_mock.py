@@ -132,7 +132,7 @@ def monet_loss(x, dec, lm, std):
 
 def mask_kl(lm, dec, detach=True):
     K, B = lm.shape[0], lm.shape[1]
-    lmr = torch.log_softmax(dec[:, :, 3:], dim=0)
+    lmr = torch.log_softmax(dec[:, :, 3:] if dec.shape[2] == 4 else dec, dim=0)
     if detach:
         lmr = lmr.detach()
     q = lm.exp().clamp_min(1e-5).permute(1, 2, 3, 4, 0).reshape(-1, K)

@@ -259,7 +259,8 @@ def test_variant_genesis_comp_symmetric_engine_matches_reference():
 @pytest.mark.parametrize('name,over', [('variant_genesisv2_k4_klm', dict(klm_loss=True)),
                                        ('variant_genesisv2_k4_klm_nodetach', dict(klm_loss=True, detach_mr_in_klm=False)),
                                        ('variant_genesisv2_k4_noprior', dict(autoreg_prior=False)),
-                                       ('variant_genesis_k3_nocompprior', dict(comp_prior=False))])
+                                       ('variant_genesis_k3_nocompprior', dict(comp_prior=False)),
+                                       ('variant_monet_k4_scope', dict(prior_mode='scope'))])
 def test_flag_variants_engine_matches_reference(name, over):
     """Engine vs the reference goldens of the flag variants (ops.mask_kl for klm_loss; prior flags)."""
     import numpy as np

@@ -199,3 +199,23 @@ def test_genesisv2_klm_loss_variant_host_logic(monkeypatch, detach):
     U.engine_total_loss(losses).backward()
     M.total_loss(ref).backward()
     check_grads(m, P, tol=5e-3)
+
+
+def test_monet_scope_prior_variant_host_logic(monkeypatch):
+    """prior_mode='scope' (reference monet_config.py:141-153), forward + backward and sample()."""
+    m, (recon, losses, stats, att, comp), P, ref = run_plugin(monkeypatch, 'monet', 3, 2, 'multid', prior_mode='scope')
+    np.testing.assert_allclose(losses['err'].detach().numpy(), ref['err'].detach().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(losses['kl_m'].detach().numpy(), ref['kl_m'].detach().numpy(), rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(stack(stats['log_m_r_k']), stack(ref['log_m_r_k']), atol=1e-4)
+    import util_parity as U
+    U.engine_total_loss(losses).backward()
+    M.total_loss(ref).backward()
+    check_grads(m, P, tol=5e-3)
+    m.eval()
+    m.set_noise_tape(O.NoiseTape(seed=4))
+    img, st = m.sample(2, 3)
+    m.set_noise_tape(None)
+    with torch.no_grad():
+        sref = M.SAMPLE['monet']({k: v.detach() for k, v in m.state_dict().items()}, 2, O.NoiseTape(seed=4),
+                                 M.make_cfg('monet', K_steps=3, img_size=64, prior_mode='scope'), training=False)
+    np.testing.assert_allclose(img.numpy(), sref['image'].numpy(), atol=1e-5)

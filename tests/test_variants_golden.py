@@ -2,7 +2,7 @@
 oracle/make_golden.py --variants; the engine's holders re-create the variant's seeded parameters and the oracle reproduces
 outputs and gradient summaries.  Variants so far: GENESIS with enc_norm = dec_norm = 'in' (genesis_config.py:39-40); one-stage GENESIS (two_stage=False,
 genesis_config.py:121-126, 178-185); GENESIS with comp_prior=False; GENESIS with comp_symmetric=True (genesis_config.py:101-120); GENESIS-V2 with autoreg_prior=False; GENESIS-V2 with klm_loss=True
-(detach_mr_in_klm True / False, genesisv2_config.py:171-176).  (GENESIS with
+(detach_mr_in_klm True / False, genesisv2_config.py:171-176); MONet with prior_mode='scope' (monet_config.py:141-153).  (GENESIS with
 autoreg_prior=False is not a valid reference configuration: genesis_config.py:212 dereferences self.prior_lstm regardless.)"""
 import glob
 import os
