@@ -366,10 +366,11 @@ def comp_encode(enc, packed, act):
     return ops.linear(h, m[11].weight, m[11].bias)
 
 
-def broadcast_decode(dec, z, act, nsig):
+def broadcast_decode(dec, z, act, nsig, head_act=None):
     """BroadcastDecoder (reference decoders.py:21-35) without materialising the broadcast: the first VALID
     3x3 conv over [z tiled | coords] splits into a per-sample vector (sum of the z-taps) plus a
-    sample-independent coordinate map.  Returns NCHW [N, nout, D, D]."""
+    sample-independent coordinate map.  Returns NCHW [N, nout, D, D]; with `head_act` the final 1x1
+    conv is a feature layer instead (BaselineVAE broadcast decoder, vae_config.py:53-60): NHWC [N, D, D, nout] after head_act."""
     L, D = dec.num_layers, dec.img_dim
     d = D + 2 * L
     c1 = dec.seq[1]
@@ -383,6 +384,8 @@ def broadcast_decode(dec, z, act, nsig):
         c = dec.seq[1 + 2 * i]
         h = ops.conv2d(h, c.weight, c.bias, 1, 0, act)
     last = dec.seq[1 + 2 * L]
+    if head_act is not None:
+        return ops.conv2d(h, last.weight, last.bias, 1, 0, head_act)
     return ops.out1x1(h, last.weight, last.bias, nsig)
 
 

@@ -4,7 +4,7 @@ Same Forge contract (flags of vae_config.py:26-31, `load(cfg)`, forward -> (reco
 None, None), sample(), get_features()) and the same state_dict names (`vae.q_z_nn.*`, `vae.q_z_mean`, `vae.q_z_var.0`,
 `vae.p_x_nn.*`, `vae.p_x_mean`), on the engine's kernels: the gated conv encoder / conv-transpose decoder are the ones
 GENESIS uses for its attention core (holders.sylvester_encode / sylvester_decode), the Gaussian pixel likelihood is the
-mixture kernel with one slot and a zero log-mask.  The default `broadcast_decoder=False` variant only.
+mixture kernel with one slot and a zero log-mask.  Both decoder variants (`broadcast_decoder` False / True, vae_config.py:53-61).
 NOTE: written after the round-1 GPU budget was spent -- exercised on a B200 by tests/test_pending_next_round.py first."""
 import os
 import sys
@@ -53,10 +53,13 @@ class BaselineVAE(nn.Module, NoiseMixin):
         self.pixel_bound = cfg.pixel_bound
         self.debug = cfg.debug
         self.img_size = cfg.img_size
-        if getattr(cfg, 'broadcast_decoder', False):
-            raise NotImplementedError('engine covers the default deconvolutional BaselineVAE (SURVEY.md section 8f.4)')
+        self.broadcast_decoder = bool(getattr(cfg, 'broadcast_decoder', False))
         nin = cfg.input_channels if hasattr(cfg, 'input_channels') else 3
         self.vae = H.SylvesterVAE(self.ldim, [nin, cfg.img_size, cfg.img_size], nin)
+        if self.broadcast_decoder:          # reference vae_config.py:53-61 (replaces the modules AFTER the full VAE was built)
+            self.vae.p_x_nn = nn.Sequential(nn.Identity(), H.BroadcastDecoderHolder(self.ldim, 64, 64, 4, cfg.img_size),
+                                            nn.Identity())
+            self.vae.p_x_mean = nn.Conv2d(64, nin, 1, 1, 0)
         self.register_buffer('_std', torch.full((1,), float(cfg.pixel_std)), persistent=False)
 
     def forward(self, x):
@@ -71,7 +74,7 @@ class BaselineVAE(nn.Module, NoiseMixin):
         wmv = torch.cat([core.q_z_mean.weight, core.q_z_var[0].weight], 0)
         bmv = torch.cat([core.q_z_mean.bias, core.q_z_var[0].bias], 0)
         z, mu, sigma = H.gauss_head(ops.linear(h, wmv, bmv), self._normal((B, self.ldim), x))
-        recon = H.sylvester_decode(core, z, self.training, 3 if self.pixel_bound else 0)   # NCHW [B,nin,H,W]
+        recon = self._decode(z)                                                            # NCHW [B,nin,H,W]
         # -log N(x; recon, std) summed over pixels = the mixture likelihood with one slot and log m = 0
         log_m = torch.zeros(1, B, 1, self.img_size, self.img_size, device=x.device)
         err, _, _ = ops.mixture_nll(x, recon.unsqueeze(0), log_m, self._std, False)
@@ -80,10 +83,17 @@ class BaselineVAE(nn.Module, NoiseMixin):
         stats = AttrDict(x=recon, mu=mu, sigma=sigma, z=z)
         return recon, losses, stats, None, None
 
+    def _decode(self, z):
+        nsig = 3 if self.pixel_bound else 0
+        if self.broadcast_decoder:
+            h = H.broadcast_decode(self.vae.p_x_nn[1], z, 'elu', 0, head_act='elu')       # NHWC [B,H,W,64]
+            return ops.out1x1(h, self.vae.p_x_mean.weight, self.vae.p_x_mean.bias, nsig)
+        return H.sylvester_decode(self.vae, z, self.training, nsig)
+
     def sample(self, batch_size, *args, **kwargs):
         with torch.no_grad():
             z = self._normal((batch_size, self.ldim), self._std)
-            x = H.sylvester_decode(self.vae, z, self.training, 3 if self.pixel_bound else 0)
+            x = self._decode(z)
         return x, AttrDict(z=z)
 
     def get_features(self, image_batch):

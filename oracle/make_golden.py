@@ -133,9 +133,9 @@ def run_sample_case(name, fwd_case, sb):
     print(name, 'image mean', float(image.mean()), '->', path, os.path.getsize(path) // 1024, 'KiB')
 
 
-def run_vae_case(name='vae_b4', B=4, img=64, gen='multid'):
+def run_vae_case(name='vae_b4', B=4, img=64, gen='multid', **over):
     """BaselineVAE (config c1, models/vae_config.py): forward + backward of err.mean + kl_l.mean (train.py:227-239)."""
-    cfg = M.make_cfg('vae', K_steps=1, img_size=img)
+    cfg = M.make_cfg('vae', K_steps=1, img_size=img, **over)
     ref = ref_loader.load_reference('vae', cfg, seed=0)
     ref.train()
     names, sums = param_checksums(ref.state_dict())
@@ -160,6 +160,8 @@ def run_vae_case(name='vae_b4', B=4, img=64, gen='multid'):
     g['err'] = losses['err'].detach().numpy()
     g['kl_l'] = losses['kl_l'].detach().numpy()
     g['z'] = stats['z'].detach().numpy()
+    if over:
+        g['overrides'] = np.array(['%s=%s' % kv for kv in sorted(over.items())])
     path = os.path.join(OUT_DIR, name + '.npz')
     np.savez_compressed(path, **g)
     print(name, 'err', g['err'], '->', path, os.path.getsize(path) // 1024, 'KiB')
@@ -213,6 +215,7 @@ if __name__ == '__main__':
         sys.exit(0)
     if '--vae' in sys.argv:
         run_vae_case()
+        run_vae_case('vae_b2_broadcast', B=2, broadcast_decoder=True)
         sys.exit(0)
     if '--evals' in sys.argv:
         for case in EVAL_CASES:

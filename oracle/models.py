@@ -326,7 +326,11 @@ def vae_forward(P, x, tape, cfg, training=True):
     mu = O.linear(h, P, 'vae.q_z_mean')
     sigma = O.to_var(O.linear(h, P, 'vae.q_z_var.0')).sqrt()
     z = mu + sigma * tape.normal(mu.shape, dt)
-    recon = O.sylvester_decode(z, P, 'vae', img, None, training, upd)
+    if cfg.get('broadcast_decoder', False):        # vae_config.py:53-61
+        hdec = F.elu(O.broadcast_decoder(z, P, 'vae.p_x_nn.1', img, 4, O.act_fn('elu')))
+        recon = F.conv2d(hdec, P['vae.p_x_mean.weight'], P['vae.p_x_mean.bias'])
+    else:
+        recon = O.sylvester_decode(z, P, 'vae', img, None, training, upd)
     if cfg.pixel_bound:
         recon = torch.sigmoid(recon)
     err = -O.normal_log_prob(x, recon, torch.tensor(cfg.pixel_std, dtype=dt)).sum(dim=(1, 2, 3))

@@ -175,12 +175,13 @@ def test_engine_eval_forward_matches_reference(name):
     np.testing.assert_allclose(torch.stack(list(stats['log_m_k']), 0).cpu().numpy(), g['log_m_k'], atol=1e-2, rtol=1e-2)
 
 
-def test_vae_engine_matches_reference_golden():
-    """BaselineVAE plug-in (genesis_b200/model_configs/vae_config.py) forward + backward vs tests/golden/vae_b4.npz."""
+@pytest.mark.parametrize('name,over', [('vae_b4', {}), ('vae_b2_broadcast', {'broadcast_decoder': True})])
+def test_vae_engine_matches_reference_golden(name, over):
+    """BaselineVAE plug-in (genesis_b200/model_configs/vae_config.py) forward + backward vs tests/golden/vae_*.npz."""
     import numpy as np
     from test_oracle_golden import build_engine_model, direction, tape_from_golden
-    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'vae_b4.npz'))
-    m, cfg = build_engine_model('vae', 1, 64)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', name + '.npz'))
+    m, cfg = build_engine_model('vae', 1, 64, **over)
     m = m.cuda().train()
     m.set_noise_tape(tape_from_golden(g))
     recon, losses, stats, _, _ = m(torch.from_numpy(g['x']).cuda())

@@ -117,8 +117,9 @@ def test_genesisv2_host_logic(monkeypatch):
     check_grads(m, P, tol=5e-3)
 
 
-def test_vae_host_logic(monkeypatch):
-    m, (recon, losses, stats, _, _), P, ref = run_plugin(monkeypatch, 'vae', 1, 3, 'multid')
+@pytest.mark.parametrize('over', [{}, {'broadcast_decoder': True}], ids=['deconv', 'broadcast'])
+def test_vae_host_logic(monkeypatch, over):
+    m, (recon, losses, stats, _, _), P, ref = run_plugin(monkeypatch, 'vae', 1, 3, 'multid', **over)
     np.testing.assert_allclose(losses['err'].detach().numpy(), ref['err'].detach().numpy(), rtol=1e-5)
     np.testing.assert_allclose(losses['kl_l'].detach().numpy(), ref['kl_l'].detach().numpy(), rtol=1e-4, atol=1e-3)
     np.testing.assert_allclose(recon.detach().numpy(), ref['recon'].detach().numpy(), atol=1e-5)

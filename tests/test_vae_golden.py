@@ -9,12 +9,17 @@ import torch
 from oracle import models as M
 from test_oracle_golden import build_engine_model, direction, tape_from_golden
 
-PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'vae_b4.npz')
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CASES = [(os.path.join(HERE, 'golden', 'vae_b4.npz'), {}), (os.path.join(HERE, 'golden', 'vae_b2_broadcast.npz'), {'broadcast_decoder': True})]
+PATH = CASES[0][0]
 
 
-def test_vae_init_matches_reference_checksums():
-    g = np.load(PATH)
-    m, _ = build_engine_model('vae', 1, 64)
+@pytest.mark.parametrize('path,over', CASES, ids=['deconv', 'broadcast'])
+def test_vae_init_matches_reference_checksums(path, over):
+    g = np.load(path)
+    m, _ = build_engine_model('vae', 1, 64, **over)
     sd = m.state_dict()
     assert sorted(sd.keys()) == list(g['param_names'])
     for n, (s, a) in zip(g['param_names'], g['param_sums']):
@@ -23,9 +28,10 @@ def test_vae_init_matches_reference_checksums():
         assert abs(t.abs().sum().item() - a) <= 1e-9 * max(1.0, a), n
 
 
-def test_vae_oracle_matches_golden():
-    g = np.load(PATH)
-    m, cfg = build_engine_model('vae', 1, 64)
+@pytest.mark.parametrize('path,over', CASES, ids=['deconv', 'broadcast'])
+def test_vae_oracle_matches_golden(path, over):
+    g = np.load(path)
+    m, cfg = build_engine_model('vae', 1, 64, **over)
     P = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in m.state_dict().items()}
     out = M.FORWARD['vae'](P, torch.from_numpy(g['x']), tape_from_golden(g), cfg, training=True)
     np.testing.assert_allclose(out['err'].detach().numpy(), g['err'], rtol=2e-6)
