@@ -30,6 +30,7 @@ except ImportError:
 
 from genesis_b200 import holders as H  # noqa: E402
 from genesis_b200 import ops  # noqa: E402
+from genesis_b200.noise import NoiseMixin  # noqa: E402,F401  (re-exported: the other plug-ins use genesis_config.NoiseMixin)
 
 # Flag names / defaults: reference models/genesis_config.py:33-52
 flags.DEFINE_boolean('two_stage', True, 'Use two stages if two, else only one.')
@@ -61,24 +62,6 @@ class LatentSBPHolder(nn.Module):
         self.core = core
         self.lstm = nn.LSTM(core.z_size + 256, 2 * core.z_size)
         self.linear = nn.Linear(2 * core.z_size, 2 * core.z_size)
-
-
-class NoiseMixin(object):
-    """eps / u source: torch's device RNG in production, a recorded tape for parity runs."""
-    _tape = None
-
-    def set_noise_tape(self, tape):
-        self._tape = tape
-
-    def _normal(self, shape, like):
-        if self._tape is not None:
-            return self._tape.normal(shape).to(like.device)
-        return torch.randn(shape, device=like.device, dtype=torch.float32)
-
-    def _uniform(self, shape, like):
-        if self._tape is not None:
-            return self._tape.uniform(shape).to(like.device)
-        return torch.rand(shape, device=like.device, dtype=torch.float32)
 
 
 class Genesis(nn.Module, NoiseMixin):

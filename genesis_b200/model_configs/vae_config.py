@@ -30,7 +30,7 @@ except ImportError:
 
 from genesis_b200 import holders as H  # noqa: E402
 from genesis_b200 import ops  # noqa: E402
-from genesis_b200.model_configs.genesis_config import NoiseMixin  # noqa: E402
+from genesis_b200.noise import NoiseMixin  # noqa: E402  (not via genesis_config: that would register its flags, e.g. a second `pixel_bound`)
 
 # Flag names / defaults: reference models/vae_config.py:26-31
 flags.DEFINE_integer('latent_dimension', 64, 'Latent channels.')
