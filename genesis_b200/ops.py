@@ -916,7 +916,8 @@ def mask_kl(lm, dec, detach=True):
 # Monte-Carlo KL, forward and backward (csrc/latent.cu).  Switched by set_fused_latent(); OFF by default until the kernels
 # have been validated on a B200 (tests/test_pending_next_round.py) -- the ATen formulation in holders.py stays the
 # validated path.
-_FUSED = {'on': False}
+import os as _os
+_FUSED = {'on': _os.environ.get('G2_FUSED_LATENT', '0') == '1'}      # environment switch for A/B runs; default off
 
 
 def set_fused_latent(on):
