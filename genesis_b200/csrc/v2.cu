@@ -51,6 +51,16 @@ constexpr int CD = 8;
 constexpr int IC_THREADS = 1024;
 constexpr int IC_MAXPPT = 16;       // pixels per thread (P <= 16384)
 
+// KT: 0 gaussian  alpha = exp(-|c - seed|^2 / sigma);  1 laplacian  alpha = exp(-sqrt(clamp(|c - seed|^2, 1e-10, 1e10)) / sigma)
+// (blocks.py:49-61);  2 epanechnikov  alpha = relu(1 - |c - seed|^2 / sigma)   (attention.py:195-203).
+template <int KT>
+__device__ __forceinline__ float icsbp_alpha(float dist, float inv_sigma) {
+    if constexpr (KT == 0) return expf(-dist * inv_sigma);
+    else if constexpr (KT == 1) return expf(-sqrtf(fminf(fmaxf(dist, 1e-10f), 1e10f)) * inv_sigma);
+    else return fmaxf(1.f - dist * inv_sigma, 0.f);
+}
+
+template <int KT>
 __global__ void __launch_bounds__(IC_THREADS) icsbp_fwd_kernel(const float* __restrict__ colour, const float* __restrict__ u,
                                                                const float* __restrict__ log_sigma, float* __restrict__ log_m,
                                                                float* __restrict__ log_s, int* __restrict__ seed_idx, int B, int P, int K) {
@@ -107,7 +117,7 @@ __global__ void __launch_bounds__(IC_THREADS) icsbp_fwd_kernel(const float* __re
                 const float d0 = c0.x - s_seed[0], d1 = c0.y - s_seed[1], d2 = c0.z - s_seed[2], d3 = c0.w - s_seed[3];
                 const float d4 = c1.x - s_seed[4], d5 = c1.y - s_seed[5], d6 = c1.z - s_seed[6], d7 = c1.w - s_seed[7];
                 const float dist = ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3)) + ((d4 * d4 + d5 * d5) + (d6 * d6 + d7 * d7));
-                float a = expf(-dist * inv_sigma);
+                float a = icsbp_alpha<KT>(dist, inv_sigma);
                 a = fminf(fmaxf(a, 0.01f), 0.99f);
                 log_s[k * KB + (long)b * P + p] = ls[j];
                 log_m[k * KB + (long)b * P + p] = ls[j] + logf(a);
@@ -131,6 +141,9 @@ __global__ void __launch_bounds__(IC_THREADS) icsbp_fwd_kernel(const float* __re
 //   R = G_{K-1};  for k = K-2..0: d(alpha_c) = G_k / ac - R / (1 - ac)   (straight-through clamp);  R += G_k
 //   d(dist) = -d(alpha) * alpha / sigma;  d log_sigma += d(alpha) * alpha * dist / sigma
 //   d colour_p += 2 (colour_p - seed) d(dist);  d seed -= sum_p 2 (colour_p - seed) d(dist)  -> colour[idx_k]
+// Other kernels (KT): laplacian  d = sqrt(clamp_ste(dist)):  d(dist) = -d(alpha) alpha / (2 d sigma),  d log_sigma += d(alpha) alpha d / sigma;
+// epanechnikov, where 1 - dist / sigma > 0:  d(dist) = -d(alpha) / sigma,  d log_sigma += d(alpha) dist / sigma  (else both 0).
+template <int KT>
 __global__ void __launch_bounds__(IC_THREADS) icsbp_bwd_kernel(const float* __restrict__ colour, const float* __restrict__ log_sigma,
                                                                const int* __restrict__ seed_idx, const float* __restrict__ dlog_m,
                                                                float* __restrict__ dcolour, float* __restrict__ dlog_sigma_b,
@@ -175,13 +188,24 @@ __global__ void __launch_bounds__(IC_THREADS) icsbp_bwd_kernel(const float* __re
                 float dist = 0.f;
 #pragma unroll
                 for (int c = 0; c < CD; ++c) dist += df[c] * df[c];
-                const float a = expf(-dist * inv_sigma);
+                const float a = icsbp_alpha<KT>(dist, inv_sigma);
                 const float ac = fminf(fmaxf(a, 0.01f), 0.99f);
                 const float G = __ldg(dlog_m + (long)k * KB + (long)b * P + p);
                 const float da = G / ac - R[j] / (1.f - ac);
                 R[j] += G;
-                const float dd = -da * a * inv_sigma;
-                dls += da * a * dist * inv_sigma;
+                float dd;
+                if constexpr (KT == 0) {
+                    dd = -da * a * inv_sigma;
+                    dls += da * a * dist * inv_sigma;
+                } else if constexpr (KT == 1) {
+                    const float d = sqrtf(fminf(fmaxf(dist, 1e-10f), 1e10f));
+                    dd = -da * a * inv_sigma * (0.5f / d);
+                    dls += da * a * d * inv_sigma;
+                } else {
+                    const bool on = 1.f - dist * inv_sigma > 0.f;
+                    dd = on ? -da * inv_sigma : 0.f;
+                    dls += on ? da * dist * inv_sigma : 0.f;
+                }
                 float g[CD];
 #pragma unroll
                 for (int c = 0; c < CD; ++c) { g[c] = 2.f * df[c] * dd; dseed[c] -= g[c]; }
@@ -324,7 +348,18 @@ int g2_icsbp_fwd_f32(const float* colour, const float* u, const float* log_sigma
                      int B, int P, int K, int colour_dim, cudaStream_t stream) {
     G2_CHECK_ARG(colour && u && log_sigma && log_m && log_s && seed_idx && B > 0 && K >= 2);
     G2_CHECK_ARG(colour_dim == CD && P > 0 && P <= IC_THREADS * IC_MAXPPT);
-    icsbp_fwd_kernel<<<B, IC_THREADS, 0, stream>>>(colour, u, log_sigma, log_m, log_s, seed_idx, B, P, K);
+    icsbp_fwd_kernel<0><<<B, IC_THREADS, 0, stream>>>(colour, u, log_sigma, log_m, log_s, seed_idx, B, P, K);
+    G2_LAUNCH_RET();
+}
+
+// Same contract with the kernel of InstanceColouringSBP selectable: 0 gaussian, 1 laplacian, 2 epanechnikov.
+int g2_icsbp_kernel_fwd_f32(const float* colour, const float* u, const float* log_sigma, float* log_m, float* log_s, int* seed_idx,
+                            int B, int P, int K, int colour_dim, int kernel_type, cudaStream_t stream) {
+    G2_CHECK_ARG(colour && u && log_sigma && log_m && log_s && seed_idx && B > 0 && K >= 2);
+    G2_CHECK_ARG(colour_dim == CD && P > 0 && P <= IC_THREADS * IC_MAXPPT && kernel_type >= 0 && kernel_type <= 2);
+    if (kernel_type == 0) icsbp_fwd_kernel<0><<<B, IC_THREADS, 0, stream>>>(colour, u, log_sigma, log_m, log_s, seed_idx, B, P, K);
+    else if (kernel_type == 1) icsbp_fwd_kernel<1><<<B, IC_THREADS, 0, stream>>>(colour, u, log_sigma, log_m, log_s, seed_idx, B, P, K);
+    else icsbp_fwd_kernel<2><<<B, IC_THREADS, 0, stream>>>(colour, u, log_sigma, log_m, log_s, seed_idx, B, P, K);
     G2_LAUNCH_RET();
 }
 
@@ -332,7 +367,17 @@ int g2_icsbp_bwd_f32(const float* colour, const float* log_sigma, const int* see
                      float* dlog_sigma_b, int B, int P, int K, int colour_dim, cudaStream_t stream) {
     G2_CHECK_ARG(colour && log_sigma && seed_idx && dlog_m && dcolour && dlog_sigma_b && B > 0 && K >= 2);
     G2_CHECK_ARG(colour_dim == CD && P > 0 && P <= IC_THREADS * IC_MAXPPT);
-    icsbp_bwd_kernel<<<B, IC_THREADS, 0, stream>>>(colour, log_sigma, seed_idx, dlog_m, dcolour, dlog_sigma_b, B, P, K);
+    icsbp_bwd_kernel<0><<<B, IC_THREADS, 0, stream>>>(colour, log_sigma, seed_idx, dlog_m, dcolour, dlog_sigma_b, B, P, K);
+    G2_LAUNCH_RET();
+}
+
+int g2_icsbp_kernel_bwd_f32(const float* colour, const float* log_sigma, const int* seed_idx, const float* dlog_m, float* dcolour,
+                            float* dlog_sigma_b, int B, int P, int K, int colour_dim, int kernel_type, cudaStream_t stream) {
+    G2_CHECK_ARG(colour && log_sigma && seed_idx && dlog_m && dcolour && dlog_sigma_b && B > 0 && K >= 2);
+    G2_CHECK_ARG(colour_dim == CD && P > 0 && P <= IC_THREADS * IC_MAXPPT && kernel_type >= 0 && kernel_type <= 2);
+    if (kernel_type == 0) icsbp_bwd_kernel<0><<<B, IC_THREADS, 0, stream>>>(colour, log_sigma, seed_idx, dlog_m, dcolour, dlog_sigma_b, B, P, K);
+    else if (kernel_type == 1) icsbp_bwd_kernel<1><<<B, IC_THREADS, 0, stream>>>(colour, log_sigma, seed_idx, dlog_m, dcolour, dlog_sigma_b, B, P, K);
+    else icsbp_bwd_kernel<2><<<B, IC_THREADS, 0, stream>>>(colour, log_sigma, seed_idx, dlog_m, dcolour, dlog_sigma_b, B, P, K);
     G2_LAUNCH_RET();
 }
 

@@ -68,13 +68,23 @@ class SemiConvHolder(nn.Module):
 class ICSBPHolder(nn.Module):
     """modules/attention.py:136-160."""
 
-    def __init__(self, K_steps, feat_dim, colour_dim=8):
+    def __init__(self, K_steps, feat_dim, colour_dim=8, kernel='gaussian', semiconv=True):
         super().__init__()
         self.colour_dim = colour_dim
+        self.kernel = kernel
         # numpy float64 -> float64 parameter, exactly as the reference (modules/attention.py:146-155)
-        sigma_init = 1.0 / (K_steps * np.log(2))
+        if kernel == 'laplacian':
+            sigma_init = 1.0 / (np.sqrt(K_steps) * np.log(2))
+        elif kernel == 'gaussian':
+            sigma_init = 1.0 / (K_steps * np.log(2))
+        elif kernel == 'epanechnikov':
+            sigma_init = 2.0 / K_steps
+        else:
+            raise ValueError("No valid kernel.")
         self.log_sigma = nn.Parameter(torch.tensor(sigma_init).log())
-        self.colour_head = SemiConvHolder(feat_dim, colour_dim)
+        # modules/attention.py:157-160: SemiConv (1x1 conv, scalar gate, pixel coordinates added to the last two channels)
+        # or a plain 1x1 conv
+        self.colour_head = SemiConvHolder(feat_dim, colour_dim) if semiconv else nn.Conv2d(feat_dim, colour_dim, 1)
 
 
 class GenesisV2(nn.Module, _g.NoiseMixin):
@@ -90,16 +100,16 @@ class GenesisV2(nn.Module, _g.NoiseMixin):
         self.debug = cfg.debug
         self.multi_gpu = cfg.multi_gpu
         self.img_size = cfg.img_size
-        if cfg.kernel != 'gaussian' or not cfg.semiconv or cfg.dynamic_K:
-            raise NotImplementedError('engine covers GENESIS-V2 with the gaussian kernel, semiconv and fixed K '
-                                      '(SURVEY.md section 8f.4)')
+        if cfg.dynamic_K:
+            raise NotImplementedError('engine covers GENESIS-V2 with fixed K (SURVEY.md section 8f.4)')
+        self.semiconv = bool(cfg.semiconv)
         if cfg.feat_dim != 64:
             raise NotImplementedError('engine is tiled for feat_dim=64')
         c = cfg.feat_dim
         # construction order == reference (genesisv2_config.py:63-105) so seeded init is identical
         self.encoder = H.UNetHolder(int(math.log2(cfg.img_size) - 1), cfg.img_size, min(c, 64), 3, c, norm='gn')
         self.encoder.final_conv = nn.Identity()
-        self.att_process = ICSBPHolder(self.K_steps, c)
+        self.att_process = ICSBPHolder(self.K_steps, c, kernel=cfg.kernel, semiconv=self.semiconv)
         self.seg_head = H._conv_block(c, c, 'gn')
         self.feat_head = nn.Sequential(H._conv_block(c, c, 'gn'), nn.Conv2d(c, 2 * c, 1))
         self.z_head = nn.Sequential(nn.LayerNorm(2 * c), nn.Linear(2 * c, 2 * c), nn.Identity(), nn.Linear(2 * c, 2 * c))
@@ -149,12 +159,16 @@ class GenesisV2(nn.Module, _g.NoiseMixin):
         seg = H.conv_norm_relu(self.seg_head, enc_feat, 'gn')
         ap = self.att_process
         ch = ap.colour_head
-        out = ops.conv2d(seg, ch.conv.weight, ch.conv.bias, 1, 0) * ch.gate.gate             # [B,H,W,8] NHWC
         cd = ap.colour_dim
-        uv = torch.cat([out.new_zeros(1, S, S, cd - 2), H.coords_nhwc(S, x.device)], dim=3)
-        colour = out + uv
+        if self.semiconv:
+            out = ops.conv2d(seg, ch.conv.weight, ch.conv.bias, 1, 0) * ch.gate.gate         # [B,H,W,8] NHWC
+            uv = torch.cat([out.new_zeros(1, S, S, cd - 2), H.coords_nhwc(S, x.device)], dim=3)
+            colour = out + uv
+        else:                                   # plain 1x1 colour head: no coordinate offsets, delta = None (attention.py:174-178)
+            out = None
+            colour = ops.conv2d(seg, ch.weight, ch.bias, 1, 0)
         u = self._uniform((B, 1, S, S), x)
-        log_m, log_s, seed_idx = ops.icsbp(colour, u, ap.log_sigma, K)                       # [K,B,1,H,W]
+        log_m, log_s, seed_idx = ops.icsbp(colour, u, ap.log_sigma, K, ap.kernel)            # [K,B,1,H,W]
         # --- slot latents (reference genesisv2_config.py:145-161), feat_head evaluated once
         f = H.conv_norm_relu(self.feat_head[0], enc_feat, 'gn')
         f = ops.conv2d(f, self.feat_head[1].weight, self.feat_head[1].bias, 1, 0)            # [B,H,W,128]
@@ -214,7 +228,8 @@ class GenesisV2(nn.Module, _g.NoiseMixin):
             seeds = [flat[torch.arange(B, device=x.device), seed_idx[k].long()] for k in range(K - 1)]
         stats = AttrDict(recon=recon, log_m_k=log_m_k, log_s_k=list(log_s.unbind(0)), x_r_k=x_r_k,
                          log_m_r_k=log_m_r_k, mx_r_k=mx_r_k, instance_seg=inst, instance_seg_r=inst_r)
-        att_stats = AttrDict(colour=colour_nchw, delta=out.permute(0, 3, 1, 2)[:, -2:], seeds=seeds, seed_idx=seed_idx)
+        att_stats = AttrDict(colour=colour_nchw, delta=(out.permute(0, 3, 1, 2)[:, -2:] if out is not None else None),
+                             seeds=seeds, seed_idx=seed_idx)
         comp_stats = AttrDict(mu_k=mu_k, sigma_k=sigma_k, z_k=z_k, kl_l_k=[], pmu_k=pmu, psigma_k=psig)
         if self.debug:
             _g.check_log_masks(log_m_k)

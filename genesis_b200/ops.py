@@ -775,7 +775,7 @@ class _ICSBP(Function):
     """colour [B,H,W,8] NHWC, u [B,1,H,W], log_sigma [] -> log_m [K,B,1,H,W], log_s [K,B,1,H,W], seed_idx [K-1,B]."""
 
     @staticmethod
-    def forward(ctx, colour, u, log_sigma, K):
+    def forward(ctx, colour, u, log_sigma, K, kernel='gaussian'):
         colour, u = _c(colour), _c(u)
         B, H, W, CD = colour.shape
         P = H * W
@@ -783,9 +783,13 @@ class _ICSBP(Function):
         log_s = _new(colour, K, B, 1, H, W)
         idx = torch.empty((K - 1, B), device=colour.device, dtype=torch.int32)
         ls = log_sigma.detach().reshape(1).float().contiguous()
-        _call('g2_icsbp_fwd_f32', colour, u, ls, log_m, log_s, idx, B, P, K, CD)
+        kt = ICSBP_KERNELS[kernel]
+        if kt == 0:
+            _call('g2_icsbp_fwd_f32', colour, u, ls, log_m, log_s, idx, B, P, K, CD)
+        else:
+            _call('g2_icsbp_kernel_fwd_f32', colour, u, ls, log_m, log_s, idx, B, P, K, CD, kt)
         ctx.save_for_backward(colour, ls, idx)
-        ctx.K = K
+        ctx.K, ctx.kt = K, kt
         ctx.ls_dtype = log_sigma.dtype
         ctx.mark_non_differentiable(log_s, idx)
         return log_m, log_s, idx
@@ -796,12 +800,18 @@ class _ICSBP(Function):
         B, H, W, CD = colour.shape
         dcol = torch.empty_like(colour)
         dsig = _new(colour, B)
-        _call('g2_icsbp_bwd_f32', colour, ls, idx, _c(dlog_m), dcol, dsig, B, H * W, ctx.K, CD)
-        return dcol, None, dsig.sum().reshape(()).to(ctx.ls_dtype), None
+        if ctx.kt == 0:
+            _call('g2_icsbp_bwd_f32', colour, ls, idx, _c(dlog_m), dcol, dsig, B, H * W, ctx.K, CD)
+        else:
+            _call('g2_icsbp_kernel_bwd_f32', colour, ls, idx, _c(dlog_m), dcol, dsig, B, H * W, ctx.K, CD, ctx.kt)
+        return dcol, None, dsig.sum().reshape(()).to(ctx.ls_dtype), None, None
 
 
-def icsbp(colour, u, log_sigma, K):
-    return _ICSBP.apply(colour, u, log_sigma, K)
+ICSBP_KERNELS = {'gaussian': 0, 'laplacian': 1, 'epanechnikov': 2}       # reference modules/attention.py:146-153
+
+
+def icsbp(colour, u, log_sigma, K, kernel='gaussian'):
+    return _ICSBP.apply(colour, u, log_sigma, K, kernel)
 
 
 # ----------------------------------------------------------------------------------------- masked pooling

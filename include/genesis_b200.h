@@ -125,6 +125,13 @@ int g2_icsbp_fwd_f32(const float* colour, const float* u, const float* log_sigma
                      int* seed_idx, int B, int P, int K, int colour_dim, g2_stream_t stream);
 int g2_icsbp_bwd_f32(const float* colour, const float* log_sigma, const int* seed_idx, const float* dlog_m,
                      float* dcolour, float* dlog_sigma_b, int B, int P, int K, int colour_dim, g2_stream_t stream);
+/* The same with the `kernel` option of InstanceColouringSBP (modules/attention.py:146-153, 195-203):
+ * kernel_type 0 gaussian, 1 laplacian (euclidian distance, blocks.py:49-61), 2 epanechnikov (relu(1 - d2 / sigma)). */
+int g2_icsbp_kernel_fwd_f32(const float* colour, const float* u, const float* log_sigma, float* log_m, float* log_s,
+                            int* seed_idx, int B, int P, int K, int colour_dim, int kernel_type, g2_stream_t stream);
+int g2_icsbp_kernel_bwd_f32(const float* colour, const float* log_sigma, const int* seed_idx, const float* dlog_m,
+                            float* dcolour, float* dlog_sigma_b, int B, int P, int K, int colour_dim, int kernel_type,
+                            g2_stream_t stream);
 /* masked feature pooling of models/genesisv2_config.py:147-152: num[k,b,c] = sum_p m_k f, msum[k,b] = sum_p m_k */
 int g2_masked_pool_fwd_f32(const float* f, const float* log_m, float* num, float* msum, int B, int P, int C, int K,
                            g2_stream_t stream);

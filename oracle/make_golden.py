@@ -203,6 +203,11 @@ def run_eval_case(name, fwd_case):
 
 
 if __name__ == '__main__':
+    if '--variants-icsbp' in sys.argv:      # GENESIS-V2 attention options (modules/attention.py:138-160)
+        run_case('variant_genesisv2_k4_laplacian', 'genesisv2', 4, 64, 2, 'multid', kernel='laplacian')
+        run_case('variant_genesisv2_k4_epanechnikov', 'genesisv2', 4, 64, 2, 'rooms', kernel='epanechnikov')
+        run_case('variant_genesisv2_k4_nosemiconv', 'genesisv2', 4, 64, 2, 'stacks', semiconv=False)
+        sys.exit(0)
     if '--variants' in sys.argv:     # non-default model variants
         run_case('variant_genesis_k3_in', 'genesis', 3, 64, 3, 'multid', enc_norm='in', dec_norm='in')
         run_case('variant_genesis_k3_onestage', 'genesis', 3, 64, 2, 'multid', two_stage=False)

@@ -213,8 +213,8 @@ def monet_forward(P, x, tape, cfg, training=True):
 
 
 # ============================================================================ GENESIS-V2
-def icsbp(colour, u, log_sigma, steps):
-    """InstanceColouringSBP.forward (modules/attention.py:177-223), gaussian kernel, dynamic_K=False.
+def icsbp(colour, u, log_sigma, steps, kernel='gaussian'):
+    """InstanceColouringSBP.forward (modules/attention.py:177-223), dynamic_K=False; `kernel` as :195-205.
     colour [B,C,H,W] (after SemiConv), u [B,1,H,W] uniform draws, `steps` = K-1.  The bilinear resize
     of the scope at :185-186 is the identity because colour and scope share img_size."""
     B, C, H, W = colour.shape
@@ -226,7 +226,15 @@ def icsbp(colour, u, log_sigma, steps):
         idx = probs.flatten(2).argmax(2).flatten()                           # :187-188
         seed = flat[torch.arange(B), :, idx]                                  # :190-192, keeps grad
         dist = ((colour - seed.view(B, C, 1, 1)) ** 2).sum(1)                 # blocks.py:63-71
-        alpha = torch.exp(-dist / log_sigma.exp()).unsqueeze(1)               # :198-200
+        if kernel == 'gaussian':
+            alpha = torch.exp(-dist / log_sigma.exp())                        # :198-200
+        elif kernel == 'laplacian':                                           # :195-197, blocks.py:49-61
+            alpha = torch.exp(-O.clamp_ste(dist, 1e-10, 1e10).sqrt() / log_sigma.exp())
+        elif kernel == 'epanechnikov':                                        # :201-203
+            alpha = (1 - dist / log_sigma.exp()).relu()
+        else:
+            raise ValueError("No valid kernel.")
+        alpha = alpha.unsqueeze(1)
         alpha = O.clamp_ste(alpha, 0.01, 0.99)                                # :213
         log_m_k.append(log_s_k[k] + torch.log(alpha))
         log_s_k.append(log_s_k[k] + torch.log(1 - alpha))
@@ -266,13 +274,17 @@ def genesisv2_forward(P, x, tape, cfg, training=True):
     enc_feat = F.relu(O.unet(x, P, 'encoder', nb, 'gn'))                       # :114-115
     seg = conv_gn_relu(enc_feat, 'seg_head')
     # SemiConv (blocks.py:167-178)
-    cw, cb = P['att_process.colour_head.conv.weight'], P['att_process.colour_head.conv.bias']
-    out = P['att_process.colour_head.gate.gate'] * F.conv2d(seg, cw, cb)
-    delta = out[:, -2:]
-    uv = torch.cat([torch.zeros(1, out.shape[1] - 2, img, img, dtype=dt), O.pixel_coords(img, dt)], 1)
-    colour = out + uv
+    if getattr(cfg, 'semiconv', True):
+        cw, cb = P['att_process.colour_head.conv.weight'], P['att_process.colour_head.conv.bias']
+        out = P['att_process.colour_head.gate.gate'] * F.conv2d(seg, cw, cb)
+        delta = out[:, -2:]
+        uv = torch.cat([torch.zeros(1, out.shape[1] - 2, img, img, dtype=dt), O.pixel_coords(img, dt)], 1)
+        colour = out + uv
+    else:                                                                      # attention.py:159-160: plain 1x1 conv
+        colour = F.conv2d(seg, P['att_process.colour_head.weight'], P['att_process.colour_head.bias'])
+        delta = None
     u = tape.uniform((B, 1, img, img), dt)                                     # attention.py:177-178
-    log_m_k, log_s_k, seeds, idxs = icsbp(colour, u, P['att_process.log_sigma'], K - 1)
+    log_m_k, log_s_k, seeds, idxs = icsbp(colour, u, P['att_process.log_sigma'], K - 1, getattr(cfg, 'kernel', 'gaussian'))
     # slot latents (:145-161); feat_head evaluated once -- identical values to the K recomputations
     f = conv_gn_relu(enc_feat, 'feat_head.0')
     f = F.conv2d(f, P['feat_head.1.weight'], P['feat_head.1.bias'])

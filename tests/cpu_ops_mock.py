@@ -148,9 +148,9 @@ def up2(x):
     return F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2.0, mode='nearest').permute(0, 2, 3, 1).contiguous()
 
 
-def icsbp(colour, u, log_sigma, K):
+def icsbp(colour, u, log_sigma, K, kernel='gaussian'):
     from oracle import models as M
-    log_m_k, log_s_k, seeds, idxs = M.icsbp(colour.permute(0, 3, 1, 2), u, log_sigma, K - 1)
+    log_m_k, log_s_k, seeds, idxs = M.icsbp(colour.permute(0, 3, 1, 2), u, log_sigma, K - 1, kernel)
     return torch.stack(log_m_k, 0), torch.stack(log_s_k[:K], 0).detach(), torch.stack(idxs, 0).int()
 
 

@@ -261,7 +261,10 @@ def test_variant_genesis_comp_symmetric_engine_matches_reference():
                                        ('variant_genesisv2_k4_klm_nodetach', dict(klm_loss=True, detach_mr_in_klm=False)),
                                        ('variant_genesisv2_k4_noprior', dict(autoreg_prior=False)),
                                        ('variant_genesis_k3_nocompprior', dict(comp_prior=False)),
-                                       ('variant_monet_k4_scope', dict(prior_mode='scope'))])
+                                       ('variant_monet_k4_scope', dict(prior_mode='scope')),
+                                       ('variant_genesisv2_k4_laplacian', dict(kernel='laplacian')),
+                                       ('variant_genesisv2_k4_epanechnikov', dict(kernel='epanechnikov')),
+                                       ('variant_genesisv2_k4_nosemiconv', dict(semiconv=False))])
 def test_flag_variants_engine_matches_reference(name, over):
     """Engine vs the reference goldens of the flag variants (ops.mask_kl for klm_loss; prior flags)."""
     import numpy as np
@@ -285,3 +288,35 @@ def test_flag_variants_engine_matches_reference(name, over):
         gd = params[str(n)].grad.detach().double().cpu().flatten()
         worst = max(worst, abs(gd.norm().item() - nrm) / (nrm + 1e-3 * gmax))
     assert worst <= 0.3, worst          # V2 per-tensor TF32 tolerance of DESIGN.md section 5
+
+
+@pytest.mark.parametrize('kernel', ['gaussian', 'laplacian', 'epanechnikov'])
+@pytest.mark.parametrize('K', [2, 6])
+def test_icsbp_kernel_types_match_oracle(kernel, K):
+    """icsbp_fwd/bwd_kernel<KT> (csrc/v2.cu) against the oracle's InstanceColouringSBP (pinned to the reference by the
+    variant goldens) on the same colours / uniform draws: seeds identical, log-masks, d colour, d log_sigma."""
+    from genesis_b200 import ops
+    from oracle import models as M
+    torch.manual_seed(K)
+    B, S, CD = 3, 32, 8
+    scale = torch.tensor([0.03, 0.3, 1.5])[torch.randint(0, 3, (B, S, S, 1))]
+    colour = scale * torch.randn(B, S, S, CD)
+    u = torch.rand(B, 1, S, S)
+    sigma0 = {'gaussian': 1.0 / (K * 0.6931), 'laplacian': 1.0 / (K ** 0.5 * 0.6931), 'epanechnikov': 2.0 / K}[kernel]
+    ls = torch.tensor(sigma0, dtype=torch.float64).log()
+    c64 = colour.double().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    ls64 = ls.clone().requires_grad_(True)
+    log_m_k, log_s_k, seeds, idxs = M.icsbp(c64, u.double(), ls64, K - 1, kernel)
+    ref = torch.stack(log_m_k, 0)
+    w = torch.randn(ref.shape, dtype=torch.float64)
+    (ref * w).sum().backward()
+    cg = colour.cuda().requires_grad_(True)
+    lsg = ls.cuda().requires_grad_(True)
+    log_m, log_s, idx = ops.icsbp(cg, u.cuda(), lsg, K, kernel)
+    assert torch.equal(idx.cpu().long(), torch.stack(idxs, 0))
+    torch.testing.assert_close(log_m.detach().cpu().double(), ref.detach(), rtol=1e-4, atol=2e-4)
+    (log_m * w.float().cuda()).sum().backward()
+    gref = c64.grad.permute(0, 2, 3, 1)
+    err = (cg.grad.cpu().double() - gref).norm() / gref.norm()
+    assert err < 1e-4, err
+    assert abs(lsg.grad.item() - ls64.grad.item()) <= 1e-4 * abs(ls64.grad.item()) + 1e-3

@@ -220,3 +220,18 @@ def test_monet_scope_prior_variant_host_logic(monkeypatch):
         sref = M.SAMPLE['monet']({k: v.detach() for k, v in m.state_dict().items()}, 2, O.NoiseTape(seed=4),
                                  M.make_cfg('monet', K_steps=3, img_size=64, prior_mode='scope'), training=False)
     np.testing.assert_allclose(img.numpy(), sref['image'].numpy(), atol=1e-5)
+
+
+@pytest.mark.parametrize('over', [dict(kernel='laplacian'), dict(kernel='epanechnikov'), dict(semiconv=False)],
+                         ids=['laplacian', 'epanechnikov', 'nosemiconv'])
+def test_genesisv2_attention_option_variants_host_logic(monkeypatch, over):
+    """InstanceColouringSBP options (reference modules/attention.py:138-160, 195-205): kernel type and the plain 1x1 colour head."""
+    m, (recon, losses, stats, att, comp), P, ref = run_plugin(monkeypatch, 'genesisv2', 4, 2, 'multid', **over)
+    np.testing.assert_allclose(losses['err'].detach().numpy(), ref['err'].detach().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(stack(stats['log_m_k']), stack(ref['log_m_k']), atol=1e-4)
+    np.testing.assert_allclose(att['colour'].detach().numpy(), ref['att']['colour'].detach().numpy(), atol=1e-5)
+    assert (att['delta'] is None) == (ref['att']['delta'] is None)
+    import util_parity as U
+    U.engine_total_loss(losses).backward()
+    M.total_loss(ref).backward()
+    check_grads(m, P, tol=5e-3)
