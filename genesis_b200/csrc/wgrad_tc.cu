@@ -302,13 +302,350 @@ bool make_plan(int N, int Hg, int Wg, int Cg, int Ht, int Wt, int Ct, int R, int
 
 }  // namespace wg
 
+
+// =====================================================================================================================
+// EXPERIMENTAL (G2_WGRAD_HALO=1; off by default, not yet run on a B200): the same weight gradient on a "halo" layout.
+// The kernel above re-loads one shifted G tile per tap (R*S loads of the same pixels through L2).  Here one CTA item is
+// (window of TH rows of one image, one 32-channel block of G): a single TMA box lands the zero-padded G window
+// [(TH+R-1) * Wp pixel rows][32 ch] and one box per 32-channel block of T lands [TH * Wp][32 ch] with the SAME row pitch
+// Wp = Wt + S - 1 (the Wp - Wt pad columns are out of bounds of T and arrive as zeros).  With flat pixel index p as the
+// MMA's K dimension every tap is a row shift of the resident window (tests/test_wgrad_halo_math.py):
+//     dW[tap] += G[toff : toff + F]^T  T[0 : F],     toff = (dh - dh_min) * Wp + (dw - dw_min),  F = TH * Wp,
+// and the four 32-row atoms of the M = 128 operand are four TAPS of one channel block: atoms are LBO bytes apart, so
+// LBO = 128 B stacks taps (dh, dw..dw+3) and LBO = Wp * 128 B stacks (dh..dh+3, dw) -- no data is duplicated.
+// Requires that the MN-major operand fetch applies the 128-byte swizzle to absolute shared-memory addresses (the K-major
+// path of igemm_halo.cu relies on the same property; tests/test_pending_next_round.py probes it for MN-major).
+namespace wgh {
+using namespace wg;
+
+constexpr int MAX_GRP = 12;          // M-groups per channel block (5x5: 7, 3x3: 3)
+
+struct Maps { CUtensorMap g; CUtensorMap t; };
+
+struct P {
+    float* ws;                       // [splits][ntaps][Cg][Ct]
+    int N, Ht, TH, Wp, win_per_img, windows, win_per_cta;
+    int Cg, Ct, ntaps, ngroups, cbs_per_cta, ncb;
+    int g_rows, dh_min, dw_min, ksteps;
+    int g_box_bytes, t_box_bytes;    // TMA transaction bytes per box
+    int g_buf, t_blk, t_buf;         // smem bytes: one G window (incl. slack), one T channel block, all T blocks
+    int slack_off, slack_bytes;      // zero-filled tail of each G buffer (the last taps' shifts and unused atoms read into it)
+    short grp_off[MAX_GRP], grp_lbo[MAX_GRP], grp_n[MAX_GRP], grp_tap[MAX_GRP][4];   // rows, rows, valid atoms, tap index per atom
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* sm = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    uint8_t* sG = sm;                                   // 2 x g_buf
+    uint8_t* sT = sm + 2 * p.g_buf;                     // 2 x t_buf
+    uint64_t* full = reinterpret_cast<uint64_t*>(sT + 2 * p.t_buf);
+    uint64_t* empty = full + 2;
+    uint64_t* accf = empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accf + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = blockIdx.x;
+    const int cb_begin = blockIdx.y * p.cbs_per_cta;
+    const int ncb = min(p.cbs_per_cta, p.ncb - cb_begin);
+    const int w_begin = split * p.win_per_cta;
+    const int nwin = max(0, min(p.win_per_cta, p.windows - w_begin));
+    const int nitems = nwin * ncb;
+
+    // zero the slack rows behind both G windows (never written by TMA; read by shifted / unused atoms: must be finite)
+    for (int i = threadIdx.x * 16; i < p.slack_bytes; i += blockDim.x * 16) {
+        *reinterpret_cast<uint4*>(sG + p.slack_off + i) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(sG + p.g_buf + p.slack_off + i) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < 2; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+            mbar_init(accf, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        int it = 0;
+        for (int w = 0; w < nwin; ++w) {
+            const int win = w_begin + w;
+            const int n = win / p.win_per_img;
+            const int h0 = (win - n * p.win_per_img) * p.TH;
+            for (int c = 0; c < ncb; ++c, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                if (elect_one()) {
+                    mbar_expect_tx(&full[buf], (uint32_t)(p.g_box_bytes + (BN / 32) * p.t_box_bytes));
+                    tma_load_4d(sG + buf * p.g_buf, &maps.g, &full[buf], (cb_begin + c) * 32, p.dw_min, h0 + p.dh_min, n);
+#pragma unroll
+                    for (int j = 0; j < BN / 32; ++j)
+                        tma_load_4d(sT + buf * p.t_buf + j * p.t_blk, &maps.t, &full[buf], j * 32, 0, h0, n);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        int it = 0;
+        for (int w = 0; w < nwin; ++w) {
+            for (int c = 0; c < ncb; ++c, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&full[buf], (uint32_t)(it >> 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t bdesc = make_desc_mn_sw128(smem_u32(sT + buf * p.t_buf), (uint32_t)p.t_blk);
+                const uint32_t gbase = smem_u32(sG + buf * p.g_buf);
+                if (elect_one()) {
+                    for (int g = 0; g < p.ngroups; ++g) {
+                        const uint64_t adesc = make_desc_mn_sw128(gbase + (uint32_t)p.grp_off[g] * 128u, (uint32_t)p.grp_lbo[g] * 128u);
+                        const uint32_t d = tmem_base + (uint32_t)((c * p.ngroups + g) * BN);
+                        for (int kk = 0; kk < p.ksteps; ++kk)        // 8 pixel rows (1024 B = 64 descriptor units) per instruction
+                            umma_tf32(d, adesc + 64 * kk, bdesc + 64 * kk, idesc, (w > 0 || kk > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty[buf]);
+                }
+                __syncwarp();
+            }
+        }
+        if (elect_one()) umma_commit(accf);
+        __syncwarp();
+    } else {
+        const int q = warp & 3;                  // TMEM lane quarter == atom (tap) index within the M-group
+        mbar_wait(accf, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float* wsp = p.ws + (long)split * p.ntaps * p.Cg * p.Ct;
+        for (int c = 0; c < ncb; ++c) {
+            for (int g = 0; g < p.ngroups; ++g) {
+                const bool valid = q < p.grp_n[g];
+                const int tap = valid ? p.grp_tap[g][q] : 0;
+                const int a = (cb_begin + c) * 32 + lane;
+                float* dst = wsp + ((long)tap * p.Cg + a) * p.Ct;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((c * p.ngroups + g) * BN + c0), v);
+                    if (valid) {
+                        if (nitems == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = 0u;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<uint4*>(dst + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
+struct HPlan {
+    int TH, Wp, g_rows, win_per_img, windows, ngroups, cbs_per_cta, grid_y, splits, wpc, slack_rows, ksteps;
+    int g_buf, t_blk, t_buf, smem;
+    short grp_off[MAX_GRP], grp_lbo[MAX_GRP], grp_n[MAX_GRP], grp_tap[MAX_GRP][4];
+};
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// Tap groups of one channel block: rows of four consecutive dw (LBO = 1 pixel row); what is left of each filter row is
+// stacked along dh (LBO = Wp rows) when that needs fewer groups than short row groups; a group of one tap uses LBO = 1 row.
+int make_groups(int R, int S, int Wp, HPlan* pl) {
+    int ng = 0;
+    auto add = [&](int off, int lbo, int n, const int* taps) {
+        if (ng >= MAX_GRP) { ng = MAX_GRP + 1; return; }
+        pl->grp_off[ng] = (short)off; pl->grp_lbo[ng] = (short)lbo; pl->grp_n[ng] = (short)n;
+        for (int j = 0; j < 4; ++j) pl->grp_tap[ng][j] = (short)(j < n ? taps[j] : 0);
+        ++ng;
+    };
+    const int rem = S % 4;
+    for (int r = 0; r < R && ng <= MAX_GRP; ++r)
+        for (int s0 = 0; s0 + 4 <= S; s0 += 4) {
+            const int taps[4] = {r * S + s0, r * S + s0 + 1, r * S + s0 + 2, r * S + s0 + 3};
+            add(r * Wp + s0, 1, 4, taps);
+        }
+    if (rem) {
+        const int col_groups = rem * ((R + 3) / 4);
+        if (col_groups < R) {
+            for (int s = S - rem; s < S; ++s)
+                for (int r0 = 0; r0 < R && ng <= MAX_GRP; r0 += 4) {
+                    const int n = R - r0 < 4 ? R - r0 : 4;
+                    int taps[4] = {0, 0, 0, 0};
+                    for (int j = 0; j < n; ++j) taps[j] = (r0 + j) * S + s;
+                    add(r0 * Wp + s, n == 1 ? 1 : Wp, n, taps);
+                }
+        } else {
+            for (int r = 0; r < R && ng <= MAX_GRP; ++r) {
+                int taps[4] = {0, 0, 0, 0};
+                for (int j = 0; j < rem; ++j) taps[j] = r * S + (S - rem) + j;
+                add(r * Wp + (S - rem), 1, rem, taps);
+            }
+        }
+    }
+    return ng;
+}
+
+bool make_hplan(int N, int Hg, int Wg, int Cg, int Ht, int Wt, int Ct, int R, int S, int stride, HPlan* pl) {
+    if (stride != 1 || Cg % 32 != 0 || !(Ct == 32 || Ct == 64 || Ct == 128)) return false;
+    if (R * S < 4 || R * S > 32) return false;                   // 1x1 / tiny filters: the tile kernel packs channel blocks instead
+    if ((long)Ht * Wt < 256) return false;
+    const int budget = 212 * 1024;
+    long best_cost = -1;
+    HPlan cand;
+    // pitch candidates: the exact window width, or rounded up to 4 / 8 pixels (any TH then gives whole 8-row K steps)
+    for (int align = 1; align <= 8; align *= 2) {
+        const int Wp = round_up(Wt + S - 1, align);
+        if (align == 2 || Wp > 256) continue;
+        cand = *pl;
+        cand.Wp = Wp;
+        cand.ngroups = make_groups(R, S, Wp, &cand);
+        if (cand.ngroups > MAX_GRP || cand.ngroups * Ct > 512) return false;
+        int max_row = 0;            // furthest first row of any atom, valid or not
+        for (int g = 0; g < cand.ngroups; ++g) {
+            const int r = cand.grp_off[g] + 3 * cand.grp_lbo[g];
+            if (r > max_row) max_row = r;
+        }
+        for (int TH = (Ht < 64 ? Ht : 64); TH >= 2; --TH) {
+            if ((TH * Wp) % 8) continue;
+            const int g_rows = TH + R - 1;
+            if (g_rows > 256) continue;
+            const int slack = max_row + TH * Wp - g_rows * Wp;      // rows read past the window by the furthest atom
+            const int slack_rows = round_up(slack > 0 ? slack : 0, 8) + 8;
+            const int g_buf = round_up((g_rows * Wp + slack_rows) * 128, 1024);
+            const int t_blk = round_up(TH * Wp * 128, 1024);
+            const int t_buf = (Ct / 32) * t_blk;
+            const int smem = 2 * (g_buf + t_buf) + 1024 + 256;
+            if (smem > budget) continue;
+            // cost ~ MMA K rows issued per image and group, plus the halo rows of the G loads at a quarter weight
+            const long cost = (long)g2_cdiv(Ht, TH) * (4L * TH * Wp + (long)(R - 1) * Wp);
+            if (best_cost < 0 || cost < best_cost) {
+                best_cost = cost;
+                cand.TH = TH; cand.g_rows = g_rows; cand.slack_rows = slack_rows; cand.g_buf = g_buf; cand.t_blk = t_blk;
+                cand.t_buf = t_buf; cand.smem = smem;
+                *pl = cand;
+            }
+        }
+    }
+    if (best_cost < 0) return false;
+    const int Wp = pl->Wp;
+    pl->ksteps = pl->TH * Wp / 8;
+    pl->win_per_img = g2_cdiv(Ht, pl->TH);
+    pl->windows = N * pl->win_per_img;
+    const int ncb = Cg / 32;
+    const int max_cbs = 512 / (pl->ngroups * Ct);
+    pl->grid_y = g2_cdiv(ncb, max_cbs);
+    pl->cbs_per_cta = g2_cdiv(ncb, pl->grid_y);
+    int splits = 148 / pl->grid_y;
+    if (splits < 1) splits = 1;
+    if (splits > pl->windows) splits = pl->windows;
+    pl->wpc = g2_cdiv(pl->windows, splits);
+    pl->splits = g2_cdiv(pl->windows, pl->wpc);
+    return true;
+}
+
+bool enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("G2_WGRAD_HALO"); on = (e && e[0] == '1') ? 1 : 0; }
+    return on == 1;
+}
+
+}  // namespace wgh
+
 extern "C" {
 
 // Bytes of workspace g2_conv_wgrad_tf32 needs for this problem, or 0 if the shape is not supported.
 long g2_conv_wgrad_tf32_workspace(int N, int Hg, int Wg, int Cg, int Ht, int Wt, int Ct, int R, int S, int stride) {
     wg::Plan pl;
     if (!wg::make_plan(N, Hg, Wg, Cg, Ht, Wt, Ct, R, S, stride, &pl)) return 0;
-    return (long)pl.splits * R * S * Cg * Ct * (long)sizeof(float);
+    int splits = pl.splits;
+    wgh::HPlan hp;
+    if (wgh::enabled() && wgh::make_hplan(N, Hg, Wg, Cg, Ht, Wt, Ct, R, S, stride, &hp) && hp.splits > splits) splits = hp.splits;
+    return (long)splits * R * S * Cg * Ct * (long)sizeof(float);
+}
+
+// Host-only: the halo plan of a problem (for the CPU replay test).  out[0..15] = supported, TH, Wp, g_rows, win_per_img,
+// windows, ngroups, cbs_per_cta, grid_y, splits, windows per CTA, slack rows, ksteps, g_buf, t_blk, smem; then per group
+// 7 ints: first row, LBO in rows, valid atoms, tap of atom 0..3.  Returns the number of ints written.
+int g2_conv_wgrad_halo_plan(int N, int Hg, int Wg, int Cg, int Ht, int Wt, int Ct, int R, int S, int stride, int* out) {
+    wgh::HPlan hp;
+    memset(&hp, 0, sizeof(hp));
+    const bool ok = wgh::make_hplan(N, Hg, Wg, Cg, Ht, Wt, Ct, R, S, stride, &hp);
+    out[0] = ok ? 1 : 0;
+    if (!ok) return 1;
+    const int head[15] = {hp.TH, hp.Wp, hp.g_rows, hp.win_per_img, hp.windows, hp.ngroups, hp.cbs_per_cta, hp.grid_y, hp.splits,
+                          hp.wpc, hp.slack_rows, hp.ksteps, hp.g_buf, hp.t_blk, hp.smem};
+    for (int i = 0; i < 15; ++i) out[1 + i] = head[i];
+    int n = 16;
+    for (int g = 0; g < hp.ngroups; ++g) {
+        out[n++] = hp.grp_off[g]; out[n++] = hp.grp_lbo[g]; out[n++] = hp.grp_n[g];
+        for (int j = 0; j < 4; ++j) out[n++] = hp.grp_tap[g][j];
+    }
+    return n;
+}
+
+static int wgrad_halo_launch(const wgh::HPlan& hp, const float* g, const float* t, float* dw, float* ws, int N, int Hg, int Wg,
+                             int Cg, int Ht, int Wt, int Ct, int R, int S, int pad, long s_tap, long s_a, long s_b, int a_lim,
+                             int b_lim, int accumulate, cudaStream_t stream) {
+    wgh::Maps maps;
+    memset(&maps, 0, sizeof(maps));
+    wgh::P p;
+    memset(&p, 0, sizeof(p));
+    p.ws = ws; p.N = N; p.Ht = Ht; p.TH = hp.TH; p.Wp = hp.Wp; p.win_per_img = hp.win_per_img; p.windows = hp.windows;
+    p.win_per_cta = hp.wpc; p.Cg = Cg; p.Ct = Ct; p.ntaps = R * S; p.ngroups = hp.ngroups; p.cbs_per_cta = hp.cbs_per_cta;
+    p.ncb = Cg / 32; p.g_rows = hp.g_rows; p.dh_min = -pad; p.dw_min = -pad; p.ksteps = hp.ksteps;
+    p.g_box_bytes = hp.g_rows * hp.Wp * 128; p.t_box_bytes = hp.TH * hp.Wp * 128;
+    p.g_buf = hp.g_buf; p.t_blk = hp.t_blk; p.t_buf = hp.t_buf;
+    p.slack_off = hp.g_rows * hp.Wp * 128; p.slack_bytes = hp.g_buf - p.slack_off;
+    for (int i = 0; i < hp.ngroups; ++i) {
+        p.grp_off[i] = hp.grp_off[i]; p.grp_lbo[i] = hp.grp_lbo[i]; p.grp_n[i] = hp.grp_n[i];
+        for (int j = 0; j < 4; ++j) p.grp_tap[i][j] = hp.grp_tap[i][j];
+    }
+    {
+        const cuuint32_t box[4] = {32, (cuuint32_t)hp.Wp, (cuuint32_t)hp.TH, 1};
+        const cuuint64_t dims[4] = {(cuuint64_t)Ct, (cuuint64_t)Wt, (cuuint64_t)Ht, (cuuint64_t)N};
+        const cuuint64_t str[3] = {(cuuint64_t)Ct * 4, (cuuint64_t)Wt * Ct * 4, (cuuint64_t)Ht * Wt * Ct * 4};
+        if (!wg::encode4(&maps.t, t, dims, str, box)) return G2_ERR_UNSUPPORTED;
+    }
+    {
+        const cuuint32_t box[4] = {32, (cuuint32_t)hp.Wp, (cuuint32_t)hp.g_rows, 1};
+        const cuuint64_t dims[4] = {(cuuint64_t)Cg, (cuuint64_t)Wg, (cuuint64_t)Hg, (cuuint64_t)N};
+        const cuuint64_t str[3] = {(cuuint64_t)Cg * 4, (cuuint64_t)Wg * Cg * 4, (cuuint64_t)Hg * Wg * Cg * 4};
+        if (!wg::encode4(&maps.g, g, dims, str, box)) return G2_ERR_UNSUPPORTED;
+    }
+    dim3 grid((unsigned)hp.splits, (unsigned)hp.grid_y, 1);
+    cudaError_t e = cudaSuccess;
+#define WGH_LAUNCH(BN)                                                                                                     \
+    {                                                                                                                      \
+        static int attr = 0;                                                                                               \
+        if (attr < hp.smem) {                                                                                              \
+            e = cudaFuncSetAttribute(wgh::wgrad_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, hp.smem);         \
+            if (e != cudaSuccess) return (int)e;                                                                           \
+            attr = hp.smem;                                                                                                \
+        }                                                                                                                  \
+        wgh::wgrad_halo_kernel<BN><<<grid, 192, hp.smem, stream>>>(maps, p);                                                   \
+    }
+    if (Ct == 32) WGH_LAUNCH(32) else if (Ct == 64) WGH_LAUNCH(64) else WGH_LAUNCH(128)
+#undef WGH_LAUNCH
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    const long total = (long)R * S * Cg * Ct;
+    long blocks = (total + 255) / 256;
+    if (blocks > 148L * 8) blocks = 148L * 8;
+    wg::wgrad_reduce_kernel<<<(int)blocks, 256, 0, stream>>>(ws, dw, hp.splits, R * S, Cg, Ct, s_tap, s_a, s_b, a_lim, b_lim, accumulate);
+    G2_LAUNCH_RET();
 }
 
 // Same contract as g2_conv_wgrad_f32 (TF32 operands, fp32 accumulation); `ws` is caller-owned scratch of
@@ -322,6 +659,12 @@ static int wgrad_impl(const float* g, const float* t, float* dw, float* ws, int 
     if (!make_plan(N, Hg, Wg, Cg, Ht, Wt, Ct, R, S, stride, &pl)) return G2_ERR_UNSUPPORTED;
     G2_CHECK_ARG((reinterpret_cast<uintptr_t>(g) & 15) == 0 && (reinterpret_cast<uintptr_t>(t) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(ws) & 15) == 0);
+    if (wgh::enabled()) {
+        wgh::HPlan hp;
+        if (wgh::make_hplan(N, Hg, Wg, Cg, Ht, Wt, Ct, R, S, stride, &hp))
+            return wgrad_halo_launch(hp, g, t, dw, ws, N, Hg, Wg, Cg, Ht, Wt, Ct, R, S, pad, s_tap, s_a, s_b, a_lim, b_lim,
+                                     accumulate, stream);
+    }
     Maps maps;
     memset(&maps, 0, sizeof(maps));
     P p;

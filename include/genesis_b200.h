@@ -177,6 +177,9 @@ int g2_conv_igemm_tf32(const float* in, const float* w, const float* bias, float
 /* Weight gradient on the tensor cores (wgrad_tc.cu; MN-major operands): same contract as g2_conv_wgrad_f32 plus
  * a caller-owned workspace of g2_conv_wgrad_tf32_workspace(...) bytes (0 = shape not supported). */
 long g2_conv_wgrad_tf32_workspace(int N, int Hg, int Wg, int Cg, int Ht, int Wt, int Ct, int R, int S, int stride);
+/* Host-only query: plan of the experimental halo weight-gradient kernel (G2_WGRAD_HALO=1; csrc/wgrad_tc.cu, namespace wgh) for
+ * the CPU replay test; out needs 16 + 7 * 12 ints.  Returns the number of ints written (out[0] = 0: shape not covered). */
+int g2_conv_wgrad_halo_plan(int N, int Hg, int Wg, int Cg, int Ht, int Wt, int Ct, int R, int S, int stride, int* out);
 int g2_conv_wgrad_tf32(const float* g, const float* t, float* dw, float* ws, int N, int Hg, int Wg, int Cg, int Ht,
                        int Wt, int Ct, int R, int S, int stride, int pad, int outT, g2_stream_t stream);
 /* C[M,N] = A[M,K] W[N,K]^T + bias[N] */

@@ -128,6 +128,24 @@ def test_persistent_halo_kernel_passes_the_halo_suite():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
+def test_halo_wgrad_kernel_passes_the_wgrad_suite():
+    """The experimental halo weight-gradient kernel (G2_WGRAD_HALO=1, read once per process; csrc/wgrad_tc.cu namespace wgh)
+    must pass the exactness tests of the tile kernel (stride-1 cases take the new path, the others fall through) and the
+    direct-gradient / engine parity tests; child process with the switch on.  Run the MN-major probe below first: the
+    kernel relies on exactly what it probes."""
+    import subprocess
+    import sys
+    env = dict(os.environ, G2_WGRAD_HALO='1')
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(here, 'test_tc_gpu.py'), '-x', '-q', '-m', 'gpu', '-k', 'wgrad'],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(here, 'test_direct_grad_gpu.py'),
+                        os.path.join(here, 'test_genesis_gpu.py'), '-x', '-q', '-m', 'gpu'],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_mn_major_operand_with_row_shift_and_overlapping_atoms():
     """Feasibility probe for the halo layout of the weight-gradient kernel: an MN-major TF32 A operand (pixels are the K
     dimension, SWIZZLE_128B_BASE32B) that (1) starts at an arbitrary pixel row of a resident window and (2) takes its four
