@@ -367,7 +367,11 @@ __global__ void __launch_bounds__(192, 1) conv_halo_persistent_kernel(const __gr
         h0 = th_i * p.TH; w0 = tw_i * p.TW; n0c = by * BN;
         rows_valid = min(p.TH, p.Hv - h0); cols_valid = min(p.TW, p.Wv - w0); imgs_valid = min(p.TNB, p.N - n0);
         m_tiles = (((imgs_valid - 1) * p.RH + rows_valid - 1) * p.Wp + cols_valid - 1) / 128 + 1;
-        nch = p.TNB > 1 ? 1 : min(p.nch, (rows_valid + p.span_h + p.ch_rows - 1) / p.ch_rows);
+        // Every item loads ALL chunks of its window, also the ones a bottom-edge tile does not need (they lie outside the
+        // image: TMA zero-fills them without touching memory).  Skipping them, as the one-item kernel above does, would
+        // leave their mbarriers one phase behind the (u >> 1) & 1 parity the next full item waits with, and that wait
+        // would pass on the stale phase (tests/test_persistent_protocol.py::test_skipping_chunks_breaks_the_parity_scheme).
+        nch = p.TNB > 1 ? 1 : p.nch;
     };
 
     if (warp == 0) {
@@ -458,6 +462,9 @@ __global__ void __launch_bounds__(192, 1) conv_halo_persistent_kernel(const __gr
                     __syncwarp();
                     if (!pp.b_resident && ++bi == STAGES) { bi = 0; bph ^= 1u; }
                 }
+                // chunks no tap needed (bottom-edge tiles) must have landed too before the window is handed back: the next
+                // load of this buffer re-arms their barriers
+                while (waited < nch) { mbar_wait(&fullA[buf * MAX_CHUNKS + waited], aph); ++waited; }
                 if (elect_one()) commit(&emptyA[buf]);           // window free when these MMAs retire
                 __syncwarp();
             }

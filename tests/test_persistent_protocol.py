@@ -32,8 +32,11 @@ class Bar(object):
 
 
 class Sim(object):
-    def __init__(self, n_items, cblocks, ntaps, stages, resident, nch, seed):
+    def __init__(self, n_items, cblocks, ntaps, stages, resident, nch, seed, nch_items=None, skip_unneeded=False):
         self.rng = random.Random(seed)
+        # nch_items[i]: chunks item i NEEDS (bottom-edge tiles need fewer); skip_unneeded: the producer loads only those
+        self.nch_items = nch_items or [nch] * n_items
+        self.skip_unneeded = skip_unneeded
         self.n_items, self.cblocks, self.ntaps, self.stages, self.resident, self.nch = n_items, cblocks, ntaps, stages, resident, nch
         self.t = 0.0
         self.events = []          # (time, seq, fn)
@@ -111,7 +114,7 @@ class Sim(object):
             for cb in range(self.cblocks):
                 buf = u & 1
                 yield (self.emptyA[buf], ((u >> 1) & 1) ^ 1)
-                for j in range(self.nch):
+                for j in range(self.nch_items[item] if self.skip_unneeded else self.nch):
                     self.tma_A(buf, j, (item, cb))
                 if self.resident:
                     if not b_loaded:
@@ -144,7 +147,8 @@ class Sim(object):
                         s, ph, btag = bi, bph, (it, cb, tap)
                     yield (self.fullB[s], ph)
                     # tap 0 stops one chunk short of the window's end; later taps (and a lone tap) reach the last chunk
-                    need = self.nch - 1 if (tap > 0 or self.ntaps == 1) else max(0, self.nch - 2)
+                    nn = self.nch_items[it]
+                    need = nn - 1 if (tap > 0 or self.ntaps == 1) else max(0, nn - 2)
                     while waited <= need:
                         yield (self.fullA[buf][waited], aph)
                         waited += 1
@@ -154,6 +158,9 @@ class Sim(object):
                         bi += 1
                         if bi == self.stages:
                             bi, bph = 0, bph ^ 1
+                while waited < (self.nch_items[it] if self.skip_unneeded else self.nch):     # chunks no tap needed have landed too
+                    yield (self.fullA[buf][waited], aph)
+                    waited += 1
                 self.commit(self.emptyA[buf])
                 u += 1
             done = self.accFull[acc]
@@ -249,3 +256,29 @@ def test_persistent_protocol(cfg, seed):
     sim.run()
     assert not sim.errors, sim.errors[:5]
     assert sim.drained == list(range(n_items))
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2])
+def test_ragged_items_with_all_chunks_loaded(seed):
+    """Bottom-edge tiles need fewer window chunks; the kernel loads all of them anyway (zero-filled by TMA)."""
+    nch_items = [4, 4, 2, 4, 3, 4, 4, 1, 4, 4]
+    sim = Sim(len(nch_items), 1, 9, 9, True, 4, seed, nch_items=nch_items)
+    sim.run()
+    assert not sim.errors, sim.errors[:5]
+    assert sim.drained == list(range(len(nch_items)))
+
+
+def test_skipping_chunks_breaks_the_parity_scheme():
+    """Why: if the producer skipped the chunks an item does not need (as the one-item kernel does), their barriers would fall
+    one phase behind the (u >> 1) & 1 parity of the next full item, whose wait then passes on the stale phase and the MMA
+    reads the previous window's chunk (or the protocol deadlocks).  The model must flag that policy."""
+    nch_items = [4, 4, 2, 4, 4, 4, 4, 4]
+    bad = 0
+    for seed in range(4):
+        sim = Sim(len(nch_items), 1, 9, 9, True, 4, seed, nch_items=nch_items, skip_unneeded=True)
+        try:
+            sim.run()
+            bad += bool(sim.errors)
+        except AssertionError:
+            bad += 1
+    assert bad == 4
