@@ -60,10 +60,14 @@ __device__ __forceinline__ float icsbp_alpha(float dist, float inv_sigma) {
     else return fmaxf(1.f - dist * inv_sigma, 0.f);
 }
 
-template <int KT>
+// DYN (`dynamic_K`, attention.py:168-169, 218-219): a step whose mask would hold fewer than 20 pixels ends the image's loop
+// BEFORE the mask is appended; the current scope becomes the last mask.  n_masks[b] = number of masks (<= K); the unused
+// slots k >= n_masks[b] are filled with -1e10 as GenesisV2.forward does for batches (genesisv2_config.py:126-131).
+template <int KT, bool DYN>
 __global__ void __launch_bounds__(IC_THREADS) icsbp_fwd_kernel(const float* __restrict__ colour, const float* __restrict__ u,
                                                                const float* __restrict__ log_sigma, float* __restrict__ log_m,
-                                                               float* __restrict__ log_s, int* __restrict__ seed_idx, int B, int P, int K) {
+                                                               float* __restrict__ log_s, int* __restrict__ seed_idx,
+                                                               int* __restrict__ n_masks, int B, int P, int K) {
     const int b = blockIdx.x, tid = threadIdx.x;
     const int ppt = (P + IC_THREADS - 1) / IC_THREADS;
     __shared__ float s_val[32];
@@ -76,6 +80,9 @@ __global__ void __launch_bounds__(IC_THREADS) icsbp_fwd_kernel(const float* __re
 #pragma unroll
     for (int j = 0; j < IC_MAXPPT; ++j) ls[j] = 0.f;
     const long KB = (long)B * P;
+    __shared__ float s_sum[32];
+    __shared__ float s_total;
+    int kf = K - 1;                       // index of the final mask (= scope)
     for (int k = 0; k < K - 1; ++k) {
         // ---- block argmax of u * scope (first maximum, as torch.argmax)
         float best = -1.f; int bi = 0x7fffffff;
@@ -108,6 +115,26 @@ __global__ void __launch_bounds__(IC_THREADS) icsbp_fwd_kernel(const float* __re
         __syncthreads();
         if (tid < CD) s_seed[tid] = __ldg(col + (long)s_best * CD + tid);
         __syncthreads();
+        if constexpr (DYN) {
+            // ---- would-be mask mass sum_p exp(log_s + log alpha); fewer than 20 pixels ends the loop (attention.py:218-219)
+            float part = 0.f;
+#pragma unroll
+            for (int j = 0; j < IC_MAXPPT; ++j) {
+                const int p = tid + j * IC_THREADS;
+                if (j < ppt && p < P) {
+                    const float4 c0 = g2_ldg4(col + (long)p * CD), c1 = g2_ldg4(col + (long)p * CD + 4);
+                    const float d0 = c0.x - s_seed[0], d1 = c0.y - s_seed[1], d2 = c0.z - s_seed[2], d3 = c0.w - s_seed[3];
+                    const float d4 = c1.x - s_seed[4], d5 = c1.y - s_seed[5], d6 = c1.z - s_seed[6], d7 = c1.w - s_seed[7];
+                    const float dist = ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3)) + ((d4 * d4 + d5 * d5) + (d6 * d6 + d7 * d7));
+                    const float a = fminf(fmaxf(icsbp_alpha<KT>(dist, inv_sigma), 0.01f), 0.99f);
+                    part += expf(ls[j] + logf(a));
+                }
+            }
+            part = g2_block_sum(part, s_sum);
+            if (tid == 0) s_total = part;
+            __syncthreads();
+            if (s_total < 20.f) { kf = k; break; }
+        }
         // ---- masks
 #pragma unroll
         for (int j = 0; j < IC_MAXPPT; ++j) {
@@ -130,8 +157,20 @@ __global__ void __launch_bounds__(IC_THREADS) icsbp_fwd_kernel(const float* __re
     for (int j = 0; j < IC_MAXPPT; ++j) {
         const int p = tid + j * IC_THREADS;
         if (j < ppt && p < P) {
-            log_s[(long)(K - 1) * KB + (long)b * P + p] = ls[j];
-            log_m[(long)(K - 1) * KB + (long)b * P + p] = ls[j];
+            log_s[(long)kf * KB + (long)b * P + p] = ls[j];
+            log_m[(long)kf * KB + (long)b * P + p] = ls[j];
+            if constexpr (DYN) {
+                for (int k2 = kf + 1; k2 < K; ++k2) {
+                    log_s[(long)k2 * KB + (long)b * P + p] = ls[j];
+                    log_m[(long)k2 * KB + (long)b * P + p] = -1e10f;
+                }
+            }
+        }
+    }
+    if constexpr (DYN) {
+        if (tid == 0) {
+            n_masks[b] = kf + 1;
+            for (int k2 = kf + 1; k2 < K - 1; ++k2) seed_idx[(long)k2 * B + b] = -1;
         }
     }
 }
@@ -147,8 +186,9 @@ template <int KT>
 __global__ void __launch_bounds__(IC_THREADS) icsbp_bwd_kernel(const float* __restrict__ colour, const float* __restrict__ log_sigma,
                                                                const int* __restrict__ seed_idx, const float* __restrict__ dlog_m,
                                                                float* __restrict__ dcolour, float* __restrict__ dlog_sigma_b,
-                                                               int B, int P, int K) {
+                                                               const int* __restrict__ n_masks, int B, int P, int Kmax) {
     const int b = blockIdx.x, tid = threadIdx.x;
+    const int K = n_masks ? __ldg(n_masks + b) : Kmax;         // dynamic_K: masks of this image; slots beyond it carry no gradient
     const int ppt = (P + IC_THREADS - 1) / IC_THREADS;
     __shared__ float s_seed[CD];
     __shared__ float s_red[32][CD + 1];
@@ -348,7 +388,7 @@ int g2_icsbp_fwd_f32(const float* colour, const float* u, const float* log_sigma
                      int B, int P, int K, int colour_dim, cudaStream_t stream) {
     G2_CHECK_ARG(colour && u && log_sigma && log_m && log_s && seed_idx && B > 0 && K >= 2);
     G2_CHECK_ARG(colour_dim == CD && P > 0 && P <= IC_THREADS * IC_MAXPPT);
-    icsbp_fwd_kernel<0><<<B, IC_THREADS, 0, stream>>>(colour, u, log_sigma, log_m, log_s, seed_idx, B, P, K);
+    icsbp_fwd_kernel<0, false><<<B, IC_THREADS, 0, stream>>>(colour, u, log_sigma, log_m, log_s, seed_idx, nullptr, B, P, K);
     G2_LAUNCH_RET();
 }
 
@@ -357,9 +397,9 @@ int g2_icsbp_kernel_fwd_f32(const float* colour, const float* u, const float* lo
                             int B, int P, int K, int colour_dim, int kernel_type, cudaStream_t stream) {
     G2_CHECK_ARG(colour && u && log_sigma && log_m && log_s && seed_idx && B > 0 && K >= 2);
     G2_CHECK_ARG(colour_dim == CD && P > 0 && P <= IC_THREADS * IC_MAXPPT && kernel_type >= 0 && kernel_type <= 2);
-    if (kernel_type == 0) icsbp_fwd_kernel<0><<<B, IC_THREADS, 0, stream>>>(colour, u, log_sigma, log_m, log_s, seed_idx, B, P, K);
-    else if (kernel_type == 1) icsbp_fwd_kernel<1><<<B, IC_THREADS, 0, stream>>>(colour, u, log_sigma, log_m, log_s, seed_idx, B, P, K);
-    else icsbp_fwd_kernel<2><<<B, IC_THREADS, 0, stream>>>(colour, u, log_sigma, log_m, log_s, seed_idx, B, P, K);
+    if (kernel_type == 0) icsbp_fwd_kernel<0, false><<<B, IC_THREADS, 0, stream>>>(colour, u, log_sigma, log_m, log_s, seed_idx, nullptr, B, P, K);
+    else if (kernel_type == 1) icsbp_fwd_kernel<1, false><<<B, IC_THREADS, 0, stream>>>(colour, u, log_sigma, log_m, log_s, seed_idx, nullptr, B, P, K);
+    else icsbp_fwd_kernel<2, false><<<B, IC_THREADS, 0, stream>>>(colour, u, log_sigma, log_m, log_s, seed_idx, nullptr, B, P, K);
     G2_LAUNCH_RET();
 }
 
@@ -367,7 +407,7 @@ int g2_icsbp_bwd_f32(const float* colour, const float* log_sigma, const int* see
                      float* dlog_sigma_b, int B, int P, int K, int colour_dim, cudaStream_t stream) {
     G2_CHECK_ARG(colour && log_sigma && seed_idx && dlog_m && dcolour && dlog_sigma_b && B > 0 && K >= 2);
     G2_CHECK_ARG(colour_dim == CD && P > 0 && P <= IC_THREADS * IC_MAXPPT);
-    icsbp_bwd_kernel<0><<<B, IC_THREADS, 0, stream>>>(colour, log_sigma, seed_idx, dlog_m, dcolour, dlog_sigma_b, B, P, K);
+    icsbp_bwd_kernel<0><<<B, IC_THREADS, 0, stream>>>(colour, log_sigma, seed_idx, dlog_m, dcolour, dlog_sigma_b, nullptr, B, P, K);
     G2_LAUNCH_RET();
 }
 
@@ -375,9 +415,33 @@ int g2_icsbp_kernel_bwd_f32(const float* colour, const float* log_sigma, const i
                             float* dlog_sigma_b, int B, int P, int K, int colour_dim, int kernel_type, cudaStream_t stream) {
     G2_CHECK_ARG(colour && log_sigma && seed_idx && dlog_m && dcolour && dlog_sigma_b && B > 0 && K >= 2);
     G2_CHECK_ARG(colour_dim == CD && P > 0 && P <= IC_THREADS * IC_MAXPPT && kernel_type >= 0 && kernel_type <= 2);
-    if (kernel_type == 0) icsbp_bwd_kernel<0><<<B, IC_THREADS, 0, stream>>>(colour, log_sigma, seed_idx, dlog_m, dcolour, dlog_sigma_b, B, P, K);
-    else if (kernel_type == 1) icsbp_bwd_kernel<1><<<B, IC_THREADS, 0, stream>>>(colour, log_sigma, seed_idx, dlog_m, dcolour, dlog_sigma_b, B, P, K);
-    else icsbp_bwd_kernel<2><<<B, IC_THREADS, 0, stream>>>(colour, log_sigma, seed_idx, dlog_m, dcolour, dlog_sigma_b, B, P, K);
+    if (kernel_type == 0) icsbp_bwd_kernel<0><<<B, IC_THREADS, 0, stream>>>(colour, log_sigma, seed_idx, dlog_m, dcolour, dlog_sigma_b, nullptr, B, P, K);
+    else if (kernel_type == 1) icsbp_bwd_kernel<1><<<B, IC_THREADS, 0, stream>>>(colour, log_sigma, seed_idx, dlog_m, dcolour, dlog_sigma_b, nullptr, B, P, K);
+    else icsbp_bwd_kernel<2><<<B, IC_THREADS, 0, stream>>>(colour, log_sigma, seed_idx, dlog_m, dcolour, dlog_sigma_b, nullptr, B, P, K);
+    G2_LAUNCH_RET();
+}
+
+// dynamic_K variant (models/genesisv2_config.py:118-137, modules/attention.py:168-169, 218-219): as g2_icsbp_kernel_*_f32 plus
+// n_masks [B] (int32): masks produced for each image; log_m slots k >= n_masks[b] hold -1e10, seed_idx entries beyond the
+// last step hold -1.
+int g2_icsbp_dynamic_fwd_f32(const float* colour, const float* u, const float* log_sigma, float* log_m, float* log_s, int* seed_idx,
+                             int* n_masks, int B, int P, int K, int colour_dim, int kernel_type, cudaStream_t stream) {
+    G2_CHECK_ARG(colour && u && log_sigma && log_m && log_s && seed_idx && n_masks && B > 0 && K >= 2);
+    G2_CHECK_ARG(colour_dim == CD && P > 0 && P <= IC_THREADS * IC_MAXPPT && kernel_type >= 0 && kernel_type <= 2);
+    if (kernel_type == 0) icsbp_fwd_kernel<0, true><<<B, IC_THREADS, 0, stream>>>(colour, u, log_sigma, log_m, log_s, seed_idx, n_masks, B, P, K);
+    else if (kernel_type == 1) icsbp_fwd_kernel<1, true><<<B, IC_THREADS, 0, stream>>>(colour, u, log_sigma, log_m, log_s, seed_idx, n_masks, B, P, K);
+    else icsbp_fwd_kernel<2, true><<<B, IC_THREADS, 0, stream>>>(colour, u, log_sigma, log_m, log_s, seed_idx, n_masks, B, P, K);
+    G2_LAUNCH_RET();
+}
+
+int g2_icsbp_dynamic_bwd_f32(const float* colour, const float* log_sigma, const int* seed_idx, const int* n_masks, const float* dlog_m,
+                             float* dcolour, float* dlog_sigma_b, int B, int P, int K, int colour_dim, int kernel_type,
+                             cudaStream_t stream) {
+    G2_CHECK_ARG(colour && log_sigma && seed_idx && n_masks && dlog_m && dcolour && dlog_sigma_b && B > 0 && K >= 2);
+    G2_CHECK_ARG(colour_dim == CD && P > 0 && P <= IC_THREADS * IC_MAXPPT && kernel_type >= 0 && kernel_type <= 2);
+    if (kernel_type == 0) icsbp_bwd_kernel<0><<<B, IC_THREADS, 0, stream>>>(colour, log_sigma, seed_idx, dlog_m, dcolour, dlog_sigma_b, n_masks, B, P, K);
+    else if (kernel_type == 1) icsbp_bwd_kernel<1><<<B, IC_THREADS, 0, stream>>>(colour, log_sigma, seed_idx, dlog_m, dcolour, dlog_sigma_b, n_masks, B, P, K);
+    else icsbp_bwd_kernel<2><<<B, IC_THREADS, 0, stream>>>(colour, log_sigma, seed_idx, dlog_m, dcolour, dlog_sigma_b, n_masks, B, P, K);
     G2_LAUNCH_RET();
 }
 

@@ -100,8 +100,6 @@ class GenesisV2(nn.Module, _g.NoiseMixin):
         self.debug = cfg.debug
         self.multi_gpu = cfg.multi_gpu
         self.img_size = cfg.img_size
-        if cfg.dynamic_K:
-            raise NotImplementedError('engine covers GENESIS-V2 with fixed K (SURVEY.md section 8f.4)')
         self.semiconv = bool(cfg.semiconv)
         if cfg.feat_dim != 64:
             raise NotImplementedError('engine is tiled for feat_dim=64')
@@ -167,8 +165,21 @@ class GenesisV2(nn.Module, _g.NoiseMixin):
         else:                                   # plain 1x1 colour head: no coordinate offsets, delta = None (attention.py:174-178)
             out = None
             colour = ops.conv2d(seg, ch.weight, ch.bias, 1, 0)
-        u = self._uniform((B, 1, S, S), x)
-        log_m, log_s, seed_idx = ops.icsbp(colour, u, ap.log_sigma, K, ap.kernel)            # [K,B,1,H,W]
+        n_seeds = K - 1
+        if self.dynamic_K:
+            # reference :118-137: the attention runs image by image (one [1,1,H,W] uniform draw each) and stops early once a
+            # mask would hold fewer than 20 pixels; batches are padded with -1e10 masks up to K_steps, a single image keeps
+            # only the masks it produced (the number of slots then decides every shape downstream: one host sync)
+            u = torch.cat([self._uniform((1, 1, S, S), x) for _ in range(B)], 0)
+            log_m, log_s, seed_idx, n_masks = ops.icsbp_dynamic(colour, u, ap.log_sigma, K, ap.kernel)
+            if B == 1:
+                k_eff = int(n_masks.item())
+                n_seeds = min(k_eff, K - 1)          # the seed of the step that stopped the loop is still recorded (attention.py:193)
+                K = k_eff
+                log_m, log_s = log_m[:K], log_s[:K]
+        else:
+            u = self._uniform((B, 1, S, S), x)
+            log_m, log_s, seed_idx = ops.icsbp(colour, u, ap.log_sigma, K, ap.kernel)        # [K,B,1,H,W]
         # --- slot latents (reference genesisv2_config.py:145-161), feat_head evaluated once
         f = H.conv_norm_relu(self.feat_head[0], enc_feat, 'gn')
         f = ops.conv2d(f, self.feat_head[1].weight, self.feat_head[1].bias, 1, 0)            # [B,H,W,128]
@@ -225,11 +236,13 @@ class GenesisV2(nn.Module, _g.NoiseMixin):
             inst_r = torch.argmax(log_m_r.squeeze(2).permute(1, 0, 2, 3), dim=1)
             colour_nchw = colour.permute(0, 3, 1, 2)
             flat = colour.reshape(B, S * S, cd)
-            seeds = [flat[torch.arange(B, device=x.device), seed_idx[k].long()] for k in range(K - 1)]
-        stats = AttrDict(recon=recon, log_m_k=log_m_k, log_s_k=list(log_s.unbind(0)), x_r_k=x_r_k,
+            seeds = [flat[torch.arange(B, device=x.device), seed_idx[k].long().clamp_min(0)] for k in range(n_seeds)]
+        batched_dynamic = self.dynamic_K and B > 1          # reference :121-122: log_s_k and att_stats are None on that path
+        stats = AttrDict(recon=recon, log_m_k=log_m_k, log_s_k=(None if batched_dynamic else list(log_s.unbind(0))), x_r_k=x_r_k,
                          log_m_r_k=log_m_r_k, mx_r_k=mx_r_k, instance_seg=inst, instance_seg_r=inst_r)
-        att_stats = AttrDict(colour=colour_nchw, delta=(out.permute(0, 3, 1, 2)[:, -2:] if out is not None else None),
-                             seeds=seeds, seed_idx=seed_idx)
+        att_stats = None if batched_dynamic else AttrDict(
+            colour=colour_nchw, delta=(out.permute(0, 3, 1, 2)[:, -2:] if out is not None else None), seeds=seeds,
+            seed_idx=seed_idx[:n_seeds])
         comp_stats = AttrDict(mu_k=mu_k, sigma_k=sigma_k, z_k=z_k, kl_l_k=[], pmu_k=pmu, psigma_k=psig)
         if self.debug:
             _g.check_log_masks(log_m_k)

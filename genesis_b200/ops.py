@@ -810,6 +810,40 @@ class _ICSBP(Function):
 ICSBP_KERNELS = {'gaussian': 0, 'laplacian': 1, 'epanechnikov': 2}       # reference modules/attention.py:146-153
 
 
+class _ICSBPDynamic(Function):
+    """dynamic_K form of _ICSBP: also returns n_masks [B] (int32); log_m slots k >= n_masks[b] hold -1e10."""
+
+    @staticmethod
+    def forward(ctx, colour, u, log_sigma, K, kernel):
+        colour, u = _c(colour), _c(u)
+        B, H, W, CD = colour.shape
+        log_m = _new(colour, K, B, 1, H, W)
+        log_s = _new(colour, K, B, 1, H, W)
+        idx = torch.empty((K - 1, B), device=colour.device, dtype=torch.int32)
+        n = torch.empty((B,), device=colour.device, dtype=torch.int32)
+        ls = log_sigma.detach().reshape(1).float().contiguous()
+        kt = ICSBP_KERNELS[kernel]
+        _call('g2_icsbp_dynamic_fwd_f32', colour, u, ls, log_m, log_s, idx, n, B, H * W, K, CD, kt)
+        ctx.save_for_backward(colour, ls, idx, n)
+        ctx.K, ctx.kt = K, kt
+        ctx.ls_dtype = log_sigma.dtype
+        ctx.mark_non_differentiable(log_s, idx, n)
+        return log_m, log_s, idx, n
+
+    @staticmethod
+    def backward(ctx, dlog_m, _dls, _didx, _dn):
+        colour, ls, idx, n = ctx.saved_tensors
+        B, H, W, CD = colour.shape
+        dcol = torch.empty_like(colour)
+        dsig = _new(colour, B)
+        _call('g2_icsbp_dynamic_bwd_f32', colour, ls, idx, n, _c(dlog_m), dcol, dsig, B, H * W, ctx.K, CD, ctx.kt)
+        return dcol, None, dsig.sum().reshape(()).to(ctx.ls_dtype), None, None
+
+
+def icsbp_dynamic(colour, u, log_sigma, K, kernel='gaussian'):
+    return _ICSBPDynamic.apply(colour, u, log_sigma, K, kernel)
+
+
 def icsbp(colour, u, log_sigma, K, kernel='gaussian'):
     return _ICSBP.apply(colour, u, log_sigma, K, kernel)
 

@@ -132,6 +132,15 @@ int g2_icsbp_kernel_fwd_f32(const float* colour, const float* u, const float* lo
 int g2_icsbp_kernel_bwd_f32(const float* colour, const float* log_sigma, const int* seed_idx, const float* dlog_m,
                             float* dcolour, float* dlog_sigma_b, int B, int P, int K, int colour_dim, int kernel_type,
                             g2_stream_t stream);
+/* dynamic_K (models/genesisv2_config.py:118-137, modules/attention.py:168-169, 218-219): a step whose mask would hold fewer than
+ * 20 pixels ends that image's loop and the current scope becomes its last mask.  n_masks [B] int32 = masks per image;
+ * log_m slots k >= n_masks[b] are -1e10 (the reference's batch padding), seed_idx beyond the last step is -1. */
+int g2_icsbp_dynamic_fwd_f32(const float* colour, const float* u, const float* log_sigma, float* log_m, float* log_s,
+                             int* seed_idx, int* n_masks, int B, int P, int K, int colour_dim, int kernel_type,
+                             g2_stream_t stream);
+int g2_icsbp_dynamic_bwd_f32(const float* colour, const float* log_sigma, const int* seed_idx, const int* n_masks,
+                             const float* dlog_m, float* dcolour, float* dlog_sigma_b, int B, int P, int K, int colour_dim,
+                             int kernel_type, g2_stream_t stream);
 /* masked feature pooling of models/genesisv2_config.py:147-152: num[k,b,c] = sum_p m_k f, msum[k,b] = sum_p m_k */
 int g2_masked_pool_fwd_f32(const float* f, const float* log_m, float* num, float* msum, int B, int P, int C, int K,
                            g2_stream_t stream);

@@ -49,10 +49,17 @@ def ref_total_loss(losses):
     return tot
 
 
-def run_case(name, model, K, img, B, gen, **over):
+def run_case(name, model, K, img, B, gen, param_add=None, **over):
+    """param_add: {parameter name: value added to the seeded initial value} -- used where the initial parameters never reach
+    a branch (dynamic_K's early exit needs a wider IC-SBP kernel than the initial log_sigma); recorded in the golden."""
     cfg = M.make_cfg(model, K_steps=K, img_size=img, **over)
     ref = ref_loader.load_reference(model, cfg, seed=0)
     ref.train()
+    if param_add:
+        sd_ = dict(ref.named_parameters())
+        with torch.no_grad():
+            for k_, v_ in param_add.items():
+                sd_[k_].add_(v_)
     names, sums = param_checksums(ref.state_dict())
     x = torch.from_numpy(synth.GENERATORS[gen](B, img, 1)[0])
     tape = O.NoiseTape(seed=2)
@@ -93,6 +100,9 @@ def run_case(name, model, K, img, B, gen, **over):
     g['meta'] = np.array([model, str(K), str(img), str(B), gen])
     if over:
         g['overrides'] = np.array(['%s=%s' % kv for kv in sorted(over.items())])
+    if param_add:
+        g['param_add_names'] = np.array(sorted(param_add))
+        g['param_add_values'] = np.array([param_add[k_] for k_ in sorted(param_add)], dtype=np.float64)
     os.makedirs(OUT_DIR, exist_ok=True)
     path = os.path.join(OUT_DIR, name + '.npz')
     np.savez_compressed(path, **g)
@@ -203,6 +213,13 @@ def run_eval_case(name, fwd_case):
 
 
 if __name__ == '__main__':
+    if '--variants-dynamic' in sys.argv:    # GENESIS-V2 dynamic_K (genesisv2_config.py:118-137): batch (padded) and single image (truncated)
+        import math
+        run_case('variant_genesisv2_k6_dynamic_b3', 'genesisv2', 6, 64, 3, 'multid', dynamic_K=True,
+                 param_add={'att_process.log_sigma': math.log(16.0)})
+        run_case('variant_genesisv2_k8_dynamic_b1', 'genesisv2', 8, 64, 1, 'rooms', dynamic_K=True,
+                 param_add={'att_process.log_sigma': math.log(32.0)})
+        sys.exit(0)
     if '--variants-icsbp' in sys.argv:      # GENESIS-V2 attention options (modules/attention.py:138-160)
         run_case('variant_genesisv2_k4_laplacian', 'genesisv2', 4, 64, 2, 'multid', kernel='laplacian')
         run_case('variant_genesisv2_k4_epanechnikov', 'genesisv2', 4, 64, 2, 'rooms', kernel='epanechnikov')

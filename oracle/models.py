@@ -213,7 +213,7 @@ def monet_forward(P, x, tape, cfg, training=True):
 
 
 # ============================================================================ GENESIS-V2
-def icsbp(colour, u, log_sigma, steps, kernel='gaussian'):
+def icsbp(colour, u, log_sigma, steps, kernel='gaussian', dynamic_K=False):
     """InstanceColouringSBP.forward (modules/attention.py:177-223), dynamic_K=False; `kernel` as :195-205.
     colour [B,C,H,W] (after SemiConv), u [B,1,H,W] uniform draws, `steps` = K-1.  The bilinear resize
     of the scope at :185-186 is the identity because colour and scope share img_size."""
@@ -236,10 +236,14 @@ def icsbp(colour, u, log_sigma, steps, kernel='gaussian'):
             raise ValueError("No valid kernel.")
         alpha = alpha.unsqueeze(1)
         alpha = O.clamp_ste(alpha, 0.01, 0.99)                                # :213
-        log_m_k.append(log_s_k[k] + torch.log(alpha))
-        log_s_k.append(log_s_k[k] + torch.log(1 - alpha))
-        seeds.append(seed)
+        seeds.append(seed)                                                    # :193 (before the early exit)
         idxs.append(idx)
+        log_m = log_s_k[k] + torch.log(alpha)
+        if dynamic_K and log_m.exp().sum() < 20:                              # :218-219 (batch of one, :168-169)
+            assert B == 1
+            break
+        log_m_k.append(log_m)
+        log_s_k.append(log_s_k[k] + torch.log(1 - alpha))
     log_m_k.append(log_s_k[-1])
     return log_m_k, log_s_k, seeds, idxs
 
@@ -283,8 +287,24 @@ def genesisv2_forward(P, x, tape, cfg, training=True):
     else:                                                                      # attention.py:159-160: plain 1x1 conv
         colour = F.conv2d(seg, P['att_process.colour_head.weight'], P['att_process.colour_head.bias'])
         delta = None
-    u = tape.uniform((B, 1, img, img), dt)                                     # attention.py:177-178
-    log_m_k, log_s_k, seeds, idxs = icsbp(colour, u, P['att_process.log_sigma'], K - 1, getattr(cfg, 'kernel', 'gaussian'))
+    kern = getattr(cfg, 'kernel', 'gaussian')
+    if getattr(cfg, 'dynamic_K', False):                                       # genesisv2_config.py:118-137
+        if B > 1:       # image by image (one uniform draw each), padded with -1e10 masks; log_s_k / att_stats are None there
+            per = [icsbp(colour[b:b + 1], tape.uniform((1, 1, img, img), dt), P['att_process.log_sigma'], K - 1, kern, True)
+                   for b in range(B)]
+            pad = torch.full((1, 1, img, img), -1e10, dtype=dt)
+            log_m_k = [torch.cat([r[0][k] if k < len(r[0]) else pad for r in per], 0) for k in range(K)]
+            log_s_k, seeds, idxs = None, None, None
+            n_masks = [len(r[0]) for r in per]
+        else:
+            log_m_k, log_s_k, seeds, idxs = icsbp(colour, tape.uniform((1, 1, img, img), dt), P['att_process.log_sigma'], K - 1,
+                                                  kern, True)
+            n_masks = [len(log_m_k)]
+            K = len(log_m_k)
+    else:
+        u = tape.uniform((B, 1, img, img), dt)                                 # attention.py:177-178
+        log_m_k, log_s_k, seeds, idxs = icsbp(colour, u, P['att_process.log_sigma'], K - 1, kern)
+        n_masks = [K] * B
     # slot latents (:145-161); feat_head evaluated once -- identical values to the K recomputations
     f = conv_gn_relu(enc_feat, 'feat_head.0')
     f = F.conv2d(f, P['feat_head.1.weight'], P['feat_head.1.bias'])
@@ -315,7 +335,7 @@ def genesisv2_forward(P, x, tape, cfg, training=True):
     kl_l_k = [O.mc_kl(z_k[k], mu_k[k], sigma_k[k], pmu_k[k], psig_k[k]) for k in range(K)]
     out = dict(recon=recon, err=err, kl_l_k=kl_l_k, log_m_k=log_m_k, log_s_k=log_s_k, x_r_k=x_r_k,
                log_m_r_k=log_m_r_k,
-               att=dict(colour=colour, delta=delta, seeds=seeds, seed_idx=idxs),
+               att=dict(colour=colour, delta=delta, seeds=seeds, seed_idx=idxs), n_masks=n_masks,
                comp=dict(mu_k=mu_k, sigma_k=sigma_k, z_k=z_k, pmu_k=pmu_k[1:], psigma_k=psig_k[1:]),
                bn_updates={})
     if cfg.get('klm_loss', False):          # genesisv2_config.py:171-176: KL(masks || reconstructed masks), the latter detached by default

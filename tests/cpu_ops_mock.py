@@ -154,6 +154,23 @@ def icsbp(colour, u, log_sigma, K, kernel='gaussian'):
     return torch.stack(log_m_k, 0), torch.stack(log_s_k[:K], 0).detach(), torch.stack(idxs, 0).int()
 
 
+def icsbp_dynamic(colour, u, log_sigma, K, kernel='gaussian'):
+    """g2_icsbp_dynamic_*: per image, early exit, -1e10 padding up to K, n_masks [B]."""
+    from oracle import models as M
+    B, Hh, Ww = colour.shape[0], colour.shape[1], colour.shape[2]
+    lm, ls, idx, n = [], [], [], []
+    for b in range(B):
+        log_m_k, log_s_k, seeds, idxs = M.icsbp(colour[b:b + 1].permute(0, 3, 1, 2), u[b:b + 1], log_sigma, K - 1, kernel, True)
+        nb = len(log_m_k)
+        pad = torch.full((1, 1, Hh, Ww), -1e10, dtype=colour.dtype)
+        lm.append(torch.stack(log_m_k + [pad] * (K - nb), 0))
+        ls.append(torch.stack(log_s_k + [log_s_k[-1]] * (K - nb), 0).detach())
+        ii = [int(i) for i in idxs][:K - 1]
+        idx.append(torch.tensor(ii + [-1] * (K - 1 - len(ii)), dtype=torch.int32))
+        n.append(nb)
+    return torch.cat(lm, 1), torch.cat(ls, 1), torch.stack(idx, 1), torch.tensor(n, dtype=torch.int32)
+
+
 def masked_pool(f, log_m):
     m = log_m.exp().flatten(2)                                   # [K,B,P]
     num = torch.einsum('kbp,bpc->kbc', m, f.flatten(1, 2))
@@ -174,7 +191,7 @@ def install(monkeypatch, ops):
     g = globals()
     for name in ('to_nhwc', 'to_nchw', 'to_nhwc_padded', 'conv2d', 'conv_transpose2d', 'linear', 'norm_post', 'sbp_scan',
                  'comp_pack', 'bcast_add_act', 'out1x1', 'mixture_nll', 'mixture_nll_packed', 'monet_loss', 'down2', 'up2',
-                 'icsbp', 'masked_pool', 'mask_kl'):
+                 'icsbp', 'icsbp_dynamic', 'masked_pool', 'mask_kl'):
         monkeypatch.setattr(ops, name, g[name])
     monkeypatch.setattr(ops, 'get_precision', lambda: 'fp32')
     monkeypatch.setattr(ops, 'side_streams_enabled', lambda: False)

@@ -74,3 +74,24 @@ def test_closed_form_matches_autograd(kernel, kt, K):
     assert (a < 0.01).any() and ((a > 0.05) & (a < 0.95)).any()                         # the draw exercises the clamp and the open range
     torch.testing.assert_close(dcol, ref, rtol=1e-9, atol=1e-10)
     torch.testing.assert_close(dls, gs, rtol=1e-9, atol=1e-10)
+
+
+@pytest.mark.parametrize('kernel,kt', [('gaussian', 0), ('epanechnikov', 2)])
+def test_closed_form_with_dynamic_K(kernel, kt):
+    """dynamic_K: an image whose loop stopped after n masks gets gradient only through those n (the backward kernel runs its
+    reverse scan with K = n_masks[b]; padded slots are constants)."""
+    torch.manual_seed(5 + kt)
+    H, W, CD, K = 16, 16, 8, 7
+    colour = (0.3 * torch.randn(1, CD, H, W, dtype=torch.float64)).requires_grad_(True)
+    u = torch.rand(1, 1, H, W, dtype=torch.float64)
+    log_sigma = torch.tensor(3.0, dtype=torch.float64).log().requires_grad_(True)      # wide kernel: the scope empties quickly
+    log_m_k, log_s_k, seeds, idxs = M.icsbp(colour, u, log_sigma, K - 1, kernel, dynamic_K=True)
+    n = len(log_m_k)
+    assert 1 < n < K                                                    # stopped early, with at least one real step
+    log_m = torch.stack(log_m_k, 0)
+    dlog_m = torch.randn_like(log_m)
+    gc, gs = torch.autograd.grad((log_m * dlog_m).sum(), [colour, log_sigma])
+    col_nhwc = colour.detach().permute(0, 2, 3, 1).reshape(1, H * W, CD)
+    dcol, dls = closed_form_backward(col_nhwc, log_sigma.detach(), torch.stack(idxs, 0)[:n - 1], dlog_m.reshape(n, 1, H * W), kt)
+    torch.testing.assert_close(dcol, gc.permute(0, 2, 3, 1).reshape(1, H * W, CD), rtol=1e-9, atol=1e-10)
+    torch.testing.assert_close(dls, gs, rtol=1e-9, atol=1e-10)

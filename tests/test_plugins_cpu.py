@@ -235,3 +235,36 @@ def test_genesisv2_attention_option_variants_host_logic(monkeypatch, over):
     U.engine_total_loss(losses).backward()
     M.total_loss(ref).backward()
     check_grads(m, P, tol=5e-3)
+
+
+@pytest.mark.parametrize('K,B,mult', [(6, 3, 16.0), (8, 1, 32.0)], ids=['batch-padded', 'single-truncated'])
+def test_genesisv2_dynamic_K_host_logic(monkeypatch, K, B, mult):
+    """dynamic_K (reference genesisv2_config.py:118-137): per-image uniform draws, early exit, -1e10 padding for batches, fewer
+    slots for a single image.  log_sigma is widened so that the early exit is actually taken (as in the goldens)."""
+    import math
+    from genesis_b200 import ops
+    cpu_ops_mock.install(monkeypatch, ops)
+    m, cfg = build_engine_model('genesisv2', K, 64, dynamic_K=True)
+    with torch.no_grad():
+        m.att_process.log_sigma.add_(math.log(mult))
+    m.train()
+    sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = torch.from_numpy(synth.GENERATORS['multid'](B, 64, 5)[0])
+    m.set_noise_tape(O.NoiseTape(seed=3))
+    recon, losses, stats, att, comp = m(x.as_subclass(cpu_ops_mock.AsCuda))
+    m.set_noise_tape(None)
+    P = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in sd0.items()}
+    ref = M.FORWARD['genesisv2'](P, x, O.NoiseTape(seed=3), cfg, training=True)
+    assert min(ref['n_masks']) < K                                    # the early exit is exercised
+    assert len(stats['log_m_k']) == len(ref['log_m_k'])
+    np.testing.assert_allclose(stack(stats['log_m_k']), stack(ref['log_m_k']), atol=1e-4)
+    np.testing.assert_allclose(losses['err'].detach().numpy(), ref['err'].detach().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(stack(losses['kl_l_k']), stack(ref['kl_l_k']), atol=1e-3, rtol=1e-4)
+    if B > 1:
+        assert att is None and stats['log_s_k'] is None               # reference :121-122
+    else:
+        assert len(att['seeds']) == len(ref['att']['seeds']) and len(stats['log_s_k']) == len(ref['log_s_k'])
+    import util_parity as U
+    U.engine_total_loss(losses).backward()
+    M.total_loss(ref).backward()
+    check_grads(m, P, tol=5e-3)

@@ -2,7 +2,9 @@
 oracle/make_golden.py --variants; the engine's holders re-create the variant's seeded parameters and the oracle reproduces
 outputs and gradient summaries.  Variants so far: GENESIS with enc_norm = dec_norm = 'in' (genesis_config.py:39-40); one-stage GENESIS (two_stage=False,
 genesis_config.py:121-126, 178-185); GENESIS with comp_prior=False; GENESIS with comp_symmetric=True (genesis_config.py:101-120); GENESIS-V2 with autoreg_prior=False; GENESIS-V2 with klm_loss=True
-(detach_mr_in_klm True / False, genesisv2_config.py:171-176); MONet with prior_mode='scope' (monet_config.py:141-153).  (GENESIS with
+(detach_mr_in_klm True / False, genesisv2_config.py:171-176); MONet with prior_mode='scope' (monet_config.py:141-153); GENESIS-V2 with the
+laplacian / epanechnikov IC-SBP kernels, the plain 1x1 colour head (semiconv=False) and dynamic_K (batch: padded masks; single image:
+fewer slots).  (GENESIS with
 autoreg_prior=False is not a valid reference configuration: genesis_config.py:212 dereferences self.prior_lstm regardless.)"""
 import glob
 import os
@@ -26,11 +28,21 @@ def overrides(g):
     return out
 
 
+def apply_param_add(m, g):
+    """Goldens whose branch the seeded initial parameters never reach record an offset (oracle/make_golden.py run_case)."""
+    if 'param_add_names' in g.files:
+        params = dict(m.named_parameters())
+        with torch.no_grad():
+            for n, v in zip(g['param_add_names'], g['param_add_values']):
+                params[str(n)].add_(float(v))
+
+
 @pytest.mark.parametrize('path', VARIANTS, ids=[os.path.basename(p)[:-4] for p in VARIANTS])
 def test_variant_oracle_matches_reference(path):
     g = np.load(path)
     model, K, img, B, gen = (str(v) for v in g['meta'])
     m, cfg = build_engine_model(model, int(K), int(img), **overrides(g))
+    apply_param_add(m, g)
     sd = m.state_dict()
     assert sorted(sd.keys()) == list(g['param_names'])
     for n, (s, a) in zip(g['param_names'], g['param_sums']):
