@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of the next round: validate everything that was written after the round-1 GPU budget was spent.
-#   gpurun --timeout 900 -- 'bash scripts/validate_pending.sh'
+#   gpurun --timeout 1800 -- 'bash scripts/validate_pending.sh'   (about 20 GPU-minutes: two test passes incl. child-process suites, three A/B benches)
 # Writes gpurun_out/pending_*.txt.  Nothing here changes defaults; flip them in the source once the numbers are in.
 set -u
 mkdir -p gpurun_out
