@@ -26,3 +26,9 @@ for cfg in "G2_FUSED_LATENT=0 G2_HALO_PERSISTENT=0" "G2_FUSED_LATENT=1 G2_HALO_P
   echo "-- $cfg" | tee -a gpurun_out/pending_summary.txt
   env $cfg timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['last_elbo'])" | tee -a gpurun_out/pending_summary.txt
 done
+# Optional follow-ups (each a separate, short GPU call; ncu replays every kernel ~40x, so keep -c small):
+#   ncu --set full --clock-control none --import-source on -k regex:conv_halo_persistent -c 2 -o gpurun_out/r02_halo_persistent \
+#       env G2_HALO_PERSISTENT=1 python scripts/conv_bench.py --only c2_bdec_fwd70 --reps 1
+#   ncu --set full --clock-control none --import-source on -k regex:wgrad_halo -c 2 -o gpurun_out/r02_wgrad_halo \
+#       env G2_WGRAD_HALO=1 python scripts/conv_bench.py --wgrad --only c2_att64_fwd --reps 1
+#   python scripts/ncu_summary.py gpurun_out/r02_*.ncu-rep > profiles/r02_ncu_<kernel>_summary.txt
