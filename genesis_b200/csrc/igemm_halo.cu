@@ -675,6 +675,9 @@ static int launch_persistent(const Maps& maps, const PP& pp, int n_ctas, cudaStr
     return e == cudaSuccess ? G2_OK : (int)e;
 }
 
+struct TapSet;
+static bool persistent_geo(int N, const TapSet& t, int Ci, int Co, int BN, int sh, int sw, Geo* g, int* pstages, bool* resident);
+
 static int pick_bn(int Co) {
     if (Co == 32 || Co == 64 || Co == 128) return Co;
     if (Co % 128 == 0) return 128;
@@ -728,6 +731,17 @@ static void spans(const TapSet& t, int* dh_min, int* dw_min, int* span_h, int* s
         c = t.dw[i] < c ? t.dw[i] : c; d = t.dw[i] > d ? t.dw[i] : d;
     }
     *dh_min = a; *dw_min = c; *span_h = b - a; *span_w = d - c;
+}
+
+// Geometry of the experimental persistent variant: weights resident when all (cb, tap) tiles fit beside two windows, else a
+// deeper ring; two windows and two accumulator sets (<= 256 TMEM columns each) per CTA.  false: use the one-item kernel.
+static bool persistent_geo(int N, const TapSet& t, int Ci, int Co, int BN, int sh, int sw, Geo* g, int* pstages, bool* resident) {
+    if (!persistent_mode()) return false;
+    const int b_all = t.n * (Ci / 32);
+    *resident = Co == BN && b_all <= MAX_PSTAGES && b_all * BN * 128 <= 72 * 1024;
+    *pstages = *resident ? b_all : (BN == 32 ? 8 : BN == 64 ? 4 : 2);
+    const int a_budget = (227 * 1024 - 1024 - *pstages * BN * 128 - PSTAGE_BYTES - 2048 - 512) / 2;
+    return a_budget >= 128 * 144 && pick_geo(N, t.Hv, t.Wv, sh, sw, t.n, Ci / 32, BN, *pstages, g, a_budget, 256);
 }
 
 static bool enabled() {
@@ -801,15 +815,9 @@ int g2_conv_halo_tf32(const float* in, const float* w, const float* bias, float*
         int dh_min, dw_min, sh, sw;
         spans(t, &dh_min, &dw_min, &sh, &sw);
         Geo g;
-        // experimental persistent variant: weights resident when all (cb, tap) tiles fit beside two windows, else a deeper ring
-        const int b_all = t.n * (Ci / 32);
-        const bool resident = persistent_mode() && Co == BN && b_all <= MAX_PSTAGES && b_all * BN * 128 <= 72 * 1024;
-        const int pstages = resident ? b_all : (BN == 32 ? 8 : BN == 64 ? 4 : 2);
-        bool use_p = false;
-        if (persistent_mode()) {
-            const int a_budget = (227 * 1024 - 1024 - pstages * BN * 128 - PSTAGE_BYTES - 2048 - 512) / 2;
-            use_p = a_budget >= 128 * 144 && pick_geo(N, t.Hv, t.Wv, sh, sw, t.n, Ci / 32, BN, pstages, &g, a_budget, 256);
-        }
+        bool resident = false;
+        int pstages = 0;
+        const bool use_p = persistent_geo(N, t, Ci, Co, BN, sh, sw, &g, &pstages, &resident);
         if (!use_p && !pick_geo(N, t.Hv, t.Wv, sh, sw, t.n, Ci / 32, BN, stages_of(BN, t.n, Ci / 32), &g)) return G2_ERR_UNSUPPORTED;
         P p;
         memset(&p, 0, sizeof(p));
@@ -878,12 +886,20 @@ int g2_conv_halo_plan(int N, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int
     int dh_min, dw_min, sh, sw;
     spans(t, &dh_min, &dw_min, &sh, &sw);
     Geo g;
-    if (!pick_geo(N, t.Hv, t.Wv, sh, sw, t.n, Ci / 32, BN, stages_of(BN, t.n, Ci / 32), &g)) return G2_ERR_UNSUPPORTED;
+    bool resident = false;
+    int pstages = 0;
+    // with G2_HALO_PERSISTENT=1 the plan is the persistent variant's (plan[22] = 1, [23] = resident weights, [24] = weight
+    // stages, [25] = TMEM columns of the two accumulator sets), so the same numpy replay validates its geometry
+    const bool use_p = persistent_geo(N, t, Ci, Co, BN, sh, sw, &g, &pstages, &resident);
+    if (!use_p && !pick_geo(N, t.Hv, t.Wv, sh, sw, t.n, Ci / 32, BN, stages_of(BN, t.n, Ci / 32), &g)) return G2_ERR_UNSUPPORTED;
     const int Wp = g.Wp;
+    const int smem = use_p ? 2 * g.a_bytes + pstages * BN * 128 + PSTAGE_BYTES + 2048 + 512 + 1024
+                           : g.a_bytes + stages_of(BN, t.n, Ci / 32) * BN * 128 + 1024 + 1024;
     const int v[22] = {nc, g.TH, g.TNB, g.RH, g.ch_rows, g.nch, g.m, g.a_bytes, g.tiles_h, Wp, dh_min, dw_min, t.os, t.ph, t.pw,
-                       t.Hv, t.Wv, t.n, BN, g.a_bytes + stages_of(BN, t.n, Ci / 32) * BN * 128 + 1024 + 1024, g.TW, g.tiles_w};
+                       t.Hv, t.Wv, t.n, BN, smem, g.TW, g.tiles_w};
     for (int i = 0; i < 96; ++i) plan[i] = 0;
     for (int i = 0; i < 22; ++i) plan[i] = v[i];
+    plan[22] = use_p ? 1 : 0; plan[23] = resident ? 1 : 0; plan[24] = pstages; plan[25] = use_p ? 2 * g.m * BN : g.m * BN;
     for (int i = 0; i < t.n; ++i) {
         plan[32 + i] = (t.dh[i] - dh_min) * Wp + (t.dw[i] - dw_min);
         plan[64 + i] = t.widx[i];

@@ -5,6 +5,9 @@ The replay below performs the kernel's index arithmetic -- TMA boxes with zero o
 run of pixel rows, M tiles of 128 consecutive flat positions, taps as row shifts, the epilogue's validity mask --
 and must reproduce torch's conv2d / conv_transpose2d exactly on integer data.  No GPU, no kernel launch."""
 import ctypes
+import os
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -42,6 +45,7 @@ def plan_of(case, cls):
     keys = ['nclasses', 'TH', 'TNB', 'RH', 'ch_rows', 'nch', 'm', 'a_bytes', 'tiles_h', 'Wp', 'dh_min', 'dw_min', 'os', 'ph', 'pw',
             'Hv', 'Wv', 'ntaps', 'BN', 'smem', 'TW', 'tiles_w']
     d = dict(zip(keys, v[:22]))
+    d['persistent'], d['resident'], d['pstages'], d['tmem_cols'] = v[22:26]
     d['toff'] = v[32:32 + d['ntaps']]
     d['widx'] = v[64:64 + d['ntaps']]
     d['Ho'], d['Wo'] = Ho, Wo
@@ -58,6 +62,9 @@ def replay(case, x_nhwc, wp, out):
         span_h = RH - TH
         alloc_pix = pl['a_bytes'] // 128
         assert pl['a_bytes'] % 1024 == 0 and pl['smem'] <= 227 * 1024 and pl['m'] * pl['BN'] <= 512
+        assert pl['tmem_cols'] <= 512 and pl['persistent'] == (1 if os.environ.get('G2_HALO_PERSISTENT') == '1' else 0)
+        if pl['resident']:
+            assert pl['pstages'] == pl['ntaps'] * (Ci // 32) and pl['pstages'] <= 64
         if TNB == 1:
             assert (pl['ch_rows'] * Wp * 128) % 1024 == 0 and pl['nch'] <= 8 and pl['nch'] * pl['ch_rows'] >= RH
         groups = (N + TNB - 1) // TNB
@@ -132,3 +139,14 @@ def test_halo_plan_fits_two_ctas_per_sm_for_the_headline_layers():
     for case in CASES[:5]:
         pl = plan_of(case, 0)
         assert pl['smem'] <= 112 * 1024 and pl['m'] * pl['BN'] <= 256, pl
+
+
+@pytest.mark.skipif(os.environ.get('G2_HALO_PERSISTENT') == '1', reason='already inside the persistent-mode child run')
+def test_halo_plan_replay_in_persistent_mode():
+    """The experimental persistent kernel picks its tile geometry under a different budget (two windows, two accumulator
+    sets, resident weights).  G2_HALO_PERSISTENT is read once per process, so the same replay runs in a child process with
+    the switch on: g2_conv_halo_plan then reports the persistent geometry and the numpy replay must still be exact."""
+    env = dict(os.environ, G2_HALO_PERSISTENT='1')
+    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.abspath(__file__), '-q', '-x', '-k', 'replay_matches_torch'],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
