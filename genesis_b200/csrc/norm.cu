@@ -334,7 +334,8 @@ inline int ew_blocks(long work) {
 
 extern "C" {
 
-int g2_norm_stats_f32(const float* y, double* sums, int N, int HW, int C, cudaStream_t stream) {
+int g2_norm_stats_f32(const float* y, double* sums, int N, int HW, int Cy, cudaStream_t stream) {
+    const int C = Cy;       // channels of y as stored (2C' for a gated layer), named as in the header
     G2_CHECK_ARG(y && sums && N > 0 && HW > 0 && C >= 4 && (C % 4) == 0 && C <= 1024);
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)N * C, stream);
     if (e != cudaSuccess) return (int)e;
@@ -349,8 +350,9 @@ int g2_norm_stats_f32(const float* y, double* sums, int N, int HW, int C, cudaSt
 
 int g2_norm_finalize_f32(const double* sums, const float* g0, const float* b0, const float* g1, const float* b1,
                          float* rm0, float* rv0, float* rm1, float* rv1, float* mean, float* rstd, float* scale,
-                         float* shift, int N, int HW, int C, int half, int mode, int groups, int training,
+                         float* shift, int N, int HW, int Cy, int half, int mode, int groups, int training,
                          float eps, float momentum, cudaStream_t stream) {
+    const int C = Cy;
     G2_CHECK_ARG(mean && rstd && scale && shift && N > 0 && C > 0 && half > 0 && half <= C);
     G2_CHECK_ARG(mode == G2_NORM_BATCH || mode == G2_NORM_INSTANCE || mode == G2_NORM_GROUP);
     if (mode == G2_NORM_GROUP) G2_CHECK_ARG(groups > 0 && C % groups == 0);
