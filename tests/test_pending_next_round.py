@@ -374,3 +374,61 @@ def test_dynamic_K_engine_matches_reference(name):
             continue
         gd = params[str(n)].grad.detach().double().cpu().flatten()
         assert abs(gd.norm().item() - nrm) <= 2e-2 * nrm + 1e-3 * gmax, (n, gd.norm().item(), nrm)
+
+
+FULL_SIZE = [  # model, K, img, B (BASELINE.json configs c2, c3, c5 per GPU), generator, images of the subset run
+    ('genesis', 5, 64, 64, 'multid', 8),
+    ('genesisv2', 7, 64, 128, 'stacks', 8),
+    ('monet', 7, 128, 64, 'multid', 4),
+]
+
+
+@pytest.mark.parametrize('model,K,img,B,gen,n', FULL_SIZE, ids=[c[0] for c in FULL_SIZE])
+def test_full_size_identities_and_batch_partition_invariance(model, K, img, B, gen, n):
+    """BASELINE.json's full per-GPU sizes, where the CPU oracle would take minutes: the size-independent properties of
+    tests/full_size_props.py (checked on the CPU at small sizes by tests/test_full_size_props_cpu.py).  Identities under the
+    default TF32 path; batch-partition invariance under the exact-fp32 path (tile shapes, hence summation orders, depend on
+    the batch)."""
+    import full_size_props as FP
+    from genesis_b200 import ops
+    from oracle import synth
+    from test_oracle_golden import build_engine_model
+    m, cfg = build_engine_model(model, K, img)
+    m = m.cuda()
+    x = torch.from_numpy(synth.GENERATORS[gen](B, img, 11)[0]).cuda()
+    std = float(m.std) if model == 'genesisv2' else m.std.reshape(-1)
+
+    def forward(xb, tape):
+        m.set_noise_tape(tape)
+        with torch.no_grad():
+            out = m(xb)
+        torch.cuda.synchronize()
+        m.set_noise_tape(None)
+        return out
+
+    if model == 'genesis':
+        m.train()
+        forward(x, FP.SubsetTape(1, B, B, K))       # move the BatchNorm running statistics
+        m.eval()
+    else:
+        m.train()
+    full = forward(x, FP.SubsetTape(5, B, B, K))
+    FP.check_identities(model, x, full, std, tol=5.0)
+    prev = ops.get_precision()
+    ops.set_precision('fp32')
+    try:
+        full32 = forward(x, FP.SubsetTape(5, B, B, K))
+        sub32 = forward(x[:n], FP.SubsetTape(5, B, n, K))
+    finally:
+        ops.set_precision(prev)
+    FP.check_subset_invariance(full32, sub32, n, rtol=2e-4, atol=2e-4)
+    # training step at full size: every parameter receives a finite gradient
+    import util_parity as U
+    m.train()
+    m.set_noise_tape(FP.SubsetTape(7, B, B, K))
+    m.zero_grad(set_to_none=True)
+    U.engine_total_loss(m(x)[1]).backward()
+    torch.cuda.synchronize()
+    m.set_noise_tape(None)
+    for name, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
