@@ -4,6 +4,8 @@ Every heavy operator of the hot path (conv, conv-transpose, linear, norm+gate/Re
 broadcast-decoder layers, mixture likelihood) is a torch.autograd.Function whose forward and backward
 enqueue hand-written sm_100a kernels on the current CUDA stream.  Activations are NHWC fp32.
 There is no CPU or library fallback: a non-CUDA tensor raises."""
+import os
+
 import torch
 from torch.autograd import Function
 
@@ -361,7 +363,9 @@ class _Linear(Function):
         M, K = x.shape
         N = wd.shape[0]
         y = _new(x, M, N)
-        if _gemm_tc_ok(M, N, K):
+        if _skinny_ok(M, N, K):
+            _call('g2_gemm_skinny_f32', x, wd, b, y, M, N, K, K, K, N, 0, 1, act, 0)
+        elif _gemm_tc_ok(M, N, K):
             _call('g2_gemm_tf32', x, wd, b, y, M, N, K)
             if act != ACT_NONE:      # split-K GEMMs cannot fuse the activation; keep it a separate pass
                 if N % 4 != 0:
@@ -387,14 +391,18 @@ class _Linear(Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            if _gemm_tc_ok(M, K, N):
+            if _skinny_ok(M, K, N):
+                _call('g2_gemm_skinny_f32', dpre, w, None, dx, M, K, N, N, K, K, 0, 0, ACT_NONE, 0)
+            elif _gemm_tc_ok(M, K, N):
                 _call('g2_gemm_tf32', dpre, w.t().contiguous(), None, dx, M, K, N)
             else:
                 _call('g2_gemm_f32', dpre, w, None, dx, M, K, N, N, K, K, 0, 0, ACT_NONE, 0)
         if ctx.needs_input_grad[1]:
             if _direct(w_param):
                 with _GradStream(dpre, x):
-                    if _gemm_tc_ok(N, K, M):
+                    if _skinny_ok(N, K, M):
+                        _call('g2_gemm_skinny_f32', dpre, x, None, w_param.grad, N, K, M, N, K, K, 1, 0, ACT_NONE, 1)
+                    elif _gemm_tc_ok(N, K, M):
                         dwt = torch.empty_like(w)
                         _call('g2_gemm_tf32', dpre.t().contiguous(), x.t().contiguous(), None, dwt, N, K, M)
                         w_param.grad.add_(dwt)
@@ -403,6 +411,9 @@ class _Linear(Function):
                     if has_b and ctx.needs_input_grad[2] and _direct(b_param):
                         _bias_grad(dpre, b_param, N)
                         has_b = False
+            elif _skinny_ok(N, K, M):
+                dw = torch.empty_like(w)
+                _call('g2_gemm_skinny_f32', dpre, x, None, dw, N, K, M, N, K, K, 1, 0, ACT_NONE, 0)
             elif _gemm_tc_ok(N, K, M):
                 dw = torch.empty_like(w)
                 _call('g2_gemm_tf32', dpre.t().contiguous(), x.t().contiguous(), None, dw, N, K, M)
@@ -412,6 +423,19 @@ class _Linear(Function):
         if has_b and ctx.needs_input_grad[2]:
             db = _bias_grad(dpre, b_param, N)
         return dx, dw, db, None
+
+
+_SKINNY = {'on': os.environ.get('G2_SKINNY_GEMM', '0') == '1', 'max_flop': 4e8}
+
+
+def set_skinny_gemm(on):
+    """Route the small products of the latent path (LSTM steps, heads, prior MLP) to the exact-fp32 skinny GEMM
+    (csrc/gemm_skinny.cu).  Off by default until it has been validated and timed on a B200."""
+    _SKINNY['on'] = bool(on)
+
+
+def _skinny_ok(m_rows, n_out, k_red):
+    return _SKINNY['on'] and 2.0 * m_rows * n_out * k_red <= _SKINNY['max_flop']
 
 
 def _gemm_tc_ok(m_rows, n_out, k_red):

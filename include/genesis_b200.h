@@ -69,6 +69,11 @@ int g2_conv_wgrad_f32(const float* g, const float* t, float* dw, int N, int Hg, 
  * and the full-map gated convs VAE.py:23,29 viewed as GEMMs. */
 int g2_gemm_f32(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int lda,
                 int ldb, int ldc, int transA, int transB, int act, int accumulate, g2_stream_t stream);
+/* Same contract, for the small latency-bound products of the latent path (csrc/gemm_skinny.cu: 32x32 tiles, register-prefetched
+ * K loop, one writer per element -> deterministic; `accumulate` adds to C without atomics).  Experimental: ops.py routes to
+ * it only under G2_SKINNY_GEMM=1. */
+int g2_gemm_skinny_f32(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int lda,
+                       int ldb, int ldc, int transA, int transB, int act, int accumulate, g2_stream_t stream);
 /* out[c] (+)= sum_m x[m,c]   (bias gradients) */
 int g2_colsum_f32(const float* x, float* out, long M, int C, int accumulate, g2_stream_t stream);
 

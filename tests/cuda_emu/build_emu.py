@@ -1,0 +1,101 @@
+"""TEST INFRASTRUCTURE: compile a plain-SIMT .cu file of genesis_b200/csrc for the CPU emulation of tests/cuda_emu/cuda_emu.h.
+
+The source is used as it is except for the launch statements, which g++ cannot parse:
+    kernel<T...><<<grid, block, smem, stream>>>(args);   ->   emu::launch(grid, block, [&] { kernel<T...>(args); });
+so the extern "C" host entry points (argument checks, grid computation, kernel selection) are exercised too."""
+import hashlib
+import os
+import re
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), 'genesis_b200', 'csrc')
+OUT = os.path.join(HERE, '_build')
+
+PRELUDE = '''#define CUDA_EMU_MAIN
+#include <cstring>
+#include "cuda_emu.h"
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return cudaSuccess; }
+'''
+
+
+def _balanced(text, i, open_ch, close_ch):
+    """text[i] == open_ch -> index just past the matching close_ch."""
+    depth = 0
+    for j in range(i, len(text)):
+        if text[j] == open_ch:
+            depth += 1
+        elif text[j] == close_ch:
+            depth -= 1
+            if depth == 0:
+                return j + 1
+    raise ValueError('unbalanced')
+
+
+def _split_top(s):
+    parts, depth, cur = [], 0, ''
+    for ch in s:
+        if ch in '(<[':
+            depth += 1
+        elif ch in ')>]':
+            depth -= 1
+        if ch == ',' and depth == 0:
+            parts.append(cur.strip())
+            cur = ''
+        else:
+            cur += ch
+    parts.append(cur.strip())
+    return parts
+
+
+def transform(src):
+    out, pos = '', 0
+    for m in re.finditer(r'<<<', src):
+        i = m.start()
+        if i < pos:
+            continue
+        # kernel name (with template arguments) = the token run before <<<
+        k = i
+        depth = 0
+        while k > 0:
+            ch = src[k - 1]
+            if ch == '>':
+                depth += 1
+            elif ch == '<':
+                depth -= 1
+            elif depth == 0 and not (ch.isalnum() or ch in '_:'):
+                break
+            k -= 1
+        name = src[k:i]
+        j = src.index('>>>', i)
+        cfg = _split_top(src[i + 3:j])
+        a0 = j + 3
+        assert src[a0] == '(', src[a0:a0 + 20]
+        a1 = _balanced(src, a0, '(', ')')
+        semi = src[a1] == ';'           # a launch inside a macro body has no semicolon of its own
+        out += src[pos:k] + 'emu::launch(%s, %s, [&] { %s%s; })%s' % (cfg[0], cfg[1], name, src[a0:a1], ';' if semi else '')
+        pos = a1 + (1 if semi else 0)
+    out += src[pos:]
+    # dynamic shared memory: one static arena (blocks run one after another)
+    return re.sub(r'extern\s+__shared__\s+(\w+)\s+(\w+)\[\];', r'\1* \2 = reinterpret_cast<\1*>(emu::dyn_smem);', out)
+
+
+def build(cu_name):
+    """-> path of the shared object emulating genesis_b200/csrc/<cu_name> (cached on the source hash)."""
+    src = open(os.path.join(CSRC, cu_name)).read()
+    code = PRELUDE + transform(src)
+    deps = code + open(os.path.join(HERE, 'cuda_emu.h')).read() + open(os.path.join(CSRC, 'common.cuh')).read()
+    tag = hashlib.sha1(deps.encode()).hexdigest()[:12]
+    os.makedirs(OUT, exist_ok=True)
+    base = os.path.join(OUT, '%s_%s' % (cu_name[:-3], tag))
+    so = base + '.so'
+    if not os.path.exists(so):
+        with open(base + '.cpp', 'w') as f:
+            f.write(code)
+        cmd = ['g++', '-O1', '-std=c++17', '-pthread', '-shared', '-fPIC', '-w', '-I', os.path.join(HERE, 'shim'), '-I', HERE,
+               '-I', CSRC, base + '.cpp', '-o', so]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('g++ failed for the emulation of %s:\n%s' % (cu_name, r.stderr[-4000:]))
+    return so

@@ -1,0 +1,246 @@
+"""CPU: the plain-SIMT kernels that were written without a GPU at hand, executed on the CPU (tests/cuda_emu: the kernel source
+compiled unchanged by g++, one OS thread per CUDA thread, real barriers and warp shuffles) and compared with numpy / torch /
+the oracle: the skinny GEMM (csrc/gemm_skinny.cu), the fused latent kernels (csrc/latent.cu) and the IC-SBP kernels with
+their kernel-type and dynamic_K instantiations (csrc/v2.cu).  The extern "C" entry points are emulated too, so argument
+checks, grid sizes and kernel selection are covered.  This validates indexing, tile edges, barrier placement and scan order --
+not performance, and not the product library (which is only ever run on a GPU)."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'cuda_emu'))
+import build_emu  # noqa: E402
+
+from oracle import models as M  # noqa: E402
+
+P = ctypes.c_void_p
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(P)
+
+
+@pytest.fixture(scope='module')
+def emu():
+    libs = {}
+
+    def get(name):
+        if name not in libs:
+            libs[name] = ctypes.CDLL(build_emu.build(name))
+        return libs[name]
+    return get
+
+
+# ------------------------------------------------------------------------------------------------ skinny GEMM
+GEMM_CASES = [  # M, N, K, tA, tB, bias, act, accumulate
+    (64, 96, 160, 0, 1, True, 0, 0),       # forward  x[M,K] w[N,K]^T
+    (37, 50, 70, 0, 1, True, 2, 0),        # ragged in every dimension, ELU
+    (33, 40, 33, 0, 1, False, 1, 0),       # K < one tile (BK = 32 path), ReLU
+    (64, 72, 128, 0, 0, False, 0, 0),      # data gradient  dpre[M,N'] w[N',K']
+    (96, 40, 64, 1, 0, False, 0, 1),       # weight gradient  dpre[Mred,N]^T x[Mred,K], accumulated into .grad
+    (31, 33, 200, 1, 1, True, 5, 0),       # both transposed, sigmoid
+]
+
+
+@pytest.mark.parametrize('case', GEMM_CASES, ids=[str(c) for c in GEMM_CASES])
+def test_skinny_gemm(emu, case):
+    Mm, N, K, tA, tB, has_bias, act, acc = case
+    lib = emu('gemm_skinny.cu')
+    rng = np.random.RandomState(0)
+    A = rng.randn(*((K, Mm) if tA else (Mm, K))).astype(np.float32)
+    B = rng.randn(*((N, K) if tB else (K, N))).astype(np.float32)
+    bias = rng.randn(N).astype(np.float32) if has_bias else None
+    C0 = rng.randn(Mm, N).astype(np.float32)
+    C = C0.copy()
+    rc = lib.g2_gemm_skinny_f32(ptr(A), ptr(B), ptr(bias), ptr(C), Mm, N, K, A.shape[1], B.shape[1], N, tA, tB, act, acc, None)
+    assert rc == 0
+    ref = (A.T if tA else A).astype(np.float64) @ (B.T if tB else B).astype(np.float64)
+    if has_bias:
+        ref = ref + bias
+    if act == 1:
+        ref = np.maximum(ref, 0)
+    elif act == 2:
+        ref = np.where(ref > 0, ref, np.expm1(ref))
+    elif act == 5:
+        ref = 1 / (1 + np.exp(-ref))
+    if acc:
+        ref = ref + C0
+    np.testing.assert_allclose(C, ref, rtol=2e-5, atol=2e-5)
+
+
+def test_skinny_gemm_rejects_bad_arguments(emu):
+    lib = emu('gemm_skinny.cu')
+    a = np.zeros((4, 4), np.float32)
+    assert lib.g2_gemm_skinny_f32(ptr(a), ptr(a), None, ptr(a), 4, 4, 4, 4, 4, 2, 0, 1, 0, 0, None) == -1      # ldc < N
+    assert lib.g2_gemm_skinny_f32(ptr(a), ptr(a), None, ptr(a), 4, 4, 4, 4, 4, 4, 0, 1, 3, 0, None) == -1      # gradient-type act
+
+
+# ------------------------------------------------------------------------------------------------ fused latent kernels
+def test_latent_lstm_cell(emu):
+    lib = emu('latent.cu')
+    torch.manual_seed(0)
+    B, H = 5, 12
+    gx = torch.randn(B, 4 * H, requires_grad=True)
+    gh = torch.randn(B, 4 * H, requires_grad=True)
+    for with_prev in (True, False):
+        cp = torch.randn(B, H, requires_grad=True) if with_prev else None
+        i, f, g, o = torch.chunk(gx + gh, 4, dim=1)
+        c_ref = torch.sigmoid(i) * torch.tanh(g) + (torch.sigmoid(f) * cp if with_prev else 0)
+        h_ref = torch.sigmoid(o) * torch.tanh(c_ref)
+        h = np.empty((B, H), np.float32)
+        c = np.empty((B, H), np.float32)
+        cpn = cp.detach().numpy().copy() if with_prev else None
+        assert lib.g2_lstm_cell_fwd_f32(ptr(gx.detach().numpy()), ptr(gh.detach().numpy()), ptr(cpn), ptr(h), ptr(c), B, H, None) == 0
+        np.testing.assert_allclose(h, h_ref.detach().numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(c, c_ref.detach().numpy(), rtol=1e-5, atol=1e-6)
+        dh, dc = torch.randn(B, H), torch.randn(B, H)
+        grads = torch.autograd.grad((h_ref * dh).sum() + (c_ref * dc).sum(), [gx] + ([cp] if with_prev else []))
+        dg = np.empty((B, 4 * H), np.float32)
+        dcp = np.empty((B, H), np.float32) if with_prev else None
+        assert lib.g2_lstm_cell_bwd_f32(ptr(gx.detach().numpy()), ptr(gh.detach().numpy()), ptr(cpn), ptr(c), ptr(dh.numpy()),
+                                        ptr(dc.numpy()), ptr(dg), ptr(dcp), B, H, None) == 0
+        np.testing.assert_allclose(dg, grads[0].numpy(), rtol=1e-4, atol=1e-6)
+        if with_prev:
+            np.testing.assert_allclose(dcp, grads[1].numpy(), rtol=1e-4, atol=1e-6)
+
+
+def test_latent_heads_and_kl(emu):
+    lib = emu('latent.cu')
+    torch.manual_seed(1)
+    B, D = 7, 10
+    lo = (2 * torch.randn(B, 2 * D)).requires_grad_(True)
+    eps = torch.randn(B, D)
+    mu_ref, raw = torch.chunk(lo, 2, dim=1)
+    sig_ref = torch.nn.functional.softplus(raw + 0.5) + 1e-8
+    z_ref = mu_ref + sig_ref * eps
+    z, mu, sig = (np.empty((B, D), np.float32) for _ in range(3))
+    assert lib.g2_gauss_head_fwd_f32(ptr(lo.detach().numpy()), ptr(eps.numpy()), ptr(z), ptr(mu), ptr(sig), B, D, None) == 0
+    np.testing.assert_allclose(z, z_ref.detach().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(sig, sig_ref.detach().numpy(), rtol=1e-5, atol=1e-7)
+    dz, dmu, dsig = torch.randn(B, D), torch.randn(B, D), torch.randn(B, D)
+    (g_ref,) = torch.autograd.grad((z_ref * dz).sum() + (mu_ref * dmu).sum() + (sig_ref * dsig).sum(), [lo])
+    dlo = np.empty((B, 2 * D), np.float32)
+    assert lib.g2_gauss_head_bwd_f32(ptr(lo.detach().numpy()), ptr(eps.numpy()), ptr(dz.numpy()), ptr(dmu.numpy()), ptr(dsig.numpy()),
+                                     ptr(dlo), B, D, None) == 0
+    np.testing.assert_allclose(dlo, g_ref.numpy(), rtol=1e-4, atol=1e-6)
+    # prior head
+    for use_tanh in (1, 0):
+        a, b = torch.chunk(lo, 2, dim=1)
+        pm_ref = torch.tanh(a) if use_tanh else a
+        ps_ref = torch.sigmoid(b + 4) + 1e-4
+        pm, ps = np.empty((B, D), np.float32), np.empty((B, D), np.float32)
+        assert lib.g2_prior_head_fwd_f32(ptr(lo.detach().numpy()), ptr(pm), ptr(ps), B, D, use_tanh, None) == 0
+        np.testing.assert_allclose(pm, pm_ref.detach().numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(ps, ps_ref.detach().numpy(), rtol=1e-5, atol=1e-7)
+        (g_ref,) = torch.autograd.grad((pm_ref * dz).sum() + (ps_ref * dsig).sum(), [lo])
+        assert lib.g2_prior_head_bwd_f32(ptr(pm), ptr(ps), ptr(dz.numpy()), ptr(dsig.numpy()), ptr(dlo), B, D, use_tanh, None) == 0
+        np.testing.assert_allclose(dlo, g_ref.numpy(), rtol=1e-4, atol=1e-6)
+    # Monte-Carlo KL, D not a multiple of the warp size
+    from oracle import functional as O
+    D2 = 45
+    zz, m, pm = (torch.randn(B, D2, requires_grad=True) for _ in range(3))
+    s = (torch.rand(B, D2) + 0.3).requires_grad_(True)
+    ps = (torch.rand(B, D2) + 0.2).requires_grad_(True)
+    for prior in (True, False):
+        kl_ref = O.mc_kl(zz, m, s, pm if prior else None, ps if prior else None)
+        kl = np.empty(B, np.float32)
+        args = [t.detach().numpy() for t in (zz, m, s)] + ([pm.detach().numpy(), ps.detach().numpy()] if prior else [None, None])
+        assert lib.g2_mc_kl_fwd_f32(*[ptr(a) for a in args], ptr(kl), B, D2, None) == 0
+        np.testing.assert_allclose(kl, kl_ref.detach().numpy(), rtol=1e-4, atol=1e-4)
+        dkl = torch.randn(B)
+        grads = torch.autograd.grad((kl_ref * dkl).sum(), [zz, m, s] + ([pm, ps] if prior else []))
+        outs = [np.empty((B, D2), np.float32) for _ in range(5)]
+        assert lib.g2_mc_kl_bwd_f32(*[ptr(a) for a in args], ptr(dkl.numpy()), ptr(outs[0]), ptr(outs[1]), ptr(outs[2]),
+                                    ptr(outs[3]) if prior else None, ptr(outs[4]) if prior else None, B, D2, None) == 0
+        for got, ref in zip(outs, grads):
+            np.testing.assert_allclose(got, ref.numpy(), rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ IC-SBP
+def icsbp_inputs(B, S, seed):
+    torch.manual_seed(seed)
+    scale = torch.tensor([0.03, 0.3, 1.5])[torch.randint(0, 3, (B, S, S, 1))]
+    colour = (scale * torch.randn(B, S, S, 8)).contiguous()
+    u = torch.rand(B, 1, S, S)
+    return colour, u
+
+
+@pytest.mark.parametrize('kernel,kt', [('gaussian', 0), ('laplacian', 1), ('epanechnikov', 2)])
+@pytest.mark.parametrize('S,K', [(16, 4), (40, 3)])          # 40 x 40 = 1600 pixels: two pixels per thread
+def test_icsbp_kernels(emu, kernel, kt, S, K):
+    lib = emu('v2.cu')
+    B = 2
+    colour, u = icsbp_inputs(B, S, 3 + kt)
+    sigma0 = {0: 1.0 / (K * 0.6931), 1: 1.0 / (K ** 0.5 * 0.6931), 2: 2.0 / K}[kt]
+    ls = torch.tensor(sigma0).log()
+    c_ref = colour.permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    ls_ref = ls.clone().requires_grad_(True)
+    log_m_k, log_s_k, seeds, idxs = M.icsbp(c_ref, u, ls_ref, K - 1, kernel)
+    ref = torch.stack(log_m_k, 0)                                             # [K,B,1,S,S]
+    Pn = S * S
+    log_m, log_s = np.empty((K, B, Pn), np.float32), np.empty((K, B, Pn), np.float32)
+    idx = np.empty((K - 1, B), np.int32)
+    lsn = np.array([ls.item()], np.float32)
+    if kt == 0:     # the validated gaussian entry point and the kernel-type entry point must agree
+        assert lib.g2_icsbp_fwd_f32(ptr(colour.numpy()), ptr(u.numpy()), ptr(lsn), ptr(log_m), ptr(log_s), ptr(idx), B, Pn, K, 8, None) == 0
+        first = log_m.copy()
+    assert lib.g2_icsbp_kernel_fwd_f32(ptr(colour.numpy()), ptr(u.numpy()), ptr(lsn), ptr(log_m), ptr(log_s), ptr(idx), B, Pn, K, 8, kt, None) == 0
+    if kt == 0:
+        np.testing.assert_array_equal(first, log_m)
+    np.testing.assert_array_equal(idx, torch.stack(idxs, 0).numpy())
+    np.testing.assert_allclose(log_m.reshape(ref.shape), ref.detach().numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(log_s.reshape(ref.shape), torch.stack(log_s_k[:K], 0).detach().numpy(), rtol=1e-4, atol=1e-4)
+    w = torch.randn(ref.shape)
+    gc, gs = torch.autograd.grad((ref * w).sum(), [c_ref, ls_ref])
+    dcol, dsig = np.empty((B, Pn, 8), np.float32), np.empty(B, np.float32)
+    assert lib.g2_icsbp_kernel_bwd_f32(ptr(colour.numpy()), ptr(lsn), ptr(idx), ptr(w.numpy()), ptr(dcol), ptr(dsig), B, Pn, K, 8, kt, None) == 0
+    gref = gc.permute(0, 2, 3, 1).reshape(B, Pn, 8).numpy()
+    assert np.linalg.norm(dcol - gref) <= 2e-4 * np.linalg.norm(gref)
+    assert abs(dsig.sum() - gs.item()) <= 2e-4 * abs(gs.item()) + 1e-4
+
+
+@pytest.mark.parametrize('kernel,kt', [('gaussian', 0), ('epanechnikov', 2)])
+def test_icsbp_dynamic_K(emu, kernel, kt):
+    """Early exit per image, -1e10 padding, n_masks, and the backward's per-image scan length."""
+    lib = emu('v2.cu')
+    B, S, K = 3, 16, 7
+    colour, u = icsbp_inputs(B, S, 11 + kt)
+    colour = colour * 0.3
+    sigmas = {0: 3.0, 2: 6.0}
+    ls = torch.tensor(sigmas[kt]).log()                                       # wide kernel: the scope empties quickly
+    Pn = S * S
+    c_ref = colour.permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    ls_ref = ls.clone().requires_grad_(True)
+    per = [M.icsbp(c_ref[b:b + 1], u[b:b + 1], ls_ref, K - 1, kernel, dynamic_K=True) for b in range(B)]
+    n_ref = [len(r[0]) for r in per]
+    assert min(n_ref) < K                                                     # the early exit is taken
+    log_m, log_s = np.empty((K, B, Pn), np.float32), np.empty((K, B, Pn), np.float32)
+    idx = np.empty((K - 1, B), np.int32)
+    n = np.empty(B, np.int32)
+    lsn = np.array([ls.item()], np.float32)
+    assert lib.g2_icsbp_dynamic_fwd_f32(ptr(colour.numpy()), ptr(u.numpy()), ptr(lsn), ptr(log_m), ptr(log_s), ptr(idx), ptr(n),
+                                        B, Pn, K, 8, kt, None) == 0
+    assert n.tolist() == n_ref
+    w = torch.randn(K, B, Pn)
+    loss = 0
+    for b in range(B):
+        for k in range(K):
+            if k < n_ref[b]:
+                np.testing.assert_allclose(log_m[k, b], per[b][0][k].detach().numpy().reshape(-1), rtol=1e-4, atol=1e-4)
+                loss = loss + (per[b][0][k].reshape(-1) * w[k, b]).sum()
+            else:
+                assert (log_m[k, b] == -1e10).all()
+        steps = min(n_ref[b], K - 1)                                          # the step that stopped the loop still recorded its seed
+        assert idx[:steps, b].tolist() == [int(i) for i in per[b][3]][:steps]
+        assert (idx[steps:, b] == -1).all()
+    gc, gs = torch.autograd.grad(loss, [c_ref, ls_ref])
+    dcol, dsig = np.empty((B, Pn, 8), np.float32), np.empty(B, np.float32)
+    assert lib.g2_icsbp_dynamic_bwd_f32(ptr(colour.numpy()), ptr(lsn), ptr(idx), ptr(n), ptr(w.numpy()), ptr(dcol), ptr(dsig),
+                                        B, Pn, K, 8, kt, None) == 0
+    gref = gc.permute(0, 2, 3, 1).reshape(B, Pn, 8).numpy()
+    assert np.linalg.norm(dcol - gref) <= 2e-4 * np.linalg.norm(gref)
+    assert abs(dsig.sum() - gs.item()) <= 2e-4 * abs(gs.item()) + 1e-4
