@@ -17,6 +17,10 @@ PRELUDE = '''#define CUDA_EMU_MAIN
 #include "cuda_emu.h"
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return cudaSuccess; }
+static inline cudaError_t cudaMemset2DAsync(void* p, size_t pitch, int v, size_t w, size_t h, cudaStream_t) {
+    for (size_t r = 0; r < h; ++r) std::memset((char*)p + r * pitch, v, w);
+    return cudaSuccess;
+}
 '''
 
 

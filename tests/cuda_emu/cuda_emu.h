@@ -120,10 +120,15 @@ static inline double atomicAdd(double* p, double v) {
     std::lock_guard<std::mutex> lk(emu::atomic_mutex);
     const double old = *p; *p = old + v; return old;
 }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) {
+    std::lock_guard<std::mutex> lk(emu::atomic_mutex);
+    const unsigned old = *p; *p = old + v; return old;
+}
 static inline int atomicAdd(int* p, int v) {
     std::lock_guard<std::mutex> lk(emu::atomic_mutex);
     const int old = *p; *p = old + v; return old;
 }
+static inline float rsqrtf(float x) { return 1.f / sqrtf(x); }
 #define __expf(x) expf(x)
 #define __logf(x) logf(x)
 static inline float __fdividef(float a, float b) { return a / b; }

@@ -244,3 +244,102 @@ def test_icsbp_dynamic_K(emu, kernel, kt):
     gref = gc.permute(0, 2, 3, 1).reshape(B, Pn, 8).numpy()
     assert np.linalg.norm(dcol - gref) <= 2e-4 * np.linalg.norm(gref)
     assert abs(dsig.sum() - gs.item()) <= 2e-4 * abs(gs.item()) + 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ optimiser, scans, losses
+def test_fused_adam_matches_torch_optim(emu):
+    """g2_adam_f32 (flat arena, step counter read from memory, gradient scale, fused zero-grad) vs torch.optim.Adam."""
+    lib = emu('pointwise.cu')
+    lib.g2_adam_f32.argtypes = [P, P, P, P, ctypes.c_long, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, P,
+                                ctypes.c_float, ctypes.c_int, P]
+    torch.manual_seed(0)
+    n = 1024 + 64
+    p0 = torch.randn(n)
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    p, m, v = p0.numpy().copy(), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    step = np.zeros(1, np.float32)
+    world = 2.0
+    for it in range(4):
+        g = torch.randn(n) * (10.0 ** (it - 2))
+        ref.grad = g.clone()
+        opt.step()
+        gbuf = (g * world).numpy().copy()           # the arena holds the SUM over ranks; the kernel applies 1 / world
+        step += 1
+        assert lib.g2_adam_f32(ptr(p), ptr(gbuf), ptr(m), ptr(v), n, 1e-3, 0.9, 0.999, 1e-8, ptr(step), 1.0 / world, 1, None) == 0
+        assert np.abs(gbuf).max() == 0.0
+        assert np.abs(p - ref.detach().numpy()).max() <= 2e-6 * max(1.0, ref.detach().abs().max().item())
+
+
+@pytest.mark.parametrize('nl_is_K', [True, False])
+def test_sbp_scan(emu, nl_is_K):
+    lib = emu('pointwise.cu')
+    lib.g2_sbp_scan_fwd_f32.argtypes = [P, P, P, ctypes.c_long, ctypes.c_int, ctypes.c_int, P]
+    lib.g2_sbp_scan_bwd_f32.argtypes = [P, P, P, ctypes.c_long, ctypes.c_int, ctypes.c_int, P]
+    import cpu_ops_mock
+    torch.manual_seed(2)
+    K, BP = 5, 300
+    nl = K if nl_is_K else K - 1
+    lg = (2 * torch.randn(nl, BP)).requires_grad_(True)
+    m_ref, s_ref = cpu_ops_mock.sbp_scan(lg, K)
+    log_m, log_s = np.empty((K, BP), np.float32), np.empty((nl + 1, BP), np.float32)
+    assert lib.g2_sbp_scan_fwd_f32(ptr(lg.detach().numpy()), ptr(log_m), ptr(log_s), BP, K, nl, None) == 0
+    np.testing.assert_allclose(log_m, m_ref.detach().numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(log_s, s_ref.numpy(), rtol=1e-5, atol=1e-5)
+    w = torch.randn(K, BP)
+    (g_ref,) = torch.autograd.grad((m_ref * w).sum(), [lg])
+    dlg = np.empty((nl, BP), np.float32)
+    assert lib.g2_sbp_scan_bwd_f32(ptr(lg.detach().numpy()), ptr(w.numpy()), ptr(dlg), BP, K, nl, None) == 0
+    np.testing.assert_allclose(dlg, g_ref.numpy(), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('cs', [1, 4], ids=['plain-logits', 'packed-decoder-plane'])
+def test_mask_kl_both_layouts(emu, cs):
+    """The stand-alone mask KL of ops.mask_kl: logits as their own [K,B,1,P] tensor (MONet prior_mode='scope') or as plane 3 of
+    the packed decoder output [K,B,4,P] (GENESIS-V2 klm_loss)."""
+    lib = emu('loss.cu')
+    import cpu_ops_mock
+    torch.manual_seed(3)
+    K, B, Hh = 4, 3, 10
+    Pn = Hh * Hh
+    lm = torch.log_softmax(2 * torch.randn(K, B, 1, Hh, Hh), dim=0).requires_grad_(True)
+    dec = torch.randn(K, B, cs, Hh, Hh, requires_grad=True)
+    kl_ref = cpu_ops_mock.mask_kl(lm, dec, detach=False)
+    decn = dec.detach().numpy()
+    off = 3 * Pn if cs == 4 else 0
+    lg_ptr = ctypes.c_void_p(decn.ctypes.data + 4 * off)
+    lmr, kl = np.empty((K, B, Pn), np.float32), np.empty(B, np.float32)
+    assert lib.g2_mask_kl_fwd_f32(ptr(lm.detach().numpy()), lg_ptr, ptr(lmr), ptr(kl), K, B, Pn, 1, cs, None) == 0
+    np.testing.assert_allclose(kl, kl_ref.detach().numpy(), rtol=1e-4, atol=1e-4)
+    plane = dec.detach()[:, :, 3:] if cs == 4 else dec.detach()
+    np.testing.assert_allclose(lmr.reshape(K, B, 1, Hh, Hh), torch.log_softmax(plane, dim=0).numpy(), rtol=1e-5, atol=1e-5)
+    gkl = torch.randn(B)
+    g_lm, g_dec = torch.autograd.grad((kl_ref * gkl).sum(), [lm, dec])
+    dlm = np.empty((K, B, Pn), np.float32)
+    ddec = np.zeros_like(decn)
+    dlg_ptr = ctypes.c_void_p(ddec.ctypes.data + 4 * off)
+    assert lib.g2_mask_kl_bwd_f32(ptr(lm.detach().numpy()), lg_ptr, ptr(gkl.numpy()), ptr(dlm), dlg_ptr, K, B, Pn, 1, cs, 1, cs, 0,
+                                  None) == 0
+    np.testing.assert_allclose(dlm.reshape(g_lm.shape), g_lm.numpy(), rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(ddec, g_dec.numpy(), rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize('seed,deg,K', [(0, False, 7), (2, True, 5)])
+def test_seg_metrics_kernel(emu, seed, deg, K):
+    """g2_seg_metrics (one confusion matrix per image -> ARI / segmentation covering / argmax map) vs the oracle, which is
+    pinned to the reference's utils/misc functions (tests/test_metrics.py)."""
+    from oracle import metrics as OM
+    from test_metrics import random_case
+    lib = emu('metrics.cu')
+    log_m, inst = random_case(seed, K=K, degenerate=deg)
+    _, B, H, _ = log_m.shape
+    Pn = H * H
+    lm = np.ascontiguousarray(log_m.reshape(K, B, Pn).astype(np.float32))
+    ins = np.ascontiguousarray(inst.reshape(B, Pn).astype(np.int64))
+    want = OM.metrics(lm, ins)
+    seg = np.empty((B, Pn), np.int64)
+    out = np.empty((B, 8), np.float64)
+    assert lib.g2_seg_metrics(ptr(lm), None, ptr(ins), ptr(seg), ptr(out), B, Pn, K, None) == 0
+    for j, key in enumerate(('ari', 'ari_fg', 'msc', 'msc_fg', 'msc_scaled', 'msc_fg_scaled')):
+        np.testing.assert_allclose(out[:, j], want[key], atol=1e-12, err_msg=key)
+    np.testing.assert_array_equal(seg, want['instance_seg'].reshape(B, Pn))
