@@ -432,3 +432,33 @@ def test_full_size_identities_and_batch_partition_invariance(model, K, img, B, g
     m.set_noise_tape(None)
     for name, p in m.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), name
+
+
+def test_skinny_gemm_kernel_and_engine():
+    """g2_gemm_skinny_f32 on the device (the CPU emulation already checks the kernel's logic, tests/test_cuda_emu.py) and the
+    GENESIS engine with the small products routed to it (ops.set_skinny_gemm): same parity bars as the default path."""
+    import util_parity as U
+    from genesis_b200 import _lib, ops
+    from oracle import synth
+    from test_oracle_golden import build_engine_model
+    torch.manual_seed(0)
+    for (Mm, N, K, tA, tB, acc) in [(64, 512, 320, 0, 1, 0), (320, 64, 256, 0, 0, 0), (1024, 320, 64, 1, 0, 1), (37, 50, 70, 0, 1, 0)]:
+        A = torch.randn((K, Mm) if tA else (Mm, K), device='cuda')
+        B = torch.randn((N, K) if tB else (K, N), device='cuda')
+        bias = torch.randn(N, device='cuda')
+        C0 = torch.randn(Mm, N, device='cuda')
+        C = C0.clone()
+        _lib.call('g2_gemm_skinny_f32', A, B, bias, C, Mm, N, K, A.shape[1], B.shape[1], N, tA, tB, 0, acc)
+        ref = (A.t() if tA else A).double() @ (B.t() if tB else B).double() + bias.double() + (C0.double() if acc else 0)
+        assert (C.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    m, cfg = build_engine_model('genesis', 3, 64)
+    m = m.cuda().train()
+    x = torch.from_numpy(synth.GENERATORS['multid'](4, 64, 5)[0])
+    ops.set_skinny_gemm(True)
+    try:
+        recon, losses, stats, att, comp = U.run_engine(m, x, U.make_tape(3))
+    finally:
+        ops.set_skinny_gemm(False)
+    ref, P = U.run_oracle('genesis', m.state_dict(), x, U.make_tape(3), cfg)
+    assert U.rel_l2(losses['err'], ref['err']) < 1e-4
+    U.compare_grads(m, P, tol=1e-2)
