@@ -659,6 +659,8 @@ static int launch(const Maps& maps, const P& p, dim3 grid, cudaStream_t stream) 
 }
 
 static int persistent_mode() { static int v = env_int("G2_HALO_PERSISTENT", 0); return v; }
+// CTAs of the persistent launch (one per SM by default; the CPU emulation lowers it to give every CTA several items)
+static int persistent_ctas() { static int v = env_int("G2_HALO_PERSISTENT_CTAS", 148); return v < 1 ? 1 : v; }
 
 template <int BN>
 static int launch_persistent(const Maps& maps, const PP& pp, int n_ctas, cudaStream_t stream) {
@@ -852,7 +854,7 @@ int g2_conv_halo_tf32(const float* in, const float* w, const float* bias, float*
             while (pc < 2 * pp.acc_cols) pc <<= 1;
             pp.p.tmem_cols = pc;
             const long items = (long)grid.x * grid.y;
-            const int n_ctas = (int)(items < 148 ? items : 148);
+            const int n_ctas = (int)(items < persistent_ctas() ? items : persistent_ctas());
             switch (BN) {
                 case 32: rc = launch_persistent<32>(maps, pp, n_ctas, stream); break;
                 case 64: rc = launch_persistent<64>(maps, pp, n_ctas, stream); break;

@@ -53,7 +53,108 @@ def _split_top(s):
     return parts
 
 
+# ---- inline PTX -> calls into tests/cuda_emu/cuda_emu_sm100.h
+PTX_RULES = [   # (substring of the PTX text, C++ statement; {o0} = first output operand, {i0}.. = input operands)
+    ('elect.sync', '{o0} = emu::elect_one();'),
+    ('mbarrier.init', 'emu::mbar_init({i0}, {i1});'),
+    ('mbarrier.arrive.expect_tx', 'emu::mbar_expect_tx({i0}, {i1});'),
+    ('mbarrier.arrive', 'emu::mbar_arrive({i0});'),
+    ('mbarrier.try_wait.parity', '{o0} = emu::mbar_try_wait({i0}, {i1});'),
+    ('cp.async.bulk.tensor.4d', 'emu::tma_load({i0}, (const CUtensorMap*)({i1}), {i2}, 4, {i3}, {i4}, {i5}, {i6});'),
+    ('cp.async.bulk.tensor.3d', 'emu::tma_load({i0}, (const CUtensorMap*)({i1}), {i2}, 3, {i3}, {i4}, {i5}, 0);'),
+    ('cp.async.bulk', 'emu::unsupported("cp.async.bulk (bulk-copy epilogue)");'),
+    ('prefetch.tensormap', ';'),
+    ('tcgen05.mma', 'emu::mma_tf32({i0}, {i1}, {i2}, {i3}, {i4});'),
+    ('tcgen05.commit', 'emu::mbar_arrive({i0});'),
+    ('tcgen05.alloc', 'emu::tmem_alloc({i0});'),
+    ('tcgen05.relinquish', ';'), ('tcgen05.dealloc', ';'), ('tcgen05.fence', ';'), ('tcgen05.wait', ';'),
+    ('tcgen05.ld', 'emu::tmem_ld32({i0}, &({o0}));'),
+    ('fence.', ';'),
+    ('bar.sync 1, 128', 'emu::named_barrier(1, 128);'),
+    ('%%smid', '{o0} = 0;'),
+]
+
+
+def _asm_sections(body):
+    """body of asm(...) -> (ptx text, [output exprs], [input exprs])"""
+    i, ptx = 0, ''
+    n = len(body)
+    while True:                       # adjacent string literals
+        while i < n and body[i].isspace():
+            i += 1
+        if i < n and body[i] == '"':
+            j = i + 1
+            while body[j] != '"' or body[j - 1] == '\\':
+                j += 1
+            ptx += body[i + 1:j]
+            i = j + 1
+        else:
+            break
+    rest = body[i:]
+    sections, depth, cur, in_str = [], 0, '', False
+    for ch in rest:
+        if ch == '"':
+            in_str = not in_str
+        if not in_str:
+            if ch in '([':
+                depth += 1
+            elif ch in ')]':
+                depth -= 1
+            if ch == ':' and depth == 0:
+                sections.append(cur)
+                cur = ''
+                continue
+        cur += ch
+    sections.append(cur)
+    sections = sections[1:]            # text before the first ':' is empty
+
+    def operands(sec):
+        out = []
+        for m in re.finditer(r'"[^"]*"\s*\(', sec):
+            a = m.end() - 1
+            b = _balanced(sec, a, '(', ')')
+            out.append(sec[a + 1:b - 1].strip())
+        return out
+    outs = operands(sections[0]) if len(sections) > 0 else []
+    ins = operands(sections[1]) if len(sections) > 1 else []
+    return ptx, outs, ins
+
+
+def translate_asm(src):
+    out, pos = '', 0
+    for m in re.finditer(r'\basm\s*(?:volatile)?\s*\(', src):
+        if m.start() < pos:
+            continue
+        a = m.end() - 1
+        b = _balanced(src, a, '(', ')')
+        assert src[b] == ';', src[m.start():b + 5]
+        ptx, outs, ins = _asm_sections(src[a + 1:b - 1])
+        for key, stmt in PTX_RULES:
+            if key in ptx:
+                fmt = {('o%d' % i): e for i, e in enumerate(outs)}
+                fmt.update({('i%d' % i): e for i, e in enumerate(ins)})
+                repl = stmt.format(**fmt)
+                break
+        else:
+            raise ValueError('no emulation rule for PTX: %s' % ptx[:80])
+        out += src[pos:m.start()] + '{ ' + repl + ' }'
+        pos = b + 1
+    return out + src[pos:]
+
+
+def inline_includes(src):
+    """#include "umma.cuh" -> its text (it holds inline PTX that must be translated too)"""
+    def sub(m):
+        name = m.group(1)
+        if name == 'common.cuh':
+            return m.group(0)
+        text = open(os.path.join(CSRC, name)).read().replace('#pragma once', '')
+        return inline_includes(text)
+    return re.sub(r'#include\s+"(\w+\.cuh)"', sub, src)
+
+
 def transform(src):
+    src = translate_asm(inline_includes(src))
     out, pos = '', 0
     for m in re.finditer(r'<<<', src):
         i = m.start()
@@ -89,7 +190,8 @@ def build(cu_name):
     """-> path of the shared object emulating genesis_b200/csrc/<cu_name> (cached on the source hash)."""
     src = open(os.path.join(CSRC, cu_name)).read()
     code = PRELUDE + transform(src)
-    deps = code + open(os.path.join(HERE, 'cuda_emu.h')).read() + open(os.path.join(CSRC, 'common.cuh')).read()
+    deps = code + ''.join(open(os.path.join(HERE, h)).read() for h in ('cuda_emu.h', 'cuda_emu_sm100.h')) + \
+        open(os.path.join(CSRC, 'common.cuh')).read()
     tag = hashlib.sha1(deps.encode()).hexdigest()[:12]
     os.makedirs(OUT, exist_ok=True)
     base = os.path.join(OUT, '%s_%s' % (cu_name[:-3], tag))

@@ -64,7 +64,7 @@ struct Block {
 };
 extern thread_local Block* block;
 extern std::mutex atomic_mutex;
-extern unsigned char dyn_smem[256 * 1024];
+extern unsigned char dyn_smem[256 * 1024];       // 1024-byte aligned: offsets into it ARE the shared-memory addresses
 }  // namespace emu
 
 extern thread_local dim3 threadIdx, blockIdx;
@@ -76,7 +76,7 @@ dim3 blockDim, gridDim;
 namespace emu {
 thread_local Block* block = nullptr;
 std::mutex atomic_mutex;
-alignas(16) unsigned char dyn_smem[256 * 1024];
+alignas(1024) unsigned char dyn_smem[256 * 1024];
 }
 #endif
 
@@ -128,6 +128,8 @@ static inline int atomicAdd(int* p, int v) {
     std::lock_guard<std::mutex> lk(emu::atomic_mutex);
     const int old = *p; *p = old + v; return old;
 }
+static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 static inline float rsqrtf(float x) { return 1.f / sqrtf(x); }
 #define __expf(x) expf(x)
 #define __logf(x) logf(x)

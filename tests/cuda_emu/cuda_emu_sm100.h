@@ -1,0 +1,214 @@
+// TEST INFRASTRUCTURE: functional model of the sm_100a asynchronous machinery as the kernels of genesis_b200/csrc use it --
+// mbarriers with transaction counts, TMA tiled loads (zero out-of-bounds fill, 128-byte swizzles), tcgen05.mma kind::tf32 with
+// shared-memory matrix descriptors (K-major SWIZZLE_128B and MN-major SWIZZLE_128B_BASE32B), tcgen05.commit, TMEM and its
+// 32x32b loads.  tests/cuda_emu/build_emu.py rewrites every inline-PTX statement of a kernel file into a call below, so the
+// kernel's own control flow, barrier parities, descriptor arithmetic and epilogue indexing run on the CPU.
+//
+// What it is NOT: asynchronous (loads and MMAs complete when issued; ordering hazards are the business of
+// tests/test_persistent_protocol.py) and not evidence about the hardware.  The operand-fetch rules encoded here -- the swizzle
+// XOR is applied to the absolute shared-memory address, M/N atoms are LBO apart -- are the assumptions the kernels were
+// written against; the model is calibrated on kernels that ARE validated on a B200 (conv_halo_kernel, wgrad_tc_kernel must
+// reproduce torch here exactly as they do there) before it is trusted on the ones that are not.
+#pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <memory>
+
+typedef uint32_t cuuint32_t;
+typedef uint64_t cuuint64_t;
+typedef int CUresult;
+enum { CUDA_SUCCESS = 0 };
+enum CUtensorMapDataType { CU_TENSOR_MAP_DATA_TYPE_FLOAT32 = 7, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 = 11 };
+enum CUtensorMapInterleave { CU_TENSOR_MAP_INTERLEAVE_NONE = 0 };
+enum CUtensorMapSwizzle { CU_TENSOR_MAP_SWIZZLE_NONE = 0, CU_TENSOR_MAP_SWIZZLE_128B = 3, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B = 4 };
+enum CUtensorMapL2promotion { CU_TENSOR_MAP_L2_PROMOTION_L2_256B = 3 };
+enum CUtensorMapFloatOOBfill { CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE = 0 };
+struct CUtensorMap {
+    const char* base; int rank; uint64_t dims[5]; uint64_t strides[5]; uint32_t box[5]; int swizzle;
+    char pad_[8];
+};
+typedef CUresult (*PFN_cuTensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0 };
+enum { cudaEnableDefault = 0 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <class K> static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
+
+namespace emu {
+
+static inline CUresult encode_tiled(CUtensorMap* m, CUtensorMapDataType, cuuint32_t rank, void* base, const cuuint64_t* dims,
+                                    const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle sw, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
+    m->base = (const char*)base; m->rank = (int)rank; m->swizzle = (int)sw;
+    for (cuuint32_t i = 0; i < rank; ++i) { m->dims[i] = dims[i]; m->box[i] = box[i]; m->strides[i] = i == 0 ? 4 : strides[i - 1]; }
+    if (box[0] * 4 > 128) return 1;                    // inner box extent must fit the 128-byte swizzle span
+    for (cuuint32_t i = 0; i < rank; ++i) if (box[i] > 256 || box[i] == 0) return 1;
+    return CUDA_SUCCESS;
+}
+
+static inline size_t smem_addr(const void* p) { return (size_t)((const unsigned char*)p - dyn_smem); }
+static inline unsigned char* smem_ptr(uint32_t a) {
+    if (a >= sizeof(dyn_smem)) { std::fprintf(stderr, "emu: shared-memory address 0x%x out of range\n", a); std::abort(); }
+    return dyn_smem + a;
+}
+static inline uint32_t swizzle_addr(uint32_t a, int mode) {
+    if (mode == CU_TENSOR_MAP_SWIZZLE_128B) return a ^ (((a >> 7) & 7u) << 4);             // 16-byte chunks ^ row (mod 8)
+    if (mode == CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) return a ^ (((a >> 7) & 3u) << 5);    // 32-byte chunks ^ row (mod 4)
+    return a;
+}
+
+// ---- mbarrier: the 64-bit word in shared memory holds {phase:1 | pending:15 | count:15 | - | tx:32}
+extern std::mutex mbar_mutex;
+extern std::condition_variable mbar_cv;
+struct MbarView { uint64_t* w; };
+static inline void mbar_complete_if_done(uint64_t* w) {
+    const int pending = (int)((*w >> 1) & 0x7FFF), count = (int)((*w >> 16) & 0x7FFF);
+    const int32_t tx = (int32_t)(*w >> 32);
+    if (pending == 0 && tx == 0) {
+        const uint64_t phase = (*w & 1) ^ 1;
+        *w = phase | ((uint64_t)count << 1) | ((uint64_t)count << 16);
+        mbar_cv.notify_all();
+    }
+}
+static inline void mbar_init(uint32_t a, int count) {
+    std::lock_guard<std::mutex> lk(mbar_mutex);
+    *(uint64_t*)smem_ptr(a) = ((uint64_t)count << 1) | ((uint64_t)count << 16);
+}
+static inline void mbar_add(uint32_t a, int arrivals, int32_t tx_delta) {
+    std::lock_guard<std::mutex> lk(mbar_mutex);
+    uint64_t* w = (uint64_t*)smem_ptr(a);
+    int pending = (int)((*w >> 1) & 0x7FFF);
+    int32_t tx = (int32_t)(*w >> 32) + tx_delta;
+    if (arrivals > pending) { std::fprintf(stderr, "emu: mbarrier 0x%x over-arrived\n", a); std::abort(); }
+    pending -= arrivals;
+    *w = (*w & 1) | ((uint64_t)pending << 1) | (*w & (0x7FFFull << 16)) | ((uint64_t)(uint32_t)tx << 32);
+    mbar_complete_if_done(w);
+}
+static inline void mbar_expect_tx(uint32_t a, uint32_t bytes) { mbar_add(a, 1, (int32_t)bytes); }
+static inline void mbar_arrive(uint32_t a) { mbar_add(a, 1, 0); }
+// Blocking; a protocol deadlock aborts the run.  Warp-collective, as on the hardware where a converged warp tests the barrier
+// in ONE instruction: only lane 0 waits and the other lanes follow it.  (Lanes are independent OS threads here; a lagging lane
+// testing a barrier that has meanwhile completed a further phase would alias parities, which cannot happen to a converged
+// warp.)  The kernels call mbar_wait warp-uniformly by construction.
+static inline uint32_t mbar_try_wait_lane0(uint32_t a, uint32_t parity);
+static inline uint32_t mbar_try_wait(uint32_t a, uint32_t parity) {
+    if ((::threadIdx.x & 31u) == 0) mbar_try_wait_lane0(a, parity);
+    block->warps[::threadIdx.x >> 5]->wait();
+    return 1;
+}
+static inline uint32_t mbar_try_wait_lane0(uint32_t a, uint32_t parity) {
+    std::unique_lock<std::mutex> lk(mbar_mutex);
+    uint64_t* w = (uint64_t*)smem_ptr(a);
+    static const int limit = std::getenv("EMU_TIMEOUT_S") ? std::atoi(std::getenv("EMU_TIMEOUT_S")) : 60;
+    const bool ok = mbar_cv.wait_for(lk, std::chrono::seconds(limit), [&] { return (uint32_t)(*w & 1) != (parity & 1u); });
+    if (!ok) {
+        std::fprintf(stderr, "emu: DEADLOCK block %u thread %u (warp %u) waits on mbarrier 0x%x parity %u; word: phase %u pending %u tx %d\n",
+                     ::blockIdx.x, ::threadIdx.x, ::threadIdx.x >> 5, a, parity, (unsigned)(*w & 1), (unsigned)((*w >> 1) & 0x7FFF),
+                     (int)(int32_t)(*w >> 32));
+        lk.unlock();
+        std::this_thread::sleep_for(std::chrono::seconds(2));       // let the other stuck threads report too
+        std::abort();
+    }
+    return 1;
+}
+
+static inline uint32_t elect_one() { return (::threadIdx.x & 31u) == 0 ? 1u : 0u; }
+
+// ---- TMA tiled load: box element (i_{r-1}..i_0) -> dst + linear offset, swizzled by destination address
+static inline void tma_load(uint32_t dst, const CUtensorMap* m, uint32_t bar, int rank, int c0, int c1, int c2, int c3) {
+    const int c[4] = {c0, c1, c2, c3};
+    uint32_t idx[4] = {0, 0, 0, 0};
+    uint32_t n = 1;
+    for (int i = 0; i < rank; ++i) n *= m->box[i];
+    for (uint32_t lin = 0; lin < n; ++lin) {
+        uint32_t t = lin;
+        bool oob = false;
+        long off = 0;
+        for (int i = 0; i < rank; ++i) {
+            idx[i] = t % m->box[i]; t /= m->box[i];
+            const long coord = (long)c[i] + idx[i];
+            if (coord < 0 || coord >= (long)m->dims[i]) oob = true;
+            off += coord * (long)m->strides[i];
+        }
+        const float v = oob ? 0.f : *(const float*)(m->base + off);
+        *(float*)smem_ptr(swizzle_addr(dst + lin * 4u, m->swizzle)) = v;
+    }
+    mbar_add(bar, 0, -(int32_t)(n * 4u));
+}
+
+// ---- TMEM and tcgen05.mma kind::tf32 (M = 128, K = 8 per instruction)
+extern float tmem[128][512];
+static inline void tmem_alloc(uint32_t slot_addr) { *(uint32_t*)smem_ptr(slot_addr) = 0u; }
+static inline float operand(uint64_t desc, bool mn_major, int r, int k) {
+    const uint32_t start = (uint32_t)(desc & 0x3FFF) << 4, lbo = (uint32_t)((desc >> 16) & 0x3FFF) << 4,
+                   sbo = (uint32_t)((desc >> 32) & 0x3FFF) << 4;
+    const int layout = (int)(desc >> 61);
+    uint32_t a;
+    if (!mn_major) {            // K-major SWIZZLE_128B: rows of 128 B, 8-row groups SBO apart, K = 8 tf32 = 32 B inside the row
+        if (layout != 2) { std::fprintf(stderr, "emu: K-major operand with layout type %d\n", layout); std::abort(); }
+        a = start + (uint32_t)(r >> 3) * sbo + (uint32_t)(r & 7) * 128u + (uint32_t)k * 4u;
+        a = swizzle_addr(a, CU_TENSOR_MAP_SWIZZLE_128B);
+    } else {                    // MN-major SWIZZLE_128B_BASE32B: a 128-byte row = 32 M/N elements of one k; 4-row k atoms SBO apart
+        if (layout != 1) { std::fprintf(stderr, "emu: MN-major operand with layout type %d\n", layout); std::abort(); }
+        a = start + (uint32_t)(r >> 5) * lbo + (uint32_t)(k >> 2) * sbo + (uint32_t)(k & 3) * 128u + (uint32_t)(r & 31) * 4u;
+        a = swizzle_addr(a, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    }
+    return *(const float*)smem_ptr(a);
+}
+static inline void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    const int N = (int)((idesc >> 17) & 0x3F) << 3, M = (int)((idesc >> 24) & 0x1F) << 4;
+    const bool a_mn = (idesc >> 15) & 1u, b_mn = (idesc >> 16) & 1u;
+    const uint32_t col0 = tmem_d & 0xFFFFu;
+    if (M != 128 || (tmem_d >> 16) != 0 || col0 + (uint32_t)N > 512u) { std::fprintf(stderr, "emu: bad MMA shape / TMEM address\n"); std::abort(); }
+    float bt[256][8];
+    for (int n = 0; n < N; ++n)
+        for (int k = 0; k < 8; ++k) bt[n][k] = operand(bdesc, b_mn, n, k);
+    for (int m = 0; m < 128; ++m) {
+        float at[8];
+        for (int k = 0; k < 8; ++k) at[k] = operand(adesc, a_mn, m, k);
+        for (int n = 0; n < N; ++n) {
+            float s = accumulate ? tmem[m][col0 + n] : 0.f;
+            for (int k = 0; k < 8; ++k) s += at[k] * bt[n][k];
+            tmem[m][col0 + n] = s;
+        }
+    }
+}
+static inline void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    const uint32_t lane = (taddr >> 16) + (::threadIdx.x & 31u), col = taddr & 0xFFFFu;
+    if (lane >= 128 || col + 32 > 512) { std::fprintf(stderr, "emu: TMEM load out of range\n"); std::abort(); }
+    std::memcpy(v, &tmem[lane][col], 32 * sizeof(float));
+}
+
+// ---- named barriers (bar.sync id, n)
+extern std::mutex named_mutex;
+extern std::map<int, std::unique_ptr<Barrier>> named;
+static inline void named_barrier(int id, int n) {
+    Barrier* b;
+    {
+        std::lock_guard<std::mutex> lk(named_mutex);
+        auto& p = named[id];
+        if (!p) p.reset(new Barrier(n));
+        b = p.get();
+    }
+    b->wait();
+}
+static inline void unsupported(const char* what) { std::fprintf(stderr, "emu: %s is not modelled\n", what); std::abort(); }
+
+#ifdef CUDA_EMU_MAIN
+std::mutex mbar_mutex;
+std::condition_variable mbar_cv;
+float tmem[128][512];
+std::mutex named_mutex;
+std::map<int, std::unique_ptr<Barrier>> named;
+#endif
+}  // namespace emu
+
+static inline cudaError_t cudaGetDriverEntryPoint(const char*, void** f, int, cudaDriverEntryPointQueryResult* q) {
+    *f = (void*)&emu::encode_tiled; *q = cudaDriverEntryPointSuccess; return cudaSuccess;
+}
+static inline size_t __cvta_generic_to_shared(const void* p) { return emu::smem_addr(p); }
+static inline long long clock64() { return 0; }
+static inline void __trap() { std::fprintf(stderr, "emu: __trap()\n"); std::abort(); }

@@ -1,0 +1,54 @@
+"""TEST INFRASTRUCTURE: run g2_conv_halo_tf32 of genesis_b200/csrc/igemm_halo.cu under the CPU emulation on one case and compare
+with torch (integer-valued data: every product and sum is exact in fp32, so the comparison is exact).
+
+    python tests/cuda_emu/run_halo_emu.py mode N H W Ci Co R stride pad act [persistent]
+
+Runs in its own process: the kernel's environment switches are read once per process, and a protocol deadlock aborts."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import build_emu  # noqa: E402
+
+
+def main():
+    mode, N, H, W, Ci, Co, R, s, p, act = (int(a) for a in sys.argv[1:11])
+    if len(sys.argv) > 11 and sys.argv[11] == 'persistent':
+        os.environ['G2_HALO_PERSISTENT'] = '1'
+    lib = ctypes.CDLL(build_emu.build('igemm_halo.cu'))
+    rng = np.random.RandomState(0)
+    x = torch.from_numpy(rng.randint(-3, 4, (N, Ci, H, W)).astype(np.float32))
+    w = torch.from_numpy(rng.randint(-2, 3, (Co, Ci, R, R) if mode == 0 else (Ci, Co, R, R)).astype(np.float32))
+    b = torch.from_numpy(rng.randint(-4, 5, (Co,)).astype(np.float32))
+    if mode == 0:
+        ref = F.conv2d(x.double(), w.double(), b.double(), stride=s, padding=p)
+        wp = w.permute(2, 3, 0, 1).reshape(R * R, Co, Ci)
+    else:
+        ref = F.conv_transpose2d(x.double(), w.double(), b.double(), stride=s, padding=p, output_padding=s - 1)
+        wp = w.permute(2, 3, 1, 0).reshape(R * R, Co, Ci)
+    if act == 1:
+        ref = F.relu(ref)
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    xg = np.ascontiguousarray(x.permute(0, 2, 3, 1).numpy())
+    wpn = np.ascontiguousarray(wp.numpy())
+    out = np.full((N, Ho, Wo, Co), np.nan, np.float32)
+    P = ctypes.c_void_p
+    assert lib.g2_conv_halo_supported(N, H, W, Ci, Ho, Wo, Co, R, R, s, p, mode) == 1
+    rc = lib.g2_conv_halo_tf32(xg.ctypes.data_as(P), wpn.ctypes.data_as(P), b.numpy().ctypes.data_as(P), out.ctypes.data_as(P),
+                               N, H, W, Ci, Ho, Wo, Co, R, R, s, p, mode, act, None)
+    assert rc == 0, rc
+    got = torch.from_numpy(out).permute(0, 3, 1, 2).double()
+    assert torch.isfinite(got).all(), 'unwritten outputs'
+    err = (got - ref).abs().max().item()
+    print('max abs err', err)
+    assert err == 0.0
+    print('OK')
+
+
+if __name__ == '__main__':
+    main()
