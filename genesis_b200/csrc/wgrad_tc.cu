@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cstdlib>
 #include <mutex>
 
 namespace wg {
@@ -548,7 +549,8 @@ bool make_hplan(int N, int Hg, int Wg, int Cg, int Ht, int Wt, int Ct, int R, in
     const int max_cbs = 512 / (pl->ngroups * Ct);
     pl->grid_y = g2_cdiv(ncb, max_cbs);
     pl->cbs_per_cta = g2_cdiv(ncb, pl->grid_y);
-    int splits = 148 / pl->grid_y;
+    static const int ctas = [] { const char* e = getenv("G2_WGRAD_HALO_CTAS"); const int v = e && *e ? atoi(e) : 148; return v < 1 ? 1 : v; }();
+    int splits = ctas / pl->grid_y;         // one CTA per SM; the CPU emulation lowers it so that a CTA accumulates several windows
     if (splits < 1) splits = 1;
     if (splits > pl->windows) splits = pl->windows;
     pl->wpc = g2_cdiv(pl->windows, splits);

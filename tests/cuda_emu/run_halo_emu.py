@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE: run g2_conv_halo_tf32 of genesis_b200/csrc/igemm_halo.cu under the CPU emulation on one case and compare
 with torch (integer-valued data: every product and sum is exact in fp32, so the comparison is exact).
 
-    python tests/cuda_emu/run_halo_emu.py mode N H W Ci Co R stride pad act [persistent]
+    python tests/cuda_emu/run_halo_emu.py "mode N H W Ci Co R stride pad act; ..." [persistent]
 
 Runs in its own process: the kernel's environment switches are read once per process, and a protocol deadlock aborts."""
 import ctypes
@@ -16,11 +16,8 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import build_emu  # noqa: E402
 
 
-def main():
-    mode, N, H, W, Ci, Co, R, s, p, act = (int(a) for a in sys.argv[1:11])
-    if len(sys.argv) > 11 and sys.argv[11] == 'persistent':
-        os.environ['G2_HALO_PERSISTENT'] = '1'
-    lib = ctypes.CDLL(build_emu.build('igemm_halo.cu'))
+def run_case(lib, case):
+    mode, N, H, W, Ci, Co, R, s, p, act = case
     rng = np.random.RandomState(0)
     x = torch.from_numpy(rng.randint(-3, 4, (N, Ci, H, W)).astype(np.float32))
     w = torch.from_numpy(rng.randint(-2, 3, (Co, Ci, R, R) if mode == 0 else (Ci, Co, R, R)).astype(np.float32))
@@ -47,7 +44,16 @@ def main():
     err = (got - ref).abs().max().item()
     print('max abs err', err)
     assert err == 0.0
-    print('OK')
+    print('OK', case)
+
+
+def main():
+    if len(sys.argv) > 2 and sys.argv[2] == 'persistent':
+        os.environ['G2_HALO_PERSISTENT'] = '1'
+    lib = ctypes.CDLL(build_emu.build('igemm_halo.cu'))
+    for c in sys.argv[1].split(';'):
+        if c.strip():
+            run_case(lib, tuple(int(a) for a in c.split()))
 
 
 if __name__ == '__main__':

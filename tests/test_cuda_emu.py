@@ -343,3 +343,57 @@ def test_seg_metrics_kernel(emu, seed, deg, K):
     for j, key in enumerate(('ari', 'ari_fg', 'msc', 'msc_fg', 'msc_scaled', 'msc_fg_scaled')):
         np.testing.assert_allclose(out[:, j], want[key], atol=1e-12, err_msg=key)
     np.testing.assert_array_equal(seg, want['instance_seg'].reshape(B, Pn))
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 / TMA kernels
+def _run_child(script, cases, mode, env_extra):
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, EMU_TIMEOUT_S='20', **env_extra)
+    cmd = [sys.executable, os.path.join(here, 'cuda_emu', script), ';'.join(cases)] + ([mode] if mode else [])
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count('OK') == len(cases), r.stdout[-2000:]
+
+
+HALO_CASES = [  # mode N H W Ci Co R stride pad act
+    '0 2 18 20 32 32 3 1 1 1',        # 3x3, resident weights in the persistent variant
+    '1 3 16 16 64 64 5 1 2 0',        # 5x5 conv-transpose, two channel blocks, several images per CTA, weight ring
+    '0 2 19 23 32 32 3 1 1 0',        # ragged: bottom-edge tiles
+    '1 2 16 16 32 64 5 2 2 1',        # stride-2 conv-transpose: four sub-pixel classes
+    '0 2 16 16 32 256 3 1 1 1',       # two output-channel blocks: bias reload between items
+]
+
+
+def test_halo_conv_kernel_calibrates_the_model():
+    """conv_halo_kernel is validated on a B200 (tests/test_halo_gpu.py); under the functional model of mbarriers, TMA and
+    tcgen05 (tests/cuda_emu/cuda_emu_sm100.h) it must give the same exact answers -- this is what entitles the model to say
+    anything about the kernels below."""
+    _run_child('run_halo_emu.py', HALO_CASES[:4], None, {})
+
+
+def test_persistent_halo_kernel_under_the_model():
+    """conv_halo_persistent_kernel (G2_HALO_PERSISTENT=1, never run on a GPU): exact results with two CTAs walking several
+    items each -- double-buffered windows, alternating accumulator sets, weight ring and resident weights, bias reload."""
+    _run_child('run_halo_emu.py', HALO_CASES, 'persistent', {'G2_HALO_PERSISTENT_CTAS': '2'})
+
+
+WGRAD_CASES = [  # N Hg Wg Cg Ct R pad
+    '4 18 18 32 32 3 1',              # 3x3: three-tap groups, the unused fourth atom reads the zeroed slack
+    '3 20 20 64 32 5 2',              # 5x5: row groups + a column group + a single, two channel blocks per CTA, 2 windows per CTA
+    '5 16 16 128 64 5 2',             # grid_y = 4, ten windows per CTA
+    '1 19 23 32 64 3 1',              # ragged
+    '2 22 22 32 32 3 0',              # VALID
+]
+
+
+def test_wgrad_tile_kernel_calibrates_the_mn_major_model():
+    """wgrad_tc_kernel is validated on a B200 (tests/test_tc_gpu.py): MN-major operands, SWIZZLE_128B_ATOM_32B boxes."""
+    _run_child('run_wgrad_emu.py', WGRAD_CASES[:2], None, {})
+
+
+def test_halo_wgrad_kernel_under_the_model():
+    """wgrad_halo_kernel (G2_WGRAD_HALO=1, never run on a GPU): taps as LBO-strided M atoms of one resident window, exact under
+    the model's rule that the swizzle is a function of the absolute shared-memory address (the rule the B200 probe in
+    tests/test_pending_next_round.py checks on the hardware)."""
+    _run_child('run_wgrad_emu.py', WGRAD_CASES, 'halo', {'G2_WGRAD_HALO_CTAS': '4'})
