@@ -1,9 +1,12 @@
-// TEST INFRASTRUCTURE: run plain-SIMT CUDA kernels of genesis_b200/csrc on the CPU, one OS thread per CUDA thread.
+// TEST INFRASTRUCTURE: run the CUDA kernels of genesis_b200/csrc on the CPU, one fiber (ucontext) per CUDA thread.
 //
 // The kernel SOURCE is compiled unchanged with g++ (tests/test_cuda_emu.py extracts the kernel namespace of a .cu file and
 // wraps it): the CUDA keywords become no-ops, threadIdx / blockIdx are thread-local, __shared__ becomes `static` (blocks run one
 // after another, so one copy per kernel instantiation is the block's shared memory), __syncthreads is a barrier over the
-// block's threads, warp shuffles exchange through a per-warp slot array between two warp barriers.  This checks what a
+// block's threads, warp shuffles exchange through a per-warp slot array between two warp barriers.  The threads of a block are
+// cooperative fibers on ONE OS thread, scheduled round-robin and switched only at barriers / shuffles / mbarrier waits: runs are
+// deterministic, a kernel without barriers costs well under a microsecond per CUDA thread, and a round in which no fiber makes
+// progress is reported as a deadlock instead of hanging.  This checks what a
 // kernel written without a GPU at hand is most likely to get wrong -- index arithmetic, tile edges, barrier placement, the
 // order of a scan -- against numpy/torch references.  It says nothing about performance, and it cannot run the tcgen05 /
 // TMA kernels.  Nothing in the product uses it.
@@ -12,10 +15,14 @@
 #include <cmath>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <thread>
+#include <ucontext.h>
 #include <vector>
 
 #define __global__
@@ -42,20 +49,32 @@ typedef int cudaError_t;
 enum { cudaSuccess = 0 };
 
 namespace emu {
-// reusable barrier (C++17 has no std::barrier)
+struct Fiber {
+    ucontext_t ctx;
+    dim3 tid;
+    bool done;
+    const char* waiting;        // what the fiber is blocked on (for the deadlock report)
+    unsigned wait_a, wait_b;
+};
+extern ucontext_t sched_ctx;
+extern Fiber* cur;
+extern long progress;           // bumped by every state change another fiber could be waiting for
+static inline void yield(const char* why = "barrier", unsigned a = 0, unsigned b = 0) {
+    cur->waiting = why; cur->wait_a = a; cur->wait_b = b;
+    swapcontext(&cur->ctx, &sched_ctx);
+}
+// reusable barrier over n fibers
 class Barrier {
 public:
     explicit Barrier(int n) : n_(n), count_(0), gen_(0) {}
     void wait() {
-        std::unique_lock<std::mutex> lk(m_);
-        const int g = gen_;
-        if (++count_ == n_) { count_ = 0; ++gen_; cv_.notify_all(); }
-        else cv_.wait(lk, [&] { return gen_ != g; });
+        ++progress;
+        if (++count_ == n_) { count_ = 0; ++gen_; }
+        else { const long g = gen_; while (gen_ == g) yield("barrier", (unsigned)n_, (unsigned)count_); }
     }
 private:
-    int n_, count_, gen_;
-    std::mutex m_;
-    std::condition_variable cv_;
+    int n_, count_;
+    long gen_;
 };
 struct Block {
     Barrier* all;
@@ -65,6 +84,8 @@ struct Block {
 extern thread_local Block* block;
 extern std::mutex atomic_mutex;
 extern unsigned char dyn_smem[256 * 1024];       // 1024-byte aligned: offsets into it ARE the shared-memory addresses
+extern std::function<void()>* body_fn;
+void trampoline();
 }  // namespace emu
 
 extern thread_local dim3 threadIdx, blockIdx;
@@ -77,6 +98,15 @@ namespace emu {
 thread_local Block* block = nullptr;
 std::mutex atomic_mutex;
 alignas(1024) unsigned char dyn_smem[256 * 1024];
+ucontext_t sched_ctx;
+Fiber* cur = nullptr;
+long progress = 0;
+std::function<void()>* body_fn = nullptr;
+void trampoline() {
+    (*body_fn)();
+    cur->done = true;
+    swapcontext(&cur->ctx, &sched_ctx);
+}
 }
 #endif
 
@@ -136,17 +166,22 @@ static inline float rsqrtf(float x) { return 1.f / sqrtf(x); }
 static inline float __fdividef(float a, float b) { return a / b; }
 
 namespace emu {
-// Run `body` as a grid of `grid` blocks of `block` threads (1-D blocks; x must be a multiple of 32), blocks one after another.
+// Run `body` as a grid of `grid` blocks of `blk` threads (block size a multiple of 32), blocks one after another.
 template <class F> static inline void launch(dim3 grid, dim3 blk, F body) {
     ::blockDim = blk; ::gridDim = grid;
     const int n = (int)(blk.x * blk.y * blk.z);
+    constexpr size_t STACK = 256 * 1024;
+    static std::vector<char*> stacks;                 // reused across launches, never initialised
+    while ((int)stacks.size() < n) stacks.push_back((char*)std::malloc(STACK));
+    std::function<void()> fn = body;
+    body_fn = &fn;
+    std::vector<Fiber> fibers((size_t)n);
     for (unsigned bz = 0; bz < grid.z; ++bz)
         for (unsigned by = 0; by < grid.y; ++by)
             for (unsigned bx = 0; bx < grid.x; ++bx) {
                 Block b;
                 Barrier all(n);
                 b.all = &all;
-                std::vector<Barrier> wb;
                 const int nw = (n + 31) / 32;
                 std::vector<std::unique_ptr<Barrier>> own;
                 for (int w = 0; w < nw; ++w) {
@@ -155,16 +190,43 @@ template <class F> static inline void launch(dim3 grid, dim3 blk, F body) {
                     b.warps.push_back(own.back().get());
                     b.slots.emplace_back(32, 0);
                 }
-                std::vector<std::thread> ts;
-                ts.reserve(n);
-                for (int t = 0; t < n; ++t)
-                    ts.emplace_back([&, t] {
-                        emu::block = &b;
-                        ::threadIdx = dim3((unsigned)t % blk.x, ((unsigned)t / blk.x) % blk.y, (unsigned)t / (blk.x * blk.y));
-                        ::blockIdx = dim3(bx, by, bz);
-                        body();
-                    });
-                for (auto& th : ts) th.join();
+                emu::block = &b;
+                ::blockIdx = dim3(bx, by, bz);
+                for (int t = 0; t < n; ++t) {
+                    Fiber& f = fibers[(size_t)t];
+                    getcontext(&f.ctx);
+                    f.ctx.uc_stack.ss_sp = stacks[(size_t)t];
+                    f.ctx.uc_stack.ss_size = STACK;
+                    f.ctx.uc_link = nullptr;
+                    f.tid = dim3((unsigned)t % blk.x, ((unsigned)t / blk.x) % blk.y, (unsigned)t / (blk.x * blk.y));
+                    f.done = false; f.waiting = nullptr;
+                    makecontext(&f.ctx, (void (*)())trampoline, 0);
+                }
+                int live = n;
+                while (live) {
+                    const long before = progress;
+                    for (int t = 0; t < n; ++t) {
+                        Fiber& f = fibers[(size_t)t];
+                        if (f.done) continue;
+                        cur = &f;
+                        ::threadIdx = f.tid;
+                        swapcontext(&sched_ctx, &f.ctx);
+                        if (f.done) { --live; ++progress; }
+                    }
+                    if (live && progress == before) {
+                        std::fprintf(stderr, "emu: DEADLOCK in block (%u,%u,%u): %d of %d threads blocked\n", bx, by, bz, live, n);
+                        int shown = 0;
+                        for (int t = 0; t < n && shown < 12; ++t)
+                            if (!fibers[(size_t)t].done && (t % 32) == 0) {
+                                std::fprintf(stderr, "  thread %d (warp %d): %s 0x%x %u\n", t, t / 32,
+                                             fibers[(size_t)t].waiting ? fibers[(size_t)t].waiting : "?", fibers[(size_t)t].wait_a,
+                                             fibers[(size_t)t].wait_b);
+                                ++shown;
+                            }
+                        std::abort();
+                    }
+                }
             }
+    body_fn = nullptr;
 }
 }  // namespace emu

@@ -61,8 +61,6 @@ static inline uint32_t swizzle_addr(uint32_t a, int mode) {
 }
 
 // ---- mbarrier: the 64-bit word in shared memory holds {phase:1 | pending:15 | count:15 | - | tx:32}
-extern std::mutex mbar_mutex;
-extern std::condition_variable mbar_cv;
 struct MbarView { uint64_t* w; };
 static inline void mbar_complete_if_done(uint64_t* w) {
     const int pending = (int)((*w >> 1) & 0x7FFF), count = (int)((*w >> 16) & 0x7FFF);
@@ -70,15 +68,14 @@ static inline void mbar_complete_if_done(uint64_t* w) {
     if (pending == 0 && tx == 0) {
         const uint64_t phase = (*w & 1) ^ 1;
         *w = phase | ((uint64_t)count << 1) | ((uint64_t)count << 16);
-        mbar_cv.notify_all();
     }
 }
 static inline void mbar_init(uint32_t a, int count) {
-    std::lock_guard<std::mutex> lk(mbar_mutex);
+    ++progress;
     *(uint64_t*)smem_ptr(a) = ((uint64_t)count << 1) | ((uint64_t)count << 16);
 }
 static inline void mbar_add(uint32_t a, int arrivals, int32_t tx_delta) {
-    std::lock_guard<std::mutex> lk(mbar_mutex);
+    ++progress;
     uint64_t* w = (uint64_t*)smem_ptr(a);
     int pending = (int)((*w >> 1) & 0x7FFF);
     int32_t tx = (int32_t)(*w >> 32) + tx_delta;
@@ -100,18 +97,8 @@ static inline uint32_t mbar_try_wait(uint32_t a, uint32_t parity) {
     return 1;
 }
 static inline uint32_t mbar_try_wait_lane0(uint32_t a, uint32_t parity) {
-    std::unique_lock<std::mutex> lk(mbar_mutex);
     uint64_t* w = (uint64_t*)smem_ptr(a);
-    static const int limit = std::getenv("EMU_TIMEOUT_S") ? std::atoi(std::getenv("EMU_TIMEOUT_S")) : 60;
-    const bool ok = mbar_cv.wait_for(lk, std::chrono::seconds(limit), [&] { return (uint32_t)(*w & 1) != (parity & 1u); });
-    if (!ok) {
-        std::fprintf(stderr, "emu: DEADLOCK block %u thread %u (warp %u) waits on mbarrier 0x%x parity %u; word: phase %u pending %u tx %d\n",
-                     ::blockIdx.x, ::threadIdx.x, ::threadIdx.x >> 5, a, parity, (unsigned)(*w & 1), (unsigned)((*w >> 1) & 0x7FFF),
-                     (int)(int32_t)(*w >> 32));
-        lk.unlock();
-        std::this_thread::sleep_for(std::chrono::seconds(2));       // let the other stuck threads report too
-        std::abort();
-    }
+    while ((uint32_t)(*w & 1) == (parity & 1u)) yield("mbarrier", a, parity);     // the scheduler reports a deadlock
     return 1;
 }
 
@@ -198,8 +185,6 @@ static inline void named_barrier(int id, int n) {
 static inline void unsupported(const char* what) { std::fprintf(stderr, "emu: %s is not modelled\n", what); std::abort(); }
 
 #ifdef CUDA_EMU_MAIN
-std::mutex mbar_mutex;
-std::condition_variable mbar_cv;
 float tmem[128][512];
 std::mutex named_mutex;
 std::map<int, std::unique_ptr<Barrier>> named;
