@@ -142,19 +142,22 @@ def translate_asm(src):
     return out + src[pos:]
 
 
-def inline_includes(src):
-    """#include "umma.cuh" -> its text (it holds inline PTX that must be translated too)"""
+def inline_includes(src, seen):
+    """#include "umma.cuh" -> its text, once per translation unit (it holds inline PTX that must be translated too)"""
     def sub(m):
         name = m.group(1)
         if name == 'common.cuh':
             return m.group(0)
+        if name in seen:
+            return ''
+        seen.add(name)
         text = open(os.path.join(CSRC, name)).read().replace('#pragma once', '')
-        return inline_includes(text)
+        return inline_includes(text, seen)
     return re.sub(r'#include\s+"(\w+\.cuh)"', sub, src)
 
 
-def transform(src):
-    src = translate_asm(inline_includes(src))
+def transform(src, seen=None):
+    src = translate_asm(inline_includes(src, set() if seen is None else seen))
     out, pos = '', 0
     for m in re.finditer(r'<<<', src):
         i = m.start()
@@ -186,10 +189,17 @@ def transform(src):
     return re.sub(r'extern\s+__shared__\s+(\w+)\s+(\w+)\[\];', r'\1* \2 = reinterpret_cast<\1*>(emu::dyn_smem);', out)
 
 
+# files whose extern "C" entry points call into another file: built into one shared object
+LINK_WITH = {'igemm_tc.cu': ['igemm_halo.cu']}
+
+
 def build(cu_name):
     """-> path of the shared object emulating genesis_b200/csrc/<cu_name> (cached on the source hash)."""
     src = open(os.path.join(CSRC, cu_name)).read()
-    code = PRELUDE + transform(src)
+    seen = set()
+    code = PRELUDE + transform(src, seen)
+    for other in LINK_WITH.get(cu_name, []):            # same translation unit: one emulator state, shared headers once
+        code += '\n// ---- linked: %s\n' % other + transform(open(os.path.join(CSRC, other)).read(), seen)
     deps = code + ''.join(open(os.path.join(HERE, h)).read() for h in ('cuda_emu.h', 'cuda_emu_sm100.h')) + \
         open(os.path.join(CSRC, 'common.cuh')).read()
     tag = hashlib.sha1(deps.encode()).hexdigest()[:12]
