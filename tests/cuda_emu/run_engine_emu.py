@@ -3,7 +3,7 @@ emulation of the kernel sources (tests/cuda_emu/emu_lib.py), compared with the o
 noise: loss terms, masks and the gradient of every parameter.  The path exercised is the product's -- plug-in ->
 genesis_b200.ops autograd Functions -> C-ABI argument marshalling -> kernel source -- minus the GPU.
 
-    python tests/cuda_emu/run_engine_emu.py MODEL K B [key=value ...] [--fused-latent] [--skinny] [--precision fp32|tf32]
+    python tests/cuda_emu/run_engine_emu.py MODEL K B [key=value ...] [--fused-latent] [--skinny] [--direct] [--precision fp32|tf32]
                                             [--param-add name=value] [--gen multid]
 
 Minutes per run (a 64x64 model is a few GFLOP of scalar C++); used by hand and by the opt-in test
@@ -41,6 +41,8 @@ def parse(argv):
             flags['fused'] = True
         elif a == '--skinny':
             flags['skinny'] = True
+        elif a == '--direct':
+            flags['direct'] = True
         elif a in ('--precision', '--gen'):
             flags[a[2:]] = next(it)
         elif a == '--param-add':
@@ -66,6 +68,11 @@ def main():
     m.train()
     x = torch.from_numpy(synth.GENERATORS[flags['gen']](B, 64, 5)[0])
     sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    if flags.get('direct'):     # trainer.TrainStep's mode: kernels accumulate weight / bias gradients straight into pre-zeroed .grad
+        for p_ in m.parameters():
+            p_.grad = torch.zeros_like(p_)
+        ops.set_side_streams(False)
+        ops.set_direct_grad(True)
     m.set_noise_tape(O.NoiseTape(seed=3))
     t0 = time.time()
     out = m(x.as_subclass(cpu_ops_mock.AsCuda))
@@ -76,6 +83,7 @@ def main():
     else:
         U.engine_total_loss(losses).backward()
     t2 = time.time()
+    ops.set_direct_grad(False)
     P = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in sd0.items()}
     fwd = M.vae_forward if model == 'vae' else M.FORWARD[model]
     ref = fwd(P, x, O.NoiseTape(seed=3), cfg, training=True)
