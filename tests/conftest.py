@@ -8,6 +8,12 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+if os.environ.get('G2_EMU') == '1':      # GPU tests on the CPU emulation of the kernel sources (tests/cuda_emu/emu_mode.py)
+    sys.path.insert(0, os.path.join(ROOT, 'tests', 'cuda_emu'))
+    import emu_mode
+    emu_mode.enable()
+
+
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
 
