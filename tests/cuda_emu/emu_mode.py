@@ -24,6 +24,15 @@ def _is_cuda(d):
     return False
 
 
+class HostTensor(torch.Tensor):
+    """What `.cpu()` returns in emulation mode: the one kind of tensor that answers is_cuda = False, so that the product's
+    `CPU tensors are rejected` behaviour stays testable."""
+
+    @property
+    def is_cuda(self):
+        return False
+
+
 class CpuAsCuda(TorchFunctionMode):
     def __torch_function__(self, func, types, args=(), kwargs=None):
         kwargs = dict(kwargs or {})
@@ -31,7 +40,9 @@ class CpuAsCuda(TorchFunctionMode):
             kwargs['device'] = 'cpu'
         name = getattr(func, '__name__', '')
         if name == 'cuda' and args and isinstance(args[0], torch.Tensor):
-            return args[0]
+            return args[0].as_subclass(torch.Tensor) if isinstance(args[0], HostTensor) else args[0]
+        if name == 'cpu' and args and isinstance(args[0], torch.Tensor) and type(args[0]) is torch.Tensor:
+            return args[0].as_subclass(HostTensor)
         if name in ('to', 'pin_memory') and args and isinstance(args[0], torch.Tensor):
             if name == 'pin_memory':
                 return args[0]
