@@ -3,7 +3,12 @@ part of the `-m gpu` gate (a wrong expectation in an unvalidated test must not m
 
     G2_RUN_PENDING=1 python -m pytest tests/test_pending_next_round.py -q
 
-on a GPU box; once green they move into the regular GPU files with the `gpu` marker."""
+on a GPU box; once green they move into the regular GPU files with the `gpu` marker.
+
+They HAVE run on the CPU emulation of the kernel sources (G2_EMU=1 G2_RUN_PENDING=1, tests/cuda_emu/emu_mode.py; minutes per test):
+every test below except the hardware probe and the two full-size ones passes there (profiles/r01_emulated_gpu_tests.txt), so
+what remains open on the B200 is the hardware itself (the MN-major probe), TF32 rounding against the stated tolerances, and
+speed."""
 import os
 
 import pytest
