@@ -229,6 +229,7 @@ struct NormBwdFinP {
     float *m1, *m2;                     // [Ns, Cy]
     float *dg0, *db0, *dg1, *db1;       // parameter grads (may be null)
     int N, HW, Cy, half, mode, groups;
+    int accumulate;                     // 1: add the parameter gradients to dg* / db* (direct-gradient mode: they point into param.grad)
 };
 
 // Blocks [0, main_blocks): one thread per (n, c) -> m1, m2 (instance / group mode).
@@ -254,8 +255,8 @@ __global__ void norm_bwd_finalize_kernel(const NormBwdFinP p, int main_blocks) {
         }
         const bool sec = c >= p.half; const int ch = sec ? c - p.half : c;
         float* dg = sec ? p.dg1 : p.dg0; float* db = sec ? p.db1 : p.db0;
-        if (dg) dg[ch] = (float)s2;
-        if (db) db[ch] = (float)s1;
+        if (dg) dg[ch] = p.accumulate ? dg[ch] + (float)s2 : (float)s2;
+        if (db) db[ch] = p.accumulate ? db[ch] + (float)s1 : (float)s1;
         return;
     }
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -392,16 +393,30 @@ int g2_norm_bwd_stats_f32(const float* y, const float* dout, const float* scale,
     G2_LAUNCH_RET();
 }
 
-int g2_norm_bwd_finalize_f32(const double* sums2, const float* g0, const float* g1, float* m1, float* m2, float* dg0,
-                             float* db0, float* dg1, float* db1, int N, int HW, int Cy, int half, int mode, int groups,
-                             cudaStream_t stream) {
+static int norm_bwd_finalize_impl(const double* sums2, const float* g0, const float* g1, float* m1, float* m2, float* dg0,
+                                  float* db0, float* dg1, float* db1, int N, int HW, int Cy, int half, int mode, int groups,
+                                  int accumulate, cudaStream_t stream) {
     G2_CHECK_ARG(sums2 && m1 && m2 && N > 0 && Cy > 0 && half > 0 && half <= Cy);
     G2_CHECK_ARG(mode == G2_NORM_BATCH || mode == G2_NORM_INSTANCE || mode == G2_NORM_GROUP);
     if (mode == G2_NORM_GROUP) G2_CHECK_ARG(groups > 0 && Cy % groups == 0);
-    NormBwdFinP p{sums2, g0, g1, m1, m2, dg0, db0, dg1, db1, N, HW, Cy, half, mode, groups};
+    NormBwdFinP p{sums2, g0, g1, m1, m2, dg0, db0, dg1, db1, N, HW, Cy, half, mode, groups, accumulate ? 1 : 0};
     const int main_blocks = mode == G2_NORM_BATCH ? 0 : g2_cdiv((long)N * Cy, 128);
     norm_bwd_finalize_kernel<<<main_blocks + g2_cdiv((long)Cy * 32, 128), 128, 0, stream>>>(p, main_blocks);
     G2_LAUNCH_RET();
+}
+
+int g2_norm_bwd_finalize_f32(const double* sums2, const float* g0, const float* g1, float* m1, float* m2, float* dg0,
+                             float* db0, float* dg1, float* db1, int N, int HW, int Cy, int half, int mode, int groups,
+                             cudaStream_t stream) {
+    return norm_bwd_finalize_impl(sums2, g0, g1, m1, m2, dg0, db0, dg1, db1, N, HW, Cy, half, mode, groups, 0, stream);
+}
+
+// As above with `accumulate`: the parameter gradients are ADDED to dg* / db* (which then point into param.grad), one thread per
+// element, so the caller orders it after other writers of those tensors on the stream.
+int g2_norm_bwd_finalize_acc_f32(const double* sums2, const float* g0, const float* g1, float* m1, float* m2, float* dg0,
+                                 float* db0, float* dg1, float* db1, int N, int HW, int Cy, int half, int mode, int groups,
+                                 int accumulate, cudaStream_t stream) {
+    return norm_bwd_finalize_impl(sums2, g0, g1, m1, m2, dg0, db0, dg1, db1, N, HW, Cy, half, mode, groups, accumulate, stream);
 }
 
 int g2_norm_bwd_apply_f32(const float* y, const float* dout, const float* scale, const float* shift, const float* mean,

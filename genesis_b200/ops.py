@@ -202,6 +202,13 @@ def set_direct_grad(on):
     _DIRECT['on'] = bool(on)
 
 
+_NORM_DIRECT = {'on': os.environ.get('G2_NORM_DIRECT', '0') == '1'}     # experimental: off until timed on a B200
+
+
+def set_norm_direct(on):
+    _NORM_DIRECT['on'] = bool(on)
+
+
 def _direct(p):
     return (_DIRECT['on'] and p is not None and p.is_leaf and p.requires_grad and p.grad is not None
             and p.grad.is_contiguous() and p.grad.data_ptr() % 16 == 0)
@@ -490,6 +497,7 @@ class _NormPost(Function):
         _call('g2_norm_apply_f32', y, scale, shift, out, N, HW, C, sn, post)
         ctx.save_for_backward(y, scale, shift, mean, rstd, g0, g1)
         ctx.cfg = (mode, post, groups, half)
+        ctx.params = (g0, b0, g1, b1)
         return out
 
     @staticmethod
@@ -512,11 +520,20 @@ class _NormPost(Function):
         sums2 = _new(y, N, Cy, 2, dtype=torch.float64)
         _call('g2_norm_bwd_stats_f32', y, dout, scale, shift, mean, rstd, sums2, N, HW, C, sn, post)
         m1, m2 = _new(y, Ns, Cy), _new(y, Ns, Cy)
-        dg0 = _new(y, half) if g0 is not None else None
-        db0 = _new(y, half) if g0 is not None else None
-        dg1 = _new(y, Cy - half) if g1 is not None else None
-        db1 = _new(y, Cy - half) if g1 is not None else None
-        _call('g2_norm_bwd_finalize_f32', sums2, g0, g1, m1, m2, dg0, db0, dg1, db1, N, HW, Cy, half, mode, groups)
+        params = [p_ for p_ in ctx.params if p_ is not None]
+        if _NORM_DIRECT['on'] and params and all(_direct(p_) for p_ in params):
+            # direct-gradient mode (experimental switch): the finalize kernel adds the affine-parameter gradients to param.grad
+            # itself -- no four small tensors and no AccumulateGrad `add_` per norm layer.  The same stream orders repeated
+            # uses of one layer (MONet's recurrent UNet); nothing else writes these .grad tensors.
+            pg0, pb0, pg1, pb1 = ((p_.grad if p_ is not None else None) for p_ in ctx.params)
+            _call('g2_norm_bwd_finalize_acc_f32', sums2, g0, g1, m1, m2, pg0, pb0, pg1, pb1, N, HW, Cy, half, mode, groups, 1)
+            dg0 = db0 = dg1 = db1 = None
+        else:
+            dg0 = _new(y, half) if g0 is not None else None
+            db0 = _new(y, half) if g0 is not None else None
+            dg1 = _new(y, Cy - half) if g1 is not None else None
+            db1 = _new(y, Cy - half) if g1 is not None else None
+            _call('g2_norm_bwd_finalize_f32', sums2, g0, g1, m1, m2, dg0, db0, dg1, db1, N, HW, Cy, half, mode, groups)
         dy = torch.empty_like(y)
         _call('g2_norm_bwd_apply_f32', y, dout, scale, shift, mean, rstd, m1, m2, dy, N, HW, C, sn, post)
         return (dy, dg0, db0, dg1, db1) + (None,) * 10

@@ -97,6 +97,10 @@ int g2_norm_bwd_stats_f32(const float* y, const float* dout, const float* scale,
 int g2_norm_bwd_finalize_f32(const double* sums2, const float* g0, const float* g1, float* m1, float* m2,
                              float* dg0, float* db0, float* dg1, float* db1, int N, int HW, int Cy, int half,
                              int mode, int groups, g2_stream_t stream);
+/* the same with `accumulate`: dg0 / db0 / dg1 / db1 are added to (direct-gradient mode: they point into param.grad) */
+int g2_norm_bwd_finalize_acc_f32(const double* sums2, const float* g0, const float* g1, float* m1, float* m2,
+                                 float* dg0, float* db0, float* dg1, float* db1, int N, int HW, int Cy, int half,
+                                 int mode, int groups, int accumulate, g2_stream_t stream);
 int g2_norm_bwd_apply_f32(const float* y, const float* dout, const float* scale, const float* shift,
                           const float* mean, const float* rstd, const float* m1, const float* m2, float* dy,
                           int N, int HW, int C, int sn, int post, g2_stream_t stream);

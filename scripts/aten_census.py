@@ -30,11 +30,18 @@ class Census(TorchDispatchMode):
     def __init__(self):
         super().__init__()
         self.ops = collections.Counter()
+        self.sites = collections.Counter()
+        self.trace = set(a[8:].split(',')[0] for a in sys.argv if a.startswith('--trace=')) | set(sum([a[8:].split(',') for a in sys.argv if a.startswith('--trace=')], []))
 
     def __torch_dispatch__(self, func, types, args=(), kwargs=None):
         name = func.overloadpacket.__name__
         if name not in VIEWS:
             self.ops[name] += 1
+            if name in self.trace:
+                import traceback
+                fr = [f for f in traceback.extract_stack() if 'genesis_b200' in f.filename]
+                key = '%s:%d' % (os.path.basename(fr[-1].filename), fr[-1].lineno) if fr else 'autograd engine'
+                self.sites[(name, key)] += 1
         return func(*args, **(kwargs or {}))
 
 
@@ -46,6 +53,7 @@ def main():
     ops.set_precision('fp32')
     ops.set_fused_latent('--fused-latent' in sys.argv)
     ops.set_skinny_gemm('--skinny' in sys.argv)
+    sys.argv = [a for a in sys.argv]
     m, cfg = build_engine_model(model, K, 64)
     m.train()
     x = torch.from_numpy(synth.GENERATORS['multid'](1, 64, 5)[0])
@@ -60,6 +68,8 @@ def main():
     ops.set_direct_grad(False)
     print('%s K=%d %s: %d ATen operators, %d C-ABI calls' % (model, K, ' '.join(sys.argv[3:]) or 'default', sum(c.ops.values()), len(emu.calls)))
     print('  top ATen:', ', '.join('%s x%d' % kv for kv in c.ops.most_common(14)))
+    for (name, site), n in c.sites.most_common(24):
+        print('    %-8s %-40s x%d' % (name, site, n))
 
 
 if __name__ == '__main__':

@@ -22,7 +22,7 @@ for p in 0 1; do
 done
 tail -24 gpurun_out/pending_wgrad_bench.txt >> gpurun_out/pending_summary.txt
 echo "== 4. whole step: fused latent kernels off / on, persistent off / on, halo wgrad off / on, skinny GEMM off / on" | tee -a gpurun_out/pending_summary.txt
-for cfg in "G2_FUSED_LATENT=0 G2_HALO_PERSISTENT=0" "G2_FUSED_LATENT=1 G2_HALO_PERSISTENT=0" "G2_FUSED_LATENT=1 G2_HALO_PERSISTENT=1" "G2_FUSED_LATENT=0 G2_WGRAD_HALO=1" "G2_FUSED_LATENT=0 G2_SKINNY_GEMM=1" "G2_FUSED_LATENT=1 G2_SKINNY_GEMM=1" "G2_FUSED_LATENT=1 G2_HALO_PERSISTENT=1 G2_WGRAD_HALO=1"; do
+for cfg in "G2_FUSED_LATENT=0 G2_HALO_PERSISTENT=0" "G2_FUSED_LATENT=1 G2_HALO_PERSISTENT=0" "G2_FUSED_LATENT=1 G2_HALO_PERSISTENT=1" "G2_FUSED_LATENT=0 G2_WGRAD_HALO=1" "G2_FUSED_LATENT=0 G2_SKINNY_GEMM=1" "G2_FUSED_LATENT=1 G2_SKINNY_GEMM=1" "G2_FUSED_LATENT=1 G2_SKINNY_GEMM=1 G2_NORM_DIRECT=1" "G2_FUSED_LATENT=1 G2_HALO_PERSISTENT=1 G2_WGRAD_HALO=1"; do
   echo "-- $cfg" | tee -a gpurun_out/pending_summary.txt
   env $cfg timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['last_elbo'])" | tee -a gpurun_out/pending_summary.txt
 done
