@@ -1,0 +1,129 @@
+"""CPU: genesis_b200.ops autograd Functions on CPU tensors with their C-ABI calls routed to the emulated kernel sources
+(tests/cuda_emu/emu_lib.py), against the plain-torch contract of each op (tests/cpu_ops_mock.py): argument marshalling, strides,
+workspaces and saved tensors of the Functions themselves, which the kernel-level emulation tests do not see."""
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'cuda_emu'))
+import cpu_ops_mock as R  # noqa: E402
+import emu_lib  # noqa: E402
+
+
+@pytest.fixture
+def ops(monkeypatch):
+    from genesis_b200 import ops as _ops
+    emu_lib.install(monkeypatch)
+    prev = _ops.get_precision()
+    _ops.set_precision('fp32')
+    yield _ops
+    _ops.set_precision(prev)
+
+
+def grads(out, ins, w):
+    return torch.autograd.grad((out * w).sum(), ins, allow_unused=True)
+
+
+@pytest.mark.parametrize('mode,post', [(1, 0), (2, 1), (3, 1), (1, 2)], ids=['batch-gate', 'instance-relu', 'group-relu', 'batch-none'])
+def test_norm_post(ops, mode, post):
+    torch.manual_seed(mode * 3 + post)
+    N, Hh, C = 3, 6, 16
+    Cy = 2 * C if post == 0 else C
+    y = torch.randn(N, Hh, Hh, Cy, requires_grad=True)
+    half = C if post == 0 else Cy
+    g0, b0 = (torch.rand(half) + 0.5).requires_grad_(True), torch.randn(half, requires_grad=True)
+    g1 = (torch.rand(Cy - half) + 0.5).requires_grad_(True) if post == 0 else None
+    b1 = torch.randn(Cy - half, requires_grad=True) if post == 0 else None
+    rm = [torch.zeros(half), torch.ones(half), torch.zeros(Cy - half), torch.ones(Cy - half)]
+    rm2 = [t.clone() for t in rm]
+    kw = dict(mode=mode, post=post, groups=4, training=True)
+    out = ops.norm_post(y, g0, b0, g1, b1, rm[0], rm[1], rm[2] if post == 0 else None, rm[3] if post == 0 else None, **kw)
+    ref = R.norm_post(y, g0, b0, g1, b1, rm2[0], rm2[1], rm2[2] if post == 0 else None, rm2[3] if post == 0 else None, **kw)
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-5)
+    if mode == 1:
+        torch.testing.assert_close(rm[0], rm2[0], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(rm[1], rm2[1], rtol=1e-5, atol=1e-6)
+    w = torch.randn_like(ref)
+    ins = [t for t in (y, g0, b0, g1, b1) if t is not None]
+    for a, b in zip(grads(out, ins, w), grads(ref, ins, w)):
+        torch.testing.assert_close(a, b, rtol=2e-3, atol=2e-4)
+
+
+def test_norm_post_direct_accumulation(ops):
+    """G2_NORM_DIRECT: in direct-gradient mode the finalize kernel adds the affine-parameter gradients to param.grad."""
+    torch.manual_seed(0)
+    N, Hh, C = 2, 5, 8
+    y = torch.randn(N, Hh, Hh, 2 * C, requires_grad=True)
+    ps = [torch.nn.Parameter(torch.rand(C) + 0.5), torch.nn.Parameter(torch.randn(C)), torch.nn.Parameter(torch.rand(C) + 0.5),
+          torch.nn.Parameter(torch.randn(C))]
+    base = [torch.randn(C) for _ in ps]
+    for p_, b_ in zip(ps, base):
+        p_.grad = b_.clone()
+    w = torch.randn(N, Hh, Hh, C)
+    ref = R.norm_post(y, *[p_.detach().clone().requires_grad_(True) for p_ in ps], mode=2, post=0)
+    ops.set_direct_grad(True)
+    ops.set_norm_direct(True)
+    try:
+        out = ops.norm_post(y, *ps, mode=2, post=0)
+        (out * w).sum().backward()
+    finally:
+        ops.set_direct_grad(False)
+        ops.set_norm_direct(False)
+    y2 = y.detach().clone().requires_grad_(True)
+    qs = [p_.detach().clone().requires_grad_(True) for p_ in ps]
+    gref = torch.autograd.grad((R.norm_post(y2, *qs, mode=2, post=0) * w).sum(), [y2] + qs)
+    torch.testing.assert_close(y.grad, gref[0], rtol=2e-3, atol=2e-4)
+    for p_, b_, g_ in zip(ps, base, gref[1:]):
+        torch.testing.assert_close(p_.grad, b_ + g_, rtol=2e-3, atol=2e-4)        # added to what was there
+
+
+def test_linear_with_the_skinny_gemm(ops):
+    torch.manual_seed(1)
+    x = torch.randn(37, 70, requires_grad=True)
+    w = torch.randn(52, 70, requires_grad=True)           # the activation-backward kernel works on float4s: N % 4 == 0
+    b = torch.randn(52, requires_grad=True)
+    ops.set_skinny_gemm(True)
+    try:
+        out = ops.linear(x, w, b, 'elu')
+        ref = R.linear(x, w, b, 'elu')
+        torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-5)
+        g = torch.randn_like(ref)
+        for a, c in zip(grads(out, [x, w, b], g), grads(ref, [x, w, b], g)):
+            torch.testing.assert_close(a, c, rtol=1e-4, atol=1e-4)
+    finally:
+        ops.set_skinny_gemm(False)
+
+
+@pytest.mark.parametrize('kernel', ['gaussian', 'laplacian', 'epanechnikov'])
+def test_icsbp_function(ops, kernel):
+    torch.manual_seed(2)
+    B, S, K = 2, 16, 4
+    colour = (0.4 * torch.randn(B, S, S, 8)).requires_grad_(True)
+    u = torch.rand(B, 1, S, S)
+    ls = torch.tensor(0.4).log().requires_grad_(True)
+    log_m, log_s, idx = ops.icsbp(colour, u, ls, K, kernel)
+    rm, rs, ridx = R.icsbp(colour, u, ls, K, kernel)
+    assert torch.equal(idx.long(), ridx.long())
+    torch.testing.assert_close(log_m, rm, rtol=1e-4, atol=1e-4)
+    w = torch.randn_like(rm)
+    for a, c in zip(grads(log_m, [colour, ls], w), grads(rm, [colour, ls], w)):
+        torch.testing.assert_close(a, c.to(a.dtype), rtol=2e-3, atol=2e-4)
+
+
+def test_mask_kl_function_plain_and_packed(ops):
+    torch.manual_seed(3)
+    K, B, Hh = 3, 2, 8
+    lm = torch.log_softmax(torch.randn(K, B, 1, Hh, Hh), 0).requires_grad_(True)
+    for cs, detach in ((4, True), (4, False), (1, False)):
+        dec = torch.randn(K, B, cs, Hh, Hh, requires_grad=True)
+        out = ops.mask_kl(lm, dec, detach)
+        ref = R.mask_kl(lm, dec, detach)
+        torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
+        g = torch.randn(B)
+        for a, c in zip(grads(out, [lm, dec], g), grads(ref, [lm, dec], g)):
+            if c is None:
+                assert a is None or a.abs().max() == 0
+            else:
+                torch.testing.assert_close(a, c, rtol=2e-3, atol=1e-5)
