@@ -74,6 +74,10 @@ class _Lib(object):
                         raise RuntimeError('%s: argument %s must be a CUDA tensor' % (name, an))
                     if not a.is_contiguous():
                         raise RuntimeError('%s: argument %s must be contiguous' % (name, an))
+                    if a.device.index != torch.cuda.current_device():
+                        # the launch goes to the CURRENT device's stream: a tensor of another GPU would be a silent fault
+                        raise RuntimeError('%s: argument %s lives on cuda:%d but the current device is cuda:%d'
+                                           % (name, an, a.device.index, torch.cuda.current_device()))
                     conv.append(a.data_ptr())
                 else:
                     conv.append(int(a))

@@ -39,6 +39,7 @@ struct P {
     int N, Hv, Wv, TH, TW, TNB, tiles_h, tiles_w;
     int Ho, Wo, Co, os, ph, pw, flat_wi;
     int ntaps, cblocks, kb_total, kb_per_split, act, atomic;
+    long split_stride;      // split-K: floats between the partial outputs of consecutive splits (workspace mode)
     Taps taps;
 };
 
@@ -241,28 +242,18 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ Ma
         else { oh = hv * p.os + p.ph; ow = wv * p.os + p.pw; }
         valid = valid && oh < p.Ho && ow < p.Wo;
         const long pix = valid ? ((long)(n + tn) * p.Ho + oh) * p.Wo + ow : -1;
-        if (p.atomic) {
-            float* outp = p.out + pix * p.Co + n0c;
-            const bool add_bias = p.bias != nullptr && blockIdx.z == 0;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-                if (valid) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        atomicAdd(outp + c0 + j, __uint_as_float(v[j]) + (add_bias ? sBias[c0 + j] : 0.f));
-                }
-            }
-        } else {
+        {
+            // split-K: split z writes its partial tile to its own slab of the workspace (plain stores, no bias); the ordered
+            // reduction kernel adds the slabs in split order, so the result is bitwise reproducible (no float atomics)
+            float* const outz = p.out + (long)blockIdx.z * p.split_stride;
             // all MMAs have retired, so stage 0 of the A ring is free: transpose each 32 x 128-byte block through a swizzled
             // 4 KB staging tile so that every store instruction writes four complete 128-byte rows
             float* stage = reinterpret_cast<float*>(sA) + q * 1024;
             switch (p.act) {
-                case G2_ACT_RELU: store_tile<BN, G2_ACT_RELU>(p.out, p.Co, n0c, tmem_base, sBias, stage, pix); break;
-                case G2_ACT_ELU: store_tile<BN, G2_ACT_ELU>(p.out, p.Co, n0c, tmem_base, sBias, stage, pix); break;
-                case G2_ACT_SIGMOID: store_tile<BN, G2_ACT_SIGMOID>(p.out, p.Co, n0c, tmem_base, sBias, stage, pix); break;
-                default: store_tile<BN, G2_ACT_NONE>(p.out, p.Co, n0c, tmem_base, sBias, stage, pix); break;
+                case G2_ACT_RELU: store_tile<BN, G2_ACT_RELU>(outz, p.Co, n0c, tmem_base, sBias, stage, pix); break;
+                case G2_ACT_ELU: store_tile<BN, G2_ACT_ELU>(outz, p.Co, n0c, tmem_base, sBias, stage, pix); break;
+                case G2_ACT_SIGMOID: store_tile<BN, G2_ACT_SIGMOID>(outz, p.Co, n0c, tmem_base, sBias, stage, pix); break;
+                default: store_tile<BN, G2_ACT_NONE>(outz, p.Co, n0c, tmem_base, sBias, stage, pix); break;
             }
         }
     }
@@ -343,6 +334,25 @@ inline void pick_tile(int Hv, int Wv, int* TH, int* TW, int* TNB) {
 }
 
 }  // namespace tc
+
+// Ordered split-K reduction: C = act(bias + slab_0 + slab_1 + ...), float4 per thread; fixed order -> bitwise reproducible.
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, const float* __restrict__ bias, float* __restrict__ C,
+                                     long n4, int N4, int splits, int act) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const int c4 = (int)(i % N4) * 4;
+    float4 a = bias ? make_float4(bias[c4], bias[c4 + 1], bias[c4 + 2], bias[c4 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = 0; z < splits; ++z) {
+        const float4 v = reinterpret_cast<const float4*>(ws)[(long)z * n4 + i];
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    if (act == G2_ACT_RELU) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+    else if (act == G2_ACT_ELU) {
+        a.x = a.x > 0.f ? a.x : __expf(a.x) - 1.f; a.y = a.y > 0.f ? a.y : __expf(a.y) - 1.f;
+        a.z = a.z > 0.f ? a.z : __expf(a.z) - 1.f; a.w = a.w > 0.f ? a.w : __expf(a.w) - 1.f;
+    }
+    reinterpret_cast<float4*>(C)[i] = a;
+}
 
 extern "C" {
 
@@ -479,14 +489,38 @@ int g2_conv_igemm_tf32(const float* in, const float* w, const float* bias, float
     return G2_OK;
 }
 
-// C[M,N] = A[M,K] * W[N,K]^T + bias[N]   (TF32 operands, fp32 accumulate); split-K accumulates atomically.
-int g2_gemm_tf32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, cudaStream_t stream) {
+// C[M,N] = act(A[M,K] * W[N,K]^T + bias[N])   (TF32 operands, fp32 accumulate).
+// Split-K (few output tiles, long reduction) is deterministic: every split writes its partial product to its own slab of
+// the caller's workspace and splitk_reduce_kernel adds the slabs in split order, with bias and activation fused.
+static int gemm_splits(int M, int N, int K, int BN, int* kb_per_split) {
+    const int kb_total = K / 32;
+    const int tiles = g2_cdiv(M, 128) * (N / BN);
+    int splits = 1;
+    if (tiles < 148 && kb_total >= 16) {
+        splits = (296 + tiles - 1) / tiles;
+        if (splits > kb_total / 4) splits = kb_total / 4;
+        if (splits < 1) splits = 1;
+    }
+    const int per = (kb_total + splits - 1) / splits;
+    if (kb_per_split) *kb_per_split = per;
+    return (kb_total + per - 1) / per;
+}
+
+long g2_gemm_tf32_workspace(int M, int N, int K) {
+    const int BN = tc::pick_bn(N);
+    if (BN == 0 || K % 32 != 0 || M <= 0) return 0;
+    const int splits = gemm_splits(M, N, K, BN, nullptr);
+    return splits > 1 ? (long)sizeof(float) * splits * (long)M * (long)N : 0;
+}
+
+static int gemm_tf32_impl(const float* A, const float* W, const float* bias, float* C, float* ws, int M, int N, int K, int act,
+                          cudaStream_t stream) {
     using namespace tc;
     G2_CHECK_ARG(A && W && C && M > 0 && N > 0 && K > 0);
     const int BN = pick_bn(N);
     if (BN == 0 || K % 32 != 0) return G2_ERR_UNSUPPORTED;
     G2_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
-                 (reinterpret_cast<uintptr_t>(C) & 15) == 0);
+                 (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (reinterpret_cast<uintptr_t>(ws) & 15) == 0);
     Maps maps;
     memset(&maps, 0, sizeof(maps));
     {
@@ -501,24 +535,31 @@ int g2_gemm_tf32(const float* A, const float* W, const float* bias, float* C, in
     }
     P p;
     memset(&p, 0, sizeof(p));
-    p.out = C; p.bias = bias; p.N = 1; p.Hv = 1; p.Wv = M; p.TH = 1; p.TW = 128; p.TNB = 1; p.tiles_h = 1; p.tiles_w = g2_cdiv(M, 128);
-    p.Ho = 1; p.Wo = M; p.Co = N; p.os = 1; p.ntaps = 1; p.cblocks = K / 32; p.kb_total = K / 32; p.act = G2_ACT_NONE;
-    const int tiles = p.tiles_w * (N / BN);
-    int splits = 1;
-    if (tiles < 148 && p.kb_total >= 16) {
-        splits = (296 + tiles - 1) / tiles;
-        if (splits > p.kb_total / 4) splits = p.kb_total / 4;
-        if (splits < 1) splits = 1;
-    }
-    p.kb_per_split = (p.kb_total + splits - 1) / splits;
-    splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
-    p.atomic = splits > 1;
-    if (p.atomic) {
-        cudaError_t e = cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, stream);
-        if (e != cudaSuccess) return (int)e;
+    p.N = 1; p.Hv = 1; p.Wv = M; p.TH = 1; p.TW = 128; p.TNB = 1; p.tiles_h = 1; p.tiles_w = g2_cdiv(M, 128);
+    p.Ho = 1; p.Wo = M; p.Co = N; p.os = 1; p.ntaps = 1; p.cblocks = K / 32; p.kb_total = K / 32;
+    int splits = ws ? gemm_splits(M, N, K, BN, &p.kb_per_split) : 1;
+    if (splits == 1) {
+        p.kb_per_split = p.kb_total;
+        p.out = C; p.bias = bias; p.act = act; p.split_stride = 0;
+    } else {
+        p.out = ws; p.bias = nullptr; p.act = G2_ACT_NONE; p.split_stride = (long)M * N;
     }
     dim3 grid((unsigned)p.tiles_w, (unsigned)(N / BN), (unsigned)splits);
-    return dispatch(maps, p, BN, grid, stream);
+    const int rc = dispatch(maps, p, BN, grid, stream);
+    if (rc != G2_OK || splits == 1) return rc;
+    const long n4 = (long)M * N / 4;
+    const int blocks = (int)((n4 + 255) / 256);
+    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(ws, bias, C, n4, N / 4, splits, act);
+    G2_LAUNCH_RET();
+}
+
+int g2_gemm_tf32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, cudaStream_t stream) {
+    return gemm_tf32_impl(A, W, bias, C, nullptr, M, N, K, G2_ACT_NONE, stream);
+}
+
+int g2_gemm_tf32_ws(const float* A, const float* W, const float* bias, float* C, float* ws, int M, int N, int K, int act,
+                    cudaStream_t stream) {
+    return gemm_tf32_impl(A, W, bias, C, ws, M, N, K, act, stream);
 }
 
 }  // extern "C"

@@ -305,7 +305,8 @@ bool make_plan(int N, int Hg, int Wg, int Cg, int Ht, int Wt, int Ct, int R, int
 
 
 // =====================================================================================================================
-// EXPERIMENTAL (G2_WGRAD_HALO=1; off by default, not yet run on a B200): the same weight gradient on a "halo" layout.
+// Default path for stride-1 filters with >= 4 taps (validated on B200 in round 2: 1.7-2.0x the tile kernel; G2_WGRAD_HALO=0
+// switches it off): the same weight gradient on a "halo" layout.
 // The kernel above re-loads one shifted G tile per tap (R*S loads of the same pixels through L2).  Here one CTA item is
 // (window of TH rows of one image, one 32-channel block of G): a single TMA box lands the zero-padded G window
 // [(TH+R-1) * Wp pixel rows][32 ch] and one box per 32-channel block of T lands [TH * Wp][32 ch] with the SAME row pitch
@@ -560,7 +561,7 @@ bool make_hplan(int N, int Hg, int Wg, int Cg, int Ht, int Wt, int Ct, int R, in
 
 bool enabled() {
     static int on = -1;
-    if (on < 0) { const char* e = getenv("G2_WGRAD_HALO"); on = (e && e[0] == '1') ? 1 : 0; }
+    if (on < 0) { const char* e = getenv("G2_WGRAD_HALO"); on = (e && e[0] == '0') ? 0 : 1; }      // default on (G2_WGRAD_HALO=0: tile kernel only)
     return on == 1;
 }
 

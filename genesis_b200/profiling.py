@@ -23,8 +23,8 @@ def algo_cost(name, a):
         N, Hg, Wg, Cg, Ht, Wt, Ct, R, S = a[o:o + 9]
         f = 2.0 * N * Ht * Wt * Cg * Ct * R * S
         b = 4.0 * (N * Hg * Wg * Cg + N * Ht * Wt * Ct + R * S * Cg * Ct)
-    elif name in ('g2_gemm_f32', 'g2_gemm_tf32'):
-        M, N, K = a[4:7]           # (A, B, bias, C, M, N, K, ...) for both entry points
+    elif name in ('g2_gemm_f32', 'g2_gemm_tf32', 'g2_gemm_tf32_ws'):
+        M, N, K = a[5:8] if name == 'g2_gemm_tf32_ws' else a[4:7]    # (A, B, bias, C, [ws,] M, N, K, ...)
         f = 2.0 * M * N * K
         b = 4.0 * (M * K + N * K + M * N)
     elif name == 'g2_norm_stats_f32':

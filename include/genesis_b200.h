@@ -69,11 +69,6 @@ int g2_conv_wgrad_f32(const float* g, const float* t, float* dw, int N, int Hg, 
  * and the full-map gated convs VAE.py:23,29 viewed as GEMMs. */
 int g2_gemm_f32(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int lda,
                 int ldb, int ldc, int transA, int transB, int act, int accumulate, g2_stream_t stream);
-/* Same contract, for the small latency-bound products of the latent path (csrc/gemm_skinny.cu: 32x32 tiles, register-prefetched
- * K loop, one writer per element -> deterministic; `accumulate` adds to C without atomics).  Experimental: ops.py routes to
- * it only under G2_SKINNY_GEMM=1. */
-int g2_gemm_skinny_f32(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int lda,
-                       int ldb, int ldc, int transA, int transB, int act, int accumulate, g2_stream_t stream);
 /* out[c] (+)= sum_m x[m,c]   (bias gradients) */
 int g2_colsum_f32(const float* x, float* out, long M, int C, int accumulate, g2_stream_t stream);
 
@@ -214,6 +209,13 @@ int g2_pack_conv_weight_f32(const float* w, float* packA, float* packB, int Co, 
                             int transposed, g2_stream_t stream);
 int g2_gemm_tf32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K,
                  g2_stream_t stream);
+/* Same product with a caller-owned workspace of g2_gemm_tf32_workspace(M, N, K) bytes (0 = no split needed; ws may then be
+ * NULL) and a fused activation (G2_ACT_NONE / RELU / ELU).  Long reductions with few output tiles are split along K: every
+ * split writes its partial product to its own slab of `ws` and an ordered reduction adds the slabs, bias and activation --
+ * no float atomics, bitwise reproducible.  g2_gemm_tf32 is the unsplit form. */
+long g2_gemm_tf32_workspace(int M, int N, int K);
+int g2_gemm_tf32_ws(const float* A, const float* W, const float* bias, float* C, float* ws, int M, int N, int K, int act,
+                    g2_stream_t stream);
 
 /* Halo variant of g2_conv_igemm_tf32 (igemm_halo.cu): stride-1 problems and the sub-pixel classes of stride-2
  * conv-transposes with the zero-padded activation window loaded once per CTA and all filter taps issued from it

@@ -1,5 +1,5 @@
 """Count the ATen operators (~ CUDA kernel launches outside our C ABI) and the C-ABI calls of one training step, on the CPU
-emulation of the kernels (no GPU needed): python scripts/aten_census.py MODEL K [--fused-latent] [--skinny].
+emulation of the kernels (no GPU needed): python scripts/aten_census.py MODEL K [--fused-latent].
 View-only operators (reshape / chunk / permute / ...) are not counted: they launch nothing."""
 import collections
 import os
@@ -52,7 +52,6 @@ def main():
     torch.Tensor.is_cuda = property(lambda self: True)      # the plug-ins and holders branch on it
     ops.set_precision('fp32')
     ops.set_fused_latent('--fused-latent' in sys.argv)
-    ops.set_skinny_gemm('--skinny' in sys.argv)
     sys.argv = [a for a in sys.argv]
     m, cfg = build_engine_model(model, K, 64)
     m.train()

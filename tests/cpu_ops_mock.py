@@ -194,6 +194,7 @@ def install(monkeypatch, ops):
                  'icsbp', 'icsbp_dynamic', 'masked_pool', 'mask_kl'):
         monkeypatch.setattr(ops, name, g[name])
     monkeypatch.setattr(ops, 'get_precision', lambda: 'fp32')
+    monkeypatch.setattr(ops, 'fused_latent', lambda: False)      # the ATen formulation in holders.py is the contract of the fused latent kernels
     monkeypatch.setattr(ops, 'side_streams_enabled', lambda: False)
     monkeypatch.setattr(torch.cuda, 'current_stream', lambda *a, **k: _STREAM)
     monkeypatch.setattr(torch.cuda, 'stream', lambda s: contextlib.nullcontext())

@@ -3,7 +3,7 @@ emulation of the kernel sources (tests/cuda_emu/emu_lib.py), compared with the o
 noise: loss terms, masks and the gradient of every parameter.  The path exercised is the product's -- plug-in ->
 genesis_b200.ops autograd Functions -> C-ABI argument marshalling -> kernel source -- minus the GPU.
 
-    python tests/cuda_emu/run_engine_emu.py MODEL K B [key=value ...] [--fused-latent] [--skinny] [--direct] [--precision fp32|tf32]
+    python tests/cuda_emu/run_engine_emu.py MODEL K B [key=value ...] [--fused-latent] [--direct] [--precision fp32|tf32]
                                             [--param-add name=value] [--gen multid]
 
 Minutes per run (a 64x64 model is a few GFLOP of scalar C++); used by hand and by the opt-in test
@@ -39,8 +39,6 @@ def parse(argv):
     for a in it:
         if a == '--fused-latent':
             flags['fused'] = True
-        elif a == '--skinny':
-            flags['skinny'] = True
         elif a == '--direct':
             flags['direct'] = True
         elif a in ('--precision', '--gen'):
@@ -60,7 +58,6 @@ def main():
     emu = emu_lib.install(mp)
     ops.set_precision(flags['precision'])
     ops.set_fused_latent(bool(flags.get('fused')))
-    ops.set_skinny_gemm(bool(flags.get('skinny')))
     m, cfg = build_engine_model(model, K, 64, **over)
     with torch.no_grad():
         for k, v in padd.items():

@@ -63,7 +63,7 @@ def check_identities(model_name, x, out, std, tol=1.0):
     if 'log_m_r_k' in stats:
         assert (_stack(stats['log_m_r_k']).exp().sum(0) - 1).abs().max().item() < 1e-4 * tol
     torch.testing.assert_close(_d(recon), (used.exp() * x_r).sum(0), rtol=0, atol=2e-5 * tol)
-    std_t = torch.as_tensor(std, dtype=torch.float64).reshape(-1)
+    std_t = (std.detach().double().cpu() if torch.is_tensor(std) else torch.as_tensor(std, dtype=torch.float64)).reshape(-1)
     std_arg = float(std_t[0]) if std_t.numel() == 1 else std_t
     err = O.mixture_nll(x, list(used.unbind(0)), list(x_r.unbind(0)), std_arg)
     torch.testing.assert_close(_d(losses['err']), err, rtol=2e-5 * tol, atol=1e-2 * tol)

@@ -7,7 +7,7 @@ from genesis_b200 import _lib
 
 # host-only queries / switches: no launch, no stream
 QUERIES = ('g2_abi_version', 'g2_conv_tf32_supported', 'g2_conv_wgrad_tf32_workspace', 'g2_conv_halo_enable',
-           'g2_conv_halo_supported', 'g2_conv_halo_plan', 'g2_conv_halo_debug', 'g2_conv_wgrad_halo_plan')
+           'g2_conv_halo_supported', 'g2_conv_halo_plan', 'g2_conv_halo_debug', 'g2_conv_wgrad_halo_plan', 'g2_gemm_tf32_workspace')
 
 
 def test_header_parses():

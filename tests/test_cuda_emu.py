@@ -1,6 +1,6 @@
 """CPU: the plain-SIMT kernels that were written without a GPU at hand, executed on the CPU (tests/cuda_emu: the kernel source
 compiled unchanged by g++, one OS thread per CUDA thread, real barriers and warp shuffles) and compared with numpy / torch /
-the oracle: the skinny GEMM (csrc/gemm_skinny.cu), the fused latent kernels (csrc/latent.cu) and the IC-SBP kernels with
+the oracle: the fused latent kernels (csrc/latent.cu) and the IC-SBP kernels with
 their kernel-type and dynamic_K instantiations (csrc/v2.cu).  The extern "C" entry points are emulated too, so argument
 checks, grid sizes and kernel selection are covered.  This validates indexing, tile edges, barrier placement and scan order --
 not performance, and not the product library (which is only ever run on a GPU)."""
@@ -33,50 +33,6 @@ def emu():
             libs[name] = ctypes.CDLL(build_emu.build(name))
         return libs[name]
     return get
-
-
-# ------------------------------------------------------------------------------------------------ skinny GEMM
-GEMM_CASES = [  # M, N, K, tA, tB, bias, act, accumulate
-    (64, 96, 160, 0, 1, True, 0, 0),       # forward  x[M,K] w[N,K]^T
-    (37, 50, 70, 0, 1, True, 2, 0),        # ragged in every dimension, ELU
-    (33, 40, 33, 0, 1, False, 1, 0),       # K < one tile (BK = 32 path), ReLU
-    (64, 72, 128, 0, 0, False, 0, 0),      # data gradient  dpre[M,N'] w[N',K']
-    (96, 40, 64, 1, 0, False, 0, 1),       # weight gradient  dpre[Mred,N]^T x[Mred,K], accumulated into .grad
-    (31, 33, 200, 1, 1, True, 5, 0),       # both transposed, sigmoid
-]
-
-
-@pytest.mark.parametrize('case', GEMM_CASES, ids=[str(c) for c in GEMM_CASES])
-def test_skinny_gemm(emu, case):
-    Mm, N, K, tA, tB, has_bias, act, acc = case
-    lib = emu('gemm_skinny.cu')
-    rng = np.random.RandomState(0)
-    A = rng.randn(*((K, Mm) if tA else (Mm, K))).astype(np.float32)
-    B = rng.randn(*((N, K) if tB else (K, N))).astype(np.float32)
-    bias = rng.randn(N).astype(np.float32) if has_bias else None
-    C0 = rng.randn(Mm, N).astype(np.float32)
-    C = C0.copy()
-    rc = lib.g2_gemm_skinny_f32(ptr(A), ptr(B), ptr(bias), ptr(C), Mm, N, K, A.shape[1], B.shape[1], N, tA, tB, act, acc, None)
-    assert rc == 0
-    ref = (A.T if tA else A).astype(np.float64) @ (B.T if tB else B).astype(np.float64)
-    if has_bias:
-        ref = ref + bias
-    if act == 1:
-        ref = np.maximum(ref, 0)
-    elif act == 2:
-        ref = np.where(ref > 0, ref, np.expm1(ref))
-    elif act == 5:
-        ref = 1 / (1 + np.exp(-ref))
-    if acc:
-        ref = ref + C0
-    np.testing.assert_allclose(C, ref, rtol=2e-5, atol=2e-5)
-
-
-def test_skinny_gemm_rejects_bad_arguments(emu):
-    lib = emu('gemm_skinny.cu')
-    a = np.zeros((4, 4), np.float32)
-    assert lib.g2_gemm_skinny_f32(ptr(a), ptr(a), None, ptr(a), 4, 4, 4, 4, 4, 2, 0, 1, 0, 0, None) == -1      # ldc < N
-    assert lib.g2_gemm_skinny_f32(ptr(a), ptr(a), None, ptr(a), 4, 4, 4, 4, 4, 4, 0, 1, 3, 0, None) == -1      # gradient-type act
 
 
 # ------------------------------------------------------------------------------------------------ fused latent kernels

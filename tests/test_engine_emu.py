@@ -12,7 +12,7 @@ pytestmark = pytest.mark.skipif(os.environ.get('G2_RUN_EMU_MODELS') != '1', reas
 HERE = os.path.dirname(os.path.abspath(__file__))
 CASES = [
     ['genesis', '2', '2'],
-    ['genesis', '2', '2', '--fused-latent', '--skinny'],
+    ['genesis', '2', '2', '--fused-latent'],
     ['genesisv2', '3', '2'],
     ['monet', '2', '2'],
     ['vae', '1', '2'],

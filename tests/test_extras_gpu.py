@@ -1,21 +1,14 @@
-"""Tests written at the end of round 1 AFTER the GPU budget was spent: they have not run on a B200 yet, so they are not
-part of the `-m gpu` gate (a wrong expectation in an unvalidated test must not mask the validated suite).  Run them with
-
-    G2_RUN_PENDING=1 python -m pytest tests/test_pending_next_round.py -q
-
-on a GPU box; once green they move into the regular GPU files with the `gpu` marker.
-
-They HAVE run on the CPU emulation of the kernel sources (G2_EMU=1 G2_RUN_PENDING=1, tests/cuda_emu/emu_mode.py; minutes per test):
-every test below except the hardware probe and the two full-size ones passes there (profiles/r01_emulated_gpu_tests.txt), so
-what remains open on the B200 is the hardware itself (the MN-major probe), TF32 rounding against the stated tolerances, and
-speed."""
+"""GPU: the parts of the engine beyond the three default models -- fused Adam vs torch.optim.Adam, the fused latent kernels vs
+autograd, evaluation-mode forwards, the BaselineVAE plug-in, every non-default variant of SURVEY.md section 8 f.4 against the
+goldens of the real reference, the IC-SBP kernel types, dynamic_K, the MN-major operand probe the halo weight-gradient kernel
+relies on, and the size-independent identities + batch-partition invariance at BASELINE.json's full per-GPU sizes
+(c2 B=64, c3 B=128, c5 B=64).  First validated on a B200 in round 2 (profiles/r02_pending_validation.txt)."""
 import os
 
 import pytest
 import torch
 
-pytestmark = pytest.mark.skipif(os.environ.get('G2_RUN_PENDING') != '1' or not torch.cuda.is_available(),
-                                reason='pending validation on a B200 (set G2_RUN_PENDING=1)')
+pytestmark = pytest.mark.gpu
 
 
 def test_fused_adam_equals_torch_optim_adam():
@@ -77,7 +70,7 @@ def test_fused_latent_ops_equal_autograd():
                 g = torch.autograd.grad(loss, [t for t in xs if t is not None])
                 outs.append(([t.detach() for t in o[:n_out]], g))
             finally:
-                ops.set_fused_latent(False)
+                ops.set_fused_latent(True)
         for a, b in zip(outs[0][0] + list(outs[0][1]), outs[1][0] + list(outs[1][1])):
             assert (a - b).abs().max().item() <= 2e-5 * max(1.0, a.abs().max().item())
 
@@ -112,43 +105,13 @@ def test_fused_latent_model_equals_unfused(model, K, B, gen):
         try:
             recon, losses, stats, att, comp = U.run_engine(m, x.cpu(), U.make_tape(11))
         finally:
-            ops.set_fused_latent(False)
+            ops.set_fused_latent(True)
         res.append((losses['err'].detach().clone(), {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}))
     assert (res[0][0] - res[1][0]).abs().max().item() <= 1e-4 * res[0][0].abs().max().item()
     gmax = max(g.norm().item() for g in res[0][1].values())
     for n, g in res[0][1].items():
         d = (res[1][1][n] - g).norm().item()
         assert d <= 2e-2 * g.norm().item() + 1e-3 * gmax, (n, d, g.norm().item())       # run-to-run TF32 noise is ~1e-3
-
-
-def test_persistent_halo_kernel_passes_the_halo_suite():
-    """The experimental persistent variant of the halo kernel (G2_HALO_PERSISTENT=1, read once per process) must pass the
-    same exactness tests as the default kernel; run them in a child process with the switch on."""
-    import subprocess
-    import sys
-    env = dict(os.environ, G2_HALO_PERSISTENT='1')
-    here = os.path.dirname(os.path.abspath(__file__))
-    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(here, 'test_halo_gpu.py'), os.path.join(here, 'test_tc_gpu.py'),
-                        '-x', '-q', '-m', 'gpu'], env=env, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
-
-
-def test_halo_wgrad_kernel_passes_the_wgrad_suite():
-    """The experimental halo weight-gradient kernel (G2_WGRAD_HALO=1, read once per process; csrc/wgrad_tc.cu namespace wgh)
-    must pass the exactness tests of the tile kernel (stride-1 cases take the new path, the others fall through) and the
-    direct-gradient / engine parity tests; child process with the switch on.  Run the MN-major probe below first: the
-    kernel relies on exactly what it probes."""
-    import subprocess
-    import sys
-    env = dict(os.environ, G2_WGRAD_HALO='1')
-    here = os.path.dirname(os.path.abspath(__file__))
-    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(here, 'test_tc_gpu.py'), '-x', '-q', '-m', 'gpu', '-k', 'wgrad'],
-                       env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
-    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(here, 'test_direct_grad_gpu.py'),
-                        os.path.join(here, 'test_genesis_gpu.py'), '-x', '-q', '-m', 'gpu'],
-                       env=env, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 @pytest.mark.skipif(os.environ.get('G2_EMU') == '1', reason='a probe of the HARDWARE; the CPU model only encodes the assumption it tests')
@@ -438,33 +401,3 @@ def test_full_size_identities_and_batch_partition_invariance(model, K, img, B, g
     m.set_noise_tape(None)
     for name, p in m.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), name
-
-
-def test_skinny_gemm_kernel_and_engine():
-    """g2_gemm_skinny_f32 on the device (the CPU emulation already checks the kernel's logic, tests/test_cuda_emu.py) and the
-    GENESIS engine with the small products routed to it (ops.set_skinny_gemm): same parity bars as the default path."""
-    import util_parity as U
-    from genesis_b200 import _lib, ops
-    from oracle import synth
-    from test_oracle_golden import build_engine_model
-    torch.manual_seed(0)
-    for (Mm, N, K, tA, tB, acc) in [(64, 512, 320, 0, 1, 0), (320, 64, 256, 0, 0, 0), (1024, 320, 64, 1, 0, 1), (37, 50, 70, 0, 1, 0)]:
-        A = torch.randn((K, Mm) if tA else (Mm, K), device='cuda')
-        B = torch.randn((N, K) if tB else (K, N), device='cuda')
-        bias = torch.randn(N, device='cuda')
-        C0 = torch.randn(Mm, N, device='cuda')
-        C = C0.clone()
-        _lib.call('g2_gemm_skinny_f32', A, B, bias, C, Mm, N, K, A.shape[1], B.shape[1], N, tA, tB, 0, acc)
-        ref = (A.t() if tA else A).double() @ (B.t() if tB else B).double() + bias.double() + (C0.double() if acc else 0)
-        assert (C.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
-    m, cfg = build_engine_model('genesis', 3, 64)
-    m = m.cuda().train()
-    x = torch.from_numpy(synth.GENERATORS['multid'](4, 64, 5)[0])
-    ops.set_skinny_gemm(True)
-    try:
-        recon, losses, stats, att, comp = U.run_engine(m, x, U.make_tape(3))
-    finally:
-        ops.set_skinny_gemm(False)
-    ref, P = U.run_oracle('genesis', m.state_dict(), x, U.make_tape(3), cfg)
-    assert U.rel_l2(losses['err'], ref['err']) < 1e-4
-    U.compare_grads(m, P, tol=1e-2)

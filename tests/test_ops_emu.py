@@ -79,23 +79,6 @@ def test_norm_post_direct_accumulation(ops):
         torch.testing.assert_close(p_.grad, b_ + g_, rtol=2e-3, atol=2e-4)        # added to what was there
 
 
-def test_linear_with_the_skinny_gemm(ops):
-    torch.manual_seed(1)
-    x = torch.randn(37, 70, requires_grad=True)
-    w = torch.randn(52, 70, requires_grad=True)           # the activation-backward kernel works on float4s: N % 4 == 0
-    b = torch.randn(52, requires_grad=True)
-    ops.set_skinny_gemm(True)
-    try:
-        out = ops.linear(x, w, b, 'elu')
-        ref = R.linear(x, w, b, 'elu')
-        torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-5)
-        g = torch.randn_like(ref)
-        for a, c in zip(grads(out, [x, w, b], g), grads(ref, [x, w, b], g)):
-            torch.testing.assert_close(a, c, rtol=1e-4, atol=1e-4)
-    finally:
-        ops.set_skinny_gemm(False)
-
-
 @pytest.mark.parametrize('kernel', ['gaussian', 'laplacian', 'epanechnikov'])
 def test_icsbp_function(ops, kernel):
     torch.manual_seed(2)
