@@ -3,8 +3,9 @@
 Adam), GENESIS K=5 on 64x64 synthetic Multi-dSprites-shaped batches, B=64 per GPU, at N GPUs of one node.
 
     python bench.py --gpus N --steps K --warmup W              # engine (one process per GPU; torchrun for N>1)
-    python bench.py --impl reference --steps K --warmup W      # reference arm: the oracle port of the
-                                                               # reference's PyTorch path on the host cores
+    python bench.py --impl reference --steps K --warmup W      # reference arm: the reference's own nn.Modules
+                                                               # (oracle/_ref; else the oracle port) on the host cores
+    python bench.py --workload c3|c4|c5 ...                    # the other BASELINE configs' per-GPU shapes
 
 One JSON line on stdout (rank 0).  See DESIGN.md section 5 for what each key means.
 """
@@ -31,6 +32,10 @@ WORKLOADS = {   # name: (model, K, img, batch per GPU, generator, fwd GFLOP / im
     'c5': ('monet', 7, 128, 64, 'multid', 14.022),
 }
 MODEL, K_SLOTS, IMG, B_PER_GPU, GEN, FWD_GFLOP_PER_IMG = WORKLOADS['c2']
+
+
+def workload_name():
+    return '%s K=%d %dx%d %s-shaped synthetic, batch %d per GPU' % (MODEL, K_SLOTS, IMG, IMG, GEN, B_PER_GPU)
 
 
 def select_workload(name):
@@ -81,7 +86,7 @@ class ClockSampler(threading.Thread):
 
 
 def synthetic_batches(n_batches, batch, seed):
-    from oracle import synth    # test-infrastructure generator of dataset-shaped images (inputs only)
+    from genesis_b200.datasets import synth    # the product's own generator of dataset-shaped images
     return [torch.from_numpy(synth.GENERATORS[GEN](batch, IMG, seed + i)[0]) for i in range(n_batches)]
 
 
@@ -96,15 +101,39 @@ def build_cfg():
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
-def cpu_port_step_fn(batch):
-    """The oracle port of the reference's PyTorch path (oracle/models.py) on the host: fwd + loss + bwd."""
+def cpu_step_fn(batch):
+    """One training step of the reference's PyTorch path on the host: forward + loss assembly (train.py:227-259 without GECO's
+    host sync) + backward.  Preferred: the reference's OWN nn.Module from oracle/_ref (byte-identical copy of models/,
+    modules/, third_party/sylvester; kind "reference"); fallback: the oracle port (oracle/models.py; kind "port").
+    Returns (step function, kind)."""
+    from oracle import ref_loader
+    xs = synthetic_batches(2, batch, 100)
+    if ref_loader.available():
+        from oracle import models as M
+        cfg = dict(M.make_cfg(MODEL, K_steps=K_SLOTS, img_size=IMG))
+        model = ref_loader.load_reference(MODEL, cfg, seed=0).train()
+
+        def step(i):
+            model.zero_grad(set_to_none=True)
+            torch.manual_seed(i)
+            recon, losses, stats, att, comp = model(xs[i % len(xs)])
+            err = losses.err.mean(0)
+            kl = err.new_zeros(())
+            for key in ('kl_m_k', 'kl_l_k'):
+                if key in losses and len(losses[key]):
+                    kl = kl + torch.stack(list(losses[key]), dim=1).mean(0).sum()
+            for key in ('kl_m', 'kl_l'):
+                if key in losses and torch.is_tensor(losses[key]):
+                    kl = kl + losses[key].mean(0)
+            (err + kl).backward()
+            return float(err.detach())
+        return step, 'reference'
     from oracle import models as M, functional as O
     plugin, cfg = build_cfg()
     torch.manual_seed(0)
     holder = plugin.load(cfg)
     P = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in holder.state_dict().items()}
     ocfg = M.make_cfg(MODEL, K_steps=K_SLOTS, img_size=IMG)
-    xs = synthetic_batches(2, batch, 100)
 
     def step(i):
         for p in P.values():
@@ -113,7 +142,7 @@ def cpu_port_step_fn(batch):
         out = M.FORWARD[MODEL](P, xs[i % len(xs)], O.NoiseTape(seed=i), ocfg, training=True)
         M.total_loss(out).backward()
         return float(out['err'].mean())
-    return step
+    return step, 'port'
 
 
 def run_reference_arm(args):
@@ -122,22 +151,25 @@ def run_reference_arm(args):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_b = 16
-    step = cpu_port_step_fn(sample_b)
+    batch = B_PER_GPU                     # the config's own per-GPU batch (c2: 64), not a reduced sample
+    step, kind = cpu_step_fn(batch)
     for i in range(max(1, min(args.warmup, 2))):
         step(i)
     t0 = time.perf_counter()
     for i in range(args.steps):
         step(i)
     dt = time.perf_counter() - t0
-    v = sample_b * args.steps / dt
+    v = batch * args.steps / dt
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': '%s K=%d %dx%d fwd+bwd, CPU sample batch=%d per step (config B=%d)' % (MODEL, K_SLOTS, IMG, IMG, sample_b, B_PER_GPU)},
-        'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                         'sample': '%d steps x batch %d, torch %s CPU fp32, %d threads' % (args.steps, sample_b, torch.__version__, cores)},
+        'config': {'workload': workload_name() + ', fwd+bwd on the host CPU', 'global_batch': batch,
+                   'same_config': True},
+        'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': kind,
+                         'sample': '%d steps x batch %d (the config batch), torch %s CPU fp32, %d threads; %s' % (
+                             args.steps, batch, torch.__version__, cores,
+                             "the reference's own nn.Modules from oracle/_ref" if kind == 'reference' else 'oracle port (oracle/_ref absent)')},
         'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -233,54 +265,58 @@ def run_engine(args):
         rows = prof.table()
         total_ms = sum(r['ms'] for r in rows)
         top = rows[0]
-        # DRAM bytes per launch of the dominant kernel from the committed ncu pass (profiles/r01_traffic.json; c2 only)
+        # DRAM bytes per C-ABI CALL of the dominant entry point from the committed ncu pass over one eager step of this
+        # workload (profiles/r02_traffic_<workload>.json: dram__bytes_read.sum + dram__bytes_write.sum summed over the kernel
+        # launches of that entry point, divided by its calls per step) -- the same unit as the algorithmic bytes / flops
+        # below, which are per call too (one call = 1 kernel launch, or 4 for the sub-pixel classes of a stride-2 layer).
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
-        if args.workload == 'c2' and os.path.exists(tpath):
+        calls_per_step = top['calls'] // 2
+        tpath = os.path.join(ROOT, 'profiles', 'r02_traffic_%s.json' % args.workload)
+        if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            if top['key'] in tj:
-                traffic = tj[top['key']]['dram_bytes_per_launch']
-                traffic_src = 'profiles/r01_traffic.json (ncu dram__bytes_read+write per launch, %d launches of one step)' % tj[top['key']]['launches']
+            if top['key'] in tj and calls_per_step > 0:
+                traffic = tj[top['key']]['dram_bytes'] / calls_per_step
+                traffic_src = ('profiles/r02_traffic_%s.json: ncu dram bytes of the %d kernel launches of this entry point in one eager '
+                               'step / %d calls per step' % (args.workload, tj[top['key']]['launches'], calls_per_step))
         tensor_like = top['flops'] > 0 and top['key'].startswith(('g2_conv', 'g2_gemm'))
+        common = {'kernel': top['key'], 'traffic': traffic, 'traffic_source': traffic_src, 'unit_of_launch': 'one C-ABI call',
+                  'share_of_step': top['ms'] / total_ms, 'launch_ms': top['ms'] / top['calls'], 'calls_per_step': calls_per_step,
+                  'algorithmic_bytes_per_launch': top['bytes'] / top['calls'],
+                  'timing': 'CUDA events around each call on the launch stream, 2 eager steps, side streams off'}
         if tensor_like:
             ach = top['flops'] / (top['ms'] * 1e-3) / 1e12
-            roof = {'bound': 'tensor', 'kernel': top['key'], 'achieved': ach, 'peak': pk['tf_sus'], 'unit': 'TFLOP/s',
-                    'frac': ach / pk['tf_sus'], 'traffic': traffic, 'traffic_source': traffic_src,
-                    'peak_source': pk['src'] + ' bf16 sustained (kernel runs TF32 operands: nominal TF32 dense peak is half of bf16)',
-                    'share_of_step': top['ms'] / total_ms, 'launch_ms': top['ms'] / top['calls'],
-                    'algorithmic_flops_per_launch': top['flops'] / top['calls'],
-                    'algorithmic_bytes_per_launch': top['bytes'] / top['calls']}
+            roof = dict(common, bound='tensor', achieved=ach, peak=pk['tf_sus'], unit='TFLOP/s', frac=ach / pk['tf_sus'],
+                        peak_source=pk['src'] + ' bf16 sustained (kernel runs TF32 operands: nominal TF32 dense peak is half of bf16)',
+                        algorithmic_flops_per_launch=top['flops'] / top['calls'])
         else:
             ach = top['bytes'] / (top['ms'] * 1e-3) / 1e9
-            roof = {'bound': 'hbm', 'kernel': top['key'], 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s',
-                    'frac': ach / pk['hbm'], 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': pk['src'],
-                    'share_of_step': top['ms'] / total_ms, 'launch_ms': top['ms'] / top['calls'],
-                    'algorithmic_bytes_per_launch': top['bytes'] / top['calls']}
+            roof = dict(common, bound='hbm', achieved=ach, peak=pk['hbm'], unit='GB/s', frac=ach / pk['hbm'], peak_source=pk['src'])
         breakdown = [{'kernel': r['key'], 'ms_per_step': r['ms'] / 2, 'calls_per_step': r['calls'] // 2,
                       'tflops': (r['flops'] / (r['ms'] * 1e-3) / 1e12) if r['flops'] else None,
                       'gbs': (r['bytes'] / (r['ms'] * 1e-3) / 1e9) if r['bytes'] else None} for r in rows[:8]]
         step_tf = 3 * FWD_GFLOP_PER_IMG * B_PER_GPU * world * args.steps / (ms * 1e-3) / 1e3
-        # ---- CPU baseline: bounded sample of the same workload with the oracle port on the host cores
+        # ---- CPU baseline: bounded sample of the same workload (the config's own batch) on the host cores
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
-            sb = 16
-            step = cpu_port_step_fn(sb)
+            step, kind = cpu_step_fn(B_PER_GPU)
             step(0)
             t0 = time.perf_counter()
-            n_cpu = 3
-            for i in range(n_cpu):
-                step(i + 1)
+            n_cpu = 0
+            while n_cpu < 3 and (n_cpu == 0 or time.perf_counter() - t0 < 30.0):
+                step(n_cpu + 1)
+                n_cpu += 1
             dt = time.perf_counter() - t0
-            cpu = {'value': sb * n_cpu / dt, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                   'sample': '1 warm-up + %d steps of batch %d (config batch is %d), oracle port, torch CPU fp32' % (n_cpu, sb, B_PER_GPU)}
+            cpu = {'value': B_PER_GPU * n_cpu / dt, 'unit': 'images/s', 'cores': cores, 'kind': kind,
+                   'sample': '1 warm-up + %d steps of batch %d (the config batch), %s, torch CPU fp32, %d threads' % (
+                       n_cpu, B_PER_GPU, "the reference's own nn.Modules (oracle/_ref)" if kind == 'reference' else 'oracle port', cores)}
         imgs = B_PER_GPU * world * args.steps
         line = {
             'metric': METRIC, 'value': imgs / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(3, args.warmup), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': '%s K=%d %dx%d %s-shaped synthetic, batch %d per GPU, fwd+bwd+allreduce+Adam+GECO' % (MODEL, K_SLOTS, IMG, IMG, GEN, B_PER_GPU),
+            'vs_baseline': None, 'dtype': 'tf32', 'data': 'synthetic',
+            'config': {'workload': workload_name() + ', fwd+bwd+allreduce+Adam+GECO',
                        'global_batch': B_PER_GPU * world, 'parallelism': 'dp%d' % world,
                        'l2': 'per-step working set (activations > 4 GB) exceeds the 126 MB L2; inputs rotate over %d batches' % n_in,
                        'step_tflops_algorithmic': step_tf, 'last_elbo': last, 'cuda_graph': graphed,

@@ -1,7 +1,6 @@
-"""ORACLE / test infrastructure -- import the REAL reference in the build container.
-
-/root/reference is read-only and absent on the GPU box; this module is only used by
-oracle/make_golden.py and by tests that skip when the checkout is missing.  The reference needs
+"""ORACLE / test infrastructure -- import the REAL reference: the live checkout in the build container, or the
+byte-identical copy under oracle/_ref (oracle/build_ref.py; git-ignored, shipped to the GPU box) where /root/reference does
+not exist.  Used by oracle/make_golden.py, by tests that skip when neither is present, and by bench.py's CPU reference arm.  The reference needs
 `attrdict`, `forge`, `tensorflow`, `simplejson`: the stand-ins under
 genesis_b200/compat are put on sys.path.  Noise is replayed from a NoiseTape by patching
 torch.distributions.normal._standard_normal and Tensor.uniform_ for the duration of a forward."""
@@ -11,8 +10,19 @@ import sys
 
 import torch
 
-REF_ROOT = os.environ.get('GENESIS_REFERENCE_ROOT', '/root/reference')
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _default_root():
+    env = os.environ.get('GENESIS_REFERENCE_ROOT')
+    if env:
+        return env
+    if os.path.isdir('/root/reference'):
+        return '/root/reference'
+    return os.path.join(_REPO, 'oracle', '_ref')
+
+
+REF_ROOT = _default_root()
 
 
 def available():

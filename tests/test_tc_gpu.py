@@ -94,9 +94,41 @@ def test_unsupported_shapes_are_reported():
 
 
 @pytest.mark.parametrize('M,N,K', [(64, 512, 16384), (320, 32768, 64), (448, 256, 4096), (100, 128, 96), (320, 256, 1024)])
-def test_gemm_tf32(M, N, K):
+@pytest.mark.parametrize('act', [0, 2])
+def test_gemm_tf32(M, N, K, act):
+    """g2_gemm_tf32_ws (what ops.linear calls): exact operands -> float64 reference within fp32 accumulation error; the
+    split-K shapes (few tiles, K >= 512) are reduced in a fixed order, so two runs are BITWISE equal (no float atomics);
+    bias + activation fused in both the split and the unsplit form."""
     from genesis_b200 import _lib
     torch.manual_seed(1)
+    a = tf32_round(torch.randn(M, K))
+    w = tf32_round(torch.randn(N, K) / K ** 0.5)
+    b = torch.randn(N)
+    ref = a.double() @ w.double().t() + b.double()
+    if act == 2:
+        ref = torch.where(ref > 0, ref, torch.expm1(ref))
+    ws_bytes = _lib.lib().query('g2_gemm_tf32_workspace', M, N, K)
+    if (M, N, K) == (64, 512, 16384):
+        assert ws_bytes > 0                                  # the long-reduction shape is split
+    ws = torch.empty(max(ws_bytes // 4, 1), device=DEV) if ws_bytes else None
+    ad, wd, bd = a.to(DEV), w.to(DEV), b.to(DEV)
+    outs = []
+    for _ in range(2):
+        out = torch.full((M, N), float('nan'), device=DEV)
+        _lib.call('g2_gemm_tf32_ws', ad, wd, bd, out, ws, M, N, K, act)
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    got = outs[0].double().cpu()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() / ref.abs().max().item() < 2e-5
+
+
+def test_gemm_tf32_unsplit_entry():
+    """g2_gemm_tf32 (no workspace -> never split): one fp32 accumulation chain over the whole reduction."""
+    from genesis_b200 import _lib
+    torch.manual_seed(1)
+    M, N, K = 448, 256, 4096
     a = tf32_round(torch.randn(M, K))
     w = tf32_round(torch.randn(N, K) / K ** 0.5)
     b = torch.randn(N)
@@ -104,9 +136,7 @@ def test_gemm_tf32(M, N, K):
     out = torch.full((M, N), float('nan'), device=DEV)
     _lib.call('g2_gemm_tf32', a.to(DEV), w.to(DEV), b.to(DEV), out, M, N, K)
     torch.cuda.synchronize()
-    got = out.double().cpu()
-    assert torch.isfinite(got).all()
-    assert (got - ref).abs().max().item() / ref.abs().max().item() < 2e-5
+    assert (out.double().cpu() - ref).abs().max().item() / ref.abs().max().item() < 5e-5
 
 
 WGRAD_CASES = [  # kind, N, H, W, Ci, Co, R, stride, pad   (conv: x[N,H,W,Ci] -> y; convT: x[N,H,W,Ci] -> y upsampled)
