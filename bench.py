@@ -199,7 +199,8 @@ def run_engine(args):
     plugin, cfg = build_cfg()
     torch.manual_seed(0)
     model = plugin.load(cfg).to(dev).train()
-    ts = trainer.TrainStep(model, lr=1e-4, img_size=IMG, world_size=world)
+    # same parameters on every rank (manual_seed(0) above), independent eps / IC-SBP seed noise per rank (noise_seed + rank)
+    ts = trainer.TrainStep(model, lr=1e-4, img_size=IMG, world_size=world, rank=rank, noise_seed=1234)
     lib = _lib.lib()
 
     n_in = 4

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) mixture_fwd_kernel(const MixP p) {
 
 struct MixBP {
     const float* x; const float* xr; const float* lm /* log masks (post-softmax when softmax) */; const float* stdv;
-    const float* lse; const float* gerr;   // [B] upstream gradient of err
+    const float* lse; const float* gerr;   // [B] upstream gradient of err (PIX: [B,3,P] upstream gradient of the per-pixel, per-channel loss)
     float* dxr;            // [K,B,3,P]
     float* dlm;            // [K,B,P]   gradient w.r.t. log masks, or w.r.t. mask LOGITS when softmax != 0
     int K, B, P, softmax;
@@ -173,18 +173,20 @@ struct MixBP {
 
 // r_kc = exp(a_kc - lse_c);  d err / d log m_k = - sum_c r_kc;  d err / d xr_kc = - r_kc (x_c - xr_kc)/std_k^2
 // softmax: d/d logit_k = G_k - m_k * sum_j G_j   with sum_j G_j = -3 (responsibilities sum to one per channel)
+template <bool PIX>
 __global__ void __launch_bounds__(256) mixture_bwd_kernel(const MixBP p) {
     const int b = blockIdx.y;
     const int i4 = blockIdx.x * blockDim.x + threadIdx.x;
     const int P4 = p.P >> 2;
     if (i4 >= P4) return;
     const long KBP = (long)p.B * p.P;
-    const float g = __ldg(p.gerr + b);
-    float4 xv[3], Lv[3];
+    const float g = PIX ? 1.f : __ldg(p.gerr + b);
+    float4 xv[3], Lv[3], Gv[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const long o = ((long)b * 3 + c) * p.P + i4 * 4;
         xv[c] = g2_ldg4(p.x + o); Lv[c] = g2_ldg4(p.lse + o);
+        if (PIX) Gv[c] = g2_ldg4(p.gerr + o);
     }
     for (int k = 0; k < p.K; ++k) {
         const float4 l = g2_ldg4(p.lm + ((long)k * p.B + b) * p.lm_cs * p.P + i4 * 4);
@@ -199,13 +201,14 @@ __global__ void __launch_bounds__(256) mixture_bwd_kernel(const MixBP p) {
             const float rv[4] = {r4.x, r4.y, r4.z, r4.w};
             const float xx[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
             const float LL[4] = {Lv[c].x, Lv[c].y, Lv[c].z, Lv[c].w};
+            const float GG[4] = {PIX ? Gv[c].x : 1.f, PIX ? Gv[c].y : 1.f, PIX ? Gv[c].z : 1.f, PIX ? Gv[c].w : 1.f};
             float dr[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float d = xx[j] - rv[j];
                 const float r = expf(lv[j] + cst - d * d * inv2v - LL[j]);
-                gm[j] += r;
-                dr[j] = -g * r * d * 2.f * inv2v;
+                if (PIX) { gm[j] += GG[j] * r; dr[j] = -GG[j] * r * d * 2.f * inv2v; }
+                else { gm[j] += r; dr[j] = -g * r * d * 2.f * inv2v; }
             }
             *reinterpret_cast<float4*>(p.dxr + o) = make_float4(dr[0], dr[1], dr[2], dr[3]);
         }
@@ -351,7 +354,19 @@ int g2_mixture_bwd_f32(const float* x, const float* xr, const float* lm, const f
     G2_CHECK_ARG(x && xr && lm && stdv && lse && gerr && dxr && dlm && K >= 1 && B > 0 && P > 0 && (P % 4) == 0);
     MixBP p{x, xr, lm, stdv, lse, gerr, dxr, dlm, K, B, P, softmax, xr_cs, lm_cs, dlm_cs};
     dim3 grid(g2_cdiv(P / 4, 256), B);
-    mixture_bwd_kernel<<<grid, 256, 0, stream>>>(p);
+    mixture_bwd_kernel<false><<<grid, 256, 0, stream>>>(p);
+    G2_LAUNCH_RET();
+}
+
+// Backward of the PIXEL-WISE loss (Genesis.x_loss(pixel_wise=True), genesis_config.py:283-284): err_ppc = -lse [B,3,P] with
+// upstream gradient gpix [B,3,P]; given masks only (softmax = 0).
+int g2_mixture_bwd_pix_f32(const float* x, const float* xr, const float* lm, const float* stdv, const float* lse,
+                           const float* gpix, float* dxr, float* dlm, int K, int B, int P, int xr_cs, int lm_cs, int dlm_cs,
+                           cudaStream_t stream) {
+    G2_CHECK_ARG(x && xr && lm && stdv && lse && gpix && dxr && dlm && K >= 1 && B > 0 && P > 0 && (P % 4) == 0);
+    MixBP p{x, xr, lm, stdv, lse, gpix, dxr, dlm, K, B, P, 0, xr_cs, lm_cs, dlm_cs};
+    dim3 grid(g2_cdiv(P / 4, 256), B);
+    mixture_bwd_kernel<true><<<grid, 256, 0, stream>>>(p);
     G2_LAUNCH_RET();
 }
 

@@ -300,3 +300,94 @@ extern "C" int g2_adam_f32(float* p, float* g, float* m, float* v, long n, float
     adam_kernel<<<(int)b, 256, 0, stream>>>(p, g, m, v, n / 4, lr, b1, b2, eps, step, grad_scale, zero_grad);
     G2_LAUNCH_RET();
 }
+
+// ---- fused RMSprop / SGD over the flat arena: the other two optimisers train.py offers (train.py:171-176:
+// optim.RMSprop(params, lr) -> alpha 0.99, eps 1e-8, no momentum, not centred; optim.SGD(params, lr, 0.9) -> momentum 0.9,
+// no dampening, no Nesterov, the first step initialises the buffer with the gradient).  Same conventions as adam_kernel:
+// gradients are scaled by grad_scale (1 / world after an NCCL sum) and zeroed for the next step; `step` is the 1-based
+// device counter (SGD needs it to recognise the first step).
+namespace {
+__global__ void rmsprop_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ sq, long n4, float lr, float alpha,
+                               float eps, float gscale, int zero_grad) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        float4 pp = *reinterpret_cast<float4*>(p + i * 4), gg = *reinterpret_cast<float4*>(g + i * 4);
+        float4 ss = *reinterpret_cast<float4*>(sq + i * 4);
+        float* pa = &pp.x; float* ga = &gg.x; float* sa = &ss.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float gr = ga[j] * gscale;
+            sa[j] = alpha * sa[j] + (1.f - alpha) * gr * gr;
+            pa[j] -= lr * gr / (sqrtf(sa[j]) + eps);
+        }
+        *reinterpret_cast<float4*>(p + i * 4) = pp;
+        *reinterpret_cast<float4*>(sq + i * 4) = ss;
+        if (zero_grad) *reinterpret_cast<float4*>(g + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+__global__ void sgd_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ buf, long n4, float lr, float momentum,
+                           const float* __restrict__ step, float gscale, int zero_grad) {
+    const bool first = __ldg(step) <= 1.f;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        float4 pp = *reinterpret_cast<float4*>(p + i * 4), gg = *reinterpret_cast<float4*>(g + i * 4);
+        float4 bb = *reinterpret_cast<float4*>(buf + i * 4);
+        float* pa = &pp.x; float* ga = &gg.x; float* ba = &bb.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float gr = ga[j] * gscale;
+            ba[j] = first ? gr : momentum * ba[j] + gr;
+            pa[j] -= lr * ba[j];
+        }
+        *reinterpret_cast<float4*>(p + i * 4) = pp;
+        *reinterpret_cast<float4*>(buf + i * 4) = bb;
+        if (zero_grad) *reinterpret_cast<float4*>(g + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// GECO (utils/geco.py:35-51) as ONE single-thread kernel on device scalars -- no host sync, graph-replayable:
+//   err_ema = started ? (1-alpha) err + alpha err_ema : err;  constraint = goal - err_ema;
+//   beta = clamp(beta * exp(rate * constraint), beta_min, beta_max),  rate = step_size * (constraint > 0 ? speedup : 1).
+// state = {beta, err_ema, started}; also steps the optimiser's step counter (+1) and emits elbo = err + kl.
+__global__ void geco_kernel(float* __restrict__ state, const float* __restrict__ err_kl, float* __restrict__ step_count,
+                            float* __restrict__ elbo, float inv_world, float goal, float step_size, float alpha, float speedup,
+                            float beta_min, float beta_max, int update) {
+    const float err = err_kl[0] * inv_world, kl = err_kl[1] * inv_world;
+    if (update) {
+        const float ema = state[2] > 0.f ? (1.f - alpha) * err + alpha * state[1] : err;
+        state[1] = ema;
+        state[2] = 1.f;
+        const float c = goal - ema;
+        const float rate = (speedup > 0.f && c > 0.f) ? speedup * step_size : step_size;
+        state[0] = fminf(fmaxf(state[0] * expf(rate * c), beta_min), beta_max);
+    }
+    if (step_count) step_count[0] += 1.f;
+    if (elbo) elbo[0] = err + kl;
+}
+}  // namespace
+
+extern "C" int g2_rmsprop_f32(float* p, float* g, float* sq, long n, float lr, float alpha, float eps, float grad_scale,
+                              int zero_grad, cudaStream_t stream) {
+    G2_CHECK_ARG(p && g && sq && n > 0 && (n % 4) == 0);
+    long b = (n / 4 + 255) / 256;
+    if (b > 148L * 16) b = 148L * 16;
+    rmsprop_kernel<<<(int)b, 256, 0, stream>>>(p, g, sq, n / 4, lr, alpha, eps, grad_scale, zero_grad);
+    G2_LAUNCH_RET();
+}
+
+extern "C" int g2_sgd_f32(float* p, float* g, float* buf, long n, float lr, float momentum, const float* step, float grad_scale,
+                          int zero_grad, cudaStream_t stream) {
+    G2_CHECK_ARG(p && g && buf && step && n > 0 && (n % 4) == 0);
+    long b = (n / 4 + 255) / 256;
+    if (b > 148L * 16) b = 148L * 16;
+    sgd_kernel<<<(int)b, 256, 0, stream>>>(p, g, buf, n / 4, lr, momentum, step, grad_scale, zero_grad);
+    G2_LAUNCH_RET();
+}
+
+extern "C" int g2_geco_step_f32(float* state, const float* err_kl, float* step_count, float* elbo, float inv_world, float goal,
+                                float step_size, float alpha, float speedup, float beta_min, float beta_max, int update,
+                                cudaStream_t stream) {
+    G2_CHECK_ARG(state && err_kl);
+    geco_kernel<<<1, 1, 0, stream>>>(state, err_kl, step_count, elbo, inv_world, goal, step_size, alpha, speedup, beta_min, beta_max,
+                                     update);
+    G2_LAUNCH_RET();
+}

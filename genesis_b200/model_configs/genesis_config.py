@@ -83,14 +83,18 @@ class Genesis(nn.Module, NoiseMixin):
         self.side_stream = True         # overlap the prior / KL branch with the decoders (see forward)
         assert cfg.montecarlo_kl == True  # noqa: E712  (reference genesis_config.py:80)
         self.comp_symmetric = bool(cfg.comp_symmetric) and self.two_stage
-        if self.K_steps < 2:
-            raise NotImplementedError('engine covers GENESIS with K >= 2 (SURVEY.md section 8f.4)')
         input_channels = cfg.input_channels if hasattr(cfg, 'input_channels') else 3
         # construction order == reference (genesis_config.py:86-138) so seeded init is identical
         core = H.SylvesterVAE(self.ldim, [input_channels, cfg.img_size, cfg.img_size], 1,
                               cfg.enc_norm, cfg.dec_norm)
-        self.att_steps = self.K_steps
-        self.att_process = LatentSBPHolder(core)
+        if self.K_steps > 1:
+            self.att_steps = self.K_steps
+            self.att_process = LatentSBPHolder(core)
+        else:
+            # K_steps == 1 (reference genesis_config.py:94-96, 161-166): no attention process -- the core was built (it consumes
+            # the seeded generator exactly as in the reference) but is not part of the model; a single all-ones mask.
+            assert self.two_stage       # reference :122
+            self.autoreg_prior = False
         if self.two_stage:
             self.comp_vae = H.ComponentVAEHolder(nout=input_channels, cfg=cfg)
             if self.comp_symmetric:     # reference genesis_config.py:101-120
@@ -140,6 +144,8 @@ class Genesis(nn.Module, NoiseMixin):
             raise RuntimeError('genesis_b200 runs on CUDA (sm_100a) only; there is no CPU path')
         K, B = self.K_steps, x.shape[0]
         x = x.contiguous().float()
+        if K == 1:
+            return self._forward_single_slot(x)
         log_m, log_s, att_stats = self._masks(x)                     # [K,B,1,H,W], [K+1,B,1,H,W]
         z_k = att_stats.z_k
         if not self.two_stage:
@@ -219,6 +225,33 @@ class Genesis(nn.Module, NoiseMixin):
             check_log_masks(log_m_k)
         return recon, losses, stats, att_stats, comp_stats
 
+    def _forward_single_slot(self, x):
+        """K_steps == 1 (reference genesis_config.py:161-166, 226-228, 249-255): the only mask is all ones (log m = 0, log s =
+        -1e10), the component VAE sees cat(0, x), the component prior is N(0,1), `kl_m` is the constant 0 and att_stats None."""
+        B = x.shape[0]
+        cv = self.comp_vae
+        log_m = x.new_zeros(1, B, 1, self.img_size, self.img_size)
+        packed = ops.comp_pack(x, log_m, 32 if ops.get_precision() == 'tf32' else 4)
+        if self.comp_symmetric:
+            enc = H.symmetric_comp_encode(cv, packed, self.training)
+        else:
+            enc = H.comp_encode(cv.encoder_module, packed, 'elu')
+        cz, cmu, csig = H.gauss_head(enc, self._normal((enc.shape[0], enc.shape[1] // 2), x))
+        kl = H.mc_kl(cz, cmu, csig)
+        if self.comp_symmetric:
+            x_r = H.symmetric_comp_decode(cv, cz, self.training, 3 if self.pixel_bound else 0)
+        else:
+            x_r = H.broadcast_decode(cv.decoder_module, cz, 'elu', 3 if self.pixel_bound else 0)
+        x_r = x_r.view(1, B, x.shape[1], self.img_size, self.img_size)
+        err, recon, _ = ops.mixture_nll(x, x_r, log_m, self.std.reshape(-1), False)
+        losses = AttrDict(err=err, kl_m=x.new_zeros(()), kl_l_k=[kl])
+        comp_stats = AttrDict(mu_k=[cmu], sigma_k=[csig], z_k=[cz])
+        with torch.no_grad():
+            mx = x_r * log_m.exp()
+        stats = AttrDict(recon=recon, log_m_k=list(log_m.unbind(0)), log_s_k=[torch.full_like(log_m[0], -1e10)],
+                         x_r_k=list(x_r.unbind(0)), mx_r_k=list(mx.unbind(0)))
+        return recon, losses, stats, None, comp_stats
+
     def _forward_one_stage(self, x, log_m, log_s, att_stats):
         """two_stage=False (reference genesis_config.py:178-185, 198-228): appearances = BroadcastDecoder(z_m,k), no component
         VAE and no component KL; losses = {err, kl_m_k}; comp_stats is None."""
@@ -251,19 +284,21 @@ class Genesis(nn.Module, NoiseMixin):
     @staticmethod
     def x_loss(x, log_m_k, x_r_k, std, pixel_wise=False):
         """Genesis.x_loss (reference genesis_config.py:273-286) on the fused kernel."""
-        if pixel_wise:
-            raise NotImplementedError
         K = len(log_m_k)
         if not torch.is_tensor(std):
             std = torch.full((K,), float(std), device=x.device)
         std = std.reshape(-1).to(x.device).float()
         if std.numel() == 1:
             std = std.expand(K).contiguous()
+        if pixel_wise:      # per pixel and channel, [B,3,H,W] (reference :283-284): the kernel's saved log-sum-exp, negated
+            return ops.mixture_nll_pixelwise(x, torch.stack(list(x_r_k), 0), torch.stack(list(log_m_k), 0), std)
         err, _, _ = ops.mixture_nll(x, torch.stack(list(x_r_k), 0), torch.stack(list(log_m_k), 0), std, False)
         return err
 
     def sample(self, batch_size, K_steps=None):
         """Ancestral sampling (reference genesis_config.py:345-425) on the engine's decoders."""
+        if self.K_steps == 1:
+            raise NotImplementedError       # reference :346-347
         K = self.K_steps if K_steps is None else K_steps
         assert K == self.K_steps
         dev = self.std.device
@@ -320,6 +355,8 @@ class Genesis(nn.Module, NoiseMixin):
     def get_features(self, image_batch):
         with torch.no_grad():
             _, _, _, att_stats, comp_stats = self.forward(image_batch)
+        if att_stats is None:           # K_steps == 1: no mask latents
+            return torch.cat(list(comp_stats['z_k']), dim=1)
         if comp_stats is None:          # one stage: no component latents
             return torch.cat(att_stats['z_k'][:self.K_steps - 1], dim=1)
         return torch.cat([*att_stats['z_k'][:self.K_steps - 1], *comp_stats['z_k']], dim=1)

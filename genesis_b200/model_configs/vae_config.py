@@ -5,7 +5,7 @@ None, None), sample(), get_features()) and the same state_dict names (`vae.q_z_n
 `vae.p_x_nn.*`, `vae.p_x_mean`), on the engine's kernels: the gated conv encoder / conv-transpose decoder are the ones
 GENESIS uses for its attention core (holders.sylvester_encode / sylvester_decode), the Gaussian pixel likelihood is the
 mixture kernel with one slot and a zero log-mask.  Both decoder variants (`broadcast_decoder` False / True, vae_config.py:53-61).
-NOTE: written after the round-1 GPU budget was spent -- exercised on a B200 by tests/test_pending_next_round.py first."""
+Validated on a B200 in round 2 (tests/test_extras_gpu.py, tests/test_train_py_dropin.py)."""
 import os
 import sys
 
@@ -48,6 +48,9 @@ class BaselineVAE(nn.Module, NoiseMixin):
     def __init__(self, cfg):
         super().__init__()
         cfg.K_steps = None                                   # reference vae_config.py:44
+        # train.py:463 reads `model.K_steps` for every model; the reference's BaselineVAE does not define it, so its own
+        # train.py dies in visualise_outputs() at iteration 0.  The plug-in carries the attribute (one slot) so the caller runs.
+        self.K_steps = 1
         self.ldim = cfg.latent_dimension
         self.pixel_std = cfg.pixel_std
         self.pixel_bound = cfg.pixel_bound

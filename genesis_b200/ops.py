@@ -712,6 +712,36 @@ def mixture_nll(x, xr, lm, std, softmax=False):
     return _Mixture.apply(x, xr, lm, std, softmax)
 
 
+class _MixturePixelwise(Function):
+    """Genesis.x_loss(pixel_wise=True): per pixel and channel loss [B,3,H,W] = -log sum_k exp(log m_k + log N(x; xr_k, std_k))."""
+
+    @staticmethod
+    def forward(ctx, x, xr, lm, std):
+        x, xr, lm, std = _c(x), _c(xr), _c(lm), _c(std)
+        K, B = lm.shape[0], lm.shape[1]
+        P = x.shape[2] * x.shape[3]
+        err = _new(x, B)
+        recon = torch.empty_like(x)
+        lse = torch.empty_like(x)
+        _call('g2_mixture_fwd_f32', x, xr, lm, std, err, recon, lse, None, K, B, P, 0, 3, 1)
+        ctx.save_for_backward(x, xr, lm, std, lse)
+        return -lse
+
+    @staticmethod
+    def backward(ctx, gpix):
+        x, xr, lm, std, lse = ctx.saved_tensors
+        K, B = lm.shape[0], lm.shape[1]
+        P = x.shape[2] * x.shape[3]
+        dxr = torch.empty_like(xr)
+        dlm = torch.empty_like(lm)
+        _call('g2_mixture_bwd_pix_f32', x, xr, lm, std, lse, _c(gpix), dxr, dlm, K, B, P, 3, 1, 1)
+        return None, dxr, dlm, None
+
+
+def mixture_nll_pixelwise(x, xr, lm, std):
+    return _MixturePixelwise.apply(x, xr, lm, std)
+
+
 class _MixturePacked(Function):
     """Mixture likelihood on a packed decoder output dec [K,B,4,H,W] (planes 0-2 = x_r, plane 3 = mask logit).
     mode 'softmax': masks = log_softmax over K of plane 3 (GENESIS-V2, genesisv2_config.py:213-223); gradients flow to

@@ -1,26 +1,30 @@
 """Data-parallel training step of the engine: forward + loss assembly + backward + one gradient all-reduce +
-fused Adam, with GECO kept on the device.
+fused optimiser, with GECO kept on the device.
 
 Mirrors the caller's hot loop in the reference (train.py:215-263 and utils/geco.py:35-51) without its host
 syncs.  One process per GPU; parameters and gradients live in flat fp32 arenas so the data-parallel exchange
 is ONE all-reduce per step over NCCL (NVLink / NVSwitch), with the batch-mean `err` and `kl` appended to the
-arena so every rank updates GECO's beta identically (replaces nn.DataParallel, train.py:153-155)."""
+arena so every rank updates GECO's beta identically (replaces nn.DataParallel, train.py:153-155).
+
+Checkpoints interchange with the reference: `TrainStep.checkpoint()` / `restore()` use train.py:410-416's layout
+(`model_state_dict`, `optimiser_state_dict` in torch.optim's own format, `beta`, `iter_idx`, `err_ema`)."""
 import torch
 import torch.distributed as dist
 
-from . import _lib, ops
+from . import _lib, noise, ops
 
 
 class GecoState(object):
-    """utils/geco.py:19-51 as device tensors (no .item()): loss = err + beta*kl; err_ema; beta update."""
+    """utils/geco.py:19-51 as ONE device tensor {beta, err_ema, started} updated by one kernel (g2_geco_step_f32): no
+    `.item()`, no host sync, replayable inside a CUDA graph."""
 
     def __init__(self, goal, step_size, device, alpha=0.99, beta_init=1.0, beta_min=1e-10, beta_max=1e10,
                  speedup=10.0):
-        self.goal, self.step_size, self.alpha, self.speedup = float(goal), float(step_size), alpha, speedup
-        self.beta = torch.tensor(beta_init, device=device)
-        self.err_ema = torch.zeros((), device=device)
-        self.started = torch.zeros((), device=device)
-        self.beta_min, self.beta_max = beta_min, beta_max
+        self.goal, self.step_size, self.alpha = float(goal), float(step_size), float(alpha)
+        self.speedup = float(speedup) if speedup else 0.0
+        self.beta_min, self.beta_max = float(beta_min), float(beta_max)
+        self.vec = torch.tensor([float(beta_init), 0.0, 0.0], device=device)
+        self.beta, self.err_ema, self.started = self.vec[0], self.vec[1], self.vec[2]     # 0-dim views
 
     def state(self):
         """What train.py:410-416 stores in a checkpoint ('beta', 'err_ema')."""
@@ -29,20 +33,21 @@ class GecoState(object):
     @torch.no_grad()
     def load_state(self, state):
         """Restore from a reference checkpoint dict (train.py:197-203)."""
-        if 'beta' in state:
+        if 'beta' in state and state['beta'] is not None:
             self.beta.copy_(torch.as_tensor(state['beta'], dtype=torch.float32))
-        if 'err_ema' in state:
+        if 'err_ema' in state and state['err_ema'] is not None:
             self.err_ema.copy_(torch.as_tensor(state['err_ema'], dtype=torch.float32))
             self.started.fill_(1.0)
 
+    def step(self, err_kl, step_count, elbo, inv_world, update=True):
+        _lib.call('g2_geco_step_f32', self.vec, err_kl, step_count, elbo, inv_world, self.goal, self.step_size, self.alpha,
+                  self.speedup, self.beta_min, self.beta_max, 1 if update else 0)
+
     @torch.no_grad()
     def update(self, err):
-        ema = torch.where(self.started > 0, (1.0 - self.alpha) * err + self.alpha * self.err_ema, err)
-        self.err_ema.copy_(ema)
-        self.started.fill_(1.0)
-        constraint = self.goal - self.err_ema
-        rate = torch.where(constraint > 0, self.speedup * self.step_size, self.step_size) if self.speedup else self.step_size
-        self.beta.copy_((torch.exp(rate * constraint) * self.beta).clamp(self.beta_min, self.beta_max))
+        """Same update from a ready batch-mean `err` (0-dim device tensor); used by tests against utils/geco.py."""
+        pair = torch.stack([err.detach().float().reshape(()), torch.zeros((), device=self.vec.device)])
+        self.step(pair, None, None, 1.0)
 
 
 class FlatArena(object):
@@ -60,23 +65,24 @@ class FlatArena(object):
         self.n_pad = sum((p.numel() + a - 1) // a * a for p in params)
         self.flat_p = torch.zeros(self.n_pad, device=dev)
         self.flat_g = torch.zeros(self.n_pad + self.TAIL, device=dev)
+        self.offsets = []
         off = 0
         for p in params:
             k = p.numel()
             self.flat_p[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat_p[off:off + k].view_as(p)
             p.grad = self.flat_g[off:off + k].view_as(p)
+            self.offsets.append(off)
             off += (k + a - 1) // a * a
         self.tail = self.flat_g[self.n_pad:]
 
     def exchange(self, err, kl, world):
-        """ONE all-reduce(sum) of gradients + (err, kl); returns the global-batch means of err and kl.  Gradients are left
-        as the SUM over ranks: the optimiser applies the 1/world scale."""
+        """ONE all-reduce(sum) of gradients + (err, kl).  Gradients and the tail are left as the SUM over ranks: the
+        optimiser and the GECO kernel apply the 1/world scale."""
         self.tail[0].copy_(err)
         self.tail[1].copy_(kl)
         if world > 1:
             dist.all_reduce(self.flat_g)
-        return self.tail[0] / world, self.tail[1] / world
 
 
 def shard_batch(x, rank, world):
@@ -86,50 +92,88 @@ def shard_batch(x, rank, world):
     return x[rank * per:(rank + 1) * per]
 
 
+OPTIMISERS = ('adam', 'rmsprop', 'sgd')          # train.py:171-176
+
+
 class TrainStep(object):
-    """step(x) = one optimisation step on the local shard `x` (float32 [B,3,H,W], device or pinned host)."""
+    """step(x) = one optimisation step on the local shard `x` (float32 [B,3,H,W], device or pinned host).
+
+    optimiser / lr, geco + g_* and beta / beta_warmup / train_iter take the values of the caller's flags (train.py:62-86).
+    rank / noise_seed: every rank builds the model under the same torch.manual_seed so parameters match; the device noise
+    generator is then re-seeded with noise_seed + rank, so the ranks draw INDEPENDENT eps / IC-SBP seeds for their shards (what
+    nn.DataParallel's per-device generators give the reference; identical noise on every rank would correlate the global batch)."""
 
     def __init__(self, model, lr=1e-4, img_size=64, g_goal=0.5655, g_lr=1e-5, g_alpha=0.99, g_init=1.0,
-                 g_min=1e-10, g_speedup=10.0, geco=True, world_size=1):
+                 g_min=1e-10, g_speedup=10.0, geco=True, world_size=1, rank=0, noise_seed=None, optimiser='adam',
+                 beta=0.5, beta_warmup=False, train_iter=500000):
+        if optimiser not in OPTIMISERS:
+            raise ValueError('optimiser must be one of %s' % (OPTIMISERS,))
+        if getattr(model, 'multi_gpu', False):
+            raise ValueError('nn.DataParallel (--multi_gpu) is not supported: run one process per GPU (torchrun)')
         self.model = model
         self.world = world_size
+        self.rank = rank
         self.lr = lr
+        self.optimiser = optimiser
         params = [p for p in model.parameters() if p.requires_grad]
         self.arena = FlatArena(params)
         self.n_params, self.n_pad = self.arena.n_params, self.arena.n_pad
         self.flat_p, self.flat_g = self.arena.flat_p, self.arena.flat_g
         dev = self.flat_p.device
-        self.flat_m = torch.zeros(self.n_pad, device=dev)
-        self.flat_v = torch.zeros(self.n_pad, device=dev)
+        self.flat_m = torch.zeros(self.n_pad, device=dev)          # Adam exp_avg | RMSprop square_avg | SGD momentum buffer
+        self.flat_v = torch.zeros(self.n_pad, device=dev) if optimiser == 'adam' else None
         self.params = params
         self.step_count = torch.zeros((), device=dev)
-        self.geco = None
-        if geco:
-            # reference train.py:159-169
-            self.geco = GecoState(g_goal * 3 * img_size ** 2, g_lr * (64 ** 2 / img_size ** 2), dev,
-                                  alpha=g_alpha, beta_init=g_init, beta_min=g_min, speedup=g_speedup)
+        self.use_geco = bool(geco)
+        self.fixed_beta, self.beta_warmup, self.train_iter = float(beta), bool(beta_warmup), int(train_iter)
+        # reference train.py:159-169; without GECO the same object only carries err / kl / elbo bookkeeping
+        self.geco = GecoState(g_goal * 3 * img_size ** 2, g_lr * (64 ** 2 / img_size ** 2), dev,
+                              alpha=g_alpha, beta_init=g_init, beta_min=g_min, speedup=g_speedup)
+        self.elbo = torch.zeros((), device=dev)
         self.x_dev = None
         self.graph = None
         self.launches_per_step = None
+        if noise_seed is not None:
+            noise.seed_rank(noise_seed, rank, dev)
 
+    # ------------------------------------------------------------------------------------------ loss
     def loss_terms(self, losses):
-        """train.py:227-239."""
+        """train.py:227-239 (if / elif: the stacked per-step lists win over a plain tensor of the same stage)."""
         err = losses['err'].mean(0)
         kl = err.new_zeros(())
-        for key in ('kl_l_k', 'kl_m_k'):
-            if key in losses and len(losses[key]):
-                kl = kl + torch.stack(list(losses[key]), dim=1).mean(0).sum()
-        for key in ('kl_l', 'kl_m'):
-            if key in losses and torch.is_tensor(losses[key]):
-                kl = kl + losses[key].mean(0)
+        for plain, listed in (('kl_m', 'kl_m_k'), ('kl_l', 'kl_l_k')):
+            if plain in losses and torch.is_tensor(losses[plain]):
+                kl = kl + losses[plain].mean(0)
+            elif listed in losses and len(losses[listed]):
+                kl = kl + torch.stack(list(losses[listed]), dim=1).mean(0).sum()
         return err, kl
 
+    def current_beta(self):
+        """beta of the objective for THIS step (train.py:249-259)."""
+        if self.use_geco:
+            return self.geco.beta
+        if self.beta_warmup:        # linear over the first 20 % of training; step_count == iter_idx before the update
+            return (self.step_count * (self.fixed_beta / (0.2 * self.train_iter))).clamp(0.0, self.fixed_beta)
+        return self.fixed_beta
+
+    # ------------------------------------------------------------------------------------------ graph
+    def _mutable_state(self):
+        ts = [self.flat_p, self.flat_m, self.step_count, self.geco.vec, self.elbo]
+        if self.flat_v is not None:
+            ts.append(self.flat_v)
+        ts += [b for b in self.model.buffers()]
+        return ts
+
     def capture(self, x_example, warmup=3):
-        """Capture forward + backward + all-reduce + GECO + Adam of one step into a CUDA graph (static input
-        buffer, static ELBO output).  After this, step()/step_device() replay the graph: zero host work per step."""
+        """Capture forward + backward + all-reduce + GECO + optimiser of one step into a CUDA graph (static input buffer,
+        static ELBO output).  The warm-up steps capture needs run on a snapshot: parameters, optimiser state, GECO, the
+        BatchNorm buffers and the step counter are restored afterwards, so capture() does not train.  After this,
+        step()/step_device() replay the graph: zero host work per step."""
         dev = self.flat_p.device
         self.x_static = torch.empty_like(x_example, device=dev)
         self.x_static.copy_(x_example)
+        snapshot = [t.detach().clone() for t in self._mutable_state()]
+        rng = torch.cuda.get_rng_state(dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -143,42 +187,52 @@ class TrainStep(object):
         with torch.cuda.graph(graph):
             self.elbo_static = self._step_eager(self.x_static)
         self.launches_per_step = lib.launches - l0
+        with torch.no_grad():
+            for t, s in zip(self._mutable_state(), snapshot):
+                t.copy_(s)
+            self.flat_g.zero_()
+        torch.cuda.set_rng_state(rng, dev)
+        torch.cuda.synchronize()
         self.graph = graph
         return self
 
     def step_device(self, x):
-        """x already resident on the device.  Returns the (detached) ELBO scalar tensor."""
+        """x already resident on the device.  Returns the (detached) ELBO scalar tensor of this step (a fresh tensor: the
+        graph's static output is overwritten by the next replay)."""
         if self.graph is not None:
             if x is not self.x_static:
                 self.x_static.copy_(x, non_blocking=True)
             self.graph.replay()
-            return self.elbo_static
-        return self._step_eager(x)
+            return self.elbo_static.clone()
+        return self._step_eager(x).clone()
 
     def _step_eager(self, x):
-        # the arena gradients are pre-zeroed and re-zeroed by the fused Adam kernel, so the conv / linear kernels may
+        # the arena gradients are pre-zeroed and re-zeroed by the fused optimiser kernel, so the conv / linear kernels may
         # accumulate weight and bias gradients straight into p.grad (no permute copy + AccumulateGrad add per parameter)
         ops.set_direct_grad(True)
         try:
             recon, losses, stats, att, comp = self.model(x)
             err, kl = self.loss_terms(losses)
-            beta = self.geco.beta if self.geco is not None else 1.0
-            loss = err + beta * kl
+            loss = err + self.current_beta() * kl
             loss.backward()
             ops.join_grad_stream(self.flat_p.device)      # parameter-gradient kernels run on a side stream
         finally:
             ops.set_direct_grad(False)
-        tail = self.arena.tail
         with torch.no_grad():
-            gerr, gkl = self.arena.exchange(err.detach(), kl.detach(), self.world)      # ONE exchange per step
-            if self.geco is not None:
-                self.geco.update(gerr)
-            self.step_count += 1
-            elbo = (gerr + gkl).clone()
-            _lib.call('g2_adam_f32', self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.n_pad, self.lr,
-                      0.9, 0.999, 1e-8, self.step_count, 1.0 / self.world, 1)
-            tail.zero_()
-        return elbo
+            self.arena.exchange(err.detach(), kl.detach(), self.world)      # ONE exchange per step
+            inv = 1.0 / self.world
+            # GECO (or plain bookkeeping) + step counter + elbo in one scalar kernel; then the fused optimiser, which
+            # scales the summed gradients by 1/world and re-zeroes them
+            self.geco.step(self.arena.tail, self.step_count, self.elbo, inv, update=self.use_geco)
+            if self.optimiser == 'adam':
+                _lib.call('g2_adam_f32', self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.n_pad, self.lr,
+                          0.9, 0.999, 1e-8, self.step_count, inv, 1)
+            elif self.optimiser == 'rmsprop':
+                _lib.call('g2_rmsprop_f32', self.flat_p, self.flat_g, self.flat_m, self.n_pad, self.lr, 0.99, 1e-8, inv, 1)
+            else:
+                _lib.call('g2_sgd_f32', self.flat_p, self.flat_g, self.flat_m, self.n_pad, self.lr, 0.9, self.step_count, inv, 1)
+            self.arena.tail.zero_()
+        return self.elbo
 
     def step(self, x):
         """Public entry point: x on the host (ideally pinned) or the device; returns the ELBO tensor."""
@@ -193,3 +247,75 @@ class TrainStep(object):
                 self.x_dev.copy_(x, non_blocking=True)
                 x = self.x_dev
         return self.step_device(x)
+
+    # ------------------------------------------------------------------------------------------ checkpoints
+    def _torch_optimiser(self):
+        """A torch.optim object of the caller's kind over the same parameters (train.py:171-176): the source of the
+        `param_groups` layout, so that the exported state loads into the reference's optimiser and vice versa."""
+        if self.optimiser == 'adam':
+            return torch.optim.Adam(self.params, self.lr)
+        if self.optimiser == 'rmsprop':
+            return torch.optim.RMSprop(self.params, self.lr)
+        return torch.optim.SGD(self.params, self.lr, 0.9)
+
+    def optimiser_state_dict(self):
+        """The fused optimiser's state in torch.optim's own `state_dict()` format (per-parameter `step`, `exp_avg`,
+        `exp_avg_sq` for Adam; `step`, `square_avg` for RMSprop; `momentum_buffer` for SGD)."""
+        sd = self._torch_optimiser().state_dict()
+        state = {}
+        stepped = float(self.step_count.item()) > 0
+        if stepped:
+            for i, (p, off) in enumerate(zip(self.params, self.arena.offsets)):
+                k = p.numel()
+                m = self.flat_m[off:off + k].view_as(p).detach().clone()
+                if self.optimiser == 'adam':
+                    state[i] = {'step': self.step_count.detach().clone().cpu(), 'exp_avg': m,
+                                'exp_avg_sq': self.flat_v[off:off + k].view_as(p).detach().clone()}
+                elif self.optimiser == 'rmsprop':
+                    state[i] = {'step': self.step_count.detach().clone().cpu(), 'square_avg': m}
+                else:
+                    state[i] = {'momentum_buffer': m}
+        sd['state'] = state
+        return sd
+
+    @torch.no_grad()
+    def load_optimiser_state_dict(self, sd):
+        """Load a torch.optim state_dict (the `optimiser_state_dict` of a reference checkpoint, train.py:194) into the flat
+        moment arenas and the device step counter."""
+        state = sd.get('state', {})
+        self.flat_m.zero_()
+        if self.flat_v is not None:
+            self.flat_v.zero_()
+        step = 0.0
+        key_m = {'adam': 'exp_avg', 'rmsprop': 'square_avg', 'sgd': 'momentum_buffer'}[self.optimiser]
+        for i, (p, off) in enumerate(zip(self.params, self.arena.offsets)):
+            st = state.get(i, state.get(str(i)))
+            if not st:
+                continue
+            k = p.numel()
+            if st.get(key_m) is not None:
+                self.flat_m[off:off + k].copy_(st[key_m].reshape(-1))
+            if self.optimiser == 'adam':
+                self.flat_v[off:off + k].copy_(st['exp_avg_sq'].reshape(-1))
+            step = max(step, float(st['step']) if 'step' in st else 1.0)
+        self.step_count.fill_(step)
+
+    def checkpoint(self, iter_idx=None):
+        """The dict train.py:410-416 saves; loads in the reference's resume path (train.py:180-207) and in restore()."""
+        ck = {'model_state_dict': self.model.state_dict(), 'optimiser_state_dict': self.optimiser_state_dict(),
+              'beta': self.geco.beta.detach().clone() if self.use_geco else torch.tensor(self.fixed_beta),
+              'iter_idx': int(self.step_count.item()) - 1 if iter_idx is None else iter_idx}
+        if self.use_geco:
+            ck['err_ema'] = self.geco.err_ema.detach().clone()
+        return ck
+
+    @torch.no_grad()
+    def restore(self, ck):
+        sd = dict(ck['model_state_dict'])
+        for legacy in ('comp_vae.decoder_module.seq.0.pixel_coords.g_1', 'comp_vae.decoder_module.seq.0.pixel_coords.g_2'):
+            sd.pop(legacy, None)                       # train.py:191-192
+        self.model.load_state_dict(sd)                 # copies INTO the arena views
+        self.load_optimiser_state_dict(ck['optimiser_state_dict'])
+        if self.use_geco:
+            self.geco.load_state(ck)
+        return ck.get('iter_idx', -1) + 1

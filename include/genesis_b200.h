@@ -167,6 +167,11 @@ int g2_mixture_fwd_f32(const float* x, const float* xr, const float* lm, const f
 int g2_mixture_bwd_f32(const float* x, const float* xr, const float* lm, const float* stdv, const float* lse,
                        const float* gerr, float* dxr, float* dlm, int K, int B, int P, int softmax, int xr_cs,
                        int lm_cs, int dlm_cs, g2_stream_t stream);
+/* Backward of the pixel-wise form (Genesis.x_loss(pixel_wise=True), models/genesis_config.py:283-284): the loss is -lse
+ * [B,3,P] and gpix [B,3,P] its upstream gradient; masks are given (no softmax). */
+int g2_mixture_bwd_pix_f32(const float* x, const float* xr, const float* lm, const float* stdv, const float* lse,
+                           const float* gpix, float* dxr, float* dlm, int K, int B, int P, int xr_cs, int lm_cs, int dlm_cs,
+                           g2_stream_t stream);
 /* xr_cs / lm_cs / dlm_cs: channels per (slot,image) in the xr / lm / dlm tensors -- 3,1,1 for separate tensors, 4,4,4
  * when x_r and the mask logit are the 4 planes of one decoder output [K,B,4,P] (lm = dec + 3P). */
 
@@ -285,6 +290,19 @@ int g2_debug_umma_probe(const float* a_img, const float* b_img, float* D, int a_
  * caller's loop (train.py:175,263).  `step` is a device-resident float counter (1-based). n % 4 == 0. */
 int g2_adam_f32(float* p, float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps,
                 const float* step, float grad_scale, int zero_grad, g2_stream_t stream);
+/* The other two optimisers train.py:171-176 offers, same conventions: RMSprop(lr) = alpha 0.99, eps 1e-8, no momentum;
+ * SGD(lr, 0.9) = momentum buffer initialised with the first gradient (step <= 1). */
+int g2_rmsprop_f32(float* p, float* g, float* sq, long n, float lr, float alpha, float eps, float grad_scale,
+                   int zero_grad, g2_stream_t stream);
+int g2_sgd_f32(float* p, float* g, float* buf, long n, float lr, float momentum, const float* step, float grad_scale,
+               int zero_grad, g2_stream_t stream);
+/* GECO update (utils/geco.py:35-51) on device scalars, one launch, no host sync: state = {beta, err_ema, started};
+ * err_kl = {sum over ranks of the batch-mean err, ditto kl} (the tail of the gradient arena after the all-reduce);
+ * update = 0 leaves the GECO state alone (plain beta objective).  Also advances the optimiser step counter and writes
+ * elbo = err + kl (either may be NULL). */
+int g2_geco_step_f32(float* state, const float* err_kl, float* step_count, float* elbo, float inv_world, float goal,
+                     float step_size, float alpha, float speedup, float beta_min, float beta_max, int update,
+                     g2_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -41,8 +41,14 @@ def test_reference_checkpoint_round_trip(model, K, img):
         assert torch.equal(a, b), k
 
 
-def test_geco_state_round_trip():
-    """beta / err_ema of a reference checkpoint (train.py:197-203, 410-416) restore into the device-resident GECO."""
+def test_geco_state_round_trip(monkeypatch):
+    """beta / err_ema of a reference checkpoint (train.py:197-203, 410-416) restore into the device-resident GECO (its one
+    kernel runs through the CPU emulation of the source here)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'cuda_emu'))
+    import emu_lib
+    emu_lib.install(monkeypatch)
     from genesis_b200 import trainer
     g = trainer.GecoState(goal=0.5655 * 3 * 64 ** 2, step_size=1e-5, device='cpu')
     st = {'beta': torch.tensor(0.37), 'err_ema': torch.tensor(6789.0)}

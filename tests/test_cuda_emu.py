@@ -227,6 +227,33 @@ def test_fused_adam_matches_torch_optim(emu):
         assert np.abs(p - ref.detach().numpy()).max() <= 2e-6 * max(1.0, ref.detach().abs().max().item())
 
 
+@pytest.mark.parametrize('kind', ['rmsprop', 'sgd'])
+def test_fused_rmsprop_sgd_match_torch_optim(emu, kind):
+    """g2_rmsprop_f32 / g2_sgd_f32 vs torch.optim.RMSprop(lr) / torch.optim.SGD(lr, 0.9) (train.py:171-176)."""
+    lib = emu('pointwise.cu')
+    lib.g2_rmsprop_f32.argtypes = [P, P, P, ctypes.c_long, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, P]
+    lib.g2_sgd_f32.argtypes = [P, P, P, ctypes.c_long, ctypes.c_float, ctypes.c_float, P, ctypes.c_float, ctypes.c_int, P]
+    torch.manual_seed(0)
+    n = 512 + 64
+    p0 = torch.randn(n)
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.RMSprop([ref], 1e-3) if kind == 'rmsprop' else torch.optim.SGD([ref], 1e-3, 0.9)
+    p, m = p0.numpy().copy(), np.zeros(n, np.float32)
+    step = np.zeros(1, np.float32)
+    for it in range(5):
+        g = torch.randn(n) * (10.0 ** (it - 2))
+        ref.grad = g.clone()
+        opt.step()
+        gbuf = (g * 2.0).numpy().copy()
+        step += 1
+        if kind == 'rmsprop':
+            assert lib.g2_rmsprop_f32(ptr(p), ptr(gbuf), ptr(m), n, 1e-3, 0.99, 1e-8, 0.5, 1, None) == 0
+        else:
+            assert lib.g2_sgd_f32(ptr(p), ptr(gbuf), ptr(m), n, 1e-3, 0.9, ptr(step), 0.5, 1, None) == 0
+        assert np.abs(gbuf).max() == 0.0
+        assert np.abs(p - ref.detach().numpy()).max() <= 3e-6 * max(1.0, ref.detach().abs().max().item()), it
+
+
 @pytest.mark.parametrize('nl_is_K', [True, False])
 def test_sbp_scan(emu, nl_is_K):
     lib = emu('pointwise.cu')

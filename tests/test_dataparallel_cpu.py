@@ -46,7 +46,8 @@ def _worker(rank, world, port, x, out):
     xs = shard_batch(x, rank, world)
     err, kl = _loss_terms(_losses(model, xs))
     (err + 0.7 * kl).backward()
-    gerr, gkl = arena.exchange(err.detach(), kl.detach(), world)
+    arena.exchange(err.detach(), kl.detach(), world)
+    gerr, gkl = arena.tail[0] / world, arena.tail[1] / world      # the tail carries the SUM over ranks of the batch means
     out[rank] = (arena.flat_g[:arena.n_pad].clone() / world, gerr.clone(), gkl.clone(),
                  [p.grad.data_ptr() for p in model.parameters()], arena.flat_g.data_ptr())
     dist.destroy_process_group()
@@ -94,3 +95,29 @@ def test_shard_batch_rejects_ragged():
     assert shard_batch(x, 1, 3).shape[0] == 2
     with pytest.raises(AssertionError):
         shard_batch(x, 0, 4)
+
+
+def _noise_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from genesis_b200 import noise
+    torch.manual_seed(0)                                 # every rank constructs the model under the same seed ...
+    model = _model()
+    noise.seed_rank(1234, rank, 'cpu')                   # ... and then takes its own noise stream (trainer.TrainStep does this)
+    src = noise.NoiseMixin()
+    like = next(model.parameters())
+    out[rank] = (torch.cat([p.detach().flatten() for p in model.parameters()]), src._normal((4, 8), like), src._uniform((4, 8), like))
+    dist.destroy_process_group()
+
+
+def test_ranks_share_parameters_but_draw_independent_noise():
+    """Data-parallel ranks must not replay the same eps / IC-SBP seed noise on every shard (correlated noise across the global
+    batch): identical parameters, different noise -- the reference's nn.DataParallel replicas draw per-device noise too."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_noise_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    p0, n0, u0 = out[0]
+    p1, n1, u1 = out[1]
+    assert torch.equal(p0, p1)
+    assert not torch.equal(n0, n1) and not torch.equal(u0, u1)
+    assert abs(float((n0 * n1).mean())) < 0.5            # and not merely shifted copies

@@ -401,3 +401,66 @@ def test_full_size_identities_and_batch_partition_invariance(model, K, img, B, g
     m.set_noise_tape(None)
     for name, p in m.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), name
+
+
+def test_genesis_single_slot_matches_the_real_reference():
+    """GENESIS with K_steps = 1 (reference genesis_config.py:94-96, 161-166, 226-228): no attention process (the core is built
+    -- it consumes the seeded generator -- but is not part of the model), one all-ones mask, standard-normal component prior,
+    `kl_m` = 0, att_stats None, sample() raises NotImplementedError.  Compared with the reference itself (oracle/_ref)."""
+    import util_parity as U
+    from oracle import models as M, ref_loader
+    from genesis_b200.datasets import synth
+    from genesis_b200.model_configs import genesis_config as plugin
+    if not ref_loader.available():
+        pytest.skip('neither the reference checkout nor oracle/_ref is present')
+    cfg = M.make_cfg('genesis', K_steps=1, img_size=64)
+    x = torch.from_numpy(synth.multid(3, 64, 4)[0])
+    ref, out = U.run_reference('genesis', cfg, x, U.make_tape(9), seed=3)
+    torch.manual_seed(3)
+    eng = plugin.load(M.make_cfg('genesis', K_steps=1, img_size=64))
+    assert [k for k, _ in eng.state_dict().items()] == [k for k, _ in ref.state_dict().items()]
+    for (k, a), (_, b) in zip(eng.state_dict().items(), ref.state_dict().items()):
+        assert torch.equal(a, b), k                       # seeded initialisation is bit-identical (same generator consumption)
+    eng = eng.cuda().train()
+    recon, losses, stats, att, comp = U.run_engine(eng, x, U.make_tape(9))
+    assert att is None and out[3] is None
+    assert U.rel_l2(losses['err'], out[1]['err']) < 1e-4
+    assert float(losses['kl_m']) == 0.0 and float(out[1]['kl_m']) == 0.0
+    assert (losses['kl_l_k'][0].cpu() - out[1]['kl_l_k'][0]).abs().max().item() < 1e-2
+    assert U.rel_l2(recon, out[0]) < 1e-3
+    assert float(stats['log_m_k'][0].abs().max()) == 0.0 and float(stats['log_s_k'][0].max()) == -1e10
+    U.compare_grads_with_module(eng, ref, tol=1e-2)
+    with pytest.raises(NotImplementedError):
+        eng.sample(2)
+
+
+def test_x_loss_pixel_wise_matches_the_real_reference():
+    """Genesis.x_loss(..., pixel_wise=True) (reference genesis_config.py:273-286): values and the gradients w.r.t. the component
+    means and the log-masks under a per-pixel upstream gradient."""
+    from oracle import ref_loader
+    from genesis_b200.model_configs import genesis_config as plugin
+    if not ref_loader.available():
+        pytest.skip('neither the reference checkout nor oracle/_ref is present')
+    ref_loader._setup()
+    from models.genesis_config import Genesis as RefGenesis
+    torch.manual_seed(0)
+    K, B, Hh = 4, 3, 16
+    x = torch.rand(B, 3, Hh, Hh)
+    xr = [torch.rand(B, 3, Hh, Hh, requires_grad=True) for _ in range(K)]
+    lm = torch.log_softmax(torch.randn(B, 1, Hh, Hh, K), dim=4)
+    lmk = [lm[..., k].clone().requires_grad_(True) for k in range(K)]
+    std = torch.tensor([0.7, 0.5, 0.9, 0.7]).view(1, 1, 1, 1, K)
+    w = torch.randn(B, 3, Hh, Hh)
+    ref = RefGenesis.x_loss(x, lmk, xr, std, pixel_wise=True)
+    (ref * w).sum().backward()
+    xr_g = [t.detach().cuda().requires_grad_(True) for t in xr]
+    lm_g = [t.detach().cuda().requires_grad_(True) for t in lmk]
+    got = plugin.Genesis.x_loss(x.cuda(), lm_g, xr_g, std.cuda(), pixel_wise=True)
+    assert got.shape == ref.shape
+    (got * w.cuda()).sum().backward()
+    torch.testing.assert_close(got.cpu(), ref.detach(), rtol=1e-5, atol=1e-5)
+    for a, b in zip(xr_g + lm_g, xr + lmk):
+        torch.testing.assert_close(a.grad.cpu(), b.grad, rtol=1e-4, atol=1e-5)
+    # and the summed form is consistent with it
+    summed = plugin.Genesis.x_loss(x.cuda(), lm_g, xr_g, std.cuda())
+    torch.testing.assert_close(summed, got.sum((1, 2, 3)), rtol=1e-5, atol=1e-3)

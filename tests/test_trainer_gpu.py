@@ -1,0 +1,138 @@
+"""GPU: trainer.TrainStep beyond the bench step -- the three optimisers of train.py:171-176 against torch.optim, the optimiser
+state in torch.optim's own state_dict format (checkpoints interchange with the reference, train.py:194, 410-416), a restored
+TrainStep continuing exactly where the saved one would, capture() not consuming training steps, the non-GECO objective with
+beta / beta_warmup (train.py:249-259), and bitwise run-to-run reproducibility of the GEMM path."""
+import pytest
+import torch
+
+import util_parity as U
+from genesis_b200.datasets import synth
+from test_oracle_golden import build_engine_model
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('kind', ['adam', 'rmsprop', 'sgd'])
+def test_fused_optimisers_equal_torch_optim(kind):
+    from genesis_b200 import _lib
+    torch.manual_seed(0)
+    n = 4096 + 64
+    p0 = torch.randn(n, device='cuda')
+    ref = p0.clone().requires_grad_(True)
+    opt = {'adam': lambda: torch.optim.Adam([ref], 1e-3), 'rmsprop': lambda: torch.optim.RMSprop([ref], 1e-3),
+           'sgd': lambda: torch.optim.SGD([ref], 1e-3, 0.9)}[kind]()
+    p, m, v = p0.clone(), torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
+    step = torch.zeros((), device='cuda')
+    world = 4.0
+    for it in range(6):
+        g = torch.randn(n, device='cuda') * (10.0 ** (it - 3))
+        ref.grad = g.clone()
+        opt.step()
+        gbuf = (g * world).clone()          # the arena holds the SUM over ranks; the kernels apply 1 / world
+        step += 1
+        if kind == 'adam':
+            _lib.call('g2_adam_f32', p, gbuf, m, v, n, 1e-3, 0.9, 0.999, 1e-8, step, 1.0 / world, 1)
+        elif kind == 'rmsprop':
+            _lib.call('g2_rmsprop_f32', p, gbuf, m, n, 1e-3, 0.99, 1e-8, 1.0 / world, 1)
+        else:
+            _lib.call('g2_sgd_f32', p, gbuf, m, n, 1e-3, 0.9, step, 1.0 / world, 1)
+        torch.cuda.synchronize()
+        assert gbuf.abs().max().item() == 0.0
+        assert (p - ref.detach()).abs().max().item() <= 3e-6 * max(1.0, ref.detach().abs().max().item()), it
+
+
+def _make(kind='adam', **kw):
+    from genesis_b200 import trainer
+    m, cfg = build_engine_model('genesis', 3, 64)
+    m = m.cuda().train()
+    return trainer.TrainStep(m, lr=1e-3, img_size=64, optimiser=kind, **kw), m
+
+
+@pytest.mark.parametrize('kind', ['adam', 'rmsprop', 'sgd'])
+def test_optimiser_state_round_trips_through_torch_optim(kind):
+    """Export after 2 steps -> torch.optim.<kind>.load_state_dict accepts it and holds the same moments -> a fresh TrainStep
+    restored from the checkpoint continues with the same parameters as the original."""
+    from genesis_b200 import trainer
+    x = [torch.from_numpy(synth.multid(4, 64, s)[0]).cuda() for s in (1, 2, 3)]
+    ts, m = _make(kind, noise_seed=5)
+    for i in range(2):
+        ts.step(x[i])
+    ck = ts.checkpoint()
+    assert ck['iter_idx'] == 1 and set(ck) >= {'model_state_dict', 'optimiser_state_dict', 'beta', 'err_ema', 'iter_idx'}
+    # (1) torch.optim takes the exported state
+    clones = [torch.nn.Parameter(p.detach().clone()) for p in ts.params]
+    topt = {'adam': lambda: torch.optim.Adam(clones, 1e-3), 'rmsprop': lambda: torch.optim.RMSprop(clones, 1e-3),
+            'sgd': lambda: torch.optim.SGD(clones, 1e-3, 0.9)}[kind]()
+    topt.load_state_dict(ck['optimiser_state_dict'])
+    key = {'adam': 'exp_avg', 'rmsprop': 'square_avg', 'sgd': 'momentum_buffer'}[kind]
+    for i, (c, off) in enumerate(zip(clones, ts.arena.offsets)):
+        assert torch.equal(topt.state[c][key].flatten(), ts.flat_m[off:off + c.numel()])
+    # (2) and a torch.optim state loads back: same flat arenas
+    ts2, m2 = _make(kind, noise_seed=99)
+    it = ts2.restore({k: (v if k != 'optimiser_state_dict' else topt.state_dict()) for k, v in ck.items()})
+    assert it == 2
+    assert torch.equal(ts2.flat_p, ts.flat_p) and torch.equal(ts2.flat_m, ts.flat_m)
+    if kind == 'adam':
+        assert torch.equal(ts2.flat_v, ts.flat_v)
+    assert float(ts2.step_count) == float(ts.step_count) == 2.0
+    assert torch.equal(ts2.geco.vec, ts.geco.vec)
+    # (3) both continue identically (same noise stream from here on)
+    from genesis_b200 import noise
+    for t in (ts, ts2):
+        noise.seed_rank(77, 0, 'cuda')
+        t.step(x[2])
+    torch.cuda.synchronize()
+    d = (ts.flat_p - ts2.flat_p).abs().max().item()
+    assert d <= 1e-5, d
+
+
+def test_capture_does_not_train_and_replay_equals_eager():
+    """capture() runs its warm-up on a snapshot (parameters, moments, GECO, BatchNorm buffers, step counter, noise stream are
+    restored), so a captured TrainStep and an eager one started from the same state stay together."""
+    from genesis_b200 import noise
+    x = torch.from_numpy(synth.multid(4, 64, 1)[0]).cuda()
+    ts_e, m_e = _make()
+    ts_g, m_g = _make()
+    noise.seed_rank(3, 0, 'cuda')
+    p_before = ts_g.flat_p.clone()
+    bufs_before = [b.clone() for b in m_g.buffers()]
+    ts_g.capture(x)
+    assert torch.equal(ts_g.flat_p, p_before) and float(ts_g.step_count) == 0.0 and float(ts_g.geco.started) == 0.0
+    assert all(torch.equal(a, b) for a, b in zip(m_g.buffers(), bufs_before))
+    assert ts_g.flat_m.abs().max().item() == 0.0 and ts_g.flat_g.abs().max().item() == 0.0
+    e_g, e_e = [], []
+    noise.seed_rank(3, 0, 'cuda')
+    for _ in range(3):
+        e_g.append(ts_g.step(x))            # fresh tensors: keeping them must not alias the graph's static output
+    noise.seed_rank(3, 0, 'cuda')
+    for _ in range(3):
+        e_e.append(ts_e.step(x))
+    torch.cuda.synchronize()
+    assert len({float(e) for e in e_g}) == 3
+    for a, b in zip(e_g, e_e):
+        assert float(a) == pytest.approx(float(b), rel=2e-4)
+    assert U.rel_l2(ts_g.flat_p, ts_e.flat_p) < 1e-3
+
+
+def test_plain_beta_objective_and_warmup():
+    """geco=False: loss = err + beta * kl with the caller's --beta, or the linear warm-up over the first 20 % of training
+    (train.py:249-259); the GECO state stays untouched."""
+    x = torch.from_numpy(synth.multid(2, 64, 1)[0]).cuda()
+    ts, m = _make(geco=False, beta=0.5)
+    assert ts.current_beta() == 0.5
+    ts.step(x)
+    assert float(ts.geco.started) == 0.0 and float(ts.geco.beta) == 1.0 and float(ts.step_count) == 1.0
+    tw, _ = _make(geco=False, beta=0.5, beta_warmup=True, train_iter=100)
+    assert float(tw.current_beta()) == 0.0                      # iteration 0
+    tw.step_count.fill_(10.0)
+    assert float(tw.current_beta()) == pytest.approx(0.25)      # 0.5 * 10 / (0.2 * 100)
+    tw.step_count.fill_(1000.0)
+    assert float(tw.current_beta()) == pytest.approx(0.5)
+
+
+def test_multi_gpu_flag_is_rejected():
+    from genesis_b200 import trainer
+    m, cfg = build_engine_model('genesis', 3, 64)
+    m.multi_gpu = True
+    with pytest.raises(ValueError):
+        trainer.TrainStep(m.cuda())

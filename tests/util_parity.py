@@ -80,3 +80,23 @@ def global_grad_rel_l2(model, P):
         g = p.grad.detach().double().cpu() if p.grad is not None else torch.zeros_like(ref, dtype=torch.float64)
         num += (g - ref.double()).pow(2).sum().item()
     return (num / max(den, 1e-300)) ** 0.5
+
+
+def run_reference(name, cfg, x, tape, seed=0, state_dict=None):
+    """The REAL reference nn.Module (live checkout, or the byte-identical copy under oracle/_ref on the GPU box) on the CPU:
+    seeded construction (or a given state dict), noise replayed from the tape, total loss as train.py:227-259 with beta = 1,
+    backward.  Returns (module, outputs 5-tuple)."""
+    from oracle import ref_loader
+    ref = ref_loader.load_reference(name, dict(cfg), seed=seed).train()
+    if state_dict is not None:
+        ref.load_state_dict({k: v.detach().cpu() for k, v in state_dict.items()})
+    ref.zero_grad(set_to_none=True)
+    with ref_loader.replay_noise(tape):
+        out = ref(x.cpu())
+    engine_total_loss(out[1]).backward()
+    return ref, out
+
+
+def compare_grads_with_module(model, ref, tol, floor_frac=1e-4):
+    P = dict(ref.named_parameters())
+    return compare_grads(model, P, tol, floor_frac)
