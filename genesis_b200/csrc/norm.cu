@@ -15,7 +15,10 @@
 namespace {
 
 // ---------------------------------------------------------------------------------- forward stats
-// y [N, HW, C]; sums [N, C, 2] (double, pre-zeroed).  grid = (chunks, N), 256 threads.
+// y [N, HW, C]; sums [N, C, 2] (double, pre-zeroed).  grid = (chunks, N), 256 threads.  A thread owns one channel quad and
+// strides over rows; the loads of NORM_U rows are issued before any of them is used (bytes in flight per thread).
+constexpr int NORM_U = 4;
+
 __global__ void __launch_bounds__(256) norm_stats_kernel(const float* __restrict__ y, double* __restrict__ sums,
                                                          int HW, int C, int rows_per_block) {
     const int q = C >> 2;
@@ -28,13 +31,21 @@ __global__ void __launch_bounds__(256) norm_stats_kernel(const float* __restrict
     float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
     if (lane < lanes) {
         const float* base = y + ((long)n * HW) * C + quad * 4;
-        for (int r = r0 + lane; r < r1; r += lanes) {
-            const float4 v = g2_ldg4(base + (long)r * C);
-            s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-            ss[0] += v.x * v.x; ss[1] += v.y * v.y; ss[2] += v.z * v.z; ss[3] += v.w * v.w;
+        for (int r = r0 + lane; r < r1; r += lanes * NORM_U) {
+            float4 v[NORM_U];
+#pragma unroll
+            for (int u = 0; u < NORM_U; ++u) {
+                const int rr = r + u * lanes;
+                v[u] = rr < r1 ? g2_ldg4(base + (long)rr * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < NORM_U; ++u) {
+                s[0] += v[u].x; s[1] += v[u].y; s[2] += v[u].z; s[3] += v[u].w;
+                ss[0] += v[u].x * v[u].x; ss[1] += v[u].y * v[u].y; ss[2] += v[u].z * v[u].z; ss[3] += v[u].w * v[u].w;
+            }
         }
     }
-    __shared__ double sm[256 * 8];
+    __shared__ float sm[256 * 8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) { sm[t * 8 + j] = s[j]; sm[t * 8 + 4 + j] = ss[j]; }
     __syncthreads();
@@ -42,7 +53,7 @@ __global__ void __launch_bounds__(256) norm_stats_kernel(const float* __restrict
     for (int o = t; o < q * 8; o += 256) {
         const int qq = o >> 3, j = o & 7;
         double acc = 0.0;
-        for (int l = 0; l < lanes; ++l) acc += sm[(l * q + qq) * 8 + j];
+        for (int l = 0; l < lanes; ++l) acc += (double)sm[(l * q + qq) * 8 + j];
         const int c = qq * 4 + (j & 3);
         atomicAdd(sums + ((long)n * C + c) * 2 + (j >> 2), acc);
     }
@@ -106,55 +117,70 @@ __global__ void norm_finalize_kernel(const NormFinP p) {
 
 // ---------------------------------------------------------------------------------- forward apply
 // POST_GATE: y [N,HW,2C] -> out [N,HW,C];  POST_RELU: y [N,HW,C] -> out [N,HW,C].
-// scale/shift [Ns, Cy] (null -> identity), sn = stride over n (0 for batch mode).
+// scale/shift [Ns, Cy] (null -> identity), sn = stride over n (0 for batch mode).  grid = (chunks, N): a thread owns one channel
+// quad of one image, so its scale / shift live in registers; rows are strided with NORM_U loads in flight.
+__device__ __forceinline__ float4 affine4(const float4 a, const float4 v, const float4 b) {
+    return make_float4(fmaf(a.x, v.x, b.x), fmaf(a.y, v.y, b.y), fmaf(a.z, v.z, b.z), fmaf(a.w, v.w, b.w));
+}
+
 template <int POST>
 __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict__ y, const float* __restrict__ scale,
                                                          const float* __restrict__ shift, float* __restrict__ out,
-                                                         long total_quads, int HW, int C, int sn) {
+                                                         int HW, int C, int sn, int rows_per_block) {
     const int q = C >> 2;
     const int Cy = POST == G2_POST_GATE ? 2 * C : C;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total_quads; i += (long)gridDim.x * blockDim.x) {
-        const int quad = (int)(i % q);
-        const long row = i / q;               // n*HW + p
-        const int n = (int)(row / HW);
-        const int c = quad * 4;
-        const float* yp = y + row * Cy + c;
-        float4 h = g2_ldg4(yp);
-        float4 a = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (scale) { a = g2_ldg4(scale + (long)n * sn + c); b = g2_ldg4(shift + (long)n * sn + c); }
-        h.x = fmaf(a.x, h.x, b.x); h.y = fmaf(a.y, h.y, b.y); h.z = fmaf(a.z, h.z, b.z); h.w = fmaf(a.w, h.w, b.w);
-        float4 o;
-        if (POST == G2_POST_GATE) {
-            float4 g = g2_ldg4(yp + C);
-            float4 ag = make_float4(1.f, 1.f, 1.f, 1.f), bg = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (scale) { ag = g2_ldg4(scale + (long)n * sn + C + c); bg = g2_ldg4(shift + (long)n * sn + C + c); }
-            g.x = fmaf(ag.x, g.x, bg.x); g.y = fmaf(ag.y, g.y, bg.y); g.z = fmaf(ag.z, g.z, bg.z); g.w = fmaf(ag.w, g.w, bg.w);
-            o.x = h.x * g2_sigmoidf(g.x); o.y = h.y * g2_sigmoidf(g.y);
-            o.z = h.z * g2_sigmoidf(g.z); o.w = h.w * g2_sigmoidf(g.w);
-        } else if (POST == G2_POST_RELU) {
-            o.x = fmaxf(h.x, 0.f); o.y = fmaxf(h.y, 0.f); o.z = fmaxf(h.z, 0.f); o.w = fmaxf(h.w, 0.f);
-        } else {
-            o = h;
+    const int lanes = 256 / q;
+    const int lane = threadIdx.x / q, quad = threadIdx.x - lane * q;
+    if (lane >= lanes) return;
+    const int n = blockIdx.y;
+    const int c = quad * 4;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(HW, r0 + rows_per_block);
+    float4 a = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f), ag = a, bg = b;
+    if (scale) {
+        a = g2_ldg4(scale + (long)n * sn + c); b = g2_ldg4(shift + (long)n * sn + c);
+        if (POST == G2_POST_GATE) { ag = g2_ldg4(scale + (long)n * sn + C + c); bg = g2_ldg4(shift + (long)n * sn + C + c); }
+    }
+    const float* yb = y + (long)n * HW * Cy + c;
+    float* ob = out + (long)n * HW * C + c;
+    for (int r = r0 + lane; r < r1; r += lanes * NORM_U) {
+        float4 hv[NORM_U], gv[NORM_U];
+#pragma unroll
+        for (int u = 0; u < NORM_U; ++u) {
+            const int rr = r + u * lanes;
+            if (rr < r1) {
+                hv[u] = g2_ldg4(yb + (long)rr * Cy);
+                if (POST == G2_POST_GATE) gv[u] = g2_ldg4(yb + (long)rr * Cy + C);
+            }
         }
-        *reinterpret_cast<float4*>(out + row * C + c) = o;
+#pragma unroll
+        for (int u = 0; u < NORM_U; ++u) {
+            const int rr = r + u * lanes;
+            if (rr >= r1) break;
+            const float4 h = affine4(a, hv[u], b);
+            float4 o;
+            if (POST == G2_POST_GATE) {
+                const float4 g = affine4(ag, gv[u], bg);
+                o.x = h.x * g2_sigmoidf(g.x); o.y = h.y * g2_sigmoidf(g.y);
+                o.z = h.z * g2_sigmoidf(g.z); o.w = h.w * g2_sigmoidf(g.w);
+            } else if (POST == G2_POST_RELU) {
+                o.x = fmaxf(h.x, 0.f); o.y = fmaxf(h.y, 0.f); o.z = fmaxf(h.z, 0.f); o.w = fmaxf(h.w, 0.f);
+            } else {
+                o = h;
+            }
+            *reinterpret_cast<float4*>(ob + (long)rr * C) = o;
+        }
     }
 }
 
-// gradient w.r.t. the normalised+affine values for 4 channels
+// gradient w.r.t. the normalised+affine values for 4 channels, from the RAW conv outputs hv (features) / gv (gate) and the
+// per-thread affine (a,b) / (ag,bg): dh for the feature half, dg for the gate half
 template <int POST>
-__device__ __forceinline__ void post_grad(const float* __restrict__ yrow, const float* __restrict__ scale,
-                                          const float* __restrict__ shift, long sbase, int C, int c,
-                                          const float4 d, float4& dh, float4& dg) {
-    float4 h = g2_ldg4(yrow + c);
-    float4 a = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (scale) { a = g2_ldg4(scale + sbase + c); b = g2_ldg4(shift + sbase + c); }
-    h.x = fmaf(a.x, h.x, b.x); h.y = fmaf(a.y, h.y, b.y); h.z = fmaf(a.z, h.z, b.z); h.w = fmaf(a.w, h.w, b.w);
+__device__ __forceinline__ void post_grad(const float4 hv, const float4 gv, const float4 a, const float4 b, const float4 ag,
+                                          const float4 bg, const float4 d, float4& dh, float4& dg) {
+    const float4 h = affine4(a, hv, b);
     if (POST == G2_POST_GATE) {
-        float4 g = g2_ldg4(yrow + C + c);
-        float4 ag = make_float4(1.f, 1.f, 1.f, 1.f), bg = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (scale) { ag = g2_ldg4(scale + sbase + C + c); bg = g2_ldg4(shift + sbase + C + c); }
-        const float s0 = g2_sigmoidf(fmaf(ag.x, g.x, bg.x)), s1 = g2_sigmoidf(fmaf(ag.y, g.y, bg.y));
-        const float s2 = g2_sigmoidf(fmaf(ag.z, g.z, bg.z)), s3 = g2_sigmoidf(fmaf(ag.w, g.w, bg.w));
+        const float s0 = g2_sigmoidf(fmaf(ag.x, gv.x, bg.x)), s1 = g2_sigmoidf(fmaf(ag.y, gv.y, bg.y));
+        const float s2 = g2_sigmoidf(fmaf(ag.z, gv.z, bg.z)), s3 = g2_sigmoidf(fmaf(ag.w, gv.w, bg.w));
         dh = make_float4(d.x * s0, d.y * s1, d.z * s2, d.w * s3);
         dg = make_float4(d.x * h.x * s0 * (1.f - s0), d.y * h.y * s1 * (1.f - s1),
                          d.z * h.z * s2 * (1.f - s2), d.w * h.w * s3 * (1.f - s3));
@@ -170,7 +196,7 @@ __device__ __forceinline__ void post_grad(const float* __restrict__ yrow, const 
 // ---------------------------------------------------------------------------------- backward stats
 // sums2 [N, Cy, 2] (double, pre-zeroed): (sum d_n, sum d_n * yhat) per sample and normalised channel.
 template <int POST>
-__global__ void __launch_bounds__(256) norm_bwd_stats_kernel(const float* __restrict__ y, const float* __restrict__ dout,
+__global__ void __launch_bounds__(256, 2) norm_bwd_stats_kernel(const float* __restrict__ y, const float* __restrict__ dout,
                                                              const float* __restrict__ scale, const float* __restrict__ shift,
                                                              const float* __restrict__ mean, const float* __restrict__ rstd,
                                                              double* __restrict__ sums2, int HW, int C, int sn, int rows_per_block) {
@@ -189,35 +215,52 @@ __global__ void __launch_bounds__(256) norm_bwd_stats_kernel(const float* __rest
     if (lane < lanes) {
         const long sbase = (long)n * sn;
         const float4 mh = g2_ldg4(mean + sbase + c), rh = g2_ldg4(rstd + sbase + c);
-        float4 mg = mh, rg = rh;
-        if (POST == G2_POST_GATE) { mg = g2_ldg4(mean + sbase + C + c); rg = g2_ldg4(rstd + sbase + C + c); }
-        for (int r = r0 + lane; r < r1; r += lanes) {
-            const long row = (long)n * HW + r;
-            const float* yrow = y + row * Cy;
-            const float4 d = g2_ldg4(dout + row * C + c);
-            float4 dh, dg;
-            post_grad<POST>(yrow, scale, shift, sbase, C, c, d, dh, dg);
-            const float4 yh = g2_ldg4(yrow + c);
-            acc[0] += dh.x; acc[1] += dh.y; acc[2] += dh.z; acc[3] += dh.w;
-            acc[4] += dh.x * (yh.x - mh.x) * rh.x; acc[5] += dh.y * (yh.y - mh.y) * rh.y;
-            acc[6] += dh.z * (yh.z - mh.z) * rh.z; acc[7] += dh.w * (yh.w - mh.w) * rh.w;
-            if (POST == G2_POST_GATE) {
-                const float4 yg = g2_ldg4(yrow + C + c);
-                acc[8] += dg.x; acc[9] += dg.y; acc[10] += dg.z; acc[11] += dg.w;
-                acc[12] += dg.x * (yg.x - mg.x) * rg.x; acc[13] += dg.y * (yg.y - mg.y) * rg.y;
-                acc[14] += dg.z * (yg.z - mg.z) * rg.z; acc[15] += dg.w * (yg.w - mg.w) * rg.w;
+        const float4 a = g2_ldg4(scale + sbase + c), b = g2_ldg4(shift + sbase + c);
+        float4 mg = mh, rg = rh, ag = a, bg = b;
+        if (POST == G2_POST_GATE) {
+            mg = g2_ldg4(mean + sbase + C + c); rg = g2_ldg4(rstd + sbase + C + c);
+            ag = g2_ldg4(scale + sbase + C + c); bg = g2_ldg4(shift + sbase + C + c);
+        }
+        const float* yb = y + (long)n * HW * Cy + c;
+        const float* db = dout + (long)n * HW * C + c;
+        for (int r = r0 + lane; r < r1; r += lanes * NORM_U) {
+            float4 hv[NORM_U], gv[NORM_U], dv[NORM_U];
+#pragma unroll
+            for (int u = 0; u < NORM_U; ++u) {
+                const int rr = r + u * lanes;
+                if (rr < r1) {
+                    hv[u] = g2_ldg4(yb + (long)rr * Cy);
+                    if (POST == G2_POST_GATE) gv[u] = g2_ldg4(yb + (long)rr * Cy + C);
+                    dv[u] = g2_ldg4(db + (long)rr * C);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < NORM_U; ++u) {
+                if (r + u * lanes >= r1) break;
+                float4 dh, dg;
+                post_grad<POST>(hv[u], POST == G2_POST_GATE ? gv[u] : hv[u], a, b, ag, bg, dv[u], dh, dg);
+                const float4 yh = hv[u];
+                acc[0] += dh.x; acc[1] += dh.y; acc[2] += dh.z; acc[3] += dh.w;
+                acc[4] += dh.x * (yh.x - mh.x) * rh.x; acc[5] += dh.y * (yh.y - mh.y) * rh.y;
+                acc[6] += dh.z * (yh.z - mh.z) * rh.z; acc[7] += dh.w * (yh.w - mh.w) * rh.w;
+                if (POST == G2_POST_GATE) {
+                    const float4 yg = gv[u];
+                    acc[8] += dg.x; acc[9] += dg.y; acc[10] += dg.z; acc[11] += dg.w;
+                    acc[12] += dg.x * (yg.x - mg.x) * rg.x; acc[13] += dg.y * (yg.y - mg.y) * rg.y;
+                    acc[14] += dg.z * (yg.z - mg.z) * rg.z; acc[15] += dg.w * (yg.w - mg.w) * rg.w;
+                }
             }
         }
     }
-    __shared__ double sm[256 * 16];
+    constexpr int NJ = POST == G2_POST_GATE ? 16 : 8;
+    __shared__ float sm[256 * NJ];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) sm[t * 16 + j] = acc[j];
+    for (int j = 0; j < NJ; ++j) sm[t * NJ + j] = acc[j];
     __syncthreads();
-    const int nj = POST == G2_POST_GATE ? 16 : 8;
-    for (int o = t; o < q * nj; o += 256) {
-        const int qq = o / nj, j = o - qq * nj;
+    for (int o = t; o < q * NJ; o += 256) {
+        const int qq = o / NJ, j = o - qq * NJ;
         double a = 0.0;
-        for (int l = 0; l < lanes; ++l) a += sm[(l * q + qq) * 16 + j];
+        for (int l = 0; l < lanes; ++l) a += (double)sm[(l * q + qq) * NJ + j];
         const int cc = qq * 4 + (j & 3) + (j >= 8 ? C : 0);
         atomicAdd(sums2 + ((long)n * Cy + cc) * 2 + ((j >> 2) & 1), a);
     }
@@ -283,52 +326,100 @@ __global__ void norm_bwd_finalize_kernel(const NormBwdFinP p, int main_blocks) {
 }
 
 // ---------------------------------------------------------------------------------- backward apply
-// dy [N,HW,Cy] = rstd * (gamma * d_n - m1 - yhat * m2)   (mode NONE: dy = d_n)
+// dy [N,HW,Cy] = rstd * (gamma * d_n - m1 - yhat * m2)   (mode NONE: dy = d_n).  grid = (chunks, N); per-thread constants in
+// registers; NORM_U rows in flight.  dbias (optional, [Cy]): the gradient of the bias of the convolution that produced y,
+// dbias[c] += sum over rows of dy -- fused here so that no separate column-sum pass re-reads dy (float atomics, one per
+// channel and CTA).
 template <int POST>
-__global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const float* __restrict__ y, const float* __restrict__ dout,
+__global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(const float* __restrict__ y, const float* __restrict__ dout,
                                                              const float* __restrict__ scale, const float* __restrict__ shift,
                                                              const float* __restrict__ mean, const float* __restrict__ rstd,
                                                              const float* __restrict__ m1, const float* __restrict__ m2,
-                                                             float* __restrict__ dy, long total_quads, int HW, int C, int sn) {
+                                                             float* __restrict__ dy, float* __restrict__ dbias, int HW, int C, int sn,
+                                                             int rows_per_block) {
+    constexpr int NH = POST == G2_POST_GATE ? 2 : 1;
     const int q = C >> 2;
-    const int Cy = POST == G2_POST_GATE ? 2 * C : C;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total_quads; i += (long)gridDim.x * blockDim.x) {
-        const int quad = (int)(i % q);
-        const long row = i / q;
-        const int n = (int)(row / HW);
-        const int c = quad * 4;
-        const long sbase = (long)n * sn;
-        const float* yrow = y + row * Cy;
-        const float4 d = g2_ldg4(dout + row * C + c);
-        float4 dh, dg;
-        post_grad<POST>(yrow, scale, shift, sbase, C, c, d, dh, dg);
-        if (scale == nullptr) {      // no normalisation: dy = d_n
-            *reinterpret_cast<float4*>(dy + row * Cy + c) = dh;
-            if (POST == G2_POST_GATE) *reinterpret_cast<float4*>(dy + row * Cy + C + c) = dg;
-            continue;
-        }
+    const int Cy = NH * C;
+    const int lanes = 256 / q;
+    const int t = threadIdx.x;
+    const int lane = t / q, quad = t - lane * q;
+    const int n = blockIdx.y;
+    const int c = quad * 4;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(HW, r0 + rows_per_block);
+    float bsum[4 * NH];
 #pragma unroll
-        for (int half = 0; half < (POST == G2_POST_GATE ? 2 : 1); ++half) {
-            const int cc = c + half * C;
-            const float4 dn = half ? dg : dh;
-            const float4 yv = g2_ldg4(yrow + cc);
-            const float4 mu = g2_ldg4(mean + sbase + cc), rs = g2_ldg4(rstd + sbase + cc);
-            const float4 sc = g2_ldg4(scale + sbase + cc);           // gamma * rstd
-            const float4 a1 = g2_ldg4(m1 + sbase + cc), a2 = g2_ldg4(m2 + sbase + cc);
-            float4 o;
-            o.x = sc.x * dn.x - rs.x * (a1.x + (yv.x - mu.x) * rs.x * a2.x);
-            o.y = sc.y * dn.y - rs.y * (a1.y + (yv.y - mu.y) * rs.y * a2.y);
-            o.z = sc.z * dn.z - rs.z * (a1.z + (yv.z - mu.z) * rs.z * a2.z);
-            o.w = sc.w * dn.w - rs.w * (a1.w + (yv.w - mu.w) * rs.w * a2.w);
-            *reinterpret_cast<float4*>(dy + row * Cy + cc) = o;
+    for (int j = 0; j < 4 * NH; ++j) bsum[j] = 0.f;
+    if (lane < lanes) {
+        const long sbase = (long)n * sn;
+        const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        // dy = gamma rstd d_n - rstd (m1 + (y - mean) rstd m2) = a d_n + k0 + k1 (y - mean)   with  k0 = -rstd m1,  k1 = -rstd^2 m2
+        float4 a[2] = {one, one}, b[2] = {zero, zero}, k0[2] = {zero, zero}, k1[2] = {zero, zero}, mu[2] = {zero, zero};
+        if (scale) {
+#pragma unroll
+            for (int hf = 0; hf < NH; ++hf) {
+                const long o = sbase + c + hf * C;
+                a[hf] = g2_ldg4(scale + o); b[hf] = g2_ldg4(shift + o);
+                mu[hf] = g2_ldg4(mean + o);
+                const float4 rs = g2_ldg4(rstd + o), a1 = g2_ldg4(m1 + o), a2 = g2_ldg4(m2 + o);
+                k1[hf] = make_float4(-rs.x * rs.x * a2.x, -rs.y * rs.y * a2.y, -rs.z * rs.z * a2.z, -rs.w * rs.w * a2.w);
+                k0[hf] = make_float4(-rs.x * a1.x, -rs.y * a1.y, -rs.z * a1.z, -rs.w * a1.w);
+            }
         }
+        const float* yb = y + (long)n * HW * Cy + c;
+        const float* db = dout + (long)n * HW * C + c;
+        float* ob = dy + (long)n * HW * Cy + c;
+        for (int r = r0 + lane; r < r1; r += lanes * NORM_U) {
+            float4 hv[NORM_U], gv[NORM_U], dv[NORM_U];
+#pragma unroll
+            for (int u = 0; u < NORM_U; ++u) {
+                const int rr = r + u * lanes;
+                if (rr < r1) {
+                    hv[u] = g2_ldg4(yb + (long)rr * Cy);
+                    if (POST == G2_POST_GATE) gv[u] = g2_ldg4(yb + (long)rr * Cy + C);
+                    dv[u] = g2_ldg4(db + (long)rr * C);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < NORM_U; ++u) {
+                const int rr = r + u * lanes;
+                if (rr >= r1) break;
+                float4 dn[2];
+                post_grad<POST>(hv[u], POST == G2_POST_GATE ? gv[u] : hv[u], a[0], b[0], a[NH - 1], b[NH - 1], dv[u], dn[0], dn[1]);
+#pragma unroll
+                for (int hf = 0; hf < NH; ++hf) {
+                    float4 o = dn[hf];
+                    if (scale) {
+                        const float4 yv = hf ? gv[u] : hv[u];
+                        o.x = fmaf(a[hf].x, dn[hf].x, fmaf(k1[hf].x, yv.x - mu[hf].x, k0[hf].x));
+                        o.y = fmaf(a[hf].y, dn[hf].y, fmaf(k1[hf].y, yv.y - mu[hf].y, k0[hf].y));
+                        o.z = fmaf(a[hf].z, dn[hf].z, fmaf(k1[hf].z, yv.z - mu[hf].z, k0[hf].z));
+                        o.w = fmaf(a[hf].w, dn[hf].w, fmaf(k1[hf].w, yv.w - mu[hf].w, k0[hf].w));
+                    }
+                    *reinterpret_cast<float4*>(ob + (long)rr * Cy + hf * C) = o;
+                    bsum[4 * hf] += o.x; bsum[4 * hf + 1] += o.y; bsum[4 * hf + 2] += o.z; bsum[4 * hf + 3] += o.w;
+                }
+            }
+        }
+    }
+    if (dbias == nullptr) return;          // uniform over the grid
+    __shared__ float sm[256 * 4 * NH];
+#pragma unroll
+    for (int j = 0; j < 4 * NH; ++j) sm[t * 4 * NH + j] = bsum[j];
+    __syncthreads();
+    for (int o = t; o < q * 4 * NH; o += 256) {
+        const int qq = o / (4 * NH), j = o - qq * (4 * NH);
+        float acc = 0.f;
+        for (int l = 0; l < lanes; ++l) acc += sm[(l * q + qq) * 4 * NH + j];
+        atomicAdd(dbias + qq * 4 + (j & 3) + (j >= 4 ? C : 0), acc);
     }
 }
 
-inline int ew_blocks(long work) {
-    long b = (work + 255) / 256;
-    const long cap = 148L * 16;
-    return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+// rows per block for the (chunks, N) streaming kernels: a few waves of 148 SMs, at least one unrolled pass per thread
+inline int norm_rows_per_block(int N, int HW, int C) {
+    const int lanes = 256 / (C / 4);
+    int rpb = lanes * NORM_U * 2;
+    while ((long)g2_cdiv(HW, rpb) * N > 148L * 24 && rpb < HW) rpb *= 2;
+    return rpb;
 }
 
 }  // namespace
@@ -340,9 +431,9 @@ int g2_norm_stats_f32(const float* y, double* sums, int N, int HW, int Cy, cudaS
     G2_CHECK_ARG(y && sums && N > 0 && HW > 0 && C >= 4 && (C % 4) == 0 && C <= 1024);
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)N * C, stream);
     if (e != cudaSuccess) return (int)e;
+    // keep the grid near a few waves of 148 SMs (measured: 4x smaller blocks are 15-20 % slower -- reduction + atomics tail)
     const int lanes = 256 / (C / 4);
     int rpb = lanes * 32;
-    // keep the grid near a few waves of 148 SMs (measured: 4x smaller blocks are 15-20 % slower -- reduction + atomics tail)
     while ((long)g2_cdiv(HW, rpb) * N > 148L * 32 && rpb < HW) rpb *= 2;
     dim3 grid(g2_cdiv(HW, rpb), N);
     norm_stats_kernel<<<grid, 256, 0, stream>>>(y, sums, HW, C, rpb);
@@ -367,11 +458,12 @@ int g2_norm_finalize_f32(const double* sums, const float* g0, const float* b0, c
 
 int g2_norm_apply_f32(const float* y, const float* scale, const float* shift, float* out, int N, int HW, int C,
                       int sn, int post, cudaStream_t stream) {
-    G2_CHECK_ARG(y && out && N > 0 && HW > 0 && C >= 4 && (C % 4) == 0 && (scale == nullptr) == (shift == nullptr));
-    const long quads = (long)N * HW * (C / 4);
-    if (post == G2_POST_GATE) norm_apply_kernel<G2_POST_GATE><<<ew_blocks(quads), 256, 0, stream>>>(y, scale, shift, out, quads, HW, C, sn);
-    else if (post == G2_POST_RELU) norm_apply_kernel<G2_POST_RELU><<<ew_blocks(quads), 256, 0, stream>>>(y, scale, shift, out, quads, HW, C, sn);
-    else if (post == G2_POST_NONE) norm_apply_kernel<G2_POST_NONE><<<ew_blocks(quads), 256, 0, stream>>>(y, scale, shift, out, quads, HW, C, sn);
+    G2_CHECK_ARG(y && out && N > 0 && HW > 0 && C >= 4 && (C % 4) == 0 && C <= 1024 && (scale == nullptr) == (shift == nullptr));
+    const int rpb = norm_rows_per_block(N, HW, C);
+    dim3 grid(g2_cdiv(HW, rpb), N);
+    if (post == G2_POST_GATE) norm_apply_kernel<G2_POST_GATE><<<grid, 256, 0, stream>>>(y, scale, shift, out, HW, C, sn, rpb);
+    else if (post == G2_POST_RELU) norm_apply_kernel<G2_POST_RELU><<<grid, 256, 0, stream>>>(y, scale, shift, out, HW, C, sn, rpb);
+    else if (post == G2_POST_NONE) norm_apply_kernel<G2_POST_NONE><<<grid, 256, 0, stream>>>(y, scale, shift, out, HW, C, sn, rpb);
     else return G2_ERR_ARG;
     G2_LAUNCH_RET();
 }
@@ -419,17 +511,34 @@ int g2_norm_bwd_finalize_acc_f32(const double* sums2, const float* g0, const flo
     return norm_bwd_finalize_impl(sums2, g0, g1, m1, m2, dg0, db0, dg1, db1, N, HW, Cy, half, mode, groups, accumulate, stream);
 }
 
+static int norm_bwd_apply_impl(const float* y, const float* dout, const float* scale, const float* shift, const float* mean,
+                               const float* rstd, const float* m1, const float* m2, float* dy, float* dbias, int N, int HW, int C,
+                               int sn, int post, cudaStream_t stream) {
+    G2_CHECK_ARG(y && dout && dy && N > 0 && HW > 0 && C >= 4 && (C % 4) == 0 && C <= 1024);
+    if (scale) G2_CHECK_ARG(shift && mean && rstd && m1 && m2);
+    const int rpb = norm_rows_per_block(N, HW, C);
+    dim3 grid(g2_cdiv(HW, rpb), N);
+    if (post == G2_POST_GATE) norm_bwd_apply_kernel<G2_POST_GATE><<<grid, 256, 0, stream>>>(y, dout, scale, shift, mean, rstd, m1, m2, dy, dbias, HW, C, sn, rpb);
+    else if (post == G2_POST_RELU) norm_bwd_apply_kernel<G2_POST_RELU><<<grid, 256, 0, stream>>>(y, dout, scale, shift, mean, rstd, m1, m2, dy, dbias, HW, C, sn, rpb);
+    else if (post == G2_POST_NONE) norm_bwd_apply_kernel<G2_POST_NONE><<<grid, 256, 0, stream>>>(y, dout, scale, shift, mean, rstd, m1, m2, dy, dbias, HW, C, sn, rpb);
+    else return G2_ERR_ARG;
+    G2_LAUNCH_RET();
+}
+
 int g2_norm_bwd_apply_f32(const float* y, const float* dout, const float* scale, const float* shift, const float* mean,
                           const float* rstd, const float* m1, const float* m2, float* dy, int N, int HW, int C, int sn,
                           int post, cudaStream_t stream) {
-    G2_CHECK_ARG(y && dout && dy && N > 0 && HW > 0 && C >= 4 && (C % 4) == 0);
-    if (scale) G2_CHECK_ARG(shift && mean && rstd && m1 && m2);
-    const long quads = (long)N * HW * (C / 4);
-    if (post == G2_POST_GATE) norm_bwd_apply_kernel<G2_POST_GATE><<<ew_blocks(quads), 256, 0, stream>>>(y, dout, scale, shift, mean, rstd, m1, m2, dy, quads, HW, C, sn);
-    else if (post == G2_POST_RELU) norm_bwd_apply_kernel<G2_POST_RELU><<<ew_blocks(quads), 256, 0, stream>>>(y, dout, scale, shift, mean, rstd, m1, m2, dy, quads, HW, C, sn);
-    else if (post == G2_POST_NONE) norm_bwd_apply_kernel<G2_POST_NONE><<<ew_blocks(quads), 256, 0, stream>>>(y, dout, scale, shift, mean, rstd, m1, m2, dy, quads, HW, C, sn);
-    else return G2_ERR_ARG;
-    G2_LAUNCH_RET();
+    return norm_bwd_apply_impl(y, dout, scale, shift, mean, rstd, m1, m2, dy, nullptr, N, HW, C, sn, post, stream);
+}
+
+// As above, and dbias[c] += sum over all rows of dy[.., c] for the Cy channels of y: the bias gradient of the convolution that
+// produced y (third_party/sylvester/layers.py:19-20,65-67: gated convs carry a bias in front of their norm), accumulated into
+// a caller-initialised buffer (param.grad in direct-gradient mode, a zeroed tensor otherwise).
+int g2_norm_bwd_apply_bias_f32(const float* y, const float* dout, const float* scale, const float* shift, const float* mean,
+                               const float* rstd, const float* m1, const float* m2, float* dy, float* dbias, int N, int HW, int C,
+                               int sn, int post, cudaStream_t stream) {
+    G2_CHECK_ARG(dbias != nullptr);
+    return norm_bwd_apply_impl(y, dout, scale, shift, mean, rstd, m1, m2, dy, dbias, N, HW, C, sn, post, stream);
 }
 
 }  // extern "C"

@@ -126,6 +126,48 @@ __global__ void act_bwd_kernel(const float* __restrict__ dout, const float* __re
     }
 }
 
+// dpre = dout * act'(out) and, in the same pass, dbias[c] += sum over rows of dpre[row][c]  (rows x C, C % 4 == 0): the
+// activation backward of a conv + bias + activation layer fused with its bias gradient (no separate column-sum pass over
+// dpre).  A thread owns one channel quad and strides over rows, 4 rows in flight; block partials -> float atomics.
+__global__ void __launch_bounds__(256) act_bwd_bias_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                                           float* __restrict__ dpre, float* __restrict__ dbias, long M, int C,
+                                                           long rows_per_block, int act) {
+    const int q = C >> 2, lanes = 256 / q;
+    const int t = threadIdx.x, lane = t / q, quad = t - lane * q;
+    const long r0 = (long)blockIdx.x * rows_per_block;
+    const long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < lanes) {
+        for (long r = r0 + lane; r < r1; r += 4L * lanes) {
+            float4 d[4], o[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long rr = r + (long)u * lanes;
+                if (rr < r1) { d[u] = g2_ldg4(dout + rr * C + quad * 4); o[u] = g2_ldg4(out + rr * C + quad * 4); }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long rr = r + (long)u * lanes;
+                if (rr >= r1) break;
+                float4 v;
+                v.x = g2_apply_act(d[u].x, act, o[u].x); v.y = g2_apply_act(d[u].y, act, o[u].y);
+                v.z = g2_apply_act(d[u].z, act, o[u].z); v.w = g2_apply_act(d[u].w, act, o[u].w);
+                *reinterpret_cast<float4*>(dpre + rr * C + quad * 4) = v;
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+        }
+    }
+    __shared__ float4 sm[256];
+    sm[t] = s;
+    __syncthreads();
+    if (t < q) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = 0; l < lanes; ++l) { const float4 v = sm[l * q + t]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+        float* o = dbias + t * 4;
+        atomicAdd(o, a.x); atomicAdd(o + 1, a.y); atomicAdd(o + 2, a.z); atomicAdd(o + 3, a.w);
+    }
+}
+
 // out[n, c] = sum_p x[n, p, c]      grid (chunks, N), atomicAdd into pre-zeroed out
 __global__ void __launch_bounds__(256) seg_colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int P, int C,
                                                          int rows_per_block) {
@@ -210,6 +252,19 @@ int g2_act_bwd_f32(const float* dout, const float* out, float* dpre, long total,
     G2_CHECK_ARG(act == G2_ACT_RELU || act == G2_ACT_ELU);
     const int code = act == G2_ACT_RELU ? G2_ACT_MUL_RELU_GRAD : G2_ACT_MUL_ELU_GRAD;
     act_bwd_kernel<<<ew_blocks(total / 4), 256, 0, stream>>>(dout, out, dpre, total / 4, code);
+    G2_LAUNCH_RET();
+}
+
+// dpre = dout * act'(out);  dbias[c] += column sums of dpre (accumulated into a caller-initialised buffer)
+int g2_act_bwd_bias_f32(const float* dout, const float* out, float* dpre, float* dbias, long M, int C, int act,
+                        cudaStream_t stream) {
+    G2_CHECK_ARG(dout && out && dpre && dbias && M > 0 && C >= 4 && (C % 4) == 0 && C <= 1024);
+    G2_CHECK_ARG(act == G2_ACT_RELU || act == G2_ACT_ELU);
+    const int code = act == G2_ACT_RELU ? G2_ACT_MUL_RELU_GRAD : G2_ACT_MUL_ELU_GRAD;
+    const int lanes = 256 / (C / 4);
+    long rpb = (long)lanes * 8;
+    while (g2_cdiv(M, rpb) > 148L * 24) rpb *= 2;
+    act_bwd_bias_kernel<<<g2_cdiv(M, rpb), 256, 0, stream>>>(dout, out, dpre, dbias, M, C, rpb, code);
     G2_LAUNCH_RET();
 }
 

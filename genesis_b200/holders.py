@@ -229,27 +229,28 @@ def pad_cin(w, cin):
 def gated_forward(layer, x, training):
     """GatedConv2d / GatedConvTranspose2d forward on NHWC x (reference layers.py:42-54, 88-101)."""
     conv = layer.conv
+    # the conv's bias gradient (column sums of the gradient w.r.t. y) is accumulated by the gate / norm backward pass
     if layer.transposed:
-        y = ops.conv_transpose2d(x, conv.weight, conv.bias, layer.stride, layer.pad)
+        y = ops.conv_transpose2d(x, conv.weight, conv.bias, layer.stride, layer.pad, bias_grad=False)
     else:
-        y = ops.conv2d(x, conv.weight, conv.bias, layer.stride, layer.pad)
-    return gate_norm(layer, y, training)
+        y = ops.conv2d(x, conv.weight, conv.bias, layer.stride, layer.pad, bias_grad=False)
+    return gate_norm(layer, y, training, conv_bias=conv.bias)
 
 
-def gate_norm(layer, y, training):
+def gate_norm(layer, y, training, conv_bias=None):
     hn, gn = layer.h_norm, layer.g_norm
     if hn is None:
-        return ops.norm_post(y, mode=ops.NORM_NONE, post=ops.POST_GATE)
+        return ops.norm_post(y, mode=ops.NORM_NONE, post=ops.POST_GATE, conv_bias=conv_bias)
     if layer.norm == 'bn':
         out = ops.norm_post(y, hn.weight, hn.bias, gn.weight, gn.bias, hn.running_mean, hn.running_var,
                             gn.running_mean, gn.running_var, mode=ops.NORM_BATCH, post=ops.POST_GATE,
-                            training=training, eps=hn.eps, momentum=hn.momentum)
+                            training=training, eps=hn.eps, momentum=hn.momentum, conv_bias=conv_bias)
         if training:
             hn.num_batches_tracked += 1
             gn.num_batches_tracked += 1
         return out
     return ops.norm_post(y, hn.weight, hn.bias, gn.weight, gn.bias, mode=ops.NORM_INSTANCE,
-                         post=ops.POST_GATE, eps=hn.eps)
+                         post=ops.POST_GATE, eps=hn.eps, conv_bias=conv_bias)
 
 
 def sylvester_encode(core, x_nhwc, training):

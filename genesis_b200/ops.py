@@ -231,7 +231,7 @@ def _bias_grad(dpre, b, C):
     return _colsum(dpre, C, dpre)
 
 
-def _conv_fwd_common(ctx, x, w, b, stride, pad, act, transposed):
+def _conv_fwd_common(ctx, x, w, b, stride, pad, act, transposed, bias_grad=True):
     """Shared forward of Conv2d (mode 0) / ConvTranspose2d (mode 1, output_padding = stride-1).  The weight may have fewer
     input channels than x (x zero-padded to a 32-channel k-block): the missing channels are zero in the packs."""
     x = _c(x)
@@ -263,7 +263,7 @@ def _conv_fwd_common(ctx, x, w, b, stride, pad, act, transposed):
               mode_f, 0, act)
     ctx.save_for_backward(x, wd, out if act != ACT_NONE else None, pb)
     ctx.params = (w, b)
-    ctx.cfg = (stride, pad, act, b is not None, transposed)
+    ctx.cfg = (stride, pad, act, b is not None and bias_grad, transposed)
     return out
 
 
@@ -279,8 +279,18 @@ def _conv_bwd_common(ctx, dout):
     dout = _c(dout)
     _, Ho, Wo, _ = dout.shape
     mode_d = 0 if transposed else 1
-    dpre = _act_bwd(dout, out, act)
     dx = dw = db = None
+    if act != ACT_NONE and has_b and ctx.needs_input_grad[2] and Co % 4 == 0 and Co <= 1024:
+        # conv + bias + activation: activation backward and bias gradient in ONE pass over dout (no column-sum re-read of dpre)
+        dpre = torch.empty_like(dout)
+        if _direct(b_param):
+            _call('g2_act_bwd_bias_f32', dout, out, dpre, b_param.grad, dout.numel() // Co, Co, act)
+        else:
+            db = torch.zeros(Co, device=dout.device, dtype=torch.float32)
+            _call('g2_act_bwd_bias_f32', dout, out, dpre, db, dout.numel() // Co, Co, act)
+        has_b = False
+    else:
+        dpre = _act_bwd(dout, out, act)
     if ctx.needs_input_grad[0]:
         dx = torch.empty_like(x)
         if pb is not None:
@@ -322,39 +332,40 @@ def _conv_bwd_common(ctx, dout):
                 dw = dwp.permute(3, 2, 0, 1)[:, :Ci].contiguous()
     if has_b and ctx.needs_input_grad[2]:
         db = _bias_grad(dpre, b_param, Co)
-    return dx, dw, db, None, None, None
+    return dx, dw, db, None, None, None, None
 
 
 class _Conv(Function):
     """nn.Conv2d on NHWC activations; w in torch layout [Co,Ci,R,S] (Ci may be smaller than x's zero-padded channels)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, stride, pad, act):
-        return _conv_fwd_common(ctx, x, w, b, stride, pad, act, False)
+    def forward(ctx, x, w, b, stride, pad, act, bias_grad=True):
+        return _conv_fwd_common(ctx, x, w, b, stride, pad, act, False, bias_grad)
 
     @staticmethod
     def backward(ctx, dout):
         return _conv_bwd_common(ctx, dout)
 
 
-def conv2d(x, w, b=None, stride=1, pad=0, act=None):
-    return _Conv.apply(x, w, b, stride, pad, ACTS[act])
+def conv2d(x, w, b=None, stride=1, pad=0, act=None, bias_grad=True):
+    """bias_grad=False: the bias gradient is produced elsewhere (norm_post(conv_bias=b) fuses it into the norm backward)."""
+    return _Conv.apply(x, w, b, stride, pad, ACTS[act], bias_grad)
 
 
 class _ConvT(Function):
     """nn.ConvTranspose2d (output_padding = stride-1) on NHWC activations; w torch layout [Ci,Co,R,S]."""
 
     @staticmethod
-    def forward(ctx, x, w, b, stride, pad, act):
-        return _conv_fwd_common(ctx, x, w, b, stride, pad, act, True)
+    def forward(ctx, x, w, b, stride, pad, act, bias_grad=True):
+        return _conv_fwd_common(ctx, x, w, b, stride, pad, act, True, bias_grad)
 
     @staticmethod
     def backward(ctx, dout):
         return _conv_bwd_common(ctx, dout)
 
 
-def conv_transpose2d(x, w, b=None, stride=1, pad=0, act=None):
-    return _ConvT.apply(x, w, b, stride, pad, ACTS[act])
+def conv_transpose2d(x, w, b=None, stride=1, pad=0, act=None, bias_grad=True):
+    return _ConvT.apply(x, w, b, stride, pad, ACTS[act], bias_grad)
 
 
 # ----------------------------------------------------------------------------------------- linear
@@ -453,8 +464,9 @@ class _NormPost(Function):
     params: (g0,b0) affine of the first half / whole, (g1,b1) affine of the second (gate) half."""
 
     @staticmethod
-    def forward(ctx, y, g0, b0, g1, b1, rm0, rv0, rm1, rv1, mode, post, groups, training, eps, momentum):
+    def forward(ctx, y, g0, b0, g1, b1, rm0, rv0, rm1, rv1, mode, post, groups, training, eps, momentum, conv_bias=None):
         y = _c(y)
+        ctx.conv_bias = conv_bias
         N, H, W, Cy = y.shape
         HW = H * W
         C = Cy // 2 if post == POST_GATE else Cy
@@ -484,13 +496,27 @@ class _NormPost(Function):
     def backward(ctx, dout):
         mode, post, groups, half = ctx.cfg
         dout = _c(dout)
+        cb = ctx.conv_bias
+        want_cb = cb is not None and ctx.needs_input_grad[15]
+        dcb = None
+
+        def conv_bias_buffer(Cy):
+            # the bias gradient of the producing convolution = column sums of dy, accumulated by the backward-apply kernel
+            if _direct(cb):
+                return cb.grad, None
+            buf = torch.zeros(Cy, device=dout.device, dtype=torch.float32)
+            return buf, buf
         if mode == NORM_NONE:
             (y,) = ctx.saved_tensors
             N, H, W, Cy = y.shape
             C = dout.shape[3]
             dy = torch.empty_like(y)
-            _call('g2_norm_bwd_apply_f32', y, dout, None, None, None, None, None, None, dy, N, H * W, C, 0, post)
-            return (dy,) + (None,) * 14
+            if want_cb:
+                buf, dcb = conv_bias_buffer(Cy)
+                _call('g2_norm_bwd_apply_bias_f32', y, dout, None, None, None, None, None, None, dy, buf, N, H * W, C, 0, post)
+            else:
+                _call('g2_norm_bwd_apply_f32', y, dout, None, None, None, None, None, None, dy, N, H * W, C, 0, post)
+            return (dy,) + (None,) * 14 + (dcb,)
         y, scale, shift, mean, rstd, g0, g1 = ctx.saved_tensors
         N, H, W, Cy = y.shape
         HW = H * W
@@ -515,13 +541,19 @@ class _NormPost(Function):
             db1 = _new(y, Cy - half) if g1 is not None else None
             _call('g2_norm_bwd_finalize_f32', sums2, g0, g1, m1, m2, dg0, db0, dg1, db1, N, HW, Cy, half, mode, groups)
         dy = torch.empty_like(y)
-        _call('g2_norm_bwd_apply_f32', y, dout, scale, shift, mean, rstd, m1, m2, dy, N, HW, C, sn, post)
-        return (dy, dg0, db0, dg1, db1) + (None,) * 10
+        if want_cb:
+            buf, dcb = conv_bias_buffer(Cy)
+            _call('g2_norm_bwd_apply_bias_f32', y, dout, scale, shift, mean, rstd, m1, m2, dy, buf, N, HW, C, sn, post)
+        else:
+            _call('g2_norm_bwd_apply_f32', y, dout, scale, shift, mean, rstd, m1, m2, dy, N, HW, C, sn, post)
+        return (dy, dg0, db0, dg1, db1) + (None,) * 10 + (dcb,)
 
 
 def norm_post(y, g0=None, b0=None, g1=None, b1=None, rm0=None, rv0=None, rm1=None, rv1=None,
-              mode=NORM_NONE, post=POST_GATE, groups=1, training=True, eps=1e-5, momentum=0.1):
-    return _NormPost.apply(y, g0, b0, g1, b1, rm0, rv0, rm1, rv1, mode, post, groups, training, eps, momentum)
+              mode=NORM_NONE, post=POST_GATE, groups=1, training=True, eps=1e-5, momentum=0.1, conv_bias=None):
+    """conv_bias: the bias parameter of the convolution that produced y (called with bias_grad=False); its gradient -- the column
+    sums of dy -- is then accumulated by the norm backward pass itself instead of a separate pass over dy."""
+    return _NormPost.apply(y, g0, b0, g1, b1, rm0, rv0, rm1, rv1, mode, post, groups, training, eps, momentum, conv_bias)
 
 
 # ----------------------------------------------------------------------------------------- SBP scan

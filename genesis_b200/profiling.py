@@ -36,8 +36,8 @@ def algo_cost(name, a):
     elif name == 'g2_norm_bwd_stats_f32':
         N, HW, C, sn, post = a[7:12]
         b = 4.0 * N * HW * C * (3 if post == 0 else 2)
-    elif name == 'g2_norm_bwd_apply_f32':
-        N, HW, C, sn, post = a[9:14]
+    elif name in ('g2_norm_bwd_apply_f32', 'g2_norm_bwd_apply_bias_f32'):
+        N, HW, C, sn, post = a[10:15] if name.endswith('bias_f32') else a[9:14]
         b = 4.0 * N * HW * C * (5 if post == 0 else 3)
     elif name == 'g2_mixture_fwd_f32':
         K, B, P = a[8:11]
@@ -47,6 +47,57 @@ def algo_cost(name, a):
         b = 4.0 * B * P * ((6 + 4 * K) + 4 * K)
     elif name == 'g2_act_bwd_f32':
         b = 12.0 * a[3]
+    elif name == 'g2_act_bwd_bias_f32':
+        b = 12.0 * a[4] * a[5]
+    elif name == 'g2_colsum_f32':
+        b = 4.0 * a[2] * a[3]
+    elif name == 'g2_head_wgrad_f32':
+        b = 4.0 * a[3] * (a[4] + 4)
+        f = 2.0 * a[3] * a[4] * 4
+    elif name == 'g2_sbp_scan_fwd_f32':
+        BP, K, nl = a[3:6]
+        b = 4.0 * BP * (nl + K + nl + 1)
+    elif name == 'g2_sbp_scan_bwd_f32':
+        BP, K, nl = a[3:6]
+        b = 4.0 * BP * (nl + K + nl)
+    elif name == 'g2_comp_pack_f32':
+        K, B, P, cp = a[3:7]
+        b = 4.0 * B * P * (3 + K + K * cp)
+    elif name == 'g2_nhwc_pad_f32':
+        N, C, P, cp = a[2:6]
+        b = 4.0 * N * P * (C + cp)
+    elif name == 'g2_layout_f32':
+        N, C, P = a[2:5]
+        b = 8.0 * N * C * P
+    elif name == 'g2_resample_f32':
+        N, Ho, Wo, C, mode = a[2:7]
+        # (Ho, Wo) is the OUTPUT map: 0 = nearest x0.5 (read 1 of 4 inputs), 1 = nearest x2, 2 = adjoint of x0.5, 3 = adjoint of x2
+        b = 4.0 * N * Ho * Wo * C * {0: 2.0, 1: 1.25, 2: 1.25, 3: 5.0}[mode]
+    elif name in ('g2_icsbp_fwd_f32', 'g2_icsbp_kernel_fwd_f32', 'g2_icsbp_dynamic_fwd_f32'):
+        o = 7 if name == 'g2_icsbp_dynamic_fwd_f32' else 6
+        B, P, K, CD = a[o:o + 4]
+        b = 4.0 * B * P * (CD + 1 + 2 * K)
+    elif name in ('g2_icsbp_bwd_f32', 'g2_icsbp_kernel_bwd_f32', 'g2_icsbp_dynamic_bwd_f32'):
+        o = 7 if name == 'g2_icsbp_dynamic_bwd_f32' else 6
+        B, P, K, CD = a[o:o + 4]
+        b = 4.0 * B * P * (2 * CD + K)
+    elif name == 'g2_masked_pool_fwd_f32':
+        B, P, C, K = a[4:8]
+        b = 4.0 * B * P * (C + K)
+    elif name == 'g2_masked_pool_bwd_f32':
+        B, P, C, K = a[6:10]
+        b = 4.0 * B * P * (2 * C + 2 * K)
+    elif name in ('g2_mask_kl_fwd_f32',):
+        K, B, P = a[4:7]
+        b = 4.0 * B * P * 3 * K
+    elif name in ('g2_mask_kl_bwd_f32',):
+        K, B, P = a[5:8]
+        b = 4.0 * B * P * 4 * K
+    elif name == 'g2_pack_conv_weight_f32':
+        Co, Ci, Cp, RS = a[3:7]
+        b = 4.0 * RS * Co * (Ci + 2 * Cp)
+    elif name in ('g2_rmsprop_f32', 'g2_sgd_f32'):
+        b = 20.0 * a[3]
     elif name == 'g2_bcast_add_act_f32':
         N, P, C = a[3:6]
         b = 4.0 * N * P * C

@@ -99,6 +99,11 @@ int g2_norm_bwd_finalize_acc_f32(const double* sums2, const float* g0, const flo
 int g2_norm_bwd_apply_f32(const float* y, const float* dout, const float* scale, const float* shift,
                           const float* mean, const float* rstd, const float* m1, const float* m2, float* dy,
                           int N, int HW, int C, int sn, int post, g2_stream_t stream);
+/* Same, and dbias[c] += column sums of dy over all N*HW rows (Cy channels): the bias gradient of the convolution that produced
+ * y, fused so that no separate pass re-reads dy.  dbias is accumulated into (caller-initialised). */
+int g2_norm_bwd_apply_bias_f32(const float* y, const float* dout, const float* scale, const float* shift,
+                               const float* mean, const float* rstd, const float* m1, const float* m2, float* dy,
+                               float* dbias, int N, int HW, int C, int sn, int post, g2_stream_t stream);
 
 /* ---- layout, scans, packing, reductions (pointwise.cu) --------------------------------------------- */
 /* x [N,C,P] <-> y [N,P,C] */
@@ -116,6 +121,10 @@ int g2_nhwc_pad_f32(const float* x, float* y, long N, int C, int P, int Cp, g2_s
 int g2_bcast_add_act_f32(const float* a, const float* m, float* out, long N, int P, int C, int act,
                          g2_stream_t stream);
 int g2_act_bwd_f32(const float* dout, const float* out, float* dpre, long total, int act, g2_stream_t stream);
+/* The same fused with the bias gradient of a conv + bias + activation layer: dbias[c] += column sums of dpre viewed as
+ * [M rows, C] (accumulated into a caller-initialised buffer). */
+int g2_act_bwd_bias_f32(const float* dout, const float* out, float* dpre, float* dbias, long M, int C, int act,
+                        g2_stream_t stream);
 int g2_seg_colsum_f32(const float* x, float* out, int N, int P, int C, g2_stream_t stream);
 int g2_sum_dim0_f32(const float* x, float* out, int N, long J, g2_stream_t stream);
 

@@ -31,13 +31,13 @@ def to_nhwc_padded(x, cp):
     return F.pad(y, (0, cp - y.shape[3])).contiguous()
 
 
-def conv2d(x, w, b=None, stride=1, pad=0, act=None):
+def conv2d(x, w, b=None, stride=1, pad=0, act=None, bias_grad=True):      # bias_grad: where the kernel layer computes db (autograd here)
     ci = w.shape[1]
     y = F.conv2d(x[..., :ci].permute(0, 3, 1, 2), w, b, stride=stride, padding=pad)
     return _act(y, act).permute(0, 2, 3, 1).contiguous()
 
 
-def conv_transpose2d(x, w, b=None, stride=1, pad=0, act=None):
+def conv_transpose2d(x, w, b=None, stride=1, pad=0, act=None, bias_grad=True):
     ci = w.shape[0]
     y = F.conv_transpose2d(x[..., :ci].permute(0, 3, 1, 2), w, b, stride=stride, padding=pad, output_padding=stride - 1)
     return _act(y, act).permute(0, 2, 3, 1).contiguous()
@@ -58,7 +58,7 @@ def _norm(t, mode, w, b, rm, rv, groups, training, eps, momentum):
 
 
 def norm_post(y, g0=None, b0=None, g1=None, b1=None, rm0=None, rv0=None, rm1=None, rv1=None,
-              mode=NORM_NONE, post=POST_GATE, groups=1, training=True, eps=1e-5, momentum=0.1):
+              mode=NORM_NONE, post=POST_GATE, groups=1, training=True, eps=1e-5, momentum=0.1, conv_bias=None):
     t = y.permute(0, 3, 1, 2)
     if post == POST_GATE:
         h, g = torch.chunk(t, 2, dim=1)

@@ -110,3 +110,50 @@ def test_mask_kl_function_plain_and_packed(ops):
                 assert a is None or a.abs().max() == 0
             else:
                 torch.testing.assert_close(a, c, rtol=2e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize('direct', [False, True])
+def test_gated_conv_bias_gradient_fused_into_the_norm_backward(ops, direct):
+    """conv2d(bias_grad=False) + norm_post(conv_bias=b): the conv's bias gradient (column sums of dy) comes out of the norm
+    backward-apply kernel -- returned to autograd, or accumulated into b.grad in direct-gradient mode."""
+    torch.manual_seed(5)
+    N, Hh, C = 2, 6, 8
+    x = torch.randn(N, Hh, Hh, 4, requires_grad=True)
+    w = (0.3 * torch.randn(2 * C, 4, 3, 3)).requires_grad_(True)
+    b = torch.randn(2 * C, requires_grad=True)
+    g0, b0 = (torch.rand(C) + 0.5).requires_grad_(True), torch.randn(C, requires_grad=True)
+    g1, b1 = (torch.rand(C) + 0.5).requires_grad_(True), torch.randn(C, requires_grad=True)
+    wgt = torch.randn(N, Hh, Hh, C)
+
+    def fwd(mod, fused):
+        y = mod.conv2d(x, w, b, 1, 1, bias_grad=not fused)
+        return mod.norm_post(y, g0, b0, g1, b1, mode=2, post=0, conv_bias=b if fused else None)
+    ref = torch.autograd.grad((fwd(R, False) * wgt).sum(), [x, w, b])
+    if direct:
+        b.grad = torch.full_like(b, 0.5)
+        ops.set_direct_grad(True)
+        try:
+            out = fwd(ops, True)
+            got = torch.autograd.grad((out * wgt).sum(), [x, w, b], allow_unused=True)
+        finally:
+            ops.set_direct_grad(False)
+        assert got[2] is None
+        torch.testing.assert_close(b.grad - 0.5, ref[2], rtol=2e-3, atol=2e-4)
+    else:
+        got = torch.autograd.grad((fwd(ops, True) * wgt).sum(), [x, w, b])
+        torch.testing.assert_close(got[2], ref[2], rtol=2e-3, atol=2e-4)
+    torch.testing.assert_close(got[0], ref[0], rtol=2e-3, atol=2e-4)
+    torch.testing.assert_close(got[1], ref[1], rtol=2e-3, atol=2e-4)
+
+
+def test_conv_activation_bias_gradient_fused(ops):
+    """conv + bias + ELU: activation backward and bias gradient in one kernel (g2_act_bwd_bias_f32)."""
+    torch.manual_seed(6)
+    x = torch.randn(3, 7, 7, 4, requires_grad=True)
+    w = (0.3 * torch.randn(8, 4, 3, 3)).requires_grad_(True)
+    b = torch.randn(8, requires_grad=True)
+    wgt = torch.randn(3, 5, 5, 8)
+    ref = torch.autograd.grad((R.conv2d(x, w, b, 1, 0, 'elu') * wgt).sum(), [x, w, b])
+    got = torch.autograd.grad((ops.conv2d(x, w, b, 1, 0, 'elu') * wgt).sum(), [x, w, b])
+    for a, c in zip(got, ref):
+        torch.testing.assert_close(a, c, rtol=2e-3, atol=2e-4)
