@@ -313,6 +313,7 @@ struct PP {
     int items_x, items_y;               // work items: blockIdx.x / blockIdx.y space of the non-persistent launch
     int acc_cols;                       // TMEM columns of one accumulator set (m_tiles * BN)
     int b_resident;                     // 1: every (cb, tap) weight tile has its own stage and is loaded once per CTA
+    int kouter;                         // experiment: MMA order k-step outer / tile inner
 };
 
 template <int BN>
@@ -449,6 +450,16 @@ __global__ void __launch_bounds__(192, 1) conv_halo_persistent_kernel(const __gr
                     const uint32_t alo = a0 + (uint32_t)toff * 8u;
                     const uint32_t first = (cb | tap) != 0 ? 1u : 0u;
                     if (elect_one()) {
+                        if (pp.kouter) {
+                            // k-step outer, tile inner: consecutive MMAs write DIFFERENT accumulators (no back-to-back
+                            // read-modify-write of one TMEM tile)
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                for (int t = 0; t < m_tiles; ++t) {
+                                    const uint64_t adesc = hi | (uint64_t)((alo + (uint32_t)t * 1024u) & 0x3FFFu);
+                                    mma_tf32(tacc + (uint32_t)(t * BN), adesc + 2 * ks, bdesc + 2 * ks, idesc, ks ? 1u : first);
+                                }
+                        } else
                         for (int t = 0; t < m_tiles; ++t) {
                             const uint64_t adesc = hi | (uint64_t)((alo + (uint32_t)t * 1024u) & 0x3FFFu);
                             const uint32_t d = tacc + (uint32_t)(t * BN);
@@ -742,8 +753,10 @@ static bool persistent_geo(int N, const TapSet& t, int Ci, int Co, int BN, int s
     const int b_all = t.n * (Ci / 32);
     *resident = Co == BN && b_all <= MAX_PSTAGES && b_all * BN * 128 <= 72 * 1024;
     *pstages = *resident ? b_all : (BN == 32 ? 8 : BN == 64 ? 4 : 2);
-    const int a_budget = (227 * 1024 - 1024 - *pstages * BN * 128 - PSTAGE_BYTES - 2048 - 512) / 2;
-    return a_budget >= 128 * 144 && pick_geo(N, t.Hv, t.Wv, sh, sw, t.n, Ci / 32, BN, *pstages, g, a_budget, 256);
+    // experiments: shared memory per CTA (113 KB -> two persistent CTAs per SM) and TMEM columns per accumulator set
+    static int smem_kb = env_int("G2_HALO_PERSISTENT_SMEM_KB", 227), cols = env_int("G2_HALO_PERSISTENT_COLS", 256);
+    const int a_budget = (smem_kb * 1024 - 1024 - *pstages * BN * 128 - PSTAGE_BYTES - 2048 - 512) / 2;
+    return a_budget >= 128 * 144 && pick_geo(N, t.Hv, t.Wv, sh, sw, t.n, Ci / 32, BN, *pstages, g, a_budget, cols);
 }
 
 static bool enabled() {
@@ -850,6 +863,7 @@ int g2_conv_halo_tf32(const float* in, const float* w, const float* bias, float*
             pp.items_x = (int)grid.x; pp.items_y = (int)grid.y;
             pp.acc_cols = g.m * BN;
             pp.b_resident = resident ? 1 : 0;
+            { static int ko = env_int("G2_HALO_KOUTER", 0); pp.kouter = ko; }
             int pc = 32;
             while (pc < 2 * pp.acc_cols) pc <<= 1;
             pp.p.tmem_cols = pc;

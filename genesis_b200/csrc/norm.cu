@@ -414,6 +414,19 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_apply_kernel(const float* __r
     }
 }
 
+// rows per block of the two statistics kernels (grid = (chunks, N)): about 12 CTAs per SM over the whole launch -- large maps get
+// long row runs per CTA (the block reduction + atomics tail is paid once per CTA), small maps still fill the machine (round 1
+// used >= 32 passes per CTA: 320 CTAs for a 32 x 32 map, 2.3 TB/s)
+inline int stats_rows_per_block(int N, int HW, int C) {
+    const int lanes = 256 / (C / 4);
+    const int unit = lanes * NORM_U;
+    long rpb = ((long)HW * N + 148L * 12 - 1) / (148L * 12);
+    rpb = (rpb + unit - 1) / unit * unit;
+    if (rpb < unit) rpb = unit;
+    if (rpb > HW) rpb = (HW + unit - 1) / unit * unit;
+    return (int)rpb;
+}
+
 // rows per block for the (chunks, N) streaming kernels: a few waves of 148 SMs, at least one unrolled pass per thread
 inline int norm_rows_per_block(int N, int HW, int C) {
     const int lanes = 256 / (C / 4);
@@ -431,10 +444,7 @@ int g2_norm_stats_f32(const float* y, double* sums, int N, int HW, int Cy, cudaS
     G2_CHECK_ARG(y && sums && N > 0 && HW > 0 && C >= 4 && (C % 4) == 0 && C <= 1024);
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)N * C, stream);
     if (e != cudaSuccess) return (int)e;
-    // keep the grid near a few waves of 148 SMs (measured: 4x smaller blocks are 15-20 % slower -- reduction + atomics tail)
-    const int lanes = 256 / (C / 4);
-    int rpb = lanes * 32;
-    while ((long)g2_cdiv(HW, rpb) * N > 148L * 32 && rpb < HW) rpb *= 2;
+    const int rpb = stats_rows_per_block(N, HW, C);
     dim3 grid(g2_cdiv(HW, rpb), N);
     norm_stats_kernel<<<grid, 256, 0, stream>>>(y, sums, HW, C, rpb);
     G2_LAUNCH_RET();
@@ -474,9 +484,7 @@ int g2_norm_bwd_stats_f32(const float* y, const float* dout, const float* scale,
     const int Cy = post == G2_POST_GATE ? 2 * C : C;
     cudaError_t e = cudaMemsetAsync(sums2, 0, sizeof(double) * 2 * (size_t)N * Cy, stream);
     if (e != cudaSuccess) return (int)e;
-    const int lanes = 256 / (C / 4);
-    int rpb = lanes * 32;
-    while ((long)g2_cdiv(HW, rpb) * N > 148L * 32 && rpb < HW) rpb *= 2;
+    const int rpb = stats_rows_per_block(N, HW, C);
     dim3 grid(g2_cdiv(HW, rpb), N);
     if (post == G2_POST_GATE) norm_bwd_stats_kernel<G2_POST_GATE><<<grid, 256, 0, stream>>>(y, dout, scale, shift, mean, rstd, sums2, HW, C, sn, rpb);
     else if (post == G2_POST_RELU) norm_bwd_stats_kernel<G2_POST_RELU><<<grid, 256, 0, stream>>>(y, dout, scale, shift, mean, rstd, sums2, HW, C, sn, rpb);

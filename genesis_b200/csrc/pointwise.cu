@@ -446,3 +446,47 @@ extern "C" int g2_geco_step_f32(float* state, const float* err_kl, float* step_c
                                      update);
     G2_LAUNCH_RET();
 }
+
+// ---- 3xTF32 operand split ("tf32x3": a * b ~= a_hi b_hi + a_hi b_lo + a_lo b_hi, error ~2^-21 instead of 2^-11).
+// hi = x rounded to TF32 (10-bit mantissa; exactly representable, so the TMA / tensor-core operand rounding leaves it
+// unchanged), lo = x - hi (exact in fp32; its own TF32 rounding is a 2^-22 relative error of x).  The three products run as ONE
+// tensor-core contraction over a 3x longer reduction: the activation is written as [hi | hi | lo] channel blocks and the weight as
+// [w_hi | w_lo | w_hi], so no kernel needs an accumulate mode.  mode 0: out [rows, 3C] = [hi | hi | lo];  1: out [rows, 2C] =
+// [hi | lo] (weight-gradient operands: all four blocks come out, three are summed);  2: out [rows, C] = hi;  3: out = lo.
+namespace {
+__device__ __forceinline__ float tf32_hi(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, float* __restrict__ out, long rows, int C,
+                                                         int mode) {
+    const int q = C >> 2;
+    const long total = rows * q;
+    const int oc = mode == 0 ? 3 * C : mode == 1 ? 2 * C : C;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / q;
+        const int c = (int)(i - r * q) * 4;
+        const float4 v = g2_ldg4(x + r * C + c);
+        const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+        const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        float* o = out + r * oc + c;
+        if (mode == 0) {
+            *reinterpret_cast<float4*>(o) = h; *reinterpret_cast<float4*>(o + C) = h; *reinterpret_cast<float4*>(o + 2 * C) = l;
+        } else if (mode == 1) {
+            *reinterpret_cast<float4*>(o) = h; *reinterpret_cast<float4*>(o + C) = l;
+        } else {
+            *reinterpret_cast<float4*>(o) = mode == 2 ? h : l;
+        }
+    }
+}
+}  // namespace
+
+extern "C" int g2_split_tf32_f32(const float* x, float* out, long rows, int C, int mode, cudaStream_t stream) {
+    G2_CHECK_ARG(x && out && rows > 0 && C >= 4 && (C % 4) == 0 && mode >= 0 && mode <= 3);
+    long b = (rows * (C / 4) + 255) / 256;
+    if (b > 148L * 16) b = 148L * 16;
+    split_tf32_kernel<<<(int)b, 256, 0, stream>>>(x, out, rows, C, mode);
+    G2_LAUNCH_RET();
+}

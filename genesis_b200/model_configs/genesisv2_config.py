@@ -101,6 +101,8 @@ class GenesisV2(nn.Module, _g.NoiseMixin):
         self.multi_gpu = cfg.multi_gpu
         self.img_size = cfg.img_size
         self.semiconv = bool(cfg.semiconv)
+        self.precise_backbone = True    # 3xTF32 in the UNet backbone + seg / feat heads (fp32-level accuracy on the tensor cores)
+        self.precise_decoder = False    # the same for the conv-transpose decoder (experiments)
         if cfg.feat_dim != 64:
             raise NotImplementedError('engine is tiled for feat_dim=64')
         c = cfg.feat_dim
@@ -140,8 +142,12 @@ class GenesisV2(nn.Module, _g.NoiseMixin):
                        z.new_zeros(N, d, d, cpad - z.shape[1] - 2)], dim=3).contiguous()
         for ci in (1, 4, 7, 10):
             conv, gn = dm[ci], dm[ci + 1]
-            y = ops.conv_transpose2d(h, conv.weight, conv.bias, 2, 2)     # the op zero-pads the weight to h's channel count
-            h = ops.norm_post(y, gn.weight, gn.bias, mode=ops.NORM_GROUP, groups=gn.num_groups, post=ops.POST_RELU, eps=gn.eps)
+            # the first layer (4x4 -> 8x8 maps, a few MFLOP) is always a precise layer with the backbone: its weight gradient is
+            # the one decoder tensor that plain TF32 leaves near the 2e-2 bar; `precise_decoder` extends that to all four
+            with ops.precise(self.precise_decoder or (ci == 1 and self.precise_backbone)):
+                y = ops.conv_transpose2d(h, conv.weight, conv.bias, 2, 2, bias_grad=False)     # the op zero-pads the weight to h's channels
+            h = ops.norm_post(y, gn.weight, gn.bias, mode=ops.NORM_GROUP, groups=gn.num_groups, post=ops.POST_RELU, eps=gn.eps,
+                              conv_bias=conv.bias)
         return ops.out1x1(h, dm[13].weight, dm[13].bias, 3 if self.pixel_bound else 0)
 
     def forward(self, x):
@@ -152,9 +158,12 @@ class GenesisV2(nn.Module, _g.NoiseMixin):
         S = self.img_size
         tc = ops.get_precision() == 'tf32'
         xh = ops.to_nhwc_padded(x, 32) if tc else ops.to_nhwc(x)
-        enc_feat = H.unet_forward(self.encoder, xh)            # ends in ReLU: F.relu(enc_feat) (:115) is the identity
-        # --- attention masks (reference attention.py:162-226)
-        seg = H.conv_norm_relu(self.seg_head, enc_feat, 'gn')
+        # the GroupNorm UNet backbone and the two heads that read it run as 3xTF32 (ops.precise): plain TF32 operand rounding is
+        # amplified by the per-sample norms into 5-15 % errors on their gradients (profiles/r01_parity_report.txt)
+        with ops.precise(self.precise_backbone):
+            enc_feat = H.unet_forward(self.encoder, xh)        # ends in ReLU: F.relu(enc_feat) (:115) is the identity
+            # --- attention masks (reference attention.py:162-226)
+            seg = H.conv_norm_relu(self.seg_head, enc_feat, 'gn')
         ap = self.att_process
         ch = ap.colour_head
         cd = ap.colour_dim
@@ -181,14 +190,18 @@ class GenesisV2(nn.Module, _g.NoiseMixin):
             u = self._uniform((B, 1, S, S), x)
             log_m, log_s, seed_idx = ops.icsbp(colour, u, ap.log_sigma, K, ap.kernel)        # [K,B,1,H,W]
         # --- slot latents (reference genesisv2_config.py:145-161), feat_head evaluated once
-        f = H.conv_norm_relu(self.feat_head[0], enc_feat, 'gn')
-        f = ops.conv2d(f, self.feat_head[1].weight, self.feat_head[1].bias, 1, 0)            # [B,H,W,128]
+        with ops.precise(self.precise_backbone):
+            f = H.conv_norm_relu(self.feat_head[0], enc_feat, 'gn')
+            f = ops.conv2d(f, self.feat_head[1].weight, self.feat_head[1].bias, 1, 0)        # [B,H,W,128]
         num, msum = ops.masked_pool(f, log_m)                                                # [K,B,128], [K,B]
         obj = (num / (msum.unsqueeze(2) + 1e-5)).reshape(K * B, -1)
         zh = self.z_head
-        t = H.layer_norm(obj, zh[0])
-        t = ops.linear(t, zh[1].weight, zh[1].bias, 'relu')
-        lo = ops.linear(t, zh[3].weight, zh[3].bias)
+        # z_head: two [K*B,128] x [128,128] products whose BACKWARD carries the whole attention gradient (masks -> pooled features
+        # -> latents -> decoder): 3xTF32 in both directions (measured: colour-head gate gradient 5.8e-2 -> see DESIGN.md section 5)
+        with ops.precise(self.precise_backbone, backward=True):
+            t = H.layer_norm(obj, zh[0])
+            t = ops.linear(t, zh[1].weight, zh[1].bias, 'relu')
+            lo = ops.linear(t, zh[3].weight, zh[3].bias)
         # the reference draws one [B,64] normal per slot, in slot order (:156-157)
         eps = torch.cat([self._normal((B, lo.shape[1] // 2), x) for _ in range(K)], 0)
         z, mu, sigma = H.gauss_head(lo, eps)

@@ -70,6 +70,8 @@ class MONet(nn.Module, _g.NoiseMixin):
         std = cfg.pixel_std2 * torch.ones(1, 1, 1, 1, self.K_steps)
         std[0, 0, 0, 0, 0] = cfg.pixel_std1
         self.register_buffer('std', std)
+        self.precise_unet = True        # 3xTF32 in the attention UNet (fp32-level accuracy on the tensor cores); False = plain TF32
+        self.precise_comp_encoder = True
 
     def _attention(self, x):
         """SimpleSBP.forward (reference attention.py:31-51): K-1 sequential UNet passes on cat(x, log_s_k)."""
@@ -84,7 +86,9 @@ class MONet(nn.Module, _g.NoiseMixin):
         core_w0 = torch.cat([w0[:, 3:4], w0[:, :3]], dim=1)
         for _ in range(K - 1):
             h = ops.comp_pack(x, log_s_k[-1].view(1, B, 1, *HW), cp)
-            h = H.unet_forward(_FirstWeight(core, core_w0), h)
+            # K-1 recurrent passes through per-sample norms amplify operand rounding: the UNet runs as 3xTF32 (ops.precise)
+            with ops.precise(self.precise_unet):
+                h = H.unet_forward(_FirstWeight(core, core_w0), h)
             a = ops.out1x1(h, core.final_conv.weight[:1], core.final_conv.bias[:1], 0)       # core_out[:, :1]
             log_m_k.append(log_s_k[-1] + F.logsigmoid(a))
             log_s_k.append(log_s_k[-1] + F.logsigmoid(-a))
@@ -99,7 +103,8 @@ class MONet(nn.Module, _g.NoiseMixin):
         log_m_k, log_s_k = self._attention(x)
         log_m = torch.stack(log_m_k, 0)                                     # [K,B,1,H,W]
         cv = self.comp_vae
-        enc = H.comp_encode(cv.encoder_module, ops.comp_pack(x, log_m, 32 if ops.get_precision() == 'tf32' else 4), 'relu')
+        with ops.precise(self.precise_comp_encoder):    # log-mask inputs down to -9: TF32 rounding of the operand alone is 4e-3 absolute
+            enc = H.comp_encode(cv.encoder_module, ops.comp_pack(x, log_m, 32 if ops.get_precision() == 'tf32' else 4), 'relu')
         cz, cmu, csig = H.gauss_head(enc, self._normal((enc.shape[0], enc.shape[1] // 2), x))
         dec = H.broadcast_decode(cv.decoder_module, cz, 'relu', 3 if self.pixel_bound else 0)
         dec = dec.view(K, B, 4, self.img_size, self.img_size)

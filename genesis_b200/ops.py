@@ -250,7 +250,20 @@ def _conv_fwd_common(ctx, x, w, b, stride, pad, act, transposed, bias_grad=True)
     wd = w.detach()
     out = _new(x, N, Ho, Wo, Co)
     pb = None
-    if _tc_ok(N, H, W, Cx, Ho, Wo, Co, R, S, stride, pad, mode_f):
+    if _X3['on'] and _X3['fwd'] and Cx % 32 == 0 and _tc_ok(N, H, W, 3 * Cx, Ho, Wo, Co, R, S, stride, pad, mode_f):
+        # precise layer (ops.precise): the FORWARD contraction as 3xTF32 -- [x_hi|x_hi|x_lo] against [w_hi|w_lo|w_hi] over a 3x
+        # longer reduction, fp32-level accuracy.  Measured on B200 (profiles/r02_parity_x3.txt): the gradient errors of the
+        # UNet models come from the forward rounding alone, so the backward contractions below stay plain TF32.
+        wp = _pad_dim(wd, 0 if transposed else 1, Cx)
+        w_hi, w_lo = _w_hi_lo(wp)
+        w3 = torch.cat([w_hi, w_lo, w_hi], dim=0 if transposed else 1)
+        pa3 = _new(x, R * S, Co, 3 * Cx)
+        _call('g2_pack_conv_weight_f32', _c(w3), pa3, None, Co, 3 * Cx, 3 * Cx, R * S, 1 if transposed else 0)
+        _conv_tc(_split(x, Cx, 0), pa3, b, out, (N, H, W, 3 * Cx, Ho, Wo, Co), R, S, stride, pad, mode_f, act)
+        if ctx.needs_input_grad[0] and _tc_ok(N, Ho, Wo, Co, H, W, Cx, R, S, stride, pad, mode_d):
+            pb = _new(x, R * S, Cx, Co)
+            _call('g2_pack_conv_weight_f32', _c(wd), _new(x, R * S, Co, Cx), pb, Co, Ci, Cx, R * S, 1 if transposed else 0)
+    elif _tc_ok(N, H, W, Cx, Ho, Wo, Co, R, S, stride, pad, mode_f):
         pa = _new(x, R * S, Co, Cx)
         if ctx.needs_input_grad[0] and _tc_ok(N, Ho, Wo, Co, H, W, Cx, R, S, stride, pad, mode_d):
             pb = _new(x, R * S, Cx, Co)
@@ -349,6 +362,8 @@ class _Conv(Function):
 
 def conv2d(x, w, b=None, stride=1, pad=0, act=None, bias_grad=True):
     """bias_grad=False: the bias gradient is produced elsewhere (norm_post(conv_bias=b) fuses it into the norm backward)."""
+    if _x3_conv_ok(x, w, stride, pad, False):
+        return _ConvX3.apply(x, w, b, stride, pad, ACTS[act], False, bias_grad)
     return _Conv.apply(x, w, b, stride, pad, ACTS[act], bias_grad)
 
 
@@ -365,7 +380,194 @@ class _ConvT(Function):
 
 
 def conv_transpose2d(x, w, b=None, stride=1, pad=0, act=None, bias_grad=True):
+    if _x3_conv_ok(x, w, stride, pad, True):
+        return _ConvX3.apply(x, w, b, stride, pad, ACTS[act], True, bias_grad)
     return _ConvT.apply(x, w, b, stride, pad, ACTS[act], bias_grad)
+
+
+# ----------------------------------------------------------------------------------------- tf32x3 ("precise") layers
+# GENESIS-V2's and MONet's UNets (per-sample norms over flat images, K-1 recurrent passes) amplify the 2^-11 operand rounding of a
+# plain TF32 contraction into 5-15 % per-tensor gradient errors.  Inside `with ops.precise():` convolutions and linears run as
+# 3xTF32: every operand is split into hi = tf32(x) and lo = x - hi, and a * b ~= a_hi b_hi + a_hi b_lo + a_lo b_hi is evaluated as
+# ONE tensor-core contraction over a 3x longer reduction ([hi|hi|lo] channel blocks against [w_hi|w_lo|w_hi]) -- fp32-level
+# accuracy (2^-21) on the same tcgen05 kernels, forward, data gradient and weight gradient.
+import contextlib as _contextlib
+
+_X3 = {'on': False, 'fwd': True, 'dgrad': False, 'wgrad': False}     # measured: forward rounding is what matters
+
+
+@_contextlib.contextmanager
+def precise(on=True, backward=None):
+    """Layers created inside run their forward contraction as 3xTF32; backward=True also their data- and weight-gradient
+    contractions (small latent heads whose backward GEMMs sit on a sensitive gradient path)."""
+    prev = dict(_X3)
+    _X3['on'] = bool(on) and _PRECISION['mode'] == 'tf32'
+    if backward is not None:
+        _X3['dgrad'] = _X3['wgrad'] = bool(backward)
+    try:
+        yield
+    finally:
+        _X3.update(prev)
+
+
+def set_precise_parts(fwd=True, dgrad=False, wgrad=False):
+    """Which of the three contractions of a precise layer use 3xTF32 (experiments: the others stay plain TF32)."""
+    _X3.update(fwd=bool(fwd), dgrad=bool(dgrad), wgrad=bool(wgrad))
+
+
+def _split(x2d_like, C, mode):
+    """x viewed as [rows, C] -> [hi|hi|lo] (mode 0), [hi|lo] (1), hi (2), lo (3) along the last dim."""
+    x = _c(x2d_like)
+    rows = x.numel() // C
+    oc = {0: 3 * C, 1: 2 * C, 2: C, 3: C}[mode]
+    out = _new(x, *x.shape[:-1], oc)
+    _call('g2_split_tf32_f32', x, out, rows, C, mode)
+    return out
+
+
+def _w_hi_lo(w):
+    w = _c(w)
+    n = w.numel()
+    if n % 4 != 0:       # tiny odd-sized weights: plain torch (bit-identical definition of hi / lo)
+        hi = (w.view(torch.int32) + 0x1000).bitwise_and(-8192).view(torch.float32)
+        return hi, w - hi
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    _call('g2_split_tf32_f32', w, hi, n // 4, 4, 2)
+    _call('g2_split_tf32_f32', w, lo, n // 4, 4, 3)
+    return hi, lo
+
+
+class _ConvX3(Function):
+    """Conv2d / ConvTranspose2d (output_padding = stride-1) on NHWC activations as 3xTF32 contractions; same contract as _Conv."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, pad, act, transposed, bias_grad):
+        x = _c(x)
+        N, H, W, Cx = x.shape
+        if transposed:
+            Ci, Co, R, S = w.shape
+            Ho = (H - 1) * stride - 2 * pad + R + stride - 1
+            Wo = (W - 1) * stride - 2 * pad + S + stride - 1
+        else:
+            Co, Ci, R, S = w.shape
+            Ho = (H + 2 * pad - R) // stride + 1
+            Wo = (W + 2 * pad - S) // stride + 1
+        mode_f = 1 if transposed else 0
+        wd = _pad_dim(w.detach(), 0 if transposed else 1, Cx)           # zero rows for the padded input channels
+        w_hi, w_lo = _w_hi_lo(wd)
+        out = _new(x, N, Ho, Wo, Co)
+        cin_dim = 0 if transposed else 1
+        if _X3['fwd']:
+            x3 = _split(x, Cx, 0)
+            w3 = torch.cat([w_hi, w_lo, w_hi], dim=cin_dim)
+            pa = _new(x, R * S, Co, 3 * Cx)
+            _call('g2_pack_conv_weight_f32', _c(w3), pa, None, Co, 3 * Cx, 3 * Cx, R * S, 1 if transposed else 0)
+            _conv_tc(x3, pa, b, out, (N, H, W, 3 * Cx, Ho, Wo, Co), R, S, stride, pad, mode_f, act)
+        else:
+            pa = _new(x, R * S, Co, Cx)
+            _call('g2_pack_conv_weight_f32', _c(wd), pa, None, Co, Cx, Cx, R * S, 1 if transposed else 0)
+            _conv_tc(x, pa, b, out, (N, H, W, Cx, Ho, Wo, Co), R, S, stride, pad, mode_f, act)
+        ctx.save_for_backward(x, w_hi, w_lo, out if act != ACT_NONE else None)
+        ctx.params = (w, b)
+        ctx.cfg = (stride, pad, act, b is not None and bias_grad, transposed, Ci)
+        ctx.parts = (_X3['dgrad'], _X3['wgrad'])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w_hi, w_lo, out = ctx.saved_tensors
+        x3_dgrad, x3_wgrad = ctx.parts
+        w_param, b_param = ctx.params
+        stride, pad, act, has_b, transposed, Ci = ctx.cfg
+        N, H, W, Cx = x.shape
+        if transposed:
+            _, Co, R, S = w_hi.shape
+        else:
+            Co, _, R, S = w_hi.shape
+        dout = _c(dout)
+        _, Ho, Wo, _ = dout.shape
+        mode_d = 0 if transposed else 1
+        dx = dw = db = None
+        if act != ACT_NONE and has_b and ctx.needs_input_grad[2] and Co % 4 == 0:
+            dpre = torch.empty_like(dout)
+            if _direct(b_param):
+                _call('g2_act_bwd_bias_f32', dout, out, dpre, b_param.grad, dout.numel() // Co, Co, act)
+            else:
+                db = torch.zeros(Co, device=dout.device, dtype=torch.float32)
+                _call('g2_act_bwd_bias_f32', dout, out, dpre, db, dout.numel() // Co, Co, act)
+            has_b = False
+        else:
+            dpre = _act_bwd(dout, out, act)
+        co_dim = 1 if transposed else 0
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            if x3_dgrad:
+                d3 = _split(dpre, Co, 0)                                         # [hi|hi|lo] over the reduction (Co)
+                w3 = torch.cat([w_hi, w_lo, w_hi], dim=co_dim)                   # 3*Co output channels
+                pb = _new(x, R * S, Cx, 3 * Co)
+                _call('g2_pack_conv_weight_f32', _c(w3), _new(x, R * S, 3 * Co, Cx), pb, 3 * Co, Cx, Cx, R * S, 1 if transposed else 0)
+                _conv_tc(d3, pb, None, dx, (N, Ho, Wo, 3 * Co, H, W, Cx), R, S, stride, pad, mode_d, ACT_NONE)
+            else:
+                wd = w_hi + w_lo
+                pb = _new(x, R * S, Cx, Co)
+                _call('g2_pack_conv_weight_f32', _c(wd), _new(x, R * S, Co, Cx), pb, Co, Cx, Cx, R * S, 1 if transposed else 0)
+                _conv_tc(dpre, pb, None, dx, (N, Ho, Wo, Co, H, W, Cx), R, S, stride, pad, mode_d, ACT_NONE)
+        if ctx.needs_input_grad[1]:
+            # conv: g = x (a = Cx), t = dpre (b = Co);  conv-transpose: g = dpre (a = Co), t = x (b = Cx)
+            if transposed:
+                g, t, Cg, Ct, dims = dpre, x, Co, Cx, (N, Ho, Wo, None, H, W, None)
+            else:
+                g, t, Cg, Ct, dims = x, dpre, Cx, Co, (N, H, W, None, Ho, Wo, None)
+            use3 = x3_wgrad
+            mult = 2 if use3 else 1
+            d = (dims[0], dims[1], dims[2], mult * Cg, dims[4], dims[5], mult * Ct)
+            ws_bytes = _lib.lib().query('g2_conv_wgrad_tf32_workspace', *d, R, S, stride)
+            stream_ctx = _GradStream(g, t) if _direct(w_param) else _contextlib.nullcontext()
+            with stream_ctx:
+                if ws_bytes > 0:
+                    g2 = _split(g, Cg, 1) if use3 else g
+                    t2 = _split(t, Ct, 1) if use3 else t
+                    dwp = _new(x, R, S, mult * Cg, mult * Ct)
+                    ws = _new(x, ws_bytes // 4)
+                    _call('g2_conv_wgrad_tf32', g2, t2, dwp, ws, *d, R, S, stride, pad, 0)
+                    if use3:     # [hi|lo] x [hi|lo]: hh + hl + lh (ll is below fp32 resolution)
+                        dwp = dwp[:, :, :Cg, :Ct] + dwp[:, :, :Cg, Ct:] + dwp[:, :, Cg:, :Ct]
+                else:            # shape outside the tensor-core tiles: exact fp32 SIMT
+                    dwp = _new(x, R, S, Cg, Ct)
+                    _call('g2_conv_wgrad_f32', g, t, dwp, dims[0], dims[1], dims[2], Cg, dims[4], dims[5], Ct, R, S, stride, pad, 0)
+                # dwp [R,S,a,b] -> torch layout: conv [Co,Ci,R,S] (a = Cx, b = Co);  conv-transpose [Ci,Co,R,S] (a = Co, b = Cx)
+                dwt = dwp.permute(3, 2, 0, 1)
+                dwt = dwt[:Ci] if transposed else dwt[:, :Ci]
+                if _direct(w_param):
+                    w_param.grad.add_(dwt)
+                else:
+                    dw = dwt.contiguous()
+                if has_b and ctx.needs_input_grad[2] and _direct(b_param):
+                    _bias_grad(dpre, b_param, Co)
+                    has_b = False
+        if has_b and ctx.needs_input_grad[2]:
+            db = _bias_grad(dpre, b_param, Co)
+        return dx, dw, db, None, None, None, None, None
+
+
+def _x3_conv_ok(x, w, stride, pad, transposed):
+    """Full 3xTF32 route (_ConvX3: also the backward contractions; experiments, scripts/parity_report.py): TF32 mode, inside
+    `precise()`, a backward part requested, and the tensor-core kernels cover the 3x-reduction shapes.  The default precise
+    layer (forward only) goes through _Conv / _ConvT."""
+    if not _X3['on'] or _PRECISION['mode'] != 'tf32' or not (_X3['dgrad'] or _X3['wgrad']):
+        return False
+    N, H, W, Cx = x.shape
+    if transposed:
+        Ci, Co, R, S = w.shape
+        Ho = (H - 1) * stride - 2 * pad + R + stride - 1
+        Wo = (W - 1) * stride - 2 * pad + S + stride - 1
+    else:
+        Co, Ci, R, S = w.shape
+        Ho = (H + 2 * pad - R) // stride + 1
+        Wo = (W + 2 * pad - S) // stride + 1
+    mf, md = (1, 0) if transposed else (0, 1)
+    return (Cx % 32 == 0 and _tc_ok(N, H, W, 3 * Cx, Ho, Wo, Co, R, S, stride, pad, mf)
+            and _tc_ok(N, Ho, Wo, 3 * Co, H, W, Cx, R, S, stride, pad, md))
 
 
 # ----------------------------------------------------------------------------------------- linear
@@ -381,7 +583,13 @@ class _Linear(Function):
         M, K = x.shape
         N = wd.shape[0]
         y = _new(x, M, N)
-        if _gemm_tc_ok(M, N, K):
+        ctx.x3 = _X3['on'] and (_X3['dgrad'] or _X3['wgrad'])
+        if _X3['on'] and _X3['fwd'] and _gemm_tc_ok(M, N, 3 * K):
+            w_hi, w_lo = _w_hi_lo(wd)
+            _gemm_tc(_split(x, K, 0), torch.cat([w_hi, w_lo, w_hi], dim=1), b, y, M, N, 3 * K, act)      # 3xTF32
+        elif _X3['on'] and _X3['fwd']:
+            _call('g2_gemm_f32', x, wd, b, y, M, N, K, K, K, N, 0, 1, act, 0)                              # exact fp32
+        elif _gemm_tc_ok(M, N, K):
             _gemm_tc(x, wd, b, y, M, N, K, act)      # deterministic split-K; bias + activation fused
         else:
             _call('g2_gemm_f32', x, wd, b, y, M, N, K, K, K, N, 0, 1, act, 0)
@@ -399,16 +607,29 @@ class _Linear(Function):
         N = w.shape[0]
         dpre = _act_bwd(_c(dy), y, act)
         dx = dw = db = None
+        x3 = getattr(ctx, 'x3', False)
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            if _gemm_tc_ok(M, K, N):
+            if x3 and _gemm_tc_ok(M, K, 3 * N):
+                wt_hi, wt_lo = _w_hi_lo(w.t().contiguous())
+                _gemm_tc(_split(dpre, N, 0), torch.cat([wt_hi, wt_lo, wt_hi], dim=1), None, dx, M, K, 3 * N)
+            elif x3:
+                _call('g2_gemm_f32', dpre, w, None, dx, M, K, N, N, K, K, 0, 0, ACT_NONE, 0)
+            elif _gemm_tc_ok(M, K, N):
                 _gemm_tc(dpre, w.t().contiguous(), None, dx, M, K, N)
             else:
                 _call('g2_gemm_f32', dpre, w, None, dx, M, K, N, N, K, K, 0, 0, ACT_NONE, 0)
         if ctx.needs_input_grad[1]:
             if _direct(w_param):
                 with _GradStream(dpre, x):
-                    if _gemm_tc_ok(N, K, M):
+                    if x3 and _gemm_tc_ok(N, K, 3 * M):
+                        dwt = torch.empty_like(w)
+                        xt_hi, xt_lo = _w_hi_lo(x.t().contiguous())
+                        _gemm_tc(_split(dpre.t().contiguous(), M, 0), torch.cat([xt_hi, xt_lo, xt_hi], dim=1), None, dwt, N, K, 3 * M)
+                        w_param.grad.add_(dwt)
+                    elif x3:
+                        _call('g2_gemm_f32', dpre, x, None, w_param.grad, N, K, M, N, K, K, 1, 0, ACT_NONE, 1)
+                    elif _gemm_tc_ok(N, K, M):
                         dwt = torch.empty_like(w)
                         _gemm_tc(dpre.t().contiguous(), x.t().contiguous(), None, dwt, N, K, M)
                         w_param.grad.add_(dwt)
@@ -417,6 +638,13 @@ class _Linear(Function):
                     if has_b and ctx.needs_input_grad[2] and _direct(b_param):
                         _bias_grad(dpre, b_param, N)
                         has_b = False
+            elif x3 and _gemm_tc_ok(N, K, 3 * M):
+                dw = torch.empty_like(w)
+                xt_hi, xt_lo = _w_hi_lo(x.t().contiguous())
+                _gemm_tc(_split(dpre.t().contiguous(), M, 0), torch.cat([xt_hi, xt_lo, xt_hi], dim=1), None, dw, N, K, 3 * M)
+            elif x3:
+                dw = torch.empty_like(w)
+                _call('g2_gemm_f32', dpre, x, None, dw, N, K, M, N, K, K, 1, 0, ACT_NONE, 0)
             elif _gemm_tc_ok(N, K, M):
                 dw = torch.empty_like(w)
                 _gemm_tc(dpre.t().contiguous(), x.t().contiguous(), None, dw, N, K, M)

@@ -294,6 +294,12 @@ int g2_debug_umma_probe(const float* a_img, const float* b_img, float* D, int a_
                         long bdesc_t, int idesc, int N, int nk, int a_kstep, int b_kstep, int a_off, int b_off,
                         int base_off_auto, g2_stream_t stream);
 
+/* 3xTF32 operand split (pointwise.cu): hi = x rounded to TF32, lo = x - hi.  mode 0: out [rows,3C] = [hi|hi|lo] (activation
+ * side of a tf32x3 contraction whose weight side is [w_hi|w_lo|w_hi]); 1: out [rows,2C] = [hi|lo]; 2: out = hi; 3: out = lo.
+ * With it the ill-conditioned layers (MONet / GENESIS-V2 UNet: modules/unet.py:53-65, modules/blocks.py:151-165) run on the
+ * tensor cores at fp32-level accuracy through the unchanged conv / GEMM entry points. */
+int g2_split_tf32_f32(const float* x, float* out, long rows, int C, int mode, g2_stream_t stream);
+
 /* ---- optimiser (pointwise.cu) --------------------------------------------------------------------
  * Fused Adam over a flat fp32 parameter / gradient arena; replaces torch.optim.Adam.step() in the
  * caller's loop (train.py:175,263).  `step` is a device-resident float counter (1-based). n % 4 == 0. */

@@ -1,5 +1,11 @@
 """Compact parity table: engine (CUDA) vs oracle (CPU) on identical parameters, inputs and noise, for every model and
-both precisions.  Run on the GPU box:  python scripts/parity_report.py > gpurun_out/parity.txt"""
+precision mode.  Run on the GPU box:  python scripts/parity_report.py [model ...] [--modes tf32,tf32x3,fp32] > gpurun_out/parity.txt
+  tf32   = plain TF32 tensor-core operands everywhere (round 1's product path)
+  tf32x3 = the product default: 3xTF32 (ops.precise) in the GENESIS-V2 backbone / MONet attention UNet, plain TF32 elsewhere
+  fp32   = exact-fp32 SIMT kernels everywhere
+  tf32x3:fwd+dgrad+wgrad / ... = 3xTF32 also in the named backward contractions of the precise layers (experiments; the
+           default is the forward contraction only -- measured to be what matters)
+  tf32x3+dec / tf32x3+enc = additionally the GENESIS-V2 decoder / the MONet component encoder as precise layers"""
 import os
 import sys
 
@@ -15,16 +21,33 @@ from genesis_b200 import ops  # noqa: E402
 
 CASES = [('genesis', 5, 4, 64, 'multid'), ('genesisv2', 7, 4, 64, 'stacks'), ('genesisv2', 11, 2, 64, 'rooms'),
          ('monet', 7, 3, 64, 'multid'), ('monet', 3, 2, 128, 'multid')]
-if len(sys.argv) > 1:
-    CASES = [c for c in CASES if c[0] in sys.argv[1:]]
+MODES = ['tf32', 'tf32x3', 'fp32']
+_args = sys.argv[1:]
+if '--modes' in _args:
+    i = _args.index('--modes')
+    MODES = _args[i + 1].split(',')
+    _args = _args[:i] + _args[i + 2:]
+if _args:
+    CASES = [c for c in CASES if c[0] in _args]
 
 
 def main():
     for model, K, B, img, gen in CASES:
-        for prec in ('tf32', 'fp32'):
-            ops.set_precision(prec)
+        for prec in MODES:
+            if model == 'genesis' and prec.startswith('tf32x3'):
+                continue                      # GENESIS has no precise layers: tf32x3 == tf32
+            ops.set_precision('fp32' if prec == 'fp32' else 'tf32')
+            parts = prec.split(':')[1].split('+') if ':' in prec else ['fwd']
+            prec_tag = prec
+            ops.set_precise_parts('fwd' in parts, 'dgrad' in parts, 'wgrad' in parts)
             m, cfg = build_engine_model(model, K, img, seed=3)
             m = m.cuda().train()
+            for attr in ('precise_unet', 'precise_backbone'):
+                if hasattr(m, attr):
+                    setattr(m, attr, prec.startswith('tf32x3'))
+            for attr in ('precise_decoder', 'precise_comp_encoder'):
+                if hasattr(m, attr):
+                    setattr(m, attr, prec.startswith('tf32x3') and ('+dec' in prec or '+enc' in prec))
             if model == 'genesisv2':
                 with torch.no_grad():
                     m.att_process.colour_head.gate.gate.fill_(0.3)

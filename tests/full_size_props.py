@@ -39,6 +39,22 @@ class SubsetTape(object):
         return self._draw(lambda s: torch.rand(s, generator=self.gen, dtype=torch.float32), shape).to(dtype)
 
 
+class RowTape(SubsetTape):
+    """As SubsetTape, for an arbitrary subset of rows of the full batch (a data-parallel rank's shard)."""
+
+    def __init__(self, seed, full_B, rows, K):
+        super().__init__(seed, full_B, len(rows), K)
+        self.rows = torch.as_tensor(list(rows), dtype=torch.long)
+
+    def _draw(self, fn, shape):
+        shape = tuple(int(s) for s in shape)
+        if shape[0] == self.sub_B:
+            return fn((self.full_B,) + shape[1:])[self.rows].clone()
+        if shape[0] == self.K * self.sub_B:
+            return fn((self.K, self.full_B) + shape[1:])[:, self.rows].reshape(shape).clone()
+        raise AssertionError('unexpected noise shape %r for B=%d K=%d' % (shape, self.sub_B, self.K))
+
+
 def _d(t):
     return t.detach().double().cpu()
 

@@ -15,17 +15,20 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = sorted(glob.glob(os.path.join(HERE, 'golden', 'genesisv2_*.npz')) + glob.glob(os.path.join(HERE, 'golden', 'monet*.npz')))
 
-# Stated tolerances (DESIGN.md section 6).  Forward: `err` rel 1e-4; KL terms abs 1e-2 + rel 1e-3; log masks
+# Stated tolerances (DESIGN.md section 5).  Forward: `err` rel 1e-4; KL terms abs 1e-2 + rel 1e-3; log masks
 # |d| <= LM_TOL * (1 + |ref|).  Backward, per model and precision: GLOBAL = rel-L2 error of the whole gradient vector,
 # TENSOR = worst per-parameter rel-L2 (denominator floored at 2e-4 of the largest gradient norm).
-# 'fp32' = exact-fp32 SIMT kernels (the parity-proof path), 'tf32' = tcgen05 TF32 operands / fp32 accumulate (the product
-# default; the same operand precision torch's cuDNN convolutions use by default on this GPU).  MONet's K-1 recurrent
-# InstanceNorm UNet passes on flat synthetic images are ill-conditioned: the reference's OWN fp32 gradients differ from
-# fp64 by 6.5e-4 per tensor there (GENESIS: 3e-5), see profiles/r01_parity_report.txt.
+# 'tf32' = the PRODUCT path: tcgen05 TF32 operands / fp32 accumulate, with the layers that amplify operand rounding (GENESIS-V2:
+# UNet backbone, seg / feat heads, z_head, first decoder layer; MONet: attention UNet, component encoder) run as 3xTF32
+# (ops.precise -- fp32-level accuracy on the same tensor-core kernels).  'fp32' = exact-fp32 SIMT kernels everywhere.
+# Round 1 ran plain TF32 everywhere and needed TENSOR 0.3 / GLOBAL 6e-2 (measured worst 0.16); measured now
+# (profiles/r02_parity_x3.txt): GENESIS-V2 worst tensor 1.6e-2, global 1.4e-3; MONet worst 8.3e-3, global 1.4e-3 -- the level
+# of the exact-fp32 path, whose own distance to the reference is set by the conditioning of the K-1 recurrent InstanceNorm UNet
+# passes on flat synthetic images (the reference's fp32 gradients differ from its fp64 ones by 6.5e-4 per tensor there).
 ERR_RTOL, KL_ATOL = 1e-4, 1e-2
 LM_TOL = {'tf32': 5e-3, 'fp32': 2e-4}
-GLOBAL_TOL = {('genesisv2', 'tf32'): 1.5e-2, ('genesisv2', 'fp32'): 1e-4, ('monet', 'tf32'): 6e-2, ('monet', 'fp32'): 5e-3}
-TENSOR_TOL = {('genesisv2', 'tf32'): 0.3, ('genesisv2', 'fp32'): 2e-3, ('monet', 'tf32'): 0.3, ('monet', 'fp32'): 2e-2}
+GLOBAL_TOL = {('genesisv2', 'tf32'): 5e-3, ('genesisv2', 'fp32'): 1e-4, ('monet', 'tf32'): 5e-3, ('monet', 'fp32'): 5e-3}
+TENSOR_TOL = {('genesisv2', 'tf32'): 2e-2, ('genesisv2', 'fp32'): 2e-3, ('monet', 'tf32'): 2e-2, ('monet', 'fp32'): 2e-2}
 
 
 @pytest.fixture(params=['tf32', 'fp32'])
