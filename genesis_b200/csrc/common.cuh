@@ -27,6 +27,26 @@ enum { G2_POST_GATE = 0, G2_POST_RELU = 1, G2_POST_NONE = 2 };
 
 static inline int g2_cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: a process-wide `static bool` would leave every
+// device after the first without the opt-in (one process driving several GPUs).  One bit per device ordinal in a 64-bit mask
+// (set-attribute is idempotent, so a race between two threads is benign).  `want` lets a call site raise the size later.
+#include <atomic>
+struct G2DevOnce {
+    std::atomic<unsigned long long> mask{0};
+    std::atomic<int> size{0};
+    bool needed(int want = 1) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (want > size.load(std::memory_order_acquire)) { size.store(want, std::memory_order_release); mask.store(0, std::memory_order_release); }
+        return (mask.load(std::memory_order_acquire) & (1ull << (dev & 63))) == 0;
+    }
+    void done() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        mask.fetch_or(1ull << (dev & 63), std::memory_order_acq_rel);
+    }
+};
+
 __device__ __forceinline__ float g2_sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
 
 __device__ __forceinline__ float g2_apply_act(float v, int act, float aux) {

@@ -658,11 +658,11 @@ static bool pick_geo(int N, int Hv, int Wv, int span_h, int span_w, int ntaps, i
 template <int BN>
 static int launch(const Maps& maps, const P& p, dim3 grid, cudaStream_t stream) {
     const int smem = p.a_bytes + p.stages * BN * 128 + 1024 + 1024;
-    static int attr_set = 0;
-    if (attr_set < smem) {
+    static G2DevOnce once;
+    if (once.needed()) {
         cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
-        attr_set = 227 * 1024;
+        once.done();
     }
     conv_halo_kernel<BN><<<grid, 192, smem, stream>>>(maps, p);
     cudaError_t e = cudaGetLastError();
@@ -677,11 +677,11 @@ template <int BN>
 static int launch_persistent(const Maps& maps, const PP& pp, int n_ctas, cudaStream_t stream) {
     const int smem = 2 * pp.p.a_bytes + pp.p.stages * BN * 128 + PSTAGE_BYTES + 2048 + 512 + 1024;
     if (smem > 227 * 1024) return G2_ERR_UNSUPPORTED;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static G2DevOnce once;
+    if (once.needed()) {
         cudaError_t e = cudaFuncSetAttribute(conv_halo_persistent_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
+        once.done();
     }
     conv_halo_persistent_kernel<BN><<<n_ctas, 192, smem, stream>>>(maps, pp);
     cudaError_t e = cudaGetLastError();

@@ -294,11 +294,11 @@ bool encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, 
 template <int BN, int STAGES>
 int launch(const Maps& maps, const P& p, dim3 grid, cudaStream_t stream) {
     constexpr int smem = STAGES * (A_BYTES + BN * 128) + 128 + BN * 4 + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static G2DevOnce once;
+    if (once.needed()) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
+        once.done();
     }
     conv_tc_kernel<BN, STAGES><<<grid, 192, smem, stream>>>(maps, p);
     cudaError_t e = cudaGetLastError();

@@ -632,11 +632,11 @@ static int wgrad_halo_launch(const wgh::HPlan& hp, const float* g, const float* 
     cudaError_t e = cudaSuccess;
 #define WGH_LAUNCH(BN)                                                                                                     \
     {                                                                                                                      \
-        static int attr = 0;                                                                                               \
-        if (attr < hp.smem) {                                                                                              \
-            e = cudaFuncSetAttribute(wgh::wgrad_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, hp.smem);         \
+        static G2DevOnce once;                                                                                             \
+        if (once.needed(hp.smem)) {                                                                                        \
+            e = cudaFuncSetAttribute(wgh::wgrad_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);  \
             if (e != cudaSuccess) return (int)e;                                                                           \
-            attr = hp.smem;                                                                                                \
+            once.done();                                                                                                   \
         }                                                                                                                  \
         wgh::wgrad_halo_kernel<BN><<<grid, 192, hp.smem, stream>>>(maps, p);                                                   \
     }
@@ -711,11 +711,11 @@ static int wgrad_impl(const float* g, const float* t, float* dw, float* ws, int 
 #define WG_LAUNCH(BN)                                                                                                     \
     {                                                                                                                     \
         constexpr int smem = STAGES * 4 * TILE_BYTES + 2 * (BN / 32) * TILE_BYTES + (2 * STAGES + 5) * 8 + 16 + 1024;     \
-        static bool attr = false;                                                                                         \
-        if (!attr) {                                                                                                      \
+        static G2DevOnce once;                                                                                            \
+        if (once.needed()) {                                                                                              \
             e = cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);             \
             if (e != cudaSuccess) return (int)e;                                                                          \
-            attr = true;                                                                                                  \
+            once.done();                                                                                                  \
         }                                                                                                                 \
         wgrad_tc_kernel<BN><<<grid, 192, smem, stream>>>(maps, p);                                                        \
     }

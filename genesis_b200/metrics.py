@@ -23,6 +23,11 @@ def _run(log_m_k=None, pred=None, instances=None, want_seg=False):
     else:
         pr = pred.reshape(B, P).contiguous().long()
         _lib.call('g2_seg_metrics', None, pr, inst, seg, out, B, P, 16)
+    # out[:, 7] = pixels that entered the confusion matrix: the kernel holds ground-truth labels 0..31 and predicted labels 0..15
+    # (the reference's sklearn / np.unique code takes any labels); a dropped pixel must be an error, not a silently wrong metric
+    if bool((out[:, 7] != P).any()):
+        raise ValueError('segmentation metrics: an instance label >= 32 (or < 0) or a predicted label >= 16; remap the labels '
+                         'to dense ids first')
     return out, seg
 
 

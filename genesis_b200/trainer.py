@@ -316,6 +316,9 @@ class TrainStep(object):
             sd.pop(legacy, None)                       # train.py:191-192
         self.model.load_state_dict(sd)                 # copies INTO the arena views
         self.load_optimiser_state_dict(ck['optimiser_state_dict'])
+        nxt = ck.get('iter_idx', -1) + 1
+        if self.optimiser == 'sgd' and nxt > 0:
+            self.step_count.fill_(float(nxt))          # torch's SGD state carries no step: the checkpoint's iteration does
         if self.use_geco:
             self.geco.load_state(ck)
-        return ck.get('iter_idx', -1) + 1
+        return nxt

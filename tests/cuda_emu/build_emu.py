@@ -17,6 +17,7 @@ PRELUDE = '''#define CUDA_EMU_MAIN
 #include "cuda_emu.h"
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return cudaSuccess; }
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaMemset2DAsync(void* p, size_t pitch, int v, size_t w, size_t h, cudaStream_t) {
     for (size_t r = 0; r < h; ++r) std::memset((char*)p + r * pitch, v, w);
     return cudaSuccess;
@@ -56,6 +57,8 @@ def _split_top(s):
 # ---- inline PTX -> calls into tests/cuda_emu/cuda_emu_sm100.h
 PTX_RULES = [   # (substring of the PTX text, C++ statement; {o0} = first output operand, {i0}.. = input operands)
     ('elect.sync', '{o0} = emu::elect_one();'),
+    # round to nearest (ties away from zero in magnitude) to a 10-bit mantissa, kept in an fp32 container
+    ('cvt.rna.tf32.f32', '{{ uint32_t b__; float f__ = {i0}; std::memcpy(&b__, &f__, 4); b__ = (b__ + 0x1000u) & 0xFFFFE000u; {o0} = b__; }}'),
     ('mbarrier.init', 'emu::mbar_init({i0}, {i1});'),
     ('mbarrier.arrive.expect_tx', 'emu::mbar_expect_tx({i0}, {i1});'),
     ('mbarrier.arrive', 'emu::mbar_arrive({i0});'),

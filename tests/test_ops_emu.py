@@ -157,3 +157,50 @@ def test_conv_activation_bias_gradient_fused(ops):
     got = torch.autograd.grad((ops.conv2d(x, w, b, 1, 0, 'elu') * wgt).sum(), [x, w, b])
     for a, c in zip(got, ref):
         torch.testing.assert_close(a, c, rtol=2e-3, atol=2e-4)
+
+
+@pytest.mark.parametrize('transposed', [False, True])
+def test_precise_conv_3xtf32_plumbing(ops, transposed):
+    """ops.precise(): the forward contraction as ONE 3x-longer tensor-core reduction ([x_hi|x_hi|x_lo] against [w_hi|w_lo|w_hi]),
+    backward on the plain path -- operand split, channel-concatenated packs and the tcgen05 kernels under the functional
+    emulation, against torch.  (Accuracy versus plain TF32 is a property of the hardware rounding: measured on the B200,
+    profiles/r02_parity_x3.txt.)"""
+    ops.set_precision('tf32')
+    torch.manual_seed(8)
+    N, Hh, Ci, Co = 2, 16, 32, 32
+    x = torch.randn(N, Hh, Hh, Ci, requires_grad=True)
+    w = (0.2 * torch.randn(Ci, Co, 3, 3) if transposed else 0.2 * torch.randn(Co, Ci, 3, 3)).requires_grad_(True)
+    b = torch.randn(Co, requires_grad=True)
+    fn_o = ops.conv_transpose2d if transposed else ops.conv2d
+    fn_r = R.conv_transpose2d if transposed else R.conv2d
+    calls = []
+    import genesis_b200._lib as L
+    orig = L._LIB.call
+    L._LIB.call = lambda name, *a: (calls.append((name, a)), orig(name, *a))[1]
+    try:
+        with ops.precise():
+            out = fn_o(x, w, b, 1, 1, 'relu')
+    finally:
+        L._LIB.call = orig
+    convs = [a for n, a in calls if n in ('g2_conv_halo_tf32', 'g2_conv_igemm_tf32')]
+    assert len(convs) == 1 and convs[0][7] == 3 * Ci                      # one contraction over the 3x reduction
+    assert sum(n == 'g2_split_tf32_f32' for n, _ in calls) == 3            # x -> [hi|hi|lo], w -> hi, lo
+    ref = fn_r(x, w, b, 1, 1, 'relu')
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
+    g = torch.randn_like(ref)
+    for a, c in zip(grads(out, [x, w, b], g), grads(ref, [x, w, b], g)):
+        torch.testing.assert_close(a, c, rtol=5e-3, atol=5e-3)            # backward = plain TF32 tensor-core path
+
+
+def test_split_tf32_kernel_is_exact(ops):
+    """hi + lo == x exactly, hi has a 10-bit mantissa, the three layouts of g2_split_tf32_f32."""
+    import genesis_b200._lib as L
+    torch.manual_seed(9)
+    x = torch.randn(6, 8) * torch.tensor([1e-6, 1e-3, 1.0, 1e3, 1e6, 1.0, 1.0, 1.0])
+    out3, out2, hi, lo = torch.empty(6, 24), torch.empty(6, 16), torch.empty(6, 8), torch.empty(6, 8)
+    for o, mode in ((out3, 0), (out2, 1), (hi, 2), (lo, 3)):
+        L.call('g2_split_tf32_f32', x, o, 6, 8, mode)
+    assert torch.equal(hi + lo, x)
+    assert (hi.view(torch.int32) & 0x1FFF).abs().max().item() == 0
+    assert ((x - hi).abs() <= x.abs() * 2.0 ** -11).all()
+    assert torch.equal(out3, torch.cat([hi, hi, lo], 1)) and torch.equal(out2, torch.cat([hi, lo], 1))
