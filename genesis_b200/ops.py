@@ -214,6 +214,50 @@ def _direct(p):
             and p.grad.is_contiguous() and p.grad.data_ptr() % 16 == 0)
 
 
+# Gradient-ready tracking (data-parallel overlap, trainer.TrainStep with world_size > 1): in direct-gradient mode the autograd
+# Functions write parameter gradients themselves, so they also know WHEN a parameter's gradient is complete: every forward use is
+# counted, every backward that has enqueued its gradient kernels counts down, and at zero the callback fires -- the trainer then
+# all-reduces the bucket the parameter belongs to while the rest of the backward pass is still running.
+_GRAD_TRACK = {'cb': None, 'uses': {}}
+
+
+def set_grad_ready_callback(cb):
+    _GRAD_TRACK['cb'] = cb
+    _GRAD_TRACK['uses'] = {}
+
+
+def reset_grad_tracking():
+    _GRAD_TRACK['uses'] = {}
+
+
+def all_side_streams(device):
+    """Every auxiliary stream created for `device` so far (a collective must be ordered after all of them)."""
+    dev = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    return [s_ for (d, _), s_ in _SIDE.items() if d == dev]
+
+
+def _track_use(*params):
+    if _GRAD_TRACK['cb'] is None or not _DIRECT['on'] or not torch.is_grad_enabled():
+        return
+    uses = _GRAD_TRACK['uses']
+    for p in params:
+        if p is not None and _direct(p):
+            uses[id(p)] = uses.get(id(p), 0) + 1
+
+
+def _track_done(*params):
+    cb = _GRAD_TRACK['cb']
+    if cb is None or not _DIRECT['on']:
+        return
+    uses = _GRAD_TRACK['uses']
+    for p in params:
+        if p is not None and id(p) in uses:
+            uses[id(p)] -= 1
+            if uses[id(p)] == 0:
+                del uses[id(p)]
+                cb(p)
+
+
 def _pad_dim(w, dim, size):
     if w.shape[dim] == size:
         return w
@@ -277,6 +321,7 @@ def _conv_fwd_common(ctx, x, w, b, stride, pad, act, transposed, bias_grad=True)
     ctx.save_for_backward(x, wd, out if act != ACT_NONE else None, pb)
     ctx.params = (w, b)
     ctx.cfg = (stride, pad, act, b is not None and bias_grad, transposed)
+    _track_use(w, b if bias_grad else None)
     return out
 
 
@@ -345,6 +390,7 @@ def _conv_bwd_common(ctx, dout):
                 dw = dwp.permute(3, 2, 0, 1)[:, :Ci].contiguous()
     if has_b and ctx.needs_input_grad[2]:
         db = _bias_grad(dpre, b_param, Co)
+    _track_done(w_param, b_param if ctx.cfg[3] else None)
     return dx, dw, db, None, None, None, None
 
 
@@ -471,6 +517,7 @@ class _ConvX3(Function):
         ctx.params = (w, b)
         ctx.cfg = (stride, pad, act, b is not None and bias_grad, transposed, Ci)
         ctx.parts = (_X3['dgrad'], _X3['wgrad'])
+        _track_use(w, b if bias_grad else None)
         return out
 
     @staticmethod
@@ -547,6 +594,7 @@ class _ConvX3(Function):
                     has_b = False
         if has_b and ctx.needs_input_grad[2]:
             db = _bias_grad(dpre, b_param, Co)
+        _track_done(w_param, b_param if ctx.cfg[3] else None)
         return dx, dw, db, None, None, None, None, None
 
 
@@ -596,6 +644,7 @@ class _Linear(Function):
         ctx.save_for_backward(x, wd, y if act != ACT_NONE else None)
         ctx.params = (w, b)
         ctx.cfg = (act, b is not None)
+        _track_use(w, b)
         return y
 
     @staticmethod
@@ -653,6 +702,7 @@ class _Linear(Function):
                 _call('g2_gemm_f32', dpre, x, None, dw, N, K, M, N, K, K, 1, 0, ACT_NONE, 0)
         if has_b and ctx.needs_input_grad[2]:
             db = _bias_grad(dpre, b_param, N)
+        _track_done(w_param, b_param)
         return dx, dw, db, None
 
 
@@ -704,6 +754,7 @@ class _NormPost(Function):
             _call('g2_norm_apply_f32', y, None, None, out, N, HW, C, 0, post)
             ctx.save_for_backward(y)
             ctx.cfg = (mode, post, groups, half)
+            _track_use(conv_bias)
             return out
         Ns = 1 if mode == NORM_BATCH else N
         sums = None
@@ -718,6 +769,9 @@ class _NormPost(Function):
         ctx.save_for_backward(y, scale, shift, mean, rstd, g0, g1)
         ctx.cfg = (mode, post, groups, half)
         ctx.params = (g0, b0, g1, b1)
+        if _NORM_DIRECT['on']:
+            _track_use(g0, b0, g1, b1)
+        _track_use(conv_bias)
         return out
 
     @staticmethod
@@ -744,6 +798,7 @@ class _NormPost(Function):
                 _call('g2_norm_bwd_apply_bias_f32', y, dout, None, None, None, None, None, None, dy, buf, N, H * W, C, 0, post)
             else:
                 _call('g2_norm_bwd_apply_f32', y, dout, None, None, None, None, None, None, dy, N, H * W, C, 0, post)
+            _track_done(cb)
             return (dy,) + (None,) * 14 + (dcb,)
         y, scale, shift, mean, rstd, g0, g1 = ctx.saved_tensors
         N, H, W, Cy = y.shape
@@ -774,6 +829,7 @@ class _NormPost(Function):
             _call('g2_norm_bwd_apply_bias_f32', y, dout, scale, shift, mean, rstd, m1, m2, dy, buf, N, HW, C, sn, post)
         else:
             _call('g2_norm_bwd_apply_f32', y, dout, scale, shift, mean, rstd, m1, m2, dy, N, HW, C, sn, post)
+        _track_done(*ctx.params, cb)
         return (dy, dg0, db0, dg1, db1) + (None,) * 10 + (dcb,)
 
 
@@ -896,6 +952,8 @@ class _Out1x1(Function):
         ctx.save_for_backward(h, w2, out)
         ctx.params = (w, b)
         ctx.cfg = (nsig, b is not None)
+        if Cin % 32 == 0:
+            _track_use(w, b)
         return out
 
     @staticmethod
@@ -917,6 +975,7 @@ class _Out1x1(Function):
                 w_param.grad.view(nout, Cin).add_(dw4[:nout])
                 if has_b and ctx.needs_input_grad[2]:
                     b_param.grad.add_(_colsum(dpre4, 4, dpre4)[:nout])
+            _track_done(w_param, b_param)
             return dh, None, None, None
         if ctx.needs_input_grad[1]:
             dw4 = _new(h, 4, Cin)

@@ -76,13 +76,19 @@ class FlatArena(object):
             off += (k + a - 1) // a * a
         self.tail = self.flat_g[self.n_pad:]
 
-    def exchange(self, err, kl, world):
-        """ONE all-reduce(sum) of gradients + (err, kl).  Gradients and the tail are left as the SUM over ranks: the
-        optimiser and the GECO kernel apply the 1/world scale."""
+    def exchange(self, err, kl, world, skip=()):
+        """All-reduce(sum) of gradients + (err, kl) -- ONE collective over the whole arena, or, when some buckets were already
+        reduced during the backward pass (`skip`: list of (start, end) element ranges), the remaining ranges.  Gradients and the
+        tail are left as the SUM over ranks: the optimiser and the GECO kernel apply the 1/world scale."""
         self.tail[0].copy_(err)
         self.tail[1].copy_(kl)
         if world > 1:
-            dist.all_reduce(self.flat_g)
+            pos = 0
+            for a, b in sorted(skip):
+                if a > pos:
+                    dist.all_reduce(self.flat_g[pos:a])
+                pos = max(pos, b)
+            dist.all_reduce(self.flat_g[pos:])
 
 
 def shard_batch(x, rank, world):
@@ -105,7 +111,7 @@ class TrainStep(object):
 
     def __init__(self, model, lr=1e-4, img_size=64, g_goal=0.5655, g_lr=1e-5, g_alpha=0.99, g_init=1.0,
                  g_min=1e-10, g_speedup=10.0, geco=True, world_size=1, rank=0, noise_seed=None, optimiser='adam',
-                 beta=0.5, beta_warmup=False, train_iter=500000):
+                 beta=0.5, beta_warmup=False, train_iter=500000, overlap=True):
         if optimiser not in OPTIMISERS:
             raise ValueError('optimiser must be one of %s' % (OPTIMISERS,))
         if getattr(model, 'multi_gpu', False):
@@ -132,9 +138,69 @@ class TrainStep(object):
         self.elbo = torch.zeros((), device=dev)
         self.x_dev = None
         self.graph = None
+        self._tracking = False
         self.launches_per_step = None
         if noise_seed is not None:
             noise.seed_rank(noise_seed, rank, dev)
+        # data-parallel overlap: gradient buckets are all-reduced on a communication stream as soon as the backward pass has
+        # produced them (ops' gradient-ready tracking + autograd hooks), not after the whole backward
+        self.overlap = world_size > 1 and overlap
+        if self.overlap:
+            self._setup_overlap()
+
+    # ------------------------------------------------------------------------------------------ all-reduce overlap
+    def _setup_overlap(self):
+        total = self.n_pad
+        cap = max(total // 4, 1 << 20)                     # about four collectives; a larger parameter is its own bucket
+        self.buckets, self.bucket_of = [], {}
+        start, size, members = 0, 0, []
+        for p, off in zip(self.params, self.arena.offsets):
+            k = (p.numel() + FlatArena.ALIGN - 1) // FlatArena.ALIGN * FlatArena.ALIGN
+            if members and size + k > cap:
+                self.buckets.append((start, off, members))
+                start, size, members = off, 0, []
+            members.append(p)
+            size += k
+        self.buckets.append((start, total, members))
+        for bi, (_, _, members) in enumerate(self.buckets):
+            for p in members:
+                self.bucket_of[id(p)] = bi
+        self.comm = torch.cuda.Stream(device=self.flat_p.device)
+        for p in self.params:        # parameters whose gradient autograd accumulates itself (not written by a direct kernel)
+            p.register_post_accumulate_grad_hook(self._on_grad_ready)
+
+    def _begin_overlap(self):
+        ops.reset_grad_tracking()
+        ops.set_grad_ready_callback(self._on_grad_ready)
+        self._pending = [len(m) for (_, _, m) in self.buckets]
+        self._main = torch.cuda.current_stream()
+        self._reported = set()
+        self._fired = []
+
+    def _on_grad_ready(self, p):
+        if not self._tracking:
+            return
+        if id(p) in self._reported:
+            raise RuntimeError('a parameter reported its gradient complete twice in one step (it is written both by a direct '
+                               'kernel and by autograd): overlap of the gradient all-reduce is unsafe for this model; construct '
+                               'TrainStep(overlap=False)')
+        self._reported.add(id(p))
+        bi = self.bucket_of[id(p)]
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0:
+            a, b, _ = self.buckets[bi]
+            self.comm.wait_stream(self._main)
+            self.comm.wait_stream(torch.cuda.current_stream())      # a side-branch backward reports from its own stream
+            for s_ in ops.all_side_streams(self.flat_p.device):
+                self.comm.wait_stream(s_)
+            with torch.cuda.stream(self.comm):
+                dist.all_reduce(self.flat_g[a:b])
+            self._fired.append((a, b))
+
+    def _end_overlap(self):
+        ops.set_grad_ready_callback(None)
+        torch.cuda.current_stream().wait_stream(self.comm)
+        return list(self._fired)
 
     # ------------------------------------------------------------------------------------------ loss
     def loss_terms(self, losses):
@@ -210,6 +276,10 @@ class TrainStep(object):
         # the arena gradients are pre-zeroed and re-zeroed by the fused optimiser kernel, so the conv / linear kernels may
         # accumulate weight and bias gradients straight into p.grad (no permute copy + AccumulateGrad add per parameter)
         ops.set_direct_grad(True)
+        self._tracking = self.overlap
+        if self.overlap:
+            self._begin_overlap()
+        reduced = ()
         try:
             recon, losses, stats, att, comp = self.model(x)
             err, kl = self.loss_terms(losses)
@@ -218,8 +288,12 @@ class TrainStep(object):
             ops.join_grad_stream(self.flat_p.device)      # parameter-gradient kernels run on a side stream
         finally:
             ops.set_direct_grad(False)
+            self._tracking = False
+            if self.overlap:
+                reduced = self._end_overlap()
         with torch.no_grad():
-            self.arena.exchange(err.detach(), kl.detach(), self.world)      # ONE exchange per step
+            # the buckets already reduced under the backward pass are skipped; the rest + (err, kl) go now
+            self.arena.exchange(err.detach(), kl.detach(), self.world, skip=reduced)
             inv = 1.0 / self.world
             # GECO (or plain bookkeeping) + step counter + elbo in one scalar kernel; then the fused optimiser, which
             # scales the summed gradients by 1/world and re-zeroes them

@@ -55,11 +55,12 @@ def _worker(rank, world, port, name, K, img, x, seed, out):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     import full_size_props as FP
+    import util_parity as U
     from genesis_b200 import ops, trainer
     from test_oracle_golden import build_engine_model
     m, cfg = build_engine_model(name, K, img)
     m = m.cuda().train()
-    ts = trainer.TrainStep(m, world_size=world, rank=rank, geco=False, beta=1.0, noise_seed=7)
+    ts = trainer.TrainStep(m, world_size=world, rank=rank, geco=False, beta=1.0, noise_seed=7, optimiser='sgd', lr=1e-3)
     xs = trainer.shard_batch(x, rank, world).cuda()
     per = xs.shape[0]
     rows = list(range(rank * per, (rank + 1) * per))
@@ -83,7 +84,19 @@ def _worker(rank, world, port, name, K, img, x, seed, out):
     for _ in range(2):
         ts.step(xs)
     torch.cuda.synchronize()
-    out[rank] = (local, summed, ts.flat_p.detach().clone().cpu(), eps, float(ts.elbo))
+    # the same two steps with the gradient all-reduce NOT overlapped with the backward pass (one collective after it): the
+    # bucketed, overlapped exchange must give the same parameters
+    from genesis_b200 import noise
+    m2, _ = build_engine_model(name, K, img)
+    ts2 = trainer.TrainStep(m2.cuda().train(), world_size=world, rank=rank, geco=False, beta=1.0, noise_seed=7, overlap=False,
+                            optimiser='sgd', lr=1e-3)
+    torch.randn(4, device='cuda')
+    for _ in range(2):
+        ts2.step(xs)
+    torch.cuda.synchronize()
+    same = U.rel_l2(ts2.flat_p, ts.flat_p)
+    fired = len(ts._fired)
+    out[rank] = (local, summed, ts.flat_p.detach().clone().cpu(), eps, float(ts.elbo), same, fired, len(ts.buckets))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -96,7 +109,9 @@ def test_two_rank_allreduced_gradient_equals_single_process(name, K, img, B, gen
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), name, K, img, x, 5, out), nprocs=2, join=True)
-    (l0, s0, p0, e0, elbo0), (l1, s1, p1, e1, elbo1) = out[0], out[1]
+    (l0, s0, p0, e0, elbo0, same0, fired0, nb0), (l1, s1, p1, e1, elbo1, same1, fired1, nb1) = out[0], out[1]
+    assert same0 < 1e-5 and same1 < 1e-5, (same0, same1)      # overlapped == non-overlapped exchange
+    assert fired0 >= 1 and fired0 == fired1, (fired0, nb0)   # at least one bucket went out under the backward pass
     assert torch.equal(s0, s1)                                   # one all-reduce: both ranks hold the same summed gradient
     assert torch.equal(p0, p1)                                   # ... and stay bit-identical through optimiser steps
     assert elbo0 == elbo1                                        # the ELBO / GECO inputs travel in the arena tail

@@ -100,8 +100,10 @@ def test_capture_does_not_train_and_replay_equals_eager():
     restored), so a captured TrainStep and an eager one started from the same state stay together."""
     from genesis_b200 import noise
     x = torch.from_numpy(synth.multid(4, 64, 1)[0]).cuda()
-    ts_e, m_e = _make()
-    ts_g, m_g = _make()
+    # SGD: parameter differences stay proportional to gradient differences (Adam would turn the float-atomic noise of a
+    # numerically-zero gradient into an O(lr) step)
+    ts_e, m_e = _make('sgd')
+    ts_g, m_g = _make('sgd')
     noise.seed_rank(3, 0, 'cuda')
     p_before = ts_g.flat_p.clone()
     bufs_before = [b.clone() for b in m_g.buffers()]
@@ -120,7 +122,7 @@ def test_capture_does_not_train_and_replay_equals_eager():
     assert len({float(e) for e in e_g}) == 3
     for a, b in zip(e_g, e_e):
         assert float(a) == pytest.approx(float(b), rel=2e-4)
-    assert U.rel_l2(ts_g.flat_p, ts_e.flat_p) < 1e-3
+    assert U.rel_l2(ts_g.flat_p, ts_e.flat_p) < 1e-4
 
 
 def test_plain_beta_objective_and_warmup():
