@@ -200,7 +200,7 @@ def run_engine(args):
     torch.manual_seed(0)
     model = plugin.load(cfg).to(dev).train()
     # same parameters on every rank (manual_seed(0) above), independent eps / IC-SBP seed noise per rank (noise_seed + rank)
-    ts = trainer.TrainStep(model, lr=1e-4, img_size=IMG, world_size=world, rank=rank, noise_seed=1234)
+    ts = trainer.TrainStep(model, lr=1e-4, img_size=IMG, world_size=world, rank=rank, noise_seed=1234, overlap=not args.no_overlap)
     lib = _lib.lib()
 
     n_in = 4
@@ -322,7 +322,9 @@ def run_engine(args):
                        'l2': 'per-step working set (activations > 4 GB) exceeds the 126 MB L2; inputs rotate over %d batches' % n_in,
                        'step_tflops_algorithmic': step_tf, 'last_elbo': last, 'cuda_graph': graphed,
                        'precision': 'tf32 tensor-core operands, fp32 accumulate / storage',
-                       'streams': 'one captured graph; prior/KL branch and parameter-gradient kernels on side streams'},
+                       'streams': 'one captured graph; prior/KL branch and parameter-gradient kernels on side streams',
+                       'allreduce': ('none (1 GPU)' if world == 1 else 'single collective after backward' if args.no_overlap else
+                                     '%d gradient buckets all-reduced under the backward pass + 1 tail collective' % len(ts.buckets))},
             'e2e': {'value': imgs / (ms_e2e * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': B_PER_GPU * 3 * IMG * IMG * 4,
                     'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': launches,
@@ -350,6 +352,8 @@ def main():
     ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
     ap.add_argument('--no-cpu-baseline', dest='no_cpu_baseline', action='store_true')
     ap.add_argument('--no-graph', dest='no_graph', action='store_true')
+    ap.add_argument('--no-overlap', dest='no_overlap', action='store_true',
+                    help='one gradient all-reduce after the backward pass instead of bucketed collectives under it (A/B)')
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     args = ap.parse_args()
     select_workload(args.workload)
