@@ -41,6 +41,7 @@ struct P {
     int tiles_h, tiles_w, dh_min, dw_min, span_h;
     int Ho, Wo, Co, os, ph, pw;
     int ntaps, cblocks, act, tmem_cols, a_bytes, stages, epi;
+    int x3, w_lo_off;                   // 3xTF32 mode (see conv_halo_kernel); channel offset of the w_lo half in the weight pack
     long long* dbg;                     // optional per-CTA phase timestamps [grid][8] (scripts/conv_bench.py --timeline)
     int toff[MAX_TAPS];
     short widx[MAX_TAPS];
@@ -160,6 +161,8 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
     uint64_t* emptyB = fullB + MAX_STAGES;
     uint64_t* accf = emptyB + MAX_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accf + 1);
+    uint64_t* p12 = accf + 2;                                   // 3xTF32: passes 1+2 of a channel block retired (window may be rewritten)
+    uint64_t* loready = accf + 3;                               // 3xTF32: the window now holds lo = x - trunc(x)
     float* sBias = reinterpret_cast<float*>(fullA) + 96;        // 384 B past the start of the barrier block
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -188,6 +191,8 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
             mbar_init(emptyA, 1);
             for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
             mbar_init(accf, 1);
+            mbar_init(p12, 1);
+            mbar_init(loready, 128);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -199,6 +204,12 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
     fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (dbg && threadIdx.x == 32) dbg[1] = clock64();          // prologue done
+    // 3xTF32 mode (p.x3): the window holds RAW fp32 activations (tensor map of type FLOAT32: no TMA rounding).  The tensor core
+    // truncates fp32 operand bits to TF32 (tests/test_umma_layouts_gpu.py::test_tf32_mma_operand_conversion...), so the raw
+    // window IS x_hi = trunc(x).  Per channel block: pass 1 (x_hi, w_hi) and pass 2 (x_hi, w_lo) issue from the raw window; the
+    // four epilogue warps then rewrite it IN PLACE to x_lo = x - trunc(x) (exact in fp32) and pass 3 (x_lo, w_hi) follows:
+    // a * b ~= a_hi b_hi + a_hi b_lo + a_lo b_hi at 2^-21 relative error, with no extra shared memory and no split pass over HBM.
+    const int wtiles = p.x3 ? 3 * p.ntaps : p.ntaps;           // weight tiles per channel block, in issue order
 
     if (warp == 0) {
         // ---- TMA producer: the whole warp walks the schedule (uniform control flow), one elected lane issues
@@ -214,12 +225,14 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
                 }
             }
             __syncwarp();
-            for (int tap = 0; tap < p.ntaps; ++tap) {
+            for (int wt = 0; wt < wtiles; ++wt) {
+                const int tap = wt % p.ntaps;
+                const int wc = cb * 32 + (wt / p.ntaps == 1 ? p.w_lo_off : 0);     // x3: taps with w_hi, then w_lo, then w_hi again
                 const int s = bi;
                 mbar_wait(&emptyB[s], bph ^ 1u);
                 if (elect_one()) {
                     mbar_expect_tx(&fullB[s], B_BYTES);
-                    tma_load_3d(sB + s * B_BYTES, &maps.b, &fullB[s], cb * 32, n0c, p.widx[tap]);
+                    tma_load_3d(sB + s * B_BYTES, &maps.b, &fullB[s], wc, n0c, p.widx[tap]);
                 }
                 __syncwarp();
                 if (++bi == STAGES) { bi = 0; bph ^= 1u; }
@@ -234,7 +247,15 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
         uint32_t bph = 0;
         for (int cb = 0; cb < p.cblocks; ++cb) {
             int waited = 0;
-            for (int tap = 0; tap < p.ntaps; ++tap) {
+            for (int wt = 0; wt < wtiles; ++wt) {
+                const int tap = wt % p.ntaps;
+                if (p.x3 && wt == 2 * p.ntaps) {
+                    // passes 1 + 2 issued: signal their retirement, then wait until the window has been rewritten to x_lo
+                    if (elect_one()) commit(p12);
+                    __syncwarp();
+                    mbar_wait(loready, (uint32_t)cb & 1u);
+                    fence_after();
+                }
                 const int s = bi;
                 mbar_wait(&fullB[s], bph);
                 if (dbg && lane == 0 && cb == 0 && tap < 28) dbg[8 + 2 * tap] = clock64();          // weight tile of this tap landed
@@ -246,7 +267,7 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
                 fence_after();
                 if (dbg && lane == 0 && cb == 0 && tap == 0) dbg[2] = clock64();      // first weight tile + its activation chunks landed
                 const uint32_t alo = a0 + (uint32_t)toff * 8u;
-                const uint32_t first = (cb | tap) != 0 ? 1u : 0u;
+                const uint32_t first = (cb | wt) != 0 ? 1u : 0u;
                 if (elect_one()) {
                     for (int t = 0; t < m_tiles; ++t) {
                         const uint64_t adesc = hi | (uint64_t)((alo + (uint32_t)t * 1024u) & 0x3FFFu);
@@ -270,6 +291,27 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
         if (dbg && lane == 0) dbg[3] = clock64();       // last MMA issued
     } else {
         // ---- epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31
+        if (p.x3) {
+            // 3xTF32: between pass 2 and pass 3 of every channel block rewrite the window in place, x -> x - trunc(x)
+            const int tid = threadIdx.x - 64;
+            const int n4 = nch * p.ch_pix * 8;                  // float4s of the loaded window (128 B = 8 float4 per position)
+            for (int cb = 0; cb < p.cblocks; ++cb) {
+                const uint32_t ph = (uint32_t)cb & 1u;
+                for (int j = 0; j < nch; ++j) mbar_wait(&fullA[j], ph);      // the TMA writes of this channel block are visible
+                mbar_wait(p12, ph);                                          // ... and no MMA reads the raw window any more
+                float4* w4 = reinterpret_cast<float4*>(sA);
+                for (int i = tid; i < n4; i += 128) {
+                    float4 v = w4[i];
+                    v.x -= __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                    v.y -= __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                    v.z -= __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                    v.w -= __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                    w4[i] = v;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads
+                mbar_arrive(loready);
+            }
+        }
         mbar_wait(accf, 0);
         fence_after();
         if (dbg && threadIdx.x == 64) dbg[4] = clock64();       // accumulators complete
@@ -531,11 +573,12 @@ static PFN_cuTensorMapEncodeTiled get_encode() {
 }
 
 static bool encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                   const cuuint32_t* box) {
+                   const cuuint32_t* box, bool raw_fp32 = false) {
     PFN_cuTensorMapEncodeTiled enc = get_encode();
     if (!enc) return false;
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, es,
+    // TFLOAT32: the TMA rounds fp32 to TF32 on the way in; FLOAT32 (3xTF32 mode): the raw bits land and the tensor core truncates
+    CUresult r = enc(m, raw_fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
@@ -804,9 +847,25 @@ int g2_conv_halo_supported(int N, int Hi, int Wi, int Ci, int Ho, int Wo, int Co
     return 1;
 }
 
+static int conv_halo_impl(const float* in, const float* w, const float* bias, float* out, int N, int Hi, int Wi, int Ci,
+                          int Ho, int Wo, int Co, int R, int S, int stride, int pad, int mode, int act, int x3, cudaStream_t stream);
+
 // Same contract as g2_conv_igemm_tf32 for the problems g2_conv_halo_supported accepts.
 int g2_conv_halo_tf32(const float* in, const float* w, const float* bias, float* out, int N, int Hi, int Wi, int Ci,
                       int Ho, int Wo, int Co, int R, int S, int stride, int pad, int mode, int act, cudaStream_t stream) {
+    return conv_halo_impl(in, w, bias, out, N, Hi, Wi, Ci, Ho, Wo, Co, R, S, stride, pad, mode, act, 0, stream);
+}
+
+// 3xTF32 form of the same convolution (fp32-level accuracy on the tensor cores): `w` is the pack [R*S][Co][2*Ci] whose channel
+// halves are w_hi = the weights as exact TF32 values and w_lo = w - w_hi; `in` is the plain fp32 activation.  The kernel issues
+// (x_hi, w_hi), (x_hi, w_lo), rewrites its activation window in place to x_lo = x - trunc(x) and issues (x_lo, w_hi).
+int g2_conv_halo_x3_tf32(const float* in, const float* w, const float* bias, float* out, int N, int Hi, int Wi, int Ci,
+                         int Ho, int Wo, int Co, int R, int S, int stride, int pad, int mode, int act, cudaStream_t stream) {
+    return conv_halo_impl(in, w, bias, out, N, Hi, Wi, Ci, Ho, Wo, Co, R, S, stride, pad, mode, act, 1, stream);
+}
+
+static int conv_halo_impl(const float* in, const float* w, const float* bias, float* out, int N, int Hi, int Wi, int Ci,
+                          int Ho, int Wo, int Co, int R, int S, int stride, int pad, int mode, int act, int x3, cudaStream_t stream) {
     using namespace halo;
     G2_CHECK_ARG(in && w && out && N > 0);
     G2_CHECK_ARG((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
@@ -820,8 +879,9 @@ int g2_conv_halo_tf32(const float* in, const float* w, const float* bias, float*
     Maps maps;
     memset(&maps, 0, sizeof(maps));
     {
-        cuuint64_t dims[3] = {(cuuint64_t)Ci, (cuuint64_t)Co, (cuuint64_t)(R * S)};
-        cuuint64_t str[2] = {(cuuint64_t)Ci * 4, (cuuint64_t)Ci * Co * 4};
+        const int Cw = x3 ? 2 * Ci : Ci;                 // channels of the weight pack (3xTF32: [w_hi | w_lo])
+        cuuint64_t dims[3] = {(cuuint64_t)Cw, (cuuint64_t)Co, (cuuint64_t)(R * S)};
+        cuuint64_t str[2] = {(cuuint64_t)Cw * 4, (cuuint64_t)Cw * Co * 4};
         cuuint32_t box[3] = {32, (uint32_t)BN, 1};
         if (!encode(&maps.b, w, 3, dims, str, box)) return G2_ERR_UNSUPPORTED;
     }
@@ -832,7 +892,7 @@ int g2_conv_halo_tf32(const float* in, const float* w, const float* bias, float*
         Geo g;
         bool resident = false;
         int pstages = 0;
-        const bool use_p = persistent_geo(N, t, Ci, Co, BN, sh, sw, &g, &pstages, &resident);
+        const bool use_p = !x3 && persistent_geo(N, t, Ci, Co, BN, sh, sw, &g, &pstages, &resident);
         if (!use_p && !pick_geo(N, t.Hv, t.Wv, sh, sw, t.n, Ci / 32, BN, stages_of(BN, t.n, Ci / 32), &g)) return G2_ERR_UNSUPPORTED;
         P p;
         memset(&p, 0, sizeof(p));
@@ -841,6 +901,7 @@ int g2_conv_halo_tf32(const float* in, const float* w, const float* bias, float*
         p.tiles_h = g.tiles_h; p.tiles_w = g.tiles_w; p.dh_min = dh_min; p.dw_min = dw_min; p.span_h = sh;
         p.Ho = Ho; p.Wo = Wo; p.Co = Co; p.os = t.os; p.ph = t.ph; p.pw = t.pw;
         p.ntaps = t.n; p.cblocks = Ci / 32; p.act = act; p.a_bytes = g.a_bytes; p.stages = stages_of(BN, t.n, Ci / 32); p.dbg = g_dbg; p.epi = epi_mode();
+        p.x3 = x3; p.w_lo_off = Ci;
         int cols = 32;
         while (cols < g.m * BN) cols <<= 1;
         p.tmem_cols = cols;
@@ -852,7 +913,7 @@ int g2_conv_halo_tf32(const float* in, const float* w, const float* bias, float*
             cuuint64_t dims[4] = {(cuuint64_t)Ci, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)N};
             cuuint64_t str[3] = {(cuuint64_t)Ci * 4, (cuuint64_t)Wi * Ci * 4, (cuuint64_t)Hi * Wi * Ci * 4};
             cuuint32_t box[4] = {32, (uint32_t)p.Wp, (uint32_t)g.ch_rows, (uint32_t)g.TNB};
-            if (!encode(&maps.a, in, 4, dims, str, box)) return G2_ERR_UNSUPPORTED;
+            if (!encode(&maps.a, in, 4, dims, str, box, x3 != 0)) return G2_ERR_UNSUPPORTED;
         }
         dim3 grid((unsigned)(((N + g.TNB - 1) / g.TNB) * g.tiles_h * g.tiles_w), (unsigned)(Co / BN), 1);
         int rc;

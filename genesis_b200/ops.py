@@ -300,10 +300,19 @@ def _conv_fwd_common(ctx, x, w, b, stride, pad, act, transposed, bias_grad=True)
         # UNet models come from the forward rounding alone, so the backward contractions below stay plain TF32.
         wp = _pad_dim(wd, 0 if transposed else 1, Cx)
         w_hi, w_lo = _w_hi_lo(wp)
-        w3 = torch.cat([w_hi, w_lo, w_hi], dim=0 if transposed else 1)
-        pa3 = _new(x, R * S, Co, 3 * Cx)
-        _call('g2_pack_conv_weight_f32', _c(w3), pa3, None, Co, 3 * Cx, 3 * Cx, R * S, 1 if transposed else 0)
-        _conv_tc(_split(x, Cx, 0), pa3, b, out, (N, H, W, 3 * Cx, Ho, Wo, Co), R, S, stride, pad, mode_f, act)
+        cin_dim = 0 if transposed else 1
+        if _lib.lib().query('g2_conv_halo_supported', N, H, W, Cx, Ho, Wo, Co, R, S, stride, pad, mode_f) == 1:
+            # in-kernel split (igemm_halo.cu): the kernel derives x_lo from its resident window -- no [hi|hi|lo] copy of the
+            # activation in HBM; only the (tiny) weight is split here
+            pa2 = _new(x, R * S, Co, 2 * Cx)
+            _call('g2_pack_conv_weight_f32', _c(torch.cat([w_hi, w_lo], dim=cin_dim)), pa2, None, Co, 2 * Cx, 2 * Cx, R * S,
+                  1 if transposed else 0)
+            _call('g2_conv_halo_x3_tf32', x, pa2, b, out, N, H, W, Cx, Ho, Wo, Co, R, S, stride, pad, mode_f, act)
+        else:
+            w3 = torch.cat([w_hi, w_lo, w_hi], dim=cin_dim)
+            pa3 = _new(x, R * S, Co, 3 * Cx)
+            _call('g2_pack_conv_weight_f32', _c(w3), pa3, None, Co, 3 * Cx, 3 * Cx, R * S, 1 if transposed else 0)
+            _conv_tc(_split(x, Cx, 0), pa3, b, out, (N, H, W, 3 * Cx, Ho, Wo, Co), R, S, stride, pad, mode_f, act)
         if ctx.needs_input_grad[0] and _tc_ok(N, Ho, Wo, Co, H, W, Cx, R, S, stride, pad, mode_d):
             pb = _new(x, R * S, Cx, Co)
             _call('g2_pack_conv_weight_f32', _c(wd), _new(x, R * S, Co, Cx), pb, Co, Ci, Cx, R * S, 1 if transposed else 0)

@@ -10,7 +10,7 @@ from . import _lib
 def algo_cost(name, a):
     """(flops, bytes) a call must perform / move at minimum, from its arguments (pointer args included)."""
     f = b = 0
-    if name in ('g2_conv_igemm_f32', 'g2_conv_igemm_tf32', 'g2_conv_halo_tf32'):
+    if name in ('g2_conv_igemm_f32', 'g2_conv_igemm_tf32', 'g2_conv_halo_tf32', 'g2_conv_halo_x3_tf32'):
         o = 5 if name.endswith('f32') and not name.endswith('tf32') else 4
         N, Hi, Wi, Ci, Ho, Wo, Co, R, S, stride, pad, mode = a[o:o + 12]
         if mode == 0:

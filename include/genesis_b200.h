@@ -238,6 +238,12 @@ int g2_gemm_tf32_ws(const float* A, const float* W, const float* bias, float* C,
  * g2_conv_halo_plan fills plan[96] with the launch plan of sub-pixel class `cls` (host-only query, no launch):
  * {nclasses, TH, TNB, RH, chunk_rows, chunks, m_tiles, a_bytes, tiles_h, Wp, dh_min, dw_min, os, ph, pw, Hv, Wv,
  *  ntaps, BN, smem_bytes}, plan[32+i] = flat row offset of tap i, plan[64+i] = its weight index. */
+/* 3xTF32 form of g2_conv_halo_tf32 (same problems, fp32-level accuracy on the tensor cores): `w` is the pack [R*S][Co][2*Ci]
+ * with channel halves w_hi (the weights as exact TF32 values) | w_lo = w - w_hi; `in` is the plain fp32 activation.  Per channel
+ * block the kernel issues (x_hi, w_hi) and (x_hi, w_lo) from the raw window (the tensor core truncates fp32 operand bits to TF32),
+ * rewrites the window in place to x_lo = x - trunc(x) and issues (x_lo, w_hi): no split pass over HBM, no extra shared memory. */
+int g2_conv_halo_x3_tf32(const float* in, const float* w, const float* bias, float* out, int N, int Hi, int Wi, int Ci,
+                         int Ho, int Wo, int Co, int R, int S, int stride, int pad, int mode, int act, g2_stream_t stream);
 int g2_conv_halo_enable(int on);
 /* debug: per-CTA clock64() phase timestamps of subsequent halo launches into a device buffer [CTAs][64] (NULL = off) */
 int g2_conv_halo_debug(int64_t* buf);

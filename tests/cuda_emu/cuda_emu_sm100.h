@@ -150,12 +150,15 @@ static inline void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uin
     const bool a_mn = (idesc >> 15) & 1u, b_mn = (idesc >> 16) & 1u;
     const uint32_t col0 = tmem_d & 0xFFFFu;
     if (M != 128 || (tmem_d >> 16) != 0 || col0 + (uint32_t)N > 512u) { std::fprintf(stderr, "emu: bad MMA shape / TMEM address\n"); std::abort(); }
+    // kind::tf32 TRUNCATES the fp32 bits it finds in shared memory (low 13 mantissa bits ignored) -- measured on a B200,
+    // tests/test_umma_layouts_gpu.py::test_tf32_mma_operand_conversion_of_raw_fp32_bits; the in-kernel 3xTF32 split relies on it
+    auto tf32 = [](float v) { uint32_t b; std::memcpy(&b, &v, 4); b &= 0xFFFFE000u; std::memcpy(&v, &b, 4); return v; };
     float bt[256][8];
     for (int n = 0; n < N; ++n)
-        for (int k = 0; k < 8; ++k) bt[n][k] = operand(bdesc, b_mn, n, k);
+        for (int k = 0; k < 8; ++k) bt[n][k] = tf32(operand(bdesc, b_mn, n, k));
     for (int m = 0; m < 128; ++m) {
         float at[8];
-        for (int k = 0; k < 8; ++k) at[k] = operand(adesc, a_mn, m, k);
+        for (int k = 0; k < 8; ++k) at[k] = tf32(operand(adesc, a_mn, m, k));
         for (int n = 0; n < N; ++n) {
             float s = accumulate ? tmem[m][col0 + n] : 0.f;
             for (int k = 0; k < 8; ++k) s += at[k] * bt[n][k];

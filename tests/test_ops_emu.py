@@ -160,14 +160,16 @@ def test_conv_activation_bias_gradient_fused(ops):
 
 
 @pytest.mark.parametrize('transposed', [False, True])
-def test_precise_conv_3xtf32_plumbing(ops, transposed):
-    """ops.precise(): the forward contraction as ONE 3x-longer tensor-core reduction ([x_hi|x_hi|x_lo] against [w_hi|w_lo|w_hi]),
-    backward on the plain path -- operand split, channel-concatenated packs and the tcgen05 kernels under the functional
-    emulation, against torch.  (Accuracy versus plain TF32 is a property of the hardware rounding: measured on the B200,
-    profiles/r02_parity_x3.txt.)"""
+@pytest.mark.parametrize('Hh', [16, 8])
+def test_precise_conv_3xtf32(ops, transposed, Hh):
+    """ops.precise(): the forward contraction as 3xTF32 -- (x_hi, w_hi) + (x_hi, w_lo) + (x_lo, w_hi) -- at fp32-level accuracy,
+    against torch in float64, with the plain TF32 result of the same kernel as the contrast.  16x16 maps take the halo kernel's
+    in-kernel split (the raw window is x_hi because the tensor core truncates; the epilogue warps rewrite it in place to x_lo
+    between the passes; only the weight is split on the host); 8x8 maps (< 256 pixels: tile kernel) take the [hi|hi|lo]
+    channel-concatenated form.  The emulation truncates MMA operands as the hardware was measured to do."""
     ops.set_precision('tf32')
     torch.manual_seed(8)
-    N, Hh, Ci, Co = 2, 16, 32, 32
+    N, Ci, Co = 2, 32, 32
     x = torch.randn(N, Hh, Hh, Ci, requires_grad=True)
     w = (0.2 * torch.randn(Ci, Co, 3, 3) if transposed else 0.2 * torch.randn(Co, Ci, 3, 3)).requires_grad_(True)
     b = torch.randn(Co, requires_grad=True)
@@ -182,14 +184,21 @@ def test_precise_conv_3xtf32_plumbing(ops, transposed):
             out = fn_o(x, w, b, 1, 1, 'relu')
     finally:
         L._LIB.call = orig
-    convs = [a for n, a in calls if n in ('g2_conv_halo_tf32', 'g2_conv_igemm_tf32')]
-    assert len(convs) == 1 and convs[0][7] == 3 * Ci                      # one contraction over the 3x reduction
-    assert sum(n == 'g2_split_tf32_f32' for n, _ in calls) == 3            # x -> [hi|hi|lo], w -> hi, lo
-    ref = fn_r(x, w, b, 1, 1, 'relu')
-    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
-    g = torch.randn_like(ref)
-    for a, c in zip(grads(out, [x, w, b], g), grads(ref, [x, w, b], g)):
-        torch.testing.assert_close(a, c, rtol=5e-3, atol=5e-3)            # backward = plain TF32 tensor-core path
+    names = [n for n, _ in calls]
+    if Hh == 16:
+        assert names.count('g2_conv_halo_x3_tf32') == 1 and names.count('g2_split_tf32_f32') == 2      # only w -> hi, lo
+    else:
+        convs = [a for n, a in calls if n in ('g2_conv_halo_tf32', 'g2_conv_igemm_tf32')]
+        assert len(convs) == 1 and convs[0][7] == 3 * Ci and names.count('g2_split_tf32_f32') == 3
+    plain = fn_o(x, w, b, 1, 1, 'relu')
+    ref = fn_r(x.double(), w.double(), b.double(), 1, 1, 'relu')
+    e_x3 = (out.double() - ref).abs().max().item()
+    e_plain = (plain.double() - ref).abs().max().item()
+    assert e_x3 < 2e-5 and e_plain > 20 * e_x3, (e_x3, e_plain)        # 3xTF32 is >= 20x closer than plain TF32
+    g = torch.randn_like(out)
+    ref32 = fn_r(x, w, b, 1, 1, 'relu')
+    for a, c in zip(grads(out, [x, w, b], g), grads(ref32, [x, w, b], g)):
+        torch.testing.assert_close(a, c, rtol=2e-2, atol=2e-2)            # backward = plain TF32 tensor-core path
 
 
 def test_split_tf32_kernel_is_exact(ops):

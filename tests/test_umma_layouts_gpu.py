@@ -73,3 +73,24 @@ def test_mn_major_tf32_needs_the_32b_base_layout():
     b2 = np.concatenate([image(Bb[j], 4, 7) for j in range(N // 32)])
     got = probe(a2, b2, desc(tile, 1024, 2), desc(tile, 1024, 2), idesc(N, 1, 1), npix // 8, 1024, 1024)
     assert np.count_nonzero(got) == 0          # documented behaviour: layout type 2 + MN-major TF32 -> zeros
+
+
+def test_tf32_mma_operand_conversion_of_raw_fp32_bits():
+    """What tcgen05.mma kind::tf32 does with fp32 bit patterns in shared memory whose low 13 mantissa bits are set (operands the
+    TMA did not round): TRUNCATION (the low bits are ignored) or round-to-nearest.  The in-kernel 3xTF32 split relies on the
+    answer (lo = x - hi must use the same hi the tensor core uses); recorded in profiles/r02_tf32_operand_conversion.txt."""
+    ulp = 2.0 ** -10                                    # TF32 spacing in [1, 2)
+    A = np.zeros((128, 32), np.float32)
+    for r in range(128):
+        k = r % 8
+        A[r, 0] = (1.0 + k * ulp / 8.0) * (-1.0 if (r // 8) % 2 else 1.0)     # 1 + k/8 ulp, both signs
+    B = np.zeros((N, 32), np.float32)
+    B[0, 0] = 1.0
+    got = probe(image(A, 4, 7), image(B, 4, 7), desc(16, 1024, 2), desc(16, 1024, 2), idesc(N), 4, 32, 32)[:, 0]
+    trunc = np.sign(A[:, 0]) * 1.0
+    rn = np.sign(A[:, 0]) * np.where((np.arange(128) % 8) >= 4, 1.0 + ulp, 1.0)
+    is_trunc = np.array_equal(got, trunc)
+    is_rn = np.allclose(got, rn, atol=0) or np.array_equal(np.where((np.arange(128) % 8) == 4, trunc, got),
+                                                           np.where((np.arange(128) % 8) == 4, trunc, rn))
+    print('TF32_OPERAND_CONVERSION', 'truncate' if is_trunc else 'round-to-nearest' if is_rn else 'other', got[:8].tolist())
+    assert is_trunc or is_rn, got[:16]
