@@ -146,6 +146,14 @@ __device__ __forceinline__ void epilogue_bulk(const P& p, uint32_t tmem_base, co
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all rows written before the CTA retires
 }
 
+// 3xTF32 low part of a raw fp32 operand whose high part is what the tensor core sees, trunc(x): x - trunc(x) is exact in fp32
+// (13 significant bits); it is then rounded to NEAREST TF32 here, because the tensor core would truncate it (a biased 2^-20
+// relative error of the product instead of an unbiased 2^-21).
+__device__ __forceinline__ float lo_tf32(float x) {
+    const float lo = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    return __uint_as_float((__float_as_uint(lo) + 0x1000u) & 0xFFFFE000u);
+}
+
 template <int BN>
 __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P p) {
     constexpr int B_BYTES = BN * 128;
@@ -302,10 +310,7 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
                 float4* w4 = reinterpret_cast<float4*>(sA);
                 for (int i = tid; i < n4; i += 128) {
                     float4 v = w4[i];
-                    v.x -= __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-                    v.y -= __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-                    v.z -= __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-                    v.w -= __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                    v.x = lo_tf32(v.x); v.y = lo_tf32(v.y); v.z = lo_tf32(v.z); v.w = lo_tf32(v.w);
                     w4[i] = v;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads

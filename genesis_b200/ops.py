@@ -301,13 +301,33 @@ def _conv_fwd_common(ctx, x, w, b, stride, pad, act, transposed, bias_grad=True)
         wp = _pad_dim(wd, 0 if transposed else 1, Cx)
         w_hi, w_lo = _w_hi_lo(wp)
         cin_dim = 0 if transposed else 1
-        if _lib.lib().query('g2_conv_halo_supported', N, H, W, Cx, Ho, Wo, Co, R, S, stride, pad, mode_f) == 1:
+        if _X3_INKERNEL and _lib.lib().query('g2_conv_halo_supported', N, H, W, Cx, Ho, Wo, Co, R, S, stride, pad, mode_f) == 1:
             # in-kernel split (igemm_halo.cu): the kernel derives x_lo from its resident window -- no [hi|hi|lo] copy of the
             # activation in HBM; only the (tiny) weight is split here
             pa2 = _new(x, R * S, Co, 2 * Cx)
             _call('g2_pack_conv_weight_f32', _c(torch.cat([w_hi, w_lo], dim=cin_dim)), pa2, None, Co, 2 * Cx, 2 * Cx, R * S,
                   1 if transposed else 0)
             _call('g2_conv_halo_x3_tf32', x, pa2, b, out, N, H, W, Cx, Ho, Wo, Co, R, S, stride, pad, mode_f, act)
+            if _X3_DEBUG:       # cross-check against the pre-split route (scripts/parity_report.py, G2_X3_DEBUG=1)
+                ref = torch.empty_like(out)
+                pa3 = _new(x, R * S, Co, 3 * Cx)
+                _call('g2_pack_conv_weight_f32', _c(torch.cat([w_hi, w_lo, w_hi], dim=cin_dim)), pa3, None, Co, 3 * Cx, 3 * Cx,
+                      R * S, 1 if transposed else 0)
+                _conv_tc(_split(x, Cx, 0), pa3, b, ref, (N, H, W, 3 * Cx, Ho, Wo, Co), R, S, stride, pad, mode_f, act)
+                d = (out.double() - ref.double())
+                msg = 'in-kernel vs pre-split rel-L2 %.2e' % (d.norm().item() / max(ref.double().norm().item(), 1e-30))
+                if not transposed and act == ACT_NONE:
+                    import torch.nn.functional as _F
+                    t64 = _F.conv2d(x[..., :Ci].permute(0, 3, 1, 2).double(), wd.double(), None if b is None else b.detach().double(),
+                                    stride=stride, padding=pad).permute(0, 2, 3, 1)
+                    nn = t64.norm().item()
+                    msg += ' | vs fp64: in-kernel %.2e pre-split %.2e' % ((out.double() - t64).norm().item() / nn,
+                                                                          (ref.double() - t64).norm().item() / nn)
+                    pa1 = _new(x, R * S, Co, Cx)
+                    _call('g2_pack_conv_weight_f32', _c(wp), pa1, None, Co, Cx, Cx, R * S, 0)
+                    _conv_tc(x, pa1, b, ref, (N, H, W, Cx, Ho, Wo, Co), R, S, stride, pad, mode_f, act)
+                    msg += ' plain-tf32 %.2e' % ((ref.double() - t64).norm().item() / nn)
+                print('X3DEBUG', (N, H, W, Cx, Ho, Wo, Co, R, S, stride, pad, mode_f, act), msg)
         else:
             w3 = torch.cat([w_hi, w_lo, w_hi], dim=cin_dim)
             pa3 = _new(x, R * S, Co, 3 * Cx)
@@ -449,6 +469,8 @@ def conv_transpose2d(x, w, b=None, stride=1, pad=0, act=None, bias_grad=True):
 import contextlib as _contextlib
 
 _X3 = {'on': False, 'fwd': True, 'dgrad': False, 'wgrad': False}     # measured: forward rounding is what matters
+_X3_INKERNEL = os.environ.get('G2_X3_INKERNEL', '1') != '0'          # halo kernel derives x_lo from its resident window
+_X3_DEBUG = os.environ.get('G2_X3_DEBUG', '0') == '1'
 
 
 @_contextlib.contextmanager

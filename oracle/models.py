@@ -264,6 +264,25 @@ def v2_decoder(z, P, img_size):
     return F.conv2d(h, P['decoder_module.13.weight'], P['decoder_module.13.bias'])
 
 
+def _seed_kink_margin(pre, idxs):
+    """Test conditioning guard (not part of the reference): the smallest |pre-ReLU| value of seg_head over all channels of the
+    IC-SBP seed pixels.  Every pixel's distance to a seed depends on the seed pixel's embedding, so its gradient is
+    concentrated there; with a channel within rounding of the ReLU kink the gradient is discontinuous and two correct
+    implementations can disagree by > 10 % on seg_head.0.weight / seg_head.1.bias."""
+    if not idxs:
+        return float('inf')
+    B, C = pre.shape[0], pre.shape[1]
+    flat = pre.detach().reshape(B, C, -1)
+    m = float('inf')
+    for idx in idxs:
+        idx = idx.reshape(-1).long()
+        if idx.numel() != B:
+            continue
+        v = flat[torch.arange(B), :, idx]
+        m = min(m, v.abs().min().item())
+    return m
+
+
 def genesisv2_forward(P, x, tape, cfg, training=True):
     """models/genesisv2_config.py:110-203 (dynamic_K=False, klm_loss=False defaults)."""
     K, img = cfg.K_steps, cfg.img_size
@@ -271,9 +290,12 @@ def genesisv2_forward(P, x, tape, cfg, training=True):
     dt = x.dtype
     nb = int(math.log2(img) - 1)
 
+    pre_relu = {}
+
     def conv_gn_relu(h, name):
         h = F.conv2d(h, P[name + '.0.weight'], None, padding=1)
-        return F.relu(O.group_norm(h, 8, P[name + '.1.weight'], P[name + '.1.bias']))
+        pre_relu[name] = O.group_norm(h, 8, P[name + '.1.weight'], P[name + '.1.bias'])
+        return F.relu(pre_relu[name])
 
     enc_feat = F.relu(O.unet(x, P, 'encoder', nb, 'gn'))                       # :114-115
     seg = conv_gn_relu(enc_feat, 'seg_head')
@@ -335,7 +357,8 @@ def genesisv2_forward(P, x, tape, cfg, training=True):
     kl_l_k = [O.mc_kl(z_k[k], mu_k[k], sigma_k[k], pmu_k[k], psig_k[k]) for k in range(K)]
     out = dict(recon=recon, err=err, kl_l_k=kl_l_k, log_m_k=log_m_k, log_s_k=log_s_k, x_r_k=x_r_k,
                log_m_r_k=log_m_r_k,
-               att=dict(colour=colour, delta=delta, seeds=seeds, seed_idx=idxs), n_masks=n_masks,
+               att=dict(colour=colour, delta=delta, seeds=seeds, seed_idx=idxs,
+                        seed_kink_margin=_seed_kink_margin(pre_relu['seg_head'], idxs)), n_masks=n_masks,
                comp=dict(mu_k=mu_k, sigma_k=sigma_k, z_k=z_k, pmu_k=pmu_k[1:], psigma_k=psig_k[1:]),
                bn_updates={})
     if cfg.get('klm_loss', False):          # genesisv2_config.py:171-176: KL(masks || reconstructed masks), the latter detached by default

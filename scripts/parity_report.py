@@ -19,8 +19,8 @@ from oracle import synth  # noqa: E402
 from test_oracle_golden import build_engine_model  # noqa: E402
 from genesis_b200 import ops  # noqa: E402
 
-CASES = [('genesis', 5, 4, 64, 'multid'), ('genesisv2', 7, 4, 64, 'stacks'), ('genesisv2', 11, 2, 64, 'rooms'),
-         ('monet', 7, 3, 64, 'multid'), ('monet', 3, 2, 128, 'multid')]
+CASES = [('genesis', 5, 4, 64, 'multid', 11), ('genesisv2', 7, 4, 64, 'stacks', 11), ('genesisv2', 11, 2, 64, 'rooms', 12),
+         ('monet', 7, 3, 64, 'multid', 11), ('monet', 3, 2, 128, 'multid', 11)]      # last = data seed (tests/test_v2_monet_gpu.py)
 MODES = ['tf32', 'tf32x3', 'fp32']
 _args = sys.argv[1:]
 if '--modes' in _args:
@@ -32,7 +32,7 @@ if _args:
 
 
 def main():
-    for model, K, B, img, gen in CASES:
+    for model, K, B, img, gen, dseed in CASES:
         for prec in MODES:
             if model == 'genesis' and prec.startswith('tf32x3'):
                 continue                      # GENESIS has no precise layers: tf32x3 == tf32
@@ -52,11 +52,13 @@ def main():
                 with torch.no_grad():
                     m.att_process.colour_head.gate.gate.fill_(0.3)
             sd0 = {k: v.clone() for k, v in m.state_dict().items()}
-            x = torch.from_numpy(synth.GENERATORS[gen](B, img, 11)[0])
+            x = torch.from_numpy(synth.GENERATORS[gen](B, img, dseed)[0])
             tape = U.make_tape(5)
             out, P = U.run_oracle(model, sd0, x, tape, cfg)
             recon, losses, stats, att, comp = U.run_engine(m, x, tape.rewound())
             print('== %s K=%d B=%d img=%d %s [%s]' % (model, K, B, img, gen, prec))
+            if model == 'genesisv2':
+                print('   oracle seed-pixel ReLU kink margin %.2e' % out['att']['seed_kink_margin'])
             print('   err rel %.2e | recon rel %.2e' % (U.rel_l2(losses['err'], out['err']), U.rel_l2(recon, out['recon'])))
             for key in ('kl_l_k', 'kl_m_k'):
                 if key in out and key in losses:

@@ -71,12 +71,18 @@ def test_matches_reference_golden(path, precision):
         assert abs((gd * direction(gd.numel(), i)).sum().item() - proj) <= 4 * tol, (n, proj)
 
 
-CASES = [('genesisv2', 7, 4, 64, 'stacks'), ('genesisv2', 3, 5, 64, 'rooms'), ('genesisv2', 11, 2, 64, 'rooms'),
-         ('monet', 7, 3, 64, 'multid'), ('monet', 2, 2, 64, 'stacks'), ('monet', 3, 2, 128, 'multid')]
+# (model, K, B, img, generator, data seed).  The K=11 rooms batch uses data seed 12: with seed 11 channel 9 of seg_head at one
+# IC-SBP seed pixel sits 7e-6 from the ReLU kink (oracle att['seed_kink_margin']); the gradient of seg_head.0.weight /
+# seg_head.1.bias is discontinuous there and implementations that differ by 1e-6 in the UNet output (the two 3xTF32 routes,
+# both 5e-6 from fp64, gpurun_out/r02_x3_bisect.txt) land 14 % apart on those two tensors.  The guard below keeps the comparison
+# well-posed for every case.
+CASES = [('genesisv2', 7, 4, 64, 'stacks', 11), ('genesisv2', 3, 5, 64, 'rooms', 11), ('genesisv2', 11, 2, 64, 'rooms', 12),
+         ('monet', 7, 3, 64, 'multid', 11), ('monet', 2, 2, 64, 'stacks', 11), ('monet', 3, 2, 128, 'multid', 11)]
+KINK_MARGIN = 1e-4
 
 
-@pytest.mark.parametrize('model,K,B,img,gen', CASES)
-def test_matches_oracle(model, K, B, img, gen, precision):
+@pytest.mark.parametrize('model,K,B,img,gen,dseed', CASES)
+def test_matches_oracle(model, K, B, img, gen, dseed, precision):
     gtol = TENSOR_TOL[(model, precision)]
     m, cfg = build_engine_model(model, K, img, seed=3)
     m = m.cuda().train()
@@ -85,11 +91,12 @@ def test_matches_oracle(model, K, B, img, gen, precision):
         with torch.no_grad():
             m.att_process.colour_head.gate.gate.fill_(0.3)
     sd0 = {k: v.clone() for k, v in m.state_dict().items()}
-    x = torch.from_numpy(synth.GENERATORS[gen](B, img, 11)[0])
+    x = torch.from_numpy(synth.GENERATORS[gen](B, img, dseed)[0])
     tape = U.make_tape(5)
     out, P = U.run_oracle(model, sd0, x, tape, cfg)
     recon, losses, stats, att, comp = U.run_engine(m, x, tape.rewound())
     if model == 'genesisv2':
+        assert out['att']['seed_kink_margin'] > KINK_MARGIN, 'ill-posed case: a seed pixel sits on a ReLU kink'
         # discrete seed choice first: identical argmax indices
         ref_idx = torch.stack(out['att']['seed_idx'], 0)
         assert torch.equal(att['seed_idx'].cpu().long(), ref_idx), 'IC-SBP seeds differ'
