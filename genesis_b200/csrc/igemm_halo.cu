@@ -15,9 +15,12 @@
 // consecutive flat positions; positions with w >= Wv (the Wp-Wv pad columns) are computed and dropped.
 // Versus one TMA load per (tile, tap) this cuts L2->SMEM traffic by ~taps/halo-overhead (3x3: 4-5x, 5x5: 8-14x).
 //
-// Roles: warp 0 = TMA producer (activation window in up to 4 row chunks, weight taps through a ring),
-// warp 1 = TMEM allocator + MMA issuer (tap-outer, tile-inner so each weight tile is loaded once per CTA),
-// warps 2-5 = epilogue (tcgen05.ld -> bias/activation -> global).  Two CTAs per SM overlap load / MMA / epilogue.
+// Roles (one-item kernel): warp 0 = TMA producer (activation window in up to 4 row chunks, weight taps through a ring),
+// warps 1-2 = MMA issuers (warp 1 also allocates TMEM; tap-outer, tile-inner so each weight tile is loaded once per CTA;
+// issuer i takes the M tiles t = i mod 2), warps 3-6 = epilogue (tcgen05.ld -> bias/activation -> global).
+// Why two issuers: the tcgen05.mma instructions of ONE thread retire one every ~80 clocks for N <= 128 (M = 128, K = 8 tf32),
+// whatever N is; two independent instruction streams interleave down to the shared-memory operand bound, 40 clk (N = 32) /
+// 48 clk (N = 64) -- measured with g2_debug_umma_rate, profiles/r02_umma_rate.txt.  Two CTAs per SM overlap load / MMA / epilogue.
 #include "umma.cuh"
 #include <cudaTypedefs.h>
 #include <cstdlib>
@@ -59,11 +62,12 @@ template <int ACT> __device__ __forceinline__ float act_apply(float v) {
 // staging tile so that every store instruction writes four complete 128-byte pixel rows (8 lanes x 16 B each).
 template <int BN, int ACT>
 __device__ __forceinline__ void epilogue(const P& p, uint32_t tmem_base, const float* sBias, float* stage, int m_tiles, int n0,
-                                         int h0, int w0, int n0c, int imgs_valid, int rows_valid, int cols_valid) {
+                                         int h0, int w0, int n0c, int imgs_valid, int rows_valid, int cols_valid,
+                                         int t_first = 0, int t_step = 1) {
     const int lane = threadIdx.x & 31, q = (threadIdx.x >> 5) & 3;
     const int img_pix = p.RH * p.Wp;
     const int sub = lane >> 3, chunk = lane & 7;
-    for (int t = 0; t < m_tiles; ++t) {
+    for (int t = t_first; t < m_tiles; t += t_step) {
         const int f = t * 128 + q * 32 + lane;
         const int i = f / img_pix, rem = f - i * img_pix;
         const int hl = rem / p.Wp, w = rem - hl * p.Wp;
@@ -154,8 +158,10 @@ __device__ __forceinline__ float lo_tf32(float x) {
     return __uint_as_float((__float_as_uint(lo) + 0x1000u) & 0xFFFFE000u);
 }
 
+constexpr int NISSUE = 2;            // MMA issuer warps of conv_halo_kernel
+
 template <int BN>
-__global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P p) {
+__global__ void __launch_bounds__(224) conv_halo_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P p) {
     constexpr int B_BYTES = BN * 128;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -196,17 +202,17 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
     if (warp == 1) {
         if (lane == 0) {
             for (int j = 0; j < MAX_CHUNKS; ++j) mbar_init(&fullA[j], 1);
-            mbar_init(emptyA, 1);
-            for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
-            mbar_init(accf, 1);
-            mbar_init(p12, 1);
+            mbar_init(emptyA, NISSUE);                   // every issuer commits once per channel block / stage / kernel
+            for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], NISSUE); }
+            mbar_init(accf, NISSUE);
+            mbar_init(p12, NISSUE);
             mbar_init(loready, 128);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
         tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     }
-    if (threadIdx.x >= 64 && threadIdx.x < 64 + BN) sBias[threadIdx.x - 64] = p.bias ? p.bias[n0c + threadIdx.x - 64] : 0.f;
+    if (threadIdx.x >= 96 && threadIdx.x < 96 + BN) sBias[threadIdx.x - 96] = p.bias ? p.bias[n0c + threadIdx.x - 96] : 0.f;
     fence_before();
     __syncthreads();
     fence_after();
@@ -246,50 +252,59 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
                 if (++bi == STAGES) { bi = 0; bph ^= 1u; }
             }
         }
-    } else if (warp == 1) {
-        // ---- MMA issuer: uniform control flow, one elected lane issues tcgen05.mma / commit
+    } else if (warp <= NISSUE) {
+        // ---- MMA issuers: uniform control flow, one elected lane issues tcgen05.mma / commit; issuer iw owns tiles iw, iw+2, ...
+        const int iw = warp - 1;
+        if (iw != 0) dbg = nullptr;
         constexpr uint32_t idesc = idesc_tf32(BN);
         const uint64_t hi = desc_k_sw128_hi();
         const uint32_t a0 = smem_u32(sA) >> 4;
+        const uint32_t b0 = smem_u32(sB) >> 4;
+        // Per-tap constants live in the lanes (lane L = tap L) and reach the issue loop with one shuffle each: the loop body must
+        // stay SHORT -- a tap is 8 MMAs per issuer (320 clk of tensor-core time at the operand bound) and the issuer is a single
+        // warp running dependent scalar code; with the tap table read from the parameter bank and an integer division per tap
+        // the body took ~1 000 clk and the tensor core starved (profiles/r02_ncu_halo_issue_loop.txt).
+        const int my_toff = lane < p.ntaps ? p.toff[lane] : 0;
+        const uint32_t my_alo = a0 + (uint32_t)my_toff * 8u;
+        // activation chunks a tap reads (monotone in the tile index: the last tile's)
+        const int my_need = min(nch - 1, (128 * (m_tiles - 1) + 127 + my_toff) / p.ch_pix);
+        const int npass = p.x3 ? 3 : 1;
         int bi = 0;
         uint32_t bph = 0;
         for (int cb = 0; cb < p.cblocks; ++cb) {
             int waited = 0;
-            for (int wt = 0; wt < wtiles; ++wt) {
-                const int tap = wt % p.ntaps;
-                if (p.x3 && wt == 2 * p.ntaps) {
-                    // passes 1 + 2 issued: signal their retirement, then wait until the window has been rewritten to x_lo
+            const uint32_t aph = (uint32_t)cb & 1u;
+            for (int pass = 0; pass < npass; ++pass) {
+                if (pass == 2) {
+                    // 3xTF32, passes 1 + 2 issued: signal their retirement, then wait until the window has been rewritten to x_lo
                     if (elect_one()) commit(p12);
                     __syncwarp();
-                    mbar_wait(loready, (uint32_t)cb & 1u);
+                    mbar_wait(loready, aph);
                     fence_after();
                 }
-                const int s = bi;
-                mbar_wait(&fullB[s], bph);
-                if (dbg && lane == 0 && cb == 0 && tap < 28) dbg[8 + 2 * tap] = clock64();          // weight tile of this tap landed
-                const uint64_t bdesc = make_desc_k_sw128(smem_u32(sB + s * B_BYTES));
-                const int toff = p.toff[tap];
-                // activation chunks this tap reads (monotone in the tile index: wait for the last tile's)
-                const int need = min(nch - 1, (128 * (m_tiles - 1) + 127 + toff) / p.ch_pix);
-                while (waited <= need) { mbar_wait(&fullA[waited], (uint32_t)cb & 1u); ++waited; }
-                fence_after();
-                if (dbg && lane == 0 && cb == 0 && tap == 0) dbg[2] = clock64();      // first weight tile + its activation chunks landed
-                const uint32_t alo = a0 + (uint32_t)toff * 8u;
-                const uint32_t first = (cb | wt) != 0 ? 1u : 0u;
-                if (elect_one()) {
-                    for (int t = 0; t < m_tiles; ++t) {
-                        const uint64_t adesc = hi | (uint64_t)((alo + (uint32_t)t * 1024u) & 0x3FFFu);
-                        const uint32_t d = tmem_base + (uint32_t)(t * BN);
-                        mma_tf32(d, adesc, bdesc, idesc, first);        // 4 x (K = 8 tf32 = 32 B) per 128-byte row
-                        mma_tf32(d, adesc + 2, bdesc + 2, idesc, 1u);
-                        mma_tf32(d, adesc + 4, bdesc + 4, idesc, 1u);
-                        mma_tf32(d, adesc + 6, bdesc + 6, idesc, 1u);
+                for (int tap = 0; tap < p.ntaps; ++tap) {
+                    const uint32_t alo = __shfl_sync(0xffffffffu, my_alo, tap);
+                    const int need = __shfl_sync(0xffffffffu, my_need, tap);
+                    mbar_wait(&fullB[bi], bph);
+                    while (waited <= need) { mbar_wait(&fullA[waited], aph); ++waited; }
+                    fence_after();
+                    if (dbg && lane == 0 && (cb | pass | tap) == 0) dbg[2] = clock64();     // first weight tile + its activation chunks landed
+                    const uint64_t bdesc = hi | (uint64_t)((b0 + (uint32_t)bi * (uint32_t)(B_BYTES >> 4)) & 0x3FFFu);
+                    const uint32_t first = (cb | pass | tap) != 0 ? 1u : 0u;
+                    if (elect_one()) {
+                        for (int t = iw; t < m_tiles; t += NISSUE) {
+                            const uint64_t adesc = hi | (uint64_t)((alo + (uint32_t)t * 1024u) & 0x3FFFu);
+                            const uint32_t d = tmem_base + (uint32_t)(t * BN);
+                            mma_tf32(d, adesc, bdesc, idesc, first);        // 4 x (K = 8 tf32 = 32 B) per 128-byte row
+                            mma_tf32(d, adesc + 2, bdesc + 2, idesc, 1u);
+                            mma_tf32(d, adesc + 4, bdesc + 4, idesc, 1u);
+                            mma_tf32(d, adesc + 6, bdesc + 6, idesc, 1u);
+                        }
+                        commit(&emptyB[bi]);                // weight stage free when these MMAs retire
                     }
-                    commit(&emptyB[s]);                 // weight stage free when these MMAs retire
+                    __syncwarp();
+                    if (++bi == STAGES) { bi = 0; bph ^= 1u; }
                 }
-                __syncwarp();
-                if (dbg && lane == 0 && cb == 0 && tap < 28) dbg[9 + 2 * tap] = clock64();          // MMAs of this tap issued
-                if (++bi == STAGES) { bi = 0; bph ^= 1u; }
             }
             if (elect_one()) commit(emptyA);            // activation window free
             __syncwarp();
@@ -301,7 +316,7 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
         // ---- epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31
         if (p.x3) {
             // 3xTF32: between pass 2 and pass 3 of every channel block rewrite the window in place, x -> x - trunc(x)
-            const int tid = threadIdx.x - 64;
+            const int tid = threadIdx.x - 96;
             const int n4 = nch * p.ch_pix * 8;                  // float4s of the loaded window (128 B = 8 float4 per position)
             for (int cb = 0; cb < p.cblocks; ++cb) {
                 const uint32_t ph = (uint32_t)cb & 1u;
@@ -319,7 +334,7 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
         }
         mbar_wait(accf, 0);
         fence_after();
-        if (dbg && threadIdx.x == 64) dbg[4] = clock64();       // accumulators complete
+        if (dbg && threadIdx.x == 96) dbg[4] = clock64();       // accumulators complete
         // the activation window is dead once every MMA has retired: reuse its head as store staging
         if (p.epi) {
             const int nbuf = p.a_bytes >= 2 * 128 * 144 ? 2 : 1;
@@ -338,7 +353,7 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
             default: epilogue<BN, G2_ACT_NONE>(p, tmem_base, sBias, stage, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid); break;
         }
         }
-        if (dbg && threadIdx.x == 64) dbg[5] = clock64();       // epilogue of warp 2 done
+        if (dbg && threadIdx.x == 96) dbg[5] = clock64();       // epilogue of warp 3 done
     }
     fence_before();
     __syncthreads();
@@ -352,19 +367,22 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
 // another: the producer loads window i+1 while the MMA warp works on window i, and the epilogue drains accumulator set
 // (i & 1) under the MMAs of item i+1 -- the MMA phase, which already runs at the shared-memory operand-read bound
 // (DESIGN.md 3.1), then covers the whole lifetime.  Weights stay resident when all taps fit (3x3), else they stream
-// through the ring once per item.
-constexpr int PSTAGE_BYTES = 4 * 4096;      // epilogue staging: 4 warps x (32 rows x 128 B)
+// through the ring once per item.  With ONE issuing thread this kernel is capped at ~80 clk per MMA (the per-thread retire rate,
+// profiles/r02_umma_rate.txt) and only ties with two non-persistent CTAs per SM; with two issuer warps it reaches the
+// shared-memory operand bound.
+constexpr int NEPI_P = 4;                   // epilogue warps of the persistent kernel (8 = two per TMEM lane quarter on alternate M tiles: measured slower,
+                                            // the extra 16 KB of staging shrinks the windows and the epilogue is shared-memory-bandwidth bound anyway)
+constexpr int PSTAGE_BYTES = NEPI_P * 4096; // epilogue staging: one 32 rows x 128 B tile per warp
 
 struct PP {
     P p;                                // per-item geometry, as for the kernel above
     int items_x, items_y;               // work items: blockIdx.x / blockIdx.y space of the non-persistent launch
     int acc_cols;                       // TMEM columns of one accumulator set (m_tiles * BN)
     int b_resident;                     // 1: every (cb, tap) weight tile has its own stage and is loaded once per CTA
-    int kouter;                         // experiment: MMA order k-step outer / tile inner
 };
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1) conv_halo_persistent_kernel(const __grid_constant__ Maps maps, const __grid_constant__ PP pp) {
+__global__ void __launch_bounds__(32 * (2 + NISSUE + NEPI_P), 1) conv_halo_persistent_kernel(const __grid_constant__ Maps maps, const __grid_constant__ PP pp) {
     const P& p = pp.p;
     constexpr int B_BYTES = BN * 128;
     extern __shared__ uint8_t smem_raw[];
@@ -394,8 +412,8 @@ __global__ void __launch_bounds__(192, 1) conv_halo_persistent_kernel(const __gr
     if (warp == 1) {
         if (lane == 0) {
             for (int j = 0; j < 2 * MAX_CHUNKS; ++j) mbar_init(&fullA[j], 1);
-            for (int j = 0; j < 2; ++j) { mbar_init(&emptyA[j], 1); mbar_init(&accFull[j], 1); mbar_init(&accEmpty[j], 4); }
-            for (int s = 0; s < MAX_PSTAGES; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+            for (int j = 0; j < 2; ++j) { mbar_init(&emptyA[j], NISSUE); mbar_init(&accFull[j], NISSUE); mbar_init(&accEmpty[j], NEPI_P); }
+            for (int s = 0; s < MAX_PSTAGES; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], NISSUE); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -423,11 +441,9 @@ __global__ void __launch_bounds__(192, 1) conv_halo_persistent_kernel(const __gr
     };
 
     if (warp == 0) {
-        // ---- TMA producer
+        // ---- TMA producer of the activation windows
         const uint32_t ch_bytes = (uint32_t)p.ch_pix * 128u;
-        int bi = 0; uint32_t bph = 0;
         int u = 0;                                        // activation-window load counter: buffer u & 1, use (u >> 1)
-        bool b_loaded = false;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int n0, h0, w0, n0c, rv, cv, iv, mt, nch;
             decode(item, n0, h0, w0, n0c, rv, cv, iv, mt, nch);
@@ -442,18 +458,25 @@ __global__ void __launch_bounds__(192, 1) conv_halo_persistent_kernel(const __gr
                     }
                 }
                 __syncwarp();
-                if (pp.b_resident) {
-                    if (!b_loaded && elect_one()) {       // all (cb, tap) weight tiles once per CTA (items_y == 1 when resident)
-                        for (int c2 = 0; c2 < p.cblocks; ++c2)
-                            for (int tap = 0; tap < p.ntaps; ++tap) {
-                                const int s = c2 * p.ntaps + tap;
-                                mbar_expect_tx(&fullB[s], B_BYTES);
-                                tma_load_3d(sB + s * B_BYTES, &maps.b, &fullB[s], c2 * 32, n0c, p.widx[tap]);
-                            }
+            }
+        }
+    } else if (warp == 1 + NISSUE + NEPI_P) {
+        // ---- TMA producer of the weight tiles: its own warp, so the ring refills while the window producer waits for a buffer
+        if (pp.b_resident) {
+            if (elect_one()) {                            // all (cb, tap) weight tiles once per CTA (items_y == 1 when resident)
+                for (int c2 = 0; c2 < p.cblocks; ++c2)
+                    for (int tap = 0; tap < p.ntaps; ++tap) {
+                        const int s = c2 * p.ntaps + tap;
+                        mbar_expect_tx(&fullB[s], B_BYTES);
+                        tma_load_3d(sB + s * B_BYTES, &maps.b, &fullB[s], c2 * 32, 0, p.widx[tap]);
                     }
-                    b_loaded = true;
-                    __syncwarp();
-                } else {
+            }
+            __syncwarp();
+        } else {
+            int bi = 0; uint32_t bph = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int n0c = (item / pp.items_x) * BN;
+                for (int cb = 0; cb < p.cblocks; ++cb)
                     for (int tap = 0; tap < p.ntaps; ++tap) {
                         const int s = bi;
                         mbar_wait(&emptyB[s], bph ^ 1u);
@@ -464,50 +487,49 @@ __global__ void __launch_bounds__(192, 1) conv_halo_persistent_kernel(const __gr
                         __syncwarp();
                         if (++bi == STAGES) { bi = 0; bph ^= 1u; }
                     }
-                }
             }
         }
-    } else if (warp == 1) {
-        // ---- MMA issuer
+    } else if (warp <= NISSUE) {
+        // ---- MMA issuers (two instruction streams: see conv_halo_kernel); issuer iw owns the M tiles iw, iw + 2, ... of every item
+        const int iw = warp - 1;
         constexpr uint32_t idesc = idesc_tf32(BN);
         const uint64_t hi = desc_k_sw128_hi();
+        const uint32_t b0 = smem_u32(sB) >> 4;
+        const bool resident = pp.b_resident != 0;
+        const uint32_t my_toff8 = (lane < p.ntaps ? (uint32_t)p.toff[lane] : 0u) * 8u;      // per-tap constants in the lanes (see conv_halo_kernel)
+        const int nch_all = p.TNB > 1 ? 1 : p.nch;
         int bi = 0; uint32_t bph = 0;
         int u = 0, it = 0;
+        if (resident) {                                       // the weights land once: wait for all of them here, not per tap
+            for (int s2 = 0; s2 < p.cblocks * p.ntaps; ++s2) mbar_wait(&fullB[s2], 0);
+        }
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             int n0, h0, w0, n0c, rv, cv, iv, m_tiles, nch;
             decode(item, n0, h0, w0, n0c, rv, cv, iv, m_tiles, nch);
             const int acc = it & 1;
             mbar_wait(&accEmpty[acc], (((uint32_t)(it >> 1)) & 1u) ^ 1u);      // the epilogue has drained this accumulator set
-            fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(acc * pp.acc_cols);
             for (int cb = 0; cb < p.cblocks; ++cb, ++u) {
                 const int buf = u & 1;
                 const uint32_t aph = ((uint32_t)(u >> 1)) & 1u;
                 const uint32_t a0 = smem_u32(sA0 + (size_t)buf * p.a_bytes) >> 4;
-                int waited = 0;
+                // the window was requested one or two items ago: wait for ALL of its chunks up front (no per-tap chunk arithmetic)
+                for (int j = 0; j < nch_all; ++j) mbar_wait(&fullA[buf * MAX_CHUNKS + j], aph);
+                fence_after();
                 for (int tap = 0; tap < p.ntaps; ++tap) {
-                    int s; uint32_t ph;
-                    if (pp.b_resident) { s = cb * p.ntaps + tap; ph = 0; } else { s = bi; ph = bph; }
-                    mbar_wait(&fullB[s], ph);
-                    const uint64_t bdesc = make_desc_k_sw128(smem_u32(sB + s * B_BYTES));
-                    const int toff = p.toff[tap];
-                    const int need = min(nch - 1, (128 * (m_tiles - 1) + 127 + toff) / p.ch_pix);
-                    while (waited <= need) { mbar_wait(&fullA[buf * MAX_CHUNKS + waited], aph); ++waited; }
-                    fence_after();
-                    const uint32_t alo = a0 + (uint32_t)toff * 8u;
+                    const uint32_t alo = a0 + __shfl_sync(0xffffffffu, my_toff8, tap);
+                    int s2;
+                    if (resident) {
+                        s2 = cb * p.ntaps + tap;
+                    } else {
+                        s2 = bi;
+                        mbar_wait(&fullB[s2], bph);
+                        fence_after();
+                    }
+                    const uint64_t bdesc = hi | (uint64_t)((b0 + (uint32_t)s2 * (uint32_t)(B_BYTES >> 4)) & 0x3FFFu);
                     const uint32_t first = (cb | tap) != 0 ? 1u : 0u;
                     if (elect_one()) {
-                        if (pp.kouter) {
-                            // k-step outer, tile inner: consecutive MMAs write DIFFERENT accumulators (no back-to-back
-                            // read-modify-write of one TMEM tile)
-#pragma unroll
-                            for (int ks = 0; ks < 4; ++ks)
-                                for (int t = 0; t < m_tiles; ++t) {
-                                    const uint64_t adesc = hi | (uint64_t)((alo + (uint32_t)t * 1024u) & 0x3FFFu);
-                                    mma_tf32(tacc + (uint32_t)(t * BN), adesc + 2 * ks, bdesc + 2 * ks, idesc, ks ? 1u : first);
-                                }
-                        } else
-                        for (int t = 0; t < m_tiles; ++t) {
+                        for (int t = iw; t < m_tiles; t += NISSUE) {
                             const uint64_t adesc = hi | (uint64_t)((alo + (uint32_t)t * 1024u) & 0x3FFFu);
                             const uint32_t d = tacc + (uint32_t)(t * BN);
                             mma_tf32(d, adesc, bdesc, idesc, first);
@@ -515,14 +537,11 @@ __global__ void __launch_bounds__(192, 1) conv_halo_persistent_kernel(const __gr
                             mma_tf32(d, adesc + 4, bdesc + 4, idesc, 1u);
                             mma_tf32(d, adesc + 6, bdesc + 6, idesc, 1u);
                         }
-                        if (!pp.b_resident) commit(&emptyB[s]);
+                        if (!resident) commit(&emptyB[s2]);
                     }
                     __syncwarp();
-                    if (!pp.b_resident && ++bi == STAGES) { bi = 0; bph ^= 1u; }
+                    if (!resident && ++bi == STAGES) { bi = 0; bph ^= 1u; }
                 }
-                // chunks no tap needed (bottom-edge tiles) must have landed too before the window is handed back: the next
-                // load of this buffer re-arms their barriers
-                while (waited < nch) { mbar_wait(&fullA[buf * MAX_CHUNKS + waited], aph); ++waited; }
                 if (elect_one()) commit(&emptyA[buf]);           // window free when these MMAs retire
                 __syncwarp();
             }
@@ -531,27 +550,29 @@ __global__ void __launch_bounds__(192, 1) conv_halo_persistent_kernel(const __gr
         }
     } else {
         // ---- epilogue warps: drain accumulator set (it & 1) while the MMA warp fills the other one
-        float* stage = reinterpret_cast<float*>(sStage) + (warp & 3) * 1024;
+        // warp w may touch TMEM lanes 32*(w%4)..+31: warps 3..6 and 7..10 cover the four quarters twice; the second set takes the odd tiles
+        const int ew = warp - 1 - NISSUE, t_first = ew >> 2, t_step = NEPI_P / 4;
+        float* stage = reinterpret_cast<float*>(sStage) + ew * 1024;
         int it = 0, last_n0c = -1;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             int n0, h0, w0, n0c, rows_valid, cols_valid, imgs_valid, m_tiles, nch;
             decode(item, n0, h0, w0, n0c, rows_valid, cols_valid, imgs_valid, m_tiles, nch);
             const int acc = it & 1;
             if (n0c != last_n0c) {                               // bias of this output-channel block (4 epilogue warps = 128 threads)
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const int tI = threadIdx.x - 64;
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * NEPI_P) : "memory");
+                const int tI = threadIdx.x - 32 * (1 + NISSUE);
                 if (tI < BN) sBias[tI] = p.bias ? p.bias[n0c + tI] : 0.f;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * NEPI_P) : "memory");
                 last_n0c = n0c;
             }
             mbar_wait(&accFull[acc], ((uint32_t)(it >> 1)) & 1u);
             fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(acc * pp.acc_cols);
             switch (p.act) {
-                case G2_ACT_RELU: epilogue<BN, G2_ACT_RELU>(p, tacc, sBias, stage, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid); break;
-                case G2_ACT_ELU: epilogue<BN, G2_ACT_ELU>(p, tacc, sBias, stage, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid); break;
-                case G2_ACT_SIGMOID: epilogue<BN, G2_ACT_SIGMOID>(p, tacc, sBias, stage, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid); break;
-                default: epilogue<BN, G2_ACT_NONE>(p, tacc, sBias, stage, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid); break;
+                case G2_ACT_RELU: epilogue<BN, G2_ACT_RELU>(p, tacc, sBias, stage, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid, t_first, t_step); break;
+                case G2_ACT_ELU: epilogue<BN, G2_ACT_ELU>(p, tacc, sBias, stage, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid, t_first, t_step); break;
+                case G2_ACT_SIGMOID: epilogue<BN, G2_ACT_SIGMOID>(p, tacc, sBias, stage, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid, t_first, t_step); break;
+                default: epilogue<BN, G2_ACT_NONE>(p, tacc, sBias, stage, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid, t_first, t_step); break;
             }
             fence_before();                                      // our tcgen05.ld's are complete (wait::ld inside) before we hand the set back
             __syncwarp();
@@ -712,7 +733,7 @@ static int launch(const Maps& maps, const P& p, dim3 grid, cudaStream_t stream) 
         if (e != cudaSuccess) return (int)e;
         once.done();
     }
-    conv_halo_kernel<BN><<<grid, 192, smem, stream>>>(maps, p);
+    conv_halo_kernel<BN><<<grid, 224, smem, stream>>>(maps, p);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? G2_OK : (int)e;
 }
@@ -731,7 +752,7 @@ static int launch_persistent(const Maps& maps, const PP& pp, int n_ctas, cudaStr
         if (e != cudaSuccess) return (int)e;
         once.done();
     }
-    conv_halo_persistent_kernel<BN><<<n_ctas, 192, smem, stream>>>(maps, pp);
+    conv_halo_persistent_kernel<BN><<<n_ctas, 32 * (2 + NISSUE + NEPI_P), smem, stream>>>(maps, pp);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? G2_OK : (int)e;
 }
@@ -929,7 +950,6 @@ static int conv_halo_impl(const float* in, const float* w, const float* bias, fl
             pp.items_x = (int)grid.x; pp.items_y = (int)grid.y;
             pp.acc_cols = g.m * BN;
             pp.b_resident = resident ? 1 : 0;
-            { static int ko = env_int("G2_HALO_KOUTER", 0); pp.kouter = ko; }
             int pc = 32;
             while (pc < 2 * pp.acc_cols) pc <<= 1;
             pp.p.tmem_cols = pc;

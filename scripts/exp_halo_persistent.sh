@@ -1,7 +1,5 @@
-S=c2_bdec_fwd70,c2_att64_fwd,c2_att64_dgrad,c3_unet64
+S=c2_bdec_fwd70,c2_bdec_dgrad,c2_att64_fwd,c2_att64_dgrad,c2_att32_fwd,c2_att16_fwd,c2_att_up64_fwd,c3_unet64,c3_unet32,c3_dec_up64,c5_unet128,c5_bdec_fwd
 echo "== default"; python scripts/conv_bench.py --only $S 2>&1 | grep halo
 echo "== persistent"; G2_HALO_PERSISTENT=1 python scripts/conv_bench.py --only $S 2>&1 | grep halo
-echo "== persistent kouter"; G2_HALO_PERSISTENT=1 G2_HALO_KOUTER=1 python scripts/conv_bench.py --only $S 2>&1 | grep halo
-echo "== persistent 2 CTAs/SM"; G2_HALO_PERSISTENT=1 G2_HALO_PERSISTENT_CTAS=296 G2_HALO_PERSISTENT_SMEM_KB=113 G2_HALO_PERSISTENT_COLS=128 python scripts/conv_bench.py --only $S 2>&1 | grep halo
-echo "== persistent 2 CTAs/SM kouter"; G2_HALO_PERSISTENT=1 G2_HALO_KOUTER=1 G2_HALO_PERSISTENT_CTAS=296 G2_HALO_PERSISTENT_SMEM_KB=113 G2_HALO_PERSISTENT_COLS=128 python scripts/conv_bench.py --only $S 2>&1 | grep halo
-echo "== persistent 3 CTAs/SM"; G2_HALO_PERSISTENT=1 G2_HALO_PERSISTENT_CTAS=444 G2_HALO_PERSISTENT_SMEM_KB=75 G2_HALO_PERSISTENT_COLS=64 python scripts/conv_bench.py --only $S 2>&1 | grep halo
+
+echo "== persistent tests"; G2_HALO_PERSISTENT=1 python -m pytest tests/test_halo_gpu.py tests/test_tc_gpu.py -q -x 2>&1 | tail -3

@@ -74,6 +74,7 @@ PTX_RULES = [   # (substring of the PTX text, C++ statement; {o0} = first output
     ('tcgen05.ld', 'emu::tmem_ld32({i0}, &({o0}));'),
     ('fence.', ';'),
     ('bar.sync 1, 128', 'emu::named_barrier(1, 128);'),
+    ('bar.sync 1, %0', 'emu::named_barrier(1, {i0});'),
     ('%%smid', '{o0} = 0;'),
 ]
 
