@@ -58,6 +58,9 @@ template <int ACT> __device__ __forceinline__ float act_apply(float v) {
 }
 
 // One epilogue warp: TMEM lanes 32q..32q+31 of every M tile -> +bias -> activation -> global.
+// (Measured dead end, round 2: prefetching the next TMEM block into a second register set + batching the eight staging reads
+// before the eight stores changes nothing in the persistent kernel -- it is shared-memory-bandwidth bound, not epilogue-latency
+// bound -- and costs the one-item kernel its second CTA per SM: 0.157 -> 0.216 ms on the 3x3 32->32 layer.)
 // Each lane owns one output pixel row in TMEM; the 32 x 128-byte block is transposed through a swizzled 4 KB
 // staging tile so that every store instruction writes four complete 128-byte pixel rows (8 lanes x 16 B each).
 template <int BN, int ACT>
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(224) conv_halo_kernel(const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------ persistent variant
-// EXPERIMENTAL (G2_HALO_PERSISTENT=1; off by default: written after the round-1 GPU budget was spent, not yet run on a B200).
+// Default route since round 2 (G2_HALO_PERSISTENT=0 switches it off; see persistent_mode()).
 // One CTA per SM walks the work items (item = the tile the kernel above gives to one CTA) with a static stride.  Two
 // activation windows, two TMEM accumulator sets and a dedicated store-staging tile let the three roles run ahead of one
 // another: the producer loads window i+1 while the MMA warp works on window i, and the epilogue drains accumulator set
@@ -738,7 +741,10 @@ static int launch(const Maps& maps, const P& p, dim3 grid, cudaStream_t stream) 
     return e == cudaSuccess ? G2_OK : (int)e;
 }
 
-static int persistent_mode() { static int v = env_int("G2_HALO_PERSISTENT", 0); return v; }
+// 0: one-item kernel only; 1: persistent kernel wherever its geometry fits; 2 (default): persistent except where the one-item
+// kernel measured faster (profiles/r02_conv_bench_persistent_2issuers.txt): weights streamed through the ring (not resident)
+// for two or more channel blocks of a filter with more than 9 taps -- 50+ weight tiles per item, a barrier round trip per tap.
+static int persistent_mode() { static int v = env_int("G2_HALO_PERSISTENT", 2); return v; }
 // CTAs of the persistent launch (one per SM by default; the CPU emulation lowers it to give every CTA several items)
 static int persistent_ctas() { static int v = env_int("G2_HALO_PERSISTENT_CTAS", 148); return v < 1 ? 1 : v; }
 
@@ -822,6 +828,7 @@ static bool persistent_geo(int N, const TapSet& t, int Ci, int Co, int BN, int s
     const int b_all = t.n * (Ci / 32);
     *resident = Co == BN && b_all <= MAX_PSTAGES && b_all * BN * 128 <= 72 * 1024;
     *pstages = *resident ? b_all : (BN == 32 ? 8 : BN == 64 ? 4 : 2);
+    if (persistent_mode() == 2 && !*resident && Ci / 32 >= 2 && t.n > 9) return false;
     // experiments: shared memory per CTA (113 KB -> two persistent CTAs per SM) and TMEM columns per accumulator set
     static int smem_kb = env_int("G2_HALO_PERSISTENT_SMEM_KB", 227), cols = env_int("G2_HALO_PERSISTENT_COLS", 256);
     const int a_budget = (smem_kb * 1024 - 1024 - *pstages * BN * 128 - PSTAGE_BYTES - 2048 - 512) / 2;

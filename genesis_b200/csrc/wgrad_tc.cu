@@ -335,8 +335,11 @@ struct P {
     short grp_off[MAX_GRP], grp_lbo[MAX_GRP], grp_n[MAX_GRP], grp_tap[MAX_GRP][4];   // rows, rows, valid atoms, tap index per atom
 };
 
+constexpr int NISSUE = 2;           // MMA issuer warps: one thread retires one tcgen05.mma per ~80 clk (N <= 128) whatever N is; two
+                                    // instruction streams on different accumulators reach the operand bound (profiles/r02_umma_rate.txt)
+
 template <int BN>
-__global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P p) {
+__global__ void __launch_bounds__(224, 1) wgrad_halo_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* sm = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -363,8 +366,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < 2; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-            mbar_init(accf, 1);
+            for (int s = 0; s < 2; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NISSUE); }
+            mbar_init(accf, NISSUE);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -395,7 +398,9 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
                 __syncwarp();
             }
         }
-    } else if (warp == 1) {
+    } else if (warp <= NISSUE) {
+        // issuer iw owns the tap groups iw, iw + 2, ... (each group has its own accumulator)
+        const int iw = warp - 1;
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         int it = 0;
@@ -407,7 +412,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
                 const uint64_t bdesc = make_desc_mn_sw128(smem_u32(sT + buf * p.t_buf), (uint32_t)p.t_blk);
                 const uint32_t gbase = smem_u32(sG + buf * p.g_buf);
                 if (elect_one()) {
-                    for (int g = 0; g < p.ngroups; ++g) {
+                    for (int g = iw; g < p.ngroups; g += NISSUE) {
                         const uint64_t adesc = make_desc_mn_sw128(gbase + (uint32_t)p.grp_off[g] * 128u, (uint32_t)p.grp_lbo[g] * 128u);
                         const uint32_t d = tmem_base + (uint32_t)((c * p.ngroups + g) * BN);
                         for (int kk = 0; kk < p.ksteps; ++kk)        // 8 pixel rows (1024 B = 64 descriptor units) per instruction
@@ -638,7 +643,7 @@ static int wgrad_halo_launch(const wgh::HPlan& hp, const float* g, const float* 
             if (e != cudaSuccess) return (int)e;                                                                           \
             once.done();                                                                                                   \
         }                                                                                                                  \
-        wgh::wgrad_halo_kernel<BN><<<grid, 192, hp.smem, stream>>>(maps, p);                                                   \
+        wgh::wgrad_halo_kernel<BN><<<grid, 224, hp.smem, stream>>>(maps, p);                                                   \
     }
     if (Ct == 32) WGH_LAUNCH(32) else if (Ct == 64) WGH_LAUNCH(64) else WGH_LAUNCH(128)
 #undef WGH_LAUNCH
