@@ -82,6 +82,22 @@ __device__ __forceinline__ void epilogue(const P& p, uint32_t tmem_base, const f
             uint32_t v[32];
             tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * BN + c0), v);
             tmem_ld_wait();
+            if (p.epi == 2) {
+                // direct (G2_HALO_EPI=2, experiment): the lane writes its own 128-byte row with eight 16-byte stores -- no staging
+                // traffic in shared memory, but 32 lines per store instruction: 7-12 % slower (profiles/r02_conv_bench_epilogue_direct.txt)
+                float* dst = p.out + (size_t)(pix < 0 ? 0 : pix) * p.Co + n0c + c0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b = *reinterpret_cast<const float4*>(sBias + c0 + 4 * j);
+                    float4 o;
+                    o.x = act_apply<ACT>(__uint_as_float(v[4 * j]) + b.x);
+                    o.y = act_apply<ACT>(__uint_as_float(v[4 * j + 1]) + b.y);
+                    o.z = act_apply<ACT>(__uint_as_float(v[4 * j + 2]) + b.z);
+                    o.w = act_apply<ACT>(__uint_as_float(v[4 * j + 3]) + b.w);
+                    if (pix >= 0) *reinterpret_cast<float4*>(dst + 4 * j) = o;
+                }
+                continue;
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float4 b = *reinterpret_cast<const float4*>(sBias + c0 + 4 * j);
@@ -339,7 +355,7 @@ __global__ void __launch_bounds__(224) conv_halo_kernel(const __grid_constant__ 
         fence_after();
         if (dbg && threadIdx.x == 96) dbg[4] = clock64();       // accumulators complete
         // the activation window is dead once every MMA has retired: reuse its head as store staging
-        if (p.epi) {
+        if (p.epi == 1) {
             const int nbuf = p.a_bytes >= 2 * 128 * 144 ? 2 : 1;
             switch (p.act) {
                 case G2_ACT_RELU: epilogue_bulk<BN, G2_ACT_RELU>(p, tmem_base, sBias, sA, nbuf, m_tiles, n0, h0, w0, n0c, imgs_valid, rows_valid, cols_valid); break;
@@ -827,7 +843,12 @@ static bool persistent_geo(int N, const TapSet& t, int Ci, int Co, int BN, int s
     if (!persistent_mode()) return false;
     const int b_all = t.n * (Ci / 32);
     *resident = Co == BN && b_all <= MAX_PSTAGES && b_all * BN * 128 <= 72 * 1024;
-    *pstages = *resident ? b_all : (BN == 32 ? 8 : BN == 64 ? 4 : 2);
+    // streamed weights: ring of `ring_kb` KB (tiles of BN x 128 B).  Measured (profiles/r02_conv_bench_ring.txt): 64 / 96 KB rings are
+    // 20-55 % SLOWER than 32 KB on the 5x5 layers -- the shared memory is worth more as activation window (fewer, larger items)
+    static int ring_kb = env_int("G2_HALO_RING_KB", 32);
+    *pstages = *resident ? b_all : ring_kb * 1024 / (BN * 128);
+    if (*pstages > MAX_PSTAGES) *pstages = MAX_PSTAGES;
+    if (*pstages < 2) *pstages = 2;
     if (persistent_mode() == 2 && !*resident && Ci / 32 >= 2 && t.n > 9) return false;
     // experiments: shared memory per CTA (113 KB -> two persistent CTAs per SM) and TMEM columns per accumulator set
     static int smem_kb = env_int("G2_HALO_PERSISTENT_SMEM_KB", 227), cols = env_int("G2_HALO_PERSISTENT_COLS", 256);

@@ -11,10 +11,11 @@ import csv
 import json
 import sys
 
-ENTRY = {'conv_halo_kernel': 'g2_conv_halo_tf32', 'conv_tc_kernel': 'g2_conv_igemm_tf32', 'wgrad_tc_kernel': 'g2_conv_wgrad_tf32_to'}
+ENTRY = {'conv_halo_kernel': 'g2_conv_halo_tf32', 'conv_halo_persistent_kernel': 'g2_conv_halo_tf32', 'conv_tc_kernel': 'g2_conv_igemm_tf32',
+         'wgrad_tc_kernel': 'g2_conv_wgrad_tf32_to', 'wgrad_halo_kernel': 'g2_conv_wgrad_tf32_to'}
 
 
-def main(src, dst):
+def main(src, dst, steps=1):
     rows = list(csv.reader(open(src)))
     start = next(i for i, r in enumerate(rows) if r and r[0] == 'ID')
     hdr = rows[start]
@@ -38,12 +39,14 @@ def main(src, dst):
         o['ns'] += d.get('gpu__time_duration.sum', 0.0)
         o['dram_bytes'] += d.get('dram__bytes_read.sum', 0.0) + d.get('dram__bytes_write.sum', 0.0)
     for o in out.values():
+        o['launches'] /= steps; o['ns'] /= steps; o['dram_bytes'] /= steps          # per ONE step
         o['dram_bytes_per_launch'] = o['dram_bytes'] / max(1, o['launches'])
         o['us_per_launch_under_ncu'] = o['ns'] / 1e3 / max(1, o['launches'])
-    out['_how'] = 'ncu dram__bytes_read.sum + dram__bytes_write.sum per launch over the conv kernels of one eager c2 step (cold, serialised)'
+    out['_how'] = ('ncu dram__bytes_read.sum + dram__bytes_write.sum over the conv / wgrad kernel launches of eager training steps '
+                   '(scripts/profile_step.py: %d steps captured, figures per ONE step; cold, serialised)' % steps)
     json.dump(out, open(dst, 'w'), indent=1)
     print(json.dumps(out, indent=1))
 
 
 if __name__ == '__main__':
-    main(sys.argv[1], sys.argv[2])
+    main(sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 1)
