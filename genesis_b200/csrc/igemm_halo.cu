@@ -847,8 +847,8 @@ static bool persistent_geo(int N, const TapSet& t, int Ci, int Co, int BN, int s
     // 20-55 % SLOWER than 32 KB on the 5x5 layers -- the shared memory is worth more as activation window (fewer, larger items)
     static int ring_kb = env_int("G2_HALO_RING_KB", 32);
     *pstages = *resident ? b_all : ring_kb * 1024 / (BN * 128);
-    if (*pstages > MAX_PSTAGES) *pstages = MAX_PSTAGES;
-    if (*pstages < 2) *pstages = 2;
+    if (!*resident && *pstages > MAX_PSTAGES) *pstages = MAX_PSTAGES;
+    if (!*resident && *pstages < 2) *pstages = 2;
     if (persistent_mode() == 2 && !*resident && Ci / 32 >= 2 && t.n > 9) return false;
     // experiments: shared memory per CTA (113 KB -> two persistent CTAs per SM) and TMEM columns per accumulator set
     static int smem_kb = env_int("G2_HALO_PERSISTENT_SMEM_KB", 227), cols = env_int("G2_HALO_PERSISTENT_COLS", 256);
