@@ -392,6 +392,7 @@ __global__ void __launch_bounds__(224) conv_halo_kernel(const __grid_constant__ 
 constexpr int NEPI_P = 4;                   // epilogue warps of the persistent kernel (8 = two per TMEM lane quarter on alternate M tiles: measured slower,
                                             // the extra 16 KB of staging shrinks the windows and the epilogue is shared-memory-bandwidth bound anyway)
 constexpr int PSTAGE_BYTES = NEPI_P * 4096; // epilogue staging: one 32 rows x 128 B tile per warp
+constexpr int NREWRITE_P = 4;               // 3xTF32: warps that rewrite a window in place to x_lo (idle otherwise)
 
 struct PP {
     P p;                                // per-item geometry, as for the kernel above
@@ -401,7 +402,7 @@ struct PP {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(32 * (2 + NISSUE + NEPI_P), 1) conv_halo_persistent_kernel(const __grid_constant__ Maps maps, const __grid_constant__ PP pp) {
+__global__ void __launch_bounds__(32 * (2 + NISSUE + NEPI_P + NREWRITE_P), 1) conv_halo_persistent_kernel(const __grid_constant__ Maps maps, const __grid_constant__ PP pp) {
     const P& p = pp.p;
     constexpr int B_BYTES = BN * 128;
     extern __shared__ uint8_t smem_raw[];
@@ -418,8 +419,10 @@ __global__ void __launch_bounds__(32 * (2 + NISSUE + NEPI_P), 1) conv_halo_persi
     uint64_t* emptyB = fullB + MAX_PSTAGES;
     uint64_t* accFull = emptyB + MAX_PSTAGES;            // [2]
     uint64_t* accEmpty = accFull + 2;                    // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accEmpty + 2);
-    float* sBias = reinterpret_cast<float*>(bars) + 384; // 1.5 KB past the start of the barrier block (150 barriers = 1.2 KB)
+    uint64_t* p12 = accEmpty + 2;                        // [2] 3xTF32: passes 1+2 of the unit in window b retired
+    uint64_t* loready = p12 + 2;                         // [2] 3xTF32: window b rewritten to x_lo
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(loready + 2);
+    float* sBias = reinterpret_cast<float*>(bars) + 384; // 1.5 KB past the start of the barrier block (154 barriers = 1.2 KB)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = pp.items_x * pp.items_y;
@@ -433,6 +436,7 @@ __global__ void __launch_bounds__(32 * (2 + NISSUE + NEPI_P), 1) conv_halo_persi
             for (int j = 0; j < 2 * MAX_CHUNKS; ++j) mbar_init(&fullA[j], 1);
             for (int j = 0; j < 2; ++j) { mbar_init(&emptyA[j], NISSUE); mbar_init(&accFull[j], NISSUE); mbar_init(&accEmpty[j], NEPI_P); }
             for (int s = 0; s < MAX_PSTAGES; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], NISSUE); }
+            for (int j = 0; j < 2; ++j) { mbar_init(&p12[j], NISSUE); mbar_init(&loready[j], 32 * NREWRITE_P); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -442,6 +446,12 @@ __global__ void __launch_bounds__(32 * (2 + NISSUE + NEPI_P), 1) conv_halo_persi
     __syncthreads();
     fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // 3xTF32 (p.x3): a UNIT = (item, channel block) = one window.  Units are issued in pairs, P12(u) P12(u+1) P3(u) P3(u+1):
+    // P12 = the (x_hi, w_hi) and (x_hi, w_lo) passes from the raw fp32 window (the tensor core truncates = x_hi), P3 = the
+    // (x_lo, w_hi) pass after the rewrite warps have turned the window into x_lo in place -- the rewrite of unit u runs under
+    // P12(u+1), the one of u+1 under P3(u).  The weight producer walks the same schedule.
+    const int my_items = (int)blockIdx.x < n_items ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int n_units = my_items * p.cblocks;
 
     // geometry of work item `item` (same decomposition as conv_halo_kernel's blockIdx)
     auto decode = [&](int item, int& n0, int& h0, int& w0, int& n0c, int& rows_valid, int& cols_valid, int& imgs_valid, int& m_tiles,
@@ -482,15 +492,37 @@ __global__ void __launch_bounds__(32 * (2 + NISSUE + NEPI_P), 1) conv_halo_persi
     } else if (warp == 1 + NISSUE + NEPI_P) {
         // ---- TMA producer of the weight tiles: its own warp, so the ring refills while the window producer waits for a buffer
         if (pp.b_resident) {
-            if (elect_one()) {                            // all (cb, tap) weight tiles once per CTA (items_y == 1 when resident)
-                for (int c2 = 0; c2 < p.cblocks; ++c2)
-                    for (int tap = 0; tap < p.ntaps; ++tap) {
-                        const int s = c2 * p.ntaps + tap;
-                        mbar_expect_tx(&fullB[s], B_BYTES);
-                        tma_load_3d(sB + s * B_BYTES, &maps.b, &fullB[s], c2 * 32, 0, p.widx[tap]);
-                    }
+            if (elect_one()) {                            // all (half, cb, tap) weight tiles once per CTA (items_y == 1 when resident)
+                for (int half = 0; half < (p.x3 ? 2 : 1); ++half)
+                    for (int c2 = 0; c2 < p.cblocks; ++c2)
+                        for (int tap = 0; tap < p.ntaps; ++tap) {
+                            const int s = (half * p.cblocks + c2) * p.ntaps + tap;
+                            mbar_expect_tx(&fullB[s], B_BYTES);
+                            tma_load_3d(sB + s * B_BYTES, &maps.b, &fullB[s], c2 * 32 + half * p.w_lo_off, 0, p.widx[tap]);
+                        }
             }
             __syncwarp();
+        } else if (p.x3) {
+            int bi = 0; uint32_t bph = 0;
+            auto taps = [&](int u, int half) {
+                const int n0c = ((int)(blockIdx.x + (u / p.cblocks) * gridDim.x) / pp.items_x) * BN;
+                const int cb = u % p.cblocks;
+                for (int tap = 0; tap < p.ntaps; ++tap) {
+                    mbar_wait(&emptyB[bi], bph ^ 1u);
+                    if (elect_one()) {
+                        mbar_expect_tx(&fullB[bi], B_BYTES);
+                        tma_load_3d(sB + bi * B_BYTES, &maps.b, &fullB[bi], cb * 32 + half * p.w_lo_off, n0c, p.widx[tap]);
+                    }
+                    __syncwarp();
+                    if (++bi == STAGES) { bi = 0; bph ^= 1u; }
+                }
+            };
+            for (int u = 0; u < n_units; u += 2) {
+                taps(u, 0); taps(u, 1);
+                if (u + 1 < n_units) { taps(u + 1, 0); taps(u + 1, 1); }
+                taps(u, 0);
+                if (u + 1 < n_units) taps(u + 1, 0);
+            }
         } else {
             int bi = 0; uint32_t bph = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -520,8 +552,76 @@ __global__ void __launch_bounds__(32 * (2 + NISSUE + NEPI_P), 1) conv_halo_persi
         int bi = 0; uint32_t bph = 0;
         int u = 0, it = 0;
         if (resident) {                                       // the weights land once: wait for all of them here, not per tap
-            for (int s2 = 0; s2 < p.cblocks * p.ntaps; ++s2) mbar_wait(&fullB[s2], 0);
+            for (int s2 = 0; s2 < (p.x3 ? 2 : 1) * p.cblocks * p.ntaps; ++s2) mbar_wait(&fullB[s2], 0);
         }
+        if (p.x3) {
+            auto unit_tiles = [&](int u) {
+                int n0, h0, w0, n0c, rv, cv, iv, mt, nch;
+                decode((int)(blockIdx.x + (u / p.cblocks) * gridDim.x), n0, h0, w0, n0c, rv, cv, iv, mt, nch);
+                return mt;
+            };
+            // one pass over the taps of unit u: half = which weight half (0 = w_hi, 1 = w_lo); pass 0 of channel block 0 overwrites
+            auto taps = [&](int u, int half, bool overwrite_first) {
+                const int m_tiles = unit_tiles(u);
+                const int cb = u % p.cblocks, buf = u & 1;
+                const uint32_t tacc = tmem_base + (uint32_t)(((u / p.cblocks) & 1) * pp.acc_cols);
+                const uint32_t a0 = smem_u32(sA0 + (size_t)buf * p.a_bytes) >> 4;
+                for (int tap = 0; tap < p.ntaps; ++tap) {
+                    const uint32_t alo = a0 + __shfl_sync(0xffffffffu, my_toff8, tap);
+                    int s2;
+                    if (resident) {
+                        s2 = (half * p.cblocks + cb) * p.ntaps + tap;
+                    } else {
+                        s2 = bi;
+                        mbar_wait(&fullB[s2], bph);
+                        fence_after();
+                    }
+                    const uint64_t bdesc = hi | (uint64_t)((b0 + (uint32_t)s2 * (uint32_t)(B_BYTES >> 4)) & 0x3FFFu);
+                    const uint32_t first = (overwrite_first && tap == 0) ? 0u : 1u;
+                    if (elect_one()) {
+                        for (int t = iw; t < m_tiles; t += NISSUE) {
+                            const uint64_t adesc = hi | (uint64_t)((alo + (uint32_t)t * 1024u) & 0x3FFFu);
+                            const uint32_t d = tacc + (uint32_t)(t * BN);
+                            mma_tf32(d, adesc, bdesc, idesc, first);
+                            mma_tf32(d, adesc + 2, bdesc + 2, idesc, 1u);
+                            mma_tf32(d, adesc + 4, bdesc + 4, idesc, 1u);
+                            mma_tf32(d, adesc + 6, bdesc + 6, idesc, 1u);
+                        }
+                        if (!resident) commit(&emptyB[s2]);
+                    }
+                    __syncwarp();
+                    if (!resident && ++bi == STAGES) { bi = 0; bph ^= 1u; }
+                }
+            };
+            auto P12 = [&](int u) {
+                const int itl = u / p.cblocks, cb = u % p.cblocks, buf = u & 1;
+                const uint32_t aph = ((uint32_t)(u >> 1)) & 1u;
+                if (cb == 0) mbar_wait(&accEmpty[itl & 1], (((uint32_t)(itl >> 1)) & 1u) ^ 1u);     // the epilogue has drained this set
+                for (int j = 0; j < nch_all; ++j) mbar_wait(&fullA[buf * MAX_CHUNKS + j], aph);
+                fence_after();
+                taps(u, 0, cb == 0);
+                taps(u, 1, false);
+                if (elect_one()) commit(&p12[buf]);              // the raw window may be rewritten when these retire
+                __syncwarp();
+            };
+            auto P3 = [&](int u) {
+                const int itl = u / p.cblocks, cb = u % p.cblocks, buf = u & 1;
+                mbar_wait(&loready[buf], ((uint32_t)(u >> 1)) & 1u);
+                fence_after();
+                taps(u, 0, false);
+                if (elect_one()) {
+                    commit(&emptyA[buf]);
+                    if (cb == p.cblocks - 1) commit(&accFull[itl & 1]);
+                }
+                __syncwarp();
+            };
+            for (int u = 0; u < n_units; u += 2) {
+                P12(u);
+                if (u + 1 < n_units) P12(u + 1);
+                P3(u);
+                if (u + 1 < n_units) P3(u + 1);
+            }
+        } else
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             int n0, h0, w0, n0c, rv, cv, iv, m_tiles, nch;
             decode(item, n0, h0, w0, n0c, rv, cv, iv, m_tiles, nch);
@@ -566,6 +666,27 @@ __global__ void __launch_bounds__(32 * (2 + NISSUE + NEPI_P), 1) conv_halo_persi
             }
             if (elect_one()) commit(&accFull[acc]);
             __syncwarp();
+        }
+    } else if (warp >= 2 + NISSUE + NEPI_P) {
+        // ---- 3xTF32 rewrite warps: window of unit u -> x_lo = x - trunc(x), rounded to TF32, once its passes 1 + 2 have retired
+        if (p.x3) {
+            const int tid = threadIdx.x - 32 * (2 + NISSUE + NEPI_P);
+            const int nch_all = p.TNB > 1 ? 1 : p.nch;
+            const int n4 = nch_all * p.ch_pix * 8;              // float4s of the window (128 B = 8 float4 per position)
+            for (int u = 0; u < n_units; ++u) {
+                const int buf = u & 1;
+                const uint32_t aph = ((uint32_t)(u >> 1)) & 1u;
+                for (int j = 0; j < nch_all; ++j) mbar_wait(&fullA[buf * MAX_CHUNKS + j], aph);
+                mbar_wait(&p12[buf], aph);
+                float4* w4 = reinterpret_cast<float4*>(sA0 + (size_t)buf * p.a_bytes);
+                for (int i = tid; i < n4; i += 32 * NREWRITE_P) {
+                    float4 v = w4[i];
+                    v.x = lo_tf32(v.x); v.y = lo_tf32(v.y); v.z = lo_tf32(v.z); v.w = lo_tf32(v.w);
+                    w4[i] = v;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads
+                mbar_arrive(&loready[buf]);
+            }
         }
     } else {
         // ---- epilogue warps: drain accumulator set (it & 1) while the MMA warp fills the other one
@@ -761,6 +882,11 @@ static int launch(const Maps& maps, const P& p, dim3 grid, cudaStream_t stream) 
 // kernel measured faster (profiles/r02_conv_bench_persistent_2issuers.txt): weights streamed through the ring (not resident)
 // for two or more channel blocks of a filter with more than 9 taps -- 50+ weight tiles per item, a barrier round trip per tap.
 static int persistent_mode() { static int v = env_int("G2_HALO_PERSISTENT", 2); return v; }
+// 3xTF32 launches on the one-item kernel (0, default) or on the persistent kernel (1).  Measured on a B200
+// (profiles/r02_conv_bench_x3_persistent.txt): with three passes per window the one-item kernel's load / epilogue phases are
+// already amortised (75 % of its shared-memory bound) and the persistent variant only ties (+5 % / -5 % per layer) when its
+// weights stream through the ring, and loses 20-30 % when the [w_hi | w_lo] pack is made resident at the expense of window size.
+static int x3_persistent() { static int v = env_int("G2_HALO_X3_PERSISTENT", 0); return v; }
 // CTAs of the persistent launch (one per SM by default; the CPU emulation lowers it to give every CTA several items)
 static int persistent_ctas() { static int v = env_int("G2_HALO_PERSISTENT_CTAS", 148); return v < 1 ? 1 : v; }
 
@@ -774,13 +900,13 @@ static int launch_persistent(const Maps& maps, const PP& pp, int n_ctas, cudaStr
         if (e != cudaSuccess) return (int)e;
         once.done();
     }
-    conv_halo_persistent_kernel<BN><<<n_ctas, 32 * (2 + NISSUE + NEPI_P), smem, stream>>>(maps, pp);
+    conv_halo_persistent_kernel<BN><<<n_ctas, 32 * (2 + NISSUE + NEPI_P + NREWRITE_P), smem, stream>>>(maps, pp);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? G2_OK : (int)e;
 }
 
 struct TapSet;
-static bool persistent_geo(int N, const TapSet& t, int Ci, int Co, int BN, int sh, int sw, Geo* g, int* pstages, bool* resident);
+static bool persistent_geo(int N, const TapSet& t, int Ci, int Co, int BN, int sh, int sw, Geo* g, int* pstages, bool* resident, int x3 = 0);
 
 static int pick_bn(int Co) {
     if (Co == 32 || Co == 64 || Co == 128) return Co;
@@ -839,10 +965,13 @@ static void spans(const TapSet& t, int* dh_min, int* dw_min, int* span_h, int* s
 
 // Geometry of the experimental persistent variant: weights resident when all (cb, tap) tiles fit beside two windows, else a
 // deeper ring; two windows and two accumulator sets (<= 256 TMEM columns each) per CTA.  false: use the one-item kernel.
-static bool persistent_geo(int N, const TapSet& t, int Ci, int Co, int BN, int sh, int sw, Geo* g, int* pstages, bool* resident) {
+static bool persistent_geo(int N, const TapSet& t, int Ci, int Co, int BN, int sh, int sw, Geo* g, int* pstages, bool* resident, int x3) {
     if (!persistent_mode()) return false;
-    const int b_all = t.n * (Ci / 32);
+    if (x3 && !x3_persistent()) return false;
+    const int b_all = (x3 ? 2 : 1) * t.n * (Ci / 32);          // 3xTF32: [w_hi | w_lo] halves
     *resident = Co == BN && b_all <= MAX_PSTAGES && b_all * BN * 128 <= 72 * 1024;
+    static int x3_res = env_int("G2_HALO_X3_RESIDENT", 0);
+    if (x3 && !x3_res) *resident = false;
     // streamed weights: ring of `ring_kb` KB (tiles of BN x 128 B).  Measured (profiles/r02_conv_bench_ring.txt): 64 / 96 KB rings are
     // 20-55 % SLOWER than 32 KB on the 5x5 layers -- the shared memory is worth more as activation window (fewer, larger items)
     static int ring_kb = env_int("G2_HALO_RING_KB", 32);
@@ -946,7 +1075,7 @@ static int conv_halo_impl(const float* in, const float* w, const float* bias, fl
         Geo g;
         bool resident = false;
         int pstages = 0;
-        const bool use_p = !x3 && persistent_geo(N, t, Ci, Co, BN, sh, sw, &g, &pstages, &resident);
+        const bool use_p = persistent_geo(N, t, Ci, Co, BN, sh, sw, &g, &pstages, &resident, x3);
         if (!use_p && !pick_geo(N, t.Hv, t.Wv, sh, sw, t.n, Ci / 32, BN, stages_of(BN, t.n, Ci / 32), &g)) return G2_ERR_UNSUPPORTED;
         P p;
         memset(&p, 0, sizeof(p));

@@ -50,7 +50,7 @@ def main():
     mp = pytest.MonkeyPatch()
     emu = emu_lib.install(mp)
     torch.Tensor.is_cuda = property(lambda self: True)      # the plug-ins and holders branch on it
-    ops.set_precision('fp32')
+    ops.set_precision(os.environ.get('CENSUS_PRECISION', 'fp32'))
     ops.set_fused_latent('--fused-latent' in sys.argv)
     sys.argv = [a for a in sys.argv]
     m, cfg = build_engine_model(model, K, 64)

@@ -1,6 +1,6 @@
 """Micro-benchmark of the TF32 implicit-GEMM entry points on the conv shapes of the BASELINE configs, through the C ABI.
 
-    python scripts/conv_bench.py [out.json] [--wgrad] [--ab] [--reps 10] [--only name,name]
+    python scripts/conv_bench.py [out.json] [--wgrad] [--ab] [--x3] [--reps 10] [--only name,name]     (--x3: the 3xTF32 entry point; TF/s counts the useful third)
 
 CUDA events on the launch stream, 2 warm-up calls, each timed call preceded by an L2 flush (256 MB memset) that is
 outside the event pair.  Prints TF/s (2*MACs / time) per shape.  Used under ncu for the roofline `traffic` figure."""
@@ -77,8 +77,14 @@ def main():
             print('%-20s unsupported' % name)
             continue
 
+        x3 = '--x3' in sys.argv and lib.query('g2_conv_halo_supported', N, H, W, Ci, Ho, Wo, Co, R, R, s, p, mode) == 1
+        w2 = torch.cat([w, w * 1e-4], dim=2).contiguous() if x3 else None          # [w_hi | w_lo] pack of the 3xTF32 entry point
+
         def run():
-            _lib.call('g2_conv_igemm_tf32', x, w, b, out, N, H, W, Ci, Ho, Wo, Co, R, R, s, p, mode, 0)
+            if x3:
+                _lib.call('g2_conv_halo_x3_tf32', x, w2, b, out, N, H, W, Ci, Ho, Wo, Co, R, R, s, p, mode, 0)
+            else:
+                _lib.call('g2_conv_igemm_tf32', x, w, b, out, N, H, W, Ci, Ho, Wo, Co, R, R, s, p, mode, 0)
 
         io_bytes = 4.0 * (x.numel() + out.numel() + w.numel())
         for halo in ((0, 1) if ab else (1,)):

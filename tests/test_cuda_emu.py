@@ -361,6 +361,15 @@ def test_persistent_halo_kernel_under_the_model():
     _run_child('run_halo_emu.py', HALO_CASES, 'persistent', {'G2_HALO_PERSISTENT_CTAS': '2'})
 
 
+def test_persistent_halo_kernel_3xtf32_under_the_model():
+    """3xTF32 inside the persistent kernel: units (item, channel block) issued in pairs P12(u) P12(u+1) P3(u) P3(u+1), the
+    rewrite warps turning each window into x_lo in place between its passes, resident and streamed [w_hi | w_lo] packs, two CTAs
+    walking several units each; and the one-item kernel's in-kernel split (G2_HALO_X3_PERSISTENT=0) on the same cases."""
+    _run_child('run_halo_emu.py', HALO_CASES, 'x3', {'G2_HALO_PERSISTENT_CTAS': '2', 'G2_HALO_X3_PERSISTENT': '1', 'G2_HALO_X3_RESIDENT': '1'})
+    _run_child('run_halo_emu.py', HALO_CASES[:2], 'x3', {'G2_HALO_PERSISTENT_CTAS': '2', 'G2_HALO_X3_PERSISTENT': '1', 'G2_HALO_X3_RESIDENT': '0'})
+    _run_child('run_halo_emu.py', HALO_CASES[:3], 'x3', {'G2_HALO_X3_PERSISTENT': '0'})
+
+
 WGRAD_CASES = [  # N Hg Wg Cg Ct R pad
     '4 18 18 32 32 3 1',              # 3x3: three-tap groups, the unused fourth atom reads the zeroed slack
     '3 20 20 64 32 5 2',              # 5x5: row groups + a column group + a single, two channel blocks per CTA, 2 windows per CTA

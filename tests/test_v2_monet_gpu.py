@@ -27,7 +27,10 @@ GOLD = sorted(glob.glob(os.path.join(HERE, 'golden', 'genesisv2_*.npz')) + glob.
 # passes on flat synthetic images (the reference's fp32 gradients differ from its fp64 ones by 6.5e-4 per tensor there).
 ERR_RTOL, KL_ATOL = 1e-4, 1e-2
 LM_TOL = {'tf32': 5e-3, 'fp32': 2e-4}
-GLOBAL_TOL = {('genesisv2', 'tf32'): 5e-3, ('genesisv2', 'fp32'): 1e-4, ('monet', 'tf32'): 5e-3, ('monet', 'fp32'): 5e-3}
+# GENESIS-V2 on the exact-fp32 path: 12 repeats of the K = 11 case on a B200 gave a whole-vector distance of 2.1e-5 ... 9.2e-5
+# (gpurun_out/r02_v2_flaky2.txt) -- the float atomics of the masked pooling / fp32 weight-gradient kernels change the last bits from
+# run to run and the IC-SBP model amplifies them -- so the bound is 3e-4, not the 1e-4 a single lucky run suggests.
+GLOBAL_TOL = {('genesisv2', 'tf32'): 5e-3, ('genesisv2', 'fp32'): 3e-4, ('monet', 'tf32'): 5e-3, ('monet', 'fp32'): 5e-3}
 TENSOR_TOL = {('genesisv2', 'tf32'): 2e-2, ('genesisv2', 'fp32'): 2e-3, ('monet', 'tf32'): 2e-2, ('monet', 'fp32'): 2e-2}
 
 
