@@ -42,12 +42,12 @@ def parse_header(path=HEADER):
 
 
 class _Lib(object):
-    def __init__(self):
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError('libgenesis_b200.so is not built (%s). Run `python -m genesis_b200.build`; '
-                               'there is no fallback path.' % LIB_PATH)
-        self.cdll = ctypes.CDLL(LIB_PATH)
-        self.protos = parse_header()
+    def __init__(self, lib_path=LIB_PATH, header=HEADER):
+        if not os.path.exists(lib_path):
+            raise RuntimeError('%s is not built (%s). Run `python -m genesis_b200.build`; '
+                               'there is no fallback path.' % (os.path.basename(lib_path), lib_path))
+        self.cdll = ctypes.CDLL(lib_path)
+        self.protos = parse_header(header)
         self.launches = 0
         self._fn = {}
         for name, sig in self.protos.items():
@@ -103,3 +103,16 @@ def lib():
 
 def call(name, *args):
     lib().call(name, *args)
+
+
+_PROBE = None
+
+
+def probe():
+    """TEST INFRASTRUCTURE: the tcgen05 probe library (tests/probe/, built by build.build_probe) behind the same marshalling."""
+    global _PROBE
+    if _PROBE is None:
+        root = os.path.dirname(HERE)
+        _PROBE = _Lib(os.path.join(root, 'tests', 'probe', 'libgenesis_b200_probe.so'),
+                      os.path.join(root, 'tests', 'probe', 'genesis_b200_probe.h'))
+    return _PROBE

@@ -56,5 +56,20 @@ def build(force=False, verbose=False):
     return LIB
 
 
+PROBE_SRC = os.path.join(os.path.dirname(HERE), 'tests', 'probe', 'debug_umma.cu')
+PROBE_LIB = os.path.join(os.path.dirname(HERE), 'tests', 'probe', 'libgenesis_b200_probe.so')
+
+
+def build_probe(force=False):
+    """TEST INFRASTRUCTURE: the tcgen05 probes (descriptor self-test, instruction-rate probe) as their own library."""
+    if force or _stale(PROBE_LIB, [PROBE_SRC] + sorted(glob.glob(os.path.join(CSRC, '*.cuh')))):
+        cmd = [NVCC] + FLAGS + ['-I', CSRC, '-shared', PROBE_SRC, '-o', PROBE_LIB, '-lcudart', '-lcuda']
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('nvcc failed for the probe library:\n%s\n%s' % (r.stdout, r.stderr))
+    return PROBE_LIB
+
+
 if __name__ == '__main__':
     print(build(force='--force' in sys.argv, verbose=True))
+    print(build_probe(force='--force' in sys.argv))

@@ -294,16 +294,6 @@ int g2_mc_kl_bwd_f32(const float* z, const float* mu, const float* sigma, const 
 int g2_seg_metrics(const float* log_m, const int64_t* pred, const int64_t* inst, int64_t* seg_out, double* out, int B,
                    int P, int K, g2_stream_t stream);
 
-/* UMMA descriptor self-test (debug_umma.cu): runs `nk` tcgen05.mma.kind::tf32 (M=128) on caller-provided
- * shared-memory images of A and B with caller-provided descriptor templates and dumps D[128][N]. */
-int g2_debug_umma_probe(const float* a_img, const float* b_img, float* D, int a_bytes, int b_bytes, long adesc_t,
-                        long bdesc_t, int idesc, int N, int nk, int a_kstep, int b_kstep, int a_off, int b_off,
-                        int base_off_auto, g2_stream_t stream);
-/* UMMA issue-rate probe (debug_umma.cu): out[148 * ctas_per_sm] = clocks for n_mma back-to-back tcgen05.mma.kind::tf32
- * (M = 128, N, K = 8; 4 K-steps per A start row, then the row advances by a_shift_rows) per CTA, operands in shared memory. */
-int g2_debug_umma_rate(int64_t* out, int N, int n_mma, int a_shift_rows, int n_acc, int a_rows, int ctas_per_sm,
-                       int b_tiles, g2_stream_t stream);
-
 /* 3xTF32 operand split (pointwise.cu): hi = x rounded to TF32, lo = x - hi.  mode 0: out [rows,3C] = [hi|hi|lo] (activation
  * side of a tf32x3 contraction whose weight side is [w_hi|w_lo|w_hi]); 1: out [rows,2C] = [hi|lo]; 2: out = hi; 3: out = lo.
  * With it the ill-conditioned layers (MONet / GENESIS-V2 UNet: modules/unet.py:53-65, modules/blocks.py:151-165) run on the

@@ -32,7 +32,7 @@ def rows_image(mat, row_offset=0, total_rows=None):
 def probe(a_img, b_img, ad, bd, idc, N, nk, a_k, b_k, a_off=0, b_off=0, auto=0):
     D = torch.full((128, N), float('nan'), device=DEV)
     a = torch.from_numpy(a_img).to(DEV); b = torch.from_numpy(b_img).to(DEV)
-    _lib.call('g2_debug_umma_probe', a, b, D, a.numel() * 4, b.numel() * 4, ad, bd, idc, N, nk, a_k, b_k, a_off, b_off, auto)
+    _lib.probe().call('g2_debug_umma_probe', a, b, D, a.numel() * 4, b.numel() * 4, ad, bd, idc, N, nk, a_k, b_k, a_off, b_off, auto)
     torch.cuda.synchronize()
     return D.cpu().numpy()
 

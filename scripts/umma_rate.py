@@ -14,7 +14,7 @@ from genesis_b200 import _lib  # noqa: E402
 def rate(N, shift, n_acc, ctas, b_tiles=1, n_mma=4096, a_rows=512):
     out = torch.zeros(148 * ctas, dtype=torch.int64, device='cuda')
     for _ in range(2):
-        _lib.call('g2_debug_umma_rate', out, N, n_mma, shift, n_acc, a_rows, ctas, b_tiles)
+        _lib.probe().call('g2_debug_umma_rate', out, N, n_mma, shift, n_acc, a_rows, ctas, b_tiles)
     torch.cuda.synchronize()
     o = out.double()
     return o.mean().item() / n_mma, o.max().item() / n_mma

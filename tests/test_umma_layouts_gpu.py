@@ -37,7 +37,7 @@ def probe(a_img, b_img, ad, bd, idc, nk, a_k, b_k, a_off=0):
     from genesis_b200 import _lib
     D = torch.full((128, N), float('nan'), device='cuda')
     a, b = torch.from_numpy(a_img).cuda(), torch.from_numpy(b_img).cuda()
-    _lib.call('g2_debug_umma_probe', a, b, D, a.numel() * 4, b.numel() * 4, ad, bd, idc, N, nk, a_k, b_k, a_off, 0, 0)
+    _lib.probe().call('g2_debug_umma_probe', a, b, D, a.numel() * 4, b.numel() * 4, ad, bd, idc, N, nk, a_k, b_k, a_off, 0, 0)
     torch.cuda.synchronize()
     return D.cpu().numpy()
 
