@@ -94,11 +94,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// BN = Ct (32, 64 or 128)
-constexpr int NISSUE_T = 2;         // MMA issuer warps of the tile kernel: issuer i owns the M-groups (= accumulators) i, i+2, ...
-
+// BN = Ct (32, 64 or 128).  ONE issuer warp on purpose: this kernel is bound by its L2 -> shared-memory tile reloads, a second
+// issuer (M-groups split between two warps) measured no gain (0.216 ms either way on the stride-2 5x5 layer), and the split is
+// easy to get wrong -- a consumer that skips its partner's ring stages is no longer within one phase of their barriers (its
+// parity waits pass early or block forever); the first version of it deadlocked in the training step once other kernels ran
+// beside it, while every isolated test passed (round 2).
 template <int BN>
-__global__ void __launch_bounds__(224, 1) wgrad_tc_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P p) {
+__global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P p) {
     constexpr int TB = BN / 32;                 // T channel blocks
     constexpr int T_BYTES = TB * TILE_BYTES;
     constexpr int G_STAGE = 4 * TILE_BYTES;     // one M-group = 4 blocks
@@ -125,8 +127,8 @@ __global__ void __launch_bounds__(224, 1) wgrad_tc_kernel(const __grid_constant_
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-            for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], NISSUE_T); }
-            mbar_init(accf, NISSUE_T);
+            for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 1); }
+            mbar_init(accf, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -172,10 +174,8 @@ __global__ void __launch_bounds__(224, 1) wgrad_tc_kernel(const __grid_constant_
                 __syncwarp();
             }
         }
-    } else if (warp <= NISSUE_T) {
-        // a_major = b_major = MN (bits 15, 16); M = 128; N = BN; tf32 operands, fp32 accumulate.  Two instruction streams (one
-        // thread retires one MMA per ~80 clk, profiles/r02_umma_rate.txt): each stage / accumulator belongs to ONE issuer
-        const int iw = warp - 1;
+    } else if (warp == 1) {
+        // a_major = b_major = MN (bits 15, 16); M = 128; N = BN; tf32 operands, fp32 accumulate
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         int it = 0;
@@ -184,7 +184,6 @@ __global__ void __launch_bounds__(224, 1) wgrad_tc_kernel(const __grid_constant_
             mbar_wait(&tfull[tb], (uint32_t)(c >> 1) & 1u);
             const uint64_t bdesc = make_desc_mn_sw128(smem_u32(sT + tb * T_BYTES), TILE_BYTES);
             for (int g = 0; g < ng; ++g, ++it) {
-                if ((g & (NISSUE_T - 1)) != iw) continue;
                 const int s = it % STAGES;
                 mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -727,7 +726,7 @@ static int wgrad_impl(const float* g, const float* t, float* dw, float* ws, int 
             if (e != cudaSuccess) return (int)e;                                                                          \
             once.done();                                                                                                  \
         }                                                                                                                 \
-        wgrad_tc_kernel<BN><<<grid, 224, smem, stream>>>(maps, p);                                                        \
+        wgrad_tc_kernel<BN><<<grid, 192, smem, stream>>>(maps, p);                                                        \
     }
     if (Ct == 32) WG_LAUNCH(32) else if (Ct == 64) WG_LAUNCH(64) else WG_LAUNCH(128)
 #undef WG_LAUNCH
