@@ -213,3 +213,33 @@ def test_split_tf32_kernel_is_exact(ops):
     assert (hi.view(torch.int32) & 0x1FFF).abs().max().item() == 0
     assert ((x - hi).abs() <= x.abs() * 2.0 ** -11).all()
     assert torch.equal(out3, torch.cat([hi, hi, lo], 1)) and torch.equal(out2, torch.cat([hi, lo], 1))
+
+
+@pytest.mark.parametrize('Cin,nout,nsig,NP', [(32, 3, 3, (3, 9, 7)), (32, 4, 0, (2, 20, 33)), (64, 1, 0, (2, 5, 6))])
+def test_out1x1_head_kernels(ops, Cin, nout, nsig, NP):
+    """The 1x1 output head (out1x1_fwd / out1x1_bwd with cooperative row stores / head_wgrad with four rows per load) against
+    torch, at pixel counts that are not multiples of the kernels' 16-pixel strides."""
+    import torch.nn.functional as F
+    torch.manual_seed(21)
+    N, Hh, Ww = NP
+    h = torch.randn(N, Hh, Ww, Cin, requires_grad=True)
+    w = (0.3 * torch.randn(nout, Cin, 1, 1)).requires_grad_(True)
+    b = torch.randn(nout, requires_grad=True)
+    out = ops.out1x1(h, w, b, nsig)
+    ref = F.conv2d(h.permute(0, 3, 1, 2), w, b)
+    if nsig:
+        ref = torch.cat([torch.sigmoid(ref[:, :nsig]), ref[:, nsig:]], 1)
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-5)
+    g = torch.randn_like(ref)
+    for a, c in zip(grads(out, [h, w, b], g), grads(ref, [h, w, b], g)):
+        torch.testing.assert_close(a, c, rtol=2e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize('N,J', [(5, 8), (16, 40), (37, 12)])
+def test_sum_dim0_kernel(ops, N, J):
+    import genesis_b200._lib as L
+    torch.manual_seed(22)
+    x = torch.randn(N, J)
+    out = torch.empty(J)
+    L.call('g2_sum_dim0_f32', x, out, N, J)
+    torch.testing.assert_close(out, x.sum(0), rtol=1e-5, atol=1e-5)
