@@ -237,6 +237,17 @@ def gated_forward(layer, x, training):
     return gate_norm(layer, y, training, conv_bias=conv.bias)
 
 
+# BatchNorm's num_batches_tracked counters: one multi-tensor add per encoder / decoder stack instead of one tiny kernel per
+# counter (20 launches per GENESIS step).  A layer used twice before the flush appears twice and is incremented twice.
+_NBT_PENDING = []
+
+
+def flush_batch_counters():
+    if _NBT_PENDING:
+        torch._foreach_add_(list(_NBT_PENDING), 1)
+        del _NBT_PENDING[:]
+
+
 def gate_norm(layer, y, training, conv_bias=None):
     hn, gn = layer.h_norm, layer.g_norm
     if hn is None:
@@ -246,8 +257,7 @@ def gate_norm(layer, y, training, conv_bias=None):
                             gn.running_mean, gn.running_var, mode=ops.NORM_BATCH, post=ops.POST_GATE,
                             training=training, eps=hn.eps, momentum=hn.momentum, conv_bias=conv_bias)
         if training:
-            hn.num_batches_tracked += 1
-            gn.num_batches_tracked += 1
+            _NBT_PENDING.extend((hn.num_batches_tracked, gn.num_batches_tracked))
         return out
     return ops.norm_post(y, hn.weight, hn.bias, gn.weight, gn.bias, mode=ops.NORM_INSTANCE,
                          post=ops.POST_GATE, eps=hn.eps, conv_bias=conv_bias)
@@ -265,7 +275,9 @@ def sylvester_encode(core, x_nhwc, training):
     w = last.conv.weight                                   # [512, 64, k, k]
     wm = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)     # columns in (h, w, c) order
     y = ops.linear(h.reshape(B, -1), wm, last.conv.bias)
-    return gate_norm(last, y.view(B, 1, 1, -1), training).view(B, -1)
+    out = gate_norm(last, y.view(B, 1, 1, -1), training).view(B, -1)
+    flush_batch_counters()
+    return out
 
 
 def sylvester_decode(core, z, training, nsig=0):
@@ -281,6 +293,7 @@ def sylvester_decode(core, z, training, nsig=0):
     h = gate_norm(first, y, training)
     for i in range(1, len(core.p_x_nn)):
         h = gated_forward(core.p_x_nn[i], h, training)
+    flush_batch_counters()
     return ops.out1x1(h, core.p_x_mean.weight, core.p_x_mean.bias, nsig)
 
 
