@@ -155,20 +155,25 @@ def run_reference_arm(args):
     step, kind = cpu_step_fn(batch)
     for i in range(max(1, min(args.warmup, 2))):
         step(i)
+    # a bounded sample of the workload: at most args.steps steps and at most ~150 s of host time (never fewer than 2 steps)
     t0 = time.perf_counter()
+    n_run = 0
     for i in range(args.steps):
         step(i)
+        n_run += 1
+        if n_run >= 2 and time.perf_counter() - t0 > 150.0:
+            break
     dt = time.perf_counter() - t0
-    v = batch * args.steps / dt
+    v = batch * n_run / dt
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'warmup': args.warmup, 'ms_per_step': 1e3 * dt / n_run, 'steps_timed': n_run, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': workload_name() + ', fwd+bwd on the host CPU', 'global_batch': batch,
                    'same_config': True},
         'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': kind,
                          'sample': '%d steps x batch %d (the config batch), torch %s CPU fp32, %d threads; %s' % (
-                             args.steps, batch, torch.__version__, cores,
+                             n_run, batch, torch.__version__, cores,
                              "the reference's own nn.Modules from oracle/_ref" if kind == 'reference' else 'oracle port (oracle/_ref absent)')},
         'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -347,8 +352,8 @@ def run_engine(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
     ap.add_argument('--no-cpu-baseline', dest='no_cpu_baseline', action='store_true')
     ap.add_argument('--no-graph', dest='no_graph', action='store_true')
