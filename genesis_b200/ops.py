@@ -36,7 +36,7 @@ def _call(name, *args):
 
 
 _SIDE = {}
-_SIDE_ON = {'on': True}
+_SIDE_ON = {'on': os.environ.get('G2_SIDE_STREAMS', '1') != '0', 'grad': os.environ.get('G2_GRAD_STREAM', '1') != '0'}
 
 
 def set_side_streams(on):
@@ -65,7 +65,7 @@ class _GradStream(object):
 
     def __init__(self, *operands):
         self.cur = torch.cuda.current_stream()
-        self.side = side_stream(operands[0].device, 1) if _SIDE_ON['on'] else self.cur
+        self.side = side_stream(operands[0].device, 1) if (_SIDE_ON['on'] and _SIDE_ON['grad']) else self.cur
         if self.side is not self.cur:
             self.side.wait_stream(self.cur)
             for t in operands:
