@@ -12,15 +12,18 @@ inline int ew_blocks(long work, int threads = 256) {
 }
 
 // x [N,C,P] -> y [N,P,C]   (dir 0)   or   x [N,P,C] -> y [N,C,P]   (dir 1)
-__global__ void layout_kernel(const float* __restrict__ x, float* __restrict__ y, long total, int C, int P, int dir) {
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+// Index type I: unsigned when the element count fits 31 bits (every shape of the BASELINE configs), else long -- the 64-bit
+// divisions of the index decomposition cost more than the memory access they address.
+template <typename I>
+__global__ void layout_kernel(const float* __restrict__ x, float* __restrict__ y, I total, int C, int P, int dir) {
+    for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
         // i indexes the OUTPUT (coalesced writes)
         if (dir == 0) {
-            const int c = (int)(i % C); const long t = i / C; const int p = (int)(t % P); const long n = t / P;
-            y[i] = __ldg(x + (n * C + c) * P + p);
+            const I c = i % (I)C, t = i / (I)C, p = t % (I)P, n = t / (I)P;
+            y[i] = __ldg(x + ((long)n * C + c) * P + p);
         } else {
-            const int p = (int)(i % P); const long t = i / P; const int c = (int)(t % C); const long n = t / C;
-            y[i] = __ldg(x + (n * P + p) * C + c);
+            const I p = i % (I)P, t = i / (I)P, c = t % (I)C, n = t / (I)C;
+            y[i] = __ldg(x + ((long)n * P + p) * C + c);
         }
     }
 }
@@ -75,42 +78,45 @@ __global__ void sbp_scan_bwd_kernel(const float* __restrict__ logits, const floa
 // out[(k*B+b), p, 0] = log_m[k,b,p];  out[(k*B+b), p, 1..3] = x[b, 0..2, p]      (x NCHW, out NHWC4)
 // `Cp` (multiple of 4) output channels: channels >= 4 are zero padding so the encoder's first conv fits the
 // 32-channel k-blocks of the tensor-core kernels.
+template <typename I>
 __global__ void comp_pack_kernel(const float* __restrict__ x, const float* __restrict__ log_m, float* __restrict__ out,
-                                 long total, int B, int P, int Cp) {
-    const int q = Cp >> 2;
-    for (long j = (long)blockIdx.x * blockDim.x + threadIdx.x; j < total * q; j += (long)gridDim.x * blockDim.x) {
-        const int quad = (int)(j % q);
-        const long i = j / q;
+                                 I total, int B, int P, int Cp) {
+    const I q = (I)(Cp >> 2);
+    for (I j = (I)blockIdx.x * blockDim.x + threadIdx.x; j < total * q; j += (I)gridDim.x * blockDim.x) {
+        const I quad = j % q;
+        const I i = j / q;
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
         if (quad == 0) {
-            const int p = (int)(i % P); const long kb = i / P; const int b = (int)(kb % B);
+            const I p = i % (I)P, kb = i / (I)P, b = kb % (I)B;
             o.x = __ldg(log_m + i);
             const float* xb = x + (long)b * 3 * P + p;
             o.y = __ldg(xb); o.z = __ldg(xb + P); o.w = __ldg(xb + 2 * P);
         }
-        *reinterpret_cast<float4*>(out + j * 4) = o;
+        *reinterpret_cast<float4*>(out + (long)j * 4) = o;
     }
 }
 
 // x [N,C,P] (NCHW) -> y [N,P,Cp] (NHWC, channels >= C zero)
-__global__ void nhwc_pad_kernel(const float* __restrict__ x, float* __restrict__ y, long total, int C, int P, int Cp) {
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % Cp); const long t = i / Cp; const int p = (int)(t % P); const long n = t / P;
-        y[i] = c < C ? __ldg(x + (n * C + c) * P + p) : 0.f;
+template <typename I>
+__global__ void nhwc_pad_kernel(const float* __restrict__ x, float* __restrict__ y, I total, int C, int P, int Cp) {
+    for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
+        const I c = i % (I)Cp, t = i / (I)Cp, p = t % (I)P, n = t / (I)P;
+        y[i] = c < (I)C ? __ldg(x + ((long)n * C + c) * P + p) : 0.f;
     }
 }
 
 // out[n,p,c] = act(a[n,c] + m[p,c])      (broadcast decoder first layer, see decoder ops)
+template <typename I>
 __global__ void bcast_add_act_kernel(const float* __restrict__ a, const float* __restrict__ m, float* __restrict__ out,
-                                     long total_quads, int P, int C, int act) {
-    const int q = C >> 2;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total_quads; i += (long)gridDim.x * blockDim.x) {
-        const int quad = (int)(i % q); const long row = i / q; const int p = (int)(row % P); const long n = row / P;
-        const float4 av = g2_ldg4(a + n * C + quad * 4), mv = g2_ldg4(m + (long)p * C + quad * 4);
+                                     I total_quads, int P, int C, int act) {
+    const I q = (I)(C >> 2);
+    for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total_quads; i += (I)gridDim.x * blockDim.x) {
+        const I quad = i % q, row = i / q, p = row % (I)P, n = row / (I)P;
+        const float4 av = g2_ldg4(a + (long)n * C + quad * 4), mv = g2_ldg4(m + (long)p * C + quad * 4);
         float4 o;
         o.x = g2_apply_act(av.x + mv.x, act, 0.f); o.y = g2_apply_act(av.y + mv.y, act, 0.f);
         o.z = g2_apply_act(av.z + mv.z, act, 0.f); o.w = g2_apply_act(av.w + mv.w, act, 0.f);
-        *reinterpret_cast<float4*>(out + i * 4) = o;
+        *reinterpret_cast<float4*>(out + (long)i * 4) = o;
     }
 }
 
@@ -221,7 +227,8 @@ extern "C" {
 int g2_layout_f32(const float* x, float* y, long N, int C, int P, int to_nchw, cudaStream_t stream) {
     G2_CHECK_ARG(x && y && N > 0 && C > 0 && P > 0);
     const long total = N * C * P;
-    layout_kernel<<<ew_blocks(total), 256, 0, stream>>>(x, y, total, C, P, to_nchw ? 1 : 0);
+    if (total < (1L << 31)) layout_kernel<unsigned><<<ew_blocks(total), 256, 0, stream>>>(x, y, (unsigned)total, C, P, to_nchw ? 1 : 0);
+    else layout_kernel<long><<<ew_blocks(total), 256, 0, stream>>>(x, y, total, C, P, to_nchw ? 1 : 0);
     G2_LAUNCH_RET();
 }
 
@@ -240,21 +247,24 @@ int g2_sbp_scan_bwd_f32(const float* logits, const float* dlog_m, float* dlogits
 int g2_comp_pack_f32(const float* x, const float* log_m, float* out, int K, int B, int P, int Cp, cudaStream_t stream) {
     G2_CHECK_ARG(x && log_m && out && K > 0 && B > 0 && P > 0 && Cp >= 4 && (Cp % 4) == 0);
     const long total = (long)K * B * P;
-    comp_pack_kernel<<<ew_blocks(total * (Cp / 4)), 256, 0, stream>>>(x, log_m, out, total, B, P, Cp);
+    if (total * (Cp / 4) < (1L << 31)) comp_pack_kernel<unsigned><<<ew_blocks(total * (Cp / 4)), 256, 0, stream>>>(x, log_m, out, (unsigned)total, B, P, Cp);
+    else comp_pack_kernel<long><<<ew_blocks(total * (Cp / 4)), 256, 0, stream>>>(x, log_m, out, total, B, P, Cp);
     G2_LAUNCH_RET();
 }
 
 int g2_nhwc_pad_f32(const float* x, float* y, long N, int C, int P, int Cp, cudaStream_t stream) {
     G2_CHECK_ARG(x && y && N > 0 && C > 0 && P > 0 && Cp >= C);
     const long total = N * P * Cp;
-    nhwc_pad_kernel<<<ew_blocks(total), 256, 0, stream>>>(x, y, total, C, P, Cp);
+    if (total < (1L << 31)) nhwc_pad_kernel<unsigned><<<ew_blocks(total), 256, 0, stream>>>(x, y, (unsigned)total, C, P, Cp);
+    else nhwc_pad_kernel<long><<<ew_blocks(total), 256, 0, stream>>>(x, y, total, C, P, Cp);
     G2_LAUNCH_RET();
 }
 
 int g2_bcast_add_act_f32(const float* a, const float* m, float* out, long N, int P, int C, int act, cudaStream_t stream) {
     G2_CHECK_ARG(a && m && out && N > 0 && P > 0 && C >= 4 && (C % 4) == 0);
     const long quads = N * P * (C / 4);
-    bcast_add_act_kernel<<<ew_blocks(quads), 256, 0, stream>>>(a, m, out, quads, P, C, act);
+    if (quads < (1L << 31)) bcast_add_act_kernel<unsigned><<<ew_blocks(quads), 256, 0, stream>>>(a, m, out, (unsigned)quads, P, C, act);
+    else bcast_add_act_kernel<long><<<ew_blocks(quads), 256, 0, stream>>>(a, m, out, quads, P, C, act);
     G2_LAUNCH_RET();
 }
 

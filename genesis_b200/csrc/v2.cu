@@ -16,12 +16,14 @@ inline int ew_blocks(long work, int threads = 256) {
 // mode 2: y (HxW, zeros except y[n,2h,2w,:] = x[n,h,w,:])       = backward of mode 0   (x is H/2 x W/2)
 // mode 3: y[n,h,w,:] = sum_{a,b<2} x[n,2h+a,2w+b,:]              = backward of mode 1   (x is 2H x 2W)
 // Ho, Wo are the OUTPUT sizes; C % 4 == 0.
-__global__ void resample_kernel(const float* __restrict__ x, float* __restrict__ y, long total_quads, int Ho, int Wo, int C, int mode) {
-    const int q = C >> 2;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total_quads; i += (long)gridDim.x * blockDim.x) {
-        const int quad = (int)(i % q); long t = i / q;
-        const int w = (int)(t % Wo); t /= Wo;
-        const int h = (int)(t % Ho); const long n = t / Ho;
+template <typename I>
+__global__ void resample_kernel(const float* __restrict__ x, float* __restrict__ y, I total_quads, int Ho_, int Wo_, int C, int mode) {
+    // I = unsigned when the quad count fits 31 bits: the four 64-bit divisions per float4 made this an ALU-bound kernel
+    const I q = (I)(C >> 2), Ho = (I)Ho_, Wo = (I)Wo_;
+    for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total_quads; i += (I)gridDim.x * blockDim.x) {
+        const I quad = i % q; I t = i / q;
+        const I w = t % Wo; t /= Wo;
+        const I h = t % Ho; const long n = (long)(t / Ho);
         float4 v;
         if (mode == 0) {
             v = g2_ldg4(x + ((n * (2 * Ho) + 2 * h) * (2L * Wo) + 2 * w) * C + quad * 4);
@@ -36,7 +38,7 @@ __global__ void resample_kernel(const float* __restrict__ x, float* __restrict__
             v = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y), (a0.z + a1.z) + (a2.z + a3.z),
                             (a0.w + a1.w) + (a2.w + a3.w));
         }
-        *reinterpret_cast<float4*>(y + i * 4) = v;
+        *reinterpret_cast<float4*>(y + (long)i * 4) = v;
     }
 }
 
@@ -380,7 +382,8 @@ int g2_resample_f32(const float* x, float* y, long N, int Ho, int Wo, int C, int
     G2_CHECK_ARG(x && y && N > 0 && Ho > 0 && Wo > 0 && C >= 4 && (C % 4) == 0 && mode >= 0 && mode <= 3);
     if (mode == 1 || mode == 2) G2_CHECK_ARG((Ho % 2) == 0 && (Wo % 2) == 0);
     const long quads = N * Ho * Wo * (C / 4);
-    resample_kernel<<<ew_blocks(quads), 256, 0, stream>>>(x, y, quads, Ho, Wo, C, mode);
+    if (quads < (1L << 31)) resample_kernel<unsigned><<<ew_blocks(quads), 256, 0, stream>>>(x, y, (unsigned)quads, Ho, Wo, C, mode);
+    else resample_kernel<long><<<ew_blocks(quads), 256, 0, stream>>>(x, y, quads, Ho, Wo, C, mode);
     G2_LAUNCH_RET();
 }
 
