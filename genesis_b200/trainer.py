@@ -250,7 +250,12 @@ class TrainStep(object):
         lib = _lib.lib()
         l0 = lib.launches
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        # Experiment (G2_MAIN_PRIORITY=1, off by default): capture the main chain on a HIGH-priority stream so that it wins the SMs
+        # over the side streams whenever both have persistent one-CTA-per-SM kernels pending.  Measured: 8.26 -> 8.10 ... 8.25 ms at
+        # N = 1, 8.39 -> 8.42 ms at N = 2 (the collectives then lose to the main chain): no consistent gain.
+        import os
+        cap_stream = torch.cuda.Stream(device=dev, priority=-1) if os.environ.get('G2_MAIN_PRIORITY', '0') == '1' else None
+        with (torch.cuda.graph(graph, stream=cap_stream) if cap_stream is not None else torch.cuda.graph(graph)):
             self.elbo_static = self._step_eager(self.x_static)
         self.launches_per_step = lib.launches - l0
         with torch.no_grad():
